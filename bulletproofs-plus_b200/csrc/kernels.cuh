@@ -1,0 +1,75 @@
+// Launch-side declarations of the bpp-b200 device kernels.  Definitions live in k_*.cu; engine.cu drives them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "arith.cuh"
+
+namespace bpp {
+
+// ---------------------------------------------------------------- k_point.cu
+// in: n x 8 words (Ristretto encodings).  out_tab (optional): affine-Niels table entry per point (identity when
+// invalid); ok: 1/0; out_enc (optional): re-encoding of the decoded point (8 words).
+void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out_tab, uint8_t *ok, uint32_t *out_enc);
+// extended points -> encodings (8 words each) and/or identity flags
+void launch_encode(cudaStream_t s, size_t n, const ge *in, uint32_t *out_enc, uint8_t *is_identity);
+// 64-byte uniform strings -> points: encodings and/or affine-Niels table entries
+void launch_from_uniform(cudaStream_t s, size_t n, const uint32_t *in16, uint32_t *out_enc, aniels *out_tab);
+
+// ---------------------------------------------------------------- k_msm.cu
+struct MsmShape {
+    uint32_t n_entries;   // (scalar, point) pairs over all segments
+    uint32_t n_seg;       // independent MSMs
+    int c;                // window bits
+    int W;                // windows = ceil(254 / c)
+    uint32_t B;           // buckets per window = 2^(c-1)
+};
+MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c);
+// bytes of scratch needed for a shape
+size_t msm_scratch_bytes(const MsmShape &sh);
+// scalars: n_entries x 8 words, canonical.  seg_id: per-entry segment (nullptr = all 0).  pidx: per-entry index
+// into `dyn` (bit 31 clear) or `gens` (bit 31 set); nullptr = identity mapping into dyn.
+// result: n_seg extended points.
+void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_id, const uint32_t *pidx,
+                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches);
+
+// ---------------------------------------------------------------- k_verify.cu
+struct VProof {            // per-proof metadata, device-resident
+    uint32_t chunk;        // reference call this proof belongs to
+    uint32_t m;            // aggregation factor (commitments)
+    uint32_t rounds;       // log2(n * m)
+    uint32_t pt_off;       // first dynamic point: [A, A1, B, L.., R.., V..]
+    uint32_t sc_off;       // first proof scalar: [r1, s1, d1..]
+    uint32_t ch_off;       // first challenge: [y, z, e, e_1..e_r]
+    uint32_t entry_off;    // first MSM entry of this proof's dynamic terms
+    uint32_t commit_off;   // first commitment (min_values / min_present index)
+    uint32_t nonce_off;    // first nonce: [eta_k, d_k, alpha_k (ext each), dL_jk, dR_jk (rounds*ext each)] or 0xffffffff
+    uint32_t contrib_off;  // first slot in the gi/hi contribution array (2 * n*m scalars)
+};
+struct VChunk {
+    uint32_t proof_lo, proof_hi;
+    uint32_t max_mn;       // largest n*m in the chunk
+    uint32_t entry_off;    // first MSM entry of the chunk: [Gi(max_mn) | Hi(max_mn) | G(ext) | H | dynamic...]
+};
+struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext, gens_nm; int action; };
+struct VBuffers {
+    const VProof *proofs; const VChunk *chunks;
+    const uint32_t *proof_scalars;   // words
+    const uint32_t *challenges;      // words
+    const uint32_t *weights;         // n_proofs x 8 words
+    const uint64_t *min_values; const uint8_t *min_present;
+    const uint32_t *nonces;          // words, may be null
+    uint32_t *msm_scalars;           // out: n_entries x 8 words
+    uint32_t *msm_seg;               // out: per-entry chunk id
+    uint32_t *msm_pidx;              // out: per-entry point index
+    uint32_t *contrib;               // scratch: gi/hi contributions (Montgomery form)
+    uint32_t *hg_contrib;            // scratch: per proof (1 + ext) scalars (Montgomery form): h, g_k
+    uint32_t *pervec;                // scratch: per proof 16 scalars handed from stage A to stage B
+    uint32_t *masks;                 // out: n_proofs x ext x 8 words (plain), may be null
+};
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint64_t *launches);
+
+// ---------------------------------------------------------------- k_bench.cu
+// returns elapsed seconds for `iters` dependent ops in each of `threads_total` lanes; ops counted by caller
+int microbench_run(cudaStream_t s, int which, int iters, double *ops_per_sec, double *seconds, uint64_t *launches);
+
+} // namespace bpp

@@ -1,0 +1,158 @@
+/*
+ * bpp_b200.h — C ABI of the B200-native Bulletproofs+ engine (libbpp_b200.so).
+ *
+ * This is the drop-in boundary for the MSM / inner-product-argument hot path of tari_bulletproofs_plus 0.4.1.
+ * The reference has no FFI: its seam is the trait bundle `P: CurvePointProtocol + Precomputable +
+ * MultiscalarMul` (/root/reference/src/range_proof.rs:207-213, src/traits.rs:7-43,
+ * src/protocols/curve_point_protocol.rs:18-36) instantiated once for Ristretto (src/ristretto.rs:26-64).
+ * Each entry point below names the reference call(s) it replaces.  INTEGRATION.md shows the Rust `extern "C"`
+ * block a maintainer would add.
+ *
+ * Conventions: all buffers caller-owned host memory unless a name ends in `_dev`; little-endian; scalars are
+ * 32-byte canonical encodings (values >= l are reduced where the reference would reduce, rejected where it
+ * would reject); points are 32-byte Ristretto255 encodings (RFC 9496).  Every function returns a bpp_status.
+ * No pointer is retained after return.  One bpp_ctx per (host thread, device); calls on one ctx are serialised
+ * on its CUDA stream.  There is NO CPU fallback: without a usable CUDA device every call fails with
+ * BPP_ERR_CUDA and bpp_last_error() says why.
+ */
+#ifndef BPP_B200_H
+#define BPP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes 0..5 mirror ProofError (/root/reference/src/errors.rs:12-28). */
+typedef enum {
+    BPP_OK = 0,
+    BPP_VERIFICATION_FAILED = 1,
+    BPP_INVALID_ARGUMENT = 2,
+    BPP_INVALID_LENGTH = 3,
+    BPP_INVALID_BLAKE2B = 4,
+    BPP_SIZE_OVERFLOW = 5,
+    BPP_ERR_CUDA = 100,      /* CUDA runtime / no device / launch failure */
+    BPP_ERR_INTERNAL = 101
+} bpp_status;
+
+/* VerifyAction (/root/reference/src/range_proof.rs:47-55) */
+typedef enum { BPP_RECOVER_ONLY = 0, BPP_RECOVER_AND_VERIFY = 1, BPP_VERIFY_ONLY = 2 } bpp_verify_action;
+
+#define BPP_MAX_BATCH 256          /* MAX_RANGE_PROOF_BATCH_SIZE, range_proof.rs:76 */
+#define BPP_MAX_BIT_LENGTH 64      /* MAX_RANGE_PROOF_BIT_LENGTH, range_proof.rs:71 */
+#define BPP_MAX_EXT 6              /* ExtensionDegree::AddFiveBasePoints, generators/pedersen_gens.rs:40-66 */
+#define BPP_TRANSCRIPT_BYTES 203   /* Merlin/STROBE-128 state: 200 B Keccak state, pos, pos_begin, cur_flags */
+
+typedef struct bpp_ctx bpp_ctx;
+typedef struct bpp_gens bpp_gens;
+typedef struct bpp_vbatch bpp_vbatch;
+typedef struct bpp_msm_plan bpp_msm_plan;
+
+/* ---------------------------------------------------------------- context */
+int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out);
+void bpp_ctx_destroy(bpp_ctx *ctx);
+const char *bpp_last_error(const bpp_ctx *ctx);      /* valid until the next call on ctx */
+int32_t bpp_ctx_sync(bpp_ctx *ctx);
+/* number of engine kernels launched on this ctx since creation (bench.py's gpu_launches) */
+uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx);
+void *bpp_ctx_stream(bpp_ctx *ctx);                   /* cudaStream_t, for event timing by the caller */
+
+/* ---------------------------------------------------------------- batched point primitives
+ * replace CompressedRistretto::decompress / RistrettoPoint::compress / from_uniform_bytes as issued from
+ * range_proof.rs:859-866,1067-1109 (decompress), :289,:348,:499-504,:587,:598-605 and range_statement.rs:62-65
+ * (compress), ristretto.rs:48-52 <- generators_chain.rs:44-49 (one-way map). */
+/* ok[i] = 1 iff in32[i] is a canonical encoding; out32[i] = compress(decompress(in32[i])) (== in32[i] when ok) */
+int32_t bpp_decompress_check(bpp_ctx *ctx, size_t n, const uint8_t *in32, uint8_t *ok, uint8_t *out32_or_null);
+int32_t bpp_from_uniform_batch(bpp_ctx *ctx, size_t n, const uint8_t *in64, uint8_t *out32);
+
+/* ---------------------------------------------------------------- multiscalar multiplication
+ * replaces P::vartime_multiscalar_mul (range_proof.rs:482-495,512-521), P::multiscalar_mul
+ * (generators/pedersen_gens.rs:117-120) and Precomputation::vartime_mixed_multiscalar_mul
+ * (range_proof.rs:339-345,1050-1057).  k independent MSMs per call: segment s covers entries
+ * [offsets[s], offsets[s+1]).  out32: k encodings.  A non-canonical point encoding => BPP_INVALID_ARGUMENT. */
+int32_t bpp_msm(bpp_ctx *ctx, size_t n, const uint8_t *scalars32, const uint8_t *points32, uint8_t *out32);
+int32_t bpp_msm_segmented(bpp_ctx *ctx, size_t k, const uint64_t *offsets, const uint8_t *scalars32,
+                          const uint8_t *points32, uint8_t *out32);
+/* device-resident variant for throughput measurement (BASELINE.json configs[4]): points are decompressed once */
+int32_t bpp_msm_plan_create(bpp_ctx *ctx, size_t n, const uint8_t *points32, int32_t window_bits_or_0,
+                            bpp_msm_plan **out);
+int32_t bpp_msm_plan_set_scalars(bpp_msm_plan *plan, const uint8_t *scalars32);
+int32_t bpp_msm_plan_run(bpp_msm_plan *plan, uint8_t *out32_or_null);   /* async unless out32 given */
+int32_t bpp_msm_plan_window_bits(const bpp_msm_plan *plan);
+void bpp_msm_plan_destroy(bpp_msm_plan *plan);
+
+/* ---------------------------------------------------------------- generators
+ * replaces RangeParameters::init -> BulletproofGens::new (range_parameters.rs:32-58,
+ * generators/bulletproof_gens.rs:83-112) + ristretto::create_pedersen_gens_with_extension_degree
+ * (ristretto.rs:67-112).  SHAKE256 / SHA3-512 run on the host, the one-way map on the device; the tables stay
+ * resident in HBM for the lifetime of the handle. */
+int32_t bpp_gens_create(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree,
+                        bpp_gens **out);
+void bpp_gens_destroy(bpp_gens *g);
+/* which: 0 = h_base, 1 = g_base[index], 2 = gi_base (flat, party-major), 3 = hi_base */
+int32_t bpp_gens_get(const bpp_gens *g, int32_t which, size_t index, uint8_t out32[32]);
+/* PedersenGens::commit for `count` openings: values[count], blindings32[count * n_blindings] */
+int32_t bpp_pedersen_commit_batch(bpp_gens *g, size_t count, const uint64_t *values, const uint8_t *blindings32,
+                                  int32_t n_blindings, uint8_t *out32);
+
+/* ---------------------------------------------------------------- batch verification
+ * replaces RangeProof::verify_batch -> verify (range_proof.rs:712-1065), one call for K independent
+ * reference calls ("chunks", each <= 256 proofs as verify_batch itself enforces at :739-751).
+ * All proofs of the call share `gens` (bit length, extension degree, H, G, Gi, Hi): the reference's
+ * consistency scan (:610-709) reduces to that identity.
+ *
+ * Layout: n proofs total; chunk c = proofs [chunk_offsets[c], chunk_offsets[c+1]).
+ *   proof_bytes / proof_offsets[n+1]   serialised proofs (to_bytes layout, range_proof.rs:1120-1150)
+ *   commit_offsets[n+1]                first commitment of proof i in commitments32 / min_values / min_present
+ *   seed_nonces32 (n x 32) + seed_present (n)   optional (NULL = none)
+ *   transcripts (n x 203 B)            Merlin state of each caller transcript BEFORE the call; advanced in
+ *                                      place exactly as `&mut Transcript` is in the reference
+ * Results: chunk_status[K] (bpp_status per reference call), masks32 (n x ext x 32) and mask_present (n) as
+ * Vec<Option<ExtendedMask>>. */
+typedef struct {
+    size_t n_proofs;
+    size_t n_chunks;
+    const uint64_t *chunk_offsets;
+    const uint8_t *proof_bytes;
+    const uint64_t *proof_offsets;
+    const uint8_t *commitments32;
+    const uint64_t *commit_offsets;
+    const uint64_t *min_values;
+    const uint8_t *min_present;
+    const uint8_t *seed_nonces32;
+    const uint8_t *seed_present;
+    uint8_t *transcripts;
+    int32_t action;
+} bpp_verify_args;
+
+int32_t bpp_verify_chunks(bpp_gens *g, const bpp_verify_args *args, int32_t *chunk_status,
+                          uint8_t *masks32, uint8_t *mask_present);
+
+/* Split form used to time the device path with inputs resident in HBM (bench.py `value`):
+ * create = host parsing + Fiat-Shamir + upload; run = all device work + verdict readback. */
+int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *args, bpp_vbatch **out);
+int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present);
+void bpp_vbatch_destroy(bpp_vbatch *vb);
+
+/* ---------------------------------------------------------------- proof bytes (host)
+ * RangeProof::from_bytes validation (range_proof.rs:1155-1257): returns BPP_OK and the number of (L,R) rounds. */
+int32_t bpp_proof_check_bytes(const uint8_t *bytes, size_t len, int32_t *extension_degree, int32_t *rounds);
+
+/* ---------------------------------------------------------------- Merlin transcripts (host)
+ * merlin::Transcript::new / append_message / challenge_bytes on the 203-byte state used above. */
+void bpp_transcript_new(const uint8_t *label, size_t len, uint8_t out[BPP_TRANSCRIPT_BYTES]);
+void bpp_transcript_append_message(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8_t *label, size_t label_len,
+                                   const uint8_t *msg, size_t len);
+void bpp_transcript_challenge_bytes(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8_t *label, size_t label_len,
+                                    uint8_t *out, size_t len);
+
+/* ---------------------------------------------------------------- measurement
+ * Integer-pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE, 3 IADD3, 4 field-mul,
+ * 5 field-square, 6 point madd, 7 point dbl, 8 scalar montmul.  Returns operations per second (per lane). */
+int32_t bpp_microbench(bpp_ctx *ctx, int32_t which, int32_t iters, double *ops_per_sec, double *seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

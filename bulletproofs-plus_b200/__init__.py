@@ -1,0 +1,197 @@
+"""bulletproofs-plus_b200 — python host side over the C ABI of libbpp_b200.so (sm_100a CUDA engine).
+
+Mirrors the reference's public surface for the accelerated path (names and error behaviour follow
+/root/reference/src/range_proof.rs, range_parameters.rs, range_statement.rs, range_witness.rs,
+commitment_opening.rs, extended_mask.rs, generators/pedersen_gens.rs); see api.py.  This module holds the thin
+engine-level wrappers.  There is no CPU fallback: constructing an Engine without a CUDA device raises.
+"""
+import ctypes as C
+
+from . import _ffi
+from ._ffi import (EngineError, OK, VERIFICATION_FAILED, INVALID_ARGUMENT, INVALID_LENGTH, INVALID_BLAKE2B, SIZE_OVERFLOW,
+                   RECOVER_ONLY, RECOVER_AND_VERIFY, VERIFY_ONLY, TRANSCRIPT_BYTES, MAX_BATCH, build)
+
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+def _chk(ctx, rc):
+    if rc != 0:
+        msg = ""
+        if ctx is not None and ctx.h:
+            msg = (_ffi.lib().bpp_last_error(ctx.h) or b"").decode(errors="replace")
+        raise EngineError(rc, msg)
+
+
+def _u64arr(vals):
+    return (C.c_uint64 * max(1, len(vals)))(*vals)
+
+
+class Engine:
+    """One bpp_ctx: a CUDA stream on one device.  Calls on one Engine are serialised on its stream."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        rc = _ffi.lib().bpp_ctx_create(device, C.byref(self.h))
+        if rc != 0:
+            self.h = C.c_void_p()
+            raise EngineError(rc, "bpp_ctx_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
+        self.device = device
+
+    def close(self):
+        if self.h:
+            _ffi.lib().bpp_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(_ffi.lib().bpp_ctx_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return _ffi.lib().bpp_ctx_stream(self.h)
+
+    def sync(self):
+        _chk(self, _ffi.lib().bpp_ctx_sync(self.h))
+
+    def set_host_threads(self, n):
+        _chk(self, _ffi.lib().bpp_ctx_set_host_threads(self.h, n))
+
+    # ---- batched point primitives
+    def decompress_check(self, encodings, reencode=True):
+        """encodings: bytes (n*32). Returns (ok list[int], re-encoded bytes or None)."""
+        n = len(encodings) // 32
+        ok = C.create_string_buffer(max(1, n))
+        out = C.create_string_buffer(max(1, 32 * n)) if reencode else None
+        _chk(self, _ffi.lib().bpp_decompress_check(self.h, n, encodings, ok, out))
+        return list(ok.raw[:n]), (out.raw[: 32 * n] if reencode else None)
+
+    def from_uniform(self, data):
+        n = len(data) // 64
+        out = C.create_string_buffer(max(1, 32 * n))
+        _chk(self, _ffi.lib().bpp_from_uniform_batch(self.h, n, data, out))
+        return out.raw[: 32 * n]
+
+    # ---- MSM
+    def msm(self, scalars, points):
+        """scalars, points: bytes (n*32 each) -> 32-byte encoding of sum s_i * P_i"""
+        n = len(scalars) // 32
+        out = C.create_string_buffer(32)
+        _chk(self, _ffi.lib().bpp_msm(self.h, n, scalars, points, out))
+        return out.raw
+
+    def msm_segmented(self, offsets, scalars, points):
+        k = len(offsets) - 1
+        out = C.create_string_buffer(32 * max(1, k))
+        off = _u64arr(offsets)
+        _chk(self, _ffi.lib().bpp_msm_segmented(self.h, k, C.cast(off, C.c_void_p), scalars, points, out))
+        return [out.raw[32 * i: 32 * i + 32] for i in range(k)]
+
+    def microbench(self, which, iters):
+        ops, sec = C.c_double(), C.c_double()
+        _chk(self, _ffi.lib().bpp_microbench(self.h, which, iters, C.byref(ops), C.byref(sec)))
+        return ops.value, sec.value
+
+
+class MsmPlan:
+    """Device-resident point set for repeated MSMs (BASELINE.json configs[4])."""
+
+    def __init__(self, engine, points, window_bits=0):
+        self.engine = engine
+        self.n = len(points) // 32
+        self.h = C.c_void_p()
+        _chk(engine, _ffi.lib().bpp_msm_plan_create(engine.h, self.n, points, window_bits, C.byref(self.h)))
+
+    @property
+    def window_bits(self):
+        return _ffi.lib().bpp_msm_plan_window_bits(self.h)
+
+    def set_scalars(self, scalars):
+        assert len(scalars) == 32 * self.n
+        _chk(self.engine, _ffi.lib().bpp_msm_plan_set_scalars(self.h, scalars))
+
+    def run(self, want_result=True):
+        out = C.create_string_buffer(32) if want_result else None
+        _chk(self.engine, _ffi.lib().bpp_msm_plan_run(self.h, out))
+        return out.raw if want_result else None
+
+    def close(self):
+        if self.h:
+            _ffi.lib().bpp_msm_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Gens:
+    """Device-resident generator tables: RangeParameters::init(bit_length, aggregation_factor,
+    create_pedersen_gens_with_extension_degree(ext)) (/root/reference/src/range_parameters.rs:32-58,
+    src/ristretto.rs:67-76)."""
+
+    def __init__(self, engine, bit_length, max_aggregation, extension_degree):
+        self.engine = engine
+        self.h = C.c_void_p()
+        _chk(engine, _ffi.lib().bpp_gens_create(engine.h, bit_length, max_aggregation, extension_degree, C.byref(self.h)))
+        self.bit_length, self.max_aggregation, self.extension_degree = bit_length, max_aggregation, extension_degree
+
+    def point(self, which, index=0):
+        out = C.create_string_buffer(32)
+        _chk(self.engine, _ffi.lib().bpp_gens_get(self.h, which, index, out))
+        return out.raw
+
+    def commit_batch(self, values, blindings):
+        """values: list[int]; blindings: list (per opening) of lists of ints (same length each) -> list of 32-byte encodings"""
+        n = len(values)
+        nb = len(blindings[0]) if n else 1
+        vals = _u64arr(values)
+        bl = b"".join(int(x % L).to_bytes(32, "little") for b in blindings for x in b)
+        out = C.create_string_buffer(max(1, 32 * n))
+        _chk(self.engine, _ffi.lib().bpp_pedersen_commit_batch(self.h, n, C.cast(vals, C.c_void_p), bl, nb, out))
+        return [out.raw[32 * i: 32 * i + 32] for i in range(n)]
+
+    def close(self):
+        if self.h:
+            _ffi.lib().bpp_gens_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- Merlin transcripts on the 203-byte wire form (host)
+def transcript_new(label):
+    out = C.create_string_buffer(TRANSCRIPT_BYTES)
+    _ffi.lib().bpp_transcript_new(label, len(label), out)
+    return out.raw
+
+
+def transcript_append_message(t, label, msg):
+    buf = C.create_string_buffer(t, TRANSCRIPT_BYTES)
+    _ffi.lib().bpp_transcript_append_message(buf, label, len(label), msg, len(msg))
+    return buf.raw
+
+
+def transcript_challenge_bytes(t, label, n):
+    buf = C.create_string_buffer(t, TRANSCRIPT_BYTES)
+    out = C.create_string_buffer(n)
+    _ffi.lib().bpp_transcript_challenge_bytes(buf, label, len(label), out, n)
+    return buf.raw, out.raw
+
+
+def proof_check_bytes(data):
+    """RangeProof::from_bytes validation: returns (status, extension_degree, rounds)."""
+    ext, rounds = C.c_int32(), C.c_int32()
+    rc = _ffi.lib().bpp_proof_check_bytes(data, len(data), C.byref(ext), C.byref(rounds))
+    return rc, ext.value, rounds.value

@@ -1,0 +1,425 @@
+// libbpp_b200.so — C ABI (include/bpp_b200.h): context, batched point primitives, multiscalar multiplication,
+// generator tables, Merlin helpers, proof-byte validation, microbenchmarks.
+// Batch verification lives in engine_verify.cu, the prover rounds in engine_prove.cu.
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include "engine.hpp"
+#include "hash.cuh"
+
+using namespace bpp;
+
+namespace bpp {
+int32_t fail(bpp_ctx *ctx, int32_t code, const char *what) {
+    if (ctx) ctx->err = what;
+    return code;
+}
+int32_t cuda_fail(bpp_ctx *ctx, cudaError_t e, const char *where) {
+    if (ctx) {
+        ctx->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + where;
+    }
+    return BPP_ERR_CUDA;
+}
+bool host_sc_is_canonical(const uint8_t *b32) {
+    uint32_t w[8];
+    memcpy(w, b32, 32);
+    return sc_is_canonical_words(w);
+}
+void host_sc_from_wide(const uint8_t in64[64], uint8_t out32[32]) {
+    uint32_t w[16];
+    memcpy(w, in64, 64);
+    sc r = sc_from_wide_words(w);
+    sc_tobytes(out32, r);
+}
+} // namespace bpp
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------ context
+int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
+    if (!out) return BPP_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device_ordinal < 0 || device_ordinal >= count) return BPP_ERR_CUDA;   // no CPU fallback
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return BPP_ERR_CUDA;
+    bpp_ctx *ctx = new bpp_ctx();
+    ctx->device = device_ordinal;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPP_ERR_CUDA; }
+    unsigned hc = std::thread::hardware_concurrency();
+    ctx->host_threads = hc ? (int)(hc > 64 ? 64 : hc) : 1;
+    if (const char *env = getenv("BPP_HOST_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 1024) ctx->host_threads = v; }
+    *out = ctx;
+    return BPP_OK;
+}
+void bpp_ctx_destroy(bpp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->d_in, &ctx->d_in2, &ctx->d_tab, &ctx->d_flags, &ctx->d_out, &ctx->d_scratch, &ctx->d_res, &ctx->d_misc}) b->release();
+    ctx->h_stage.release(); ctx->h_stage2.release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char *bpp_last_error(const bpp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int32_t bpp_ctx_sync(bpp_ctx *ctx) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *bpp_ctx_stream(bpp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n) {
+    if (!ctx || n < 1) return BPP_INVALID_ARGUMENT;
+    ctx->host_threads = n;
+    return BPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ point primitives
+int32_t bpp_decompress_check(bpp_ctx *ctx, size_t n, const uint8_t *in32, uint8_t *ok, uint8_t *out32_or_null) {
+    if (!ctx || (n && (!in32 || !ok))) return BPP_INVALID_ARGUMENT;
+    if (n == 0) return BPP_OK;
+    cudaSetDevice(ctx->device);
+    BPP_CUDA(ctx, ctx->d_in.ensure(32 * n));
+    BPP_CUDA(ctx, ctx->d_flags.ensure(n));
+    BPP_CUDA(ctx, ctx->d_out.ensure(32 * n));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in32, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    launch_decompress(ctx->stream, n, ctx->d_in.as<uint32_t>(), nullptr, ctx->d_flags.as<uint8_t>(),
+                      out32_or_null ? ctx->d_out.as<uint32_t>() : nullptr, nullptr);
+    ctx->launches++;
+    BPP_CUDA(ctx, cudaGetLastError());
+    BPP_CUDA(ctx, cudaMemcpyAsync(ok, ctx->d_flags.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out32_or_null) BPP_CUDA(ctx, cudaMemcpyAsync(out32_or_null, ctx->d_out.p, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+
+int32_t bpp_from_uniform_batch(bpp_ctx *ctx, size_t n, const uint8_t *in64, uint8_t *out32) {
+    if (!ctx || (n && (!in64 || !out32))) return BPP_INVALID_ARGUMENT;
+    if (n == 0) return BPP_OK;
+    cudaSetDevice(ctx->device);
+    BPP_CUDA(ctx, ctx->d_in.ensure(64 * n));
+    BPP_CUDA(ctx, ctx->d_out.ensure(32 * n));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in64, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+    launch_from_uniform(ctx->stream, n, ctx->d_in.as<uint32_t>(), ctx->d_out.as<uint32_t>(), nullptr);
+    ctx->launches++;
+    BPP_CUDA(ctx, cudaGetLastError());
+    BPP_CUDA(ctx, cudaMemcpyAsync(out32, ctx->d_out.p, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MSM
+int32_t bpp_msm_segmented(bpp_ctx *ctx, size_t k, const uint64_t *offsets, const uint8_t *scalars32, const uint8_t *points32,
+                          uint8_t *out32) {
+    if (!ctx || k == 0 || !offsets || !out32) return BPP_INVALID_ARGUMENT;
+    size_t n = offsets[k];
+    if (offsets[0] != 0) return fail(ctx, BPP_INVALID_ARGUMENT, "offsets[0] must be 0");
+    for (size_t s = 0; s < k; s++)
+        if (offsets[s + 1] < offsets[s]) return fail(ctx, BPP_INVALID_ARGUMENT, "offsets must be non-decreasing");
+    if (n >= (1ull << 31) || k >= (1u << 20)) return fail(ctx, BPP_SIZE_OVERFLOW, "too many MSM entries");
+    if (n && (!scalars32 || !points32)) return BPP_INVALID_ARGUMENT;
+    for (size_t i = 0; i < n; i++)
+        if (!host_sc_is_canonical(scalars32 + 32 * i)) return fail(ctx, BPP_INVALID_ARGUMENT, "non-canonical scalar");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    MsmShape sh = msm_shape((uint32_t)n, (uint32_t)k, 0);
+    BPP_CUDA(ctx, ctx->d_in.ensure(32 * n + 32));
+    BPP_CUDA(ctx, ctx->d_in2.ensure(32 * n + 32));
+    BPP_CUDA(ctx, ctx->d_tab.ensure(sizeof(aniels) * n + 96));
+    BPP_CUDA(ctx, ctx->d_scratch.ensure(msm_scratch_bytes(sh)));
+    BPP_CUDA(ctx, ctx->d_res.ensure(sizeof(ge) * k));
+    BPP_CUDA(ctx, ctx->d_out.ensure(32 * k));
+    BPP_CUDA(ctx, ctx->d_misc.ensure(4 * (k + 1) + 16));
+    uint32_t *d_bad = ctx->d_misc.as<uint32_t>();
+    uint32_t *d_off = d_bad + 4;
+    std::vector<uint32_t> off32(k + 1);
+    for (size_t s = 0; s <= k; s++) off32[s] = (uint32_t)offsets[s];
+    BPP_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 16, st));
+    BPP_CUDA(ctx, cudaMemcpyAsync(d_off, off32.data(), 4 * (k + 1), cudaMemcpyHostToDevice, st));
+    if (n) {
+        BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, points32, 32 * n, cudaMemcpyHostToDevice, st));
+        BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in2.p, scalars32, 32 * n, cudaMemcpyHostToDevice, st));
+        launch_decompress(st, n, ctx->d_in.as<uint32_t>(), ctx->d_tab.as<aniels>(), nullptr, nullptr, d_bad);
+        ctx->launches++;
+    }
+    launch_msm(st, sh, ctx->d_in2.as<uint32_t>(), k > 1 ? d_off : nullptr, nullptr, ctx->d_tab.as<aniels>(), nullptr, ctx->d_scratch.p,
+               ctx->d_res.as<ge>(), &ctx->launches);
+    launch_encode(st, k, ctx->d_res.as<ge>(), ctx->d_out.as<uint32_t>(), nullptr);
+    ctx->launches++;
+    BPP_CUDA(ctx, cudaGetLastError());
+    uint32_t bad = 0;
+    BPP_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(ctx, cudaMemcpyAsync(out32, ctx->d_out.p, 32 * k, cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (bad) return fail(ctx, BPP_INVALID_ARGUMENT, "point encoding failed to decompress");
+    return BPP_OK;
+}
+
+int32_t bpp_msm(bpp_ctx *ctx, size_t n, const uint8_t *scalars32, const uint8_t *points32, uint8_t *out32) {
+    uint64_t off[2] = {0, n};
+    return bpp_msm_segmented(ctx, 1, off, scalars32, points32, out32);
+}
+
+} // extern "C"
+
+struct bpp_msm_plan {
+    bpp_ctx *ctx;
+    size_t n;
+    MsmShape sh;
+    DevBuf d_tab, d_scalars, d_scratch, d_res, d_out;
+    bool have_scalars = false;
+};
+
+extern "C" {
+
+int32_t bpp_msm_plan_create(bpp_ctx *ctx, size_t n, const uint8_t *points32, int32_t window_bits_or_0, bpp_msm_plan **out) {
+    if (!ctx || !out || n == 0 || !points32) return BPP_INVALID_ARGUMENT;
+    if (n >= (1ull << 31)) return fail(ctx, BPP_SIZE_OVERFLOW, "too many MSM entries");
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    bpp_msm_plan *pl = new bpp_msm_plan();
+    pl->ctx = ctx; pl->n = n;
+    pl->sh = msm_shape((uint32_t)n, 1, window_bits_or_0);
+    cudaStream_t st = ctx->stream;
+    auto bail = [&](cudaError_t e, const char *w) { bpp_msm_plan_destroy(pl); return cuda_fail(ctx, e, w); };
+    cudaError_t e;
+    if ((e = pl->d_tab.ensure(sizeof(aniels) * n)) != cudaSuccess) return bail(e, "plan table");
+    if ((e = pl->d_scalars.ensure(32 * n)) != cudaSuccess) return bail(e, "plan scalars");
+    if ((e = pl->d_scratch.ensure(msm_scratch_bytes(pl->sh))) != cudaSuccess) return bail(e, "plan scratch");
+    if ((e = pl->d_res.ensure(sizeof(ge))) != cudaSuccess) return bail(e, "plan result");
+    if ((e = pl->d_out.ensure(64)) != cudaSuccess) return bail(e, "plan out");
+    if ((e = ctx->d_in.ensure(32 * n)) != cudaSuccess) return bail(e, "plan staging");
+    if ((e = ctx->d_misc.ensure(64)) != cudaSuccess) return bail(e, "plan misc");
+    cudaMemsetAsync(ctx->d_misc.p, 0, 16, st);
+    cudaMemcpyAsync(ctx->d_in.p, points32, 32 * n, cudaMemcpyHostToDevice, st);
+    launch_decompress(st, n, ctx->d_in.as<uint32_t>(), pl->d_tab.as<aniels>(), nullptr, nullptr, ctx->d_misc.as<uint32_t>());
+    ctx->launches++;
+    uint32_t bad = 0;
+    cudaMemcpyAsync(&bad, ctx->d_misc.p, 4, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "plan decompress");
+    if (bad) { bpp_msm_plan_destroy(pl); return fail(ctx, BPP_INVALID_ARGUMENT, "point encoding failed to decompress"); }
+    *out = pl;
+    return BPP_OK;
+}
+int32_t bpp_msm_plan_set_scalars(bpp_msm_plan *pl, const uint8_t *scalars32) {
+    if (!pl || !scalars32) return BPP_INVALID_ARGUMENT;
+    bpp_ctx *ctx = pl->ctx;
+    for (size_t i = 0; i < pl->n; i++)
+        if (!host_sc_is_canonical(scalars32 + 32 * i)) return fail(ctx, BPP_INVALID_ARGUMENT, "non-canonical scalar");
+    cudaSetDevice(ctx->device);
+    BPP_CUDA(ctx, cudaMemcpyAsync(pl->d_scalars.p, scalars32, 32 * pl->n, cudaMemcpyHostToDevice, ctx->stream));
+    BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pl->have_scalars = true;
+    return BPP_OK;
+}
+int32_t bpp_msm_plan_run(bpp_msm_plan *pl, uint8_t *out32_or_null) {
+    if (!pl || !pl->have_scalars) return BPP_INVALID_ARGUMENT;
+    bpp_ctx *ctx = pl->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    launch_msm(st, pl->sh, pl->d_scalars.as<uint32_t>(), nullptr, nullptr, pl->d_tab.as<aniels>(), nullptr, pl->d_scratch.p,
+               pl->d_res.as<ge>(), &ctx->launches);
+    BPP_CUDA(ctx, cudaGetLastError());
+    if (out32_or_null) {
+        launch_encode(st, 1, pl->d_res.as<ge>(), pl->d_out.as<uint32_t>(), nullptr);
+        ctx->launches++;
+        BPP_CUDA(ctx, cudaMemcpyAsync(out32_or_null, pl->d_out.p, 32, cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return BPP_OK;
+}
+int32_t bpp_msm_plan_window_bits(const bpp_msm_plan *pl) { return pl ? pl->sh.c : 0; }
+void bpp_msm_plan_destroy(bpp_msm_plan *pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->ctx->device);
+    cudaStreamSynchronize(pl->ctx->stream);
+    pl->d_tab.release(); pl->d_scalars.release(); pl->d_scratch.release(); pl->d_res.release(); pl->d_out.release();
+    delete pl;
+}
+
+// ------------------------------------------------------------------------------------------------ generators
+int32_t bpp_gens_create(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree, bpp_gens **out) {
+    if (!ctx || !out) return BPP_INVALID_ARGUMENT;
+    *out = nullptr;
+    // RangeParameters::init, range_parameters.rs:32-58
+    auto pow2 = [](int64_t x) { return x > 0 && (x & (x - 1)) == 0; };
+    if (!pow2(bit_length) || bit_length > BPP_MAX_BIT_LENGTH) return fail(ctx, BPP_INVALID_ARGUMENT, "Bit length must be a power of two and <= 64");
+    if (!pow2(max_aggregation)) return fail(ctx, BPP_INVALID_ARGUMENT, "Aggregation factor must be a power of two");
+    if (extension_degree < 1 || extension_degree > BPP_MAX_EXT) return fail(ctx, BPP_INVALID_ARGUMENT, "Extension degree not valid");
+    if ((int64_t)bit_length * max_aggregation > (1 << 24)) return fail(ctx, BPP_SIZE_OVERFLOW, "generator set too large");
+    cudaSetDevice(ctx->device);
+    bpp_gens *g = new bpp_gens();
+    g->ctx = ctx; g->n = bit_length; g->M = max_aggregation; g->ext = extension_degree;
+    g->nm = (size_t)bit_length * (size_t)max_aggregation;
+    size_t total = g->table_len(), nh = total - 1;
+    // uniform 64-byte strings: SHAKE256("GeneratorsChain" || 'G'|'H' || LE32(party)) per party (bulletproof_gens.rs:91-96,
+    // generators_chain.rs:23-49); SHA3-512("RISTRETTO_MASKING_BASEPOINT_" || decimal(k+1)) for G[k] (ristretto.rs:92-95)
+    std::vector<uint8_t> uni(64 * nh);
+    for (int which = 0; which < 2; which++) {
+        for (int party = 0; party < max_aggregation; party++) {
+            KeccakSponge sp;
+            sp.init(136);
+            sp.absorb((const uint8_t *)"GeneratorsChain", 15);
+            uint8_t label[5] = {(uint8_t)(which ? 'H' : 'G'), (uint8_t)party, (uint8_t)(party >> 8), (uint8_t)(party >> 16), (uint8_t)(party >> 24)};
+            sp.absorb(label, 5);
+            sp.finish(0x1f);
+            sp.squeeze(uni.data() + 64 * ((size_t)which * g->nm + (size_t)party * bit_length), 64 * (size_t)bit_length);
+        }
+    }
+    for (int k = 0; k < extension_degree; k++) {
+        char label[64];
+        int len = snprintf(label, sizeof label, "RISTRETTO_MASKING_BASEPOINT_%d", k + 1);
+        sha3_512(uni.data() + 64 * (2 * g->nm + (size_t)k), (const uint8_t *)label, (size_t)len);
+    }
+    static const uint8_t BASEPOINT[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+                                          0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+    cudaStream_t st = ctx->stream;
+    auto bail = [&](cudaError_t e, const char *w) { g->d_table.release(); delete g; return cuda_fail(ctx, e, w); };
+    cudaError_t e;
+    if ((e = g->d_table.ensure(sizeof(aniels) * total)) != cudaSuccess) return bail(e, "gens table");
+    if ((e = ctx->d_in.ensure(64 * nh + 64)) != cudaSuccess) return bail(e, "gens staging");
+    if ((e = ctx->d_out.ensure(32 * total)) != cudaSuccess) return bail(e, "gens enc");
+    g->enc.resize(32 * total);
+    cudaMemcpyAsync(ctx->d_in.p, uni.data(), 64 * nh, cudaMemcpyHostToDevice, st);
+    launch_from_uniform(st, nh, ctx->d_in.as<uint32_t>(), ctx->d_out.as<uint32_t>(), g->d_table.as<aniels>());
+    // H: decode the RFC 9496 base point encoding into the last table slot
+    uint8_t *d_h_in = ctx->d_in.as<uint8_t>() + 64 * nh;
+    cudaMemcpyAsync(d_h_in, BASEPOINT, 32, cudaMemcpyHostToDevice, st);
+    launch_decompress(st, 1, (const uint32_t *)d_h_in, g->d_table.as<aniels>() + nh, nullptr, ctx->d_out.as<uint32_t>() + 8 * nh, nullptr);
+    ctx->launches += 2;
+    cudaMemcpyAsync(g->enc.data(), ctx->d_out.p, 32 * total, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "gens derive");
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "gens derive");
+    *out = g;
+    return BPP_OK;
+}
+void bpp_gens_destroy(bpp_gens *g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    g->d_table.release();
+    delete g;
+}
+int32_t bpp_gens_get(const bpp_gens *g, int32_t which, size_t index, uint8_t out32[32]) {
+    if (!g || !out32) return BPP_INVALID_ARGUMENT;
+    const uint8_t *src = nullptr;
+    switch (which) {
+        case 0: src = g->h(); break;
+        case 1: if (index < (size_t)g->ext) src = g->g(index); break;
+        case 2: if (index < g->nm) src = g->gi(index); break;
+        case 3: if (index < g->nm) src = g->hi(index); break;
+        default: break;
+    }
+    if (!src) return BPP_INVALID_ARGUMENT;
+    memcpy(out32, src, 32);
+    return BPP_OK;
+}
+
+// PedersenGens::commit (generators/pedersen_gens.rs:112-122): value*H + sum blindings[k]*G[k]; 1 <= n_blindings <= ext
+int32_t bpp_pedersen_commit_batch(bpp_gens *g, size_t count, const uint64_t *values, const uint8_t *blindings32, int32_t n_blindings,
+                                  uint8_t *out32) {
+    if (!g || (count && (!values || !blindings32 || !out32))) return BPP_INVALID_ARGUMENT;
+    bpp_ctx *ctx = g->ctx;
+    if (n_blindings < 1 || n_blindings > g->ext) return fail(ctx, BPP_INVALID_LENGTH, "Incorrect number of blinding factors");
+    if (count == 0) return BPP_OK;
+    size_t per = 1 + (size_t)n_blindings, n = count * per;
+    if (n >= (1ull << 31)) return fail(ctx, BPP_SIZE_OVERFLOW, "too many commitments");
+    for (size_t i = 0; i < count * (size_t)n_blindings; i++)
+        if (!host_sc_is_canonical(blindings32 + 32 * i)) return fail(ctx, BPP_INVALID_ARGUMENT, "non-canonical scalar");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    // entries per opening: [value -> H, blinding_k -> G[k]]
+    std::vector<uint32_t> sc(8 * n), pidx(n), off(count + 1);
+    for (size_t i = 0; i < count; i++) {
+        uint32_t *s = &sc[8 * i * per];
+        memset(s, 0, 32);
+        s[0] = (uint32_t)values[i]; s[1] = (uint32_t)(values[i] >> 32);
+        pidx[i * per] = 0x80000000u | (uint32_t)(2 * g->nm + g->ext);
+        for (int k = 0; k < n_blindings; k++) {
+            memcpy(s + 8 * (1 + k), blindings32 + 32 * (i * n_blindings + k), 32);
+            pidx[i * per + 1 + k] = 0x80000000u | (uint32_t)(2 * g->nm + k);
+        }
+        off[i] = (uint32_t)(i * per);
+    }
+    off[count] = (uint32_t)n;
+    MsmShape sh = msm_shape((uint32_t)n, (uint32_t)count, 4);
+    BPP_CUDA(ctx, ctx->d_in2.ensure(32 * n));
+    BPP_CUDA(ctx, ctx->d_in.ensure(4 * n));
+    BPP_CUDA(ctx, ctx->d_misc.ensure(4 * (count + 1)));
+    BPP_CUDA(ctx, ctx->d_scratch.ensure(msm_scratch_bytes(sh)));
+    BPP_CUDA(ctx, ctx->d_res.ensure(sizeof(ge) * count));
+    BPP_CUDA(ctx, ctx->d_out.ensure(32 * count));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in2.p, sc.data(), 32 * n, cudaMemcpyHostToDevice, st));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, pidx.data(), 4 * n, cudaMemcpyHostToDevice, st));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_misc.p, off.data(), 4 * (count + 1), cudaMemcpyHostToDevice, st));
+    launch_msm(st, sh, ctx->d_in2.as<uint32_t>(), count > 1 ? ctx->d_misc.as<uint32_t>() : nullptr, ctx->d_in.as<uint32_t>(), nullptr,
+               g->d_table.as<aniels>(), ctx->d_scratch.p, ctx->d_res.as<ge>(), &ctx->launches);
+    launch_encode(st, count, ctx->d_res.as<ge>(), ctx->d_out.as<uint32_t>(), nullptr);
+    ctx->launches++;
+    BPP_CUDA(ctx, cudaGetLastError());
+    BPP_CUDA(ctx, cudaMemcpyAsync(out32, ctx->d_out.p, 32 * count, cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    return BPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ proof bytes
+// RangeProof::from_bytes (range_proof.rs:1155-1257): [ext:u8] d1[ext] a a1 b r1 s1 (L R)*
+int32_t bpp_proof_check_bytes(const uint8_t *bytes, size_t len, int32_t *extension_degree, int32_t *rounds) {
+    if (!bytes || len == 0) return BPP_INVALID_LENGTH;
+    int ext = bytes[0];
+    if (ext < 1 || ext > BPP_MAX_EXT) return BPP_INVALID_ARGUMENT;
+    size_t need = 1 + 32 * ((size_t)ext + 5);
+    if (len < need) return BPP_INVALID_LENGTH;
+    const uint8_t *p = bytes + 1;
+    for (int k = 0; k < ext; k++, p += 32)
+        if (!host_sc_is_canonical(p)) return BPP_INVALID_ARGUMENT;
+    p += 96;   // a, a1, b: raw encodings, not validated at parse time
+    if (!host_sc_is_canonical(p) || !host_sc_is_canonical(p + 32)) return BPP_INVALID_ARGUMENT;
+    size_t rest = len - need;
+    if (rest == 0 || rest % 64 != 0) return BPP_INVALID_LENGTH;
+    if (rest / 64 >= 32) return BPP_SIZE_OVERFLOW;
+    if (extension_degree) *extension_degree = ext;
+    if (rounds) *rounds = (int32_t)(rest / 64);
+    return BPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Merlin (host)
+void bpp_transcript_new(const uint8_t *label, size_t len, uint8_t out[BPP_TRANSCRIPT_BYTES]) {
+    Merlin m;
+    m.init(label, len);
+    m.s.store(out);
+}
+void bpp_transcript_append_message(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8_t *label, size_t label_len, const uint8_t *msg, size_t len) {
+    Merlin m;
+    m.s.load(t);
+    m.append_message(label, label_len, msg, len);
+    m.s.store(t);
+}
+void bpp_transcript_challenge_bytes(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8_t *label, size_t label_len, uint8_t *out, size_t len) {
+    Merlin m;
+    m.s.load(t);
+    m.challenge_bytes(label, label_len, out, len);
+    m.s.store(t);
+}
+// test hooks for the host hash layer (python hashlib is the checker)
+void bpp_hash_sha3_512(const uint8_t *in, size_t len, uint8_t out[64]) { sha3_512(out, in, len); }
+void bpp_hash_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen) {
+    KeccakSponge s; s.init(136); s.absorb(in, len); s.finish(0x1f); s.squeeze(out, outlen);
+}
+int32_t bpp_hash_blake2b_nonce_bytes(const uint8_t *key, size_t keylen, const uint8_t *personal, size_t plen, uint8_t out[64]) {
+    return blake2b_keyed_personal_empty(out, key, keylen, personal, plen) ? BPP_OK : BPP_INVALID_BLAKE2B;
+}
+void bpp_scalar_from_wide(const uint8_t in64[64], uint8_t out32[32]) { host_sc_from_wide(in64, out32); }
+
+// ------------------------------------------------------------------------------------------------ measurement
+int32_t bpp_microbench(bpp_ctx *ctx, int32_t which, int32_t iters, double *ops_per_sec, double *seconds) {
+    if (!ctx || !ops_per_sec || !seconds || iters <= 0) return BPP_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    int rc = microbench_run(ctx->stream, which, iters, ops_per_sec, seconds, &ctx->launches);
+    if (rc == -2) return BPP_INVALID_ARGUMENT;
+    if (rc != 0) return cuda_fail(ctx, cudaGetLastError(), "microbench");
+    return BPP_OK;
+}
+
+} // extern "C"

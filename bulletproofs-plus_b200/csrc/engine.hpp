@@ -1,0 +1,82 @@
+// Internal host-side definitions shared by the C-ABI translation units (engine.cu, engine_verify.cu, engine_prove.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/bpp_b200.h"
+#include "kernels.cuh"
+
+namespace bpp {
+
+// grow-only device / pinned-host buffers: the hot entry points are called repeatedly with similar sizes
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+} // namespace bpp
+
+struct bpp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int host_threads = 1;
+    // reusable scratch for the one-shot entry points
+    bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc;
+    bpp::PinBuf h_stage, h_stage2;
+};
+
+struct bpp_gens {
+    bpp_ctx *ctx = nullptr;
+    int n = 0, M = 0, ext = 0;
+    size_t nm = 0;                       // n * M
+    bpp::DevBuf d_table;                 // aniels[2*nm + ext + 1]: Gi | Hi | G | H
+    std::vector<uint8_t> enc;            // (2*nm + ext + 1) x 32 B compressed, same order
+    const uint8_t *gi(size_t i) const { return enc.data() + 32 * i; }
+    const uint8_t *hi(size_t i) const { return enc.data() + 32 * (nm + i); }
+    const uint8_t *g(size_t k) const { return enc.data() + 32 * (2 * nm + k); }
+    const uint8_t *h() const { return enc.data() + 32 * (2 * nm + ext); }
+    size_t table_len() const { return 2 * nm + (size_t)ext + 1; }
+};
+
+namespace bpp {
+int32_t fail(bpp_ctx *ctx, int32_t code, const char *what);
+int32_t cuda_fail(bpp_ctx *ctx, cudaError_t e, const char *where);
+#define BPP_CUDA(ctx, call)                                             \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return bpp::cuda_fail((ctx), _e, #call); \
+    } while (0)
+
+// host scalar helpers over the shared arithmetic header (portable path)
+bool host_sc_is_canonical(const uint8_t *b32);
+void host_sc_from_wide(const uint8_t in64[64], uint8_t out32[32]);
+} // namespace bpp

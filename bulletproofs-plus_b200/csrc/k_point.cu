@@ -18,14 +18,15 @@ static __device__ __forceinline__ void store8(uint32_t *p, const uint32_t w[8]) 
 static __device__ __forceinline__ void store_fe(fe *dst, const fe &a) { store8(dst->v, a.v); }
 
 __global__ void __launch_bounds__(128) k_decompress(size_t n, const uint32_t *__restrict__ in, aniels *__restrict__ out_tab,
-                                                   uint8_t *__restrict__ ok, uint32_t *__restrict__ out_enc) {
+                                                   uint8_t *__restrict__ ok, uint32_t *__restrict__ out_enc,
+                                                   uint32_t *__restrict__ bad_count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t w[8];
     load8(w, in + 8 * i);
     fe x, y, t;
     bool good = ristretto_decode(x, y, t, w);
-    if (!good) { x = fe_zero(); y = fe_one(); t = fe_zero(); }
+    if (!good) { x = fe_zero(); y = fe_one(); t = fe_zero(); if (bad_count) atomicAdd(bad_count, 1u); }
     if (ok) ok[i] = good ? 1 : 0;
     if (out_tab) {
         aniels q = ge_to_aniels_affine(x, y, t);
@@ -73,9 +74,10 @@ __global__ void __launch_bounds__(128) k_from_uniform(size_t n, const uint32_t *
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
-void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out_tab, uint8_t *ok, uint32_t *out_enc) {
+void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out_tab, uint8_t *ok, uint32_t *out_enc,
+                       uint32_t *bad_count) {
     if (n == 0) return;
-    k_decompress<<<grid_for(n, 128), 128, 0, s>>>(n, in, out_tab, ok, out_enc);
+    k_decompress<<<grid_for(n, 128), 128, 0, s>>>(n, in, out_tab, ok, out_enc, bad_count);
 }
 void launch_encode(cudaStream_t s, size_t n, const ge *in, uint32_t *out_enc, uint8_t *is_identity) {
     if (n == 0) return;

@@ -8,8 +8,9 @@ namespace bpp {
 
 // ---------------------------------------------------------------- k_point.cu
 // in: n x 8 words (Ristretto encodings).  out_tab (optional): affine-Niels table entry per point (identity when
-// invalid); ok: 1/0; out_enc (optional): re-encoding of the decoded point (8 words).
-void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out_tab, uint8_t *ok, uint32_t *out_enc);
+// invalid); ok: 1/0; out_enc (optional): re-encoding of the decoded point (8 words); bad_count (optional): += #invalid.
+void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out_tab, uint8_t *ok, uint32_t *out_enc,
+                       uint32_t *bad_count);
 // extended points -> encodings (8 words each) and/or identity flags
 void launch_encode(cudaStream_t s, size_t n, const ge *in, uint32_t *out_enc, uint8_t *is_identity);
 // 64-byte uniform strings -> points: encodings and/or affine-Niels table entries
@@ -26,10 +27,10 @@ struct MsmShape {
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c);
 // bytes of scratch needed for a shape
 size_t msm_scratch_bytes(const MsmShape &sh);
-// scalars: n_entries x 8 words, canonical.  seg_id: per-entry segment (nullptr = all 0).  pidx: per-entry index
-// into `dyn` (bit 31 clear) or `gens` (bit 31 set); nullptr = identity mapping into dyn.
+// scalars: n_entries x 8 words, canonical.  seg_offsets: n_seg + 1 entry offsets (nullptr when n_seg == 1).
+// pidx: per-entry index into `dyn` (bit 31 clear) or `gens` (bit 31 set); nullptr = identity mapping into dyn.
 // result: n_seg extended points.
-void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_id, const uint32_t *pidx,
+void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_offsets, const uint32_t *pidx,
                 const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches);
 
 // ---------------------------------------------------------------- k_verify.cu

@@ -57,6 +57,9 @@ int32_t bpp_ctx_sync(bpp_ctx *ctx);
 /* number of engine kernels launched on this ctx since creation (bench.py's gpu_launches) */
 uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx);
 void *bpp_ctx_stream(bpp_ctx *ctx);                   /* cudaStream_t, for event timing by the caller */
+/* host threads used for the Fiat-Shamir replay of bpp_verify_chunks (default: min(64, hardware threads); the
+ * reference is single-threaded, the harness supplies parallelism -- see BASELINE.md) */
+int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);
 
 /* ---------------------------------------------------------------- batched point primitives
  * replace CompressedRistretto::decompress / RistrettoPoint::compress / from_uniform_bytes as issued from
@@ -146,6 +149,14 @@ void bpp_transcript_append_message(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8_
                                    const uint8_t *msg, size_t len);
 void bpp_transcript_challenge_bytes(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8_t *label, size_t label_len,
                                     uint8_t *out, size_t len);
+
+/* host hash layer, exposed so it can be pinned against external KATs (python hashlib) without a GPU:
+ * SHA3-512 (ristretto.rs:92-95), SHAKE256 (generators_chain.rs:23-49), BLAKE2b-512 keyed+personalised with an empty
+ * message (utils/generic.rs:56-57), Scalar::from_bytes_mod_order_wide (transcript_protocol.rs:70) */
+void bpp_hash_sha3_512(const uint8_t *in, size_t len, uint8_t out[64]);
+void bpp_hash_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen);
+int32_t bpp_hash_blake2b_nonce_bytes(const uint8_t *key, size_t keylen, const uint8_t *personal, size_t plen, uint8_t out[64]);
+void bpp_scalar_from_wide(const uint8_t in64[64], uint8_t out32[32]);
 
 /* ---------------------------------------------------------------- measurement
  * Integer-pipe microbenchmarks: which = 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE, 3 IADD3, 4 field-mul,

@@ -1,0 +1,109 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/bpp_b200.h declares, its host hash
+layer matches python hashlib / the Merlin KAT / the oracle, and the compute entry points fail loudly without a GPU."""
+import ctypes as C
+import hashlib
+import os
+import random
+import re
+
+import pytest
+
+import bpp
+import orc
+
+
+@pytest.fixture(scope="module")
+def lib():
+    bpp.ffi.build()
+    return bpp.ffi.lib()
+
+
+def test_exports_match_header(lib):
+    hdr = open(bpp.ffi.HEADER_PATH).read()
+    names = sorted(set(re.findall(r"\b(bpp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert lib.bpp_ctx_create(0, C.byref(h)) == bpp.ffi.ERR_CUDA
+    with pytest.raises(bpp.pkg.EngineError):
+        bpp.pkg.Engine(0)
+
+
+def test_host_hashes_vs_hashlib(lib):
+    rnd = random.Random(5)
+    for n in [0, 1, 71, 72, 73, 135, 136, 137, 500]:
+        data = bytes(rnd.randrange(256) for _ in range(n))
+        out = C.create_string_buffer(64)
+        lib.bpp_hash_sha3_512(data, n, out)
+        assert out.raw == hashlib.sha3_512(data).digest()
+        out2 = C.create_string_buffer(300)
+        lib.bpp_hash_shake256(data, n, out2, 300)
+        assert out2.raw == hashlib.shake_256(data).digest(300)
+    for keylen in [1, 33, 38, 43, 64]:
+        for person in [b"alpha", b"dL", b"0123456789abcdef", b""]:
+            key = bytes(rnd.randrange(256) for _ in range(keylen))
+            out = C.create_string_buffer(64)
+            assert lib.bpp_hash_blake2b_nonce_bytes(key, keylen, person, len(person), out) == 0
+            assert out.raw == hashlib.blake2b(b"", key=key, person=person, digest_size=64).digest()
+    assert lib.bpp_hash_blake2b_nonce_bytes(b"x" * 65, 65, b"", 0, C.create_string_buffer(64)) == bpp.ffi.INVALID_BLAKE2B
+    assert lib.bpp_hash_blake2b_nonce_bytes(b"x", 1, b"y" * 17, 17, C.create_string_buffer(64)) == bpp.ffi.INVALID_BLAKE2B
+    for _ in range(50):
+        w = rnd.randrange(2**512)
+        out = C.create_string_buffer(32)
+        lib.bpp_scalar_from_wide(w.to_bytes(64, "little"), out)
+        assert int.from_bytes(out.raw, "little") == w % orc.L
+
+
+def test_merlin_kat_and_oracle(lib):
+    # merlin's own test vector (merlin 3.0.0 src/transcript.rs tests)
+    t = bpp.pkg.transcript_new(b"test protocol")
+    t = bpp.pkg.transcript_append_message(t, b"some label", b"some data")
+    t, ch = bpp.pkg.transcript_challenge_bytes(t, b"challenge", 32)
+    assert ch.hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    # long messages crossing the 166-byte rate, against the oracle's independent STROBE
+    rnd = random.Random(6)
+    t1 = bpp.pkg.transcript_new(b"BatchedRangeProofTest")
+    t2 = orc.transcript_new(b"BatchedRangeProofTest")
+    assert t1 == t2
+    ol = orc.lib()
+    for n in [0, 1, 32, 165, 166, 167, 400]:
+        msg = bytes(rnd.randrange(256) for _ in range(n))
+        t1 = bpp.pkg.transcript_append_message(t1, b"lbl", msg)
+        b2 = C.create_string_buffer(t2, 203)
+        ol.orc_transcript_append_message(b2, b"lbl", msg, n)
+        t2 = b2.raw
+        assert t1 == t2
+        t1, c1 = bpp.pkg.transcript_challenge_bytes(t1, b"ch", 64)
+        c2 = C.create_string_buffer(64)
+        b2 = C.create_string_buffer(t2, 203)
+        ol.orc_transcript_challenge_bytes(b2, b"ch", c2, 64)
+        t2 = b2.raw
+        assert c1 == c2.raw and t1 == t2
+
+
+def test_proof_check_bytes_matches_oracle(lib):
+    import workload
+
+    case = workload.make_case(8, [1], 2, seed_nonce=True)
+    good = case.proof_bytes()[0]
+    rc, ext, rounds = bpp.pkg.proof_check_bytes(good)
+    assert (rc, ext, rounds) == (0, 2, 3)
+    rnd = random.Random(7)
+    variants = [good[:k] for k in range(0, len(good))] + [good + bytes(k) for k in (1, 32, 63, 64, 65, 128)]
+    for k in (0, 1, 33, 65 + 96, 65 + 96 + 32):
+        b = bytearray(good)
+        b[k:k + 32] = (orc.L + 5).to_bytes(32, "little") if k else b"\x07" + bytes(b[1:32])
+        variants.append(bytes(b))
+    variants += [bytes([e]) + good[1:] for e in (0, 1, 3, 7, 255)]
+    for v in variants:
+        rc_o, _ = orc.proof_from_bytes(v)
+        rc_p, _, _ = bpp.pkg.proof_check_bytes(v)
+        assert rc_p == rc_o, (len(v), rc_p, rc_o)

@@ -1,0 +1,204 @@
+"""GPU parity: batched Ristretto decode/encode/one-way map, generator tables, Pedersen commitments and the
+Pippenger MSM, all through the C ABI, byte-for-byte against the CPU oracle."""
+import hashlib
+import random
+
+import pytest
+
+import bpp
+import orc
+
+pytestmark = pytest.mark.gpu
+L = orc.L
+
+
+def _points(n, seed):
+    """n valid encodings from the oracle's one-way map"""
+    import ctypes as C
+
+    out = []
+    o = C.create_string_buffer(32)
+    for i in range(n):
+        h = hashlib.shake_256(b"pt%d-%d" % (seed, i)).digest(64)
+        orc.lib().orc_ristretto_from_uniform(h, o)
+        out.append(o.raw)
+    return out
+
+
+def _orc_msm(scalars, points):
+    import ctypes as C
+
+    o = C.create_string_buffer(32)
+    assert orc.lib().orc_msm(b"".join(scalars), b"".join(points), len(scalars), 0, o) == 0
+    return o.raw
+
+
+def test_decompress_matches_oracle():
+    import ctypes as C
+
+    from test_oracle_primitives import RFC9496_BAD, RFC9496_MULTIPLES
+
+    e = bpp.engine()
+    rnd = random.Random(21)
+    encs = [bytes.fromhex(h) for h in RFC9496_MULTIPLES + RFC9496_BAD]
+    encs += _points(300, 1)
+    encs += [bytes(rnd.randrange(256) for _ in range(32)) for _ in range(300)]
+    encs += [(orc.P + k).to_bytes(32, "little") for k in range(0, 6)] + [(2**255 - 1).to_bytes(32, "little"), bytes(32)]
+    ok, re_enc = e.decompress_check(b"".join(encs))
+    o = C.create_string_buffer(32)
+    n_ok = 0
+    for i, enc in enumerate(encs):
+        exp_ok = orc.lib().orc_ristretto_decode_encode(enc, o)
+        assert ok[i] == exp_ok, (i, enc.hex())
+        if exp_ok:
+            n_ok += 1
+            assert re_enc[32 * i: 32 * i + 32] == enc == o.raw
+    assert n_ok > 300
+    assert e.decompress_check(b"") == ([], b"")
+
+
+def test_from_uniform_matches_oracle():
+    import ctypes as C
+
+    e = bpp.engine()
+    rnd = random.Random(22)
+    data = [bytes(rnd.randrange(256) for _ in range(64)) for _ in range(257)]
+    data += [bytes(64), b"\xff" * 64, bytes.fromhex(
+        "5d1be09e3d0c82fc538112490e35701979d99e06ca3e2b5b54bffe8b4dc772c14d98b696a1bbfb5ca32c436cc61c16563790306c79eaca7705668b47dffe5bb6")]
+    out = e.from_uniform(b"".join(data))
+    o = C.create_string_buffer(32)
+    for i, d in enumerate(data):
+        orc.lib().orc_ristretto_from_uniform(d, o)
+        assert out[32 * i: 32 * i + 32] == o.raw, i
+    # RFC 9496 one-way-map vector
+    assert out[32 * 259: 32 * 260].hex() == "3066f82a1a747d45120d1740f14358531a8f04bbffe6a819f86dfe50f44a0a46"
+
+
+@pytest.mark.parametrize("n,M,ext", [(64, 1, 1), (8, 4, 3), (64, 2, 6)])
+def test_generators_match_oracle(n, M, ext):
+    e = bpp.engine()
+    g = bpp.pkg.Gens(e, n, M, ext)
+    p = orc.Params(n, M, ext)
+    assert g.point(0) == p.point(0)
+    for k in range(ext):
+        assert g.point(1, k) == p.point(1, k)
+    for i in range(n * M):
+        assert g.point(2, i) == p.point(2, i)
+        assert g.point(3, i) == p.point(3, i)
+    with pytest.raises(bpp.pkg.EngineError):
+        g.point(1, ext)
+    # SURVEY.md §8c derived constants
+    if (n, M) == (64, 1):
+        assert g.point(2, 0).hex() == "fc3b25801422672a6a8d3adb5d8457d4301fe92324b4fc56ae934c8713ddfe2d"
+        assert g.point(3, 1).hex() == "acf2d2b95428fac99b12da3bab92edf8ea3788c2fd16769e586397eede7b5052"
+    # commitments: PedersenGens::commit
+    rnd = random.Random(n * 100 + ext)
+    vals = [0, 1, 2**64 - 1] + [rnd.randrange(2**64) for _ in range(20)]
+    for nb in sorted({1, ext}):
+        bl = [[rnd.randrange(L) for _ in range(nb)] for _ in vals]
+        bl[0] = [0] * nb
+        got = g.commit_batch(vals, bl)
+        for v, b, c in zip(vals, bl, got):
+            assert c == p.commit(v, b)
+    with pytest.raises(bpp.pkg.EngineError) as ei:
+        g.commit_batch([1], [[1] * (ext + 1)])
+    assert ei.value.code == bpp.pkg.INVALID_LENGTH
+
+
+def test_gens_argument_errors():
+    e = bpp.engine()
+    for args in [(63, 1, 1), (128, 1, 1), (64, 3, 1), (64, 1, 0), (64, 1, 7), (0, 1, 1)]:
+        with pytest.raises(bpp.pkg.EngineError) as ei:
+            bpp.pkg.Gens(e, *args)
+        assert ei.value.code == bpp.pkg.INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 64, 189, 190, 500, 2000])
+def test_msm_matches_oracle(n):
+    e = bpp.engine()
+    rnd = random.Random(100 + n)
+    pts = _points(n, n)
+    scs = [rnd.randrange(L).to_bytes(32, "little") for _ in range(n)]
+    assert e.msm(b"".join(scs), b"".join(pts)) == _orc_msm(scs, pts)
+
+
+def test_msm_scalar_distributions_and_duplicates():
+    e = bpp.engine()
+    rnd = random.Random(31)
+    base = _points(40, 77)
+    pts = [rnd.choice(base) for _ in range(600)] + [bytes(32)] * 5      # duplicates + identity points
+    special = [0, 1, L - 1, L - 2, 2**252, 2**252 - 1, 2**64 - 1, (L - 1) // 2, (L + 1) // 2]
+    scs = [rnd.choice(special) if rnd.random() < 0.6 else rnd.randrange(L) for _ in pts]
+    scs_b = [s.to_bytes(32, "little") for s in scs]
+    assert e.msm(b"".join(scs_b), b"".join(pts)) == _orc_msm(scs_b, pts)
+    # all-zero scalars -> identity
+    assert e.msm(bytes(32 * len(pts)), b"".join(pts)) == bytes(32)
+    # P - P
+    two = [base[0], base[0]]
+    assert e.msm((1).to_bytes(32, "little") + (L - 1).to_bytes(32, "little"), b"".join(two)) == bytes(32)
+
+
+def test_msm_rejects_bad_inputs():
+    e = bpp.engine()
+    pts = _points(3, 5)
+    with pytest.raises(bpp.pkg.EngineError) as ei:
+        e.msm(L.to_bytes(32, "little") * 3, b"".join(pts))
+    assert ei.value.code == bpp.pkg.INVALID_ARGUMENT
+    bad = pts[:2] + [b"\x01" + bytes(31)]
+    with pytest.raises(bpp.pkg.EngineError) as ei:
+        e.msm((5).to_bytes(32, "little") * 3, b"".join(bad))
+    assert ei.value.code == bpp.pkg.INVALID_ARGUMENT
+
+
+def test_msm_segmented_matches_oracle():
+    e = bpp.engine()
+    rnd = random.Random(41)
+    sizes = [5, 0, 66, 1, 300, 34, 18]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    pts = _points(offs[-1], 9)
+    scs = [rnd.randrange(L).to_bytes(32, "little") for _ in pts]
+    got = e.msm_segmented(offs, b"".join(scs), b"".join(pts))
+    for i, s in enumerate(sizes):
+        assert got[i] == _orc_msm(scs[offs[i]: offs[i + 1]], pts[offs[i]: offs[i + 1]]), i
+
+
+@pytest.mark.parametrize("c", [0, 4, 7, 11, 13, 16])
+def test_msm_plan_linearity_large(c):
+    """size-independent properties at sizes the oracle cannot follow: MSM(s)+MSM(t) == MSM(s+t); shard sum == whole"""
+    import ctypes as C
+
+    e = bpp.engine()
+    rnd = random.Random(50 + c)
+    n = 20000
+    base = _points(64, 3)
+    pts = [base[rnd.randrange(64)] for _ in range(n)]
+    s = [rnd.randrange(L) for _ in range(n)]
+    t = [rnd.randrange(L) for _ in range(n)]
+    u = [(a + b) % L for a, b in zip(s, t)]
+    plan = bpp.pkg.MsmPlan(e, b"".join(pts), c)
+    if c:
+        assert plan.window_bits == c
+    res = []
+    for vec in (s, t, u):
+        plan.set_scalars(b"".join(x.to_bytes(32, "little") for x in vec))
+        res.append(plan.run())
+    o = C.create_string_buffer(32)
+    assert orc.lib().orc_ristretto_add(res[0], res[1], o) == 1
+    assert o.raw == res[2]
+    # collapse duplicates on the host: sum_i s_i P_{k(i)} = sum_k (sum_{i: k(i)=k} s_i) P_k  -> 64-point oracle MSM
+    idx = {p: k for k, p in enumerate(base)}
+    agg = [0] * 64
+    for x, p in zip(s, pts):
+        agg[idx[p]] = (agg[idx[p]] + x) % L
+    assert res[0] == _orc_msm([a.to_bytes(32, "little") for a in agg], base)
+
+
+def test_microbench_runs():
+    e = bpp.engine()
+    before = e.launch_count
+    for which in (0, 1, 2, 3, 4, 5, 6, 7, 8):
+        ops, sec = e.microbench(which, 200)
+        assert ops > 1e9 and sec > 0
+    assert e.launch_count > before

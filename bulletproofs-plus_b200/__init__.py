@@ -195,3 +195,5 @@ def proof_check_bytes(data):
     ext, rounds = C.c_int32(), C.c_int32()
     rc = _ffi.lib().bpp_proof_check_bytes(data, len(data), C.byref(ext), C.byref(rounds))
     return rc, ext.value, rounds.value
+
+from . import api  # noqa: E402  (host-side mirror of the reference API; needs the definitions above)

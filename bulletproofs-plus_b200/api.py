@@ -1,0 +1,363 @@
+"""Host-side mirror of the reference's public API for the accelerated path, over the C ABI.
+
+Same names, argument meaning and error behaviour as tari_bulletproofs_plus 0.4.1:
+  RangeParameters::init            /root/reference/src/range_parameters.rs:32-58
+  RangeStatement::init             /root/reference/src/range_statement.rs:36-73
+  RangeWitness / CommitmentOpening /root/reference/src/range_witness.rs:15-41, src/commitment_opening.rs:15-38
+  ExtendedMask                     /root/reference/src/extended_mask.rs:15-41
+  PedersenGens::commit             /root/reference/src/generators/pedersen_gens.rs:112-122
+  RangeProof::{verify_batch, from_bytes, to_bytes, prove_with_rng}  /root/reference/src/range_proof.rs:232-608,712-752,1120-1257
+  merlin::Transcript               (re-exported by the reference, src/lib.rs)
+ProofError variants map to EngineError.code 1..5 (src/errors.rs:12-28).
+Points cross the boundary as 32-byte Ristretto encodings, scalars as python ints (mod l).
+"""
+import ctypes as C
+import enum
+
+from . import _ffi
+from . import Engine, Gens, EngineError, L, _chk, _u64arr
+
+ProofError = EngineError
+MAX_RANGE_PROOF_BIT_LENGTH = 64      # range_proof.rs:71
+MAX_RANGE_PROOF_BATCH_SIZE = 256     # range_proof.rs:76
+SERIALIZED_ELEMENT_SIZE = 32         # range_proof.rs:85
+
+
+class VerifyAction(enum.IntEnum):
+    RecoverOnly = 0
+    RecoverAndVerify = 1
+    VerifyOnly = 2
+
+
+class ExtensionDegree(enum.IntEnum):
+    DefaultPedersen = 1
+    AddOneBasePoint = 2
+    AddTwoBasePoints = 3
+    AddThreeBasePoints = 4
+    AddFourBasePoints = 5
+    AddFiveBasePoints = 6
+
+    @classmethod
+    def try_from(cls, v):
+        try:
+            return cls(v)
+        except ValueError:
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Extension degree not valid")
+
+
+def _sc(x):
+    return int(x % L).to_bytes(32, "little")
+
+
+class Transcript:
+    """merlin::Transcript on the 203-byte STROBE state the C ABI exchanges."""
+
+    def __init__(self, label=None, state=None):
+        if state is not None:
+            self.state = bytes(state)
+        else:
+            out = C.create_string_buffer(_ffi.TRANSCRIPT_BYTES)
+            _ffi.lib().bpp_transcript_new(label, len(label), out)
+            self.state = out.raw
+
+    def clone(self):
+        return Transcript(state=self.state)
+
+    def append_message(self, label, msg):
+        buf = C.create_string_buffer(self.state, _ffi.TRANSCRIPT_BYTES)
+        _ffi.lib().bpp_transcript_append_message(buf, label, len(label), msg, len(msg))
+        self.state = buf.raw
+
+    def challenge_bytes(self, label, n):
+        buf = C.create_string_buffer(self.state, _ffi.TRANSCRIPT_BYTES)
+        out = C.create_string_buffer(n)
+        _ffi.lib().bpp_transcript_challenge_bytes(buf, label, len(label), out, n)
+        self.state = buf.raw
+        return out.raw
+
+
+class ExtendedMask:
+    def __init__(self, blindings):
+        self._b = list(blindings)
+
+    @classmethod
+    def assign(cls, extension_degree, blindings):
+        if not blindings or len(blindings) != int(extension_degree):
+            raise EngineError(_ffi.INVALID_LENGTH, "Extended mask length must correspond to the extension degree")
+        return cls(blindings)
+
+    def blindings(self):
+        if not self._b:
+            raise EngineError(_ffi.INVALID_LENGTH, "Extended mask length cannot be 0")
+        return list(self._b)
+
+    def __eq__(self, o):
+        return isinstance(o, ExtendedMask) and self._b == o._b
+
+    def __repr__(self):
+        return "ExtendedMask(%r)" % (self._b,)
+
+
+class CommitmentOpening:
+    def __init__(self, v, r):
+        if not r:
+            raise EngineError(_ffi.INVALID_LENGTH, "Extended mask length cannot be 0")
+        self.v, self.r = int(v), [int(x) % L for x in r]
+
+
+class RangeWitness:
+    def __init__(self, openings):
+        self.openings = list(openings)
+        self.extension_degree = ExtensionDegree.try_from(len(self.openings[0].r)) if self.openings else None
+
+    @classmethod
+    def init(cls, openings):
+        if not openings:
+            raise EngineError(_ffi.INVALID_LENGTH, "Vector openings_vec length cannot be 0")
+        n = len(openings[0].r)
+        if any(len(o.r) != n for o in openings):
+            raise EngineError(_ffi.INVALID_LENGTH, "Extended mask length must be consistent")
+        return cls(openings)
+
+
+class RangeParameters:
+    """bp_gens + pc_gens, resident on the device (bpp_gens handle)."""
+
+    def __init__(self, gens):
+        self.gens = gens
+
+    @classmethod
+    def init(cls, engine, bit_length, aggregation_factor, extension_degree):
+        return cls(Gens(engine, bit_length, aggregation_factor, int(extension_degree)))
+
+    def bit_length(self):
+        return self.gens.bit_length
+
+    def max_aggregation_factor(self):
+        return self.gens.max_aggregation
+
+    def extension_degree(self):
+        return ExtensionDegree(self.gens.extension_degree)
+
+    def h_base(self):
+        return self.gens.point(0)
+
+    def g_bases(self):
+        return [self.gens.point(1, k) for k in range(self.gens.extension_degree)]
+
+    def gi_base(self, i):
+        return self.gens.point(2, i)
+
+    def hi_base(self, i):
+        return self.gens.point(3, i)
+
+    def commit(self, value, blindings):
+        """PedersenGens::commit"""
+        return self.gens.commit_batch([value], [list(blindings)])[0]
+
+
+class RangeStatement:
+    def __init__(self, generators, commitments, minimum_value_promises, seed_nonce):
+        self.generators = generators
+        self.commitments = list(commitments)
+        self.minimum_value_promises = list(minimum_value_promises)
+        self.seed_nonce = seed_nonce
+
+    @classmethod
+    def init(cls, generators, commitments, minimum_value_promises, seed_nonce=None):
+        n = len(commitments)
+        if n == 0 or n & (n - 1):
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Number of commitments must be a power of two")
+        if len(minimum_value_promises) != n:
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Incorrect number of minimum value promises")
+        if generators.max_aggregation_factor() < n:
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Not enough generators for this statement")
+        if seed_nonce is not None and n > 1:
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Mask recovery is not supported with an aggregated statement")
+        return cls(generators, commitments, minimum_value_promises, seed_nonce)
+
+
+class RangeProof:
+    """A serialised proof (range_proof.rs:58-68 in its to_bytes layout, :1120-1150)."""
+
+    def __init__(self, data, extension_degree, rounds):
+        self._bytes = bytes(data)
+        self._ext, self._rounds = extension_degree, rounds
+
+    @classmethod
+    def from_bytes(cls, data):
+        ext, rounds = C.c_int32(), C.c_int32()
+        rc = _ffi.lib().bpp_proof_check_bytes(bytes(data), len(data), C.byref(ext), C.byref(rounds))
+        if rc:
+            raise EngineError(rc, "Invalid serialized proof")
+        return cls(data, ext.value, rounds.value)
+
+    def to_bytes(self):
+        return self._bytes
+
+    def extension_degree(self):
+        return ExtensionDegree(self._ext)
+
+    @staticmethod
+    def extension_degree_from_proof_bytes(data):
+        if not data:
+            raise EngineError(_ffi.INVALID_LENGTH, "Serialized proof bytes cannot be empty")
+        return ExtensionDegree.try_from(data[0])
+
+    # ---- field views (the reference's getters a(), a1(), b(), li(), ri(), r1(), s1(), d1())
+    def _el(self, idx):
+        o = 1 + 32 * idx
+        return self._bytes[o:o + 32]
+
+    def d1(self):
+        return [int.from_bytes(self._el(k), "little") for k in range(self._ext)]
+
+    def a(self):
+        return self._el(self._ext)
+
+    def a1(self):
+        return self._el(self._ext + 1)
+
+    def b(self):
+        return self._el(self._ext + 2)
+
+    def r1(self):
+        return int.from_bytes(self._el(self._ext + 3), "little")
+
+    def s1(self):
+        return int.from_bytes(self._el(self._ext + 4), "little")
+
+    def li(self):
+        return [self._el(self._ext + 5 + 2 * j) for j in range(self._rounds)]
+
+    def ri(self):
+        return [self._el(self._ext + 6 + 2 * j) for j in range(self._rounds)]
+
+    # ---- verification
+    @staticmethod
+    def verify_batch(transcripts, statements, proofs, action):
+        """RangeProof::verify_batch: returns Vec<Option<ExtendedMask>> (min(len, 256) entries) or raises ProofError.
+        `transcripts` (list of Transcript) are advanced in place like `&mut [Transcript]`."""
+        if not statements or not proofs or not transcripts:
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Range statements or proofs length empty")
+        if len(statements) != len(proofs):
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Range statements and proofs length mismatch")
+        if len(transcripts) != len(statements):
+            raise EngineError(_ffi.INVALID_ARGUMENT, "Range statements and transcripts length mismatch")
+        status, masks = verify_chunks(statements[0].generators, [(transcripts, statements, proofs)], action)
+        if status[0]:
+            raise EngineError(status[0], "verify_batch")
+        return masks[0][:MAX_RANGE_PROOF_BATCH_SIZE]
+
+
+class _Packed:
+    """Flat host buffers for bpp_verify_args (kept alive for the duration of a call)."""
+
+    def __init__(self, params, calls, action):
+        self.params = params
+        ext = params.gens.extension_degree
+        chunk_offsets, proof_offsets, commit_offsets = [0], [0], [0]
+        pbytes, commits, minv, minp, seeds, seedp, tstates = [], [], [], [], [], [], []
+        self.transcripts = []
+        for transcripts, statements, proofs in calls:
+            if not (len(transcripts) == len(statements) == len(proofs)):
+                raise EngineError(_ffi.INVALID_ARGUMENT, "Range statements and proofs length mismatch")
+            for t, s, p in zip(transcripts, statements, proofs):
+                g = s.generators.gens
+                # verify_statements_and_generators_consistency (range_proof.rs:637-705): every statement must carry the
+                # same generators; with device-resident tables that is an identity/parameter comparison
+                if g is not params.gens and (g.bit_length, g.extension_degree) != (params.gens.bit_length, ext):
+                    raise EngineError(_ffi.INVALID_ARGUMENT, "Inconsistent generators in batch statement")
+                b = p.to_bytes()
+                pbytes.append(b)
+                proof_offsets.append(proof_offsets[-1] + len(b))
+                commits.extend(s.commitments)
+                commit_offsets.append(commit_offsets[-1] + len(s.commitments))
+                minv.extend((v or 0) for v in s.minimum_value_promises)
+                minp.extend(0 if v is None else 1 for v in s.minimum_value_promises)
+                seeds.append(_sc(s.seed_nonce) if s.seed_nonce is not None else bytes(32))
+                seedp.append(0 if s.seed_nonce is None else 1)
+                tstates.append(t.state)
+                self.transcripts.append(t)
+            chunk_offsets.append(len(pbytes))
+        n = len(pbytes)
+        self.n, self.k, self.ext = n, len(calls), ext
+        self.chunk_offsets = _u64arr(chunk_offsets)
+        self.proof_offsets = _u64arr(proof_offsets)
+        self.commit_offsets = _u64arr(commit_offsets)
+        self.proof_bytes = C.create_string_buffer(b"".join(pbytes), max(1, proof_offsets[-1]))
+        self.commitments = C.create_string_buffer(b"".join(commits), max(1, 32 * len(commits)))
+        self.min_values = _u64arr(minv)
+        self.min_present = (C.c_uint8 * max(1, len(minp)))(*minp)
+        self.seeds = C.create_string_buffer(b"".join(seeds), max(1, 32 * n))
+        self.seed_present = (C.c_uint8 * max(1, n))(*seedp)
+        self.tbuf = C.create_string_buffer(b"".join(tstates), max(1, _ffi.TRANSCRIPT_BYTES * n))
+        a = _ffi.VerifyArgs()
+        a.n_proofs, a.n_chunks = n, self.k
+        a.chunk_offsets = C.addressof(self.chunk_offsets)
+        a.proof_bytes = C.addressof(self.proof_bytes)
+        a.proof_offsets = C.addressof(self.proof_offsets)
+        a.commitments32 = C.addressof(self.commitments)
+        a.commit_offsets = C.addressof(self.commit_offsets)
+        a.min_values = C.addressof(self.min_values)
+        a.min_present = C.addressof(self.min_present)
+        a.seed_nonces32 = C.addressof(self.seeds)
+        a.seed_present = C.addressof(self.seed_present)
+        a.transcripts = C.addressof(self.tbuf)
+        a.action = int(action)
+        self.args = a
+        self.status = (C.c_int32 * max(1, self.k))()
+        self.masks = C.create_string_buffer(max(1, 32 * n * ext))
+        self.mask_present = C.create_string_buffer(max(1, n))
+
+    def results(self):
+        for i, t in enumerate(self.transcripts):
+            t.state = self.tbuf.raw[_ffi.TRANSCRIPT_BYTES * i: _ffi.TRANSCRIPT_BYTES * (i + 1)]
+        status = [self.status[c] for c in range(self.k)]
+        out = []
+        for c in range(self.k):
+            lo, hi = self.chunk_offsets[c], self.chunk_offsets[c + 1]
+            row = []
+            for i in range(lo, hi):
+                if self.mask_present.raw[i]:
+                    row.append(ExtendedMask([int.from_bytes(self.masks.raw[32 * (i * self.ext + k): 32 * (i * self.ext + k + 1)], "little")
+                                             for k in range(self.ext)]))
+                else:
+                    row.append(None)
+            out.append(row)
+        return status, out
+
+
+def verify_chunks(params, calls, action):
+    """K independent RangeProof::verify_batch calls in one device pass.
+    calls: list of (transcripts, statements, proofs).  Returns (status per call, masks per call)."""
+    pk = _Packed(params, calls, action)
+    rc = _ffi.lib().bpp_verify_chunks(params.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present)
+    _chk(params.gens.engine, rc)
+    return pk.results()
+
+
+class VerifyBatch:
+    """Split form (bpp_vbatch_*): create = host Fiat-Shamir + upload, run = device work + verdict readback."""
+
+    def __init__(self, params, calls, action):
+        self.pk = _Packed(params, calls, action)
+        self.params = params
+        self.h = C.c_void_p()
+        _chk(params.gens.engine, _ffi.lib().bpp_vbatch_create(params.gens.h, C.byref(self.pk.args), C.byref(self.h)))
+
+    def run(self):
+        pk = self.pk
+        _chk(self.params.gens.engine, _ffi.lib().bpp_vbatch_run(self.h, pk.status, pk.masks, pk.mask_present))
+        return pk.results()
+
+    def close(self):
+        if self.h:
+            _ffi.lib().bpp_vbatch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,498 @@
+// Batch verification entry points: bpp_vbatch_create / bpp_vbatch_run / bpp_verify_chunks.
+//
+// Host side restates the control flow of RangeProof::verify_batch -> verify
+// (/root/reference/src/range_proof.rs:712-1065): argument checks (:719-734), first-256 truncation (:739-751), consistency
+// (:610-709), loop 1 = Fiat-Shamir replay of every proof's transcript + the verifier weight transcript (:811-853),
+// then hands loop 2 (:856-1033) and the single merged multiscalar check (:1039-1062) to the device:
+//   K-DECOMPRESS (k_point.cu) -> K-VPREP (k_verify.cu) -> K-MSM segmented by reference call (k_msm.cu) -> identity test.
+// Error precedence of the reference is reproduced when the per-chunk status is resolved after the device returns.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include "engine.hpp"
+#include "hash.cuh"
+
+using namespace bpp;
+
+namespace {
+
+struct HProof {
+    int32_t pre_rc = 0;        // from_bytes / RangeStatement::init class errors
+    int32_t loop1_rc = 0;      // transcript replay (VerificationFailed)
+    int32_t loop2_rc = 0;      // host-known loop-2 errors (InvalidLength on rounds, y == 1)
+    int ext = 0, rounds = 0;
+    uint32_t m = 0;
+    const uint8_t *bytes = nullptr;   // serialised proof
+    bool has_seed = false;
+    uint8_t seed[32];
+    uint32_t pt_off = 0, n_pts = 0;   // slots in the point table: [A, A1, B, L.., R.., V..]
+    uint8_t y[32], z[32], e[32];
+    uint8_t ej[BPP_MAX_ROUNDS][32];
+    uint8_t wbytes[32];               // 32 bytes drawn from the proof's verifier rng -> weight transcript
+    uint8_t weight[32];
+    uint8_t tstate[BPP_TRANSCRIPT_BYTES];
+    const uint8_t *d1() const { return bytes + 1; }
+    const uint8_t *a() const { return bytes + 1 + 32 * ext; }
+    const uint8_t *a1() const { return a() + 32; }
+    const uint8_t *b() const { return a() + 64; }
+    const uint8_t *r1() const { return a() + 96; }
+    const uint8_t *s1() const { return a() + 128; }
+    const uint8_t *li(int j) const { return a() + 160 + 64 * j; }
+    const uint8_t *ri(int j) const { return a() + 192 + 64 * j; }
+};
+
+struct HChunk {
+    size_t lo = 0, hi = 0;     // proofs looked at: [lo, hi) (hi - lo <= 256)
+    int32_t pre_rc = 0;        // empty batch / from_bytes / statement / consistency errors
+    int32_t loop1_rc = 0;
+    bool computable = false;   // no host-known error: device prep + MSM (or mask recovery) runs
+    uint32_t max_mn = 0;
+    uint32_t entry_off = 0, n_entries = 0;
+};
+
+inline bool is_zero32(const uint8_t *p) {
+    uint8_t r = 0;
+    for (int i = 0; i < 32; i++) r |= p[i];
+    return r == 0;
+}
+#define LBL(s) (const uint8_t *)(s), (sizeof(s) - 1)
+
+// protocols/transcript_protocol.rs:67-78
+inline int32_t challenge_scalar(Merlin &t, const uint8_t *label, size_t ll, uint8_t out32[32]) {
+    uint8_t buf[64];
+    t.challenge_bytes(label, ll, buf, 64);
+    host_sc_from_wide(buf, out32);
+    return is_zero32(out32) ? BPP_VERIFICATION_FAILED : BPP_OK;
+}
+// protocols/transcript_protocol.rs:49-61
+inline int32_t validate_and_append_point(Merlin &t, const uint8_t *label, size_t ll, const uint8_t pt[32]) {
+    if (is_zero32(pt)) return BPP_VERIFICATION_FAILED;
+    t.append_message(label, ll, pt, 32);
+    return BPP_OK;
+}
+
+// Loop 1 body for one proof: RangeProofTranscript::new (transcripts.rs:59-121), challenges_y_z (:124-136),
+// challenge_round_e (:139-149), challenge_final_e (:152-162), to_verifier_rng (:166-179) + 32 rng bytes.
+int32_t replay_transcript(const bpp_gens *g, HProof &p, const uint8_t *commitments32, const uint64_t *min_values,
+                          const uint8_t *min_present) {
+    Merlin t;
+    t.s.load(p.tstate);
+    int32_t rc = BPP_OK;
+    t.append_message(LBL("dom-sep"), LBL("Bulletproofs+ Range Proof"));
+    do {
+        if ((rc = validate_and_append_point(t, LBL("H"), g->h()))) break;
+        for (int k = 0; k < g->ext && !rc; k++) rc = validate_and_append_point(t, LBL("G"), g->g(k));
+        if (rc) break;
+        t.append_u64(LBL("N"), (uint64_t)g->n);
+        t.append_u64(LBL("T"), (uint64_t)g->ext);
+        t.append_u64(LBL("M"), (uint64_t)p.m);
+        for (uint32_t j = 0; j < p.m; j++) t.append_message(LBL("Ci"), commitments32 + 32 * j, 32);
+        for (uint32_t j = 0; j < p.m; j++) t.append_u64(LBL("vi - minimum_value"), min_present[j] ? min_values[j] : 0);
+        if ((rc = validate_and_append_point(t, LBL("A"), p.a()))) break;
+        if ((rc = challenge_scalar(t, LBL("y"), p.y))) break;
+        if ((rc = challenge_scalar(t, LBL("z"), p.z))) break;
+        for (int j = 0; j < p.rounds && !rc; j++) {
+            if ((rc = validate_and_append_point(t, LBL("L"), p.li(j)))) break;
+            if ((rc = validate_and_append_point(t, LBL("R"), p.ri(j)))) break;
+            rc = challenge_scalar(t, LBL("e"), p.ej[j]);
+        }
+        if (rc) break;
+        if ((rc = validate_and_append_point(t, LBL("A1"), p.a1()))) break;
+        if ((rc = validate_and_append_point(t, LBL("B"), p.b()))) break;
+        if ((rc = challenge_scalar(t, LBL("e"), p.e))) break;
+        t.append_message(LBL("r1"), p.r1(), 32);
+        t.append_message(LBL("s1"), p.s1(), 32);
+        for (int k = 0; k < p.ext; k++) t.append_message(LBL("d1"), p.d1() + 32 * k, 32);
+        MerlinRng rng;
+        const uint8_t zeros[32] = {0};
+        rng.build(t, nullptr, 0, false, zeros);     // NullRng, utils/nullrng.rs
+        rng.fill(p.wbytes, 32);
+    } while (0);
+    t.s.store(p.tstate);
+    return rc;
+}
+
+// utils/generic.rs:30-60
+void nonce(const uint8_t seed[32], const char *label, bool have_j, uint32_t j, bool have_k, uint32_t k, uint8_t out32[32]) {
+    uint8_t key[43];
+    size_t kl = 0;
+    key[kl++] = 0;
+    memcpy(key + kl, seed, 32); kl += 32;
+    if (have_j) { key[kl++] = 'j'; for (int i = 0; i < 4; i++) key[kl++] = (uint8_t)(j >> (8 * i)); }
+    if (have_k) { key[kl++] = 'k'; for (int i = 0; i < 4; i++) key[kl++] = (uint8_t)(k >> (8 * i)); }
+    uint8_t h[64];
+    blake2b_keyed_personal_empty(h, key, kl, (const uint8_t *)label, strlen(label));
+    host_sc_from_wide(h, out32);
+}
+
+template <class F> void parallel_for(size_t n, int threads, F f) {
+    if (n == 0) return;
+    size_t nt = std::min<size_t>((size_t)std::max(threads, 1), (n + 7) / 8);
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    auto body = [&]() {
+        for (;;) {
+            size_t i0 = next.fetch_add(8);
+            if (i0 >= n) break;
+            size_t i1 = std::min(n, i0 + 8);
+            for (size_t i = i0; i < i1; i++) f(i);
+        }
+    };
+    for (size_t t = 1; t < nt; t++) th.emplace_back(body);
+    body();
+    for (auto &x : th) x.join();
+}
+
+} // namespace
+
+struct bpp_vbatch {
+    bpp_gens *g = nullptr;
+    int32_t action = BPP_VERIFY_ONLY;
+    size_t n_proofs = 0, n_chunks = 0;
+    std::vector<HProof> hp;
+    std::vector<HChunk> hc;
+    std::vector<uint64_t> chunk_offsets;
+    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, max_static = 0;
+    bool any_msm = false, any_masks = false;
+    MsmShape shape;
+    DevBuf d_enc, d_tab, d_ok, d_proofs, d_chunks, d_vecoff, d_pscal, d_chal, d_weights, d_minv, d_minp, d_nonces, d_mscal, d_pidx,
+        d_segoff, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident;
+    PinBuf h_ok, h_ident, h_masks;
+    void release() {
+        for (DevBuf *b : {&d_enc, &d_tab, &d_ok, &d_proofs, &d_chunks, &d_vecoff, &d_pscal, &d_chal, &d_weights, &d_minv, &d_minp, &d_nonces,
+                          &d_mscal, &d_pidx, &d_segoff, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident})
+            b->release();
+        h_ok.release(); h_ident.release(); h_masks.release();
+    }
+};
+
+extern "C" {
+
+void bpp_vbatch_destroy(bpp_vbatch *vb) {
+    if (!vb) return;
+    cudaSetDevice(vb->g->ctx->device);
+    cudaStreamSynchronize(vb->g->ctx->stream);
+    vb->release();
+    delete vb;
+}
+
+int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **out) {
+    if (!g || !a || !out) return BPP_INVALID_ARGUMENT;
+    bpp_ctx *ctx = g->ctx;
+    *out = nullptr;
+    if (a->n_chunks == 0 || !a->chunk_offsets) return fail(ctx, BPP_INVALID_ARGUMENT, "Range statements or proofs length empty");
+    if (a->chunk_offsets[0] != 0 || a->chunk_offsets[a->n_chunks] != a->n_proofs) return fail(ctx, BPP_INVALID_ARGUMENT, "bad chunk offsets");
+    for (size_t c = 0; c < a->n_chunks; c++)
+        if (a->chunk_offsets[c + 1] < a->chunk_offsets[c]) return fail(ctx, BPP_INVALID_ARGUMENT, "bad chunk offsets");
+    if (a->n_proofs && (!a->proof_bytes || !a->proof_offsets || !a->commitments32 || !a->commit_offsets || !a->min_values ||
+                        !a->min_present || !a->transcripts))
+        return fail(ctx, BPP_INVALID_ARGUMENT, "null argument");
+    if (a->action < BPP_RECOVER_ONLY || a->action > BPP_VERIFY_ONLY) return fail(ctx, BPP_INVALID_ARGUMENT, "bad action");
+    if (a->n_proofs >= (1u << 24)) return fail(ctx, BPP_SIZE_OVERFLOW, "too many proofs in one call");
+    cudaSetDevice(ctx->device);
+
+    bpp_vbatch *vb = new bpp_vbatch();
+    vb->g = g; vb->action = a->action; vb->n_proofs = a->n_proofs; vb->n_chunks = a->n_chunks;
+    vb->chunk_offsets.assign(a->chunk_offsets, a->chunk_offsets + a->n_chunks + 1);
+    vb->hp.resize(a->n_proofs);
+    vb->hc.resize(a->n_chunks);
+    const int n = g->n, ext = g->ext;
+    const bool want_masks = a->action != BPP_VERIFY_ONLY;
+
+    // ---- per-proof parsing + statement checks; per-chunk consistency
+    std::vector<size_t> work;     // proofs whose transcripts are replayed
+    for (size_t c = 0; c < a->n_chunks; c++) {
+        HChunk &hc = vb->hc[c];
+        hc.lo = a->chunk_offsets[c];
+        hc.hi = std::min<size_t>(a->chunk_offsets[c + 1], hc.lo + BPP_MAX_BATCH);       // range_proof.rs:739-751
+        if (hc.hi == hc.lo) { hc.pre_rc = BPP_INVALID_ARGUMENT; continue; }               // :719-723
+        int32_t ext_rc = 0, promise_rc = 0;
+        for (size_t i = hc.lo; i < hc.hi; i++) {
+            HProof &p = vb->hp[i];
+            size_t plen = a->proof_offsets[i + 1] - a->proof_offsets[i];
+            p.bytes = a->proof_bytes + a->proof_offsets[i];
+            int32_t pext = 0, rounds = 0;
+            p.pre_rc = bpp_proof_check_bytes(p.bytes, plen, &pext, &rounds);            // RangeProof::from_bytes
+            p.ext = pext; p.rounds = rounds;
+            uint64_t m64 = a->commit_offsets[i + 1] - a->commit_offsets[i];
+            p.m = (uint32_t)m64;
+            p.has_seed = a->seed_present && a->seed_nonces32 && a->seed_present[i];
+            if (!p.pre_rc) {                                                             // RangeStatement::init, range_statement.rs:42-61
+                if (m64 == 0 || (m64 & (m64 - 1)) || m64 > (uint64_t)g->M) p.pre_rc = BPP_INVALID_ARGUMENT;
+                else if (p.has_seed && m64 > 1) p.pre_rc = BPP_INVALID_ARGUMENT;
+            }
+            if (p.pre_rc && !hc.pre_rc) hc.pre_rc = p.pre_rc;
+            if (p.pre_rc) continue;
+            if (p.has_seed) {
+                uint32_t w[8];
+                memcpy(w, a->seed_nonces32 + 32 * i, 32);
+                sc s; for (int k = 0; k < 8; k++) s.v[k] = w[k];
+                sc_tobytes(p.seed, sc_reduce256(s));
+            }
+            if (p.ext != ext && !ext_rc) ext_rc = BPP_INVALID_ARGUMENT;                  // :637-660
+            if (n < 64)
+                for (uint32_t j = 0; j < p.m; j++) {
+                    size_t ci = a->commit_offsets[i] + j;
+                    if (a->min_present[ci] && (a->min_values[ci] >> n) > 0 && !promise_rc) promise_rc = BPP_INVALID_LENGTH;   // :675-682
+                }
+        }
+        if (!hc.pre_rc) hc.pre_rc = ext_rc ? ext_rc : promise_rc;
+        if (!hc.pre_rc)
+            for (size_t i = hc.lo; i < hc.hi; i++) work.push_back(i);
+    }
+
+    // ---- loop 1: transcript replay (parallel over proofs), then the sequential weight transcript per chunk
+    for (size_t i : work) memcpy(vb->hp[i].tstate, a->transcripts + BPP_TRANSCRIPT_BYTES * i, BPP_TRANSCRIPT_BYTES);
+    parallel_for(work.size(), ctx->host_threads, [&](size_t k) {
+        size_t i = work[k];
+        HProof &p = vb->hp[i];
+        p.loop1_rc = replay_transcript(g, p, a->commitments32 + 32 * a->commit_offsets[i], a->min_values + a->commit_offsets[i],
+                                       a->min_present + a->commit_offsets[i]);
+    });
+    parallel_for(a->n_chunks, ctx->host_threads, [&](size_t c) {
+        HChunk &hc = vb->hc[c];
+        if (hc.pre_rc) return;
+        size_t stop = hc.hi;
+        for (size_t i = hc.lo; i < hc.hi; i++)
+            if (vb->hp[i].loop1_rc) { hc.loop1_rc = vb->hp[i].loop1_rc; stop = i + 1; break; }
+        // `&mut Transcript` semantics: transcripts up to (and including) the failing one are advanced
+        for (size_t i = hc.lo; i < stop; i++) memcpy(a->transcripts + BPP_TRANSCRIPT_BYTES * i, vb->hp[i].tstate, BPP_TRANSCRIPT_BYTES);
+        if (hc.loop1_rc) return;
+        Merlin wt;
+        wt.init(LBL("Bulletproofs+ verifier weights"));                                   // :811
+        for (size_t i = hc.lo; i < hc.hi; i++) wt.append_message(LBL("proof"), vb->hp[i].wbytes, 32);   // :849
+        MerlinRng wr;
+        const uint8_t zeros[32] = {0};
+        wr.build(wt, nullptr, 0, false, zeros);                                           // :853
+        bool ok = true;
+        uint32_t max_mn = 0;
+        for (size_t i = hc.lo; i < hc.hi; i++) {
+            HProof &p = vb->hp[i];
+            uint8_t wide[64];
+            do { wr.fill(wide, 64); host_sc_from_wide(wide, p.weight); } while (is_zero32(p.weight));   // :894 random_not_zero
+            uint64_t N = (uint64_t)p.m * (uint64_t)n;
+            if (p.rounds >= 32 || (1ull << p.rounds) != N) p.loop2_rc = BPP_INVALID_LENGTH;            // :886-888
+            else {
+                uint8_t one[32] = {1};
+                if (!memcmp(p.y, one, 32)) p.loop2_rc = BPP_VERIFICATION_FAILED;                        // (y - 1) is not invertible
+            }
+            if (p.loop2_rc) ok = false;
+            max_mn = std::max<uint32_t>(max_mn, (uint32_t)N);
+        }
+        hc.computable = ok;
+        hc.max_mn = max_mn;
+    });
+
+    // ---- device layout
+    std::vector<VProof> dp(a->n_proofs);
+    std::vector<VChunk> dc(a->n_chunks);
+    std::vector<uint32_t> vecoff(a->n_proofs + 1, 0), segoff(a->n_chunks + 1, 0);
+    std::vector<uint8_t> enc, pscal, chal, weights(32 * std::max<size_t>(a->n_proofs, 1)), nonces;
+    std::vector<uint32_t> pidx;
+    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, contrib = 0, pv = 0, max_static = 0;
+    const uint32_t GEN = 0x80000000u;
+    for (size_t c = 0; c < a->n_chunks; c++) {
+        HChunk &hc = vb->hc[c];
+        VChunk &ch = dc[c];
+        ch.proof_lo = (uint32_t)hc.lo; ch.proof_hi = (uint32_t)hc.hi; ch.max_mn = hc.max_mn;
+        bool msm = hc.computable && a->action != BPP_RECOVER_ONLY;
+        ch.active = msm ? 1 : 0;
+        ch.entry_off = n_entries;
+        hc.entry_off = n_entries;
+        segoff[c] = n_entries;
+        if (msm) {
+            vb->any_msm = true;
+            uint32_t n_static = 2 * hc.max_mn + (uint32_t)ext + 1;
+            max_static = std::max(max_static, n_static);
+            for (uint32_t i = 0; i < hc.max_mn; i++) pidx.push_back(GEN | i);
+            for (uint32_t i = 0; i < hc.max_mn; i++) pidx.push_back(GEN | (uint32_t)(g->nm + i));
+            for (int k = 0; k < ext; k++) pidx.push_back(GEN | (uint32_t)(2 * g->nm + k));
+            pidx.push_back(GEN | (uint32_t)(2 * g->nm + ext));
+            n_entries += n_static;
+        }
+        for (size_t i = a->chunk_offsets[c]; i < a->chunk_offsets[c + 1]; i++) {
+            HProof &p = vb->hp[i];
+            VProof &v = dp[i];
+            memset(&v, 0, sizeof v);
+            v.nonce_off = 0xffffffffu;
+            vecoff[i] = total_vec;
+            if (i >= hc.hi || p.pre_rc || !p.bytes) continue;
+            // point table slots (decompressed whatever the chunk's fate: the flags decide InvalidArgument precedence)
+            p.pt_off = n_pts;
+            p.n_pts = 3 + 2 * (uint32_t)p.rounds + p.m;
+            enc.insert(enc.end(), p.a(), p.a() + 96);
+            for (int j = 0; j < p.rounds; j++) enc.insert(enc.end(), p.li(j), p.li(j) + 32);
+            for (int j = 0; j < p.rounds; j++) enc.insert(enc.end(), p.ri(j), p.ri(j) + 32);
+            const uint8_t *cm = a->commitments32 + 32 * a->commit_offsets[i];
+            enc.insert(enc.end(), cm, cm + 32 * (size_t)p.m);
+            n_pts += p.n_pts;
+            if (!hc.computable) continue;
+            v.m = p.m; v.rounds = (uint32_t)p.rounds;
+            v.commit_off = (uint32_t)a->commit_offsets[i];
+            v.sc_off = (uint32_t)(pscal.size() / 32);
+            pscal.insert(pscal.end(), p.r1(), p.r1() + 64);
+            pscal.insert(pscal.end(), p.d1(), p.d1() + 32 * (size_t)ext);
+            v.ch_off = (uint32_t)(chal.size() / 32);
+            chal.insert(chal.end(), p.y, p.y + 32); chal.insert(chal.end(), p.z, p.z + 32); chal.insert(chal.end(), p.e, p.e + 32);
+            for (int j = 0; j < p.rounds; j++) chal.insert(chal.end(), p.ej[j], p.ej[j] + 32);
+            memcpy(&weights[32 * i], p.weight, 32);
+            if (want_masks && p.has_seed) {
+                v.nonce_off = (uint32_t)(nonces.size() / 32);
+                size_t base = nonces.size();
+                nonces.resize(base + 32 * (size_t)ext * (3 + 2 * (size_t)p.rounds));
+                uint8_t *nn = nonces.data() + base;
+                for (int k = 0; k < ext; k++) {
+                    nonce(p.seed, "eta", false, 0, true, (uint32_t)k, nn + 32 * k);
+                    nonce(p.seed, "d", false, 0, true, (uint32_t)k, nn + 32 * (ext + k));
+                    nonce(p.seed, "alpha", false, 0, true, (uint32_t)k, nn + 32 * (2 * ext + k));
+                    for (int j = 0; j < p.rounds; j++) {
+                        nonce(p.seed, "dL", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + j * ext + k));
+                        nonce(p.seed, "dR", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + p.rounds * ext + j * ext + k));
+                    }
+                }
+                vb->any_masks = true;
+            }
+            if (msm) {
+                v.active = 1;
+                uint32_t N = 1u << p.rounds;
+                v.entry_off = n_entries;
+                v.contrib_off = contrib; contrib += 2 * N;
+                v.pv_off = pv; pv += 8 + 3 * (uint32_t)p.rounds + p.m;
+                total_vec += N;
+                uint32_t R = (uint32_t)p.rounds;
+                pidx.push_back(p.pt_off + 1); pidx.push_back(p.pt_off + 2); pidx.push_back(p.pt_off);
+                for (uint32_t j = 0; j < 2 * R + p.m; j++) pidx.push_back(p.pt_off + 3 + j);
+                n_entries += 3 + 2 * R + p.m;
+            }
+        }
+        hc.n_entries = n_entries - hc.entry_off;
+    }
+    vecoff[a->n_proofs] = total_vec;
+    segoff[a->n_chunks] = n_entries;
+    vb->n_pts = n_pts; vb->n_entries = n_entries; vb->total_vec = total_vec; vb->max_static = max_static;
+    vb->shape = msm_shape(n_entries, (uint32_t)a->n_chunks, 0);
+
+    // ---- upload
+    cudaStream_t st = ctx->stream;
+    auto up = [&](DevBuf &d, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.ensure(std::max<size_t>(bytes, 32));
+        if (e != cudaSuccess || bytes == 0) return e;
+        return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    size_t n_commit = a->commit_offsets ? a->commit_offsets[a->n_proofs] : 0;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ok(up(vb->d_enc, enc.data(), enc.size()));
+    ok(up(vb->d_proofs, dp.data(), dp.size() * sizeof(VProof)));
+    ok(up(vb->d_chunks, dc.data(), dc.size() * sizeof(VChunk)));
+    ok(up(vb->d_vecoff, vecoff.data(), vecoff.size() * 4));
+    ok(up(vb->d_pscal, pscal.data(), pscal.size()));
+    ok(up(vb->d_chal, chal.data(), chal.size()));
+    ok(up(vb->d_weights, weights.data(), weights.size()));
+    ok(up(vb->d_minv, a->min_values, n_commit * 8));
+    ok(up(vb->d_minp, a->min_present, n_commit));
+    ok(up(vb->d_nonces, nonces.data(), nonces.size()));
+    ok(up(vb->d_pidx, pidx.data(), pidx.size() * 4));
+    ok(up(vb->d_segoff, segoff.data(), segoff.size() * 4));
+    ok(vb->d_tab.ensure(sizeof(aniels) * std::max<size_t>(n_pts, 1)));
+    ok(vb->d_ok.ensure(std::max<size_t>(n_pts, 1)));
+    ok(vb->d_mscal.ensure(32 * std::max<size_t>(n_entries, 1)));
+    ok(vb->d_contrib.ensure(32 * std::max<size_t>(contrib, 1)));
+    ok(vb->d_hg.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (1 + (size_t)ext)));
+    ok(vb->d_pervec.ensure(32 * std::max<size_t>(pv, 1)));
+    ok(vb->d_masks.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext));
+    ok(vb->d_scratch.ensure(msm_scratch_bytes(vb->shape)));
+    ok(vb->d_res.ensure(sizeof(ge) * a->n_chunks));
+    ok(vb->d_ident.ensure(a->n_chunks));
+    ok(vb->h_ok.ensure(std::max<size_t>(n_pts, 1)));
+    ok(vb->h_ident.ensure(a->n_chunks));
+    ok(vb->h_masks.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // host vectors go out of scope
+    if (e != cudaSuccess) { vb->release(); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
+    *out = vb;
+    return BPP_OK;
+}
+
+int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present) {
+    if (!vb || !chunk_status) return BPP_INVALID_ARGUMENT;
+    bpp_gens *g = vb->g;
+    bpp_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const int ext = g->ext;
+    // ---- device: decompress -> prep -> MSM -> identity flags
+    if (vb->n_pts) {
+        launch_decompress(st, vb->n_pts, vb->d_enc.as<uint32_t>(), vb->d_tab.as<aniels>(), vb->d_ok.as<uint8_t>(), nullptr, nullptr);
+        ctx->launches++;
+    }
+    VDims d;
+    d.n_proofs = (uint32_t)vb->n_proofs; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)ext;
+    d.action = vb->action;
+    VBuffers b;
+    b.proofs = vb->d_proofs.as<VProof>(); b.chunks = vb->d_chunks.as<VChunk>(); b.vec_offsets = vb->d_vecoff.as<uint32_t>();
+    b.proof_scalars = vb->d_pscal.as<uint32_t>(); b.challenges = vb->d_chal.as<uint32_t>(); b.weights = vb->d_weights.as<uint32_t>();
+    b.min_values = vb->d_minv.as<uint64_t>(); b.min_present = vb->d_minp.as<uint8_t>(); b.nonces = vb->d_nonces.as<uint32_t>();
+    b.msm_scalars = vb->d_mscal.as<uint32_t>(); b.contrib = vb->d_contrib.as<uint32_t>(); b.hg_contrib = vb->d_hg.as<uint32_t>();
+    b.pervec = vb->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? vb->d_masks.as<uint32_t>() : nullptr;
+    if (vb->any_msm || vb->any_masks) launch_verify_prep(st, d, b, vb->total_vec, vb->any_msm ? vb->max_static : 0, &ctx->launches);
+    if (vb->any_msm) {
+        launch_msm(st, vb->shape, vb->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->d_segoff.as<uint32_t>() : nullptr, vb->d_pidx.as<uint32_t>(),
+                   vb->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->d_scratch.p, vb->d_res.as<ge>(), &ctx->launches);
+        launch_encode(st, vb->n_chunks, vb->d_res.as<ge>(), nullptr, vb->d_ident.as<uint8_t>());
+        ctx->launches++;
+        BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_ident.p, vb->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+    }
+    BPP_CUDA(ctx, cudaGetLastError());
+    if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_ok.p, vb->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
+    if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_masks.p, vb->d_masks.p, 32 * vb->n_proofs * (size_t)ext, cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(ctx, cudaStreamSynchronize(st));
+
+    // ---- resolve per-chunk status with the reference's precedence
+    const uint8_t *okf = vb->h_ok.as<uint8_t>();
+    const uint8_t *ident = vb->h_ident.as<uint8_t>();
+    for (size_t c = 0; c < vb->n_chunks; c++) {
+        const HChunk &hc = vb->hc[c];
+        int32_t rc = hc.pre_rc;
+        if (!rc) {   // a commitment that is not a valid encoding can not be a RangeStatement commitment (a point)
+            for (size_t i = hc.lo; i < hc.hi && !rc; i++) {
+                const HProof &p = vb->hp[i];
+                for (uint32_t j = 0; j < p.m; j++)
+                    if (!okf[p.pt_off + 3 + 2 * p.rounds + j]) { rc = BPP_INVALID_ARGUMENT; break; }
+            }
+        }
+        if (!rc) rc = hc.loop1_rc;
+        if (!rc) {
+            for (size_t i = hc.lo; i < hc.hi && !rc; i++) {                                 // loop 2, proof order
+                const HProof &p = vb->hp[i];
+                for (uint32_t j = 0; j < 3 + 2 * (uint32_t)p.rounds; j++)
+                    if (!okf[p.pt_off + j]) { rc = BPP_INVALID_ARGUMENT; break; }         // :859-866
+                if (!rc) rc = p.loop2_rc;
+            }
+        }
+        if (!rc && vb->action != BPP_RECOVER_ONLY && !ident[c]) rc = BPP_VERIFICATION_FAILED;   // :1057-1061
+        chunk_status[c] = rc;
+        // Vec<Option<ExtendedMask>>
+        for (size_t i = vb->chunk_offsets[c]; i < vb->chunk_offsets[c + 1]; i++) {
+            bool have = !rc && i < hc.hi && vb->action != BPP_VERIFY_ONLY && vb->hp[i].has_seed;
+            if (mask_present) mask_present[i] = have ? 1 : 0;
+            if (masks32) {
+                if (have) memcpy(masks32 + 32 * i * (size_t)ext, vb->h_masks.as<uint8_t>() + 32 * i * (size_t)ext, 32 * (size_t)ext);
+                else memset(masks32 + 32 * i * (size_t)ext, 0, 32 * (size_t)ext);
+            }
+        }
+    }
+    return BPP_OK;
+}
+
+int32_t bpp_verify_chunks(bpp_gens *g, const bpp_verify_args *args, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present) {
+    bpp_vbatch *vb = nullptr;
+    int32_t rc = bpp_vbatch_create(g, args, &vb);
+    if (rc) return rc;
+    rc = bpp_vbatch_run(vb, chunk_status, masks32, mask_present);
+    bpp_vbatch_destroy(vb);
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,233 @@
+// K-VPREP: per-proof scalar synthesis of the Bulletproofs+ batch verifier.
+//
+// Restates loop 2 of RangeProof::verify (/root/reference/src/range_proof.rs:856-1033) as three data-parallel stages:
+//   A  k_vprep_proof    one thread per proof: batch inversion, challenge powers, d_sum / y_sum, the dynamic MSM scalars
+//                       (A1, B, A, L_j, R_j, V_j), the proof's h / g_k contributions, optional mask recovery (:941-969)
+//   B  k_vprep_vector   one thread per (proof, i): contributions to gi_base_scalars[i] / hi_base_scalars[i] (:987-1003);
+//                       s[i] is evaluated directly as prod_j e_j^(+-1) instead of the reference's serial recurrence
+//   C  k_vprep_reduce   one thread per (chunk, static slot): column sums over the chunk's proofs (the `+=` of :999-1000,
+//                       :1017-1020), written as canonical scalars into the chunk's MSM entry list
+// All arithmetic is mod l in Montgomery form (arith.cuh sc_montmul); results are bit-exact canonical scalars.
+#include "kernels.cuh"
+
+namespace bpp {
+
+static __device__ __forceinline__ sc ld_sc(const uint32_t *p) {
+    sc r;
+    uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+static __device__ __forceinline__ void st_sc(uint32_t *p, const sc &r) {
+    reinterpret_cast<uint4 *>(p)[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    reinterpret_cast<uint4 *>(p)[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+static __device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_montmul(a, b); }
+static __device__ __forceinline__ sc ld_mont(const uint32_t *p) { return sc_to_mont(ld_sc(p)); }
+
+// pervec layout (scalars, Montgomery form), per proof at pv_off:
+//   [0] w*r1*e  [1] w*s1*e  [2] w*e^2  [3] w*e^2*z  [4] y^N  [5..7] spare
+//   [8 + j]            e_j            j < rounds
+//   [8 + R + j]        e_j^-1
+//   [8 + 2R + k]       y^-(2^k)       k < rounds
+//   [8 + 3R + j]       z^(2(j+1))     j < m
+#define PV_HDR 8
+
+__global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.n_proofs) return;
+    const VProof pr = b.proofs[p];
+    if (!pr.active && pr.nonce_off == 0xffffffffu) return;
+    const uint32_t R = pr.rounds, m = pr.m, ext = d.ext;
+    const sc one_m = sc_const_R();                 // 1 in Montgomery form
+    const uint32_t *ch = b.challenges + 8 * (size_t)pr.ch_off;
+    sc y = ld_mont(ch), z = ld_mont(ch + 8), e = ld_mont(ch + 16);
+    sc w = ld_mont(b.weights + 8 * (size_t)p);
+    const uint32_t *ps = b.proof_scalars + 8 * (size_t)pr.sc_off;
+    sc r1 = ld_mont(ps), s1 = ld_mont(ps + 8);
+
+    sc z2 = mm(z, z), e2 = mm(e, e);
+    sc yN = y;
+    for (uint32_t k = 0; k < R; k++) yN = mm(yN, yN);       // N = 2^rounds (checked on the host)
+    sc yN1 = mm(yN, y);
+    sc ym1 = sc_sub(y, one_m);
+    sc zy = mm(z2, yN1);
+
+    // batch inversion of [e_0..e_{R-1}, y, y-1, e, z^2*y^(N+1)]  (range_proof.rs:897-905 plus the two inversions of :950,:958)
+    sc ej[BPP_MAX_ROUNDS], pre[BPP_MAX_ROUNDS + 4];
+    sc acc = one_m;
+    for (uint32_t j = 0; j < R; j++) { ej[j] = ld_mont(ch + 24 + 8 * j); pre[j] = acc; acc = mm(acc, ej[j]); }
+    pre[R] = acc; acc = mm(acc, y);
+    pre[R + 1] = acc; acc = mm(acc, ym1);
+    pre[R + 2] = acc; acc = mm(acc, e);
+    pre[R + 3] = acc; acc = mm(acc, zy);
+    sc inv = scm_invert(acc);
+    sc zy_inv = mm(inv, pre[R + 3]); inv = mm(inv, zy);
+    sc e_inv = mm(inv, pre[R + 2]); inv = mm(inv, e);
+    sc ym1_inv = mm(inv, pre[R + 1]); inv = mm(inv, ym1);
+    sc y_inv = mm(inv, pre[R]); inv = mm(inv, y);
+    sc ejinv[BPP_MAX_ROUNDS];
+    for (int j = (int)R - 1; j >= 0; j--) { ejinv[j] = mm(inv, pre[j]); inv = mm(inv, ej[j]); }
+
+    // mask recovery (range_proof.rs:941-969)
+    if (pr.nonce_off != 0xffffffffu && b.masks) {
+        const uint32_t *nn = b.nonces + 8 * (size_t)pr.nonce_off;
+        sc e2inv = mm(e_inv, e_inv);
+        for (uint32_t k = 0; k < ext; k++) {
+            sc d1k = ld_mont(ps + 16 + 8 * k);
+            sc eta = ld_mont(nn + 8 * k), dk = ld_mont(nn + 8 * (ext + k)), alpha = ld_mont(nn + 8 * (2 * ext + k));
+            sc mask = sc_sub(sc_sub(d1k, eta), mm(e, dk));
+            mask = sc_sub(mm(mask, e2inv), alpha);
+            for (uint32_t j = 0; j < R; j++) {
+                sc dL = ld_mont(nn + 8 * (3 * ext + j * ext + k));
+                sc dR = ld_mont(nn + 8 * (3 * ext + R * ext + j * ext + k));
+                mask = sc_sub(mask, mm(mm(ej[j], ej[j]), dL));
+                mask = sc_sub(mask, mm(mm(ejinv[j], ejinv[j]), dR));
+            }
+            mask = mm(mask, zy_inv);
+            st_sc(b.masks + 8 * ((size_t)p * ext + k), sc_from_mont(mask));
+        }
+    }
+    if (!pr.active) return;
+
+    // y_sum = y*(y^N - 1)/(y - 1);  d_sum = (2^n - 1) * sum_{j=1..m} z^(2j) by log-doubling (range_proof.rs:908-938)
+    sc y_sum = mm(mm(sc_sub(yN, one_m), y), ym1_inv);
+    sc d_sum = z2, tz = z2;
+    for (uint32_t mmv = m; mmv > 1; mmv >>= 1) { d_sum = sc_add(d_sum, mm(d_sum, tz)); tz = mm(tz, tz); }
+    uint64_t two_n_m1 = d.bit_length >= 64 ? ~0ull : ((1ull << d.bit_length) - 1ull);
+    d_sum = mm(d_sum, sc_to_mont(sc_from_u64(two_n_m1)));
+
+    sc we2 = mm(w, e2);
+    sc neg_we2 = sc_neg(we2);
+    uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;
+    // dynamic entries of this proof: [A1, B, A, L_0.., R_0.., V_0..]
+    st_sc(out, sc_from_mont(sc_neg(mm(w, e))));
+    st_sc(out + 8, sc_from_mont(sc_neg(w)));
+    st_sc(out + 16, sc_from_mont(neg_we2));
+    for (uint32_t j = 0; j < R; j++) {
+        st_sc(out + 8 * (3 + j), sc_from_mont(mm(neg_we2, mm(ej[j], ej[j]))));
+        st_sc(out + 8 * (3 + R + j), sc_from_mont(mm(neg_we2, mm(ejinv[j], ejinv[j]))));
+    }
+    uint32_t *pv = b.pervec + 8 * (size_t)pr.pv_off;
+    sc h = sc_zero();
+    sc zpow = one_m;
+    sc neg_we2_yN1 = mm(neg_we2, yN1);
+    for (uint32_t j = 0; j < m; j++) {
+        zpow = mm(zpow, z2);
+        st_sc(pv + 8 * (PV_HDR + 3 * R + j), zpow);
+        sc weighted = mm(neg_we2_yN1, zpow);
+        st_sc(out + 8 * (3 + 2 * R + j), sc_from_mont(weighted));
+        if (b.min_present[pr.commit_off + j]) {
+            sc mv = sc_to_mont(sc_from_u64(b.min_values[pr.commit_off + j]));
+            h = sc_sub(h, mm(weighted, mv));
+        }
+    }
+    // h += w*(r1*y*s1 + e^2*(y^(N+1)*z*d_sum + (z^2 - z)*y_sum)); g_k += w*d1[k]   (range_proof.rs:1017-1020)
+    sc t = mm(mm(r1, y), s1);
+    sc u = sc_add(mm(mm(yN1, z), d_sum), mm(sc_sub(z2, z), y_sum));
+    h = sc_add(h, mm(w, sc_add(t, mm(e2, u))));
+    uint32_t *hg = b.hg_contrib + 8 * (size_t)p * (1 + ext);
+    st_sc(hg, h);
+    for (uint32_t k = 0; k < ext; k++) st_sc(hg + 8 * (1 + k), mm(w, ld_mont(ps + 16 + 8 * k)));
+
+    // hand-off to stage B
+    sc we = mm(w, e);
+    st_sc(pv, mm(we, r1));
+    st_sc(pv + 8, mm(we, s1));
+    st_sc(pv + 16, we2);
+    st_sc(pv + 24, mm(we2, z));
+    st_sc(pv + 32, yN);
+    sc yp = y_inv;
+    for (uint32_t j = 0; j < R; j++) {
+        st_sc(pv + 8 * (PV_HDR + j), ej[j]);
+        st_sc(pv + 8 * (PV_HDR + R + j), ejinv[j]);
+        st_sc(pv + 8 * (PV_HDR + 2 * R + j), yp);
+        yp = mm(yp, yp);
+    }
+}
+
+// thread -> (proof, i) through vec_offsets (prefix sums of N over active proofs)
+__global__ void __launch_bounds__(128) k_vprep_vector(VDims d, VBuffers b, uint32_t total) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    // binary search the owning proof
+    uint32_t lo = 0, hi = d.n_proofs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (b.vec_offsets[mid] <= gid) lo = mid; else hi = mid;
+    }
+    const uint32_t p = lo, i = gid - b.vec_offsets[p];
+    const VProof pr = b.proofs[p];
+    const uint32_t R = pr.rounds, N = 1u << R;
+    const uint32_t *pv = b.pervec + 8 * (size_t)pr.pv_off;
+    const sc one_m = sc_const_R();
+    // s[i] = prod_j (bit_{R-1-j}(i) ? e_j : e_j^-1);  s[N-1-i] = its inverse pattern;  y^-i from the y^-(2^k) table
+    sc s_i = one_m, s_rev = one_m, yinv_i = one_m;
+    bool first_y = true;
+    for (uint32_t j = 0; j < R; j++) {
+        bool bit = (i >> (R - 1 - j)) & 1u;
+        sc ejv = ld_sc(pv + 8 * (PV_HDR + j)), eji = ld_sc(pv + 8 * (PV_HDR + R + j));
+        if (j == 0) { s_i = bit ? ejv : eji; s_rev = bit ? eji : ejv; }
+        else { s_i = mm(s_i, bit ? ejv : eji); s_rev = mm(s_rev, bit ? eji : ejv); }
+        if ((i >> j) & 1u) {
+            sc yk = ld_sc(pv + 8 * (PV_HDR + 2 * R + j));
+            yinv_i = first_y ? yk : mm(yinv_i, yk);
+            first_y = false;
+        }
+    }
+    sc wre = ld_sc(pv), wse = ld_sc(pv + 8), we2 = ld_sc(pv + 16), we2z = ld_sc(pv + 24), yN = ld_sc(pv + 32);
+    // gi: w*(r1*e*y^-i*s[i] + e^2*z)
+    sc g = sc_add(mm(mm(wre, yinv_i), s_i), we2z);
+    // hi: w*(s1*e*s[N-1-i] - e^2*(d[i]*y^(N-i) + z)),  d[i] = z^(2(j+1)) * 2^bit
+    uint32_t party = i / d.bit_length, bitpos = i % d.bit_length;
+    sc zp = ld_sc(pv + 8 * (PV_HDR + 3 * R + party));
+    sc two_b = sc_zero();
+    two_b.v[bitpos >> 5] = 1u << (bitpos & 31);
+    sc di = mm(zp, sc_to_mont(two_b));
+    sc hterm = mm(mm(mm(di, yN), yinv_i), we2);
+    sc h = sc_sub(sc_sub(mm(wse, s_rev), hterm), we2z);
+    uint32_t *c = b.contrib + 8 * (size_t)pr.contrib_off;
+    st_sc(c + 8 * (size_t)i, g);
+    st_sc(c + 8 * ((size_t)N + i), h);
+}
+
+// one thread per (chunk, static slot): slot in [0, 2*max_mn + ext + 1)
+__global__ void __launch_bounds__(128) k_vprep_reduce(VDims d, VBuffers b) {
+    uint32_t c = blockIdx.y;
+    const VChunk chk = b.chunks[c];
+    if (!chk.active) return;
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_static = 2 * chk.max_mn + d.ext + 1;
+    if (slot >= n_static) return;
+    sc acc = sc_zero();
+    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++) {
+        const VProof pr = b.proofs[p];
+        if (!pr.active) continue;
+        uint32_t N = 1u << pr.rounds;
+        const uint32_t *src = nullptr;
+        if (slot < chk.max_mn) { if (slot < N) src = b.contrib + 8 * ((size_t)pr.contrib_off + slot); }
+        else if (slot < 2 * chk.max_mn) { uint32_t i = slot - chk.max_mn; if (i < N) src = b.contrib + 8 * ((size_t)pr.contrib_off + N + i); }
+        else if (slot < 2 * chk.max_mn + d.ext) src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext) + 1 + (slot - 2 * chk.max_mn));
+        else src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext));
+        if (src) acc = sc_add(acc, ld_sc(src));
+    }
+    st_sc(b.msm_scalars + 8 * ((size_t)chk.entry_off + slot), sc_from_mont(acc));
+}
+
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches) {
+    if (d.n_proofs == 0) return;
+    k_vprep_proof<<<(d.n_proofs + 63) / 64, 64, 0, s>>>(d, b);
+    if (launches) (*launches)++;
+    if (d.action == 0 /* RecoverOnly */) return;
+    if (total_vec) {
+        k_vprep_vector<<<(total_vec + 127) / 128, 128, 0, s>>>(d, b, total_vec);
+        if (launches) (*launches)++;
+    }
+    if (max_static) {
+        dim3 grid((max_static + 127) / 128, d.n_chunks);
+        k_vprep_reduce<<<grid, 128, 0, s>>>(d, b);
+        if (launches) (*launches)++;
+    }
+}
+
+} // namespace bpp

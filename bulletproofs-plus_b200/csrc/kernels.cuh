@@ -34,40 +34,41 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
                 const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches);
 
 // ---------------------------------------------------------------- k_verify.cu
+#define BPP_MAX_ROUNDS 24  // log2(n * m) <= 24 (generator sets are capped at 2^24 points)
 struct VProof {            // per-proof metadata, device-resident
-    uint32_t chunk;        // reference call this proof belongs to
     uint32_t m;            // aggregation factor (commitments)
     uint32_t rounds;       // log2(n * m)
-    uint32_t pt_off;       // first dynamic point: [A, A1, B, L.., R.., V..]
-    uint32_t sc_off;       // first proof scalar: [r1, s1, d1..]
-    uint32_t ch_off;       // first challenge: [y, z, e, e_1..e_r]
-    uint32_t entry_off;    // first MSM entry of this proof's dynamic terms
+    uint32_t sc_off;       // first proof scalar (in scalars): [r1, s1, d1..]
+    uint32_t ch_off;       // first challenge: [y, z, e, e_0..e_{r-1}]
+    uint32_t entry_off;    // first dynamic MSM entry of this proof: [A1, B, A, L.., R.., V..]
     uint32_t commit_off;   // first commitment (min_values / min_present index)
-    uint32_t nonce_off;    // first nonce: [eta_k, d_k, alpha_k (ext each), dL_jk, dR_jk (rounds*ext each)] or 0xffffffff
-    uint32_t contrib_off;  // first slot in the gi/hi contribution array (2 * n*m scalars)
+    uint32_t nonce_off;    // first nonce: [eta_k, d_k, alpha_k (ext each), dL_jk, dR_jk (rounds*ext each, j-major)] or 0xffffffff
+    uint32_t contrib_off;  // first slot in the gi/hi contribution array: [gi(N) | hi(N)]
+    uint32_t pv_off;       // first slot of the stage A -> B hand-off vector (8 + 3*rounds + m scalars)
+    uint32_t active;       // 1 = contributes to its chunk's MSM
 };
 struct VChunk {
     uint32_t proof_lo, proof_hi;
     uint32_t max_mn;       // largest n*m in the chunk
     uint32_t entry_off;    // first MSM entry of the chunk: [Gi(max_mn) | Hi(max_mn) | G(ext) | H | dynamic...]
+    uint32_t active;
 };
-struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext, gens_nm; int action; };
+struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext; int action; };
 struct VBuffers {
     const VProof *proofs; const VChunk *chunks;
+    const uint32_t *vec_offsets;     // n_proofs + 1: prefix sums of N over active proofs
     const uint32_t *proof_scalars;   // words
     const uint32_t *challenges;      // words
     const uint32_t *weights;         // n_proofs x 8 words
     const uint64_t *min_values; const uint8_t *min_present;
     const uint32_t *nonces;          // words, may be null
     uint32_t *msm_scalars;           // out: n_entries x 8 words
-    uint32_t *msm_seg;               // out: per-entry chunk id
-    uint32_t *msm_pidx;              // out: per-entry point index
     uint32_t *contrib;               // scratch: gi/hi contributions (Montgomery form)
     uint32_t *hg_contrib;            // scratch: per proof (1 + ext) scalars (Montgomery form): h, g_k
-    uint32_t *pervec;                // scratch: per proof 16 scalars handed from stage A to stage B
+    uint32_t *pervec;                // scratch: stage A -> B hand-off
     uint32_t *masks;                 // out: n_proofs x ext x 8 words (plain), may be null
 };
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint64_t *launches);
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches);
 
 // ---------------------------------------------------------------- k_bench.cu
 // returns elapsed seconds for `iters` dependent ops in each of `threads_total` lanes; ops counted by caller

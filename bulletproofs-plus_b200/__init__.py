@@ -59,6 +59,25 @@ class Engine:
     def sync(self):
         _chk(self, _ffi.lib().bpp_ctx_sync(self.h))
 
+    def timer_start(self):
+        _chk(self, _ffi.lib().bpp_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        """milliseconds between timer_start and now on the engine's stream (CUDA events)"""
+        ms = C.c_float()
+        _chk(self, _ffi.lib().bpp_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def phase_timing(self, enable):
+        _chk(self, _ffi.lib().bpp_ctx_phase_timing(self.h, 1 if enable else 0))
+
+    PHASES = ("decompress", "vprep", "msm_sort", "msm_bucket", "msm_reduce", "msm_combine", "encode")
+
+    def phase_ms(self):
+        arr = (C.c_float * 7)()
+        _chk(self, _ffi.lib().bpp_ctx_phase_ms(self.h, arr))
+        return dict(zip(self.PHASES, [float(x) for x in arr]))
+
     def set_host_threads(self, n):
         _chk(self, _ffi.lib().bpp_ctx_set_host_threads(self.h, n))
 

@@ -58,6 +58,8 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->d_in, &ctx->d_in2, &ctx->d_tab, &ctx->d_flags, &ctx->d_out, &ctx->d_scratch, &ctx->d_res, &ctx->d_misc}) b->release();
     ctx->h_stage.release(); ctx->h_stage2.release();
+    if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
+    for (int i = 0; i < 8; i++) if (ctx->ph[i]) cudaEventDestroy(ctx->ph[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -69,6 +71,44 @@ int32_t bpp_ctx_sync(bpp_ctx *ctx) {
 }
 uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void *bpp_ctx_stream(bpp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int32_t bpp_ctx_timer_start(bpp_ctx *ctx) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (!ctx->t0) { BPP_CUDA(ctx, cudaEventCreate(&ctx->t0)); BPP_CUDA(ctx, cudaEventCreate(&ctx->t1)); }
+    BPP_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    return BPP_OK;
+}
+int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms) {
+    if (!ctx || !ms || !ctx->t0) return BPP_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    BPP_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+    BPP_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+    BPP_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return BPP_OK;
+}
+int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (enable)
+        for (int i = 0; i < 8; i++)
+            if (!ctx->ph[i]) BPP_CUDA(ctx, cudaEventCreate(&ctx->ph[i]));
+    ctx->phase_timing = enable != 0;
+    ctx->clear_marks();
+    return BPP_OK;
+}
+// ms7[i] = time between mark i and mark i+1 of the last vbatch / plan run (0 where a mark was not reached):
+// 0 decompress, 1 verifier scalar prep, 2 MSM sort (digits+scan+scatter), 3 MSM bucket sums, 4 MSM window reduction,
+// 5 MSM Horner combine, 6 encode / identity test
+int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms7) {
+    if (!ctx || !ms7) return BPP_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 7; i++) {
+        ms7[i] = 0.f;
+        if (ctx->ph_set[i] && ctx->ph_set[i + 1]) BPP_CUDA(ctx, cudaEventElapsedTime(&ms7[i], ctx->ph[i], ctx->ph[i + 1]));
+    }
+    return BPP_OK;
+}
 int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n) {
     if (!ctx || n < 1) return BPP_INVALID_ARGUMENT;
     ctx->host_threads = n;
@@ -218,11 +258,15 @@ int32_t bpp_msm_plan_run(bpp_msm_plan *pl, uint8_t *out32_or_null) {
     bpp_ctx *ctx = pl->ctx;
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
+    ctx->clear_marks();
+    ctx->mark(2);
     launch_msm(st, pl->sh, pl->d_scalars.as<uint32_t>(), nullptr, nullptr, pl->d_tab.as<aniels>(), nullptr, pl->d_scratch.p,
-               pl->d_res.as<ge>(), &ctx->launches);
+               pl->d_res.as<ge>(), &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
+    if (ctx->phase_timing) for (int i = 3; i <= 6; i++) ctx->ph_set[i] = true;
     BPP_CUDA(ctx, cudaGetLastError());
     if (out32_or_null) {
         launch_encode(st, 1, pl->d_res.as<ge>(), pl->d_out.as<uint32_t>(), nullptr);
+        ctx->mark(7);
         ctx->launches++;
         BPP_CUDA(ctx, cudaMemcpyAsync(out32_or_null, pl->d_out.p, 32, cudaMemcpyDeviceToHost, st));
         BPP_CUDA(ctx, cudaStreamSynchronize(st));

@@ -49,6 +49,13 @@ struct bpp_ctx {
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
+    // measurement: wall timer and per-phase marks on `stream` (bench.py)
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool phase_timing = false;
+    cudaEvent_t ph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ph_set[8] = {false, false, false, false, false, false, false, false};
+    void mark(int i) { if (phase_timing && ph[i]) { cudaEventRecord(ph[i], stream); ph_set[i] = true; } }
+    void clear_marks() { for (int i = 0; i < 8; i++) ph_set[i] = false; }
     // reusable scratch for the one-shot entry points
     bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc;
     bpp::PinBuf h_stage, h_stage2;

@@ -423,10 +423,13 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     cudaStream_t st = ctx->stream;
     const int ext = g->ext;
     // ---- device: decompress -> prep -> MSM -> identity flags
+    ctx->clear_marks();
+    ctx->mark(0);
     if (vb->n_pts) {
         launch_decompress(st, vb->n_pts, vb->d_enc.as<uint32_t>(), vb->d_tab.as<aniels>(), vb->d_ok.as<uint8_t>(), nullptr, nullptr);
         ctx->launches++;
     }
+    ctx->mark(1);
     VDims d;
     d.n_proofs = (uint32_t)vb->n_proofs; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)ext;
     d.action = vb->action;
@@ -437,10 +440,14 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     b.msm_scalars = vb->d_mscal.as<uint32_t>(); b.contrib = vb->d_contrib.as<uint32_t>(); b.hg_contrib = vb->d_hg.as<uint32_t>();
     b.pervec = vb->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? vb->d_masks.as<uint32_t>() : nullptr;
     if (vb->any_msm || vb->any_masks) launch_verify_prep(st, d, b, vb->total_vec, vb->any_msm ? vb->max_static : 0, &ctx->launches);
+    ctx->mark(2);
     if (vb->any_msm) {
         launch_msm(st, vb->shape, vb->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->d_segoff.as<uint32_t>() : nullptr, vb->d_pidx.as<uint32_t>(),
-                   vb->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->d_scratch.p, vb->d_res.as<ge>(), &ctx->launches);
+                   vb->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->d_scratch.p, vb->d_res.as<ge>(), &ctx->launches,
+                   ctx->phase_timing ? &ctx->ph[3] : nullptr);
+        if (ctx->phase_timing) for (int i = 3; i <= 6; i++) ctx->ph_set[i] = true;
         launch_encode(st, vb->n_chunks, vb->d_res.as<ge>(), nullptr, vb->d_ident.as<uint8_t>());
+        ctx->mark(7);
         ctx->launches++;
         BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_ident.p, vb->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
     }

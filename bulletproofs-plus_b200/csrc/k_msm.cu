@@ -290,7 +290,7 @@ __global__ void k_msm_combine(uint32_t n_seg, int c, int W, const ge *__restrict
 
 // ------------------------------------------------------------------------------------------------ driver
 void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_offsets, const uint32_t *pidx,
-                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches) {
+                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches, cudaEvent_t *marks) {
     MsmScratch sc = msm_carve(sh, scratch);
     size_t n_keys = (size_t)sh.n_seg * sh.W * sh.B;
     uint32_t n_tiles = (uint32_t)((n_keys + SCAN_TILE - 1) / SCAN_TILE);
@@ -305,12 +305,16 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     if (sh.n_entries) {
         k_msm_digits<true><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.cursor, sc.sorted);
     }
+    if (marks) cudaEventRecord(marks[0], s);
     k_msm_bucket<<<(uint32_t)((n_keys + 127) / 128), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, sc.buckets);
+    if (marks) cudaEventRecord(marks[1], s);
     uint32_t T = sh.B >= 8 ? sh.B / 8 : 1;
     if (T > 1024) T = 1024;
     uint32_t L = sh.B / T;
     k_msm_reduce<<<sh.n_seg * sh.W, (T + 31u) / 32u * 32u, 0, s>>>(sh.B, L, T, sc.buckets, sc.windows);
+    if (marks) cudaEventRecord(marks[2], s);
     k_msm_combine<<<(sh.n_seg + 31) / 32, 32, 0, s>>>(sh.n_seg, sh.c, sh.W, sc.windows, result);
+    if (marks) cudaEventRecord(marks[3], s);
     if (launches) *launches += 6 + (sh.n_entries ? 2 : 0);
 }
 

@@ -31,7 +31,8 @@ size_t msm_scratch_bytes(const MsmShape &sh);
 // pidx: per-entry index into `dyn` (bit 31 clear) or `gens` (bit 31 set); nullptr = identity mapping into dyn.
 // result: n_seg extended points.
 void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_offsets, const uint32_t *pidx,
-                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches);
+                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches, cudaEvent_t *marks = nullptr);
+// marks (optional, 4 events): recorded after the sort phase (digits+scan+scatter), bucket sums, window reduction, Horner
 
 // ---------------------------------------------------------------- k_verify.cu
 #define BPP_MAX_ROUNDS 24  // log2(n * m) <= 24 (generator sets are capped at 2^24 points)

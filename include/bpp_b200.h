@@ -57,6 +57,13 @@ int32_t bpp_ctx_sync(bpp_ctx *ctx);
 /* number of engine kernels launched on this ctx since creation (bench.py's gpu_launches) */
 uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx);
 void *bpp_ctx_stream(bpp_ctx *ctx);                   /* cudaStream_t, for event timing by the caller */
+/* CUDA-event timing on the ctx stream: start records an event; stop records one, waits for it, returns milliseconds */
+int32_t bpp_ctx_timer_start(bpp_ctx *ctx);
+int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms);
+/* per-phase device times of the last bpp_vbatch_run / bpp_msm_plan_run (events between the kernels, when enabled):
+ * ms7 = {decompress, verifier scalar prep, MSM sort, MSM bucket sums, MSM window reduction, MSM Horner, encode/identity} */
+int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable);
+int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms7);
 /* host threads used for the Fiat-Shamir replay of bpp_verify_chunks (default: min(64, hardware threads); the
  * reference is single-threaded, the harness supplies parallelism -- see BASELINE.md) */
 int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);

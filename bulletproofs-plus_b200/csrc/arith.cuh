@@ -116,8 +116,45 @@ BPP_HD void mul256_portable(uint32_t t[16], const uint32_t a[8], const uint32_t 
     }
 }
 
+// t[0..16) = a^2: the 28 off-diagonal products once, doubled, plus the 8 diagonal squares (36 multiplies instead of 64)
+BPP_HD void sq256_any(uint32_t t[16], const uint32_t a[8]) {
+    uint32_t u[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) u[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = i + 1; j < 8; j++) {
+            c += (uint64_t)a[i] * a[j] + u[i + j];
+            u[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        u[i + 8] = (uint32_t)c;
+    }
+    uint64_t c = 0;
+    uint32_t carry_bit = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] * a[i];
+        uint32_t lo2 = (u[2 * i] << 1) | carry_bit;
+        carry_bit = u[2 * i] >> 31;
+        uint32_t hi2 = (u[2 * i + 1] << 1) | carry_bit;
+        carry_bit = u[2 * i + 1] >> 31;
+        c += (uint64_t)lo2 + (uint32_t)d;
+        t[2 * i] = (uint32_t)c;
+        c >>= 32;
+        c += (uint64_t)hi2 + (uint32_t)(d >> 32);
+        t[2 * i + 1] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+
+// The compiler's schedule of the portable schoolbook (IMAD.WIDE.U32 + IADD3.X chains) measured 6 % faster on B200
+// than the hand-chained mad.cc version (profiles/r01_microbench_int_pipe.txt: 81.5 vs 76.5 G mul/s), so the PTX core is
+// opt-in (BPP_PTX_MUL) and kept for the microbenchmark comparison.
 BPP_HD void mul256_any(uint32_t t[16], const uint32_t a[8], const uint32_t b[8]) {
-#if BPP_PTX
+#if BPP_PTX && defined(BPP_PTX_MUL)
     ptx::mul256(t, a, b);
 #else
     mul256_portable(t, a, b);
@@ -228,15 +265,17 @@ BPP_HD fe fe_reduce512(const uint32_t t[16]) {
     return r;
 }
 
-BPP_MULFN fe fe_mul(const fe &a, const fe &b) {
+// NB by-value parameters: through a __noinline__ call the CUDA ABI then keeps both operands and the result in
+// registers (a `const fe &` parameter forces the caller to spill them to local memory first).
+BPP_MULFN fe fe_mul(fe a, fe b) {
     uint32_t t[16];
     mul256_any(t, a.v, b.v);
     return fe_reduce512(t);
 }
 
-BPP_MULFN fe fe_sq(const fe &a) {
+BPP_MULFN fe fe_sq(fe a) {
     uint32_t t[16];
-    mul256_any(t, a.v, a.v);
+    sq256_any(t, a.v);
     return fe_reduce512(t);
 }
 
@@ -434,7 +473,7 @@ BPP_HD sc sc_sub(const sc &a, const sc &b) {
 BPP_HD sc sc_neg(const sc &a) { return sc_sub(sc_zero(), a); }
 
 // Montgomery product a*b*2^-256 mod l; needs a*b < l*2^256; result canonical
-BPP_MULFN sc sc_montmul(const sc &a, const sc &b) {
+BPP_MULFN sc sc_montmul(sc a, sc b) {
     uint32_t t[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) t[i] = 0;

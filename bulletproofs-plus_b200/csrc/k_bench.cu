@@ -42,9 +42,13 @@ template <int WHICH> __global__ void __launch_bounds__(MB_THREADS) k_mb_instr(in
     if (acc == 0x12345678u) sink[0] = acc;
 }
 
-static __device__ __noinline__ fe fe_mul_portable(const fe &a, const fe &b) {
+static __device__ __noinline__ fe fe_mul_portable(fe a, fe b) {   // which == 9: the hand-chained mad.cc PTX core
     uint32_t t[16];
+#if BPP_PTX
+    ptx::mul256(t, a.v, b.v);
+#else
     mul256_portable(t, a.v, b.v);
+#endif
     return fe_reduce512(t);
 }
 

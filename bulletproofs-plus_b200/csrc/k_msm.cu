@@ -38,10 +38,11 @@ static __device__ __forceinline__ ge ld_ge(const ge *p) {
 static __device__ __forceinline__ void st_ge(ge *p, const ge &r) {
     st8(p->X.v, r.X.v); st8(p->Y.v, r.Y.v); st8(p->Z.v, r.Z.v); st8(p->T.v, r.T.v);
 }
-static __device__ __noinline__ ge ge_add_nl(const ge &a, const ge &b) { return ge_add(a, b); }
-static __device__ __noinline__ ge ge_dbl_nl(const ge &a) { return ge_dbl(a); }
-static __device__ __noinline__ ge ge_madd_nl(const ge &a, const aniels &b) { return ge_madd(a, b); }
-static __device__ __noinline__ ge ge_msub_nl(const ge &a, const aniels &b) { return ge_msub(a, b); }
+// by-value so that operands and result travel in registers through the call (see arith.cuh fe_mul)
+static __device__ __noinline__ ge ge_add_nl(ge a, ge b) { return ge_add(a, b); }
+static __device__ __noinline__ ge ge_dbl_nl(ge a) { return ge_dbl(a); }
+static __device__ __noinline__ ge ge_madd_nl(ge a, aniels b) { return ge_madd(a, b); }
+static __device__ __noinline__ ge ge_msub_nl(ge a, aniels b) { return ge_msub(a, b); }
 
 static __device__ __forceinline__ ge shfl_down_ge(const ge &p, int delta) {
     ge r;
@@ -85,7 +86,7 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
         double per = (double)n_entries / (double)sh.n_seg;
         double best = 1e300;
         for (int cc = 2; cc <= 16; cc++) {
-            int W = (254 + cc - 1) / cc;
+            int W = (252 + cc - 1) / cc;
             double cost = per * W + 2.5 * (double)(1u << (cc - 1)) * W;
             if (cost < best) { best = cost; c = cc; }
         }
@@ -93,7 +94,7 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     if (c < 2) c = 2;
     if (c > 16) c = 16;
     sh.c = c;
-    sh.W = (254 + c - 1) / c;
+    sh.W = (252 + c - 1) / c;    // scalars are recoded to |s| < 2^251 (see k_msm_digits)
     sh.B = 1u << (c - 1);
     return sh;
 }
@@ -136,13 +137,32 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t n_entries, uint32_t
     if (i >= n_entries) return;
     uint32_t s[8];
     ld8(s, scalars + 8 * (size_t)i);
+    // s > l/2  ->  use (l - s, -P): the recoded scalar is < 2^251, so with c*W >= 252 the top window never overflows and
+    // no half-empty carry-only window exists (which would put half of all entries into one bucket)
+    uint32_t sneg;
+    {
+        uint32_t t[8];
+        int64_t bw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { bw += (int64_t)sc_l(k) - (int64_t)s[k]; t[k] = (uint32_t)bw; bw >>= 32; }
+        bool gt = false, decided = false;      // s > t ?
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            if (!decided && s[k] != t[k]) { gt = s[k] > t[k]; decided = true; }
+        }
+        sneg = gt ? 1u : 0u;
+        if (gt) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = t[k];
+        }
+    }
     uint32_t seg = seg_of(seg_offsets, n_seg, i);
     uint32_t key_base = seg * (uint32_t)W * B;
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
         uint32_t d = bits_at(s, w * c, c) + carry;
-        uint32_t neg = 0;
-        if (d > B) { d = (2u * B) - d; neg = 1u; carry = 1u; } else carry = 0u;
+        uint32_t neg = sneg;
+        if (d > B) { d = (2u * B) - d; neg ^= 1u; carry = 1u; } else carry = 0u;
         if (d != 0) {
             uint32_t key = key_base + (uint32_t)w * B + (d - 1u);
             uint32_t pos = atomicAdd(&counters[key], 1u);
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(128) k_msm_bucket(uint32_t n_keys, const uint3
 // ------------------------------------------------------------------------------------------------ 5: window sums
 // block = T threads for one (seg, window); thread t owns buckets [t*L, (t+1)*L): S = sum, R = sum (j+1)*bucket[tL+j],
 // contributes R + (t*L)*S; the block sums the contributions.
-__global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uint32_t nthreads, const ge *__restrict__ buckets,
+__global__ void __launch_bounds__(256) k_msm_reduce(uint32_t B, uint32_t L, uint32_t nthreads, const ge *__restrict__ buckets,
                                                     ge *__restrict__ windows) {
     __shared__ ge warp_part[32];
     uint32_t t = threadIdx.x;      // blockDim.x is a multiple of 32; threads >= nthreads only take part in the shuffles
@@ -309,7 +329,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     k_msm_bucket<<<(uint32_t)((n_keys + 127) / 128), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
     uint32_t T = sh.B >= 8 ? sh.B / 8 : 1;
-    if (T > 1024) T = 1024;
+    if (T > 256) T = 256;
     uint32_t L = sh.B / T;
     k_msm_reduce<<<sh.n_seg * sh.W, (T + 31u) / 32u * 32u, 0, s>>>(sh.B, L, T, sc.buckets, sc.windows);
     if (marks) cudaEventRecord(marks[2], s);

@@ -21,7 +21,7 @@ struct MsmShape {
     uint32_t n_entries;   // (scalar, point) pairs over all segments
     uint32_t n_seg;       // independent MSMs
     int c;                // window bits
-    int W;                // windows = ceil(254 / c)
+    int W;                // windows = ceil(252 / c)
     uint32_t B;           // buckets per window = 2^(c-1)
 };
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c);

@@ -150,11 +150,10 @@ BPP_HD void sq256_any(uint32_t t[16], const uint32_t a[8]) {
     }
 }
 
-// The compiler's schedule of the portable schoolbook (IMAD.WIDE.U32 + IADD3.X chains) measured 6 % faster on B200
-// than the hand-chained mad.cc version (profiles/r01_microbench_int_pipe.txt: 81.5 vs 76.5 G mul/s), so the PTX core is
-// opt-in (BPP_PTX_MUL) and kept for the microbenchmark comparison.
+// Measured on B200 with by-value operands (gpurun r01b): hand-chained mad.cc core 104 G mul/s, compiler-scheduled
+// portable schoolbook 81 G mul/s -> the PTX core is the default; BPP_PORTABLE_MUL selects the other one.
 BPP_HD void mul256_any(uint32_t t[16], const uint32_t a[8], const uint32_t b[8]) {
-#if BPP_PTX && defined(BPP_PTX_MUL)
+#if BPP_PTX && !defined(BPP_PORTABLE_MUL)
     ptx::mul256(t, a, b);
 #else
     mul256_portable(t, a, b);
@@ -238,6 +237,79 @@ BPP_HD fe fe_sub(const fe &a, const fe &b) {
 }
 
 BPP_HD fe fe_neg(const fe &a) { return fe_sub(fe_zero(), a); }
+
+// ------------------------------------------------------------------------------------------------ lazy add / sub
+// "loose" values: any 256-bit integer (not necessarily < 2^255).  fe_mul / fe_sq accept loose operands (the 512-bit
+// product is reduced whatever its size) and return tight ones (< 2^255), so the additions between two multiplications of
+// the point formulas need no reduction at all:
+//   fe_add_l(tight, tight) -> loose      one 8-limb carry chain
+//   fe_sub_l(loose a, TIGHT b) -> loose  a - b; if that borrowed, the wrapped value is a - b + 2^256 = a - b + 38 (mod p) and
+//                                        is >= 2^256 - 2^255 > 38, so 38 is simply taken off again (two carry chains)
+//   fe_sub_ll(loose a, loose b) -> loose same, but b - a may exceed 2^256 - 38, so taking 38 off can wrap once more
+//                                        (three carry chains; the third cannot borrow)
+BPP_HD fe fe_add_l(const fe &a, const fe &b) {
+    fe r;
+#if BPP_PTX
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    r.v[7] = ptx::addc(a.v[7], b.v[7]);
+#else
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+#endif
+    return r;
+}
+BPP_HD fe fe_sub_l(const fe &a, const fe &b) {
+    fe r;
+#if BPP_PTX
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t bw = ptx::subc(0, 0);                 // 0 or 0xffffffff
+    r.v[0] = ptx::sub_cc(r.v[0], 38u & bw);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = ptx::subc_cc(r.v[i], 0);
+    r.v[7] = ptx::subc(r.v[7], 0);
+#else
+    int64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (int64_t)a.v[i] - (int64_t)b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    int64_t d = c < 0 ? -38 : 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { d += (int64_t)r.v[i]; r.v[i] = (uint32_t)d; d >>= 32; }
+#endif
+    return r;
+}
+BPP_HD fe fe_sub_ll(const fe &a, const fe &b) {
+    fe r;
+#if BPP_PTX
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t bw = ptx::subc(0, 0);
+    r.v[0] = ptx::sub_cc(r.v[0], 38u & bw);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = ptx::subc_cc(r.v[i], 0);
+    bw = ptx::subc(0, 0);
+    r.v[0] = ptx::sub_cc(r.v[0], 38u & bw);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = ptx::subc_cc(r.v[i], 0);
+    r.v[7] = ptx::subc(r.v[7], 0);
+#else
+    int64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (int64_t)a.v[i] - (int64_t)b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    for (int pass = 0; pass < 2; pass++) {
+        int64_t d = c < 0 ? -38 : 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { d += (int64_t)r.v[i]; r.v[i] = (uint32_t)d; d >>= 32; }
+        c = d;
+    }
+#endif
+    return r;
+}
 
 // 16-limb product -> fe:  lo + 38 * hi, then fold
 BPP_HD fe fe_reduce512(const uint32_t t[16]) {

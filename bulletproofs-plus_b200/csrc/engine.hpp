@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../include/bpp_b200.h"
 #include "kernels.cuh"
+#include "hostpool.hpp"
 
 namespace bpp {
 
@@ -49,6 +50,11 @@ struct bpp_ctx {
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
+    bpp::HostPool *pool = nullptr;      // lazily created with host_threads workers
+    bpp::HostPool &workers() {
+        if (!pool || pool->size() != host_threads) { delete pool; pool = new bpp::HostPool(host_threads); }
+        return *pool;
+    }
     // measurement: wall timer and per-phase marks on `stream` (bench.py)
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool phase_timing = false;
@@ -59,6 +65,7 @@ struct bpp_ctx {
     // reusable scratch for the one-shot entry points
     bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc;
     bpp::PinBuf h_stage, h_stage2;
+    std::vector<void *> vwork_pool;     // pooled verification workspaces (engine_verify.cu)
 };
 
 struct bpp_gens {
@@ -75,6 +82,7 @@ struct bpp_gens {
 };
 
 namespace bpp {
+void vwork_pool_free(bpp_ctx *ctx);
 int32_t fail(bpp_ctx *ctx, int32_t code, const char *what);
 int32_t cuda_fail(bpp_ctx *ctx, cudaError_t e, const char *where);
 #define BPP_CUDA(ctx, call)                                             \

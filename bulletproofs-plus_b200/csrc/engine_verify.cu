@@ -126,26 +126,18 @@ void nonce(const uint8_t seed[32], const char *label, bool have_j, uint32_t j, b
     host_sc_from_wide(h, out32);
 }
 
-template <class F> void parallel_for(size_t n, int threads, F f) {
-    if (n == 0) return;
-    size_t nt = std::min<size_t>((size_t)std::max(threads, 1), (n + 7) / 8);
-    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
-    std::atomic<size_t> next(0);
-    std::vector<std::thread> th;
-    auto body = [&]() {
-        for (;;) {
-            size_t i0 = next.fetch_add(8);
-            if (i0 >= n) break;
-            size_t i1 = std::min(n, i0 + 8);
-            for (size_t i = i0; i < i1; i++) f(i);
-        }
-    };
-    for (size_t t = 1; t < nt; t++) th.emplace_back(body);
-    body();
-    for (auto &x : th) x.join();
-}
-
 } // namespace
+
+// device + pinned buffers of one verification pass; pooled per ctx so that repeated calls do not pay cudaMalloc /
+// cudaMallocHost / cudaFree every time (grow-only, returned to the pool by bpp_vbatch_destroy)
+struct VWork {
+    DevBuf d_blob, d_tab, d_ok, d_mscal, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident;
+    PinBuf h_blob, h_out;
+    void release() {
+        for (DevBuf *b : {&d_blob, &d_tab, &d_ok, &d_mscal, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident}) b->release();
+        h_blob.release(); h_out.release();
+    }
+};
 
 struct bpp_vbatch {
     bpp_gens *g = nullptr;
@@ -157,16 +149,28 @@ struct bpp_vbatch {
     uint32_t n_pts = 0, n_entries = 0, total_vec = 0, max_static = 0;
     bool any_msm = false, any_masks = false;
     MsmShape shape;
-    DevBuf d_enc, d_tab, d_ok, d_proofs, d_chunks, d_vecoff, d_pscal, d_chal, d_weights, d_minv, d_minp, d_nonces, d_mscal, d_pidx,
-        d_segoff, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident;
-    PinBuf h_ok, h_ident, h_masks;
-    void release() {
-        for (DevBuf *b : {&d_enc, &d_tab, &d_ok, &d_proofs, &d_chunks, &d_vecoff, &d_pscal, &d_chal, &d_weights, &d_minv, &d_minp, &d_nonces,
-                          &d_mscal, &d_pidx, &d_segoff, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident})
-            b->release();
-        h_ok.release(); h_ident.release(); h_masks.release();
-    }
+    VWork *w = nullptr;
+    // all inputs travel as ONE pinned blob -> ONE H2D copy; these are the section offsets inside it
+    size_t o_enc = 0, o_proofs = 0, o_chunks = 0, o_vecoff = 0, o_pscal = 0, o_chal = 0, o_weights = 0, o_minv = 0, o_minp = 0,
+           o_nonces = 0, o_pidx = 0, o_segoff = 0, blob_bytes = 0;
+    size_t ho_ok = 0, ho_ident = 0, ho_masks = 0, hout_bytes = 0;
+    template <class T> T *dev(size_t off) const { return reinterpret_cast<T *>(w->d_blob.as<uint8_t>() + off); }
 };
+
+namespace bpp {
+void vwork_pool_free(bpp_ctx *ctx) {
+    for (void *p : ctx->vwork_pool) { VWork *w = (VWork *)p; w->release(); delete w; }
+    ctx->vwork_pool.clear();
+}
+}
+static VWork *vwork_acquire(bpp_ctx *ctx) {
+    if (!ctx->vwork_pool.empty()) { VWork *w = (VWork *)ctx->vwork_pool.back(); ctx->vwork_pool.pop_back(); return w; }
+    return new VWork();
+}
+static void vwork_return(bpp_ctx *ctx, VWork *w) {
+    if (ctx->vwork_pool.size() < 4) ctx->vwork_pool.push_back(w);
+    else { w->release(); delete w; }
+}
 
 extern "C" {
 
@@ -174,7 +178,7 @@ void bpp_vbatch_destroy(bpp_vbatch *vb) {
     if (!vb) return;
     cudaSetDevice(vb->g->ctx->device);
     cudaStreamSynchronize(vb->g->ctx->stream);
-    vb->release();
+    if (vb->w) vwork_return(vb->g->ctx, vb->w);
     delete vb;
 }
 
@@ -245,13 +249,13 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
 
     // ---- loop 1: transcript replay (parallel over proofs), then the sequential weight transcript per chunk
     for (size_t i : work) memcpy(vb->hp[i].tstate, a->transcripts + BPP_TRANSCRIPT_BYTES * i, BPP_TRANSCRIPT_BYTES);
-    parallel_for(work.size(), ctx->host_threads, [&](size_t k) {
+    ctx->workers().run(work.size(), 8, [&](size_t k) {
         size_t i = work[k];
         HProof &p = vb->hp[i];
         p.loop1_rc = replay_transcript(g, p, a->commitments32 + 32 * a->commit_offsets[i], a->min_values + a->commit_offsets[i],
                                        a->min_present + a->commit_offsets[i]);
     });
-    parallel_for(a->n_chunks, ctx->host_threads, [&](size_t c) {
+    ctx->workers().run(a->n_chunks, 1, [&](size_t c) {
         HChunk &hc = vb->hc[c];
         if (hc.pre_rc) return;
         size_t stop = hc.hi;
@@ -285,14 +289,11 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         hc.max_mn = max_mn;
     });
 
-    // ---- device layout
+    // ---- device layout, pass 1: sizes and offsets
+    const uint32_t GEN = 0x80000000u;
+    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, contrib = 0, pv = 0, max_static = 0, n_pscal = 0, n_chal = 0, n_nonce = 0;
     std::vector<VProof> dp(a->n_proofs);
     std::vector<VChunk> dc(a->n_chunks);
-    std::vector<uint32_t> vecoff(a->n_proofs + 1, 0), segoff(a->n_chunks + 1, 0);
-    std::vector<uint8_t> enc, pscal, chal, weights(32 * std::max<size_t>(a->n_proofs, 1)), nonces;
-    std::vector<uint32_t> pidx;
-    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, contrib = 0, pv = 0, max_static = 0;
-    const uint32_t GEN = 0x80000000u;
     for (size_t c = 0; c < a->n_chunks; c++) {
         HChunk &hc = vb->hc[c];
         VChunk &ch = dc[c];
@@ -301,15 +302,10 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         ch.active = msm ? 1 : 0;
         ch.entry_off = n_entries;
         hc.entry_off = n_entries;
-        segoff[c] = n_entries;
         if (msm) {
             vb->any_msm = true;
             uint32_t n_static = 2 * hc.max_mn + (uint32_t)ext + 1;
             max_static = std::max(max_static, n_static);
-            for (uint32_t i = 0; i < hc.max_mn; i++) pidx.push_back(GEN | i);
-            for (uint32_t i = 0; i < hc.max_mn; i++) pidx.push_back(GEN | (uint32_t)(g->nm + i));
-            for (int k = 0; k < ext; k++) pidx.push_back(GEN | (uint32_t)(2 * g->nm + k));
-            pidx.push_back(GEN | (uint32_t)(2 * g->nm + ext));
             n_entries += n_static;
         }
         for (size_t i = a->chunk_offsets[c]; i < a->chunk_offsets[c + 1]; i++) {
@@ -317,41 +313,18 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
             VProof &v = dp[i];
             memset(&v, 0, sizeof v);
             v.nonce_off = 0xffffffffu;
-            vecoff[i] = total_vec;
             if (i >= hc.hi || p.pre_rc || !p.bytes) continue;
             // point table slots (decompressed whatever the chunk's fate: the flags decide InvalidArgument precedence)
             p.pt_off = n_pts;
             p.n_pts = 3 + 2 * (uint32_t)p.rounds + p.m;
-            enc.insert(enc.end(), p.a(), p.a() + 96);
-            for (int j = 0; j < p.rounds; j++) enc.insert(enc.end(), p.li(j), p.li(j) + 32);
-            for (int j = 0; j < p.rounds; j++) enc.insert(enc.end(), p.ri(j), p.ri(j) + 32);
-            const uint8_t *cm = a->commitments32 + 32 * a->commit_offsets[i];
-            enc.insert(enc.end(), cm, cm + 32 * (size_t)p.m);
             n_pts += p.n_pts;
             if (!hc.computable) continue;
             v.m = p.m; v.rounds = (uint32_t)p.rounds;
             v.commit_off = (uint32_t)a->commit_offsets[i];
-            v.sc_off = (uint32_t)(pscal.size() / 32);
-            pscal.insert(pscal.end(), p.r1(), p.r1() + 64);
-            pscal.insert(pscal.end(), p.d1(), p.d1() + 32 * (size_t)ext);
-            v.ch_off = (uint32_t)(chal.size() / 32);
-            chal.insert(chal.end(), p.y, p.y + 32); chal.insert(chal.end(), p.z, p.z + 32); chal.insert(chal.end(), p.e, p.e + 32);
-            for (int j = 0; j < p.rounds; j++) chal.insert(chal.end(), p.ej[j], p.ej[j] + 32);
-            memcpy(&weights[32 * i], p.weight, 32);
+            v.sc_off = n_pscal; n_pscal += 2 + (uint32_t)ext;
+            v.ch_off = n_chal; n_chal += 3 + (uint32_t)p.rounds;
             if (want_masks && p.has_seed) {
-                v.nonce_off = (uint32_t)(nonces.size() / 32);
-                size_t base = nonces.size();
-                nonces.resize(base + 32 * (size_t)ext * (3 + 2 * (size_t)p.rounds));
-                uint8_t *nn = nonces.data() + base;
-                for (int k = 0; k < ext; k++) {
-                    nonce(p.seed, "eta", false, 0, true, (uint32_t)k, nn + 32 * k);
-                    nonce(p.seed, "d", false, 0, true, (uint32_t)k, nn + 32 * (ext + k));
-                    nonce(p.seed, "alpha", false, 0, true, (uint32_t)k, nn + 32 * (2 * ext + k));
-                    for (int j = 0; j < p.rounds; j++) {
-                        nonce(p.seed, "dL", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + j * ext + k));
-                        nonce(p.seed, "dR", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + p.rounds * ext + j * ext + k));
-                    }
-                }
+                v.nonce_off = n_nonce; n_nonce += (uint32_t)ext * (3 + 2 * (uint32_t)p.rounds);
                 vb->any_masks = true;
             }
             if (msm) {
@@ -360,57 +333,116 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
                 v.entry_off = n_entries;
                 v.contrib_off = contrib; contrib += 2 * N;
                 v.pv_off = pv; pv += 8 + 3 * (uint32_t)p.rounds + p.m;
-                total_vec += N;
-                uint32_t R = (uint32_t)p.rounds;
-                pidx.push_back(p.pt_off + 1); pidx.push_back(p.pt_off + 2); pidx.push_back(p.pt_off);
-                for (uint32_t j = 0; j < 2 * R + p.m; j++) pidx.push_back(p.pt_off + 3 + j);
-                n_entries += 3 + 2 * R + p.m;
+                n_entries += 3 + 2 * (uint32_t)p.rounds + p.m;
             }
         }
         hc.n_entries = n_entries - hc.entry_off;
     }
-    vecoff[a->n_proofs] = total_vec;
-    segoff[a->n_chunks] = n_entries;
-    vb->n_pts = n_pts; vb->n_entries = n_entries; vb->total_vec = total_vec; vb->max_static = max_static;
+    size_t n_commit = a->n_proofs ? a->commit_offsets[a->n_proofs] : 0;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    vb->o_enc = carve(32 * (size_t)n_pts);
+    vb->o_proofs = carve(sizeof(VProof) * a->n_proofs);
+    vb->o_chunks = carve(sizeof(VChunk) * a->n_chunks);
+    vb->o_vecoff = carve(4 * (a->n_proofs + 1));
+    vb->o_pscal = carve(32 * (size_t)n_pscal);
+    vb->o_chal = carve(32 * (size_t)n_chal);
+    vb->o_weights = carve(32 * a->n_proofs);
+    vb->o_minv = carve(8 * n_commit);
+    vb->o_minp = carve(n_commit);
+    vb->o_nonces = carve(32 * (size_t)n_nonce);
+    vb->o_pidx = carve(4 * (size_t)n_entries);
+    vb->o_segoff = carve(4 * (a->n_chunks + 1));
+    vb->blob_bytes = off;
+    vb->n_pts = n_pts; vb->n_entries = n_entries; vb->max_static = max_static;
     vb->shape = msm_shape(n_entries, (uint32_t)a->n_chunks, 0);
+    vb->ho_ok = 0;
+    vb->ho_ident = (n_pts + 255) & ~(size_t)255;
+    vb->ho_masks = vb->ho_ident + ((a->n_chunks + 255) & ~(size_t)255);
+    vb->hout_bytes = vb->ho_masks + 32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext;
 
-    // ---- upload
-    cudaStream_t st = ctx->stream;
-    auto up = [&](DevBuf &d, const void *src, size_t bytes) -> cudaError_t {
-        cudaError_t e = d.ensure(std::max<size_t>(bytes, 32));
-        if (e != cudaSuccess || bytes == 0) return e;
-        return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st);
-    };
-    size_t n_commit = a->commit_offsets ? a->commit_offsets[a->n_proofs] : 0;
+    // ---- buffers (pooled)
+    VWork *w = vwork_acquire(ctx);
+    vb->w = w;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    ok(up(vb->d_enc, enc.data(), enc.size()));
-    ok(up(vb->d_proofs, dp.data(), dp.size() * sizeof(VProof)));
-    ok(up(vb->d_chunks, dc.data(), dc.size() * sizeof(VChunk)));
-    ok(up(vb->d_vecoff, vecoff.data(), vecoff.size() * 4));
-    ok(up(vb->d_pscal, pscal.data(), pscal.size()));
-    ok(up(vb->d_chal, chal.data(), chal.size()));
-    ok(up(vb->d_weights, weights.data(), weights.size()));
-    ok(up(vb->d_minv, a->min_values, n_commit * 8));
-    ok(up(vb->d_minp, a->min_present, n_commit));
-    ok(up(vb->d_nonces, nonces.data(), nonces.size()));
-    ok(up(vb->d_pidx, pidx.data(), pidx.size() * 4));
-    ok(up(vb->d_segoff, segoff.data(), segoff.size() * 4));
-    ok(vb->d_tab.ensure(sizeof(aniels) * std::max<size_t>(n_pts, 1)));
-    ok(vb->d_ok.ensure(std::max<size_t>(n_pts, 1)));
-    ok(vb->d_mscal.ensure(32 * std::max<size_t>(n_entries, 1)));
-    ok(vb->d_contrib.ensure(32 * std::max<size_t>(contrib, 1)));
-    ok(vb->d_hg.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (1 + (size_t)ext)));
-    ok(vb->d_pervec.ensure(32 * std::max<size_t>(pv, 1)));
-    ok(vb->d_masks.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext));
-    ok(vb->d_scratch.ensure(msm_scratch_bytes(vb->shape)));
-    ok(vb->d_res.ensure(sizeof(ge) * a->n_chunks));
-    ok(vb->d_ident.ensure(a->n_chunks));
-    ok(vb->h_ok.ensure(std::max<size_t>(n_pts, 1)));
-    ok(vb->h_ident.ensure(a->n_chunks));
-    ok(vb->h_masks.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext));
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // host vectors go out of scope
-    if (e != cudaSuccess) { vb->release(); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
+    ok(w->h_blob.ensure(vb->blob_bytes));
+    ok(w->d_blob.ensure(vb->blob_bytes));
+    ok(w->h_out.ensure(vb->hout_bytes));
+    ok(w->d_tab.ensure(sizeof(aniels) * std::max<size_t>(n_pts, 1)));
+    ok(w->d_ok.ensure(std::max<size_t>(n_pts, 1)));
+    ok(w->d_mscal.ensure(32 * std::max<size_t>(n_entries, 1)));
+    ok(w->d_contrib.ensure(32 * std::max<size_t>(contrib, 1)));
+    ok(w->d_hg.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (1 + (size_t)ext)));
+    ok(w->d_pervec.ensure(32 * std::max<size_t>(pv, 1)));
+    ok(w->d_masks.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext));
+    ok(w->d_scratch.ensure(msm_scratch_bytes(vb->shape)));
+    ok(w->d_res.ensure(sizeof(ge) * a->n_chunks));
+    ok(w->d_ident.ensure(a->n_chunks));
+    if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch buffers"); }
+
+    // ---- pass 2: fill the pinned blob (parallel over proofs), then ONE H2D copy
+    uint8_t *hb = w->h_blob.as<uint8_t>();
+    uint32_t *vecoff = (uint32_t *)(hb + vb->o_vecoff), *segoff = (uint32_t *)(hb + vb->o_segoff), *pidx = (uint32_t *)(hb + vb->o_pidx);
+    {
+        uint32_t run = 0;
+        for (size_t i = 0; i < a->n_proofs; i++) { vecoff[i] = run; if (dp[i].active) run += 1u << dp[i].rounds; }
+        vecoff[a->n_proofs] = run;
+        total_vec = run;
+        for (size_t c = 0; c < a->n_chunks; c++) segoff[c] = dc[c].entry_off;
+        segoff[a->n_chunks] = n_entries;
+    }
+    vb->total_vec = total_vec;
+    memcpy(hb + vb->o_proofs, dp.data(), sizeof(VProof) * a->n_proofs);
+    memcpy(hb + vb->o_chunks, dc.data(), sizeof(VChunk) * a->n_chunks);
+    if (n_commit) { memcpy(hb + vb->o_minv, a->min_values, 8 * n_commit); memcpy(hb + vb->o_minp, a->min_present, n_commit); }
+    for (size_t c = 0; c < a->n_chunks; c++) {
+        if (!dc[c].active) continue;
+        uint32_t *px = pidx + dc[c].entry_off, mn = dc[c].max_mn;
+        for (uint32_t i = 0; i < mn; i++) { px[i] = GEN | i; px[mn + i] = GEN | (uint32_t)(g->nm + i); }
+        for (int k = 0; k < ext; k++) px[2 * mn + k] = GEN | (uint32_t)(2 * g->nm + k);
+        px[2 * mn + ext] = GEN | (uint32_t)(2 * g->nm + ext);
+    }
+    ctx->workers().run(a->n_proofs, 32, [&](size_t i) {
+        const HProof &p = vb->hp[i];
+        const VProof &v = dp[i];
+        uint8_t *wgt = hb + vb->o_weights + 32 * i;
+        memset(wgt, 0, 32);
+        if (!p.n_pts) return;
+        uint8_t *en = hb + vb->o_enc + 32 * (size_t)p.pt_off;
+        memcpy(en, p.a(), 96);
+        for (int j = 0; j < p.rounds; j++) { memcpy(en + 32 * (3 + j), p.li(j), 32); memcpy(en + 32 * (3 + p.rounds + j), p.ri(j), 32); }
+        memcpy(en + 32 * (3 + 2 * p.rounds), a->commitments32 + 32 * a->commit_offsets[i], 32 * (size_t)p.m);
+        if (!v.rounds && !v.m) return;          // chunk not computable: only the decompression flags matter
+        uint8_t *ps = hb + vb->o_pscal + 32 * (size_t)v.sc_off;
+        memcpy(ps, p.r1(), 64);
+        memcpy(ps + 64, p.d1(), 32 * (size_t)ext);
+        uint8_t *chp = hb + vb->o_chal + 32 * (size_t)v.ch_off;
+        memcpy(chp, p.y, 32); memcpy(chp + 32, p.z, 32); memcpy(chp + 64, p.e, 32);
+        for (int j = 0; j < p.rounds; j++) memcpy(chp + 32 * (3 + j), p.ej[j], 32);
+        memcpy(wgt, p.weight, 32);
+        if (v.nonce_off != 0xffffffffu) {
+            uint8_t *nn = hb + vb->o_nonces + 32 * (size_t)v.nonce_off;
+            for (int k = 0; k < ext; k++) {
+                nonce(p.seed, "eta", false, 0, true, (uint32_t)k, nn + 32 * k);
+                nonce(p.seed, "d", false, 0, true, (uint32_t)k, nn + 32 * (ext + k));
+                nonce(p.seed, "alpha", false, 0, true, (uint32_t)k, nn + 32 * (2 * ext + k));
+                for (int j = 0; j < p.rounds; j++) {
+                    nonce(p.seed, "dL", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + j * ext + k));
+                    nonce(p.seed, "dR", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + p.rounds * ext + j * ext + k));
+                }
+            }
+        }
+        if (v.active) {
+            uint32_t *px = pidx + v.entry_off, R = (uint32_t)p.rounds;
+            px[0] = p.pt_off + 1; px[1] = p.pt_off + 2; px[2] = p.pt_off;
+            for (uint32_t j = 0; j < 2 * R + p.m; j++) px[3 + j] = p.pt_off + 3 + j;
+        }
+    });
+    cudaStream_t st = ctx->stream;
+    if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the pinned blob is reused by the next create on this ctx
+    if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
     *out = vb;
     return BPP_OK;
 }
@@ -426,7 +458,7 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     ctx->clear_marks();
     ctx->mark(0);
     if (vb->n_pts) {
-        launch_decompress(st, vb->n_pts, vb->d_enc.as<uint32_t>(), vb->d_tab.as<aniels>(), vb->d_ok.as<uint8_t>(), nullptr, nullptr);
+        launch_decompress(st, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), vb->w->d_tab.as<aniels>(), vb->w->d_ok.as<uint8_t>(), nullptr, nullptr);
         ctx->launches++;
     }
     ctx->mark(1);
@@ -434,31 +466,31 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     d.n_proofs = (uint32_t)vb->n_proofs; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)ext;
     d.action = vb->action;
     VBuffers b;
-    b.proofs = vb->d_proofs.as<VProof>(); b.chunks = vb->d_chunks.as<VChunk>(); b.vec_offsets = vb->d_vecoff.as<uint32_t>();
-    b.proof_scalars = vb->d_pscal.as<uint32_t>(); b.challenges = vb->d_chal.as<uint32_t>(); b.weights = vb->d_weights.as<uint32_t>();
-    b.min_values = vb->d_minv.as<uint64_t>(); b.min_present = vb->d_minp.as<uint8_t>(); b.nonces = vb->d_nonces.as<uint32_t>();
-    b.msm_scalars = vb->d_mscal.as<uint32_t>(); b.contrib = vb->d_contrib.as<uint32_t>(); b.hg_contrib = vb->d_hg.as<uint32_t>();
-    b.pervec = vb->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? vb->d_masks.as<uint32_t>() : nullptr;
+    b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.vec_offsets = vb->dev<uint32_t>(vb->o_vecoff);
+    b.proof_scalars = vb->dev<uint32_t>(vb->o_pscal); b.challenges = vb->dev<uint32_t>(vb->o_chal); b.weights = vb->dev<uint32_t>(vb->o_weights);
+    b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
+    b.msm_scalars = vb->w->d_mscal.as<uint32_t>(); b.contrib = vb->w->d_contrib.as<uint32_t>(); b.hg_contrib = vb->w->d_hg.as<uint32_t>();
+    b.pervec = vb->w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? vb->w->d_masks.as<uint32_t>() : nullptr;
     if (vb->any_msm || vb->any_masks) launch_verify_prep(st, d, b, vb->total_vec, vb->any_msm ? vb->max_static : 0, &ctx->launches);
     ctx->mark(2);
     if (vb->any_msm) {
-        launch_msm(st, vb->shape, vb->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->d_segoff.as<uint32_t>() : nullptr, vb->d_pidx.as<uint32_t>(),
-                   vb->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->d_scratch.p, vb->d_res.as<ge>(), &ctx->launches,
+        launch_msm(st, vb->shape, vb->w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
+                   vb->w->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->w->d_scratch.p, vb->w->d_res.as<ge>(), &ctx->launches,
                    ctx->phase_timing ? &ctx->ph[3] : nullptr);
         if (ctx->phase_timing) for (int i = 3; i <= 6; i++) ctx->ph_set[i] = true;
-        launch_encode(st, vb->n_chunks, vb->d_res.as<ge>(), nullptr, vb->d_ident.as<uint8_t>());
+        launch_encode(st, vb->n_chunks, vb->w->d_res.as<ge>(), nullptr, vb->w->d_ident.as<uint8_t>());
         ctx->mark(7);
         ctx->launches++;
-        BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_ident.p, vb->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_ident), vb->w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
     }
     BPP_CUDA(ctx, cudaGetLastError());
-    if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_ok.p, vb->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
-    if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync(vb->h_masks.p, vb->d_masks.p, 32 * vb->n_proofs * (size_t)ext, cudaMemcpyDeviceToHost, st));
+    if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_ok), vb->w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
+    if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_masks), vb->w->d_masks.p, 32 * vb->n_proofs * (size_t)ext, cudaMemcpyDeviceToHost, st));
     BPP_CUDA(ctx, cudaStreamSynchronize(st));
 
     // ---- resolve per-chunk status with the reference's precedence
-    const uint8_t *okf = vb->h_ok.as<uint8_t>();
-    const uint8_t *ident = vb->h_ident.as<uint8_t>();
+    const uint8_t *okf = (vb->w->h_out.as<uint8_t>() + vb->ho_ok);
+    const uint8_t *ident = (vb->w->h_out.as<uint8_t>() + vb->ho_ident);
     for (size_t c = 0; c < vb->n_chunks; c++) {
         const HChunk &hc = vb->hc[c];
         int32_t rc = hc.pre_rc;
@@ -485,7 +517,7 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
             bool have = !rc && i < hc.hi && vb->action != BPP_VERIFY_ONLY && vb->hp[i].has_seed;
             if (mask_present) mask_present[i] = have ? 1 : 0;
             if (masks32) {
-                if (have) memcpy(masks32 + 32 * i * (size_t)ext, vb->h_masks.as<uint8_t>() + 32 * i * (size_t)ext, 32 * (size_t)ext);
+                if (have) memcpy(masks32 + 32 * i * (size_t)ext, (vb->w->h_out.as<uint8_t>() + vb->ho_masks) + 32 * i * (size_t)ext, 32 * (size_t)ext);
                 else memset(masks32 + 32 * i * (size_t)ext, 0, 32 * (size_t)ext);
             }
         }

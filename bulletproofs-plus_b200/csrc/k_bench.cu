@@ -2,6 +2,7 @@
 // the INT32 multiply issue rate, not by HBM or tensor cores).  Every kernel runs ILP-8 dependent chains per
 // thread over a grid that fills all 148 SMs at full occupancy; the caller converts elapsed time to ops/s.
 #include "kernels.cuh"
+#include "quad.cuh"
 
 namespace bpp {
 
@@ -84,6 +85,45 @@ template <int WHICH> __global__ void __launch_bounds__(MB_THREADS) k_mb_field(in
     if (acc == 0x12345678u) sink[0] = acc;
 }
 
+// latency probes: ONE warp per SM runs a dependent chain (20 fe_mul, 21 fe_sq, 24 sc_montmul, 25 ge_dbl, 27 ge_madd,
+// 30 quad_dbl, 31 quad_add, 32 quad_add + quad_to_cached)
+template <int WHICH> __global__ void __launch_bounds__(32) k_mb_lat(int iters, uint32_t seed, uint32_t *sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    fe a, b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.v[i] = seed * (i + 3) + tid * 2654435761u; b.v[i] = (seed ^ 0x5bd1e995u) * (i + 7) + tid; }
+    a.v[7] &= 0x7fffffffu; b.v[7] &= 0x7fffffffu;
+    if (WHICH == 20) for (int it = 0; it < iters; it++) { a = fe_mul(a, b); a = fe_mul(a, b); }
+    if (WHICH == 21) for (int it = 0; it < iters; it++) { a = fe_sq(a); a = fe_sq(a); }
+    if (WHICH >= 30 && WHICH <= 32) {
+        const int role = threadIdx.x & 3, base = threadIdx.x & 28;
+        if (WHICH == 30) for (int it = 0; it < iters; it++) { a = quad_dbl(a, role, base); a = quad_dbl(a, role, base); }
+        if (WHICH == 31) for (int it = 0; it < iters; it++) { a = quad_add(a, role, base, b); a = quad_add(a, role, base, b); }
+        if (WHICH == 32) for (int it = 0; it < iters; it++) { a = quad_add(a, role, base, quad_to_cached(b, role, base)); b = quad_add(b, role, base, quad_to_cached(a, role, base)); }
+    }
+    if (WHICH == 24) {
+        sc u, v;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { u.v[i] = a.v[i]; v.v[i] = b.v[i]; }
+        u.v[7] &= 0x0fffffffu; v.v[7] &= 0x0fffffffu;
+        for (int it = 0; it < iters; it++) { u = sc_montmul(u, v); u = sc_montmul(u, v); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) a.v[i] = u.v[i];
+    }
+    if (WHICH == 25 || WHICH == 27) {
+        ge p = ge_identity();
+        aniels q; q.ypx = a; q.ymx = b; q.t2d = fe_add(a, b);
+        p.X = a; p.T = b;
+        if (WHICH == 25) for (int it = 0; it < iters; it++) { p = ge_dbl(p); p = ge_dbl(p); }
+        if (WHICH == 27) for (int it = 0; it < iters; it++) { p = ge_madd(p, q); p = ge_madd(p, q); }
+        a = fe_add(fe_add(p.X, p.Y), fe_add(p.Z, p.T));
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= a.v[i];
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
 int microbench_run(cudaStream_t s, int which, int iters, double *ops_per_sec, double *seconds, uint64_t *launches) {
     static uint32_t *sink = nullptr;
     if (!sink && cudaMalloc(&sink, 64) != cudaSuccess) return -1;
@@ -105,6 +145,8 @@ int microbench_run(cudaStream_t s, int which, int iters, double *ops_per_sec, do
             case 7: k_mb_field<7><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2.0 * iters; break;
             case 8: k_mb_field<8><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2.0 * iters; break;
             case 9: k_mb_field<9><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2.0 * iters; break;
+#define LATCASE(W) case W: k_mb_lat<W><<<148, 32, 0, s>>>(iters, 1u, sink); ops_per_thread = 2.0 * iters * (MB_BLOCKS * (double)MB_THREADS) / (148.0 * 32.0); break;
+            LATCASE(20) LATCASE(21) LATCASE(24) LATCASE(25) LATCASE(27) LATCASE(30) LATCASE(31) LATCASE(32)
             default: cudaEventDestroy(e0); cudaEventDestroy(e1); return -2;
         }
         if (launches) (*launches)++;

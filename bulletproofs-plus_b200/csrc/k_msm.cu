@@ -13,18 +13,11 @@
 //   5. k_msm_reduce   one block per (seg, window): sum_b (b+1)*bucket[b] by chunked running sums + tree reduce
 //   6. k_msm_combine  one thread per segment: Horner over the windows
 #include "kernels.cuh"
+#include "quad.cuh"
 
 namespace bpp {
 
 // ------------------------------------------------------------------------------------------------ helpers
-static __device__ __forceinline__ void ld8(uint32_t w[8], const uint32_t *p) {
-    uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-}
-static __device__ __forceinline__ void st8(uint32_t *p, const uint32_t w[8]) {
-    reinterpret_cast<uint4 *>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
 static __device__ __forceinline__ aniels ld_aniels(const aniels *p) {
     aniels q;
     ld8(q.ypx.v, p->ypx.v); ld8(q.ymx.v, p->ymx.v); ld8(q.t2d.v, p->t2d.v);
@@ -38,24 +31,6 @@ static __device__ __forceinline__ ge ld_ge(const ge *p) {
 static __device__ __forceinline__ void st_ge(ge *p, const ge &r) {
     st8(p->X.v, r.X.v); st8(p->Y.v, r.Y.v); st8(p->Z.v, r.Z.v); st8(p->T.v, r.T.v);
 }
-// by-value so that operands and result travel in registers through the call (see arith.cuh fe_mul)
-static __device__ __noinline__ ge ge_add_nl(ge a, ge b) { return ge_add(a, b); }
-static __device__ __noinline__ ge ge_dbl_nl(ge a) { return ge_dbl(a); }
-static __device__ __noinline__ ge ge_madd_nl(ge a, aniels b) { return ge_madd(a, b); }
-static __device__ __noinline__ ge ge_msub_nl(ge a, aniels b) { return ge_msub(a, b); }
-
-static __device__ __forceinline__ ge shfl_down_ge(const ge &p, int delta) {
-    ge r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], delta);
-        r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], delta);
-        r.Z.v[i] = __shfl_down_sync(0xffffffffu, p.Z.v[i], delta);
-        r.T.v[i] = __shfl_down_sync(0xffffffffu, p.T.v[i], delta);
-    }
-    return r;
-}
-
 // c-bit field of a 256-bit little-endian scalar at bit offset `off`
 static __device__ __forceinline__ uint32_t bits_at(const uint32_t s[8], int off, int c) {
     int wi = off >> 5, sh = off & 31;
@@ -107,7 +82,7 @@ struct MsmScratch {
     uint32_t *cursor;   // n_keys
     uint32_t *tile_sums;
     uint32_t *sorted;   // n_entries * W
-    ge *buckets;        // n_keys
+    cached *buckets;    // n_keys
     ge *windows;        // n_seg * W
     size_t total;
 };
@@ -121,7 +96,7 @@ static MsmScratch msm_carve(const MsmShape &sh, void *base) {
     s.cursor = (uint32_t *)(p + off); off = align_up(off + n_keys * 4, 256);
     s.tile_sums = (uint32_t *)(p + off); off = align_up(off + (n_tiles + 1) * 4, 256);
     s.sorted = (uint32_t *)(p + off); off = align_up(off + (size_t)sh.n_entries * sh.W * 4 + 4, 256);
-    s.buckets = (ge *)(p + off); off = align_up(off + n_keys * sizeof(ge), 256);
+    s.buckets = (cached *)(p + off); off = align_up(off + n_keys * sizeof(cached), 256);
     s.windows = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * sizeof(ge), 256);
     s.total = off;
     return s;
@@ -231,81 +206,102 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t *__restrict__ count
 }
 
 // ------------------------------------------------------------------------------------------------ 4: bucket sums
+// one quad per bucket; the bucket is written in cached form for the running sums
 __global__ void __launch_bounds__(128) k_msm_bucket(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
                                                    const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
-                                                   const aniels *__restrict__ gens, ge *__restrict__ buckets) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_keys) return;
-    uint32_t lo = starts[k], hi = starts[k + 1];
-    ge acc = ge_identity();
-    for (uint32_t j = lo; j < hi; j++) {
-        uint32_t e = sorted[j];
-        uint32_t idx = e & 0x7fffffffu;
-        uint32_t pi = pidx ? pidx[idx] : idx;
-        const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
-        aniels q = ld_aniels(src);
-        acc = (e >> 31) ? ge_msub_nl(acc, q) : ge_madd_nl(acc, q);
+                                                   const aniels *__restrict__ gens, cached *__restrict__ buckets) {
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int role = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
+    const bool valid = k < n_keys;
+    const uint32_t lo = valid ? starts[k] : 0u, hi = valid ? starts[k + 1] : 0u;
+    const uint32_t cnt = hi - lo;
+    const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+    fe c = quad_identity(role);
+    for (uint32_t j = 0; j < maxcnt; j++) {
+        fe q = quad_cached_identity(role);
+        if (j < cnt) {
+            uint32_t e = sorted[lo + j];
+            uint32_t idx = e & 0x7fffffffu;
+            uint32_t pi = pidx ? pidx[idx] : idx;
+            const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
+            bool neg = (e >> 31) != 0;
+            // -Q swaps (y-x, y+x) and negates 2dxy
+            if (role == 0) q = ld_fe(neg ? &src->ypx : &src->ymx);
+            else if (role == 1) q = ld_fe(neg ? &src->ymx : &src->ypx);
+            else if (role == 3) { q = ld_fe(&src->t2d); if (neg) q = fe_sub_l(fe_zero(), q); }
+        }
+        c = quad_add(c, role, base, q);
     }
-    st_ge(&buckets[k], acc);
+    fe out = quad_to_cached(c, role, base);
+    if (valid) st_fe(reinterpret_cast<fe *>(&buckets[k]) + role, out);
 }
 
 // ------------------------------------------------------------------------------------------------ 5: window sums
-// block = T threads for one (seg, window); thread t owns buckets [t*L, (t+1)*L): S = sum, R = sum (j+1)*bucket[tL+j],
-// contributes R + (t*L)*S; the block sums the contributions.
-__global__ void __launch_bounds__(256) k_msm_reduce(uint32_t B, uint32_t L, uint32_t nthreads, const ge *__restrict__ buckets,
+// one CTA per (segment, window); quad t owns buckets [t*L, (t+1)*L): S = sum, R = sum_j (j+1)*bucket[tL+j]; it contributes
+// R + (t*L)*S, and the CTA adds the contributions up.  Control flow is CTA-uniform (idle quads work on the identity).
+__global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uint32_t nq, const cached *__restrict__ buckets,
                                                     ge *__restrict__ windows) {
-    __shared__ ge warp_part[32];
-    uint32_t t = threadIdx.x;      // blockDim.x is a multiple of 32; threads >= nthreads only take part in the shuffles
-    const ge *bk = buckets + (size_t)blockIdx.x * B + (size_t)t * L;
-    ge S = ge_identity(), R = ge_identity();
-    if (t < nthreads) {
-        for (int j = (int)L - 1; j >= 0; j--) {
-            ge b = ld_ge(&bk[j]);
-            S = ge_add_nl(S, b);
-            R = ge_add_nl(R, S);
+    __shared__ fe part[32][4];
+    const uint32_t t = threadIdx.x >> 2;
+    const int role = threadIdx.x & 3, lane = threadIdx.x & 31, base = lane & ~3;
+    const cached *bk = buckets + (size_t)blockIdx.x * B + (size_t)t * L;
+    fe S = quad_identity(role), R = quad_identity(role);
+    for (int j = (int)L - 1; j >= 0; j--) {
+        fe b = t < nq ? ld_fe(reinterpret_cast<const fe *>(&bk[j]) + role) : quad_cached_identity(role);
+        S = quad_add(S, role, base, b);
+        R = quad_add(R, role, base, quad_to_cached(S, role, base));
+    }
+    // R += (t*L) * S by uniform double-and-add over the bits of the largest offset in the CTA
+    {
+        const uint32_t k = t < nq ? t * L : 0u, kmax = (nq - 1) * L;
+        const fe Sc = quad_to_cached(S, role, base);
+        fe M = quad_identity(role);
+        for (int bit = 31 - __clz(kmax | 1u); bit >= 0; bit--) {
+            M = quad_dbl(M, role, base);
+            M = quad_add(M, role, base, ((k >> bit) & 1u) ? Sc : quad_cached_identity(role));
         }
+        if (kmax) R = quad_add(R, role, base, quad_to_cached(M, role, base));
     }
-    uint32_t k = t * L;
-    if (k != 0 && t < nthreads) {
-        // R += k * S  (left-to-right double-and-add; k < B <= 2^15)
-        ge M = S;
-        int top = 31 - __clz(k);
-        for (int bit = top - 1; bit >= 0; bit--) {
-            M = ge_dbl_nl(M);
-            if ((k >> bit) & 1u) M = ge_add_nl(M, S);
-        }
-        R = ge_add_nl(R, M);
+    // tree over the 8 quads of a warp, then over warps through shared memory
+    for (int d = 16; d >= 4; d >>= 1) {
+        fe o = shfl_down_fe(R, d);
+        if (lane + d >= 32) o = quad_identity(role);
+        R = quad_add(R, role, base, quad_to_cached(o, role, base));
     }
-    // warp tree
-    for (int d = 16; d > 0; d >>= 1) {
-        ge o = shfl_down_ge(R, d);
-        bool valid = ((t & 31u) + d < 32u) && (t + d < nthreads);
-        if (valid) R = ge_add_nl(R, o);
-    }
-    if ((t & 31u) == 0) warp_part[t >> 5] = R;
+    const uint32_t warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31u) >> 5;
+    if (lane < 4) part[warp][role] = R;
     __syncthreads();
-    if (t < 32) {
-        uint32_t nwarps = (nthreads + 31u) >> 5;
-        ge V = (t < nwarps) ? warp_part[t] : ge_identity();
-        for (int d = 16; d > 0; d >>= 1) {
-            ge o = shfl_down_ge(V, d);
-            if (t + d < nwarps && (int)t + d < 32) V = ge_add_nl(V, o);
+    if (warp == 0) {
+        const uint32_t q = lane >> 2;                   // 8 quads, each folds warps q, q+8, q+16, q+24
+        fe V = quad_identity(role);
+        for (uint32_t r = 0; r < 4; r++) {
+            uint32_t src = q + 8 * r;
+            fe o = src < nwarps ? part[src][role] : quad_identity(role);
+            V = quad_add(V, role, base, quad_to_cached(o, role, base));
         }
-        if (t == 0) st_ge(&windows[blockIdx.x], V);
+        for (int d = 16; d >= 4; d >>= 1) {
+            fe o = shfl_down_fe(V, d);
+            if (lane + d >= 32) o = quad_identity(role);
+            V = quad_add(V, role, base, quad_to_cached(o, role, base));
+        }
+        if (lane < 4) st_fe(reinterpret_cast<fe *>(&windows[blockIdx.x]) + role, V);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ 6: Horner
-__global__ void k_msm_combine(uint32_t n_seg, int c, int W, const ge *__restrict__ windows, ge *__restrict__ result) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    const ge *win = windows + (size_t)s * W;
-    ge acc = ld_ge(&win[W - 1]);
+// one quad per segment
+__global__ void __launch_bounds__(32) k_msm_combine(uint32_t n_seg, int c, int W, const ge *__restrict__ windows, ge *__restrict__ result) {
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int role = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
+    const bool valid = s < n_seg;
+    const fe *win = reinterpret_cast<const fe *>(windows + (size_t)(valid ? s : 0) * W);
+    fe acc = valid ? ld_fe(win + 4 * (W - 1) + role) : quad_identity(role);
     for (int w = W - 2; w >= 0; w--) {
-        for (int k = 0; k < c; k++) acc = ge_dbl_nl(acc);
-        acc = ge_add_nl(acc, ld_ge(&win[w]));
+        for (int k = 0; k < c; k++) acc = quad_dbl(acc, role, base);
+        fe o = valid ? ld_fe(win + 4 * w + role) : quad_identity(role);
+        acc = quad_add(acc, role, base, quad_to_cached(o, role, base));
     }
-    st_ge(&result[s], acc);
+    if (valid) st_fe(reinterpret_cast<fe *>(&result[s]) + role, acc);
 }
 
 // ------------------------------------------------------------------------------------------------ driver
@@ -326,14 +322,14 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         k_msm_digits<true><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.cursor, sc.sorted);
     }
     if (marks) cudaEventRecord(marks[0], s);
-    k_msm_bucket<<<(uint32_t)((n_keys + 127) / 128), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, sc.buckets);
+    k_msm_bucket<<<(uint32_t)((n_keys + 31) / 32), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
-    uint32_t T = sh.B >= 8 ? sh.B / 8 : 1;
-    if (T > 256) T = 256;
-    uint32_t L = sh.B / T;
-    k_msm_reduce<<<sh.n_seg * sh.W, (T + 31u) / 32u * 32u, 0, s>>>(sh.B, L, T, sc.buckets, sc.windows);
+    uint32_t nq = sh.B >= 8 ? sh.B / 8 : 1;        // quads per (segment, window)
+    if (nq > 256) nq = 256;
+    uint32_t L = sh.B / nq;
+    k_msm_reduce<<<sh.n_seg * sh.W, (4 * nq + 31u) / 32u * 32u, 0, s>>>(sh.B, L, nq, sc.buckets, sc.windows);
     if (marks) cudaEventRecord(marks[2], s);
-    k_msm_combine<<<(sh.n_seg + 31) / 32, 32, 0, s>>>(sh.n_seg, sh.c, sh.W, sc.windows, result);
+    k_msm_combine<<<(sh.n_seg + 7) / 8, 32, 0, s>>>(sh.n_seg, sh.c, sh.W, sc.windows, result);
     if (marks) cudaEventRecord(marks[3], s);
     if (launches) *launches += 6 + (sh.n_entries ? 2 : 0);
 }

@@ -6,3 +6,9 @@ for w,nm in names.items():
     it = 4000 if w in (0,1,2,3,10,11) else 400
     ops,sec = e.microbench(w,it)
     print("%-16s %.4e ops/s  (%.3f ms)"%(nm,ops,sec*1e3))
+print("--- latency probes: one warp per SM, dependent chain; ns per op")
+lat = {20:'fe_mul',21:'fe_sq',24:'sc_montmul',25:'ge_dbl',27:'ge_madd',30:'quad_dbl',31:'quad_add',32:'quad_add+to_cached'}
+for w,nm in lat.items():
+    it = 2000
+    ops,sec = e.microbench(w,it)
+    print("%-16s %.1f ns/op"%(nm, sec/(2*it)*1e9))

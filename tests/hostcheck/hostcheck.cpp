@@ -8,6 +8,14 @@ using namespace bpp;
 static fe ld(const uint8_t *s) { return fe_frombytes(s, nullptr); }
 extern "C" {
 void hc_fe_mul(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe_tobytes(o, fe_mul(ld(a), ld(b))); }
+// lazy add/sub feeding a multiplication, on LOOSE (full 256-bit) inputs: o = ((a + b) * (c - d)) and ((a - b)^2)
+static fe ldl(const uint8_t *s) { fe r; memcpy(r.v, s, 32); return r; }
+void hc_fe_lazy_mul(const uint8_t *a, const uint8_t *b, const uint8_t *c, const uint8_t *d, uint8_t *o) {
+    fe_tobytes(o, fe_mul(fe_add_l(ld(a), ld(b)), fe_sub_ll(ldl(c), ldl(d))));
+}
+void hc_fe_lazy_sq(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe_tobytes(o, fe_sq(fe_sub_ll(ldl(a), ldl(b)))); }
+void hc_fe_lazy_sq_tight(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe_tobytes(o, fe_sq(fe_sub_l(ldl(a), ld(b)))); }
+void hc_fe_mul_loose_raw(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe r = fe_mul(ldl(a), ldl(b)); memcpy(o, r.v, 32); }
 void hc_fe_sq(const uint8_t *a, uint8_t *o) { fe_tobytes(o, fe_sq(ld(a))); }
 void hc_fe_add(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe_tobytes(o, fe_add(ld(a), ld(b))); }
 void hc_fe_sub(const uint8_t *a, const uint8_t *b, uint8_t *o) { fe_tobytes(o, fe_sub(ld(a), ld(b))); }

@@ -73,6 +73,24 @@ def test_field_ops(hc):
         hc.hc_fe_invert(b32(a), o); assert i32(o) == pow(a, -1, P)
 
 
+def test_lazy_add_sub_feed_multiplications(hc):
+    """fe_add_l / fe_sub_l produce loose (full 256-bit) values; fe_mul / fe_sq must reduce them correctly"""
+    rnd, o = random.Random(15), buf()
+    loose_edge = [0, 1, 37, 38, 39, 2**255 - 19, 2**255 - 1, 2**255, 2**256 - 39, 2**256 - 38, 2**256 - 1, 2**256 - 2**32]
+    tight = EDGE + [rnd.randrange(2**255) for _ in range(40)]
+    loose = loose_edge + [rnd.randrange(2**256) for _ in range(40)]
+    for a in loose:
+        for b in rnd.sample(loose, 8) + loose_edge:
+            hc.hc_fe_mul_loose_raw(b32(a), b32(b), o); assert i32(o) < 2**255 and i32(o) % P == a * b % P
+            hc.hc_fe_lazy_sq(b32(a), b32(b), o); assert i32(o) == (a - b) ** 2 % P
+            hc.hc_fe_lazy_sq_tight(b32(a), b32(b % 2**255), o); assert i32(o) == (a - b % 2**255) ** 2 % P
+    for a in tight[:30]:
+        for b in rnd.sample(tight, 4):
+            for c in rnd.sample(loose, 4) + loose_edge[:6]:
+                d = rnd.choice(loose)
+                hc.hc_fe_lazy_mul(b32(a), b32(b), b32(c), b32(d), o); assert i32(o) == (a + b) * (c - d) % P
+
+
 def test_sqrt_ratio_vs_oracle(hc):
     rnd, l = random.Random(12), orc.lib()
     o, o2 = buf(), buf()

@@ -71,10 +71,10 @@ class Engine:
     def phase_timing(self, enable):
         _chk(self, _ffi.lib().bpp_ctx_phase_timing(self.h, 1 if enable else 0))
 
-    PHASES = ("decompress", "vprep", "msm_sort", "msm_bucket", "msm_reduce", "msm_combine", "encode")
+    PHASES = ("decompress", "vprep_proof", "vprep_vector", "vprep_reduce", "msm_sort", "msm_bucket", "msm_reduce", "msm_combine", "encode")
 
     def phase_ms(self):
-        arr = (C.c_float * 7)()
+        arr = (C.c_float * 9)()
         _chk(self, _ffi.lib().bpp_ctx_phase_ms(self.h, arr))
         return dict(zip(self.PHASES, [float(x) for x in arr]))
 

@@ -622,6 +622,75 @@ BPP_HD sc scm_invert(const sc &a) {
     return acc;
 }
 
+// Inverse mod l by the binary extended Euclid with branch-free steps (plain domain; 0 -> 0).
+// Invariants: x1 * a = u and x2 * a = v (mod l), gcd(u, v) = 1.  One step: make u the even one (swap if only v is even;
+// if both are odd, order them and subtract), then halve u and x1.  bitlen(u) + bitlen(v) <= 506 drops by >= 1 per step.
+// ~130 straight-line instructions per step against ~380 dependent Montgomery multiplications for a^(l-2): about 8x
+// shorter as a single-thread latency chain, which is what the verifier's per-proof scalar prep is bound by.
+BPP_HD sc sc_invert_gcd(const sc &a) {
+    uint32_t u[8], v[8], x1[8], x2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = a.v[i]; v[i] = sc_l(i); x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    for (int step = 0; step < 520; step++) {
+        uint32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nz |= u[i];
+        if (nz == 0) break;
+        // 1. only v even -> swap
+        uint32_t sw = ((u[0] & 1u) & ~(v[0] & 1u)) ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t t = (u[i] ^ v[i]) & sw; u[i] ^= t; v[i] ^= t;
+            t = (x1[i] ^ x2[i]) & sw; x1[i] ^= t; x2[i] ^= t;
+        }
+        // 2. both odd -> u = |u - v| ordering by swap, x1 -= x2 (mod l)
+        uint32_t odd = (u[0] & 1u) ? 0xffffffffu : 0u;
+        {
+            int64_t c = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { c += (int64_t)u[i] - (int64_t)v[i]; c >>= 32; }
+            uint32_t lt = (c < 0) ? odd : 0u;       // u < v (and both odd) -> swap first
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t t = (u[i] ^ v[i]) & lt; u[i] ^= t; v[i] ^= t;
+                t = (x1[i] ^ x2[i]) & lt; x1[i] ^= t; x2[i] ^= t;
+            }
+            c = 0;
+            int64_t d = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                c += (int64_t)u[i] - (int64_t)(v[i] & odd); u[i] = (uint32_t)c; c >>= 32;
+                d += (int64_t)x1[i] - (int64_t)(x2[i] & odd); x1[i] = (uint32_t)d; d >>= 32;
+            }
+            uint32_t fix = d < 0 ? 0xffffffffu : 0u;
+            uint64_t e = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { e += (uint64_t)x1[i] + (sc_l(i) & fix); x1[i] = (uint32_t)e; e >>= 32; }
+        }
+        // 3. u is even: if it is not zero, halve u and x1 (x1 odd -> (x1 + l) / 2)
+        nz = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nz |= u[i];
+        if (nz != 0) {
+            uint32_t xo = (x1[0] & 1u) ? 0xffffffffu : 0u;
+            uint64_t e = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { e += (uint64_t)x1[i] + (sc_l(i) & xo); x1[i] = (uint32_t)e; e >>= 32; }
+#pragma unroll
+            for (int i = 0; i < 7; i++) { u[i] = (u[i] >> 1) | (u[i + 1] << 31); x1[i] = (x1[i] >> 1) | (x1[i + 1] << 31); }
+            u[7] >>= 1; x1[7] >>= 1;
+        }
+    }
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = x2[i];
+    return r;
+}
+// Montgomery-form inversion through the plain-domain Euclid: (aR)^-1 = a^-1 R^-1, times R^3 (Montgomery) = a^-1 R
+BPP_HD sc sc_const_RRR() { return BPP_SC(0x7b83a2dbu, 0x2a9e4968u, 0xaef7f3ecu, 0x278324e6u, 0x04ec5b65u, 0x8065dc6cu, 0x3599cec7u, 0x0e530b77u); }
+BPP_HD sc scm_invert_gcd(const sc &a) { return sc_montmul(sc_invert_gcd(a), sc_const_RRR()); }
+
 // ================================================================================================ points
 BPP_HD ge ge_identity() { ge r; r.X = fe_zero(); r.Y = fe_one(); r.Z = fe_one(); r.T = fe_zero(); return r; }
 BPP_HD aniels aniels_identity() { aniels r; r.ypx = fe_one(); r.ymx = fe_one(); r.t2d = fe_zero(); return r; }

@@ -46,6 +46,11 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     bpp_ctx *ctx = new bpp_ctx();
     ctx->device = device_ordinal;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPP_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream); delete ctx; return BPP_ERR_CUDA;
+    }
     unsigned hc = std::thread::hardware_concurrency();
     ctx->host_threads = hc ? (int)(hc > 64 ? 64 : hc) : 1;
     if (const char *env = getenv("BPP_HOST_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 1024) ctx->host_threads = v; }
@@ -61,7 +66,10 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     vwork_pool_free(ctx);
     delete ctx->pool;
     if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
-    for (int i = 0; i < 8; i++) if (ctx->ph[i]) cudaEventDestroy(ctx->ph[i]);
+    for (int i = 0; i < bpp_ctx::N_MARKS; i++) if (ctx->ph[i]) cudaEventDestroy(ctx->ph[i]);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -92,22 +100,22 @@ int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable) {
     if (!ctx) return BPP_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     if (enable)
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < bpp_ctx::N_MARKS; i++)
             if (!ctx->ph[i]) BPP_CUDA(ctx, cudaEventCreate(&ctx->ph[i]));
     ctx->phase_timing = enable != 0;
     ctx->clear_marks();
     return BPP_OK;
 }
-// ms7[i] = time between mark i and mark i+1 of the last vbatch / plan run (0 where a mark was not reached):
-// 0 decompress, 1 verifier scalar prep, 2 MSM sort (digits+scan+scatter), 3 MSM bucket sums, 4 MSM window reduction,
-// 5 MSM Horner combine, 6 encode / identity test
-int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms7) {
-    if (!ctx || !ms7) return BPP_INVALID_ARGUMENT;
+// ms9[i] = time between mark i and mark i+1 of the last vbatch / plan run (0 where a mark was not reached):
+// 0 decompress, 1 verifier prep per proof, 2 per (proof, i), 3 column sums, 4 MSM sort (digits+scan+scatter), 5 MSM bucket sums,
+// 6 MSM window reduction, 7 MSM Horner combine, 8 encode / identity test
+int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms9) {
+    if (!ctx || !ms9) return BPP_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < 7; i++) {
-        ms7[i] = 0.f;
-        if (ctx->ph_set[i] && ctx->ph_set[i + 1]) BPP_CUDA(ctx, cudaEventElapsedTime(&ms7[i], ctx->ph[i], ctx->ph[i + 1]));
+    for (int i = 0; i + 1 < bpp_ctx::N_MARKS; i++) {
+        ms9[i] = 0.f;
+        if (ctx->ph_set[i] && ctx->ph_set[i + 1]) BPP_CUDA(ctx, cudaEventElapsedTime(&ms9[i], ctx->ph[i], ctx->ph[i + 1]));
     }
     return BPP_OK;
 }
@@ -261,14 +269,14 @@ int32_t bpp_msm_plan_run(bpp_msm_plan *pl, uint8_t *out32_or_null) {
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     ctx->clear_marks();
-    ctx->mark(2);
+    ctx->mark(4);
     launch_msm(st, pl->sh, pl->d_scalars.as<uint32_t>(), nullptr, nullptr, pl->d_tab.as<aniels>(), nullptr, pl->d_scratch.p,
-               pl->d_res.as<ge>(), &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
-    if (ctx->phase_timing) for (int i = 3; i <= 6; i++) ctx->ph_set[i] = true;
+               pl->d_res.as<ge>(), &ctx->launches, ctx->phase_timing ? &ctx->ph[5] : nullptr);
+    if (ctx->phase_timing) for (int i = 5; i <= 8; i++) ctx->ph_set[i] = true;
     BPP_CUDA(ctx, cudaGetLastError());
     if (out32_or_null) {
         launch_encode(st, 1, pl->d_res.as<ge>(), pl->d_out.as<uint32_t>(), nullptr);
-        ctx->mark(7);
+        ctx->mark(9);
         ctx->launches++;
         BPP_CUDA(ctx, cudaMemcpyAsync(out32_or_null, pl->d_out.p, 32, cudaMemcpyDeviceToHost, st));
         BPP_CUDA(ctx, cudaStreamSynchronize(st));

@@ -47,6 +47,8 @@ struct PinBuf {
 struct bpp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // side stream: point decompression overlaps the scalar prep chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
@@ -58,10 +60,11 @@ struct bpp_ctx {
     // measurement: wall timer and per-phase marks on `stream` (bench.py)
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool phase_timing = false;
-    cudaEvent_t ph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ph_set[8] = {false, false, false, false, false, false, false, false};
+    static constexpr int N_MARKS = 10;   // 9 phases: decompress, vprep_proof, vprep_vector, vprep_reduce, msm sort/bucket/reduce/combine, encode
+    cudaEvent_t ph[N_MARKS] = {};
+    bool ph_set[N_MARKS] = {};
     void mark(int i) { if (phase_timing && ph[i]) { cudaEventRecord(ph[i], stream); ph_set[i] = true; } }
-    void clear_marks() { for (int i = 0; i < 8; i++) ph_set[i] = false; }
+    void clear_marks() { for (int i = 0; i < N_MARKS; i++) ph_set[i] = false; }
     // reusable scratch for the one-shot entry points
     bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc;
     bpp::PinBuf h_stage, h_stage2;

@@ -455,10 +455,20 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     cudaStream_t st = ctx->stream;
     const int ext = g->ext;
     // ---- device: decompress -> prep -> MSM -> identity flags
+    // The decompression (k_point.cu) only feeds the bucket sums, so it runs on the side stream next to the scalar prep
+    // chain; with phase timing on everything stays on one stream so that the per-phase events mean what they say.
     ctx->clear_marks();
     ctx->mark(0);
+    const bool overlap = !ctx->phase_timing && vb->n_pts && (vb->any_msm || vb->any_masks);
     if (vb->n_pts) {
-        launch_decompress(st, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), vb->w->d_tab.as<aniels>(), vb->w->d_ok.as<uint8_t>(), nullptr, nullptr);
+        cudaStream_t ds = st;
+        if (overlap) {
+            BPP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+            BPP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            ds = ctx->stream2;
+        }
+        launch_decompress(ds, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), vb->w->d_tab.as<aniels>(), vb->w->d_ok.as<uint8_t>(), nullptr, nullptr);
+        if (overlap) BPP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
         ctx->launches++;
     }
     ctx->mark(1);
@@ -471,15 +481,19 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
     b.msm_scalars = vb->w->d_mscal.as<uint32_t>(); b.contrib = vb->w->d_contrib.as<uint32_t>(); b.hg_contrib = vb->w->d_hg.as<uint32_t>();
     b.pervec = vb->w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? vb->w->d_masks.as<uint32_t>() : nullptr;
-    if (vb->any_msm || vb->any_masks) launch_verify_prep(st, d, b, vb->total_vec, vb->any_msm ? vb->max_static : 0, &ctx->launches);
-    ctx->mark(2);
+    if (vb->any_msm || vb->any_masks) {
+        launch_verify_prep(st, d, b, vb->total_vec, vb->any_msm ? vb->max_static : 0, &ctx->launches, ctx->phase_timing ? &ctx->ph[2] : nullptr);
+        if (ctx->phase_timing) { ctx->ph_set[2] = true; ctx->ph_set[3] = vb->action != BPP_RECOVER_ONLY; }
+    }
+    if (overlap) BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->mark(4);
     if (vb->any_msm) {
         launch_msm(st, vb->shape, vb->w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
                    vb->w->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->w->d_scratch.p, vb->w->d_res.as<ge>(), &ctx->launches,
-                   ctx->phase_timing ? &ctx->ph[3] : nullptr);
-        if (ctx->phase_timing) for (int i = 3; i <= 6; i++) ctx->ph_set[i] = true;
+                   ctx->phase_timing ? &ctx->ph[5] : nullptr);
+        if (ctx->phase_timing) for (int i = 5; i <= 8; i++) ctx->ph_set[i] = true;
         launch_encode(st, vb->n_chunks, vb->w->d_res.as<ge>(), nullptr, vb->w->d_ident.as<uint8_t>());
-        ctx->mark(7);
+        ctx->mark(9);
         ctx->launches++;
         BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_ident), vb->w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
     }

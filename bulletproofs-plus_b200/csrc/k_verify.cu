@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     pre[R + 1] = acc; acc = mm(acc, ym1);
     pre[R + 2] = acc; acc = mm(acc, e);
     pre[R + 3] = acc; acc = mm(acc, zy);
-    sc inv = scm_invert(acc);
+    sc inv = scm_invert_gcd(acc);      // binary Euclid: ~8x shorter latency chain than a^(l-2)
     sc zy_inv = mm(inv, pre[R + 3]); inv = mm(inv, zy);
     sc e_inv = mm(inv, pre[R + 2]); inv = mm(inv, e);
     sc ym1_inv = mm(inv, pre[R + 1]); inv = mm(inv, ym1);
@@ -191,16 +191,23 @@ __global__ void __launch_bounds__(128) k_vprep_vector(VDims d, VBuffers b, uint3
     st_sc(c + 8 * ((size_t)N + i), h);
 }
 
-// one thread per (chunk, static slot): slot in [0, 2*max_mn + ext + 1)
+// one WARP per (chunk, static slot), slot in [0, 2*max_mn + ext + 1): lane l adds up proofs l, l+32, .. of the chunk, then a
+// shuffle tree of modular additions (a single thread walking 256 proofs was a 150 us latency chain)
+static __device__ __forceinline__ sc shfl_down_sc(const sc &a, int delta) {
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], delta);
+    return r;
+}
 __global__ void __launch_bounds__(128) k_vprep_reduce(VDims d, VBuffers b) {
-    uint32_t c = blockIdx.y;
+    const uint32_t c = blockIdx.y;
     const VChunk chk = b.chunks[c];
     if (!chk.active) return;
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n_static = 2 * chk.max_mn + d.ext + 1;
-    if (slot >= n_static) return;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_static = 2 * chk.max_mn + d.ext + 1;
+    if (slot >= n_static) return;                       // warp-uniform
     sc acc = sc_zero();
-    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++) {
+    for (uint32_t p = chk.proof_lo + lane; p < chk.proof_hi; p += 32) {
         const VProof pr = b.proofs[p];
         if (!pr.active) continue;
         uint32_t N = 1u << pr.rounds;
@@ -211,20 +218,24 @@ __global__ void __launch_bounds__(128) k_vprep_reduce(VDims d, VBuffers b) {
         else src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext));
         if (src) acc = sc_add(acc, ld_sc(src));
     }
-    st_sc(b.msm_scalars + 8 * ((size_t)chk.entry_off + slot), sc_from_mont(acc));
+    for (int delta = 16; delta > 0; delta >>= 1) acc = sc_add(acc, shfl_down_sc(acc, delta));
+    if (lane == 0) st_sc(b.msm_scalars + 8 * ((size_t)chk.entry_off + slot), sc_from_mont(acc));
 }
 
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches) {
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches,
+                        cudaEvent_t *marks) {
     if (d.n_proofs == 0) return;
     k_vprep_proof<<<(d.n_proofs + 63) / 64, 64, 0, s>>>(d, b);
+    if (marks) cudaEventRecord(marks[0], s);
     if (launches) (*launches)++;
     if (d.action == 0 /* RecoverOnly */) return;
     if (total_vec) {
         k_vprep_vector<<<(total_vec + 127) / 128, 128, 0, s>>>(d, b, total_vec);
         if (launches) (*launches)++;
     }
+    if (marks) cudaEventRecord(marks[1], s);
     if (max_static) {
-        dim3 grid((max_static + 127) / 128, d.n_chunks);
+        dim3 grid((max_static + 3) / 4, d.n_chunks);       // 4 warps (slots) per CTA
         k_vprep_reduce<<<grid, 128, 0, s>>>(d, b);
         if (launches) (*launches)++;
     }

@@ -69,7 +69,8 @@ struct VBuffers {
     uint32_t *pervec;                // scratch: stage A -> B hand-off
     uint32_t *masks;                 // out: n_proofs x ext x 8 words (plain), may be null
 };
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches);
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches,
+                        cudaEvent_t *marks = nullptr);   // marks (optional, 2 events): after the per-proof stage, after the per-(proof, i) stage
 
 // ---------------------------------------------------------------- k_bench.cu
 // returns elapsed seconds for `iters` dependent ops in each of `threads_total` lanes; ops counted by caller

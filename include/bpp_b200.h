@@ -61,9 +61,10 @@ void *bpp_ctx_stream(bpp_ctx *ctx);                   /* cudaStream_t, for event
 int32_t bpp_ctx_timer_start(bpp_ctx *ctx);
 int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms);
 /* per-phase device times of the last bpp_vbatch_run / bpp_msm_plan_run (events between the kernels, when enabled):
- * ms7 = {decompress, verifier scalar prep, MSM sort, MSM bucket sums, MSM window reduction, MSM Horner, encode/identity} */
+ * ms9 = {decompress, verifier prep per proof, per (proof, i), column sums, MSM sort, MSM bucket sums, MSM window reduction,
+ *        MSM Horner, encode/identity} */
 int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable);
-int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms7);
+int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms9);
 /* host threads used for the Fiat-Shamir replay of bpp_verify_chunks (default: min(64, hardware threads); the
  * reference is single-threaded, the harness supplies parallelism -- see BASELINE.md) */
 int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);

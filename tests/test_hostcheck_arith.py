@@ -123,6 +123,10 @@ def test_scalar_ops(hc):
     hc.hc_sc_from_wide((2**512 - 1).to_bytes(64, "little"), o); assert i32(o) == (2**512 - 1) % L
     for a in [1, 2, L - 1, rnd.randrange(1, L)]:
         hc.hc_sc_invert(b32(a), o); assert i32(o) == pow(a, -1, L)
+    for a in [1, 2, 3, L - 1, L - 2, 2**252, 2**252 - 1, (L + 1) // 2] + [rnd.randrange(1, L) for _ in range(300)] + [2**k for k in range(0, 252, 17)]:
+        hc.hc_sc_invert_gcd(b32(a), o); assert i32(o) == pow(a, -1, L), a
+        hc.hc_scm_invert_gcd(b32(a), o); assert i32(o) == pow(a, -1, L), a
+    hc.hc_sc_invert_gcd(b32(0), o); assert i32(o) == 0
     assert hc.hc_sc_is_canonical(b32(L - 1)) == 1 and hc.hc_sc_is_canonical(b32(L)) == 0
     assert hc.hc_sc_is_canonical(b32(2**256 - 1)) == 0 and hc.hc_sc_is_canonical(b32(0)) == 1
 

@@ -78,6 +78,13 @@ class Engine:
         _chk(self, _ffi.lib().bpp_ctx_phase_ms(self.h, arr))
         return dict(zip(self.PHASES, [float(x) for x in arr]))
 
+    HOST_PHASES = ("parse", "replay", "weights", "layout", "fill", "h2d")
+
+    def host_ms(self):
+        arr = (C.c_double * 6)()
+        _chk(self, _ffi.lib().bpp_ctx_host_ms(self.h, arr))
+        return dict(zip(self.HOST_PHASES, [float(x) for x in arr]))
+
     def set_host_threads(self, n):
         _chk(self, _ffi.lib().bpp_ctx_set_host_threads(self.h, n))
 

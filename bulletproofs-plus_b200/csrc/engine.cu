@@ -119,6 +119,13 @@ int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms9) {
     }
     return BPP_OK;
 }
+// wall-clock milliseconds of the host phases of the last bpp_vbatch_create on this ctx:
+// 0 parse + statement checks, 1 transcript replay (loop 1), 2 weight transcripts, 3 layout, 4 blob fill (+ nonces), 5 H2D + sync
+int32_t bpp_ctx_host_ms(bpp_ctx *ctx, double *ms6) {
+    if (!ctx || !ms6) return BPP_INVALID_ARGUMENT;
+    for (int i = 0; i < 6; i++) ms6[i] = ctx->host_ms[i];
+    return BPP_OK;
+}
 int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n) {
     if (!ctx || n < 1) return BPP_INVALID_ARGUMENT;
     ctx->host_threads = n;

@@ -52,6 +52,7 @@ struct bpp_ctx {
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
+    double host_ms[8] = {};             // wall-clock breakdown of the last bpp_vbatch_create (see bpp_ctx_host_ms)
     bpp::HostPool *pool = nullptr;      // lazily created with host_threads workers
     bpp::HostPool &workers() {
         if (!pool || pool->size() != host_threads) { delete pool; pool = new bpp::HostPool(host_threads); }

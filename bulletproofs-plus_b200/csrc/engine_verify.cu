@@ -8,6 +8,7 @@
 // Error precedence of the reference is reproduced when the per-chunk status is resolved after the device returns.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <thread>
 #include "engine.hpp"
@@ -197,6 +198,13 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     if (a->n_proofs >= (1u << 24)) return fail(ctx, BPP_SIZE_OVERFLOW, "too many proofs in one call");
     cudaSetDevice(ctx->device);
 
+    auto t_prev = std::chrono::steady_clock::now();
+    int t_slot = 0;
+    auto lap = [&]() {
+        auto now = std::chrono::steady_clock::now();
+        ctx->host_ms[t_slot++] = std::chrono::duration<double, std::milli>(now - t_prev).count();
+        t_prev = now;
+    };
     bpp_vbatch *vb = new bpp_vbatch();
     vb->g = g; vb->action = a->action; vb->n_proofs = a->n_proofs; vb->n_chunks = a->n_chunks;
     vb->chunk_offsets.assign(a->chunk_offsets, a->chunk_offsets + a->n_chunks + 1);
@@ -247,6 +255,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
             for (size_t i = hc.lo; i < hc.hi; i++) work.push_back(i);
     }
 
+    lap();
     // ---- loop 1: transcript replay (parallel over proofs), then the sequential weight transcript per chunk
     for (size_t i : work) memcpy(vb->hp[i].tstate, a->transcripts + BPP_TRANSCRIPT_BYTES * i, BPP_TRANSCRIPT_BYTES);
     ctx->workers().run(work.size(), 8, [&](size_t k) {
@@ -255,6 +264,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         p.loop1_rc = replay_transcript(g, p, a->commitments32 + 32 * a->commit_offsets[i], a->min_values + a->commit_offsets[i],
                                        a->min_present + a->commit_offsets[i]);
     });
+    lap();
     ctx->workers().run(a->n_chunks, 1, [&](size_t c) {
         HChunk &hc = vb->hc[c];
         if (hc.pre_rc) return;
@@ -289,6 +299,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         hc.max_mn = max_mn;
     });
 
+    lap();
     // ---- device layout, pass 1: sizes and offsets
     const uint32_t GEN = 0x80000000u;
     uint32_t n_pts = 0, n_entries = 0, total_vec = 0, contrib = 0, pv = 0, max_static = 0, n_pscal = 0, n_chal = 0, n_nonce = 0;
@@ -381,6 +392,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     ok(w->d_ident.ensure(a->n_chunks));
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch buffers"); }
 
+    lap();
     // ---- pass 2: fill the pinned blob (parallel over proofs), then ONE H2D copy
     uint8_t *hb = w->h_blob.as<uint8_t>();
     uint32_t *vecoff = (uint32_t *)(hb + vb->o_vecoff), *segoff = (uint32_t *)(hb + vb->o_segoff), *pidx = (uint32_t *)(hb + vb->o_pidx);
@@ -439,10 +451,12 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
             for (uint32_t j = 0; j < 2 * R + p.m; j++) px[3 + j] = p.pt_off + 3 + j;
         }
     });
+    lap();
     cudaStream_t st = ctx->stream;
     if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the pinned blob is reused by the next create on this ctx
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
+    lap();
     *out = vb;
     return BPP_OK;
 }

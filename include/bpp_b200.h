@@ -65,6 +65,9 @@ int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms);
  *        MSM Horner, encode/identity} */
 int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable);
 int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms9);
+/* wall-clock milliseconds of the host phases of the last bpp_vbatch_create / bpp_verify_chunks on this ctx:
+ * ms6 = {parse + statement checks, transcript replay, weight transcripts, layout, blob fill, H2D + sync} */
+int32_t bpp_ctx_host_ms(bpp_ctx *ctx, double *ms6);
 /* host threads used for the Fiat-Shamir replay of bpp_verify_chunks (default: min(64, hardware threads); the
  * reference is single-threaded, the harness supplies parallelism -- see BASELINE.md) */
 int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);

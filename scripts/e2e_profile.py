@@ -32,4 +32,5 @@ for threads in (16, 8, 4, 1):
         t3 = time.perf_counter()
         if it >= 3:
             tc += t1 - t0; tr += t2 - t1; td += t3 - t2
+    print("   host phases (last call):", {k: round(v, 3) for k, v in eng.host_ms().items()})
     print("threads=%2d  create %.3f ms  run %.3f ms  destroy %.3f ms" % (threads, tc / 5 * 1e3, tr / 5 * 1e3, td / 5 * 1e3))

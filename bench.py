@@ -149,6 +149,7 @@ def workload_config(args):
     return {"workload": "verify_batch of %d non-aggregated 64-bit proofs (aggregation 1, extension degree 1, minimum-value promises) "
                         "per GPU per step, as %d reference calls of <=256 (BASELINE.json configs[1])" % (args.proofs, (args.proofs + CHUNK - 1) // CHUNK),
             "proofs_per_step_per_gpu": args.proofs, "bit_length": BIT_LENGTH, "extension_degree": EXT, "action": "VerifyOnly",
+            "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay)",
             "l2": "flushed between timed steps (256 MiB device memset outside the per-step CUDA-event brackets)"}
 
 
@@ -245,11 +246,14 @@ def run_b200(args, rank, local_rank, world):
         e2e_step()
     barrier()
     e2e_s = 0.0
+    host_acc = {}
     for _ in range(args.steps):
         l2_flush()
         t0 = time.perf_counter()
         e2e_step()                                           # synchronous: returns after the D2H of the verdicts
         e2e_s += time.perf_counter() - t0
+        for k, v in eng.host_ms().items():
+            host_acc[k] = host_acc.get(k, 0.0) + v / args.steps
     barrier()
 
     # ---------------- reduce over ranks (max time)
@@ -265,10 +269,15 @@ def run_b200(args, rank, local_rank, world):
         entries = n_chunks * (2 * BIT_LENGTH + EXT + 1) + args.proofs * (3 + 2 * 6 + 1)
         per_launch = {k: v / args.steps for k, v in phase_acc.items()}
         dominant = max(per_launch, key=per_launch.get)
-        work = {"decompress": n_pts * MUL32_DECODE}
         peak_ops, _ = eng.microbench(2, 2000)              # IMAD.WIDE (32x32+64 -> 64) issue rate, measured now on this GPU
-        W = 28                                             # c = 9 -> ceil(252 / 9) windows for 4226-entry segments
-        work["msm_bucket"] = entries * W * MUL32_MADD
+        c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
+        work = {"decompress": n_pts * MUL32_DECODE,
+                "msm_bucket": entries * W * MUL32_MADD,
+                "msm_reduce": n_chunks * W * 2 * B * 9 * MUL32_FE_MUL,
+                "msm_combine": n_chunks * (W - 1) * (c_bits * (4 * MUL32_FE_MUL + 4 * MUL32_FE_SQ) + 9 * MUL32_FE_MUL),
+                "vprep_proof": args.proofs * (130 + 380) * 100,    # ~130 scalar products + one inversion (~380 at a^(l-2) cost), 100 mul32 each
+                "vprep_vector": args.proofs * BIT_LENGTH * (3 * 6 + 8) * 100,
+                "vprep_weigh": (entries + args.proofs * 2 * BIT_LENGTH) * 100}
         alg = work.get(dominant)
         roof = {"bound": "int32-multiply (IMAD.WIDE issue rate; the path is modular big-integer arithmetic, neither HBM- nor tensor-bound)",
                 "kernel": dominant, "unit": "Tmul32/s", "peak": peak_ops / 1e12,
@@ -313,7 +322,8 @@ def run_b200(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": world * args.proofs * args.steps / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads_fiat_shamir": min(64, threads)},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads": min(64, threads),
+                    "host_ms_per_step": {k: round(v, 4) for k, v in host_acc.items()}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
         }

@@ -71,14 +71,19 @@ class Engine:
     def phase_timing(self, enable):
         _chk(self, _ffi.lib().bpp_ctx_phase_timing(self.h, 1 if enable else 0))
 
-    PHASES = ("decompress", "vprep_proof", "vprep_vector", "vprep_reduce", "msm_sort", "msm_bucket", "msm_reduce", "msm_combine", "encode")
+    PHASES = ("replay", "decompress", "vprep_proof", "vprep_vector", "host_weights_wait", "vprep_weigh", "msm_sort", "msm_bucket",
+              "msm_reduce", "msm_combine", "encode")
 
     def phase_ms(self):
-        arr = (C.c_float * 9)()
+        arr = (C.c_float * 11)()
         _chk(self, _ffi.lib().bpp_ctx_phase_ms(self.h, arr))
         return dict(zip(self.PHASES, [float(x) for x in arr]))
 
-    HOST_PHASES = ("parse", "replay", "weights", "layout", "fill", "h2d")
+    HOST_PHASES = ("parse", "layout", "fill_replay", "weights", "h2d", "run_wall")
+
+    def set_replay_mode(self, on_device):
+        """loop 1 (transcript replay) on the device (default) or on host threads"""
+        _chk(self, _ffi.lib().bpp_ctx_set_replay_mode(self.h, 1 if on_device else 0))
 
     def host_ms(self):
         arr = (C.c_double * 6)()

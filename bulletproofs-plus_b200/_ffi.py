@@ -100,7 +100,9 @@ def lib():
         "bpp_verify_chunks": (i32, [vp, P(VerifyArgs), vp, vp, vp]),
         "bpp_vbatch_create": (i32, [vp, P(VerifyArgs), P(vp)]),
         "bpp_vbatch_run": (i32, [vp, vp, vp, vp]),
+        "bpp_vbatch_transcripts": (i32, [vp, vp]),
         "bpp_vbatch_destroy": (None, [vp]),
+        "bpp_ctx_set_replay_mode": (i32, [vp, i32]),
         "bpp_proof_check_bytes": (i32, [cp, sz, P(i32), P(i32)]),
         "bpp_transcript_new": (None, [cp, sz, cp]),
         "bpp_transcript_append_message": (None, [cp, cp, sz, cp, sz]),

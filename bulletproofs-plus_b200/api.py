@@ -349,6 +349,7 @@ class VerifyBatch:
     def run(self):
         pk = self.pk
         _chk(self.params.gens.engine, _ffi.lib().bpp_vbatch_run(self.h, pk.status, pk.masks, pk.mask_present))
+        _chk(self.params.gens.engine, _ffi.lib().bpp_vbatch_transcripts(self.h, C.addressof(pk.tbuf)))
         return pk.results()
 
     def close(self):

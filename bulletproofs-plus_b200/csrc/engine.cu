@@ -48,12 +48,14 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPP_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream); delete ctx; return BPP_ERR_CUDA;
     }
     unsigned hc = std::thread::hardware_concurrency();
     ctx->host_threads = hc ? (int)(hc > 64 ? 64 : hc) : 1;
     if (const char *env = getenv("BPP_HOST_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 1024) ctx->host_threads = v; }
+    if (const char *env = getenv("BPP_HOST_REPLAY")) ctx->device_replay = atoi(env) == 0;
     *out = ctx;
     return BPP_OK;
 }
@@ -68,7 +70,7 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
     for (int i = 0; i < bpp_ctx::N_MARKS; i++) if (ctx->ph[i]) cudaEventDestroy(ctx->ph[i]);
     cudaStreamSynchronize(ctx->stream2);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_mid);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -106,21 +108,28 @@ int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable) {
     ctx->clear_marks();
     return BPP_OK;
 }
-// ms9[i] = time between mark i and mark i+1 of the last vbatch / plan run (0 where a mark was not reached):
-// 0 decompress, 1 verifier prep per proof, 2 per (proof, i), 3 column sums, 4 MSM sort (digits+scan+scatter), 5 MSM bucket sums,
-// 6 MSM window reduction, 7 MSM Horner combine, 8 encode / identity test
-int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms9) {
-    if (!ctx || !ms9) return BPP_INVALID_ARGUMENT;
+// ms11[i] = time between mark i and mark i+1 of the last vbatch / plan run (0 where a mark was not reached):
+// 0 transcript replay (+ D2H of its results), 1 decompress, 2 verifier prep per proof, 3 per (proof, i), 4 wait for the host
+// weight transcripts (device idle), 5 weighting + column sums, 6 MSM sort (digits+scan+scatter), 7 MSM bucket sums,
+// 8 MSM window reduction, 9 MSM Horner combine, 10 encode / identity test
+int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms11) {
+    if (!ctx || !ms11) return BPP_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i + 1 < bpp_ctx::N_MARKS; i++) {
-        ms9[i] = 0.f;
-        if (ctx->ph_set[i] && ctx->ph_set[i + 1]) BPP_CUDA(ctx, cudaEventElapsedTime(&ms9[i], ctx->ph[i], ctx->ph[i + 1]));
+        ms11[i] = 0.f;
+        if (ctx->ph_set[i] && ctx->ph_set[i + 1]) BPP_CUDA(ctx, cudaEventElapsedTime(&ms11[i], ctx->ph[i], ctx->ph[i + 1]));
     }
     return BPP_OK;
 }
+int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    ctx->device_replay = on_device != 0;
+    return BPP_OK;
+}
 // wall-clock milliseconds of the host phases of the last bpp_vbatch_create on this ctx:
-// 0 parse + statement checks, 1 transcript replay (loop 1), 2 weight transcripts, 3 layout, 4 blob fill (+ nonces), 5 H2D + sync
+// 0 parse + statement checks, 1 layout + buffers, 2 blob fill (+ loop-1 replay in host mode), 3 weight transcripts (host mode),
+// 4 H2D + sync, 5 unused
 int32_t bpp_ctx_host_ms(bpp_ctx *ctx, double *ms6) {
     if (!ctx || !ms6) return BPP_INVALID_ARGUMENT;
     for (int i = 0; i < 6; i++) ms6[i] = ctx->host_ms[i];
@@ -276,14 +285,14 @@ int32_t bpp_msm_plan_run(bpp_msm_plan *pl, uint8_t *out32_or_null) {
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     ctx->clear_marks();
-    ctx->mark(4);
+    ctx->mark(6);
     launch_msm(st, pl->sh, pl->d_scalars.as<uint32_t>(), nullptr, nullptr, pl->d_tab.as<aniels>(), nullptr, pl->d_scratch.p,
-               pl->d_res.as<ge>(), &ctx->launches, ctx->phase_timing ? &ctx->ph[5] : nullptr);
-    if (ctx->phase_timing) for (int i = 5; i <= 8; i++) ctx->ph_set[i] = true;
+               pl->d_res.as<ge>(), &ctx->launches, ctx->phase_timing ? &ctx->ph[7] : nullptr);
+    if (ctx->phase_timing) for (int i = 7; i <= 10; i++) ctx->ph_set[i] = true;
     BPP_CUDA(ctx, cudaGetLastError());
     if (out32_or_null) {
         launch_encode(st, 1, pl->d_res.as<ge>(), pl->d_out.as<uint32_t>(), nullptr);
-        ctx->mark(9);
+        ctx->mark(11);
         ctx->launches++;
         BPP_CUDA(ctx, cudaMemcpyAsync(out32_or_null, pl->d_out.p, 32, cudaMemcpyDeviceToHost, st));
         BPP_CUDA(ctx, cudaStreamSynchronize(st));

@@ -48,7 +48,8 @@ struct bpp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // side stream: point decompression overlaps the scalar prep chain
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
+    bool device_replay = true;          // loop 1 (transcript replay) on the device (k_replay.cu) or on host threads
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
@@ -61,7 +62,9 @@ struct bpp_ctx {
     // measurement: wall timer and per-phase marks on `stream` (bench.py)
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool phase_timing = false;
-    static constexpr int N_MARKS = 10;   // 9 phases: decompress, vprep_proof, vprep_vector, vprep_reduce, msm sort/bucket/reduce/combine, encode
+    // 11 phases between 12 marks: replay, decompress, vprep_proof, vprep_vector, (host weight transcripts: device idle),
+    // vprep_weigh, msm sort / bucket / reduce / combine, encode
+    static constexpr int N_MARKS = 12;
     cudaEvent_t ph[N_MARKS] = {};
     bool ph_set[N_MARKS] = {};
     void mark(int i) { if (phase_timing && ph[i]) { cudaEventRecord(ph[i], stream); ph_set[i] = true; } }

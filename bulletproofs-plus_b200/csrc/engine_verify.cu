@@ -1,18 +1,25 @@
-// Batch verification entry points: bpp_vbatch_create / bpp_vbatch_run / bpp_verify_chunks.
+// Batch verification entry points: bpp_vbatch_create / bpp_vbatch_run / bpp_vbatch_transcripts / bpp_verify_chunks.
 //
-// Host side restates the control flow of RangeProof::verify_batch -> verify
-// (/root/reference/src/range_proof.rs:712-1065): argument checks (:719-734), first-256 truncation (:739-751), consistency
-// (:610-709), loop 1 = Fiat-Shamir replay of every proof's transcript + the verifier weight transcript (:811-853),
-// then hands loop 2 (:856-1033) and the single merged multiscalar check (:1039-1062) to the device:
-//   K-DECOMPRESS (k_point.cu) -> K-VPREP (k_verify.cu) -> K-MSM segmented by reference call (k_msm.cu) -> identity test.
-// Error precedence of the reference is reproduced when the per-chunk status is resolved after the device returns.
+// Restates the control flow of RangeProof::verify_batch -> verify (/root/reference/src/range_proof.rs:712-1065):
+// argument checks (:719-734), first-256 truncation (:739-751), consistency (:610-709), loop 1 = Fiat-Shamir replay of every
+// proof's transcript (:816-850), the sequential verifier-weight transcript (:811, :849-853, :894), loop 2 (:856-1033) and the
+// single merged multiscalar check (:1039-1062).  Device pipeline of one call (K chunks = K reference calls):
+//
+//   stream A:  [K-REPLAY]  ->  K-VPREP A, B (weight-free)  ................  K-VPREP W, C  ->  K-MSM (segmented)  ->  identity test
+//   stream B:  K-DECOMPRESS ...........................................................^ (joins before the bucket sums)
+//   host    :  (wbytes D2H) -> weight transcripts per chunk, in parallel -> weights H2D ^
+//
+// Loop 1 runs on the device by default (k_replay.cu); `bpp_ctx_set_replay_mode(ctx, 0)` keeps it on host threads, which is
+// the split BASELINE.json's north_star describes; both produce bit-identical results (tests run both).  The weight
+// transcript is inherently sequential (one Keccak-f per weight) and stays on the host in both modes, overlapped with the
+// weight-free part of the scalar prep.  Error precedence of the reference is reproduced when the per-chunk status is
+// resolved after the device returns.
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <cstring>
-#include <thread>
 #include "engine.hpp"
 #include "hash.cuh"
+#include "replay.cuh"
 
 using namespace bpp;
 
@@ -20,19 +27,13 @@ namespace {
 
 struct HProof {
     int32_t pre_rc = 0;        // from_bytes / RangeStatement::init class errors
-    int32_t loop1_rc = 0;      // transcript replay (VerificationFailed)
-    int32_t loop2_rc = 0;      // host-known loop-2 errors (InvalidLength on rounds, y == 1)
+    int32_t loop2_rc = 0;      // host-known loop-2 error: InvalidLength when 2^rounds != n*m (:886-888)
     int ext = 0, rounds = 0;
     uint32_t m = 0;
     const uint8_t *bytes = nullptr;   // serialised proof
     bool has_seed = false;
     uint8_t seed[32];
     uint32_t pt_off = 0, n_pts = 0;   // slots in the point table: [A, A1, B, L.., R.., V..]
-    uint8_t y[32], z[32], e[32];
-    uint8_t ej[BPP_MAX_ROUNDS][32];
-    uint8_t wbytes[32];               // 32 bytes drawn from the proof's verifier rng -> weight transcript
-    uint8_t weight[32];
-    uint8_t tstate[BPP_TRANSCRIPT_BYTES];
     const uint8_t *d1() const { return bytes + 1; }
     const uint8_t *a() const { return bytes + 1 + 32 * ext; }
     const uint8_t *a1() const { return a() + 32; }
@@ -46,73 +47,13 @@ struct HProof {
 struct HChunk {
     size_t lo = 0, hi = 0;     // proofs looked at: [lo, hi) (hi - lo <= 256)
     int32_t pre_rc = 0;        // empty batch / from_bytes / statement / consistency errors
-    int32_t loop1_rc = 0;
     bool computable = false;   // no host-known error: device prep + MSM (or mask recovery) runs
     uint32_t max_mn = 0;
     uint32_t entry_off = 0, n_entries = 0;
 };
 
-inline bool is_zero32(const uint8_t *p) {
-    uint8_t r = 0;
-    for (int i = 0; i < 32; i++) r |= p[i];
-    return r == 0;
-}
-#define LBL(s) (const uint8_t *)(s), (sizeof(s) - 1)
-
-// protocols/transcript_protocol.rs:67-78
-inline int32_t challenge_scalar(Merlin &t, const uint8_t *label, size_t ll, uint8_t out32[32]) {
-    uint8_t buf[64];
-    t.challenge_bytes(label, ll, buf, 64);
-    host_sc_from_wide(buf, out32);
-    return is_zero32(out32) ? BPP_VERIFICATION_FAILED : BPP_OK;
-}
-// protocols/transcript_protocol.rs:49-61
-inline int32_t validate_and_append_point(Merlin &t, const uint8_t *label, size_t ll, const uint8_t pt[32]) {
-    if (is_zero32(pt)) return BPP_VERIFICATION_FAILED;
-    t.append_message(label, ll, pt, 32);
-    return BPP_OK;
-}
-
-// Loop 1 body for one proof: RangeProofTranscript::new (transcripts.rs:59-121), challenges_y_z (:124-136),
-// challenge_round_e (:139-149), challenge_final_e (:152-162), to_verifier_rng (:166-179) + 32 rng bytes.
-int32_t replay_transcript(const bpp_gens *g, HProof &p, const uint8_t *commitments32, const uint64_t *min_values,
-                          const uint8_t *min_present) {
-    Merlin t;
-    t.s.load(p.tstate);
-    int32_t rc = BPP_OK;
-    t.append_message(LBL("dom-sep"), LBL("Bulletproofs+ Range Proof"));
-    do {
-        if ((rc = validate_and_append_point(t, LBL("H"), g->h()))) break;
-        for (int k = 0; k < g->ext && !rc; k++) rc = validate_and_append_point(t, LBL("G"), g->g(k));
-        if (rc) break;
-        t.append_u64(LBL("N"), (uint64_t)g->n);
-        t.append_u64(LBL("T"), (uint64_t)g->ext);
-        t.append_u64(LBL("M"), (uint64_t)p.m);
-        for (uint32_t j = 0; j < p.m; j++) t.append_message(LBL("Ci"), commitments32 + 32 * j, 32);
-        for (uint32_t j = 0; j < p.m; j++) t.append_u64(LBL("vi - minimum_value"), min_present[j] ? min_values[j] : 0);
-        if ((rc = validate_and_append_point(t, LBL("A"), p.a()))) break;
-        if ((rc = challenge_scalar(t, LBL("y"), p.y))) break;
-        if ((rc = challenge_scalar(t, LBL("z"), p.z))) break;
-        for (int j = 0; j < p.rounds && !rc; j++) {
-            if ((rc = validate_and_append_point(t, LBL("L"), p.li(j)))) break;
-            if ((rc = validate_and_append_point(t, LBL("R"), p.ri(j)))) break;
-            rc = challenge_scalar(t, LBL("e"), p.ej[j]);
-        }
-        if (rc) break;
-        if ((rc = validate_and_append_point(t, LBL("A1"), p.a1()))) break;
-        if ((rc = validate_and_append_point(t, LBL("B"), p.b()))) break;
-        if ((rc = challenge_scalar(t, LBL("e"), p.e))) break;
-        t.append_message(LBL("r1"), p.r1(), 32);
-        t.append_message(LBL("s1"), p.s1(), 32);
-        for (int k = 0; k < p.ext; k++) t.append_message(LBL("d1"), p.d1() + 32 * k, 32);
-        MerlinRng rng;
-        const uint8_t zeros[32] = {0};
-        rng.build(t, nullptr, 0, false, zeros);     // NullRng, utils/nullrng.rs
-        rng.fill(p.wbytes, 32);
-    } while (0);
-    t.s.store(p.tstate);
-    return rc;
-}
+inline bool is_zero32(const uint8_t *p) { return replay_is_zero32(p); }
+#define LBL(s) BPP_LBL(s)
 
 // utils/generic.rs:30-60
 void nonce(const uint8_t seed[32], const char *label, bool have_j, uint32_t j, bool have_k, uint32_t k, uint8_t out32[32]) {
@@ -132,30 +73,40 @@ void nonce(const uint8_t seed[32], const char *label, bool have_j, uint32_t j, b
 // device + pinned buffers of one verification pass; pooled per ctx so that repeated calls do not pay cudaMalloc /
 // cudaMallocHost / cudaFree every time (grow-only, returned to the pool by bpp_vbatch_destroy)
 struct VWork {
-    DevBuf d_blob, d_tab, d_ok, d_mscal, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident;
-    PinBuf h_blob, h_out;
+    DevBuf d_blob, d_tab, d_ok, d_mscal, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident, d_weights, d_wmont, d_mid;
+    PinBuf h_blob, h_out, h_mid, h_weights;
     void release() {
-        for (DevBuf *b : {&d_blob, &d_tab, &d_ok, &d_mscal, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident}) b->release();
-        h_blob.release(); h_out.release();
+        for (DevBuf *b : {&d_blob, &d_tab, &d_ok, &d_mscal, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident, &d_weights,
+                          &d_wmont, &d_mid})
+            b->release();
+        h_blob.release(); h_out.release(); h_mid.release(); h_weights.release();
     }
 };
 
 struct bpp_vbatch {
     bpp_gens *g = nullptr;
     int32_t action = BPP_VERIFY_ONLY;
+    bool device_replay = true;
     size_t n_proofs = 0, n_chunks = 0;
     std::vector<HProof> hp;
     std::vector<HChunk> hc;
     std::vector<uint64_t> chunk_offsets;
     uint32_t n_pts = 0, n_entries = 0, total_vec = 0, max_static = 0;
-    bool any_msm = false, any_masks = false;
+    bool any_msm = false, any_masks = false, any_replay = false;
+    bool ran = false;
     MsmShape shape;
     VWork *w = nullptr;
     // all inputs travel as ONE pinned blob -> ONE H2D copy; these are the section offsets inside it
-    size_t o_enc = 0, o_proofs = 0, o_chunks = 0, o_vecoff = 0, o_pscal = 0, o_chal = 0, o_weights = 0, o_minv = 0, o_minp = 0,
-           o_nonces = 0, o_pidx = 0, o_segoff = 0, blob_bytes = 0;
+    size_t o_enc = 0, o_proofs = 0, o_chunks = 0, o_vecoff = 0, o_pscal = 0, o_chal = 0, o_minv = 0, o_minp = 0, o_nonces = 0, o_pidx = 0,
+           o_segoff = 0, o_tstate = 0, o_hg = 0, blob_bytes = 0;
+    // mid-pipeline results of loop 1: [wbytes n x 32 | flags n | tstates n x 203]; same layout on device and host
+    size_t mo_wbytes = 0, mo_flags = 0, mo_tstate = 0, mid_bytes = 0;
     size_t ho_ok = 0, ho_ident = 0, ho_masks = 0, hout_bytes = 0;
     template <class T> T *dev(size_t off) const { return reinterpret_cast<T *>(w->d_blob.as<uint8_t>() + off); }
+    uint8_t *mid() const { return w->h_mid.as<uint8_t>(); }
+    uint8_t *wbytes(size_t i) const { return mid() + mo_wbytes + 32 * i; }
+    uint8_t &flag(size_t i) const { return mid()[mo_flags + i]; }
+    uint8_t *tstate(size_t i) const { return mid() + mo_tstate + BPP_TRANSCRIPT_BYTES * i; }
 };
 
 namespace bpp {
@@ -171,6 +122,29 @@ static VWork *vwork_acquire(bpp_ctx *ctx) {
 static void vwork_return(bpp_ctx *ctx, VWork *w) {
     if (ctx->vwork_pool.size() < 4) ctx->vwork_pool.push_back(w);
     else { w->release(); delete w; }
+}
+
+// Sequential part of loop 1 + the weight draw of loop 2 for every chunk (parallel over chunks): the verifier-weight
+// transcript (range_proof.rs:811, :849, :853) and random_not_zero per proof (:894).  Needs wbytes / flags of all proofs.
+static void compute_weights(bpp_vbatch *vb) {
+    bpp_ctx *ctx = vb->g->ctx;
+    uint8_t *wts = vb->w->h_weights.as<uint8_t>();
+    ctx->workers().run(vb->n_chunks, 1, [&](size_t c) {
+        const HChunk &hc = vb->hc[c];
+        if (hc.pre_rc) return;
+        for (size_t i = hc.lo; i < hc.hi; i++)
+            if (vb->flag(i) & 1) return;                                                  // loop 1 failed: the call ends there
+        Merlin wt;
+        wt.init(LBL("Bulletproofs+ verifier weights"));                                   // :811
+        for (size_t i = hc.lo; i < hc.hi; i++) wt.append_message(LBL("proof"), vb->wbytes(i), 32);   // :849
+        MerlinRng wr;
+        const uint8_t zeros[32] = {0};
+        wr.build(wt, nullptr, 0, false, zeros);                                           // :853
+        for (size_t i = hc.lo; i < hc.hi; i++) {
+            uint8_t wide[64], *wgt = wts + 32 * i;
+            do { wr.fill(wide, 64); host_sc_from_wide(wide, wgt); } while (is_zero32(wgt));   // :894 random_not_zero
+        }
+    });
 }
 
 extern "C" {
@@ -200,6 +174,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
 
     auto t_prev = std::chrono::steady_clock::now();
     int t_slot = 0;
+    for (double &x : ctx->host_ms) x = 0;
     auto lap = [&]() {
         auto now = std::chrono::steady_clock::now();
         ctx->host_ms[t_slot++] = std::chrono::duration<double, std::milli>(now - t_prev).count();
@@ -207,102 +182,75 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     };
     bpp_vbatch *vb = new bpp_vbatch();
     vb->g = g; vb->action = a->action; vb->n_proofs = a->n_proofs; vb->n_chunks = a->n_chunks;
+    vb->device_replay = ctx->device_replay;
     vb->chunk_offsets.assign(a->chunk_offsets, a->chunk_offsets + a->n_chunks + 1);
     vb->hp.resize(a->n_proofs);
     vb->hc.resize(a->n_chunks);
     const int n = g->n, ext = g->ext;
     const bool want_masks = a->action != BPP_VERIFY_ONLY;
 
-    // ---- per-proof parsing + statement checks; per-chunk consistency
-    std::vector<size_t> work;     // proofs whose transcripts are replayed
+    // ---- per-proof parsing + statement checks (parallel), then per-chunk consistency
     for (size_t c = 0; c < a->n_chunks; c++) {
         HChunk &hc = vb->hc[c];
         hc.lo = a->chunk_offsets[c];
         hc.hi = std::min<size_t>(a->chunk_offsets[c + 1], hc.lo + BPP_MAX_BATCH);       // range_proof.rs:739-751
-        if (hc.hi == hc.lo) { hc.pre_rc = BPP_INVALID_ARGUMENT; continue; }               // :719-723
+        if (hc.hi == hc.lo) hc.pre_rc = BPP_INVALID_ARGUMENT;                             // :719-723
+    }
+    std::vector<uint8_t> looked(a->n_proofs, 0);
+    for (const HChunk &hc : vb->hc)
+        for (size_t i = hc.lo; i < hc.hi; i++) looked[i] = 1;
+    ctx->workers().run(a->n_proofs, 64, [&](size_t i) {
+        if (!looked[i]) return;
+        HProof &p = vb->hp[i];
+        size_t plen = a->proof_offsets[i + 1] - a->proof_offsets[i];
+        p.bytes = a->proof_bytes + a->proof_offsets[i];
+        int32_t pext = 0, rounds = 0;
+        p.pre_rc = bpp_proof_check_bytes(p.bytes, plen, &pext, &rounds);                // RangeProof::from_bytes
+        p.ext = pext; p.rounds = rounds;
+        uint64_t m64 = a->commit_offsets[i + 1] - a->commit_offsets[i];
+        p.m = (uint32_t)m64;
+        p.has_seed = a->seed_present && a->seed_nonces32 && a->seed_present[i];
+        if (!p.pre_rc) {                                                                 // RangeStatement::init, range_statement.rs:42-61
+            if (m64 == 0 || (m64 & (m64 - 1)) || m64 > (uint64_t)g->M) p.pre_rc = BPP_INVALID_ARGUMENT;
+            else if (p.has_seed && m64 > 1) p.pre_rc = BPP_INVALID_ARGUMENT;
+        }
+        if (p.pre_rc) return;
+        if (p.has_seed) {
+            uint32_t w[8];
+            memcpy(w, a->seed_nonces32 + 32 * i, 32);
+            sc s; for (int k = 0; k < 8; k++) s.v[k] = w[k];
+            sc_tobytes(p.seed, sc_reduce256(s));
+        }
+        uint64_t N = (uint64_t)p.m * (uint64_t)n;
+        if (p.rounds >= 32 || (1ull << p.rounds) != N) p.loop2_rc = BPP_INVALID_LENGTH;  // :886-888
+    });
+    for (size_t c = 0; c < a->n_chunks; c++) {
+        HChunk &hc = vb->hc[c];
+        if (hc.pre_rc) continue;
         int32_t ext_rc = 0, promise_rc = 0;
+        bool rounds_ok = true;
+        uint32_t max_mn = 0;
         for (size_t i = hc.lo; i < hc.hi; i++) {
-            HProof &p = vb->hp[i];
-            size_t plen = a->proof_offsets[i + 1] - a->proof_offsets[i];
-            p.bytes = a->proof_bytes + a->proof_offsets[i];
-            int32_t pext = 0, rounds = 0;
-            p.pre_rc = bpp_proof_check_bytes(p.bytes, plen, &pext, &rounds);            // RangeProof::from_bytes
-            p.ext = pext; p.rounds = rounds;
-            uint64_t m64 = a->commit_offsets[i + 1] - a->commit_offsets[i];
-            p.m = (uint32_t)m64;
-            p.has_seed = a->seed_present && a->seed_nonces32 && a->seed_present[i];
-            if (!p.pre_rc) {                                                             // RangeStatement::init, range_statement.rs:42-61
-                if (m64 == 0 || (m64 & (m64 - 1)) || m64 > (uint64_t)g->M) p.pre_rc = BPP_INVALID_ARGUMENT;
-                else if (p.has_seed && m64 > 1) p.pre_rc = BPP_INVALID_ARGUMENT;
-            }
-            if (p.pre_rc && !hc.pre_rc) hc.pre_rc = p.pre_rc;
-            if (p.pre_rc) continue;
-            if (p.has_seed) {
-                uint32_t w[8];
-                memcpy(w, a->seed_nonces32 + 32 * i, 32);
-                sc s; for (int k = 0; k < 8; k++) s.v[k] = w[k];
-                sc_tobytes(p.seed, sc_reduce256(s));
-            }
+            const HProof &p = vb->hp[i];
+            if (p.pre_rc) { if (!hc.pre_rc) hc.pre_rc = p.pre_rc; continue; }
             if (p.ext != ext && !ext_rc) ext_rc = BPP_INVALID_ARGUMENT;                  // :637-660
             if (n < 64)
                 for (uint32_t j = 0; j < p.m; j++) {
                     size_t ci = a->commit_offsets[i] + j;
                     if (a->min_present[ci] && (a->min_values[ci] >> n) > 0 && !promise_rc) promise_rc = BPP_INVALID_LENGTH;   // :675-682
                 }
+            if (p.loop2_rc) rounds_ok = false;
+            max_mn = std::max<uint32_t>(max_mn, p.m * (uint32_t)n);
         }
         if (!hc.pre_rc) hc.pre_rc = ext_rc ? ext_rc : promise_rc;
-        if (!hc.pre_rc)
-            for (size_t i = hc.lo; i < hc.hi; i++) work.push_back(i);
-    }
-
-    lap();
-    // ---- loop 1: transcript replay (parallel over proofs), then the sequential weight transcript per chunk
-    for (size_t i : work) memcpy(vb->hp[i].tstate, a->transcripts + BPP_TRANSCRIPT_BYTES * i, BPP_TRANSCRIPT_BYTES);
-    ctx->workers().run(work.size(), 8, [&](size_t k) {
-        size_t i = work[k];
-        HProof &p = vb->hp[i];
-        p.loop1_rc = replay_transcript(g, p, a->commitments32 + 32 * a->commit_offsets[i], a->min_values + a->commit_offsets[i],
-                                       a->min_present + a->commit_offsets[i]);
-    });
-    lap();
-    ctx->workers().run(a->n_chunks, 1, [&](size_t c) {
-        HChunk &hc = vb->hc[c];
-        if (hc.pre_rc) return;
-        size_t stop = hc.hi;
-        for (size_t i = hc.lo; i < hc.hi; i++)
-            if (vb->hp[i].loop1_rc) { hc.loop1_rc = vb->hp[i].loop1_rc; stop = i + 1; break; }
-        // `&mut Transcript` semantics: transcripts up to (and including) the failing one are advanced
-        for (size_t i = hc.lo; i < stop; i++) memcpy(a->transcripts + BPP_TRANSCRIPT_BYTES * i, vb->hp[i].tstate, BPP_TRANSCRIPT_BYTES);
-        if (hc.loop1_rc) return;
-        Merlin wt;
-        wt.init(LBL("Bulletproofs+ verifier weights"));                                   // :811
-        for (size_t i = hc.lo; i < hc.hi; i++) wt.append_message(LBL("proof"), vb->hp[i].wbytes, 32);   // :849
-        MerlinRng wr;
-        const uint8_t zeros[32] = {0};
-        wr.build(wt, nullptr, 0, false, zeros);                                           // :853
-        bool ok = true;
-        uint32_t max_mn = 0;
-        for (size_t i = hc.lo; i < hc.hi; i++) {
-            HProof &p = vb->hp[i];
-            uint8_t wide[64];
-            do { wr.fill(wide, 64); host_sc_from_wide(wide, p.weight); } while (is_zero32(p.weight));   // :894 random_not_zero
-            uint64_t N = (uint64_t)p.m * (uint64_t)n;
-            if (p.rounds >= 32 || (1ull << p.rounds) != N) p.loop2_rc = BPP_INVALID_LENGTH;            // :886-888
-            else {
-                uint8_t one[32] = {1};
-                if (!memcmp(p.y, one, 32)) p.loop2_rc = BPP_VERIFICATION_FAILED;                        // (y - 1) is not invertible
-            }
-            if (p.loop2_rc) ok = false;
-            max_mn = std::max<uint32_t>(max_mn, (uint32_t)N);
-        }
-        hc.computable = ok;
+        hc.computable = !hc.pre_rc && rounds_ok;
         hc.max_mn = max_mn;
-    });
+    }
+    lap();   // [0] parse
 
-    lap();
     // ---- device layout, pass 1: sizes and offsets
     const uint32_t GEN = 0x80000000u;
-    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, contrib = 0, pv = 0, max_static = 0, n_pscal = 0, n_chal = 0, n_nonce = 0;
+    uint32_t n_pts = 0, n_entries = 0, contrib = 0, pv = 0, max_static = 0, n_pscal = 0, n_chal = 0, n_nonce = 0;
     std::vector<VProof> dp(a->n_proofs);
     std::vector<VChunk> dc(a->n_chunks);
     for (size_t c = 0; c < a->n_chunks; c++) {
@@ -329,11 +277,15 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
             p.pt_off = n_pts;
             p.n_pts = 3 + 2 * (uint32_t)p.rounds + p.m;
             n_pts += p.n_pts;
-            if (!hc.computable) continue;
+            if (hc.pre_rc) continue;
+            // loop 1 runs over every proof of a call that passed the consistency checks (:816-850)
+            v.replay = 1; vb->any_replay = true;
+            v.pt_off = p.pt_off;
             v.m = p.m; v.rounds = (uint32_t)p.rounds;
             v.commit_off = (uint32_t)a->commit_offsets[i];
-            v.sc_off = n_pscal; n_pscal += 2 + (uint32_t)ext;
+            v.sc_off = n_pscal; n_pscal += 2 + (uint32_t)p.ext;
             v.ch_off = n_chal; n_chal += 3 + (uint32_t)p.rounds;
+            if (!hc.computable) continue;
             if (want_masks && p.has_seed) {
                 v.nonce_off = n_nonce; n_nonce += (uint32_t)ext * (3 + 2 * (uint32_t)p.rounds);
                 vb->any_masks = true;
@@ -358,15 +310,20 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     vb->o_vecoff = carve(4 * (a->n_proofs + 1));
     vb->o_pscal = carve(32 * (size_t)n_pscal);
     vb->o_chal = carve(32 * (size_t)n_chal);
-    vb->o_weights = carve(32 * a->n_proofs);
     vb->o_minv = carve(8 * n_commit);
     vb->o_minp = carve(n_commit);
     vb->o_nonces = carve(32 * (size_t)n_nonce);
     vb->o_pidx = carve(4 * (size_t)n_entries);
     vb->o_segoff = carve(4 * (a->n_chunks + 1));
+    vb->o_hg = carve(32 * ((size_t)ext + 1));
+    vb->o_tstate = carve(vb->device_replay ? BPP_TRANSCRIPT_BYTES * a->n_proofs : 0);
     vb->blob_bytes = off;
     vb->n_pts = n_pts; vb->n_entries = n_entries; vb->max_static = max_static;
     vb->shape = msm_shape(n_entries, (uint32_t)a->n_chunks, 0);
+    vb->mo_wbytes = 0;
+    vb->mo_flags = 32 * a->n_proofs;
+    vb->mo_tstate = (vb->mo_flags + a->n_proofs + 255) & ~(size_t)255;
+    vb->mid_bytes = vb->mo_tstate + BPP_TRANSCRIPT_BYTES * a->n_proofs;
     vb->ho_ok = 0;
     vb->ho_ident = (n_pts + 255) & ~(size_t)255;
     vb->ho_masks = vb->ho_ident + ((a->n_chunks + 255) & ~(size_t)255);
@@ -377,37 +334,47 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     vb->w = w;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    const size_t np1 = std::max<size_t>(a->n_proofs, 1);
     ok(w->h_blob.ensure(vb->blob_bytes));
     ok(w->d_blob.ensure(vb->blob_bytes));
     ok(w->h_out.ensure(vb->hout_bytes));
+    ok(w->h_mid.ensure(vb->mid_bytes + 256));
+    ok(w->d_mid.ensure(vb->mid_bytes + 256));
+    ok(w->h_weights.ensure(32 * np1));
+    ok(w->d_weights.ensure(32 * np1));
+    ok(w->d_wmont.ensure(32 * np1));
     ok(w->d_tab.ensure(sizeof(aniels) * std::max<size_t>(n_pts, 1)));
     ok(w->d_ok.ensure(std::max<size_t>(n_pts, 1)));
     ok(w->d_mscal.ensure(32 * std::max<size_t>(n_entries, 1)));
     ok(w->d_contrib.ensure(32 * std::max<size_t>(contrib, 1)));
-    ok(w->d_hg.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (1 + (size_t)ext)));
+    ok(w->d_hg.ensure(32 * np1 * (1 + (size_t)ext)));
     ok(w->d_pervec.ensure(32 * std::max<size_t>(pv, 1)));
-    ok(w->d_masks.ensure(32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext));
+    ok(w->d_masks.ensure(32 * np1 * (size_t)ext));
     ok(w->d_scratch.ensure(msm_scratch_bytes(vb->shape)));
     ok(w->d_res.ensure(sizeof(ge) * a->n_chunks));
     ok(w->d_ident.ensure(a->n_chunks));
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch buffers"); }
+    lap();   // [1] layout
 
-    lap();
-    // ---- pass 2: fill the pinned blob (parallel over proofs), then ONE H2D copy
+    // ---- pass 2: fill the pinned blob (parallel over proofs)
     uint8_t *hb = w->h_blob.as<uint8_t>();
     uint32_t *vecoff = (uint32_t *)(hb + vb->o_vecoff), *segoff = (uint32_t *)(hb + vb->o_segoff), *pidx = (uint32_t *)(hb + vb->o_pidx);
     {
         uint32_t run = 0;
         for (size_t i = 0; i < a->n_proofs; i++) { vecoff[i] = run; if (dp[i].active) run += 1u << dp[i].rounds; }
         vecoff[a->n_proofs] = run;
-        total_vec = run;
+        vb->total_vec = run;
         for (size_t c = 0; c < a->n_chunks; c++) segoff[c] = dc[c].entry_off;
         segoff[a->n_chunks] = n_entries;
     }
-    vb->total_vec = total_vec;
     memcpy(hb + vb->o_proofs, dp.data(), sizeof(VProof) * a->n_proofs);
     memcpy(hb + vb->o_chunks, dc.data(), sizeof(VChunk) * a->n_chunks);
     if (n_commit) { memcpy(hb + vb->o_minv, a->min_values, 8 * n_commit); memcpy(hb + vb->o_minp, a->min_present, n_commit); }
+    memcpy(hb + vb->o_hg, g->h(), 32);
+    memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
+    if (vb->device_replay && a->n_proofs) memcpy(hb + vb->o_tstate, a->transcripts, BPP_TRANSCRIPT_BYTES * a->n_proofs);
+    memset(vb->mid(), 0, vb->mid_bytes);
+    memset(w->h_weights.p, 0, 32 * np1);
     for (size_t c = 0; c < a->n_chunks; c++) {
         if (!dc[c].active) continue;
         uint32_t *px = pidx + dc[c].entry_off, mn = dc[c].max_mn;
@@ -415,24 +382,40 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         for (int k = 0; k < ext; k++) px[2 * mn + k] = GEN | (uint32_t)(2 * g->nm + k);
         px[2 * mn + ext] = GEN | (uint32_t)(2 * g->nm + ext);
     }
-    ctx->workers().run(a->n_proofs, 32, [&](size_t i) {
+    const bool host_replay = !vb->device_replay;
+    ctx->workers().run(a->n_proofs, host_replay ? 8 : 32, [&](size_t i) {
         const HProof &p = vb->hp[i];
         const VProof &v = dp[i];
-        uint8_t *wgt = hb + vb->o_weights + 32 * i;
-        memset(wgt, 0, 32);
         if (!p.n_pts) return;
         uint8_t *en = hb + vb->o_enc + 32 * (size_t)p.pt_off;
         memcpy(en, p.a(), 96);
         for (int j = 0; j < p.rounds; j++) { memcpy(en + 32 * (3 + j), p.li(j), 32); memcpy(en + 32 * (3 + p.rounds + j), p.ri(j), 32); }
-        memcpy(en + 32 * (3 + 2 * p.rounds), a->commitments32 + 32 * a->commit_offsets[i], 32 * (size_t)p.m);
-        if (!v.rounds && !v.m) return;          // chunk not computable: only the decompression flags matter
+        const uint8_t *cm = a->commitments32 + 32 * a->commit_offsets[i];
+        memcpy(en + 32 * (3 + 2 * p.rounds), cm, 32 * (size_t)p.m);
+        if (!v.replay) return;          // call already failed on the host: only the decompression flags matter
         uint8_t *ps = hb + vb->o_pscal + 32 * (size_t)v.sc_off;
         memcpy(ps, p.r1(), 64);
-        memcpy(ps + 64, p.d1(), 32 * (size_t)ext);
+        memcpy(ps + 64, p.d1(), 32 * (size_t)p.ext);
         uint8_t *chp = hb + vb->o_chal + 32 * (size_t)v.ch_off;
-        memcpy(chp, p.y, 32); memcpy(chp + 32, p.z, 32); memcpy(chp + 64, p.e, 32);
-        for (int j = 0; j < p.rounds; j++) memcpy(chp + 32 * (3 + j), p.ej[j], 32);
-        memcpy(wgt, p.weight, 32);
+        if (host_replay) {              // loop 1 on this host thread (north_star's split); same code as k_replay.cu
+            ReplayIn in;
+            in.tstate = a->transcripts + BPP_TRANSCRIPT_BYTES * i;
+            in.h32 = g->h(); in.g32 = g->g(0);
+            in.bit_length = (uint32_t)n; in.ext = (uint32_t)ext; in.m = p.m; in.rounds = (uint32_t)p.rounds;
+            in.commitments32 = cm;
+            in.min_values = a->min_values + a->commit_offsets[i]; in.min_present = a->min_present + a->commit_offsets[i];
+            in.a = p.a(); in.a1 = p.a1(); in.b = p.b();
+            in.l_base = p.li(0); in.r_base = p.ri(0); in.lr_stride = 64;
+            in.r1 = p.r1(); in.s1 = p.s1(); in.d1 = p.d1();
+            ReplayOut o;
+            o.y = chp; o.z = chp + 32; o.e = chp + 64; o.ej = chp + 96;
+            o.wbytes = vb->wbytes(i); o.tstate = vb->tstate(i);
+            int rc = replay_transcript_core(in, o);
+            uint8_t flag = rc ? 1 : 0;
+            uint8_t one[32] = {1};
+            if (!rc && !memcmp(chp, one, 32)) flag |= 2;
+            vb->flag(i) = flag;
+        }
         if (v.nonce_off != 0xffffffffu) {
             uint8_t *nn = hb + vb->o_nonces + 32 * (size_t)v.nonce_off;
             for (int k = 0; k < ext; k++) {
@@ -451,12 +434,14 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
             for (uint32_t j = 0; j < 2 * R + p.m; j++) px[3 + j] = p.pt_off + 3 + j;
         }
     });
-    lap();
+    lap();   // [2] fill (+ host transcript replay in host mode)
+    if (host_replay) compute_weights(vb);
+    lap();   // [3] weight transcripts (host mode; in device mode they run inside bpp_vbatch_run)
     cudaStream_t st = ctx->stream;
     if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the pinned blob is reused by the next create on this ctx
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
-    lap();
+    lap();   // [4] H2D
     *out = vb;
     return BPP_OK;
 }
@@ -467,58 +452,87 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     bpp_ctx *ctx = g->ctx;
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
+    VWork *w = vb->w;
     const int ext = g->ext;
-    // ---- device: decompress -> prep -> MSM -> identity flags
-    // The decompression (k_point.cu) only feeds the bucket sums, so it runs on the side stream next to the scalar prep
-    // chain; with phase timing on everything stays on one stream so that the per-phase events mean what they say.
-    ctx->clear_marks();
-    ctx->mark(0);
-    const bool overlap = !ctx->phase_timing && vb->n_pts && (vb->any_msm || vb->any_masks);
-    if (vb->n_pts) {
-        cudaStream_t ds = st;
-        if (overlap) {
-            BPP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-            BPP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-            ds = ctx->stream2;
-        }
-        launch_decompress(ds, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), vb->w->d_tab.as<aniels>(), vb->w->d_ok.as<uint8_t>(), nullptr, nullptr);
-        if (overlap) BPP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
-        ctx->launches++;
-    }
-    ctx->mark(1);
+    const size_t n = vb->n_proofs;
     VDims d;
-    d.n_proofs = (uint32_t)vb->n_proofs; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)ext;
+    d.n_proofs = (uint32_t)n; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)ext;
     d.action = vb->action;
     VBuffers b;
     b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.vec_offsets = vb->dev<uint32_t>(vb->o_vecoff);
-    b.proof_scalars = vb->dev<uint32_t>(vb->o_pscal); b.challenges = vb->dev<uint32_t>(vb->o_chal); b.weights = vb->dev<uint32_t>(vb->o_weights);
+    b.proof_scalars = vb->dev<uint32_t>(vb->o_pscal); b.challenges = vb->dev<uint32_t>(vb->o_chal);
+    b.weights = w->d_weights.as<uint32_t>(); b.weights_mont = w->d_wmont.as<uint32_t>();
     b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
-    b.msm_scalars = vb->w->d_mscal.as<uint32_t>(); b.contrib = vb->w->d_contrib.as<uint32_t>(); b.hg_contrib = vb->w->d_hg.as<uint32_t>();
-    b.pervec = vb->w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? vb->w->d_masks.as<uint32_t>() : nullptr;
-    if (vb->any_msm || vb->any_masks) {
-        launch_verify_prep(st, d, b, vb->total_vec, vb->any_msm ? vb->max_static : 0, &ctx->launches, ctx->phase_timing ? &ctx->ph[2] : nullptr);
-        if (ctx->phase_timing) { ctx->ph_set[2] = true; ctx->ph_set[3] = vb->action != BPP_RECOVER_ONLY; }
-    }
-    if (overlap) BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    ctx->mark(4);
-    if (vb->any_msm) {
-        launch_msm(st, vb->shape, vb->w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
-                   vb->w->d_tab.as<aniels>(), g->d_table.as<aniels>(), vb->w->d_scratch.p, vb->w->d_res.as<ge>(), &ctx->launches,
-                   ctx->phase_timing ? &ctx->ph[5] : nullptr);
-        if (ctx->phase_timing) for (int i = 5; i <= 8; i++) ctx->ph_set[i] = true;
-        launch_encode(st, vb->n_chunks, vb->w->d_res.as<ge>(), nullptr, vb->w->d_ident.as<uint8_t>());
-        ctx->mark(9);
+    b.msm_scalars = w->d_mscal.as<uint32_t>(); b.contrib = w->d_contrib.as<uint32_t>(); b.hg_contrib = w->d_hg.as<uint32_t>();
+    b.pervec = w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? w->d_masks.as<uint32_t>() : nullptr;
+
+    ctx->clear_marks();
+    // The decompression (k_point.cu) only feeds the bucket sums, so it runs on the side stream next to the transcript
+    // replay and the scalar prep chain; with phase timing on everything stays on one stream so that the per-phase events
+    // mean what they say (replay, then decompress, then the prep).
+    const bool overlap = !ctx->phase_timing && vb->n_pts && (vb->any_msm || vb->any_masks);
+    auto decompress = [&](cudaStream_t ds) {
+        launch_decompress(ds, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), w->d_tab.as<aniels>(), w->d_ok.as<uint8_t>(), nullptr, nullptr);
         ctx->launches++;
-        BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_ident), vb->w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+    };
+    if (overlap) {
+        BPP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        BPP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        decompress(ctx->stream2);
+        BPP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
+    ctx->mark(0);
+    const bool dev_replay = vb->device_replay && vb->any_replay;
+    if (dev_replay) {
+        RBuffers rb;
+        rb.proofs = b.proofs; rb.tstates_in = vb->dev<uint8_t>(vb->o_tstate); rb.hg32 = vb->dev<uint8_t>(vb->o_hg);
+        rb.enc = vb->dev<uint8_t>(vb->o_enc); rb.proof_scalars = vb->dev<uint8_t>(vb->o_pscal);
+        rb.min_values = b.min_values; rb.min_present = b.min_present;
+        rb.challenges = vb->dev<uint8_t>(vb->o_chal);
+        uint8_t *dm = w->d_mid.as<uint8_t>();
+        rb.wbytes = dm + vb->mo_wbytes; rb.flags = dm + vb->mo_flags; rb.tstates_out = dm + vb->mo_tstate;
+        launch_replay(st, d, rb, &ctx->launches);
+        BPP_CUDA(ctx, cudaMemcpyAsync(vb->mid(), dm, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
+    }
+    ctx->mark(1);
+    if (!overlap && vb->n_pts) decompress(st);
+    ctx->mark(2);
+    if (vb->any_msm || vb->any_masks) {
+        launch_verify_prep(st, d, b, vb->total_vec, &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
+        if (ctx->phase_timing) { ctx->ph_set[3] = true; ctx->ph_set[4] = true; }
+    }
+    if (dev_replay) {       // the host hashes the weight transcripts while the device runs the weight-free scalar prep
+        BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_mid));
+        compute_weights(vb);
+    }
+    if (vb->any_msm) {
+        BPP_CUDA(ctx, cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 32 * n, cudaMemcpyHostToDevice, st));
+        ctx->mark(5);
+        launch_verify_weigh(st, d, b, vb->max_static, &ctx->launches);
+        ctx->mark(6);
+        if (overlap) BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
+                   w->d_tab.as<aniels>(), g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), &ctx->launches,
+                   ctx->phase_timing ? &ctx->ph[7] : nullptr);
+        if (ctx->phase_timing) for (int i = 7; i <= 10; i++) ctx->ph_set[i] = true;
+        launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
+        ctx->mark(11);
+        ctx->launches++;
+        BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+    } else if (overlap) {
+        BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
     BPP_CUDA(ctx, cudaGetLastError());
-    if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_ok), vb->w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
-    if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync((vb->w->h_out.as<uint8_t>() + vb->ho_masks), vb->w->d_masks.p, 32 * vb->n_proofs * (size_t)ext, cudaMemcpyDeviceToHost, st));
+    if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
+    if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)ext, cudaMemcpyDeviceToHost, st));
     BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    vb->ran = true;
 
     // ---- resolve per-chunk status with the reference's precedence
-    const uint8_t *okf = (vb->w->h_out.as<uint8_t>() + vb->ho_ok);
-    const uint8_t *ident = (vb->w->h_out.as<uint8_t>() + vb->ho_ident);
+    const uint8_t *okf = w->h_out.as<uint8_t>() + vb->ho_ok;
+    const uint8_t *ident = w->h_out.as<uint8_t>() + vb->ho_ident;
+    const uint8_t *hmasks = w->h_out.as<uint8_t>() + vb->ho_masks;
     for (size_t c = 0; c < vb->n_chunks; c++) {
         const HChunk &hc = vb->hc[c];
         int32_t rc = hc.pre_rc;
@@ -529,14 +543,14 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
                     if (!okf[p.pt_off + 3 + 2 * p.rounds + j]) { rc = BPP_INVALID_ARGUMENT; break; }
             }
         }
-        if (!rc) rc = hc.loop1_rc;
-        if (!rc) {
-            for (size_t i = hc.lo; i < hc.hi && !rc; i++) {                                 // loop 2, proof order
-                const HProof &p = vb->hp[i];
-                for (uint32_t j = 0; j < 3 + 2 * (uint32_t)p.rounds; j++)
-                    if (!okf[p.pt_off + j]) { rc = BPP_INVALID_ARGUMENT; break; }         // :859-866
-                if (!rc) rc = p.loop2_rc;
-            }
+        for (size_t i = hc.lo; i < hc.hi && !rc; i++)                                       // loop 1 (:816-850)
+            if (vb->flag(i) & 1) rc = BPP_VERIFICATION_FAILED;
+        for (size_t i = hc.lo; i < hc.hi && !rc; i++) {                                     // loop 2, proof order
+            const HProof &p = vb->hp[i];
+            for (uint32_t j = 0; j < 3 + 2 * (uint32_t)p.rounds; j++)
+                if (!okf[p.pt_off + j]) { rc = BPP_INVALID_ARGUMENT; break; }             // :859-866
+            if (!rc) rc = p.loop2_rc;                                                       // :886-888
+            if (!rc && (vb->flag(i) & 2)) rc = BPP_VERIFICATION_FAILED;                     // y == 1: (y - 1) is not invertible
         }
         if (!rc && vb->action != BPP_RECOVER_ONLY && !ident[c]) rc = BPP_VERIFICATION_FAILED;   // :1057-1061
         chunk_status[c] = rc;
@@ -545,9 +559,24 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
             bool have = !rc && i < hc.hi && vb->action != BPP_VERIFY_ONLY && vb->hp[i].has_seed;
             if (mask_present) mask_present[i] = have ? 1 : 0;
             if (masks32) {
-                if (have) memcpy(masks32 + 32 * i * (size_t)ext, (vb->w->h_out.as<uint8_t>() + vb->ho_masks) + 32 * i * (size_t)ext, 32 * (size_t)ext);
+                if (have) memcpy(masks32 + 32 * i * (size_t)ext, hmasks + 32 * i * (size_t)ext, 32 * (size_t)ext);
                 else memset(masks32 + 32 * i * (size_t)ext, 0, 32 * (size_t)ext);
             }
+        }
+    }
+    return BPP_OK;
+}
+
+// `&mut Transcript` semantics of the reference: every transcript of a call that reached loop 1 is advanced, up to and
+// including the first proof whose replay failed.  transcripts: n_proofs x 203 bytes, updated in place.
+int32_t bpp_vbatch_transcripts(const bpp_vbatch *vb, uint8_t *transcripts) {
+    if (!vb || !transcripts) return BPP_INVALID_ARGUMENT;
+    if (vb->device_replay && !vb->ran) return fail(vb->g->ctx, BPP_INVALID_ARGUMENT, "bpp_vbatch_run has not been called");
+    for (const HChunk &hc : vb->hc) {
+        if (hc.pre_rc) continue;
+        for (size_t i = hc.lo; i < hc.hi; i++) {
+            memcpy(transcripts + BPP_TRANSCRIPT_BYTES * i, vb->tstate(i), BPP_TRANSCRIPT_BYTES);
+            if (vb->flag(i) & 1) break;
         }
     }
     return BPP_OK;
@@ -557,7 +586,10 @@ int32_t bpp_verify_chunks(bpp_gens *g, const bpp_verify_args *args, int32_t *chu
     bpp_vbatch *vb = nullptr;
     int32_t rc = bpp_vbatch_create(g, args, &vb);
     if (rc) return rc;
+    auto t0 = std::chrono::steady_clock::now();
     rc = bpp_vbatch_run(vb, chunk_status, masks32, mask_present);
+    g->ctx->host_ms[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (!rc) rc = bpp_vbatch_transcripts(vb, args->transcripts);
     bpp_vbatch_destroy(vb);
     return rc;
 }

@@ -5,8 +5,12 @@
 //                       (A1, B, A, L_j, R_j, V_j), the proof's h / g_k contributions, optional mask recovery (:941-969)
 //   B  k_vprep_vector   one thread per (proof, i): contributions to gi_base_scalars[i] / hi_base_scalars[i] (:987-1003);
 //                       s[i] is evaluated directly as prod_j e_j^(+-1) instead of the reference's serial recurrence
-//   C  k_vprep_reduce   one thread per (chunk, static slot): column sums over the chunk's proofs (the `+=` of :999-1000,
-//                       :1017-1020), written as canonical scalars into the chunk's MSM entry list
+//   W  k_vprep_weight   one warp per proof: multiplies the proof's dynamic scalars by its batch weight
+//   C  k_vprep_reduce   one warp per (chunk, static slot): weighted column sums over the chunk's proofs (the `+=` of
+//                       :999-1000, :1017-1020), written as canonical scalars into the chunk's MSM entry list
+// Every term of proof p carries its weight w_p exactly once (range_proof.rs:894, :999-1032), so A and B run weight-free and
+// W / C apply w_p at the end: the weights come out of a sequential Merlin transcript on the host (:811-853), and this
+// ordering lets A and B run on the device while the host is still hashing.
 // All arithmetic is mod l in Montgomery form (arith.cuh sc_montmul); results are bit-exact canonical scalars.
 #include "kernels.cuh"
 
@@ -26,7 +30,7 @@ static __device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_mo
 static __device__ __forceinline__ sc ld_mont(const uint32_t *p) { return sc_to_mont(ld_sc(p)); }
 
 // pervec layout (scalars, Montgomery form), per proof at pv_off:
-//   [0] w*r1*e  [1] w*s1*e  [2] w*e^2  [3] w*e^2*z  [4] y^N  [5..7] spare
+//   [0] r1*e  [1] s1*e  [2] e^2  [3] e^2*z  [4] y^N  [5..7] spare      (the batch weight is applied by stages W / C)
 //   [8 + j]            e_j            j < rounds
 //   [8 + R + j]        e_j^-1
 //   [8 + 2R + k]       y^-(2^k)       k < rounds
@@ -37,12 +41,11 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.n_proofs) return;
     const VProof pr = b.proofs[p];
-    if (!pr.active && pr.nonce_off == 0xffffffffu) return;
+    if (!pr.replay || (!pr.active && pr.nonce_off == 0xffffffffu)) return;
     const uint32_t R = pr.rounds, m = pr.m, ext = d.ext;
     const sc one_m = sc_const_R();                 // 1 in Montgomery form
     const uint32_t *ch = b.challenges + 8 * (size_t)pr.ch_off;
     sc y = ld_mont(ch), z = ld_mont(ch + 8), e = ld_mont(ch + 16);
-    sc w = ld_mont(b.weights + 8 * (size_t)p);
     const uint32_t *ps = b.proof_scalars + 8 * (size_t)pr.sc_off;
     sc r1 = ld_mont(ps), s1 = ld_mont(ps + 8);
 
@@ -97,45 +100,43 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     uint64_t two_n_m1 = d.bit_length >= 64 ? ~0ull : ((1ull << d.bit_length) - 1ull);
     d_sum = mm(d_sum, sc_to_mont(sc_from_u64(two_n_m1)));
 
-    sc we2 = mm(w, e2);
-    sc neg_we2 = sc_neg(we2);
+    const sc neg_e2 = sc_neg(e2);
     uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;
-    // dynamic entries of this proof: [A1, B, A, L_0.., R_0.., V_0..]
-    st_sc(out, sc_from_mont(sc_neg(mm(w, e))));
-    st_sc(out + 8, sc_from_mont(sc_neg(w)));
-    st_sc(out + 16, sc_from_mont(neg_we2));
+    // dynamic entries of this proof: [A1, B, A, L_0.., R_0.., V_0..], still WITHOUT the weight and in Montgomery form
+    st_sc(out, sc_neg(e));
+    st_sc(out + 8, sc_neg(one_m));
+    st_sc(out + 16, neg_e2);
     for (uint32_t j = 0; j < R; j++) {
-        st_sc(out + 8 * (3 + j), sc_from_mont(mm(neg_we2, mm(ej[j], ej[j]))));
-        st_sc(out + 8 * (3 + R + j), sc_from_mont(mm(neg_we2, mm(ejinv[j], ejinv[j]))));
+        st_sc(out + 8 * (3 + j), mm(neg_e2, mm(ej[j], ej[j])));
+        st_sc(out + 8 * (3 + R + j), mm(neg_e2, mm(ejinv[j], ejinv[j])));
     }
     uint32_t *pv = b.pervec + 8 * (size_t)pr.pv_off;
     sc h = sc_zero();
     sc zpow = one_m;
-    sc neg_we2_yN1 = mm(neg_we2, yN1);
+    const sc neg_e2_yN1 = mm(neg_e2, yN1);
     for (uint32_t j = 0; j < m; j++) {
         zpow = mm(zpow, z2);
         st_sc(pv + 8 * (PV_HDR + 3 * R + j), zpow);
-        sc weighted = mm(neg_we2_yN1, zpow);
-        st_sc(out + 8 * (3 + 2 * R + j), sc_from_mont(weighted));
+        sc weighted = mm(neg_e2_yN1, zpow);
+        st_sc(out + 8 * (3 + 2 * R + j), weighted);
         if (b.min_present[pr.commit_off + j]) {
             sc mv = sc_to_mont(sc_from_u64(b.min_values[pr.commit_off + j]));
             h = sc_sub(h, mm(weighted, mv));
         }
     }
-    // h += w*(r1*y*s1 + e^2*(y^(N+1)*z*d_sum + (z^2 - z)*y_sum)); g_k += w*d1[k]   (range_proof.rs:1017-1020)
+    // h += r1*y*s1 + e^2*(y^(N+1)*z*d_sum + (z^2 - z)*y_sum); g_k += d1[k]   (range_proof.rs:1017-1020, weight applied later)
     sc t = mm(mm(r1, y), s1);
     sc u = sc_add(mm(mm(yN1, z), d_sum), mm(sc_sub(z2, z), y_sum));
-    h = sc_add(h, mm(w, sc_add(t, mm(e2, u))));
+    h = sc_add(h, sc_add(t, mm(e2, u)));
     uint32_t *hg = b.hg_contrib + 8 * (size_t)p * (1 + ext);
     st_sc(hg, h);
-    for (uint32_t k = 0; k < ext; k++) st_sc(hg + 8 * (1 + k), mm(w, ld_mont(ps + 16 + 8 * k)));
+    for (uint32_t k = 0; k < ext; k++) st_sc(hg + 8 * (1 + k), ld_mont(ps + 16 + 8 * k));
 
     // hand-off to stage B
-    sc we = mm(w, e);
-    st_sc(pv, mm(we, r1));
-    st_sc(pv + 8, mm(we, s1));
-    st_sc(pv + 16, we2);
-    st_sc(pv + 24, mm(we2, z));
+    st_sc(pv, mm(e, r1));
+    st_sc(pv + 8, mm(e, s1));
+    st_sc(pv + 16, e2);
+    st_sc(pv + 24, mm(e2, z));
     st_sc(pv + 32, yN);
     sc yp = y_inv;
     for (uint32_t j = 0; j < R; j++) {
@@ -176,9 +177,9 @@ __global__ void __launch_bounds__(128) k_vprep_vector(VDims d, VBuffers b, uint3
         }
     }
     sc wre = ld_sc(pv), wse = ld_sc(pv + 8), we2 = ld_sc(pv + 16), we2z = ld_sc(pv + 24), yN = ld_sc(pv + 32);
-    // gi: w*(r1*e*y^-i*s[i] + e^2*z)
+    // gi: r1*e*y^-i*s[i] + e^2*z        (times w_p in k_vprep_reduce)
     sc g = sc_add(mm(mm(wre, yinv_i), s_i), we2z);
-    // hi: w*(s1*e*s[N-1-i] - e^2*(d[i]*y^(N-i) + z)),  d[i] = z^(2(j+1)) * 2^bit
+    // hi: s1*e*s[N-1-i] - e^2*(d[i]*y^(N-i) + z),  d[i] = z^(2(j+1)) * 2^bit
     uint32_t party = i / d.bit_length, bitpos = i % d.bit_length;
     sc zp = ld_sc(pv + 8 * (PV_HDR + 3 * R + party));
     sc two_b = sc_zero();
@@ -216,29 +217,43 @@ __global__ void __launch_bounds__(128) k_vprep_reduce(VDims d, VBuffers b) {
         else if (slot < 2 * chk.max_mn) { uint32_t i = slot - chk.max_mn; if (i < N) src = b.contrib + 8 * ((size_t)pr.contrib_off + N + i); }
         else if (slot < 2 * chk.max_mn + d.ext) src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext) + 1 + (slot - 2 * chk.max_mn));
         else src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext));
-        if (src) acc = sc_add(acc, ld_sc(src));
+        if (src) acc = sc_add(acc, mm(ld_sc(src), ld_sc(b.weights_mont + 8 * (size_t)p)));
     }
     for (int delta = 16; delta > 0; delta >>= 1) acc = sc_add(acc, shfl_down_sc(acc, delta));
     if (lane == 0) st_sc(b.msm_scalars + 8 * ((size_t)chk.entry_off + slot), sc_from_mont(acc));
 }
 
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches,
-                        cudaEvent_t *marks) {
+// one warp per proof: w_p -> Montgomery form (kept for k_vprep_reduce), dynamic scalars *= w_p and leave Montgomery form
+__global__ void __launch_bounds__(128) k_vprep_weight(VDims d, VBuffers b) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= d.n_proofs) return;
+    const VProof pr = b.proofs[p];
+    if (!pr.active) return;
+    const sc w = ld_mont(b.weights + 8 * (size_t)p);
+    if (lane == 0) st_sc(b.weights_mont + 8 * (size_t)p, w);
+    const uint32_t n_dyn = 3 + 2 * pr.rounds + pr.m;
+    uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;
+    for (uint32_t t = lane; t < n_dyn; t += 32) st_sc(out + 8 * t, sc_from_mont(mm(ld_sc(out + 8 * t), w)));
+}
+
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint64_t *launches, cudaEvent_t *marks) {
     if (d.n_proofs == 0) return;
     k_vprep_proof<<<(d.n_proofs + 63) / 64, 64, 0, s>>>(d, b);
     if (marks) cudaEventRecord(marks[0], s);
     if (launches) (*launches)++;
-    if (d.action == 0 /* RecoverOnly */) return;
-    if (total_vec) {
+    if (d.action != 0 /* RecoverOnly */ && total_vec) {
         k_vprep_vector<<<(total_vec + 127) / 128, 128, 0, s>>>(d, b, total_vec);
         if (launches) (*launches)++;
     }
     if (marks) cudaEventRecord(marks[1], s);
-    if (max_static) {
-        dim3 grid((max_static + 3) / 4, d.n_chunks);       // 4 warps (slots) per CTA
-        k_vprep_reduce<<<grid, 128, 0, s>>>(d, b);
-        if (launches) (*launches)++;
-    }
+}
+
+void launch_verify_weigh(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t max_static, uint64_t *launches) {
+    if (d.n_proofs == 0 || d.action == 0 || max_static == 0) return;
+    k_vprep_weight<<<(d.n_proofs + 3) / 4, 128, 0, s>>>(d, b);
+    dim3 grid((max_static + 3) / 4, d.n_chunks);       // 4 warps (slots) per CTA
+    k_vprep_reduce<<<grid, 128, 0, s>>>(d, b);
+    if (launches) (*launches) += 2;
 }
 
 } // namespace bpp

@@ -35,6 +35,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
 // marks (optional, 4 events): recorded after the sort phase (digits+scan+scatter), bucket sums, window reduction, Horner
 
 // ---------------------------------------------------------------- k_verify.cu
+#define BPP_TSTATE_BYTES 203 // merlin STROBE-128 state on the wire: 200 B Keccak state, pos, pos_begin, cur_flags
 #define BPP_MAX_ROUNDS 24  // log2(n * m) <= 24 (generator sets are capped at 2^24 points)
 struct VProof {            // per-proof metadata, device-resident
     uint32_t m;            // aggregation factor (commitments)
@@ -47,6 +48,8 @@ struct VProof {            // per-proof metadata, device-resident
     uint32_t contrib_off;  // first slot in the gi/hi contribution array: [gi(N) | hi(N)]
     uint32_t pv_off;       // first slot of the stage A -> B hand-off vector (8 + 3*rounds + m scalars)
     uint32_t active;       // 1 = contributes to its chunk's MSM
+    uint32_t pt_off;       // first slot in the point table / encoding array: [A, A1, B, L_0.., R_0.., V_0..]
+    uint32_t replay;       // 1 = its transcript is replayed (loop 1) and its scalars are prepared
 };
 struct VChunk {
     uint32_t proof_lo, proof_hi;
@@ -60,7 +63,8 @@ struct VBuffers {
     const uint32_t *vec_offsets;     // n_proofs + 1: prefix sums of N over active proofs
     const uint32_t *proof_scalars;   // words
     const uint32_t *challenges;      // words
-    const uint32_t *weights;         // n_proofs x 8 words
+    const uint32_t *weights;         // n_proofs x 8 words (canonical); consumed by k_vprep_weight only
+    uint32_t *weights_mont;          // scratch: n_proofs x 8 words, Montgomery form
     const uint64_t *min_values; const uint8_t *min_present;
     const uint32_t *nonces;          // words, may be null
     uint32_t *msm_scalars;           // out: n_entries x 8 words
@@ -69,8 +73,25 @@ struct VBuffers {
     uint32_t *pervec;                // scratch: stage A -> B hand-off
     uint32_t *masks;                 // out: n_proofs x ext x 8 words (plain), may be null
 };
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_static, uint64_t *launches,
-                        cudaEvent_t *marks = nullptr);   // marks (optional, 2 events): after the per-proof stage, after the per-(proof, i) stage
+// weight-free part (per proof, per (proof, i)); marks (optional, 2 events): after each of the two kernels
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint64_t *launches, cudaEvent_t *marks = nullptr);
+// weight application + column sums into the MSM entry lists (needs b.weights)
+void launch_verify_weigh(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t max_static, uint64_t *launches);
+
+// ---------------------------------------------------------------- k_replay.cu
+struct RBuffers {
+    const VProof *proofs;
+    const uint8_t *tstates_in;       // n_proofs x 203
+    const uint8_t *hg32;             // compressed H, then G[0..ext)
+    const uint8_t *enc;              // point encodings (VProof::pt_off)
+    const uint8_t *proof_scalars;    // bytes (VProof::sc_off): r1, s1, d1..
+    const uint64_t *min_values; const uint8_t *min_present;
+    uint8_t *challenges;             // out (VProof::ch_off): y, z, e, e_0..
+    uint8_t *wbytes;                 // out: n_proofs x 32
+    uint8_t *tstates_out;            // out: n_proofs x 203
+    uint8_t *flags;                  // out: n_proofs; bit 0 = loop-1 VerificationFailed, bit 1 = y == 1
+};
+void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, uint64_t *launches);
 
 // ---------------------------------------------------------------- k_bench.cu
 // returns elapsed seconds for `iters` dependent ops in each of `threads_total` lanes; ops counted by caller

@@ -61,12 +61,16 @@ void *bpp_ctx_stream(bpp_ctx *ctx);                   /* cudaStream_t, for event
 int32_t bpp_ctx_timer_start(bpp_ctx *ctx);
 int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms);
 /* per-phase device times of the last bpp_vbatch_run / bpp_msm_plan_run (events between the kernels, when enabled):
- * ms9 = {decompress, verifier prep per proof, per (proof, i), column sums, MSM sort, MSM bucket sums, MSM window reduction,
- *        MSM Horner, encode/identity} */
+ * ms11 = {transcript replay, decompress, verifier prep per proof, per (proof, i), wait for host weight transcripts, weighting +
+ *         column sums, MSM sort, MSM bucket sums, MSM window reduction, MSM Horner, encode/identity} */
 int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable);
-int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms9);
+int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms11);
+/* where loop 1 of the verifier (the per-proof Merlin transcript replay, range_proof.rs:816-850) runs: 1 = CUDA kernel (default),
+ * 0 = host worker threads (BASELINE.json north_star's host/device split).  Results are bit-identical. */
+int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
 /* wall-clock milliseconds of the host phases of the last bpp_vbatch_create / bpp_verify_chunks on this ctx:
- * ms6 = {parse + statement checks, transcript replay, weight transcripts, layout, blob fill, H2D + sync} */
+ * ms6 = {parse + statement checks, layout + buffers, blob fill (+ loop-1 replay in host mode), weight transcripts (host mode),
+ *        H2D + sync, unused} */
 int32_t bpp_ctx_host_ms(bpp_ctx *ctx, double *ms6);
 /* host threads used for the Fiat-Shamir replay of bpp_verify_chunks (default: min(64, hardware threads); the
  * reference is single-threaded, the harness supplies parallelism -- see BASELINE.md) */
@@ -120,8 +124,9 @@ int32_t bpp_pedersen_commit_batch(bpp_gens *g, size_t count, const uint64_t *val
  *   proof_bytes / proof_offsets[n+1]   serialised proofs (to_bytes layout, range_proof.rs:1120-1150)
  *   commit_offsets[n+1]                first commitment of proof i in commitments32 / min_values / min_present
  *   seed_nonces32 (n x 32) + seed_present (n)   optional (NULL = none)
- *   transcripts (n x 203 B)            Merlin state of each caller transcript BEFORE the call; advanced in
- *                                      place exactly as `&mut Transcript` is in the reference
+ *   transcripts (n x 203 B)            Merlin state of each caller transcript BEFORE the call; bpp_verify_chunks advances
+ *                                      them in place exactly as `&mut Transcript` is in the reference (the split form
+ *                                      reads them in create and hands the advanced states out via bpp_vbatch_transcripts)
  * Results: chunk_status[K] (bpp_status per reference call), masks32 (n x ext x 32) and mask_present (n) as
  * Vec<Option<ExtendedMask>>. */
 typedef struct {
@@ -147,6 +152,9 @@ int32_t bpp_verify_chunks(bpp_gens *g, const bpp_verify_args *args, int32_t *chu
  * create = host parsing + Fiat-Shamir + upload; run = all device work + verdict readback. */
 int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *args, bpp_vbatch **out);
 int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present);
+/* after bpp_vbatch_run: write the advanced Merlin states (n_proofs x 203 B) -- what `&mut [Transcript]` holds after the
+ * reference call; bpp_verify_chunks does this into args->transcripts itself */
+int32_t bpp_vbatch_transcripts(const bpp_vbatch *vb, uint8_t *transcripts);
 void bpp_vbatch_destroy(bpp_vbatch *vb);
 
 /* ---------------------------------------------------------------- proof bytes (host)

@@ -16,6 +16,14 @@ VA = api.VerifyAction
 _params_cache = {}
 
 
+@pytest.fixture(autouse=True, params=["device_replay", "host_replay"])
+def replay_mode(request):
+    """every test runs with loop 1 (the Merlin transcript replay) on the device and on host threads: same results"""
+    bpp.engine().set_replay_mode(request.param == "device_replay")
+    yield request.param
+    bpp.engine().set_replay_mode(True)
+
+
 def gpu_params(n, M, ext):
     key = (n, M, ext)
     if key not in _params_cache:

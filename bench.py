@@ -254,6 +254,7 @@ def run_b200(args, rank, local_rank, world):
         e2e_s += time.perf_counter() - t0
         for k, v in eng.host_ms().items():
             host_acc[k] = host_acc.get(k, 0.0) + v / args.steps
+    io_h2d, io_d2h = eng.io_bytes()
     barrier()
 
     # ---------------- reduce over ranks (max time)
@@ -314,8 +315,7 @@ def run_b200(args, rank, local_rank, world):
         cpu = {"value": n * cpu_reps / sec, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d x (%d proofs = %d verify_batch calls of %d), VerifyOnly, %d pthreads; C restatement, not dalek" % (
                    cpu_reps, n, len(offs) - 1, CHUNK, threads)}
-        h2d = int(pk.args.n_proofs * (16 * 32 + (2 + EXT) * 32 + (3 + 6) * 32 + 32 + 40) + 4 * entries + 64)
-        d2h = int(n_pts + n_chunks)
+        h2d, d2h = io_h2d, io_d2h          # counted by the engine from the buffers it copies (bpp_ctx_io_bytes)
         line = {
             "metric": METRIC, "value": world * args.proofs * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,

@@ -81,6 +81,12 @@ class Engine:
 
     HOST_PHASES = ("parse", "layout", "fill_replay", "weights", "h2d", "run_wall")
 
+    def io_bytes(self):
+        """(host->device, device->host) bytes of the last verification call"""
+        arr = (C.c_uint64 * 2)()
+        _chk(self, _ffi.lib().bpp_ctx_io_bytes(self.h, arr))
+        return int(arr[0]), int(arr[1])
+
     def set_replay_mode(self, on_device):
         """loop 1 (transcript replay) on the device (default) or on host threads"""
         _chk(self, _ffi.lib().bpp_ctx_set_replay_mode(self.h, 1 if on_device else 0))

@@ -84,6 +84,7 @@ def lib():
         "bpp_ctx_phase_timing": (i32, [vp, i32]),
         "bpp_ctx_phase_ms": (i32, [vp, P(C.c_float)]),
         "bpp_ctx_host_ms": (i32, [vp, P(C.c_double)]),
+        "bpp_ctx_io_bytes": (i32, [vp, P(C.c_uint64)]),
         "bpp_decompress_check": (i32, [vp, sz, cp, cp, cp]),
         "bpp_from_uniform_batch": (i32, [vp, sz, cp, cp]),
         "bpp_msm": (i32, [vp, sz, cp, cp, cp]),

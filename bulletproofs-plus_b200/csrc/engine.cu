@@ -122,6 +122,11 @@ int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms11) {
     }
     return BPP_OK;
 }
+int32_t bpp_ctx_io_bytes(bpp_ctx *ctx, uint64_t *h2d_d2h) {
+    if (!ctx || !h2d_d2h) return BPP_INVALID_ARGUMENT;
+    h2d_d2h[0] = ctx->io_bytes[0]; h2d_d2h[1] = ctx->io_bytes[1];
+    return BPP_OK;
+}
 int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device) {
     if (!ctx) return BPP_INVALID_ARGUMENT;
     ctx->device_replay = on_device != 0;

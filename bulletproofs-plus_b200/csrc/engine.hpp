@@ -53,6 +53,7 @@ struct bpp_ctx {
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
+    uint64_t io_bytes[2] = {0, 0};      // host->device / device->host bytes moved by the last verification call
     double host_ms[8] = {};             // wall-clock breakdown of the last bpp_vbatch_create (see bpp_ctx_host_ms)
     bpp::HostPool *pool = nullptr;      // lazily created with host_threads workers
     bpp::HostPool &workers() {

@@ -442,6 +442,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the pinned blob is reused by the next create on this ctx
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
     lap();   // [4] H2D
+    ctx->io_bytes[0] = vb->blob_bytes; ctx->io_bytes[1] = 0;
     *out = vb;
     return BPP_OK;
 }
@@ -528,6 +529,8 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)ext, cudaMemcpyDeviceToHost, st));
     BPP_CUDA(ctx, cudaStreamSynchronize(st));
     vb->ran = true;
+    ctx->io_bytes[0] = vb->blob_bytes + (vb->any_msm ? 32 * n : 0);
+    ctx->io_bytes[1] = (dev_replay ? vb->mid_bytes : 0) + vb->n_pts + (vb->any_msm ? vb->n_chunks : 0) + (vb->any_masks ? 32 * n * (size_t)ext : 0);
 
     // ---- resolve per-chunk status with the reference's precedence
     const uint8_t *okf = w->h_out.as<uint8_t>() + vb->ho_ok;

@@ -72,6 +72,8 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
  * ms6 = {parse + statement checks, layout + buffers, blob fill (+ loop-1 replay in host mode), weight transcripts (host mode),
  *        H2D + sync, unused} */
 int32_t bpp_ctx_host_ms(bpp_ctx *ctx, double *ms6);
+/* bytes moved host->device ([0]) and device->host ([1]) by the last bpp_vbatch_create + bpp_vbatch_run / bpp_verify_chunks */
+int32_t bpp_ctx_io_bytes(bpp_ctx *ctx, uint64_t *h2d_d2h);
 /* host threads used for the Fiat-Shamir replay of bpp_verify_chunks (default: min(64, hardware threads); the
  * reference is single-threaded, the harness supplies parallelism -- see BASELINE.md) */
 int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);

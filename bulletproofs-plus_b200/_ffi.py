@@ -58,6 +58,23 @@ class VerifyArgs(C.Structure):
     ]
 
 
+class ProveArgs(C.Structure):
+    _fields_ = [
+        ("n_proofs", C.c_size_t),
+        ("aggregation", C.c_int32),
+        ("commitments32", C.c_void_p),
+        ("values", C.c_void_p),
+        ("blindings32", C.c_void_p),
+        ("min_values", C.c_void_p),
+        ("min_present", C.c_void_p),
+        ("seed_nonces32", C.c_void_p),
+        ("seed_present", C.c_void_p),
+        ("transcripts", C.c_void_p),
+        ("rng_bytes", C.c_void_p),
+        ("rng_stride", C.c_size_t),
+    ]
+
+
 _lib = None
 
 
@@ -105,6 +122,8 @@ def lib():
         "bpp_vbatch_destroy": (None, [vp]),
         "bpp_ctx_set_replay_mode": (i32, [vp, i32]),
         "bpp_proof_check_bytes": (i32, [cp, sz, P(i32), P(i32)]),
+        "bpp_proof_size": (sz, [i32, i32]),
+        "bpp_prove_batch": (i32, [vp, P(ProveArgs), vp, sz, vp]),
         "bpp_transcript_new": (None, [cp, sz, cp]),
         "bpp_transcript_append_message": (None, [cp, cp, sz, cp, sz]),
         "bpp_transcript_challenge_bytes": (None, [cp, cp, sz, cp, sz]),

@@ -233,6 +233,75 @@ class RangeProof:
     def ri(self):
         return [self._el(self._ext + 6 + 2 * j) for j in range(self._rounds)]
 
+    # ---- proving
+    @staticmethod
+    def rng_bytes_needed(generators, aggregation):
+        """bytes the external RNG contributes to one proof: 32 per TranscriptRng rebuild (transcripts.rs:185-194)"""
+        n = generators.bit_length() * aggregation
+        return 32 * ((n - 1).bit_length() + 3)
+
+    @staticmethod
+    def prove_batch(transcripts, statements, witnesses, rng_bytes):
+        """P x RangeProof::prove_with_rng for statements of one shape, in lock-step on the device.
+        rng_bytes: per proof, the bytes its external RNG delivers (rng_bytes_needed each).
+        Returns a list with a RangeProof or a ProofError per proof; transcripts are advanced in place."""
+        P = len(statements)
+        if not (len(transcripts) == len(witnesses) == len(rng_bytes) == P) or P == 0:
+            raise EngineError(_ffi.INVALID_ARGUMENT, "prove_batch: length mismatch")
+        params = statements[0].generators
+        ext, m = params.gens.extension_degree, len(statements[0].commitments)
+        for s, w in zip(statements, witnesses):
+            if len(s.commitments) != m or s.generators.gens is not params.gens:
+                raise EngineError(_ffi.INVALID_ARGUMENT, "prove_batch: statements must share one shape and one parameter set")
+        results = [None] * P
+        live = []
+        for i, (s, w) in enumerate(zip(statements, witnesses)):
+            # range_proof.rs:248-260: witness / statement shape checks
+            if len(w.openings) != len(s.commitments):
+                results[i] = EngineError(_ffi.INVALID_LENGTH, "Witness openings and statement commitments do not match!")
+            elif w.extension_degree != params.extension_degree():
+                results[i] = EngineError(_ffi.INVALID_LENGTH, "Witness and statement extension degrees do not match!")
+            else:
+                live.append(i)
+        if live:
+            need = RangeProof.rng_bytes_needed(params, m)
+            rounds = (params.bit_length() * m - 1).bit_length()
+            plen = _ffi.lib().bpp_proof_size(ext, rounds)
+            n = len(live)
+            commits = C.create_string_buffer(b"".join(c for i in live for c in statements[i].commitments), 32 * n * m)
+            values = _u64arr([o.v for i in live for o in witnesses[i].openings])
+            blind = C.create_string_buffer(b"".join(_sc(r) for i in live for o in witnesses[i].openings for r in o.r), 32 * n * m * ext)
+            minv = _u64arr([(v or 0) for i in live for v in statements[i].minimum_value_promises])
+            minp = (C.c_uint8 * (n * m))(*[0 if v is None else 1 for i in live for v in statements[i].minimum_value_promises])
+            seeds = C.create_string_buffer(b"".join(_sc(statements[i].seed_nonce) if statements[i].seed_nonce is not None else bytes(32) for i in live), 32 * n)
+            seedp = (C.c_uint8 * n)(*[0 if statements[i].seed_nonce is None else 1 for i in live])
+            tbuf = C.create_string_buffer(b"".join(transcripts[i].state for i in live), _ffi.TRANSCRIPT_BYTES * n)
+            for i in live:
+                if len(rng_bytes[i]) < need:
+                    raise EngineError(_ffi.INVALID_LENGTH, "rng_bytes: %d bytes needed per proof" % need)
+            rbuf = C.create_string_buffer(b"".join(bytes(rng_bytes[i][:need]) for i in live), need * n)
+            a = _ffi.ProveArgs(n, m, C.addressof(commits), C.addressof(values), C.addressof(blind), C.addressof(minv), C.addressof(minp),
+                               C.addressof(seeds), C.addressof(seedp), C.addressof(tbuf), C.addressof(rbuf), need)
+            out = C.create_string_buffer(plen * n)
+            status = (C.c_int32 * n)()
+            _chk(params.gens.engine, _ffi.lib().bpp_prove_batch(params.gens.h, C.byref(a), out, plen, status))
+            for k, i in enumerate(live):
+                transcripts[i].state = tbuf.raw[_ffi.TRANSCRIPT_BYTES * k: _ffi.TRANSCRIPT_BYTES * (k + 1)]
+                if status[k]:
+                    results[i] = EngineError(status[k], "prove_with_rng")
+                else:
+                    results[i] = RangeProof(out.raw[plen * k: plen * (k + 1)], ext, rounds)
+        return results
+
+    @staticmethod
+    def prove_with_rng(transcript, statement, witness, rng):
+        """RangeProof::prove_with_rng; `rng` is any object with fill(n) -> bytes (the external CryptoRng)."""
+        need = RangeProof.rng_bytes_needed(statement.generators, len(statement.commitments))
+        res = RangeProof.prove_batch([transcript], [statement], [witness], [rng.fill(need)])[0]
+        if isinstance(res, EngineError):
+            raise res
+        return res
+
     # ---- verification
     @staticmethod
     def verify_batch(transcripts, statements, proofs, action):

@@ -42,6 +42,7 @@ struct fe { uint32_t v[8]; };
 struct sc { uint32_t v[8]; };
 struct ge { fe X, Y, Z, T; };            // extended coordinates, x = X/Z, y = Y/Z, T = XY/Z
 struct aniels { fe ypx, ymx, t2d; };     // affine Niels: (y+x, y-x, 2d*x*y); identity = (1, 1, 0)
+struct cached { fe ymx, ypx, z2, t2d; }; // projective Niels ("cached"): (Y-X, Y+X, 2Z, 2dT); fields may be loose 256-bit values
 
 // ================================================================================================ PTX helpers
 #if BPP_PTX

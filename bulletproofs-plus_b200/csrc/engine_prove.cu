@@ -1,0 +1,410 @@
+// Batched prover entry point: bpp_prove_batch = P calls of RangeProof::prove_with_rng
+// (/root/reference/src/range_proof.rs:232-608) for statements of one shape, advancing in lock-step.
+//
+// Host (this file): argument checks (:239-284), RangeProofTranscript (transcripts.rs:59-194) with the witness-keyed
+// TranscriptRng, nonces (utils/generic.rs:30-60), every random draw in the reference's order, the alpha bookkeeping and the
+// final responses (:590-594), proof serialisation (:1120-1150).  Device (k_prove.cu + k_msm.cu): A, every L / R, the generator
+// and scalar folding, A1 and B.  One host<->device meeting per round: 64 bytes (L, R) down, d_L / d_R / e (<= 13 scalars) up
+// per proof.  The caller supplies the bytes its external RNG would have delivered (32 per TranscriptRng rebuild,
+// log2(n*m) + 3 rebuilds), so a seeded RNG reproduces the reference's proof bytes.
+#include <algorithm>
+#include <cstring>
+#include "engine.hpp"
+#include "hash.cuh"
+
+using namespace bpp;
+
+namespace {
+
+#define LBL(s) (const uint8_t *)(s), (sizeof(s) - 1)
+
+inline sc sc_load(const uint8_t *b) { return sc_frombytes_raw(b); }
+inline void sc_store(uint8_t *b, const sc &a) { sc_tobytes(b, a); }
+inline sc sc_reduce_bytes(const uint8_t *b) { return sc_reduce256(sc_frombytes_raw(b)); }
+inline bool zero32(const uint8_t *p) { uint8_t r = 0; for (int i = 0; i < 32; i++) r |= p[i]; return r == 0; }
+
+inline sc wide_to_sc(const uint8_t in[64]) {
+    uint32_t w[16];
+    memcpy(w, in, 64);
+    return sc_from_wide_words(w);
+}
+
+struct PProof {
+    int32_t rc = 0;
+    bool live = false;             // takes part in the device batch
+    uint32_t slot = 0;             // index inside the device batch
+    Merlin t;
+    MerlinRng rng;
+    std::vector<uint8_t> witness;  // LE64(v) || r[0..ext) per opening (transcripts.rs:91-109)
+    bool has_seed = false;
+    uint8_t seed[32];
+    const uint8_t *rng_bytes = nullptr;
+    size_t rng_used = 0;
+    sc alpha[BPP_MAX_EXT];
+    sc y, z, e_final;
+    std::vector<sc> e_round, dL, dR;   // per round (dL/dR: rounds x ext)
+    sc r, s, d[BPP_MAX_EXT], eta[BPP_MAX_EXT];
+    uint8_t A[32], A1[32], B[32];
+    std::vector<uint8_t> LR;           // rounds x 64
+};
+
+// utils/generic.rs:30-60
+sc nonce(const uint8_t seed[32], const char *label, bool have_j, uint32_t j, bool have_k, uint32_t k) {
+    uint8_t key[43];
+    size_t kl = 0;
+    key[kl++] = 0;
+    memcpy(key + kl, seed, 32); kl += 32;
+    if (have_j) { key[kl++] = 'j'; for (int i = 0; i < 4; i++) key[kl++] = (uint8_t)(j >> (8 * i)); }
+    if (have_k) { key[kl++] = 'k'; for (int i = 0; i < 4; i++) key[kl++] = (uint8_t)(k >> (8 * i)); }
+    uint8_t h[64];
+    blake2b_keyed_personal_empty(h, key, kl, (const uint8_t *)label, strlen(label));
+    return wide_to_sc(h);
+}
+// Scalar::random_not_zero over the TranscriptRng (protocols/scalar_protocol.rs:20-30)
+sc random_not_zero(MerlinRng &rng) {
+    for (;;) {
+        uint8_t wide[64];
+        rng.fill(wide, 64);
+        sc v = wide_to_sc(wide);
+        if (!sc_is_zero(v)) return v;
+    }
+}
+// transcripts.rs:185-194: transcript.build_rng().rekey_with_witness_bytes("witness", w).finalize(external rng)
+void rebuild_rng(PProof &p) {
+    p.rng.build(p.t, p.witness.data(), p.witness.size(), true, p.rng_bytes + 32 * p.rng_used);
+    p.rng_used++;
+}
+bool append_point(Merlin &t, const uint8_t *label, size_t ll, const uint8_t pt[32]) {
+    if (zero32(pt)) return false;
+    t.append_message(label, ll, pt, 32);
+    return true;
+}
+bool challenge(Merlin &t, const uint8_t *label, size_t ll, sc &out) {
+    uint8_t buf[64];
+    t.challenge_bytes(label, ll, buf, 64);
+    out = wide_to_sc(buf);
+    return !sc_is_zero(out);
+}
+
+} // namespace
+
+extern "C" {
+
+size_t bpp_proof_size(int32_t extension_degree, int32_t rounds) {
+    return 1 + 32 * ((size_t)extension_degree + 5 + 2 * (size_t)rounds);
+}
+
+int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_out, size_t proof_stride, int32_t *status) {
+    if (!g || !a || !status) return BPP_INVALID_ARGUMENT;
+    bpp_ctx *ctx = g->ctx;
+    const size_t P0 = a->n_proofs;
+    if (P0 == 0) return BPP_OK;
+    if (!proofs_out || !a->commitments32 || !a->values || !a->blindings32 || !a->min_values || !a->min_present || !a->transcripts || !a->rng_bytes)
+        return fail(ctx, BPP_INVALID_ARGUMENT, "null argument");
+    const uint32_t n = (uint32_t)g->n, ext = (uint32_t)g->ext;
+    const int64_t m64 = a->aggregation;
+    // RangeStatement::init (range_statement.rs:42-61)
+    if (m64 <= 0 || (m64 & (m64 - 1))) return fail(ctx, BPP_INVALID_ARGUMENT, "Number of commitments must be a power of two");
+    if (m64 > g->M) return fail(ctx, BPP_INVALID_ARGUMENT, "Not enough generators for this statement");
+    const uint32_t m = (uint32_t)m64, N = n * m;
+    uint32_t rounds = 0;
+    while ((1u << rounds) < N) rounds++;
+    if (rounds > BPP_MAX_ROUNDS) return fail(ctx, BPP_SIZE_OVERFLOW, "vector too long");
+    const size_t need_rng = 32 * ((size_t)rounds + 3), plen = bpp_proof_size((int32_t)ext, (int32_t)rounds);
+    if (a->rng_stride < need_rng) return fail(ctx, BPP_INVALID_LENGTH, "rng_stride must cover 32 bytes per TranscriptRng rebuild (log2(n*m) + 3)");
+    if (proof_stride < plen) return fail(ctx, BPP_INVALID_LENGTH, "proof_stride too small");
+    if (P0 * (uint64_t)N >= (1u << 28)) return fail(ctx, BPP_SIZE_OVERFLOW, "batch too large");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+
+    std::vector<PProof> pp(P0);
+    // ---- :264-271 value range, :275-284 opening == commitment (device commit, compared as canonical encodings)
+    for (size_t i = 0; i < P0; i++) {
+        PProof &p = pp[i];
+        p.has_seed = a->seed_present && a->seed_nonces32 && a->seed_present[i];
+        if (p.has_seed && m > 1) p.rc = BPP_INVALID_ARGUMENT;     // "Mask recovery is not supported with an aggregated statement"
+        if (!p.rc && n < 64)
+            for (uint32_t j = 0; j < m; j++)
+                if ((a->values[i * m + j] >> n) > 0) p.rc = BPP_INVALID_LENGTH;
+        for (size_t k = 0; k < (size_t)m * ext && !p.rc; k++)
+            if (!host_sc_is_canonical(a->blindings32 + 32 * (i * m * ext + k))) p.rc = BPP_INVALID_ARGUMENT;
+    }
+    {
+        std::vector<uint8_t> recommit(32 * P0 * m);
+        std::vector<uint8_t> bl(a->blindings32, a->blindings32 + 32 * P0 * m * ext);
+        for (size_t i = 0; i < P0; i++)
+            if (pp[i].rc) memset(bl.data() + 32 * i * m * ext, 0, 32 * (size_t)m * ext);
+        int32_t rc = bpp_pedersen_commit_batch(g, P0 * m, a->values, bl.data(), (int32_t)ext, recommit.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < P0; i++)
+            if (!pp[i].rc && memcmp(recommit.data() + 32 * i * m, a->commitments32 + 32 * i * m, 32 * (size_t)m)) pp[i].rc = BPP_INVALID_ARGUMENT;
+    }
+
+    // ---- RangeProofTranscript::new (:287-297), bit offsets (:300-322), alpha (:325-333)
+    std::vector<uint64_t> offs;
+    std::vector<size_t> live;
+    ctx->workers().run(P0, 8, [&](size_t i) {
+        PProof &p = pp[i];
+        if (p.rc) return;
+        p.rng_bytes = a->rng_bytes + a->rng_stride * i;
+        p.t.s.load(a->transcripts + BPP_TRANSCRIPT_BYTES * i);
+        p.t.append_message(LBL("dom-sep"), LBL("Bulletproofs+ Range Proof"));
+        bool ok = append_point(p.t, LBL("H"), g->h());
+        for (uint32_t k = 0; k < ext && ok; k++) ok = append_point(p.t, LBL("G"), g->g(k));
+        if (!ok) { p.rc = BPP_VERIFICATION_FAILED; return; }
+        p.t.append_u64(LBL("N"), n);
+        p.t.append_u64(LBL("T"), ext);
+        p.t.append_u64(LBL("M"), m);
+        for (uint32_t j = 0; j < m; j++) p.t.append_message(LBL("Ci"), a->commitments32 + 32 * (i * m + j), 32);
+        for (uint32_t j = 0; j < m; j++) p.t.append_u64(LBL("vi - minimum_value"), a->min_present[i * m + j] ? a->min_values[i * m + j] : 0);
+        p.witness.resize((size_t)m * (8 + 32 * ext));
+        for (uint32_t j = 0; j < m; j++) {
+            uint8_t *w = p.witness.data() + (size_t)j * (8 + 32 * ext);
+            le64_bytes(w, a->values[i * m + j]);
+            memcpy(w + 8, a->blindings32 + 32 * ((i * m + j) * ext), 32 * (size_t)ext);
+        }
+        rebuild_rng(p);
+        for (uint32_t j = 0; j < m; j++)
+            if (a->min_present[i * m + j] && a->values[i * m + j] < a->min_values[i * m + j]) p.rc = BPP_INVALID_ARGUMENT;   // :309-311
+        if (p.rc) { p.t.s.store(a->transcripts + BPP_TRANSCRIPT_BYTES * i); return; }
+        if (p.has_seed) sc_store(p.seed, sc_reduce_bytes(a->seed_nonces32 + 32 * i));
+        for (uint32_t k = 0; k < ext; k++) p.alpha[k] = p.has_seed ? nonce(p.seed, "alpha", false, 0, true, k) : random_not_zero(p.rng);
+        p.e_round.resize(rounds); p.dL.resize((size_t)rounds * ext); p.dR.resize((size_t)rounds * ext); p.LR.resize(64 * (size_t)rounds);
+    });
+    for (size_t i = 0; i < P0; i++)
+        if (!pp[i].rc) { pp[i].live = true; pp[i].slot = (uint32_t)live.size(); live.push_back(i); }
+    const uint32_t P = (uint32_t)live.size();
+    for (size_t i = 0; i < P0; i++) status[i] = pp[i].rc;
+    if (P == 0) return BPP_OK;
+    offs.resize((size_t)P * m);
+    for (uint32_t s = 0; s < P; s++)
+        for (uint32_t j = 0; j < m; j++) {
+            size_t i = live[s];
+            offs[(size_t)s * m + j] = a->values[i * m + j] - (a->min_present[i * m + j] ? a->min_values[i * m + j] : 0);
+        }
+
+    // ---- device state
+    PDims d;
+    d.P = P; d.n = n; d.m = m; d.N = N; d.ext = ext; d.rounds = rounds; d.gens_nm = (uint32_t)g->nm;
+    const size_t max_entries = std::max<size_t>((size_t)P * (N + ext), (size_t)2 * P * (1 + ext + N));
+    DevBuf d_offs, d_a, d_b, d_ypow, d_yinv2, d_yz, d_dlr, d_e, d_fsc, d_folded, d_mscal, d_pidx, d_segoff, d_scratch, d_res, d_enc, d_ab;
+    PinBuf h_io;
+    auto release = [&]() {
+        for (DevBuf *b : {&d_offs, &d_a, &d_b, &d_ypow, &d_yinv2, &d_yz, &d_dlr, &d_e, &d_fsc, &d_folded, &d_mscal, &d_pidx, &d_segoff, &d_scratch,
+                          &d_res, &d_enc, &d_ab})
+            b->release();
+        h_io.release();
+    };
+    MsmShape shA = msm_shape((uint32_t)((size_t)P * (N + ext)), P, 0);
+    size_t scratch_bytes = msm_scratch_bytes(shA);
+    for (uint32_t r = 0; r < rounds; r++) {
+        uint32_t nn = N >> (r + 1);
+        scratch_bytes = std::max(scratch_bytes, msm_scratch_bytes(msm_shape(2 * P * (1 + ext + 2 * nn), 2 * P, 0)));
+    }
+    scratch_bytes = std::max(scratch_bytes, msm_scratch_bytes(msm_shape(P * (4 + 2 * ext), 2 * P, 0)));
+    cudaError_t ce = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+    ok(d_offs.ensure(8 * (size_t)P * m));
+    ok(d_a.ensure(32 * (size_t)P * N)); ok(d_b.ensure(32 * (size_t)P * N));
+    ok(d_ypow.ensure(32 * (size_t)P * (N + 2))); ok(d_yinv2.ensure(32 * (size_t)P * BPP_MAX_ROUNDS));
+    ok(d_yz.ensure(64 * (size_t)P)); ok(d_dlr.ensure(64 * (size_t)P * ext)); ok(d_e.ensure(32 * (size_t)P)); ok(d_fsc.ensure(32 * 6 * (size_t)P));
+    ok(d_folded.ensure(sizeof(cached) * 2 * (size_t)P * N));
+    ok(d_mscal.ensure(32 * max_entries)); ok(d_pidx.ensure(4 * max_entries)); ok(d_segoff.ensure(4 * (2 * (size_t)P + 1)));
+    ok(d_scratch.ensure(scratch_bytes)); ok(d_res.ensure(sizeof(ge) * 2 * (size_t)P)); ok(d_enc.ensure(64 * (size_t)P)); ok(d_ab.ensure(64 * (size_t)P));
+    const size_t io_bytes = std::max<size_t>(32 * (size_t)P * (4 + 2 * ext) + 4 * (size_t)P * (4 + 2 * ext), 64 * (size_t)P * std::max<uint32_t>(ext, 1) + 64 * (size_t)P) + 4 * (2 * (size_t)P + 1) + 1024;
+    ok(h_io.ensure(io_bytes));
+    if (ce != cudaSuccess) { release(); return cuda_fail(ctx, ce, "prover buffers"); }
+    PBuffers b;
+    b.offset_values = d_offs.as<uint64_t>(); b.a = d_a.as<uint32_t>(); b.b = d_b.as<uint32_t>(); b.ypow = d_ypow.as<uint32_t>();
+    b.yinv2 = d_yinv2.as<uint32_t>(); b.yz = d_yz.as<uint32_t>(); b.dlr = d_dlr.as<uint32_t>(); b.e = d_e.as<uint32_t>(); b.fsc = d_fsc.as<uint32_t>();
+    b.folded = d_folded.as<cached>(); b.msm_scalars = d_mscal.as<uint32_t>(); b.msm_pidx = d_pidx.as<uint32_t>();
+    uint8_t *hio = h_io.as<uint8_t>();
+#define PCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { release(); return cuda_fail(ctx, _e, #call); } } while (0)
+    auto upload_offsets = [&](uint32_t n_seg, const std::vector<uint32_t> &off) -> cudaError_t {
+        memcpy(hio + io_bytes - 4 * (2 * (size_t)P + 1) - 16, off.data(), 4 * (n_seg + 1));
+        return cudaMemcpyAsync(d_segoff.p, hio + io_bytes - 4 * (2 * (size_t)P + 1) - 16, 4 * (n_seg + 1), cudaMemcpyHostToDevice, st);
+    };
+    auto run_msm = [&](uint32_t n_entries, uint32_t n_seg, const std::vector<uint32_t> &off) -> cudaError_t {
+        cudaError_t e1 = upload_offsets(n_seg, off);
+        if (e1 != cudaSuccess) return e1;
+        MsmShape sh = msm_shape(n_entries, n_seg, 0);
+        launch_msm(st, sh, d_mscal.as<uint32_t>(), n_seg > 1 ? d_segoff.as<uint32_t>() : nullptr, d_pidx.as<uint32_t>(), nullptr, g->d_table.as<aniels>(),
+                   d_scratch.p, d_res.as<ge>(), &ctx->launches, nullptr, d_folded.as<cached>());
+        launch_encode(st, n_seg, d_res.as<ge>(), d_enc.as<uint32_t>(), nullptr);
+        ctx->launches++;
+        return cudaGetLastError();
+    };
+
+    // ---- A (:334-345)
+    PCUDA(cudaMemcpyAsync(d_offs.p, offs.data(), 8 * (size_t)P * m, cudaMemcpyHostToDevice, st));
+    launch_prove_bits(st, d, b);
+    ctx->launches++;
+    for (uint32_t s = 0; s < P; s++)
+        for (uint32_t k = 0; k < ext; k++) sc_store(hio + 32 * ((size_t)s * ext + k), pp[live[s]].alpha[k]);
+    PCUDA(cudaMemcpy2DAsync(d_mscal.as<uint8_t>() + 32 * (size_t)N, 32 * (size_t)(N + ext), hio, 32 * (size_t)ext, 32 * (size_t)ext, P,
+                            cudaMemcpyHostToDevice, st));
+    {
+        std::vector<uint32_t> off(P + 1);
+        for (uint32_t s = 0; s <= P; s++) off[s] = s * (N + ext);
+        PCUDA(run_msm(P * (N + ext), P, off));
+    }
+    PCUDA(cudaMemcpyAsync(hio, d_enc.p, 32 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    PCUDA(cudaStreamSynchronize(st));
+    // ---- challenges y, z (:348, transcripts.rs:124-136), alpha update (:382-392)
+    ctx->workers().run(P, 8, [&](size_t s) {
+        PProof &p = pp[live[s]];
+        memcpy(p.A, hio + 32 * s, 32);
+        bool good = append_point(p.t, LBL("A"), p.A);
+        if (good) { rebuild_rng(p); good = challenge(p.t, LBL("y"), p.y) && challenge(p.t, LBL("z"), p.z); }
+        if (!good) { p.rc = BPP_VERIFICATION_FAILED; p.y = sc_one(); p.z = sc_one(); }
+        sc z2 = sc_mul(p.z, p.z), yN1 = sc_one();
+        for (uint32_t k = 0; k < N + 1; k++) yN1 = sc_mul(yN1, p.y);
+        sc zeven = sc_one();
+        const size_t i = live[s];
+        for (uint32_t j = 0; j < m; j++) {
+            zeven = sc_mul(zeven, z2);
+            for (uint32_t k = 0; k < ext; k++) {
+                sc r = sc_load(a->blindings32 + 32 * ((i * m + j) * ext + k));
+                p.alpha[k] = sc_add(p.alpha[k], sc_mul(sc_mul(zeven, r), yN1));
+            }
+        }
+    });
+    for (uint32_t s = 0; s < P; s++) { sc_store(hio + 64 * (size_t)s, pp[live[s]].y); sc_store(hio + 64 * (size_t)s + 32, pp[live[s]].z); }
+    PCUDA(cudaMemcpyAsync(d_yz.p, hio, 64 * (size_t)P, cudaMemcpyHostToDevice, st));
+    launch_prove_init(st, d, b);
+    ctx->launches += 2;
+
+    // ---- rounds (:409-538)
+    for (uint32_t round = 0; round < rounds; round++) {
+        const uint32_t nn = N >> (round + 1);
+        PCUDA(cudaStreamSynchronize(st));      // hio is about to be rewritten
+        ctx->workers().run(P, 8, [&](size_t s) {
+            PProof &p = pp[live[s]];
+            for (uint32_t k = 0; k < ext; k++) p.dL[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dL", true, round, true, k) : random_not_zero(p.rng);
+            for (uint32_t k = 0; k < ext; k++) p.dR[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dR", true, round, true, k) : random_not_zero(p.rng);
+            for (uint32_t k = 0; k < ext; k++) {
+                sc_store(hio + 32 * ((size_t)s * 2 * ext + k), p.dL[(size_t)round * ext + k]);
+                sc_store(hio + 32 * ((size_t)s * 2 * ext + ext + k), p.dR[(size_t)round * ext + k]);
+            }
+        });
+        PCUDA(cudaMemcpyAsync(d_dlr.p, hio, 64 * (size_t)P * ext, cudaMemcpyHostToDevice, st));
+        launch_prove_round_pre(st, d, b, nn, round);
+        ctx->launches++;
+        {
+            const uint32_t seg_len = 1 + ext + 2 * nn;
+            std::vector<uint32_t> off(2 * P + 1);
+            for (uint32_t s = 0; s <= 2 * P; s++) off[s] = s * seg_len;
+            PCUDA(cudaStreamSynchronize(st));  // hio (d_L / d_R) consumed before the offsets share the staging buffer's tail
+            PCUDA(run_msm(2 * P * seg_len, 2 * P, off));
+        }
+        PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
+        PCUDA(cudaStreamSynchronize(st));
+        ctx->workers().run(P, 8, [&](size_t s) {       // transcripts.rs:139-149
+            PProof &p = pp[live[s]];
+            memcpy(p.LR.data() + 64 * (size_t)round, hio + 64 * s, 64);
+            bool good = append_point(p.t, LBL("L"), hio + 64 * s) && append_point(p.t, LBL("R"), hio + 64 * s + 32);
+            sc e = sc_one();
+            if (good) { rebuild_rng(p); good = challenge(p.t, LBL("e"), e); }
+            if (!good) { if (!p.rc) p.rc = BPP_VERIFICATION_FAILED; e = sc_one(); }
+            p.e_round[round] = e;
+        });
+        for (uint32_t s = 0; s < P; s++) sc_store(hio + 32 * (size_t)s, pp[live[s]].e_round[round]);
+        PCUDA(cudaMemcpyAsync(d_e.p, hio, 32 * (size_t)P, cudaMemcpyHostToDevice, st));
+        launch_prove_fold(st, d, b, nn, round, g->d_table.as<aniels>());
+        ctx->launches += 3;
+    }
+
+    // ---- final (:542-594)
+    launch_prove_final_ab(st, d, b, d_ab.as<uint32_t>());
+    ctx->launches++;
+    PCUDA(cudaStreamSynchronize(st));
+    std::vector<uint8_t> ab(64 * (size_t)P);
+    PCUDA(cudaMemcpyAsync(ab.data(), d_ab.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    PCUDA(cudaStreamSynchronize(st));
+    const uint32_t len1 = 3 + ext, len2 = 1 + ext, per = len1 + len2;
+    uint8_t *h_sc = hio;
+    uint32_t *h_px = reinterpret_cast<uint32_t *>(hio + 32 * (size_t)P * per);
+    const uint32_t GEN = 0x80000000u, CACHED = 0x40000000u;
+    ctx->workers().run(P, 8, [&](size_t s) {
+        PProof &p = pp[live[s]];
+        p.r = random_not_zero(p.rng);                 // always from the rng, even with a seed nonce (:542-543)
+        p.s = random_not_zero(p.rng);
+        for (uint32_t k = 0; k < ext; k++) p.d[k] = p.has_seed ? nonce(p.seed, "d", false, 0, true, k) : random_not_zero(p.rng);
+        for (uint32_t k = 0; k < ext; k++) p.eta[k] = p.has_seed ? nonce(p.seed, "eta", false, 0, true, k) : random_not_zero(p.rng);
+        const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
+        const sc ry = sc_mul(p.r, p.y), sy = sc_mul(p.s, p.y);
+        uint8_t *sv = h_sc + 32 * s * per;
+        uint32_t *px = h_px + s * per;
+        // A1 = r*Gi[0] + s*Hi[0] + (r*y*b[0] + s*y*a[0])*H + sum d[k]*G[k]      (:574-580)
+        sc_store(sv, p.r);                       px[0] = CACHED | (uint32_t)(s * N);
+        sc_store(sv + 32, p.s);                  px[1] = CACHED | (uint32_t)((size_t)P * N + s * N);
+        sc_store(sv + 64, sc_add(sc_mul(ry, b0), sc_mul(sy, a0)));   px[2] = GEN | (uint32_t)(2 * g->nm + ext);
+        for (uint32_t k = 0; k < ext; k++) { sc_store(sv + 32 * (3 + k), p.d[k]); px[3 + k] = GEN | (uint32_t)(2 * g->nm + k); }
+        // B = (r*y*s)*H + sum eta[k]*G[k]                                        (:581-584)
+        sc_store(sv + 32 * len1, sc_mul(ry, p.s)); px[len1] = GEN | (uint32_t)(2 * g->nm + ext);
+        for (uint32_t k = 0; k < ext; k++) { sc_store(sv + 32 * (len1 + 1 + k), p.eta[k]); px[len1 + 1 + k] = GEN | (uint32_t)(2 * g->nm + k); }
+    });
+    PCUDA(cudaMemcpyAsync(d_mscal.p, h_sc, 32 * (size_t)P * per, cudaMemcpyHostToDevice, st));
+    PCUDA(cudaMemcpyAsync(d_pidx.p, h_px, 4 * (size_t)P * per, cudaMemcpyHostToDevice, st));
+    {
+        std::vector<uint32_t> off(2 * P + 1);
+        for (uint32_t s = 0; s < P; s++) { off[2 * s] = s * per; off[2 * s + 1] = s * per + len1; }
+        off[2 * P] = P * per;
+        PCUDA(cudaStreamSynchronize(st));
+        PCUDA(run_msm(P * per, 2 * P, off));
+    }
+    PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    // Zeroizing<..> of the reference (:300-301, :325, :438-464, :542-571): wipe the device copies of the secrets
+    PCUDA(cudaMemsetAsync(d_a.p, 0, 32 * (size_t)P * N, st));
+    PCUDA(cudaMemsetAsync(d_b.p, 0, 32 * (size_t)P * N, st));
+    PCUDA(cudaMemsetAsync(d_offs.p, 0, 8 * (size_t)P * m, st));
+    PCUDA(cudaMemsetAsync(d_mscal.p, 0, 32 * max_entries, st));
+    PCUDA(cudaMemsetAsync(d_dlr.p, 0, 64 * (size_t)P * ext, st));
+    PCUDA(cudaMemsetAsync(d_ab.p, 0, 64 * (size_t)P, st));
+    PCUDA(cudaStreamSynchronize(st));
+    ctx->workers().run(P, 8, [&](size_t s) {
+        const size_t i = live[s];
+        PProof &p = pp[i];
+        memcpy(p.A1, hio + 64 * s, 32);
+        memcpy(p.B, hio + 64 * s + 32, 32);
+        bool good = append_point(p.t, LBL("A1"), p.A1) && append_point(p.t, LBL("B"), p.B);      // transcripts.rs:152-162
+        if (good) { rebuild_rng(p); good = challenge(p.t, LBL("e"), p.e_final); }
+        if (!good && !p.rc) p.rc = BPP_VERIFICATION_FAILED;
+        p.t.s.store(a->transcripts + BPP_TRANSCRIPT_BYTES * i);
+        if (p.rc) return;
+        const sc e = p.e_final, e2 = sc_mul(e, e);
+        const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
+        // alpha += sum_rounds d_L*e_r^2 + d_R*e_r^-2 (:535-537), with one inversion for all rounds
+        sc prod = sc_one();
+        std::vector<sc> pre(rounds);
+        for (uint32_t r = 0; r < rounds; r++) { pre[r] = prod; prod = sc_mul(prod, p.e_round[r]); }
+        sc inv = sc_invert_gcd(prod);
+        for (int r = (int)rounds - 1; r >= 0; r--) {
+            sc einv = sc_mul(inv, pre[r]);
+            inv = sc_mul(inv, p.e_round[r]);
+            sc er2 = sc_mul(p.e_round[r], p.e_round[r]), einv2 = sc_mul(einv, einv);
+            for (uint32_t k = 0; k < ext; k++)
+                p.alpha[k] = sc_add(p.alpha[k], sc_add(sc_mul(p.dL[(size_t)r * ext + k], er2), sc_mul(p.dR[(size_t)r * ext + k], einv2)));
+        }
+        uint8_t *out = proofs_out + proof_stride * i;        // to_bytes layout (:1120-1150)
+        out[0] = (uint8_t)ext;
+        for (uint32_t k = 0; k < ext; k++)
+            sc_store(out + 1 + 32 * k, sc_add(sc_add(p.eta[k], sc_mul(p.d[k], e)), sc_mul(p.alpha[k], e2)));    // d1 (:592-594)
+        uint8_t *q = out + 1 + 32 * ext;
+        memcpy(q, p.A, 32); memcpy(q + 32, p.A1, 32); memcpy(q + 64, p.B, 32);
+        sc_store(q + 96, sc_add(p.r, sc_mul(a0, e)));           // r1 (:590)
+        sc_store(q + 128, sc_add(p.s, sc_mul(b0, e)));          // s1 (:591)
+        memcpy(q + 160, p.LR.data(), 64 * (size_t)rounds);
+        // wipe host secrets
+        memset(p.witness.data(), 0, p.witness.size());
+        for (uint32_t k = 0; k < BPP_MAX_EXT; k++) { p.alpha[k] = sc_zero(); p.d[k] = sc_zero(); p.eta[k] = sc_zero(); }
+        p.r = sc_zero(); p.s = sc_zero();
+    });
+    std::fill(ab.begin(), ab.end(), 0);
+    for (size_t i = 0; i < P0; i++) status[i] = pp[i].rc;
+    release();
+#undef PCUDA
+    return BPP_OK;
+}
+
+} // extern "C"

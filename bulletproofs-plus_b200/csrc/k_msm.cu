@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t *__restrict__ count
 // one quad per bucket; the bucket is written in cached form for the running sums
 __global__ void __launch_bounds__(128) k_msm_bucket(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
                                                    const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
-                                                   const aniels *__restrict__ gens, cached *__restrict__ buckets) {
+                                                   const aniels *__restrict__ gens, const cached *__restrict__ dync,
+                                                   cached *__restrict__ buckets) {
     const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const int role = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
     const bool valid = k < n_keys;
@@ -223,12 +224,20 @@ __global__ void __launch_bounds__(128) k_msm_bucket(uint32_t n_keys, const uint3
             uint32_t e = sorted[lo + j];
             uint32_t idx = e & 0x7fffffffu;
             uint32_t pi = pidx ? pidx[idx] : idx;
-            const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
             bool neg = (e >> 31) != 0;
-            // -Q swaps (y-x, y+x) and negates 2dxy
-            if (role == 0) q = ld_fe(neg ? &src->ypx : &src->ymx);
-            else if (role == 1) q = ld_fe(neg ? &src->ymx : &src->ypx);
-            else if (role == 3) { q = ld_fe(&src->t2d); if (neg) q = fe_sub_l(fe_zero(), q); }
+            // -Q swaps (y-x, y+x) and negates 2dxy (2dT)
+            if ((pi & 0xc0000000u) == 0x40000000u) {          // projective point in cached form (prover's folded generators)
+                const cached *src = dync + (pi & 0x3fffffffu);
+                if (role == 0) q = ld_fe(neg ? &src->ypx : &src->ymx);
+                else if (role == 1) q = ld_fe(neg ? &src->ymx : &src->ypx);
+                else if (role == 2) q = ld_fe(&src->z2);
+                else { q = ld_fe(&src->t2d); if (neg) q = fe_sub_ll(fe_zero(), q); }
+            } else {
+                const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
+                if (role == 0) q = ld_fe(neg ? &src->ypx : &src->ymx);
+                else if (role == 1) q = ld_fe(neg ? &src->ymx : &src->ypx);
+                else if (role == 3) { q = ld_fe(&src->t2d); if (neg) q = fe_sub_l(fe_zero(), q); }
+            }
         }
         c = quad_add(c, role, base, q);
     }
@@ -306,7 +315,8 @@ __global__ void __launch_bounds__(32) k_msm_combine(uint32_t n_seg, int c, int W
 
 // ------------------------------------------------------------------------------------------------ driver
 void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_offsets, const uint32_t *pidx,
-                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches, cudaEvent_t *marks) {
+                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches, cudaEvent_t *marks,
+                const cached *dync) {
     MsmScratch sc = msm_carve(sh, scratch);
     size_t n_keys = (size_t)sh.n_seg * sh.W * sh.B;
     uint32_t n_tiles = (uint32_t)((n_keys + SCAN_TILE - 1) / SCAN_TILE);
@@ -322,7 +332,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         k_msm_digits<true><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.cursor, sc.sorted);
     }
     if (marks) cudaEventRecord(marks[0], s);
-    k_msm_bucket<<<(uint32_t)((n_keys + 31) / 32), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, sc.buckets);
+    k_msm_bucket<<<(uint32_t)((n_keys + 31) / 32), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
     uint32_t nq = sh.B >= 8 ? sh.B / 8 : 1;        // quads per (segment, window)
     if (nq > 256) nq = 256;

@@ -28,10 +28,12 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c);
 // bytes of scratch needed for a shape
 size_t msm_scratch_bytes(const MsmShape &sh);
 // scalars: n_entries x 8 words, canonical.  seg_offsets: n_seg + 1 entry offsets (nullptr when n_seg == 1).
-// pidx: per-entry index into `dyn` (bit 31 clear) or `gens` (bit 31 set); nullptr = identity mapping into dyn.
+// pidx: per-entry index into `gens` (bit 31 set), `dync` (bit 30 set: projective "cached" points) or `dyn`; nullptr = identity
+// mapping into dyn.
 // result: n_seg extended points.
 void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, const uint32_t *seg_offsets, const uint32_t *pidx,
-                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches, cudaEvent_t *marks = nullptr);
+                const aniels *dyn, const aniels *gens, void *scratch, ge *result, uint64_t *launches, cudaEvent_t *marks = nullptr,
+                const cached *dync = nullptr);
 // marks (optional, 4 events): recorded after the sort phase (digits+scan+scatter), bucket sums, window reduction, Horner
 
 // ---------------------------------------------------------------- k_verify.cu
@@ -92,6 +94,27 @@ struct RBuffers {
     uint8_t *flags;                  // out: n_proofs; bit 0 = loop-1 VerificationFailed, bit 1 = y == 1
 };
 void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, uint64_t *launches);
+
+// ---------------------------------------------------------------- k_prove.cu
+struct PDims { uint32_t P, n, m, N, ext, rounds, gens_nm; };   // P proofs of one shape; N = n*m; gens_nm = n * max_aggregation
+struct PBuffers {
+    const uint64_t *offset_values;   // P x m: value - minimum_value_promise
+    uint32_t *a, *b;                 // P x N scalars, Montgomery form (a_L / a_R, folded in place)
+    uint32_t *ypow;                  // P x (N + 2): y^0 .. y^(N+1), Montgomery
+    uint32_t *yinv2;                 // P x BPP_MAX_ROUNDS: y^-(2^k), Montgomery
+    const uint32_t *yz;              // P x 2 canonical: y, z
+    const uint32_t *dlr;             // P x 2 x ext canonical: d_L[k], d_R[k] of the current round
+    const uint32_t *e;               // P canonical: round challenge
+    uint32_t *fsc;                   // P x 6: fold scalars (see k_prove_round_inv)
+    cached *folded;                  // [Gi: P x N | Hi: P x N] folded generator vectors (valid from round 1 on)
+    uint32_t *msm_scalars;           // entry scalars of the MSM being assembled (canonical)
+    uint32_t *msm_pidx;              // entry point indices
+};
+void launch_prove_bits(cudaStream_t s, const PDims &d, const PBuffers &b);
+void launch_prove_init(cudaStream_t s, const PDims &d, const PBuffers &b);
+void launch_prove_round_pre(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn, uint32_t round);
+void launch_prove_fold(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn, uint32_t round, const aniels *gens);
+void launch_prove_final_ab(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t *out);
 
 // ---------------------------------------------------------------- k_bench.cu
 // returns elapsed seconds for `iters` dependent ops in each of `threads_total` lanes; ops counted by caller

@@ -21,7 +21,6 @@ static __device__ __forceinline__ void st8(uint32_t *p, const uint32_t w[8]) {
 //
 // "cached" operand of a quad addition = (Y-X, Y+X, 2Z, 2dT), one field per role; an affine-Niels table entry is the
 // cached form with 2Z = 2.
-struct cached { fe ymx, ypx, z2, t2d; };
 
 static __device__ __forceinline__ fe shfl_fe(const fe &v, int src) {
     fe r;

@@ -159,6 +159,32 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
 int32_t bpp_vbatch_transcripts(const bpp_vbatch *vb, uint8_t *transcripts);
 void bpp_vbatch_destroy(bpp_vbatch *vb);
 
+/* ---------------------------------------------------------------- batched proving
+ * replaces P calls of RangeProof::prove_with_rng (range_proof.rs:232-608) for statements of ONE shape (same bit length,
+ * extension degree and aggregation factor m), advancing in lock-step: A, every L / R, the generator / scalar folding, A1 and B
+ * run on the device; transcripts, nonces and random draws stay on the host in the reference's exact order.
+ *   commitments32 (P x m x 32), values (P x m), blindings32 (P x m x ext x 32, canonical), min_values / min_present (P x m),
+ *   seed_nonces32 / seed_present (P; a seed needs m == 1), transcripts (P x 203 B, advanced in place),
+ *   rng_bytes (P x rng_stride): the bytes the caller's external RNG yields, 32 per TranscriptRng rebuild
+ *   (transcripts.rs:185-194), log2(n*m) + 3 rebuilds per proof; with a seeded RNG the proofs are byte-identical to the
+ *   reference's.  proofs_out: P x proof_stride (>= bpp_proof_size), status: ProofError code per proof (0 = proof written). */
+typedef struct {
+    size_t n_proofs;
+    int32_t aggregation;
+    const uint8_t *commitments32;
+    const uint64_t *values;
+    const uint8_t *blindings32;
+    const uint64_t *min_values;
+    const uint8_t *min_present;
+    const uint8_t *seed_nonces32;
+    const uint8_t *seed_present;
+    uint8_t *transcripts;
+    const uint8_t *rng_bytes;
+    size_t rng_stride;
+} bpp_prove_args;
+size_t bpp_proof_size(int32_t extension_degree, int32_t rounds);
+int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *args, uint8_t *proofs_out, size_t proof_stride, int32_t *status);
+
 /* ---------------------------------------------------------------- proof bytes (host)
  * RangeProof::from_bytes validation (range_proof.rs:1155-1257): returns BPP_OK and the number of (L,R) rounds. */
 int32_t bpp_proof_check_bytes(const uint8_t *bytes, size_t len, int32_t *extension_degree, int32_t *rounds);

@@ -284,7 +284,10 @@ class RangeProof:
                                C.addressof(seeds), C.addressof(seedp), C.addressof(tbuf), C.addressof(rbuf), need)
             out = C.create_string_buffer(plen * n)
             status = (C.c_int32 * n)()
+            import time as _time
+            _t0 = _time.perf_counter()
             _chk(params.gens.engine, _ffi.lib().bpp_prove_batch(params.gens.h, C.byref(a), out, plen, status))
+            RangeProof.last_prove_call_ms = (_time.perf_counter() - _t0) * 1e3      # the C-ABI call alone (bench)
             for k, i in enumerate(live):
                 transcripts[i].state = tbuf.raw[_ffi.TRANSCRIPT_BYTES * k: _ffi.TRANSCRIPT_BYTES * (k + 1)]
                 if status[k]:

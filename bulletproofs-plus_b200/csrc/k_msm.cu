@@ -57,12 +57,13 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     sh.n_seg = n_seg ? n_seg : 1;
     int c = forced_c;
     if (c <= 0) {
-        // minimise adds = n*W + 2*B*W per segment (bucket accumulation + running-sum reduction)
+        // cost in quad stages (one warp-wide field multiplication each) per segment: a bucket add is 2 stages, a bucket in
+        // the running sums 5 (add + re-cache + add), a window of the Horner combine 2c + 3
         double per = (double)n_entries / (double)sh.n_seg;
         double best = 1e300;
         for (int cc = 2; cc <= 16; cc++) {
             int W = (252 + cc - 1) / cc;
-            double cost = per * W + 2.5 * (double)(1u << (cc - 1)) * W;
+            double cost = 2.0 * per * W + 5.0 * (double)(1u << (cc - 1)) * W + (2.0 * cc + 3.0) * W;
             if (cost < best) { best = cost; c = cc; }
         }
     }
@@ -297,6 +298,22 @@ __global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uin
     }
 }
 
+// small bucket counts (B <= 64: the prover's many short MSMs): one quad per (segment, window) walks all B buckets itself, eight
+// (segment, window) pairs per warp -- the CTA-per-window kernel above would run one active quad per warp there
+__global__ void __launch_bounds__(128) k_msm_reduce_small(uint32_t n_win, uint32_t B, const cached *__restrict__ buckets, ge *__restrict__ windows) {
+    const uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int role = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
+    const bool valid = idx < n_win;
+    const cached *bk = buckets + (size_t)(valid ? idx : 0) * B;
+    fe S = quad_identity(role), R = quad_identity(role);
+    for (int j = (int)B - 1; j >= 0; j--) {
+        fe b = valid ? ld_fe(reinterpret_cast<const fe *>(&bk[j]) + role) : quad_cached_identity(role);
+        S = quad_add(S, role, base, b);
+        R = quad_add(R, role, base, quad_to_cached(S, role, base));
+    }
+    if (valid) st_fe(reinterpret_cast<fe *>(&windows[idx]) + role, R);
+}
+
 // ------------------------------------------------------------------------------------------------ 6: Horner
 // one quad per segment
 __global__ void __launch_bounds__(32) k_msm_combine(uint32_t n_seg, int c, int W, const ge *__restrict__ windows, ge *__restrict__ result) {
@@ -334,10 +351,15 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     if (marks) cudaEventRecord(marks[0], s);
     k_msm_bucket<<<(uint32_t)((n_keys + 31) / 32), 128, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
-    uint32_t nq = sh.B >= 8 ? sh.B / 8 : 1;        // quads per (segment, window)
-    if (nq > 256) nq = 256;
-    uint32_t L = sh.B / nq;
-    k_msm_reduce<<<sh.n_seg * sh.W, (4 * nq + 31u) / 32u * 32u, 0, s>>>(sh.B, L, nq, sc.buckets, sc.windows);
+    if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
+        uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
+        k_msm_reduce_small<<<(n_win + 31) / 32, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
+    } else {
+        uint32_t nq = sh.B >= 8 ? sh.B / 8 : 1;        // quads per (segment, window)
+        if (nq > 256) nq = 256;
+        uint32_t L = sh.B / nq;
+        k_msm_reduce<<<sh.n_seg * sh.W, (4 * nq + 31u) / 32u * 32u, 0, s>>>(sh.B, L, nq, sc.buckets, sc.windows);
+    }
     if (marks) cudaEventRecord(marks[2], s);
     k_msm_combine<<<(sh.n_seg + 7) / 8, 32, 0, s>>>(sh.n_seg, sh.c, sh.W, sc.windows, result);
     if (marks) cudaEventRecord(marks[3], s);

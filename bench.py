@@ -153,6 +153,68 @@ def workload_config(args):
             "l2": "flushed between timed steps (256 MiB device memset outside the per-step CUDA-event brackets)"}
 
 
+def run_extras(eng, api, bpp, orc, args):
+    """proving throughput (batched lock-step prover, C-ABI call with host buffers) and raw MSM throughput (device-resident
+    points, scalars uploaded once), both on this GPU; CPU oracle beside the prover on a bounded sample"""
+    import hashlib
+
+    out = {}
+    # ---- prover: P non-aggregated 64-bit proofs per bpp_prove_batch call (BASELINE.json configs[0] shape, batched)
+    P = args.prove_batch
+    gp = api.RangeParameters.init(eng, BIT_LENGTH, 1, EXT)
+    rng = orc.Rng("chacha", 4242)
+    vals = [rng.next_u64() % (1 << 63) for _ in range(P)]
+    blinds = [[rng.random_not_zero()] for _ in range(P)]
+    commits = gp.gens.commit_batch(vals, blinds)
+    sts = [api.RangeStatement.init(gp, [commits[i]], [vals[i] // 3], rng.random_not_zero()) for i in range(P)]
+    wits = [api.RangeWitness.init([api.CommitmentOpening(vals[i], blinds[i])]) for i in range(P)]
+    need = api.RangeProof.rng_bytes_needed(gp, 1)
+    streams = [hashlib.shake_256(b"bench-rng-%d" % i).digest(need) for i in range(P)]
+    times = []
+    for _ in range(4):
+        trs = [api.Transcript(b"BatchedRangeProofTest") for _ in range(P)]
+        proofs = api.RangeProof.prove_batch(trs, sts, wits, streams)
+        times.append(api.RangeProof.last_prove_call_ms)
+    assert not any(isinstance(p, Exception) for p in proofs)
+    ms = sorted(times[1:])[len(times[1:]) // 2]
+    # byte-identical to the CPU oracle on the first proofs, and timed there on a bounded sample (single thread)
+    op = orc.Params(BIT_LENGTH, 1, EXT)
+    t0 = time.perf_counter()
+    n_cpu = 8
+    for i in range(n_cpu):
+        st = orc.St(op, [commits[i]], [vals[i] // 3], sts[i].seed_nonce)
+        rc, pr, _ = orc.prove(orc.transcript_new(b"BatchedRangeProofTest"), st, orc.Wit([vals[i]], [blinds[i]]), orc.Rng("buffer", data=streams[i]))
+        assert rc == 0 and orc.proof_to_bytes(pr) == proofs[i].to_bytes()
+    cpu_s = (time.perf_counter() - t0) / n_cpu
+    out["prove"] = {"metric": "64-bit range proofs proved/sec (batched lock-step, 1 GPU, through bpp_prove_batch with host buffers)",
+                    "value": P / (ms * 1e-3), "unit": "proofs/s", "batch": P, "ms_per_batch": ms,
+                    "cpu_oracle_proofs_per_s_per_core": 1.0 / cpu_s, "byte_identical_to_oracle_checked": n_cpu}
+    # ---- raw MSM (BASELINE.json configs[4]), device-resident decoded points
+    msm = {}
+    for lg in args.msm_log2:
+        nn = 1 << lg
+        seed = hashlib.shake_256(b"msm-points").digest(64)
+        uni = hashlib.shake_256(seed).digest(64 * min(nn, 1 << 14))
+        pts = eng.from_uniform(uni)
+        pts = (pts * ((nn * 32 + len(pts) - 1) // len(pts)))[: 32 * nn]          # repeat a 16 k-point set (duplicates are legal MSM input)
+        plan = bpp.pkg.MsmPlan(eng, pts)
+        sc = hashlib.shake_256(b"msm-scalars-%d" % lg).digest(32 * nn)
+        sc = bytearray(sc)
+        for i in range(31, len(sc), 32):
+            sc[i] &= 0x0F                                                           # < 2^252 < l: canonical
+        plan.set_scalars(bytes(sc))
+        plan.run(True)
+        reps = 5 if lg <= 20 else 2
+        eng.timer_start()
+        for _ in range(reps):
+            plan.run(False)
+        t = eng.timer_stop() / reps
+        msm["2^%d" % lg] = {"mpoints_per_s": nn / t / 1e3, "ms": t, "window_bits": plan.window_bits}
+        plan.close()
+    out["msm"] = msm
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
 
@@ -257,6 +319,11 @@ def run_b200(args, rank, local_rank, world):
     io_h2d, io_d2h = eng.io_bytes()
     barrier()
 
+    # ---------------- secondary metrics (BASELINE.json: "proving at 1 GPU", "MSM Mpoints/s"), rank 0 only, not the headline
+    extras = {}
+    if rank == 0 and args.extras:
+        extras = run_extras(eng, api, bpp, orc, args)
+
     # ---------------- reduce over ranks (max time)
     times = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
     if dist:
@@ -324,7 +391,7 @@ def run_b200(args, rank, local_rank, world):
             "e2e": {"value": world * args.proofs * args.steps / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads": min(64, threads),
                     "host_ms_per_step": {k: round(v, 4) for k, v in host_acc.items()}},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
@@ -341,6 +408,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--proofs", type=int, default=1024, help="proofs per GPU per step")
+    ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput on rank 0 (secondary metrics)")
+    ap.add_argument("--prove-batch", type=int, default=1024)
+    ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()

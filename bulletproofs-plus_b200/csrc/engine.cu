@@ -66,6 +66,7 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     for (DevBuf *b : {&ctx->d_in, &ctx->d_in2, &ctx->d_tab, &ctx->d_flags, &ctx->d_out, &ctx->d_scratch, &ctx->d_res, &ctx->d_misc}) b->release();
     ctx->h_stage.release(); ctx->h_stage2.release();
     vwork_pool_free(ctx);
+    prove_ws_free(ctx);
     delete ctx->pool;
     if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
     for (int i = 0; i < bpp_ctx::N_MARKS; i++) if (ctx->ph[i]) cudaEventDestroy(ctx->ph[i]);

@@ -74,6 +74,7 @@ struct bpp_ctx {
     bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc;
     bpp::PinBuf h_stage, h_stage2;
     std::vector<void *> vwork_pool;     // pooled verification workspaces (engine_verify.cu)
+    void *prove_ws = nullptr;           // persistent prover workspace (engine_prove.cu)
 };
 
 struct bpp_gens {
@@ -91,6 +92,7 @@ struct bpp_gens {
 
 namespace bpp {
 void vwork_pool_free(bpp_ctx *ctx);
+void prove_ws_free(bpp_ctx *ctx);
 int32_t fail(bpp_ctx *ctx, int32_t code, const char *what);
 int32_t cuda_fail(bpp_ctx *ctx, cudaError_t e, const char *where);
 #define BPP_CUDA(ctx, call)                                             \

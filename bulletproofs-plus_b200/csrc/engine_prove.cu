@@ -86,7 +86,26 @@ bool challenge(Merlin &t, const uint8_t *label, size_t ll, sc &out) {
     return !sc_is_zero(out);
 }
 
+// device + pinned buffers of the prover, kept per ctx across calls (grow-only; cudaMalloc / cudaFree of the ~200 MB bucket
+// scratch cost more than the proving itself); the secrets in them are wiped at the end of every call
+struct ProveWS {
+    DevBuf d_offs, d_a, d_b, d_ypow, d_yinv2, d_yz, d_dlr, d_e, d_fsc, d_folded, d_mscal, d_pidx, d_segoff, d_scratch, d_res, d_enc, d_ab;
+    PinBuf h_io;
+    void release() {
+        for (DevBuf *b : {&d_offs, &d_a, &d_b, &d_ypow, &d_yinv2, &d_yz, &d_dlr, &d_e, &d_fsc, &d_folded, &d_mscal, &d_pidx, &d_segoff, &d_scratch,
+                          &d_res, &d_enc, &d_ab})
+            b->release();
+        h_io.release();
+    }
+};
+
 } // namespace
+
+namespace bpp {
+void prove_ws_free(bpp_ctx *ctx) {
+    if (ctx->prove_ws) { ((ProveWS *)ctx->prove_ws)->release(); delete (ProveWS *)ctx->prove_ws; ctx->prove_ws = nullptr; }
+}
+}
 
 extern "C" {
 
@@ -187,14 +206,13 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     PDims d;
     d.P = P; d.n = n; d.m = m; d.N = N; d.ext = ext; d.rounds = rounds; d.gens_nm = (uint32_t)g->nm;
     const size_t max_entries = std::max<size_t>((size_t)P * (N + ext), (size_t)2 * P * (1 + ext + N));
-    DevBuf d_offs, d_a, d_b, d_ypow, d_yinv2, d_yz, d_dlr, d_e, d_fsc, d_folded, d_mscal, d_pidx, d_segoff, d_scratch, d_res, d_enc, d_ab;
-    PinBuf h_io;
-    auto release = [&]() {
-        for (DevBuf *b : {&d_offs, &d_a, &d_b, &d_ypow, &d_yinv2, &d_yz, &d_dlr, &d_e, &d_fsc, &d_folded, &d_mscal, &d_pidx, &d_segoff, &d_scratch,
-                          &d_res, &d_enc, &d_ab})
-            b->release();
-        h_io.release();
-    };
+    if (!ctx->prove_ws) ctx->prove_ws = new ProveWS();
+    ProveWS &ws = *(ProveWS *)ctx->prove_ws;
+    DevBuf &d_offs = ws.d_offs, &d_a = ws.d_a, &d_b = ws.d_b, &d_ypow = ws.d_ypow, &d_yinv2 = ws.d_yinv2, &d_yz = ws.d_yz, &d_dlr = ws.d_dlr,
+           &d_e = ws.d_e, &d_fsc = ws.d_fsc, &d_folded = ws.d_folded, &d_mscal = ws.d_mscal, &d_pidx = ws.d_pidx, &d_segoff = ws.d_segoff,
+           &d_scratch = ws.d_scratch, &d_res = ws.d_res, &d_enc = ws.d_enc, &d_ab = ws.d_ab;
+    PinBuf &h_io = ws.h_io;
+    auto release = [&]() {};       // buffers stay with the ctx
     MsmShape shA = msm_shape((uint32_t)((size_t)P * (N + ext)), P, 0);
     size_t scratch_bytes = msm_scratch_bytes(shA);
     for (uint32_t r = 0; r < rounds; r++) {

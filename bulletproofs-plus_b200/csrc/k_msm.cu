@@ -12,6 +12,8 @@
 //   4. k_msm_bucket   one thread per bucket: sum its points (affine-Niels mixed adds)   (IMAD-bound phase)
 //   5. k_msm_reduce   one block per (seg, window): sum_b (b+1)*bucket[b] by chunked running sums + tree reduce
 //   6. k_msm_combine  one thread per segment: Horner over the windows
+// field multiplications are inlined in this translation unit: every kernel here is a short loop around two or three of them
+#define BPP_INLINE_MUL
 #include "kernels.cuh"
 #include "quad.cuh"
 
@@ -57,13 +59,22 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     sh.n_seg = n_seg ? n_seg : 1;
     int c = forced_c;
     if (c <= 0) {
-        // cost in quad stages (one warp-wide field multiplication each) per segment: a bucket add is 2 stages, a bucket in
-        // the running sums 5 (add + re-cache + add), a window of the Horner combine 2c + 3
+        // Small segments (the verifier's 4226-entry chunks, the prover's L / R): cost in quad stages (one warp-wide field
+        // multiplication each) per segment -- a bucket add is 2 stages, a bucket in the running sums 5 (add + re-cache +
+        // add), a window of the Horner combine 2c + 3.  Large segments are throughput-bound in the bucket sums
+        // (~0.136 ns per add measured at 2^22) and latency-bound in the running sums (~48 ns per bucket of one window).
+        // Recoded scalars are < 2^251, so the top window only has t = 251 - c(W-1) magnitude bits: windows whose top is less
+        // than a quarter full are skipped once segments are large (their few non-empty buckets would each get n / 2^t
+        // entries: c = 13 at 2^20 points measured 120 ms against 3.9 ms for c = 14).
         double per = (double)n_entries / (double)sh.n_seg;
         double best = 1e300;
         for (int cc = 2; cc <= 16; cc++) {
             int W = (252 + cc - 1) / cc;
-            double cost = 2.0 * per * W + 5.0 * (double)(1u << (cc - 1)) * W + (2.0 * cc + 3.0) * W;
+            int top_bits = 251 - cc * (W - 1);
+            if (per >= 1024 && top_bits < cc - 3) continue;
+            double B = (double)(1u << (cc - 1));
+            double cost = per >= 16384 ? per * W * 0.136 + B * 48.0 * (sh.n_seg > 1 ? (double)sh.n_seg * W / 148.0 : 1.0)
+                                       : 2.0 * per * W + 5.0 * B * W + (2.0 * cc + 3.0) * W;
             if (cost < best) { best = cost; c = cc; }
         }
     }

@@ -346,16 +346,35 @@ def run_b200(args, rank, local_rank, world):
                 "vprep_proof": args.proofs * (130 + 380) * 100,    # ~130 scalar products + one inversion (~380 at a^(l-2) cost), 100 mul32 each
                 "vprep_vector": args.proofs * BIT_LENGTH * (3 * 6 + 8) * 100,
                 "vprep_weigh": (entries + args.proofs * 2 * BIT_LENGTH) * 100}
-        alg = work.get(dominant)
-        roof = {"bound": "int32-multiply (IMAD.WIDE issue rate; the path is modular big-integer arithmetic, neither HBM- nor tensor-bound)",
-                "kernel": dominant, "unit": "Tmul32/s", "peak": peak_ops / 1e12,
-                "peak_source": "bpp_microbench IMAD.WIDE measured in this run (MEASURED_PEAKS.json has no integer figure)",
-                "phase_ms": per_launch, "traffic": None}
-        if alg:
-            ach = alg / (per_launch[dominant] * 1e-3) / 1e12
-            roof.update({"achieved": ach, "frac": ach / roof["peak"], "algorithmic_mul32_per_launch": alg})
-        else:
-            roof.update({"achieved": None, "frac": None})
+        # Keccak-f[1600] of the transcript replay: ~130 64-bit logic / rotate ops per round = 260 32-bit ALU ops, 24 rounds, ~21
+        # permutations per 64-bit proof; its ceiling is the ALU pipe (LOP3 / IADD3 / SHF), measured by bpp_microbench(3)
+        alu_ops, _ = eng.microbench(3, 2000)
+        alu_work = {"replay": args.proofs * 21 * 24 * 260}
+        per_kernel = {}
+        for k, ms in per_launch.items():
+            if ms <= 0:
+                continue
+            if k in work:
+                ach = work[k] / (ms * 1e-3) / 1e12
+                per_kernel[k] = {"ms": ms, "achieved": ach, "peak": peak_ops / 1e12, "unit": "Tmul32/s", "frac": ach / (peak_ops / 1e12)}
+            elif k in alu_work:
+                ach = alu_work[k] / (ms * 1e-3) / 1e12
+                per_kernel[k] = {"ms": ms, "achieved": ach, "peak": alu_ops / 1e12, "unit": "Top32/s (ALU pipe)", "frac": ach / (alu_ops / 1e12)}
+            else:
+                per_kernel[k] = {"ms": ms}
+        dom = per_kernel[dominant]
+        roof = {"bound": "int32-multiply issue rate (IMAD.WIDE) for the arithmetic kernels, ALU issue rate for the Keccak replay; the path is "
+                         "modular big-integer arithmetic and hashing, neither HBM- nor tensor-bound (DRAM traffic per step: a few MB, "
+                         "profiles/r01_ncu_summary.md)",
+                "kernel": dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
+                "peak_source": "bpp_microbench (IMAD.WIDE / LOP3+IADD3 issue rates) measured in this run; MEASURED_PEAKS.json has no integer figure",
+                "algorithmic_work_per_launch": work.get(dominant, alu_work.get(dominant)),
+                "per_kernel": per_kernel, "phase_ms": per_launch,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` captures (profiles/r01_ncu_summary.md)
+                "traffic": {"replay": 964352, "msm_combine": 34304, "decompress": 588288, "vprep_proof": 547328, "msm_bucket": 3670784}.get(dominant),
+                "traffic_unit": "bytes per launch (ncu, round 1)",
+                "note": "every kernel of a 1024-proof step is latency-bound (one dependent chain per thread / quad at 2-30 % occupancy); "
+                        "throughput-regime numbers are in extras.msm"}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")

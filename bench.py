@@ -4,8 +4,10 @@
 One "step" = one pass of the verification hot path over one batch of synthetic proofs: BASELINE.json configs[1],
 "verify_batch of 1024 non-aggregated 64-bit proofs on 1 B200", issued as 4 reference calls of 256 proofs
 (RangeProof::verify_batch looks at 256 proofs per call, /root/reference/src/range_proof.rs:739-751).
-  value  : proofs/s with inputs resident in HBM (bpp_vbatch_run: decompress -> scalar prep -> segmented MSM -> verdicts)
-  e2e    : proofs/s through bpp_verify_chunks with HOST buffers (Fiat-Shamir replay, H2D, kernels, D2H inside the timing)
+  value  : proofs/s with inputs resident in HBM (bpp_vbatch_run: replay -> decompress -> scalar prep -> segmented MSM -> verdicts)
+  e2e    : proofs/s through bpp_verify_chunks with HOST buffers (parsing, Fiat-Shamir, H2D, kernels, D2H inside the timing)
+  Steps are independent; they are issued from --lanes lanes (api.VerifierPool: one bpp_ctx + host thread each) so that
+  consecutive steps overlap on the GPU.  `one_batch_at_a_time` repeats the measurement with a single lane (latency).
   N > 1  : one process per GPU (torchrun), every rank verifies its own 1024 proofs per step ("weak"), no collective
            on the data path; barrier + max-over-ranks timing.
   --impl reference : the CPU restatement of the reference (oracle/, multi-threaded over independent verify_batch calls).
@@ -150,7 +152,10 @@ def workload_config(args):
                         "per GPU per step, as %d reference calls of <=256 (BASELINE.json configs[1])" % (args.proofs, (args.proofs + CHUNK - 1) // CHUNK),
             "proofs_per_step_per_gpu": args.proofs, "bit_length": BIT_LENGTH, "extension_degree": EXT, "action": "VerifyOnly",
             "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay)",
-            "l2": "flushed between timed steps (256 MiB device memset outside the per-step CUDA-event brackets)"}
+            "steps_in_flight": "independent steps are issued from `lanes_per_gpu` lanes (one bpp_ctx + host thread each) and overlap on the GPU; "
+                               "the K timed steps are bracketed once (barrier + synchronize + CUDA events on both sides)",
+            "l2": "flushed between timed steps: every lane overwrites a %d MiB device buffer on its stream before each of its steps, "
+                  "inside the timed region (inputs of a step are ~1.3 MB, far below L2)" % int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144"))}
 
 
 def run_extras(eng, api, bpp, orc, args):
@@ -230,25 +235,26 @@ def run_b200(args, rank, local_rank, world):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api = bpp.pkg.api
-    eng = bpp.pkg.Engine(local_rank)
+    lib = bpp.ffi.lib()
+    S = max(1, min(args.lanes, args.steps))
+    cores = os.cpu_count() or 1
+    # S independent lanes (bpp_ctx + host thread each) on this GPU; the host cores are shared by the ranks of the node
+    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=max(1, cores // (S * world)))
+    eng, params = pool.lanes[0]
     params_o, cases = make_workload(args.proofs, seed=8675309 + 1000 * rank)
-    params = api.RangeParameters.init(eng, BIT_LENGTH, 1, EXT)
 
-    def build_calls():
+    def build_calls(prm):
         calls = []
         for c in cases:
-            sts = [api.RangeStatement.init(params, s.commitments, s.min_values, s.seed_nonce) for s in c.statements]
+            sts = [api.RangeStatement.init(prm, s.commitments, s.min_values, s.seed_nonce) for s in c.statements]
             prs = [api.RangeProof.from_bytes(orc.proof_to_bytes(p)) for p in c.proofs]
             trs = [api.Transcript(state=t) for t in c.transcripts]
             calls.append((trs, sts, prs))
         return calls
 
     action = api.VerifyAction.VerifyOnly
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def l2_flush():
-        flush.fill_(1)
-        torch.cuda.synchronize()
+    FLUSH_MIB = int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144"))      # 151 MB > 126 MB of L2
+    FLUSH = FLUSH_MIB << 20
 
     def barrier():
         torch.cuda.synchronize()
@@ -256,87 +262,111 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm (value)
-    vb = api.VerifyBatch(params, build_calls(), action)
-    status, _ = vb.run()
-    assert status == [0] * len(cases), status
-    for _ in range(args.warmup):
-        vb.run()
-    phase_acc = {}
+    # every lane owns its device-resident batch (bpp_vbatch: inputs in HBM) and its host-side argument block (e2e)
+    vbs = [api.VerifyBatch(prm, build_calls(prm), action) for _, prm in pool.lanes]
+    pks = [api._Packed(prm, build_calls(prm), action) for _, prm in pool.lanes]
+    t_init = bytes(pks[0].tbuf.raw)
+    for vb in vbs:
+        status, _ = vb.run()
+        assert status == [0] * len(cases), status
+
+    # ---------------- device-resident arm (value): K steps over S lanes, L2 overwritten by every lane before every step
+    def dev_step(li, e, prm, i):
+        vb = vbs[li]
+        if FLUSH:
+            e.l2_flush(FLUSH)
+        rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
+        assert rc == 0 and all(vb.pk.status[c] == 0 for c in range(len(cases))), (rc, list(vb.pk.status))
+
+    pool.run(dev_step, S * args.warmup)
     sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
-    launches0 = eng.launch_count
+    launches0 = pool.launch_count()
     t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    lib = bpp.ffi.lib()
-    for _ in range(args.steps):
-        l2_flush()
-        eng.timer_start()
-        # the C-ABI call itself (device work + verdict readback); python-side result decoding stays outside the bracket
-        rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
-        dev_ms += eng.timer_stop()
-        assert rc == 0
-    st = [vb.pk.status[c] for c in range(len(cases))]
+    ev0.record()                       # the device is idle here (barrier above): ev0 precedes every kernel of the timed steps
+    pool.run(dev_step, args.steps)     # every C call returns after its stream has drained
+    torch.cuda.synchronize()
+    ev1.record()
+    ev1.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = eng.launch_count - launches0
+    launches = pool.launch_count() - launches0
     clocks = sampler.stop()
-    assert st == [0] * len(cases)
-    # per-kernel durations for the roofline: a second pass of the same steps with CUDA events between the kernels (the
-    # events serialise the decompression with the scalar prep, which otherwise overlap on two streams, so this pass is
-    # not the one `value` is taken from)
+
+    # ---------------- one batch at a time on one lane (latency; the per-kernel figures of the roofline come from here)
+    vb = vbs[0]
+    seq_ms = 0.0
+    n_seq = min(args.steps, 20)
+    for _ in range(n_seq):
+        eng.l2_flush(FLUSH or (144 << 20))
+        eng.sync()
+        eng.timer_start()
+        rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
+        seq_ms += eng.timer_stop()
+        assert rc == 0
+    # per-kernel durations: the same steps with CUDA events between the kernels (the events serialise the decompression
+    # with the scalar prep, which otherwise overlap on two streams)
+    phase_acc = {}
     eng.phase_timing(True)
-    for _ in range(args.steps):
-        l2_flush()
+    for _ in range(n_seq):
+        eng.l2_flush(FLUSH or (144 << 20))
         rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
         assert rc == 0
         for k, v in eng.phase_ms().items():
             phase_acc[k] = phase_acc.get(k, 0.0) + v
     eng.phase_timing(False)
 
-    # ---------------- end-to-end arm (e2e): C-ABI call with host buffers
-    pk = api._Packed(params, build_calls(), action)
-    t_init = bytes(pk.tbuf.raw)
+    # ---------------- end-to-end arm (e2e): the C-ABI call with HOST buffers, K calls over S lanes
+    host_acc = {}
 
-    def e2e_step():
+    def e2e_step(li, e, prm, i):
+        pk = pks[li]
         C.memmove(pk.tbuf, t_init, len(t_init))          # `&mut Transcript`s are advanced by the call
-        rc = lib.bpp_verify_chunks(params.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present)
+        if FLUSH:
+            e.l2_flush(FLUSH)
+        rc = lib.bpp_verify_chunks(prm.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present)
         assert rc == 0 and all(pk.status[c] == 0 for c in range(pk.k)), (rc, list(pk.status))
 
-    for _ in range(args.warmup):
-        e2e_step()
+    pool.run(e2e_step, S * args.warmup)
     barrier()
-    e2e_s = 0.0
-    host_acc = {}
-    for _ in range(args.steps):
-        l2_flush()
+    t0 = time.perf_counter()
+    pool.run(e2e_step, args.steps)                       # synchronous calls: each returns after the D2H of its verdicts
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_seq_s = 0.0
+    for _ in range(n_seq):
+        eng.l2_flush(FLUSH or (144 << 20))
+        eng.sync()
         t0 = time.perf_counter()
-        e2e_step()                                           # synchronous: returns after the D2H of the verdicts
-        e2e_s += time.perf_counter() - t0
+        e2e_step(0, eng, params, 0)
+        e2e_seq_s += time.perf_counter() - t0
         for k, v in eng.host_ms().items():
-            host_acc[k] = host_acc.get(k, 0.0) + v / args.steps
+            host_acc[k] = host_acc.get(k, 0.0) + v / n_seq
     io_h2d, io_d2h = eng.io_bytes()
     barrier()
 
     # ---------------- secondary metrics (BASELINE.json: "proving at 1 GPU", "MSM Mpoints/s"), rank 0 only, not the headline
     extras = {}
     if rank == 0 and args.extras:
+        eng.set_host_threads(min(64, cores))           # the lanes shared the host cores; the prover call below is alone
         extras = run_extras(eng, api, bpp, orc, args)
 
     # ---------------- reduce over ranks (max time)
-    times = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s, seq_ms, e2e_seq_s], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max = float(times[0]), float(times[1])
+    dev_ms_max, e2e_s_max, seq_ms_max, e2e_seq_s_max = (float(x) for x in times)
 
-    # ---------------- roofline of the dominant kernel + cpu baseline (rank 0)
+    # ---------------- roofline + cpu baseline (rank 0)
     if rank == 0:
         n_pts = args.proofs * (3 + 2 * 6 + 1)
         n_chunks = len(cases)
         entries = n_chunks * (2 * BIT_LENGTH + EXT + 1) + args.proofs * (3 + 2 * 6 + 1)
-        per_launch = {k: v / args.steps for k, v in phase_acc.items()}
-        dominant = max(per_launch, key=per_launch.get)
+        per_launch = {k: v / n_seq for k, v in phase_acc.items()}
         peak_ops, _ = eng.microbench(2, 2000)              # IMAD.WIDE (32x32+64 -> 64) issue rate, measured now on this GPU
         c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
         work = {"decompress": n_pts * MUL32_DECODE,
@@ -356,25 +386,36 @@ def run_b200(args, rank, local_rank, world):
                 continue
             if k in work:
                 ach = work[k] / (ms * 1e-3) / 1e12
-                per_kernel[k] = {"ms": ms, "achieved": ach, "peak": peak_ops / 1e12, "unit": "Tmul32/s", "frac": ach / (peak_ops / 1e12)}
+                per_kernel[k] = {"ms": ms, "mul32": work[k], "achieved": ach, "peak": peak_ops / 1e12, "unit": "Tmul32/s", "frac": ach / (peak_ops / 1e12)}
             elif k in alu_work:
                 ach = alu_work[k] / (ms * 1e-3) / 1e12
-                per_kernel[k] = {"ms": ms, "achieved": ach, "peak": alu_ops / 1e12, "unit": "Top32/s (ALU pipe)", "frac": ach / (alu_ops / 1e12)}
+                per_kernel[k] = {"ms": ms, "alu_ops": alu_work[k], "achieved": ach, "peak": alu_ops / 1e12, "unit": "Top32/s (ALU pipe)", "frac": ach / (alu_ops / 1e12)}
             else:
                 per_kernel[k] = {"ms": ms}
+        # the dominant kernel = the one that carries the most algorithmic multiplies (and the most issued instructions in the ncu
+        # launch list): the MSM bucket accumulation.  Its duration is the live CUDA-event figure of the one-batch-at-a-time pass.
+        dominant = max(work, key=lambda k: work[k] if k in per_kernel else -1)
         dom = per_kernel[dominant]
-        roof = {"bound": "int32-multiply issue rate (IMAD.WIDE) for the arithmetic kernels, ALU issue rate for the Keccak replay; the path is "
-                         "modular big-integer arithmetic and hashing, neither HBM- nor tensor-bound (DRAM traffic per step: a few MB, "
-                         "profiles/r01_ncu_summary.md)",
-                "kernel": dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
-                "peak_source": "bpp_microbench (IMAD.WIDE / LOP3+IADD3 issue rates) measured in this run; MEASURED_PEAKS.json has no integer figure",
-                "algorithmic_work_per_launch": work.get(dominant, alu_work.get(dominant)),
-                "per_kernel": per_kernel, "phase_ms": per_launch,
+        step_mul32 = sum(work[k] for k in work if k in per_kernel)
+        step_ms = dev_ms_max / args.steps
+        roof = {"bound": "int32-multiply issue rate (IMAD.WIDE); the path is modular big-integer arithmetic, neither HBM- nor tensor-bound "
+                         "(DRAM traffic per step: a few MB, profiles/r01_ncu_summary.md)",
+                "kernel": "k_" + dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
+                "peak_source": "bpp_microbench (IMAD.WIDE issue rate; LOP3+IADD3 for the Keccak kernel) measured in this run; "
+                               "MEASURED_PEAKS.json has no integer figure",
+                "algorithmic_work_per_launch": work[dominant],
+                "kernel_ms": dom["ms"],
+                "whole_step": {"mul32_per_step": step_mul32, "ms_per_step_lanes_overlapped": step_ms,
+                               "achieved": step_mul32 / (step_ms * 1e-3) / 1e12, "unit": "Tmul32/s",
+                               "frac": step_mul32 / (step_ms * 1e-3) / peak_ops,
+                               "note": "all arithmetic kernels of a step over the measured time per step with %d lanes in flight" % S},
+                "longest_kernel_one_batch_alone": max(per_launch, key=per_launch.get),
+                "per_kernel": per_kernel,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` captures (profiles/r01_ncu_summary.md)
                 "traffic": {"replay": 964352, "msm_combine": 34304, "decompress": 588288, "vprep_proof": 547328, "msm_bucket": 3670784}.get(dominant),
                 "traffic_unit": "bytes per launch (ncu, round 1)",
-                "note": "every kernel of a 1024-proof step is latency-bound (one dependent chain per thread / quad at 2-30 % occupancy); "
-                        "throughput-regime numbers are in extras.msm"}
+                "note": "one 1024-proof batch alone is a chain of latency-bound kernels (2-30 % occupancy each); the lanes overlap "
+                        "independent batches, which is what `value` measures; per_kernel holds the one-batch-alone durations"}
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
@@ -402,19 +443,24 @@ def run_b200(args, rank, local_rank, world):
                "sample": "%d x (%d proofs = %d verify_batch calls of %d), VerifyOnly, %d pthreads; C restatement, not dalek" % (
                    cpu_reps, n, len(offs) - 1, CHUNK, threads)}
         h2d, d2h = io_h2d, io_d2h          # counted by the engine from the buffers it copies (bpp_ctx_io_bytes)
+        cfg = workload_config(args)
+        cfg["lanes_per_gpu"] = S
         line = {
             "metric": METRIC, "value": world * args.proofs * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
-            "config": workload_config(args),
+            "config": cfg,
             "e2e": {"value": world * args.proofs * args.steps / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads": min(64, threads),
-                    "host_ms_per_step": {k: round(v, 4) for k, v in host_acc.items()}},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": S, "host_threads_per_lane": max(1, cores // (S * world)),
+                    "one_call_at_a_time": {"value": world * args.proofs * n_seq / e2e_seq_s_max, "ms_per_call": 1e3 * e2e_seq_s_max / n_seq,
+                                           "host_ms_per_call": {k: round(v, 4) for k, v in host_acc.items()}}},
+            "one_batch_at_a_time": {"value": world * args.proofs * n_seq / (seq_ms_max * 1e-3), "ms_per_step": seq_ms_max / n_seq, "steps": n_seq,
+                                    "note": "one lane, L2 flushed outside the per-step CUDA-event bracket (the round-1 `value`)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
-    vb.close()
+    pool.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -423,7 +469,8 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=8, help="independent verification lanes (bpp_ctx + host thread) per GPU")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--proofs", type=int, default=1024, help="proofs per GPU per step")

@@ -6,6 +6,7 @@ commitment_opening.rs, extended_mask.rs, generators/pedersen_gens.rs); see api.p
 engine-level wrappers.  There is no CPU fallback: constructing an Engine without a CUDA device raises.
 """
 import ctypes as C
+import weakref
 
 from . import _ffi
 from ._ffi import (EngineError, OK, VERIFICATION_FAILED, INVALID_ARGUMENT, INVALID_LENGTH, INVALID_BLAKE2B, SIZE_OVERFLOW,
@@ -36,8 +37,15 @@ class Engine:
             self.h = C.c_void_p()
             raise EngineError(rc, "bpp_ctx_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
         self.device = device
+        self._children = weakref.WeakSet()       # Gens / MsmPlan / VerifyBatch handles that live inside this ctx
+
+    def adopt(self, child):
+        """handles created from this ctx are closed before the ctx is (their destructors touch its stream)"""
+        self._children.add(child)
 
     def close(self):
+        for ch in sorted(getattr(self, "_children", ()), key=lambda c: isinstance(c, Gens)):      # batches and plans before their Gens
+            ch.close()
         if self.h:
             _ffi.lib().bpp_ctx_destroy(self.h)
             self.h = C.c_void_p()
@@ -58,6 +66,10 @@ class Engine:
 
     def sync(self):
         _chk(self, _ffi.lib().bpp_ctx_sync(self.h))
+
+    def l2_flush(self, nbytes=256 << 20):
+        """enqueue a write of nbytes (> L2) of scratch on the engine's stream (benchmarks: cold L2 for the next call)"""
+        _chk(self, _ffi.lib().bpp_ctx_l2_flush(self.h, nbytes))
 
     def timer_start(self):
         _chk(self, _ffi.lib().bpp_ctx_timer_start(self.h))
@@ -88,8 +100,9 @@ class Engine:
         return int(arr[0]), int(arr[1])
 
     def set_replay_mode(self, on_device):
-        """loop 1 (transcript replay) on the device (default) or on host threads"""
-        _chk(self, _ffi.lib().bpp_ctx_set_replay_mode(self.h, 1 if on_device else 0))
+        """loop 1 (transcript replay): 0 / False = host threads, 1 / True = device (kernel picked by batch size),
+        2 = device, one thread per proof, 3 = device, one warp per proof"""
+        _chk(self, _ffi.lib().bpp_ctx_set_replay_mode(self.h, int(on_device)))
 
     def host_ms(self):
         arr = (C.c_double * 6)()
@@ -143,6 +156,7 @@ class MsmPlan:
         self.n = len(points) // 32
         self.h = C.c_void_p()
         _chk(engine, _ffi.lib().bpp_msm_plan_create(engine.h, self.n, points, window_bits, C.byref(self.h)))
+        engine.adopt(self)
 
     @property
     def window_bits(self):
@@ -178,6 +192,7 @@ class Gens:
         self.engine = engine
         self.h = C.c_void_p()
         _chk(engine, _ffi.lib().bpp_gens_create(engine.h, bit_length, max_aggregation, extension_degree, C.byref(self.h)))
+        engine.adopt(self)
         self.bit_length, self.max_aggregation, self.extension_degree = bit_length, max_aggregation, extension_degree
 
     def point(self, which, index=0):

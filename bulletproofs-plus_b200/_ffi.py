@@ -96,6 +96,7 @@ def lib():
         "bpp_ctx_launch_count": (C.c_uint64, [vp]),
         "bpp_ctx_stream": (vp, [vp]),
         "bpp_ctx_set_host_threads": (i32, [vp, i32]),
+        "bpp_ctx_l2_flush": (i32, [vp, sz]),
         "bpp_ctx_timer_start": (i32, [vp]),
         "bpp_ctx_timer_stop": (i32, [vp, P(C.c_float)]),
         "bpp_ctx_phase_timing": (i32, [vp, i32]),

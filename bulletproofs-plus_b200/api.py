@@ -417,6 +417,7 @@ class VerifyBatch:
         self.params = params
         self.h = C.c_void_p()
         _chk(params.gens.engine, _ffi.lib().bpp_vbatch_create(params.gens.h, C.byref(self.pk.args), C.byref(self.h)))
+        params.gens.engine.adopt(self)
 
     def run(self):
         pk = self.pk
@@ -434,3 +435,68 @@ class VerifyBatch:
             self.close()
         except Exception:
             pass
+
+
+class VerifierPool:
+    """S independent verification lanes on ONE GPU: one bpp_ctx (stream pair, pooled workspace, generator tables) and one
+    host thread per lane.  A single verify_batch call of a few hundred proofs is a chain of short dependent kernels that
+    leaves most of the 148 SMs idle; independent calls issued from different lanes overlap on the device, and
+    the host side of call i+1 (parsing, Fiat-Shamir weights, H2D) overlaps the device side of call i.  This is the C ABI's
+    threading model ("one bpp_ctx per (thread, device); different ctxs are independent", include/bpp_b200.h) wrapped for
+    Python callers; a Rust caller does the same with one ctx per worker thread.
+
+    verify_many(batches) runs batches[i] on lane i % S and returns the per-batch (status, masks) in input order; results do
+    not depend on S (every batch is verified by the same code path as RangeProof.verify_batch)."""
+
+    def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=8, host_threads_per_lane=None):
+        import os
+
+        from . import Engine
+
+        self.lanes = []
+        per = host_threads_per_lane or max(1, (os.cpu_count() or 1) // max(1, lanes))
+        for _ in range(lanes):
+            eng = Engine(device)
+            eng.set_host_threads(per)
+            self.lanes.append((eng, RangeParameters.init(eng, bit_length, max_aggregation, extension_degree)))
+
+    def __len__(self):
+        return len(self.lanes)
+
+    def run(self, fn, n_items):
+        """fn(lane_index, engine, params, item_index) for item_index in range(n_items); item i runs on lane i % S, every lane in
+        its own thread (the C calls release the GIL); returns the results in item order, re-raises the first exception"""
+        import threading
+
+        S = len(self.lanes)
+        out, errs = [None] * n_items, []
+
+        def work(li):
+            eng, params = self.lanes[li]
+            try:
+                for i in range(li, n_items, S):
+                    out[i] = fn(li, eng, params, i)
+            except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(li,)) for li in range(min(S, n_items))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def verify_many(self, batches, action=VerifyAction.VerifyOnly):
+        """batches: list of `calls` (each a list of (transcripts, statements, proofs), one entry per reference verify_batch
+        call).  Returns [(status per call, masks per call)] in input order; transcripts are advanced in place."""
+        return self.run(lambda li, eng, params, i: verify_chunks(params, batches[i], action), len(batches))
+
+    def launch_count(self):
+        return sum(eng.launch_count for eng, _ in self.lanes)
+
+    def close(self):
+        for eng, _ in self.lanes:
+            eng.close()
+        self.lanes = []

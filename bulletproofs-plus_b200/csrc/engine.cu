@@ -63,7 +63,7 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->d_in, &ctx->d_in2, &ctx->d_tab, &ctx->d_flags, &ctx->d_out, &ctx->d_scratch, &ctx->d_res, &ctx->d_misc}) b->release();
+    for (DevBuf *b : {&ctx->d_in, &ctx->d_in2, &ctx->d_tab, &ctx->d_flags, &ctx->d_out, &ctx->d_scratch, &ctx->d_res, &ctx->d_misc, &ctx->d_flush}) b->release();
     ctx->h_stage.release(); ctx->h_stage2.release();
     vwork_pool_free(ctx);
     prove_ws_free(ctx);
@@ -80,6 +80,15 @@ const char *bpp_last_error(const bpp_ctx *ctx) { return ctx ? ctx->err.c_str() :
 int32_t bpp_ctx_sync(bpp_ctx *ctx) {
     if (!ctx) return BPP_INVALID_ARGUMENT;
     BPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+// measurement aid: overwrites a scratch buffer larger than the L2 (126 MB on B200) on the ctx stream, so that the next call on
+// this ctx starts with nothing of its own in L2
+int32_t bpp_ctx_l2_flush(bpp_ctx *ctx, size_t bytes) {
+    if (!ctx || !bytes) return BPP_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    BPP_CUDA(ctx, ctx->d_flush.ensure(bytes));
+    BPP_CUDA(ctx, cudaMemsetAsync(ctx->d_flush.p, 0x5a, bytes, ctx->stream));
     return BPP_OK;
 }
 uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -130,7 +139,9 @@ int32_t bpp_ctx_io_bytes(bpp_ctx *ctx, uint64_t *h2d_d2h) {
 }
 int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device) {
     if (!ctx) return BPP_INVALID_ARGUMENT;
+    if (on_device < 0 || on_device > 3) return BPP_INVALID_ARGUMENT;
     ctx->device_replay = on_device != 0;
+    ctx->replay_kernel = on_device == 2 ? 1 : on_device == 3 ? 2 : 0;
     return BPP_OK;
 }
 // wall-clock milliseconds of the host phases of the last bpp_vbatch_create on this ctx:

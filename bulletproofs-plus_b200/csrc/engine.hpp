@@ -50,6 +50,7 @@ struct bpp_ctx {
     cudaStream_t stream2 = nullptr;     // side stream: point decompression overlaps the scalar prep chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
     bool device_replay = true;          // loop 1 (transcript replay) on the device (k_replay.cu) or on host threads
+    int replay_kernel = 0;              // 0 = by batch size, 1 = one thread per proof, 2 = one warp per proof
     std::string err;
     uint64_t launches = 0;
     int host_threads = 1;
@@ -71,7 +72,7 @@ struct bpp_ctx {
     void mark(int i) { if (phase_timing && ph[i]) { cudaEventRecord(ph[i], stream); ph_set[i] = true; } }
     void clear_marks() { for (int i = 0; i < N_MARKS; i++) ph_set[i] = false; }
     // reusable scratch for the one-shot entry points
-    bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc;
+    bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc, d_flush;
     bpp::PinBuf h_stage, h_stage2;
     std::vector<void *> vwork_pool;     // pooled verification workspaces (engine_verify.cu)
     void *prove_ws = nullptr;           // persistent prover workspace (engine_prove.cu)

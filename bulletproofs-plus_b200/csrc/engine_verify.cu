@@ -492,7 +492,12 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
         rb.challenges = vb->dev<uint8_t>(vb->o_chal);
         uint8_t *dm = w->d_mid.as<uint8_t>();
         rb.wbytes = dm + vb->mo_wbytes; rb.flags = dm + vb->mo_flags; rb.tstates_out = dm + vb->mo_tstate;
-        launch_replay(st, d, rb, &ctx->launches);
+        // one thread per proof by default.  The warp-per-proof kernel (wstrobe.cuh) was built to shorten the dependent chain of a
+        // small batch, but measured on B200 it issues 14x more warp instructions per proof (87 k vs 6 k) for a 1024-proof
+        // replay that is no shorter (283 us vs 310 us alone) and it costs 25 % of the throughput once several batches are in
+        // flight (2.9 M vs 3.7 M proofs/s with 8 lanes); it stays selectable (bpp_ctx_set_replay_mode(ctx, 3)) and tested.
+        const bool warp_replay = ctx->replay_kernel == 2;
+        launch_replay(st, d, rb, warp_replay, &ctx->launches);
         BPP_CUDA(ctx, cudaMemcpyAsync(vb->mid(), dm, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
     }

@@ -93,7 +93,7 @@ struct RBuffers {
     uint8_t *tstates_out;            // out: n_proofs x 203
     uint8_t *flags;                  // out: n_proofs; bit 0 = loop-1 VerificationFailed, bit 1 = y == 1
 };
-void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, uint64_t *launches);
+void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, bool warp_per_proof, uint64_t *launches);
 
 // ---------------------------------------------------------------- k_prove.cu
 struct PDims { uint32_t P, n, m, N, ext, rounds, gens_nm; };   // P proofs of one shape; N = n*m; gens_nm = n * max_aggregation

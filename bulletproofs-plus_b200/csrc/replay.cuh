@@ -39,7 +39,7 @@ BPP_HASH_HD inline bool replay_is_zero32(const uint8_t *p) {
     return r == 0;
 }
 // 64 challenge bytes -> Scalar::from_bytes_mod_order_wide; false if the scalar is zero
-BPP_HASH_HD BPP_HASH_NOINLINE inline bool replay_challenge(Merlin &t, const uint8_t *label, size_t ll, uint8_t out32[32]) {
+template <class TM> BPP_HASH_HD BPP_HASH_NOINLINE inline bool replay_challenge(TM &t, const uint8_t *label, size_t ll, uint8_t out32[32]) {
 #if defined(__CUDA_ARCH__)
     __align__(8) uint8_t buf[64];
 #else
@@ -53,16 +53,18 @@ BPP_HASH_HD BPP_HASH_NOINLINE inline bool replay_challenge(Merlin &t, const uint
     sc_tobytes(out32, r);
     return !sc_is_zero(r);
 }
-BPP_HASH_HD BPP_HASH_NOINLINE inline bool replay_point(Merlin &t, const uint8_t *label, size_t ll, const uint8_t pt[32]) {
+template <class TM> BPP_HASH_HD BPP_HASH_NOINLINE inline bool replay_point(TM &t, const uint8_t *label, size_t ll, const uint8_t pt[32]) {
     if (replay_is_zero32(pt)) return false;      // identity encoding: ProofError::VerificationFailed
     t.append_message(label, ll, pt, 32);
     return true;
 }
 #define BPP_LBL(s) (const uint8_t *)(s), (sizeof(s) - 1)
 
-// returns 0 (BPP_OK) or 1 (BPP_VERIFICATION_FAILED); the transcript state is written back in both cases
-BPP_HASH_HD inline int replay_transcript_core(const ReplayIn &in, const ReplayOut &out) {
-    Merlin t;
+// returns 0 (BPP_OK) or 1 (BPP_VERIFICATION_FAILED); the transcript state is written back in both cases.
+// TM / TR = Merlin / MerlinRng (one thread per transcript: host threads) or WMerlin / WMerlinRng (one warp per transcript:
+// k_replay.cu; every lane runs this function with identical arguments and writes identical outputs).
+template <class TM, class TR> BPP_HASH_HD inline int replay_transcript_core_t(const ReplayIn &in, const ReplayOut &out) {
+    TM t;
     t.s.load(in.tstate);
     int rc = 1;
     t.append_message(BPP_LBL("dom-sep"), BPP_LBL("Bulletproofs+ Range Proof"));
@@ -91,7 +93,7 @@ BPP_HASH_HD inline int replay_transcript_core(const ReplayIn &in, const ReplayOu
         t.append_message(BPP_LBL("r1"), in.r1, 32);
         t.append_message(BPP_LBL("s1"), in.s1, 32);
         for (uint32_t k = 0; k < in.ext; k++) t.append_message(BPP_LBL("d1"), in.d1 + 32 * k, 32);
-        MerlinRng rng;
+        TR rng;
         uint8_t zeros[32];
         for (int i = 0; i < 32; i++) zeros[i] = 0;
         rng.build(t, nullptr, 0, false, zeros);       // NullRng (/root/reference/src/utils/nullrng.rs:16-40)
@@ -100,6 +102,9 @@ BPP_HASH_HD inline int replay_transcript_core(const ReplayIn &in, const ReplayOu
     } while (0);
     t.s.store(out.tstate);
     return rc;
+}
+BPP_HASH_HD inline int replay_transcript_core(const ReplayIn &in, const ReplayOut &out) {
+    return replay_transcript_core_t<Merlin, MerlinRng>(in, out);
 }
 
 } // namespace bpp

@@ -57,6 +57,8 @@ int32_t bpp_ctx_sync(bpp_ctx *ctx);
 /* number of engine kernels launched on this ctx since creation (bench.py's gpu_launches) */
 uint64_t bpp_ctx_launch_count(const bpp_ctx *ctx);
 void *bpp_ctx_stream(bpp_ctx *ctx);                   /* cudaStream_t, for event timing by the caller */
+/* measurement aid: writes `bytes` (> L2 size) of scratch on the ctx stream before the next call */
+int32_t bpp_ctx_l2_flush(bpp_ctx *ctx, size_t bytes);
 /* CUDA-event timing on the ctx stream: start records an event; stop records one, waits for it, returns milliseconds */
 int32_t bpp_ctx_timer_start(bpp_ctx *ctx);
 int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms);
@@ -66,7 +68,8 @@ int32_t bpp_ctx_timer_stop(bpp_ctx *ctx, float *ms);
 int32_t bpp_ctx_phase_timing(bpp_ctx *ctx, int32_t enable);
 int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms11);
 /* where loop 1 of the verifier (the per-proof Merlin transcript replay, range_proof.rs:816-850) runs: 1 = CUDA kernel (default),
- * 0 = host worker threads (BASELINE.json north_star's host/device split).  Results are bit-identical. */
+ * 0 = host worker threads (BASELINE.json north_star's host/device split); 2 / 3 = CUDA kernel forced to one thread per proof /
+ * one warp per proof (1 = one thread per proof).  Results are bit-identical. */
 int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
 /* wall-clock milliseconds of the host phases of the last bpp_vbatch_create / bpp_verify_chunks on this ctx:
  * ms6 = {parse + statement checks, layout + buffers, blob fill (+ loop-1 replay in host mode), weight transcripts (host mode),

@@ -16,10 +16,10 @@ VA = api.VerifyAction
 _params_cache = {}
 
 
-@pytest.fixture(autouse=True, params=["device_replay", "host_replay"])
+@pytest.fixture(autouse=True, params=["device_replay_warp", "device_replay_thread", "host_replay"])
 def replay_mode(request):
     """every test runs with loop 1 (the Merlin transcript replay) on the device and on host threads: same results"""
-    bpp.engine().set_replay_mode(request.param == "device_replay")
+    bpp.engine().set_replay_mode({"device_replay_warp": 3, "device_replay_thread": 2, "host_replay": 0}[request.param])
     yield request.param
     bpp.engine().set_replay_mode(True)
 

@@ -91,7 +91,7 @@ struct bpp_vbatch {
     std::vector<HProof> hp;
     std::vector<HChunk> hc;
     std::vector<uint64_t> chunk_offsets;
-    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, max_static = 0;
+    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, max_static = 0, max_rounds = 0;
     bool any_msm = false, any_masks = false, any_replay = false;
     bool ran = false;
     MsmShape shape;
@@ -296,6 +296,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
                 v.entry_off = n_entries;
                 v.contrib_off = contrib; contrib += 2 * N;
                 v.pv_off = pv; pv += 8 + 3 * (uint32_t)p.rounds + p.m;
+                vb->max_rounds = std::max(vb->max_rounds, (uint32_t)p.rounds);
                 n_entries += 3 + 2 * (uint32_t)p.rounds + p.m;
             }
         }
@@ -505,7 +506,7 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     if (!overlap && vb->n_pts) decompress(st);
     ctx->mark(2);
     if (vb->any_msm || vb->any_masks) {
-        launch_verify_prep(st, d, b, vb->total_vec, &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
+        launch_verify_prep(st, d, b, vb->total_vec, vb->max_rounds, &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
         if (ctx->phase_timing) { ctx->ph_set[3] = true; ctx->ph_set[4] = true; }
     }
     if (dev_replay) {       // the host hashes the weight transcripts while the device runs the weight-free scalar prep

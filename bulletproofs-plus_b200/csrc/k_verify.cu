@@ -3,8 +3,10 @@
 // Restates loop 2 of RangeProof::verify (/root/reference/src/range_proof.rs:856-1033) as three data-parallel stages:
 //   A  k_vprep_proof    one thread per proof: batch inversion, challenge powers, d_sum / y_sum, the dynamic MSM scalars
 //                       (A1, B, A, L_j, R_j, V_j), the proof's h / g_k contributions, optional mask recovery (:941-969)
-//   B  k_vprep_vector   one thread per (proof, i): contributions to gi_base_scalars[i] / hi_base_scalars[i] (:987-1003);
-//                       s[i] is evaluated directly as prod_j e_j^(+-1) instead of the reference's serial recurrence
+//   B  k_vprep_vector   one CTA per proof: contributions to gi_base_scalars[i] / hi_base_scalars[i] (:987-1003).  Every
+//                       i-dependent factor (s[i], s[N-1-i], y^-i, 2^(i mod n)) is a product over the set bits of i, so three
+//                       two-level tables (low / high half of the bits of i, built in shared memory by doubling) give each
+//                       of them with ONE multiplication per element instead of the reference's serial recurrence
 //   W  k_vprep_weight   one warp per proof: multiplies the proof's dynamic scalars by its batch weight
 //   C  k_vprep_reduce   one warp per (chunk, static slot): weighted column sums over the chunk's proofs (the `+=` of
 //                       :999-1000, :1017-1020), written as canonical scalars into the chunk's MSM entry list
@@ -12,6 +14,7 @@
 // W / C apply w_p at the end: the weights come out of a sequential Merlin transcript on the host (:811-853), and this
 // ordering lets A and B run on the device while the host is still hashing.
 // All arithmetic is mod l in Montgomery form (arith.cuh sc_montmul); results are bit-exact canonical scalars.
+#include <stdlib.h>
 #include "kernels.cuh"
 
 namespace bpp {
@@ -29,11 +32,15 @@ static __device__ __forceinline__ void st_sc(uint32_t *p, const sc &r) {
 static __device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_montmul(a, b); }
 static __device__ __forceinline__ sc ld_mont(const uint32_t *p) { return sc_to_mont(ld_sc(p)); }
 
-// pervec layout (scalars, Montgomery form), per proof at pv_off:
-//   [0] r1*e  [1] s1*e  [2] e^2  [3] e^2*z  [4] y^N  [5..7] spare      (the batch weight is applied by stages W / C)
-//   [8 + j]            e_j            j < rounds
-//   [8 + R + j]        e_j^-1
-//   [8 + 2R + k]       y^-(2^k)       k < rounds
+// pervec layout (scalars, Montgomery form), per proof at pv_off (the batch weight is applied by stages W / C).
+// Bit k of i corresponds to challenge e_j with j = R-1-k (range_proof.rs:987-996: s[i] = prod_j e_j^(+-1)):
+//   [0] U0 = r1*e*s[0]      (s[0] = prod e_j^-1)         u_i = U0 * prod_{k in bits(i)} ru_k = r1*e*y^-i*s[i]
+//   [1] V0 = s1*e*s[N-1]    (s[N-1] = prod e_j)          v_i = V0 * prod_{k in bits(i)} rv_k = s1*e*s[N-1-i]
+//   [2] Q0 = e^2*y^N                                     q_i = Q0 * prod_{k in bits(i)} rq_k = e^2*y^(N-i)*2^(i mod n)
+//   [3] e^2*z    [4..7] spare
+//   [8 + k]            ru_k = e_j^2 * y^-(2^k)           k < rounds
+//   [8 + R + k]        rv_k = e_j^-2
+//   [8 + 2R + k]       rq_k = y^-(2^k) * (2^(2^k) if 2^k < n else 1)
 //   [8 + 3R + j]       z^(2(j+1))     j < m
 #define PV_HDR 8
 
@@ -69,6 +76,7 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     sc e_inv = mm(inv, pre[R + 2]); inv = mm(inv, e);
     sc ym1_inv = mm(inv, pre[R + 1]); inv = mm(inv, ym1);
     sc y_inv = mm(inv, pre[R]); inv = mm(inv, y);
+    const sc s0 = inv;                  // (prod e_j)^-1 = s[0]
     sc ejinv[BPP_MAX_ROUNDS];
     for (int j = (int)R - 1; j >= 0; j--) { ejinv[j] = mm(inv, pre[j]); inv = mm(inv, ej[j]); }
 
@@ -132,64 +140,81 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     st_sc(hg, h);
     for (uint32_t k = 0; k < ext; k++) st_sc(hg + 8 * (1 + k), ld_mont(ps + 16 + 8 * k));
 
-    // hand-off to stage B
-    st_sc(pv, mm(e, r1));
-    st_sc(pv + 8, mm(e, s1));
-    st_sc(pv + 16, e2);
+    // hand-off to stage B (layout above); pre[R] = prod e_j = s[N-1]
+    st_sc(pv, mm(mm(e, r1), s0));
+    st_sc(pv + 8, mm(mm(e, s1), pre[R]));
+    st_sc(pv + 16, mm(e2, yN));
     st_sc(pv + 24, mm(e2, z));
-    st_sc(pv + 32, yN);
     sc yp = y_inv;
-    for (uint32_t j = 0; j < R; j++) {
-        st_sc(pv + 8 * (PV_HDR + j), ej[j]);
-        st_sc(pv + 8 * (PV_HDR + R + j), ejinv[j]);
-        st_sc(pv + 8 * (PV_HDR + 2 * R + j), yp);
+    for (uint32_t k = 0; k < R; k++) {
+        const uint32_t j = R - 1 - k;
+        st_sc(pv + 8 * (PV_HDR + k), mm(mm(ej[j], ej[j]), yp));
+        st_sc(pv + 8 * (PV_HDR + R + k), mm(ejinv[j], ejinv[j]));
+        sc rq = yp;
+        if ((1u << k) < d.bit_length) rq = mm(rq, sc_to_mont(sc_from_u64(1ull << (1u << k))));     // bit_length <= 64: k <= 5
+        st_sc(pv + 8 * (PV_HDR + 2 * R + k), rq);
         yp = mm(yp, yp);
     }
 }
 
-// thread -> (proof, i) through vec_offsets (prefix sums of N over active proofs)
-__global__ void __launch_bounds__(128) k_vprep_vector(VDims d, VBuffers b, uint32_t total) {
-    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    // binary search the owning proof
-    uint32_t lo = 0, hi = d.n_proofs;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (b.vec_offsets[mid] <= gid) lo = mid; else hi = mid;
-    }
-    const uint32_t p = lo, i = gid - b.vec_offsets[p];
+// Stage B.  Table path (rounds <= VEC_TABLE_MAX_ROUNDS): i = (hi << rl) | lo, tables T_lo[lo] = base * prod_{k in bits(lo)} r_k and
+// T_hi[hi] = prod_{k in bits(hi)} r_(rl+k) for each of the three products (u, v, q), built by doubling (T[x + 2^k] = T[x] * r_k);
+// an element then costs 4 multiplications (u, v, q, q * z^(2(party+1))).  Shared memory: 3 * (2^rl + 2^rh) scalars.
+#define VEC_TABLE_MAX_ROUNDS 15
+template <bool TABLES> __global__ void __launch_bounds__(256) k_vprep_vector(VDims d, VBuffers b) {
+    const uint32_t p = blockIdx.x;
     const VProof pr = b.proofs[p];
+    if (!pr.active) return;                               // CTA-uniform
     const uint32_t R = pr.rounds, N = 1u << R;
     const uint32_t *pv = b.pervec + 8 * (size_t)pr.pv_off;
-    const sc one_m = sc_const_R();
-    // s[i] = prod_j (bit_{R-1-j}(i) ? e_j : e_j^-1);  s[N-1-i] = its inverse pattern;  y^-i from the y^-(2^k) table
-    sc s_i = one_m, s_rev = one_m, yinv_i = one_m;
-    bool first_y = true;
-    for (uint32_t j = 0; j < R; j++) {
-        bool bit = (i >> (R - 1 - j)) & 1u;
-        sc ejv = ld_sc(pv + 8 * (PV_HDR + j)), eji = ld_sc(pv + 8 * (PV_HDR + R + j));
-        if (j == 0) { s_i = bit ? ejv : eji; s_rev = bit ? eji : ejv; }
-        else { s_i = mm(s_i, bit ? ejv : eji); s_rev = mm(s_rev, bit ? eji : ejv); }
-        if ((i >> j) & 1u) {
-            sc yk = ld_sc(pv + 8 * (PV_HDR + 2 * R + j));
-            yinv_i = first_y ? yk : mm(yinv_i, yk);
-            first_y = false;
+    const sc we2z = ld_sc(pv + 24);
+    uint32_t *c = b.contrib + 8 * (size_t)pr.contrib_off;
+    const uint32_t lgn = 31 - __clz(d.bit_length);        // bit_length is a power of two
+    if (TABLES) {
+        extern __shared__ uint32_t vec_sm[];
+        const uint32_t rl = R / 2, rh = R - rl, nlo = 1u << rl, nhi = 1u << rh, per = nlo + nhi;
+        // table t in {u, v, q}: lo entries at [t*per, t*per + nlo), hi entries behind them
+        if (threadIdx.x < 3) {
+            st_sc(vec_sm + 8 * (threadIdx.x * per), ld_sc(pv + 8 * threadIdx.x));
+            st_sc(vec_sm + 8 * (threadIdx.x * per + nlo), sc_const_R());
+        }
+        __syncthreads();
+        for (uint32_t k = 0; k < rh; k++) {                // rh >= rl
+            const uint32_t span = 1u << k, items = 6 * span;
+            for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+                const uint32_t t = it / (2 * span), r = it % (2 * span), half = r / span, x = r % span;
+                if (half == 0 && k >= rl) continue;
+                const uint32_t bitpos = half ? rl + k : k;
+                uint32_t *T = vec_sm + 8 * (t * per + (half ? nlo : 0));
+                st_sc(T + 8 * (x + span), mm(ld_sc(T + 8 * x), ld_sc(pv + 8 * (PV_HDR + t * R + bitpos))));
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+            const uint32_t lo = i & (nlo - 1), hi = i >> rl;
+            const sc u = mm(ld_sc(vec_sm + 8 * (nlo + hi)), ld_sc(vec_sm + 8 * lo));
+            const sc v = mm(ld_sc(vec_sm + 8 * (per + nlo + hi)), ld_sc(vec_sm + 8 * (per + lo)));
+            const sc q = mm(ld_sc(vec_sm + 8 * (2 * per + nlo + hi)), ld_sc(vec_sm + 8 * (2 * per + lo)));
+            const sc hterm = mm(q, ld_sc(pv + 8 * (PV_HDR + 3 * R + (i >> lgn))));
+            // gi: r1*e*y^-i*s[i] + e^2*z;  hi: s1*e*s[N-1-i] - e^2*(d[i]*y^(N-i) + z),  d[i] = z^(2(party+1)) * 2^(i mod n)
+            st_sc(c + 8 * (size_t)i, sc_add(u, we2z));
+            st_sc(c + 8 * ((size_t)N + i), sc_sub(sc_sub(v, hterm), we2z));
+        }
+    } else {
+        // very long vectors (rounds > 15): walk the set bits of i
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+            sc u = ld_sc(pv), v = ld_sc(pv + 8), q = ld_sc(pv + 16);
+            for (uint32_t k = 0; k < R; k++) {
+                if (!((i >> k) & 1u)) continue;
+                u = mm(u, ld_sc(pv + 8 * (PV_HDR + k)));
+                v = mm(v, ld_sc(pv + 8 * (PV_HDR + R + k)));
+                q = mm(q, ld_sc(pv + 8 * (PV_HDR + 2 * R + k)));
+            }
+            const sc hterm = mm(q, ld_sc(pv + 8 * (PV_HDR + 3 * R + (i >> lgn))));
+            st_sc(c + 8 * (size_t)i, sc_add(u, we2z));
+            st_sc(c + 8 * ((size_t)N + i), sc_sub(sc_sub(v, hterm), we2z));
         }
     }
-    sc wre = ld_sc(pv), wse = ld_sc(pv + 8), we2 = ld_sc(pv + 16), we2z = ld_sc(pv + 24), yN = ld_sc(pv + 32);
-    // gi: r1*e*y^-i*s[i] + e^2*z        (times w_p in k_vprep_reduce)
-    sc g = sc_add(mm(mm(wre, yinv_i), s_i), we2z);
-    // hi: s1*e*s[N-1-i] - e^2*(d[i]*y^(N-i) + z),  d[i] = z^(2(j+1)) * 2^bit
-    uint32_t party = i / d.bit_length, bitpos = i % d.bit_length;
-    sc zp = ld_sc(pv + 8 * (PV_HDR + 3 * R + party));
-    sc two_b = sc_zero();
-    two_b.v[bitpos >> 5] = 1u << (bitpos & 31);
-    sc di = mm(zp, sc_to_mont(two_b));
-    sc hterm = mm(mm(mm(di, yN), yinv_i), we2);
-    sc h = sc_sub(sc_sub(mm(wse, s_rev), hterm), we2z);
-    uint32_t *c = b.contrib + 8 * (size_t)pr.contrib_off;
-    st_sc(c + 8 * (size_t)i, g);
-    st_sc(c + 8 * ((size_t)N + i), h);
 }
 
 // one WARP per (chunk, static slot), slot in [0, 2*max_mn + ext + 1): lane l adds up proofs l, l+32, .. of the chunk, then a
@@ -236,13 +261,23 @@ __global__ void __launch_bounds__(128) k_vprep_weight(VDims d, VBuffers b) {
     for (uint32_t t = lane; t < n_dyn; t += 32) st_sc(out + 8 * t, sc_from_mont(mm(ld_sc(out + 8 * t), w)));
 }
 
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint64_t *launches, cudaEvent_t *marks) {
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_rounds, uint64_t *launches,
+                        cudaEvent_t *marks) {
     if (d.n_proofs == 0) return;
     k_vprep_proof<<<(d.n_proofs + 63) / 64, 64, 0, s>>>(d, b);
     if (marks) cudaEventRecord(marks[0], s);
     if (launches) (*launches)++;
     if (d.action != 0 /* RecoverOnly */ && total_vec) {
-        k_vprep_vector<<<(total_vec + 127) / 128, 128, 0, s>>>(d, b, total_vec);
+        // one CTA per proof; max_rounds bounds the table size (all proofs of a call share one generator set, so their vector
+        // lengths differ by the aggregation factor only)
+        const uint32_t threads = max_rounds >= 8 ? 256u : max_rounds <= 5 ? 32u : (1u << max_rounds);
+        static const bool force_direct = getenv("BPP_VPREP_DIRECT") != nullptr;      // test hook for the long-vector path
+        if (max_rounds <= VEC_TABLE_MAX_ROUNDS && !force_direct) {
+            const uint32_t rl = max_rounds / 2, rh = max_rounds - rl;
+            k_vprep_vector<true><<<d.n_proofs, threads, 3 * ((1u << rl) + (1u << rh)) * 32, s>>>(d, b);
+        } else {
+            k_vprep_vector<false><<<d.n_proofs, threads, 0, s>>>(d, b);
+        }
         if (launches) (*launches)++;
     }
     if (marks) cudaEventRecord(marks[1], s);

@@ -76,7 +76,8 @@ struct VBuffers {
     uint32_t *masks;                 // out: n_proofs x ext x 8 words (plain), may be null
 };
 // weight-free part (per proof, per (proof, i)); marks (optional, 2 events): after each of the two kernels
-void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint64_t *launches, cudaEvent_t *marks = nullptr);
+void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_rounds, uint64_t *launches,
+                        cudaEvent_t *marks = nullptr);
 // weight application + column sums into the MSM entry lists (needs b.weights)
 void launch_verify_weigh(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t max_static, uint64_t *launches);
 

@@ -104,6 +104,14 @@ class Engine:
         2 = device, one thread per proof, 3 = device, one warp per proof"""
         _chk(self, _ffi.lib().bpp_ctx_set_replay_mode(self.h, int(on_device)))
 
+    def set_graphs(self, enable):
+        """verification passes as captured CUDA graphs (default) or kernel by kernel"""
+        _chk(self, _ffi.lib().bpp_ctx_set_graphs(self.h, 1 if enable else 0))
+
+    @property
+    def graph_launch_count(self):
+        return int(_ffi.lib().bpp_ctx_graph_launch_count(self.h))
+
     def host_ms(self):
         arr = (C.c_double * 6)()
         _chk(self, _ffi.lib().bpp_ctx_host_ms(self.h, arr))

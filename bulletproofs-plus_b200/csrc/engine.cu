@@ -56,6 +56,7 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     ctx->host_threads = hc ? (int)(hc > 64 ? 64 : hc) : 1;
     if (const char *env = getenv("BPP_HOST_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 1024) ctx->host_threads = v; }
     if (const char *env = getenv("BPP_HOST_REPLAY")) ctx->device_replay = atoi(env) == 0;
+    if (const char *env = getenv("BPP_NO_GRAPHS")) ctx->use_graphs = atoi(env) == 0;
     *out = ctx;
     return BPP_OK;
 }
@@ -65,6 +66,7 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->d_in, &ctx->d_in2, &ctx->d_tab, &ctx->d_flags, &ctx->d_out, &ctx->d_scratch, &ctx->d_res, &ctx->d_misc, &ctx->d_flush}) b->release();
     ctx->h_stage.release(); ctx->h_stage2.release();
+    vgraph_cache_free(ctx);
     vwork_pool_free(ctx);
     prove_ws_free(ctx);
     delete ctx->pool;
@@ -144,6 +146,12 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device) {
     ctx->replay_kernel = on_device == 2 ? 1 : on_device == 3 ? 2 : 0;
     return BPP_OK;
 }
+int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    ctx->use_graphs = enable != 0;
+    return BPP_OK;
+}
+uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->graph_launches : 0; }
 // wall-clock milliseconds of the host phases of the last bpp_vbatch_create on this ctx:
 // 0 parse + statement checks, 1 layout + buffers, 2 blob fill (+ loop-1 replay in host mode), 3 weight transcripts (host mode),
 // 4 H2D + sync, 5 unused

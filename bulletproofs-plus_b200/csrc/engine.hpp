@@ -75,6 +75,9 @@ struct bpp_ctx {
     bpp::DevBuf d_in, d_in2, d_tab, d_flags, d_out, d_scratch, d_res, d_misc, d_flush;
     bpp::PinBuf h_stage, h_stage2;
     std::vector<void *> vwork_pool;     // pooled verification workspaces (engine_verify.cu)
+    std::vector<void *> vgraphs;        // captured verification passes, keyed by workspace + layout (engine_verify.cu)
+    uint64_t vgraph_clock = 0, graph_launches = 0;
+    bool use_graphs = true;             // replay captured CUDA graphs instead of issuing the ~35 driver calls of a pass one by one
     void *prove_ws = nullptr;           // persistent prover workspace (engine_prove.cu)
 };
 
@@ -93,6 +96,7 @@ struct bpp_gens {
 
 namespace bpp {
 void vwork_pool_free(bpp_ctx *ctx);
+void vgraph_cache_free(bpp_ctx *ctx);
 void prove_ws_free(bpp_ctx *ctx);
 int32_t fail(bpp_ctx *ctx, int32_t code, const char *what);
 int32_t cuda_fail(bpp_ctx *ctx, cudaError_t e, const char *where);

@@ -124,6 +124,40 @@ static void vwork_return(bpp_ctx *ctx, VWork *w) {
     else { w->release(); delete w; }
 }
 
+// ------------------------------------------------------------------------------------------------ CUDA graphs
+// One verification pass is ~20 kernels, 2 memsets and 5 copies.  Issued one by one that is ~35 driver calls per pass, and with
+// several lanes (one bpp_ctx + host thread each) verifying concurrently the driver's submission path, not the GPU, capped a
+// B200 at ~6.5 k passes/s whatever their size (measured: 1.7 M proofs/s with 256-proof passes, 4.4 M with 1024, 6.5 M with
+// 4096).  The pass is therefore captured once per (workspace, layout) as three graphs -- A: transcript replay + D2H of its
+// results, B: point decompression || weight-free scalar prep, C: weights H2D, weighting, MSM, verdict D2H -- split where the
+// host hashes the verifier-weight transcript, and replayed with three cudaGraphLaunch calls afterwards.
+struct VGraphKey {
+    const void *bufs[18];
+    const void *gens_table;
+    size_t n_proofs, n_chunks;
+    size_t off[22];
+    uint32_t n_pts, n_entries, total_vec, max_static, max_rounds;
+    int32_t action, ext, bit_length;
+    MsmShape shape;
+    uint8_t any_msm, any_masks, any_replay, device_replay, warp_replay;
+};
+struct VGraph {
+    VGraphKey key;
+    cudaGraphExec_t ex[3] = {nullptr, nullptr, nullptr};
+    uint64_t kernels[3] = {0, 0, 0};
+    uint64_t last_use = 0;
+};
+static void vgraph_free(VGraph *g) {
+    for (auto &e : g->ex) if (e) cudaGraphExecDestroy(e);
+    delete g;
+}
+namespace bpp {
+void vgraph_cache_free(bpp_ctx *ctx) {
+    for (void *p : ctx->vgraphs) vgraph_free((VGraph *)p);
+    ctx->vgraphs.clear();
+}
+}
+
 // Sequential part of loop 1 + the weight draw of loop 2 for every chunk (parallel over chunks): the verifier-weight
 // transcript (range_proof.rs:811, :849, :853) and random_not_zero per proof (:894).  Needs wbytes / flags of all proofs.
 static void compute_weights(bpp_vbatch *vb) {
@@ -448,6 +482,141 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     return BPP_OK;
 }
 
+// kernel arguments of one pass
+struct VLaunch {
+    VDims d;
+    VBuffers b;
+    RBuffers rb;
+    bool dev_replay, warp_replay;
+};
+static VLaunch make_launch(bpp_vbatch *vb) {
+    bpp_gens *g = vb->g;
+    bpp_ctx *ctx = g->ctx;
+    VWork *w = vb->w;
+    VLaunch L;
+    VDims &d = L.d;
+    d.n_proofs = (uint32_t)vb->n_proofs; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)g->ext;
+    d.action = vb->action;
+    VBuffers &b = L.b;
+    b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.vec_offsets = vb->dev<uint32_t>(vb->o_vecoff);
+    b.proof_scalars = vb->dev<uint32_t>(vb->o_pscal); b.challenges = vb->dev<uint32_t>(vb->o_chal);
+    b.weights = w->d_weights.as<uint32_t>(); b.weights_mont = w->d_wmont.as<uint32_t>();
+    b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
+    b.msm_scalars = w->d_mscal.as<uint32_t>(); b.contrib = w->d_contrib.as<uint32_t>(); b.hg_contrib = w->d_hg.as<uint32_t>();
+    b.pervec = w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? w->d_masks.as<uint32_t>() : nullptr;
+    L.dev_replay = vb->device_replay && vb->any_replay;
+    RBuffers &rb = L.rb;
+    rb.proofs = b.proofs; rb.tstates_in = vb->dev<uint8_t>(vb->o_tstate); rb.hg32 = vb->dev<uint8_t>(vb->o_hg);
+    rb.enc = vb->dev<uint8_t>(vb->o_enc); rb.proof_scalars = vb->dev<uint8_t>(vb->o_pscal);
+    rb.min_values = b.min_values; rb.min_present = b.min_present;
+    rb.challenges = vb->dev<uint8_t>(vb->o_chal);
+    uint8_t *dm = w->d_mid.as<uint8_t>();
+    rb.wbytes = dm + vb->mo_wbytes; rb.flags = dm + vb->mo_flags; rb.tstates_out = dm + vb->mo_tstate;
+    // one thread per proof by default.  The warp-per-proof kernel (wstrobe.cuh) was built to shorten the dependent chain of a
+    // small batch, but measured on B200 it issues 14x more warp instructions per proof (87 k vs 6 k) for a 1024-proof
+    // replay that is no shorter (283 us vs 310 us alone) and it costs 25 % of the throughput once several batches are in
+    // flight (2.9 M vs 3.7 M proofs/s with 8 lanes); it stays selectable (bpp_ctx_set_replay_mode(ctx, 3)) and tested.
+    L.warp_replay = ctx->replay_kernel == 2;
+    return L;
+}
+
+// the three sections of a pass, enqueued on the ctx streams (directly, or into a stream capture); no host synchronisation
+static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section, uint64_t *kernels) {
+    bpp_gens *g = vb->g;
+    bpp_ctx *ctx = g->ctx;
+    VWork *w = vb->w;
+    cudaStream_t st = ctx->stream;
+    const size_t n = vb->n_proofs;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
+    if (section == 0) {
+        if (L.dev_replay) {
+            launch_replay(st, L.d, L.rb, L.warp_replay, kernels);
+            ok(cudaMemcpyAsync(vb->mid(), w->d_mid.p, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
+        }
+    } else if (section == 1) {
+        const bool prep = vb->any_msm || vb->any_masks;
+        const bool fork = vb->n_pts && prep;          // decompression next to the scalar prep chain, joined at the end of the section
+        if (vb->n_pts) {
+            if (fork) { ok(cudaEventRecord(ctx->ev_fork, st)); ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
+            launch_decompress(fork ? ctx->stream2 : st, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), w->d_tab.as<aniels>(), w->d_ok.as<uint8_t>(), nullptr, nullptr);
+            (*kernels)++;
+            if (fork) ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        }
+        if (prep) launch_verify_prep(st, L.d, L.b, vb->total_vec, vb->max_rounds, kernels, nullptr);
+        if (fork) ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    } else {
+        if (vb->any_msm) {
+            ok(cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 32 * n, cudaMemcpyHostToDevice, st));
+            launch_verify_weigh(st, L.d, L.b, vb->max_static, kernels);
+            launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
+                       w->d_tab.as<aniels>(), g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), kernels, nullptr);
+            launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
+            (*kernels)++;
+            ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+        }
+        if (vb->n_pts) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
+        if (vb->any_masks) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)g->ext, cudaMemcpyDeviceToHost, st));
+    }
+    ok(cudaGetLastError());
+    return e;
+}
+
+static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L) {
+    VGraphKey k;
+    memset(&k, 0, sizeof k);
+    const VWork *w = vb->w;
+    const void *bufs[18] = {w->d_blob.p, w->d_tab.p, w->d_ok.p, w->d_mscal.p, w->d_contrib.p, w->d_hg.p, w->d_pervec.p, w->d_masks.p, w->d_scratch.p,
+                            w->d_res.p, w->d_ident.p, w->d_weights.p, w->d_wmont.p, w->d_mid.p, w->h_blob.p, w->h_out.p, w->h_mid.p, w->h_weights.p};
+    memcpy(k.bufs, bufs, sizeof bufs);
+    k.gens_table = vb->g->d_table.p;
+    k.n_proofs = vb->n_proofs; k.n_chunks = vb->n_chunks;
+    const size_t off[22] = {vb->o_enc, vb->o_proofs, vb->o_chunks, vb->o_vecoff, vb->o_pscal, vb->o_chal, vb->o_minv, vb->o_minp, vb->o_nonces, vb->o_pidx,
+                            vb->o_segoff, vb->o_tstate, vb->o_hg, vb->blob_bytes, vb->mo_wbytes, vb->mo_flags, vb->mo_tstate, vb->mid_bytes,
+                            vb->ho_ok, vb->ho_ident, vb->ho_masks, vb->hout_bytes};
+    memcpy(k.off, off, sizeof off);
+    k.n_pts = vb->n_pts; k.n_entries = vb->n_entries; k.total_vec = vb->total_vec; k.max_static = vb->max_static; k.max_rounds = vb->max_rounds;
+    k.action = vb->action; k.ext = vb->g->ext; k.bit_length = vb->g->n;
+    k.shape.n_entries = vb->shape.n_entries; k.shape.n_seg = vb->shape.n_seg; k.shape.c = vb->shape.c; k.shape.W = vb->shape.W; k.shape.B = vb->shape.B;
+    k.any_msm = vb->any_msm; k.any_masks = vb->any_masks; k.any_replay = vb->any_replay; k.device_replay = L.dev_replay; k.warp_replay = L.warp_replay;
+    return k;
+}
+
+// finds or captures the three graphs of this pass; nullptr (with *err set) if a capture failed
+static VGraph *vgraph_get(bpp_vbatch *vb, const VLaunch &L, cudaError_t *err) {
+    bpp_ctx *ctx = vb->g->ctx;
+    const VGraphKey key = make_graph_key(vb, L);
+    for (void *p : ctx->vgraphs) {
+        VGraph *g = (VGraph *)p;
+        if (!memcmp(&g->key, &key, sizeof key)) { g->last_use = ++ctx->vgraph_clock; return g; }
+    }
+    VGraph *g = new VGraph();
+    g->key = key;
+    for (int sct = 0; sct < 3; sct++) {
+        if (sct == 0 && !L.dev_replay) continue;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            cudaError_t e1 = enqueue_section(vb, L, sct, &g->kernels[sct]);
+            e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (e == cudaSuccess) e = e1;
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&g->ex[sct], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { *err = e; vgraph_free(g); cudaGetLastError(); return nullptr; }
+    }
+    if (ctx->vgraphs.size() >= 8) {          // evict the least recently used layout
+        size_t victim = 0;
+        for (size_t i = 1; i < ctx->vgraphs.size(); i++)
+            if (((VGraph *)ctx->vgraphs[i])->last_use < ((VGraph *)ctx->vgraphs[victim])->last_use) victim = i;
+        vgraph_free((VGraph *)ctx->vgraphs[victim]);
+        ctx->vgraphs.erase(ctx->vgraphs.begin() + (long)victim);
+    }
+    g->last_use = ++ctx->vgraph_clock;
+    ctx->vgraphs.push_back(g);
+    return g;
+}
+
 int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present) {
     if (!vb || !chunk_status) return BPP_INVALID_ARGUMENT;
     bpp_gens *g = vb->g;
@@ -457,18 +626,29 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     VWork *w = vb->w;
     const int ext = g->ext;
     const size_t n = vb->n_proofs;
-    VDims d;
-    d.n_proofs = (uint32_t)n; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)ext;
-    d.action = vb->action;
-    VBuffers b;
-    b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.vec_offsets = vb->dev<uint32_t>(vb->o_vecoff);
-    b.proof_scalars = vb->dev<uint32_t>(vb->o_pscal); b.challenges = vb->dev<uint32_t>(vb->o_chal);
-    b.weights = w->d_weights.as<uint32_t>(); b.weights_mont = w->d_wmont.as<uint32_t>();
-    b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
-    b.msm_scalars = w->d_mscal.as<uint32_t>(); b.contrib = w->d_contrib.as<uint32_t>(); b.hg_contrib = w->d_hg.as<uint32_t>();
-    b.pervec = w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? w->d_masks.as<uint32_t>() : nullptr;
+    const VLaunch L = make_launch(vb);
+    const VDims &d = L.d;
+    const VBuffers &b = L.b;
+    const bool dev_replay = L.dev_replay;
 
     ctx->clear_marks();
+    if (ctx->use_graphs && !ctx->phase_timing) {
+        cudaError_t ge = cudaSuccess;
+        VGraph *vg = vgraph_get(vb, L, &ge);
+        if (!vg) return cuda_fail(ctx, ge, "verification graph capture");
+        if (vg->ex[0]) {
+            BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[0], st));
+            BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
+        }
+        BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[1], st));
+        if (dev_replay) {       // the host hashes the weight transcripts while the device runs section B
+            BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_mid));
+            compute_weights(vb);
+        }
+        BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[2], st));
+        ctx->launches += vg->kernels[0] + vg->kernels[1] + vg->kernels[2];
+        ctx->graph_launches += vg->ex[0] ? 3 : 2;
+    } else {
     // The decompression (k_point.cu) only feeds the bucket sums, so it runs on the side stream next to the transcript
     // replay and the scalar prep chain; with phase timing on everything stays on one stream so that the per-phase events
     // mean what they say (replay, then decompress, then the prep).
@@ -484,22 +664,9 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
     }
     ctx->mark(0);
-    const bool dev_replay = vb->device_replay && vb->any_replay;
     if (dev_replay) {
-        RBuffers rb;
-        rb.proofs = b.proofs; rb.tstates_in = vb->dev<uint8_t>(vb->o_tstate); rb.hg32 = vb->dev<uint8_t>(vb->o_hg);
-        rb.enc = vb->dev<uint8_t>(vb->o_enc); rb.proof_scalars = vb->dev<uint8_t>(vb->o_pscal);
-        rb.min_values = b.min_values; rb.min_present = b.min_present;
-        rb.challenges = vb->dev<uint8_t>(vb->o_chal);
-        uint8_t *dm = w->d_mid.as<uint8_t>();
-        rb.wbytes = dm + vb->mo_wbytes; rb.flags = dm + vb->mo_flags; rb.tstates_out = dm + vb->mo_tstate;
-        // one thread per proof by default.  The warp-per-proof kernel (wstrobe.cuh) was built to shorten the dependent chain of a
-        // small batch, but measured on B200 it issues 14x more warp instructions per proof (87 k vs 6 k) for a 1024-proof
-        // replay that is no shorter (283 us vs 310 us alone) and it costs 25 % of the throughput once several batches are in
-        // flight (2.9 M vs 3.7 M proofs/s with 8 lanes); it stays selectable (bpp_ctx_set_replay_mode(ctx, 3)) and tested.
-        const bool warp_replay = ctx->replay_kernel == 2;
-        launch_replay(st, d, rb, warp_replay, &ctx->launches);
-        BPP_CUDA(ctx, cudaMemcpyAsync(vb->mid(), dm, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
+        launch_replay(st, d, L.rb, L.warp_replay, &ctx->launches);
+        BPP_CUDA(ctx, cudaMemcpyAsync(vb->mid(), w->d_mid.p, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
     }
     ctx->mark(1);
@@ -533,6 +700,7 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     BPP_CUDA(ctx, cudaGetLastError());
     if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
     if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)ext, cudaMemcpyDeviceToHost, st));
+    }
     BPP_CUDA(ctx, cudaStreamSynchronize(st));
     vb->ran = true;
     ctx->io_bytes[0] = vb->blob_bytes + (vb->any_msm ? 32 * n : 0);

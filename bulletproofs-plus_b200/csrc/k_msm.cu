@@ -14,6 +14,7 @@
 //   6. k_msm_combine  one thread per segment: Horner over the windows
 // field multiplications are inlined in this translation unit: every kernel here is a short loop around two or three of them
 #define BPP_INLINE_MUL
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "quad.cuh"
 
@@ -275,6 +276,74 @@ __global__ void __launch_bounds__(BUCKET_CTA) k_msm_bucket(uint32_t n_keys, cons
     if (valid) st_fe(reinterpret_cast<fe *>(&buckets[k]) + role, out);
 }
 
+// Throughput variant: one THREAD per bucket (7 sequential multiplications per mixed addition, no shuffles or role selects:
+// about half the instructions of the quad kernel per addition).  The 256 buckets of a CTA are counting-sorted by size so that
+// the 32 buckets of a warp have neighbouring sizes.  Used when there are enough buckets to fill the machine with whole threads.
+__global__ void __launch_bounds__(256) k_msm_bucket_thread(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
+                                                          const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
+                                                          const aniels *__restrict__ gens, const cached *__restrict__ dync,
+                                                          cached *__restrict__ buckets) {
+    __shared__ uint32_t s_hist[256], s_perm[256];
+    const uint32_t tid = threadIdx.x, k0 = blockIdx.x * 256u;
+    {
+        const uint32_t kk = k0 + tid;
+        const uint32_t cc = kk < n_keys ? starts[kk + 1] - starts[kk] : 0u;
+        const uint32_t bin = 255u - (cc < 255u ? cc : 255u);          // descending sizes
+        s_hist[tid] = 0;
+        __syncthreads();
+        atomicAdd(&s_hist[bin], 1u);
+        __syncthreads();
+        uint32_t v = s_hist[tid];                                      // inclusive Hillis-Steele scan over the 256 bins
+        for (int d = 1; d < 256; d <<= 1) {
+            uint32_t t = (int)tid >= d ? s_hist[tid - d] : 0u;
+            __syncthreads();
+            v += t;
+            s_hist[tid] = v;
+            __syncthreads();
+        }
+        const uint32_t before = bin ? s_hist[bin - 1] : 0u;           // buckets in strictly larger-size bins
+        __syncthreads();
+        s_hist[tid] = 0;                                               // reuse as per-bin cursors
+        __syncthreads();
+        s_perm[before + atomicAdd(&s_hist[bin], 1u)] = tid;
+        __syncthreads();
+    }
+    const uint32_t k = k0 + s_perm[tid];
+    if (k >= n_keys) return;
+    const uint32_t lo = starts[k], cnt = starts[k + 1] - lo;
+    fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
+    for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t e = sorted[lo + j];
+        const uint32_t idx = e & 0x7fffffffu;
+        const uint32_t pi = pidx ? pidx[idx] : idx;
+        const bool neg = (e >> 31) != 0;
+        const bool proj = (pi & 0xc0000000u) == 0x40000000u;          // projective "cached" point (prover's folded generators)
+        const fe *qm, *qp, *qt;                                        // (y-x, y+x, 2dxy); -Q swaps the first two and negates the third
+        fe D;
+        if (proj) {
+            const cached *src = dync + (pi & 0x3fffffffu);
+            qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
+            D = fe_mul(Z, ld_fe(&src->z2));
+        } else {
+            const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
+            qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
+            D = fe_add(Z, Z);
+        }
+        const fe A = fe_mul(fe_sub_l(Y, X), ld_fe(neg ? qp : qm));
+        const fe B = fe_mul(fe_add_l(Y, X), ld_fe(neg ? qm : qp));
+        const fe C = fe_mul(T, ld_fe(qt));
+        const fe E = fe_sub_l(B, A), H = fe_add_l(B, A);
+        const fe F0 = fe_sub_l(D, C), G0 = fe_add_l(D, C);
+        const fe F = fe_select(F0, G0, neg), G = fe_select(G0, F0, neg);      // -Q: C changes sign
+        X = fe_mul(E, F); Y = fe_mul(G, H); Z = fe_mul(F, G); T = fe_mul(E, H);
+    }
+    cached *out = buckets + k;
+    st_fe(&out->ymx, fe_sub_l(Y, X));
+    st_fe(&out->ypx, fe_add_l(Y, X));
+    st_fe(&out->z2, fe_add_l(Z, Z));
+    st_fe(&out->t2d, fe_mul(T, fe_const_2d()));
+}
+
 // ------------------------------------------------------------------------------------------------ 5: window sums
 // one CTA per (segment, window); quad t owns buckets [t*L, (t+1)*L): S = sum, R = sum_j (j+1)*bucket[tL+j]; it contributes
 // R + (t*L)*S, and the CTA adds the contributions up.  Control flow is CTA-uniform (idle quads work on the identity).
@@ -378,7 +447,18 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         k_msm_digits<true><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.cursor, sc.sorted);
     }
     if (marks) cudaEventRecord(marks[0], s);
-    k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+    // whole threads per bucket once there are enough buckets to occupy the SMs that way: always from ~4 warps per SM
+    // sub-partition on; from 1 warp on only while the buckets are short (a thread walks its bucket alone: 2^16 points at c = 11
+    // are 64 additions per bucket, measured 82 M points/s with quads against 75 M with threads; the verifier's 4226-entry
+    // segments are 16 per bucket and 8 % faster with threads)
+    static const int force_bucket = getenv("BPP_MSM_BUCKET") ? atoi(getenv("BPP_MSM_BUCKET")) : 0;      // 1 = quads, 2 = threads (tests)
+    const size_t full = 148u * 4u * 32u;
+    const bool thread_buckets = force_bucket ? force_bucket == 2
+                                             : n_keys >= 4 * full || (n_keys >= full && (size_t)sh.n_entries * sh.W <= 32 * n_keys);
+    if (thread_buckets)
+        k_msm_bucket_thread<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+    else
+        k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
     if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;

@@ -71,6 +71,10 @@ int32_t bpp_ctx_phase_ms(bpp_ctx *ctx, float *ms11);
  * 0 = host worker threads (BASELINE.json north_star's host/device split); 2 / 3 = CUDA kernel forced to one thread per proof /
  * one warp per proof (1 = one thread per proof).  Results are bit-identical. */
 int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
+/* verification passes are replayed as captured CUDA graphs (default on; BPP_NO_GRAPHS=1 or enable = 0 issues every kernel and
+ * copy with its own driver call, which is also what bpp_ctx_phase_timing(ctx, 1) forces).  Results are identical. */
+int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable);
+uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx);
 /* wall-clock milliseconds of the host phases of the last bpp_vbatch_create / bpp_verify_chunks on this ctx:
  * ms6 = {parse + statement checks, layout + buffers, blob fill (+ loop-1 replay in host mode), weight transcripts (host mode),
  *        H2D + sync, unused} */

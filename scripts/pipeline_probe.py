@@ -20,7 +20,7 @@ api = bpp.pkg.api
 lib = bpp.ffi.lib()
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 S_list = [int(x) for x in sys.argv[2:]] or [1, 2, 4, 8]
-N = 1024
+N = int(os.environ.get("PROBE_PROOFS", "1024"))
 _, cases = bench.make_workload(N)
 cores = os.cpu_count() or 1
 

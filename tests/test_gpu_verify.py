@@ -16,12 +16,15 @@ VA = api.VerifyAction
 _params_cache = {}
 
 
-@pytest.fixture(autouse=True, params=["device_replay_warp", "device_replay_thread", "host_replay"])
+@pytest.fixture(autouse=True, params=["device_replay_warp", "device_replay_thread", "host_replay", "device_replay_no_graphs"])
 def replay_mode(request):
-    """every test runs with loop 1 (the Merlin transcript replay) on the device and on host threads: same results"""
-    bpp.engine().set_replay_mode({"device_replay_warp": 3, "device_replay_thread": 2, "host_replay": 0}[request.param])
+    """every test runs with loop 1 (the Merlin transcript replay) on the device (both kernels) and on host threads, and with the
+    pass issued as captured CUDA graphs (default) and kernel by kernel: same results"""
+    bpp.engine().set_replay_mode({"device_replay_warp": 3, "device_replay_thread": 2, "host_replay": 0, "device_replay_no_graphs": 1}[request.param])
+    bpp.engine().set_graphs(request.param != "device_replay_no_graphs")
     yield request.param
     bpp.engine().set_replay_mode(True)
+    bpp.engine().set_graphs(True)
 
 
 def gpu_params(n, M, ext):

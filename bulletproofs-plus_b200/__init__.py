@@ -180,9 +180,10 @@ class MsmPlan:
         return out.raw if want_result else None
 
     def close(self):
-        if self.h:
+        # a handle whose ctx is already gone (finalisers of a garbage cycle run in arbitrary order) is dropped, not destroyed
+        if self.h and self.engine.h:
             _ffi.lib().bpp_msm_plan_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -219,9 +220,9 @@ class Gens:
         return [out.raw[32 * i: 32 * i + 32] for i in range(n)]
 
     def close(self):
-        if self.h:
+        if self.h and self.engine.h:       # see MsmPlan.close
             _ffi.lib().bpp_gens_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -426,9 +426,9 @@ class VerifyBatch:
         return pk.results()
 
     def close(self):
-        if self.h:
+        if self.h and self.params.gens.h and self.params.gens.engine.h:       # never touch a destroyed ctx / generator set
             _ffi.lib().bpp_vbatch_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -231,6 +231,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL_DEBUG=VERSION/INFO prints to stdout, which carries the one JSON line
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -239,7 +240,8 @@ def run_b200(args, rank, local_rank, world):
     S = max(1, min(args.lanes, args.steps))
     cores = os.cpu_count() or 1
     # S independent lanes (bpp_ctx + host thread each) on this GPU; the host cores are shared by the ranks of the node
-    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=max(1, cores // (S * world)))
+    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=max(1, cores // (S * world)),
+                            blocking_waits=S > 1 and S * world >= cores)
     eng, params = pool.lanes[0]
     params_o, cases = make_workload(args.proofs, seed=8675309 + 1000 * rank)
 
@@ -296,10 +298,30 @@ def run_b200(args, rank, local_rank, world):
     launches = pool.launch_count() - launches0
     clocks = sampler.stop()
 
+    # ---------------- end-to-end arm (e2e): the C-ABI call with HOST buffers, K calls over S lanes
+    host_acc = {}
+
+    def e2e_step(li, e, prm, i, flush=True):
+        pk = pks[li]
+        C.memmove(pk.tbuf, t_init, len(t_init))          # `&mut Transcript`s are advanced by the call
+        if FLUSH and flush:
+            e.l2_flush(FLUSH)
+        rc = lib.bpp_verify_chunks(prm.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present)
+        assert rc == 0 and all(pk.status[c] == 0 for c in range(pk.k)), (rc, list(pk.status))
+
+    pool.run(e2e_step, S * args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    pool.run(e2e_step, args.steps)                       # synchronous calls: each returns after the D2H of its verdicts
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
     # ---------------- one batch at a time on one lane (latency; the per-kernel figures of the roofline come from here)
     vb = vbs[0]
     seq_ms = 0.0
     n_seq = min(args.steps, 20)
+    eng.set_throughput_mode(0)                             # alone: spin-wait, all host threads of this rank's share
+    eng.set_host_threads(max(1, min(64, cores // world)))
     for _ in range(n_seq):
         eng.l2_flush(FLUSH or (144 << 20))
         eng.sync()
@@ -319,30 +341,12 @@ def run_b200(args, rank, local_rank, world):
             phase_acc[k] = phase_acc.get(k, 0.0) + v
     eng.phase_timing(False)
 
-    # ---------------- end-to-end arm (e2e): the C-ABI call with HOST buffers, K calls over S lanes
-    host_acc = {}
-
-    def e2e_step(li, e, prm, i):
-        pk = pks[li]
-        C.memmove(pk.tbuf, t_init, len(t_init))          # `&mut Transcript`s are advanced by the call
-        if FLUSH:
-            e.l2_flush(FLUSH)
-        rc = lib.bpp_verify_chunks(prm.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present)
-        assert rc == 0 and all(pk.status[c] == 0 for c in range(pk.k)), (rc, list(pk.status))
-
-    pool.run(e2e_step, S * args.warmup)
-    barrier()
-    t0 = time.perf_counter()
-    pool.run(e2e_step, args.steps)                       # synchronous calls: each returns after the D2H of its verdicts
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
     e2e_seq_s = 0.0
     for _ in range(n_seq):
         eng.l2_flush(FLUSH or (144 << 20))
         eng.sync()
         t0 = time.perf_counter()
-        e2e_step(0, eng, params, 0)
+        e2e_step(0, eng, params, 0, flush=False)
         e2e_seq_s += time.perf_counter() - t0
         for k, v in eng.host_ms().items():
             host_acc[k] = host_acc.get(k, 0.0) + v / n_seq
@@ -374,7 +378,7 @@ def run_b200(args, rank, local_rank, world):
                 "msm_reduce": n_chunks * W * 2 * B * 9 * MUL32_FE_MUL,
                 "msm_combine": n_chunks * (W - 1) * (c_bits * (4 * MUL32_FE_MUL + 4 * MUL32_FE_SQ) + 9 * MUL32_FE_MUL),
                 "vprep_proof": args.proofs * (130 + 380) * 100,    # ~130 scalar products + one inversion (~380 at a^(l-2) cost), 100 mul32 each
-                "vprep_vector": args.proofs * BIT_LENGTH * (3 * 6 + 8) * 100,
+                "vprep_vector": args.proofs * (BIT_LENGTH * 4 + 3 * 14) * 100,      # 4 products per (proof, i) + three 8+8-entry tables
                 "vprep_weigh": (entries + args.proofs * 2 * BIT_LENGTH) * 100}
         # Keccak-f[1600] of the transcript replay: ~130 64-bit logic / rotate ops per round = 260 32-bit ALU ops, 24 rounds, ~21
         # permutations per 64-bit proof; its ceiling is the ALU pipe (LOP3 / IADD3 / SHF), measured by bpp_microbench(3)

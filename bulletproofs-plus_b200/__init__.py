@@ -108,6 +108,11 @@ class Engine:
         """verification passes as captured CUDA graphs (default) or kernel by kernel"""
         _chk(self, _ffi.lib().bpp_ctx_set_graphs(self.h, 1 if enable else 0))
 
+    def set_throughput_mode(self, enable):
+        """0 / False: spin-wait (lowest latency for one call); 1 / True: blocking waits (many calls in flight from many ctxs);
+        2: additionally verifier weights on the device, one graph per pass (measured slower; see include/bpp_b200.h)"""
+        _chk(self, _ffi.lib().bpp_ctx_set_throughput_mode(self.h, int(enable)))
+
     @property
     def graph_launch_count(self):
         return int(_ffi.lib().bpp_ctx_graph_launch_count(self.h))

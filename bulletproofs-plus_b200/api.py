@@ -448,16 +448,19 @@ class VerifierPool:
     verify_many(batches) runs batches[i] on lane i % S and returns the per-batch (status, masks) in input order; results do
     not depend on S (every batch is verified by the same code path as RangeProof.verify_batch)."""
 
-    def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=8, host_threads_per_lane=None):
+    def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=8, host_threads_per_lane=None, blocking_waits=None):
         import os
 
         from . import Engine
 
         self.lanes = []
         per = host_threads_per_lane or max(1, (os.cpu_count() or 1) // max(1, lanes))
+        if blocking_waits is None:          # spinning lane threads only pay while every one of them has a core to itself
+            blocking_waits = lanes > 1 and lanes >= (os.cpu_count() or 1)
         for _ in range(lanes):
             eng = Engine(device)
             eng.set_host_threads(per)
+            eng.set_throughput_mode(1 if blocking_waits else 0)   # lane threads sleep while their pass runs (bpp_ctx_set_throughput_mode)
             self.lanes.append((eng, RangeParameters.init(eng, bit_length, max_aggregation, extension_degree)))
 
     def __len__(self):

@@ -49,7 +49,12 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_mid_blocking, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream); delete ctx; return BPP_ERR_CUDA;
     }
     unsigned hc = std::thread::hardware_concurrency();
@@ -57,6 +62,7 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (const char *env = getenv("BPP_HOST_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 1024) ctx->host_threads = v; }
     if (const char *env = getenv("BPP_HOST_REPLAY")) ctx->device_replay = atoi(env) == 0;
     if (const char *env = getenv("BPP_NO_GRAPHS")) ctx->use_graphs = atoi(env) == 0;
+    if (const char *env = getenv("BPP_THROUGHPUT_MODE")) { ctx->throughput_mode = atoi(env) != 0; ctx->device_weights = atoi(env) == 2; }
     *out = ctx;
     return BPP_OK;
 }
@@ -74,6 +80,9 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     for (int i = 0; i < bpp_ctx::N_MARKS; i++) if (ctx->ph[i]) cudaEventDestroy(ctx->ph[i]);
     cudaStreamSynchronize(ctx->stream2);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_mid);
+    cudaStreamSynchronize(ctx->stream3);
+    cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join2); cudaEventDestroy(ctx->ev_done); cudaEventDestroy(ctx->ev_mid_blocking);
+    cudaStreamDestroy(ctx->stream3);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -149,6 +158,13 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device) {
 int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable) {
     if (!ctx) return BPP_INVALID_ARGUMENT;
     ctx->use_graphs = enable != 0;
+    return BPP_OK;
+}
+int32_t bpp_ctx_set_throughput_mode(bpp_ctx *ctx, int32_t enable) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    if (enable < 0 || enable > 2) return BPP_INVALID_ARGUMENT;
+    ctx->throughput_mode = enable != 0;
+    ctx->device_weights = enable == 2;
     return BPP_OK;
 }
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->graph_launches : 0; }

@@ -48,7 +48,12 @@ struct bpp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // side stream: point decompression overlaps the scalar prep chain
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
+    cudaStream_t stream3 = nullptr;     // side stream: device-side verifier-weight transcripts (throughput mode)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_mid_blocking = nullptr;
+    cudaEvent_t ev_done = nullptr;      // cudaEventBlockingSync: the host thread sleeps instead of spinning (throughput mode)
+    bool throughput_mode = false;       // blocking waits instead of spinning: see bpp_ctx_set_throughput_mode
+    bool device_weights = false;        // whole pass as ONE graph with the verifier-weight transcripts on the device (k_weights)
     bool device_replay = true;          // loop 1 (transcript replay) on the device (k_replay.cu) or on host threads
     int replay_kernel = 0;              // 0 = by batch size, 1 = one thread per proof, 2 = one warp per proof
     std::string err;

@@ -15,6 +15,7 @@
 // weight-free part of the scalar prep.  Error precedence of the reference is reproduced when the per-chunk status is
 // resolved after the device returns.
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstring>
 #include "engine.hpp"
@@ -98,7 +99,7 @@ struct bpp_vbatch {
     VWork *w = nullptr;
     // all inputs travel as ONE pinned blob -> ONE H2D copy; these are the section offsets inside it
     size_t o_enc = 0, o_proofs = 0, o_chunks = 0, o_vecoff = 0, o_pscal = 0, o_chal = 0, o_minv = 0, o_minp = 0, o_nonces = 0, o_pidx = 0,
-           o_segoff = 0, o_tstate = 0, o_hg = 0, blob_bytes = 0;
+           o_segoff = 0, o_tstate = 0, o_hg = 0, o_wtinit = 0, blob_bytes = 0;
     // mid-pipeline results of loop 1: [wbytes n x 32 | flags n | tstates n x 203]; same layout on device and host
     size_t mo_wbytes = 0, mo_flags = 0, mo_tstate = 0, mid_bytes = 0;
     size_t ho_ok = 0, ho_ident = 0, ho_masks = 0, hout_bytes = 0;
@@ -135,11 +136,11 @@ struct VGraphKey {
     const void *bufs[18];
     const void *gens_table;
     size_t n_proofs, n_chunks;
-    size_t off[22];
+    size_t off[23];
     uint32_t n_pts, n_entries, total_vec, max_static, max_rounds;
     int32_t action, ext, bit_length;
     MsmShape shape;
-    uint8_t any_msm, any_masks, any_replay, device_replay, warp_replay;
+    uint8_t any_msm, any_masks, any_replay, device_replay, warp_replay, fused;
 };
 struct VGraph {
     VGraphKey key;
@@ -352,6 +353,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     vb->o_segoff = carve(4 * (a->n_chunks + 1));
     vb->o_hg = carve(32 * ((size_t)ext + 1));
     vb->o_tstate = carve(vb->device_replay ? BPP_TRANSCRIPT_BYTES * a->n_proofs : 0);
+    vb->o_wtinit = carve(BPP_TRANSCRIPT_BYTES);
     vb->blob_bytes = off;
     vb->n_pts = n_pts; vb->n_entries = n_entries; vb->max_static = max_static;
     vb->shape = msm_shape(n_entries, (uint32_t)a->n_chunks, 0);
@@ -408,6 +410,16 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     memcpy(hb + vb->o_hg, g->h(), 32);
     memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
     if (vb->device_replay && a->n_proofs) memcpy(hb + vb->o_tstate, a->transcripts, BPP_TRANSCRIPT_BYTES * a->n_proofs);
+    {   // Transcript::new("Bulletproofs+ verifier weights") (:811), the starting state of k_weights
+        static const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> wt0 = [] {
+            std::array<uint8_t, BPP_TRANSCRIPT_BYTES> st;
+            Merlin wt;
+            wt.init(LBL("Bulletproofs+ verifier weights"));
+            wt.s.store(st.data());
+            return st;
+        }();
+        memcpy(hb + vb->o_wtinit, wt0.data(), BPP_TRANSCRIPT_BYTES);
+    }
     memset(vb->mid(), 0, vb->mid_bytes);
     memset(w->h_weights.p, 0, 32 * np1);
     for (size_t c = 0; c < a->n_chunks; c++) {
@@ -545,6 +557,40 @@ static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section
         }
         if (prep) launch_verify_prep(st, L.d, L.b, vb->total_vec, vb->max_rounds, kernels, nullptr);
         if (fork) ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    } else if (section == 3) {
+        // throughput mode: the whole pass without a host step.  st: replay -> D2H(flags, transcripts) -> scalar prep -> [weights]
+        // -> weighting -> [points] -> MSM -> verdicts;  stream2: decompression (from the start);  stream3: weight transcripts
+        // (after the replay)
+        const bool prep = vb->any_msm || vb->any_masks;
+        const bool fork_pts = vb->n_pts != 0;
+        if (fork_pts) {
+            ok(cudaEventRecord(ctx->ev_fork, st)); ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            launch_decompress(ctx->stream2, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), w->d_tab.as<aniels>(), w->d_ok.as<uint8_t>(), nullptr, nullptr);
+            (*kernels)++;
+            ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        }
+        launch_replay(st, L.d, L.rb, L.warp_replay, kernels);
+        if (vb->any_msm) {
+            ok(cudaEventRecord(ctx->ev_fork2, st)); ok(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork2, 0));
+            launch_weights(ctx->stream3, L.d, L.b.chunks, vb->dev<uint8_t>(vb->o_wtinit), L.rb.wbytes, L.rb.flags, w->d_weights.as<uint32_t>(), kernels);
+            ok(cudaEventRecord(ctx->ev_join2, ctx->stream3));
+        }
+        ok(cudaMemcpyAsync(vb->mid(), w->d_mid.p, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
+        if (prep) launch_verify_prep(st, L.d, L.b, vb->total_vec, vb->max_rounds, kernels, nullptr);
+        if (vb->any_msm) {
+            ok(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+            launch_verify_weigh(st, L.d, L.b, vb->max_static, kernels);
+            if (fork_pts) ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
+                       w->d_tab.as<aniels>(), g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), kernels, nullptr);
+            launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
+            (*kernels)++;
+            ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+        } else if (fork_pts) {
+            ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        }
+        if (vb->n_pts) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
+        if (vb->any_masks) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)g->ext, cudaMemcpyDeviceToHost, st));
     } else {
         if (vb->any_msm) {
             ok(cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 32 * n, cudaMemcpyHostToDevice, st));
@@ -562,7 +608,7 @@ static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section
     return e;
 }
 
-static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L) {
+static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L, bool fused) {
     VGraphKey k;
     memset(&k, 0, sizeof k);
     const VWork *w = vb->w;
@@ -571,7 +617,7 @@ static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L) {
     memcpy(k.bufs, bufs, sizeof bufs);
     k.gens_table = vb->g->d_table.p;
     k.n_proofs = vb->n_proofs; k.n_chunks = vb->n_chunks;
-    const size_t off[22] = {vb->o_enc, vb->o_proofs, vb->o_chunks, vb->o_vecoff, vb->o_pscal, vb->o_chal, vb->o_minv, vb->o_minp, vb->o_nonces, vb->o_pidx,
+    const size_t off[23] = {vb->o_wtinit, vb->o_enc, vb->o_proofs, vb->o_chunks, vb->o_vecoff, vb->o_pscal, vb->o_chal, vb->o_minv, vb->o_minp, vb->o_nonces, vb->o_pidx,
                             vb->o_segoff, vb->o_tstate, vb->o_hg, vb->blob_bytes, vb->mo_wbytes, vb->mo_flags, vb->mo_tstate, vb->mid_bytes,
                             vb->ho_ok, vb->ho_ident, vb->ho_masks, vb->hout_bytes};
     memcpy(k.off, off, sizeof off);
@@ -579,13 +625,14 @@ static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L) {
     k.action = vb->action; k.ext = vb->g->ext; k.bit_length = vb->g->n;
     k.shape.n_entries = vb->shape.n_entries; k.shape.n_seg = vb->shape.n_seg; k.shape.c = vb->shape.c; k.shape.W = vb->shape.W; k.shape.B = vb->shape.B;
     k.any_msm = vb->any_msm; k.any_masks = vb->any_masks; k.any_replay = vb->any_replay; k.device_replay = L.dev_replay; k.warp_replay = L.warp_replay;
+    k.fused = fused;
     return k;
 }
 
 // finds or captures the three graphs of this pass; nullptr (with *err set) if a capture failed
-static VGraph *vgraph_get(bpp_vbatch *vb, const VLaunch &L, cudaError_t *err) {
+static VGraph *vgraph_get(bpp_vbatch *vb, const VLaunch &L, bool fused, cudaError_t *err) {
     bpp_ctx *ctx = vb->g->ctx;
-    const VGraphKey key = make_graph_key(vb, L);
+    const VGraphKey key = make_graph_key(vb, L, fused);
     for (void *p : ctx->vgraphs) {
         VGraph *g = (VGraph *)p;
         if (!memcmp(&g->key, &key, sizeof key)) { g->last_use = ++ctx->vgraph_clock; return g; }
@@ -593,11 +640,11 @@ static VGraph *vgraph_get(bpp_vbatch *vb, const VLaunch &L, cudaError_t *err) {
     VGraph *g = new VGraph();
     g->key = key;
     for (int sct = 0; sct < 3; sct++) {
-        if (sct == 0 && !L.dev_replay) continue;
+        if (fused ? sct != 0 : (sct == 0 && !L.dev_replay)) continue;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
-            cudaError_t e1 = enqueue_section(vb, L, sct, &g->kernels[sct]);
+            cudaError_t e1 = enqueue_section(vb, L, fused ? 3 : sct, &g->kernels[sct]);
             e = cudaStreamEndCapture(ctx->stream, &graph);
             if (e == cudaSuccess) e = e1;
         }
@@ -632,17 +679,25 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     const bool dev_replay = L.dev_replay;
 
     ctx->clear_marks();
-    if (ctx->use_graphs && !ctx->phase_timing) {
+    const bool fused = ctx->device_weights && dev_replay && ctx->use_graphs && !ctx->phase_timing;
+    if (fused) {
         cudaError_t ge = cudaSuccess;
-        VGraph *vg = vgraph_get(vb, L, &ge);
+        VGraph *vg = vgraph_get(vb, L, true, &ge);
+        if (!vg) return cuda_fail(ctx, ge, "verification graph capture");
+        BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[0], st));
+        ctx->launches += vg->kernels[0];
+        ctx->graph_launches += 1;
+    } else if (ctx->use_graphs && !ctx->phase_timing) {
+        cudaError_t ge = cudaSuccess;
+        VGraph *vg = vgraph_get(vb, L, false, &ge);
         if (!vg) return cuda_fail(ctx, ge, "verification graph capture");
         if (vg->ex[0]) {
             BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[0], st));
-            BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
+            BPP_CUDA(ctx, cudaEventRecord(ctx->throughput_mode ? ctx->ev_mid_blocking : ctx->ev_mid, st));
         }
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[1], st));
         if (dev_replay) {       // the host hashes the weight transcripts while the device runs section B
-            BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_mid));
+            BPP_CUDA(ctx, cudaEventSynchronize(ctx->throughput_mode ? ctx->ev_mid_blocking : ctx->ev_mid));
             compute_weights(vb);
         }
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[2], st));
@@ -701,9 +756,14 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     if (vb->n_pts) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
     if (vb->any_masks) BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)ext, cudaMemcpyDeviceToHost, st));
     }
-    BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->throughput_mode) {         // sleep until the pass is done: with many lanes per GPU spinning threads starve each other
+        BPP_CUDA(ctx, cudaEventRecord(ctx->ev_done, st));
+        BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_done));
+    } else {
+        BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     vb->ran = true;
-    ctx->io_bytes[0] = vb->blob_bytes + (vb->any_msm ? 32 * n : 0);
+    ctx->io_bytes[0] = vb->blob_bytes + (vb->any_msm && !fused ? 32 * n : 0);
     ctx->io_bytes[1] = (dev_replay ? vb->mid_bytes : 0) + vb->n_pts + (vb->any_msm ? vb->n_chunks : 0) + (vb->any_masks ? 32 * n * (size_t)ext : 0);
 
     // ---- resolve per-chunk status with the reference's precedence

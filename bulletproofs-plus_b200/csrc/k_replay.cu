@@ -46,6 +46,48 @@ template <bool WARP> __global__ void __launch_bounds__(WARP ? 32 * REPLAY_WARPS 
     b.flags[p] = flag;
 }
 
+// K-WEIGHTS: the verifier-weight transcript of each chunk (/root/reference/src/range_proof.rs:811, :849, :853, :894) on the
+// device, one WARP per chunk with the warp-cooperative sponge of wstrobe.cuh.  The transcript is inherently sequential (every
+// proof appends 32 bytes, then one Keccak-f per weight drawn), so this is a ~330-permutation chain per 256-proof chunk: slower
+// than a host core for one batch alone (~0.6 ms against ~0.25 ms), but it removes the only host step from the middle of a pass,
+// so a pass becomes ONE graph launch and costs the host nothing -- what matters when many passes are in flight.
+__global__ void __launch_bounds__(32) k_weights(VDims d, const VChunk *__restrict__ chunks, const uint8_t *__restrict__ wt_init,
+                                               const uint8_t *__restrict__ wbytes, const uint8_t *__restrict__ flags, uint32_t *__restrict__ weights) {
+    const VChunk chk = chunks[blockIdx.x];
+    if (!chk.active) return;
+    const int lane = threadIdx.x & 31;
+    int bad = 0;
+    for (uint32_t p = chk.proof_lo + lane; p < chk.proof_hi; p += 32) bad |= flags[p] & 1;
+    if (__any_sync(0xffffffffu, bad)) return;            // loop 1 failed somewhere in the call: it ends there, no weights are drawn
+    WMerlin wt;
+    wt.s.load(wt_init);                                   // Transcript::new("Bulletproofs+ verifier weights"), state from the host
+    const uint8_t lbl[5] = {'p', 'r', 'o', 'o', 'f'};
+    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++) wt.append_message(lbl, 5, wbytes + 32 * (size_t)p, 32);
+    WMerlinRng wr;
+    uint8_t zeros[32];
+    for (int i = 0; i < 32; i++) zeros[i] = 0;
+    wr.build(wt, nullptr, 0, false, zeros);               // NullRng
+    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++) {
+        sc w;
+        do {                                              // Scalar::random_not_zero (:894)
+            __align__(8) uint8_t wide[64];
+            wr.fill(wide, 64);
+            uint32_t ww[16];
+            for (int i = 0; i < 16; i++)
+                ww[i] = (uint32_t)wide[4 * i] | ((uint32_t)wide[4 * i + 1] << 8) | ((uint32_t)wide[4 * i + 2] << 16) | ((uint32_t)wide[4 * i + 3] << 24);
+            w = sc_from_wide_words(ww);
+        } while (sc_is_zero(w));                          // warp-uniform
+        if (lane < 8) weights[8 * (size_t)p + lane] = w.v[lane];
+    }
+}
+
+void launch_weights(cudaStream_t s, const VDims &d, const VChunk *chunks, const uint8_t *wt_init, const uint8_t *wbytes, const uint8_t *flags,
+                    uint32_t *weights, uint64_t *launches) {
+    if (d.n_chunks == 0) return;
+    k_weights<<<d.n_chunks, 32, 0, s>>>(d, chunks, wt_init, wbytes, flags, weights);
+    if (launches) (*launches)++;
+}
+
 void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, bool warp_per_proof, uint64_t *launches) {
     if (d.n_proofs == 0) return;
     if (warp_per_proof) k_replay<true><<<(d.n_proofs + REPLAY_WARPS - 1) / REPLAY_WARPS, 32 * REPLAY_WARPS, 0, s>>>(d, b);

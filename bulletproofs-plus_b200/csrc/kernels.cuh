@@ -95,6 +95,10 @@ struct RBuffers {
     uint8_t *flags;                  // out: n_proofs; bit 0 = loop-1 VerificationFailed, bit 1 = y == 1
 };
 void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, bool warp_per_proof, uint64_t *launches);
+// verifier weights of every active chunk (one warp per chunk); wt_init = 203-byte state of the weight transcript after its
+// domain separator; weights: n_proofs x 8 words, canonical
+void launch_weights(cudaStream_t s, const VDims &d, const VChunk *chunks, const uint8_t *wt_init, const uint8_t *wbytes, const uint8_t *flags,
+                    uint32_t *weights, uint64_t *launches);
 
 // ---------------------------------------------------------------- k_prove.cu
 struct PDims { uint32_t P, n, m, N, ext, rounds, gens_nm; };   // P proofs of one shape; N = n*m; gens_nm = n * max_aggregation

@@ -75,6 +75,15 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
  * copy with its own driver call, which is also what bpp_ctx_phase_timing(ctx, 1) forces).  Results are identical. */
 int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable);
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx);
+/* throughput mode (default 0), for callers that keep several verification calls in flight from several ctxs:
+ *   1 = the calling thread sleeps on blocking events instead of spinning while the device works (with many ctxs per GPU spinning
+ *       threads starve each other and the host hashing);
+ *   2 = additionally the verifier-weight transcripts (range_proof.rs:811-853, :894) run on the device (k_weights, one warp per
+ *       chunk) and the whole pass is ONE graph launch with no host step in the middle.  Measured on B200 this is slower (a
+ *       256-proof chunk is a chain of ~330 dependent Keccak-f permutations: 4.5 ms on one warp against ~0.2 ms on a host core),
+ *       so it is not what api.VerifierPool selects; it stays as a tested option for hosts with no cycles to spare.
+ * Results are identical in every mode.  Mode 2 needs device replay and graphs (the defaults), else it behaves like mode 1. */
+int32_t bpp_ctx_set_throughput_mode(bpp_ctx *ctx, int32_t enable);
 /* wall-clock milliseconds of the host phases of the last bpp_vbatch_create / bpp_verify_chunks on this ctx:
  * ms6 = {parse + statement checks, layout + buffers, blob fill (+ loop-1 replay in host mode), weight transcripts (host mode),
  *        H2D + sync, unused} */

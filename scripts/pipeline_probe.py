@@ -28,6 +28,7 @@ cores = os.cpu_count() or 1
 class Lane:
     def __init__(self, host_threads):
         self.eng = bpp.pkg.Engine(0)
+        self.eng.set_throughput_mode(int(os.environ.get("PROBE_TPUT", "1")))
         lib.bpp_ctx_set_host_threads(self.eng.h, host_threads)
         self.params = api.RangeParameters.init(self.eng, 64, 1, 1)
         self.vb = api.VerifyBatch(self.params, self.calls(), api.VerifyAction.VerifyOnly)

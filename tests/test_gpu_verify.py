@@ -16,15 +16,19 @@ VA = api.VerifyAction
 _params_cache = {}
 
 
-@pytest.fixture(autouse=True, params=["device_replay_warp", "device_replay_thread", "host_replay", "device_replay_no_graphs"])
+@pytest.fixture(autouse=True, params=["device_replay_warp", "device_replay_thread", "host_replay", "device_replay_no_graphs", "blocking_waits", "device_weights"])
 def replay_mode(request):
     """every test runs with loop 1 (the Merlin transcript replay) on the device (both kernels) and on host threads, and with the
-    pass issued as captured CUDA graphs (default) and kernel by kernel: same results"""
-    bpp.engine().set_replay_mode({"device_replay_warp": 3, "device_replay_thread": 2, "host_replay": 0, "device_replay_no_graphs": 1}[request.param])
+    pass issued as captured CUDA graphs (default), kernel by kernel, with blocking waits, and as the single graph with the
+    verifier-weight transcripts on the device: same results"""
+    bpp.engine().set_replay_mode({"device_replay_warp": 3, "device_replay_thread": 2, "host_replay": 0}.get(request.param, 1))
     bpp.engine().set_graphs(request.param != "device_replay_no_graphs")
+    # blocking waits; one graph per pass with the verifier weights drawn on the device
+    bpp.engine().set_throughput_mode({"blocking_waits": 1, "device_weights": 2}.get(request.param, 0))
     yield request.param
     bpp.engine().set_replay_mode(True)
     bpp.engine().set_graphs(True)
+    bpp.engine().set_throughput_mode(False)
 
 
 def gpu_params(n, M, ext):

@@ -214,6 +214,15 @@ class Gens:
         _chk(self.engine, _ffi.lib().bpp_gens_get(self.h, which, index, out))
         return out.raw
 
+    def fixed_base_msm(self, scalars, gidx, n_seg):
+        """n_seg sums over the generator set (order Gi | Hi | G_k | H): scalars = n_seg * len(gidx) canonical 32-byte scalars,
+        segment-major -> list of n_seg 32-byte encodings"""
+        seg_len = len(gidx)
+        out = C.create_string_buffer(32 * n_seg)
+        gi = (C.c_uint32 * seg_len)(*gidx)
+        _chk(self.engine, _ffi.lib().bpp_gens_fixed_base_msm(self.h, n_seg, seg_len, scalars, C.cast(gi, C.c_void_p), out))
+        return [out.raw[32 * i: 32 * i + 32] for i in range(n_seg)]
+
     def commit_batch(self, values, blindings):
         """values: list[int]; blindings: list (per opening) of lists of ints (same length each) -> list of 32-byte encodings"""
         n = len(values)

@@ -115,6 +115,7 @@ def lib():
         "bpp_gens_create": (i32, [vp, i32, i32, i32, P(vp)]),
         "bpp_gens_destroy": (None, [vp]),
         "bpp_gens_get": (i32, [vp, i32, sz, cp]),
+        "bpp_gens_fixed_base_msm": (i32, [vp, sz, sz, cp, vp, cp]),
         "bpp_pedersen_commit_batch": (i32, [vp, sz, vp, cp, i32, cp]),
         "bpp_verify_chunks": (i32, [vp, P(VerifyArgs), vp, vp, vp]),
         "bpp_vbatch_create": (i32, [vp, P(VerifyArgs), P(vp)]),

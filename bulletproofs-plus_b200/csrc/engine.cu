@@ -33,6 +33,25 @@ void host_sc_from_wide(const uint8_t in64[64], uint8_t out32[32]) {
 }
 } // namespace bpp
 
+namespace bpp {
+bool gens_fb_ensure(bpp_gens *g) {
+    if (g->fb_state) return g->fb_state > 0;
+    bpp_ctx *ctx = g->ctx;
+    size_t max_mb = 2048;
+    if (const char *env = getenv("BPP_FB_MAX_MB")) max_mb = (size_t)atol(env);
+    int forced_c = 0;
+    if (const char *env = getenv("BPP_FB_C")) forced_c = atoi(env);
+    FbShape sh = fb_shape((uint32_t)g->table_len(), forced_c, max_mb << 20);
+    g->fb_state = -1;
+    if (fb_table_bytes(sh) > (max_mb << 20)) return false;
+    if (g->d_fb.ensure(fb_table_bytes(sh)) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (fb_build(ctx->stream, sh, g->d_table.as<aniels>(), g->d_fb.as<aniels>(), &ctx->launches)) { g->d_fb.release(); cudaGetLastError(); return false; }
+    g->fb = sh;
+    g->fb_state = 1;
+    return true;
+}
+}
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------ context
@@ -410,7 +429,35 @@ void bpp_gens_destroy(bpp_gens *g) {
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
     g->d_table.release();
+    g->d_fb.release();
     delete g;
+}
+// n_seg independent sums over the generator set: out[s] = sum_e scalars[s][e] * P[gidx[e]]; generator order Gi | Hi | G_k | H
+int32_t bpp_gens_fixed_base_msm(bpp_gens *g, size_t n_seg, size_t seg_len, const uint8_t *scalars32, const uint32_t *gidx, uint8_t *out32) {
+    if (!g || !scalars32 || !gidx || !out32) return BPP_INVALID_ARGUMENT;
+    bpp_ctx *ctx = g->ctx;
+    if (n_seg == 0 || seg_len == 0 || n_seg * seg_len >= (1u << 28)) return fail(ctx, BPP_INVALID_ARGUMENT, "bad segment shape");
+    for (size_t e = 0; e < seg_len; e++)
+        if (gidx[e] >= g->table_len()) return fail(ctx, BPP_INVALID_ARGUMENT, "generator index out of range");
+    for (size_t i = 0; i < n_seg * seg_len; i++)
+        if (!host_sc_is_canonical(scalars32 + 32 * i)) return fail(ctx, BPP_INVALID_ARGUMENT, "non-canonical scalar");
+    cudaSetDevice(ctx->device);
+    if (!gens_fb_ensure(g)) return fail(ctx, BPP_SIZE_OVERFLOW, "fixed-base tables exceed the memory budget (BPP_FB_MAX_MB)");
+    cudaStream_t st = ctx->stream;
+    BPP_CUDA(ctx, ctx->d_in.ensure(32 * n_seg * seg_len));
+    BPP_CUDA(ctx, ctx->d_in2.ensure(4 * seg_len));
+    BPP_CUDA(ctx, ctx->d_res.ensure(sizeof(ge) * n_seg));
+    BPP_CUDA(ctx, ctx->d_out.ensure(32 * n_seg));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, scalars32, 32 * n_seg * seg_len, cudaMemcpyHostToDevice, st));
+    BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in2.p, gidx, 4 * seg_len, cudaMemcpyHostToDevice, st));
+    launch_fb_msm(st, g->fb, (uint32_t)n_seg, (uint32_t)seg_len, 1, ctx->d_in.as<uint32_t>(), ctx->d_in2.as<uint32_t>(), g->d_fb.as<aniels>(),
+                  ctx->d_res.as<ge>(), &ctx->launches);
+    launch_encode(st, n_seg, ctx->d_res.as<ge>(), ctx->d_out.as<uint32_t>(), nullptr);
+    ctx->launches++;
+    BPP_CUDA(ctx, cudaGetLastError());
+    BPP_CUDA(ctx, cudaMemcpyAsync(out32, ctx->d_out.p, 32 * n_seg, cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(ctx, cudaStreamSynchronize(st));
+    return BPP_OK;
 }
 int32_t bpp_gens_get(const bpp_gens *g, int32_t which, size_t index, uint8_t out32[32]) {
     if (!g || !out32) return BPP_INVALID_ARGUMENT;

@@ -91,6 +91,9 @@ struct bpp_gens {
     int n = 0, M = 0, ext = 0;
     size_t nm = 0;                       // n * M
     bpp::DevBuf d_table;                 // aniels[2*nm + ext + 1]: Gi | Hi | G | H
+    bpp::DevBuf d_fb;                    // fixed-base window tables over the same generators (k_fb.cu), built on first use
+    bpp::FbShape fb = {0, 0, 0, 0};
+    int fb_state = 0;                    // 0 = not built, 1 = ready, -1 = over the memory budget (callers use the folding path)
     std::vector<uint8_t> enc;            // (2*nm + ext + 1) x 32 B compressed, same order
     const uint8_t *gi(size_t i) const { return enc.data() + 32 * i; }
     const uint8_t *hi(size_t i) const { return enc.data() + 32 * (nm + i); }
@@ -101,6 +104,8 @@ struct bpp_gens {
 
 namespace bpp {
 void vwork_pool_free(bpp_ctx *ctx);
+// builds g->d_fb on first use; false if the tables would exceed the budget (BPP_FB_MAX_MB, default 2048) or the build failed
+bool gens_fb_ensure(bpp_gens *g);
 void vgraph_cache_free(bpp_ctx *ctx);
 void prove_ws_free(bpp_ctx *ctx);
 int32_t fail(bpp_ctx *ctx, int32_t code, const char *what);

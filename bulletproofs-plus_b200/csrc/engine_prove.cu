@@ -90,10 +90,11 @@ bool challenge(Merlin &t, const uint8_t *label, size_t ll, sc &out) {
 // scratch cost more than the proving itself); the secrets in them are wiped at the end of every call
 struct ProveWS {
     DevBuf d_offs, d_a, d_b, d_ypow, d_yinv2, d_yz, d_dlr, d_e, d_fsc, d_folded, d_mscal, d_pidx, d_segoff, d_scratch, d_res, d_enc, d_ab;
+    DevBuf d_sg, d_sh, d_gidx, d_rs;      // fixed-base path
     PinBuf h_io;
     void release() {
         for (DevBuf *b : {&d_offs, &d_a, &d_b, &d_ypow, &d_yinv2, &d_yz, &d_dlr, &d_e, &d_fsc, &d_folded, &d_mscal, &d_pidx, &d_segoff, &d_scratch,
-                          &d_res, &d_enc, &d_ab})
+                          &d_res, &d_enc, &d_ab, &d_sg, &d_sh, &d_gidx, &d_rs})
             b->release();
         h_io.release();
     }
@@ -205,7 +206,13 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     // ---- device state
     PDims d;
     d.P = P; d.n = n; d.m = m; d.N = N; d.ext = ext; d.rounds = rounds; d.gens_nm = (uint32_t)g->nm;
-    const size_t max_entries = std::max<size_t>((size_t)P * (N + ext), (size_t)2 * P * (1 + ext + N));
+    // Fixed-base path (default): every commitment is a sum over the static generators, evaluated from window tables (k_fb.cu); the
+    // generator folding of the reference survives as two scalar vectors.  The folding path (k_prove_fold_pts + K-MSM) remains
+    // for generator sets whose tables would not fit BPP_FB_MAX_MB, and under BPP_PROVE_FOLD=1 for the parity tests.
+    static const bool force_fold = getenv("BPP_PROVE_FOLD") != nullptr && atoi(getenv("BPP_PROVE_FOLD")) != 0;
+    const bool fb = !force_fold && gens_fb_ensure(g);
+    const size_t max_entries = fb ? std::max<size_t>((size_t)2 * P * (1 + ext + N), (size_t)P * (2 * N + 1 + ext) + (size_t)P * (1 + ext))
+                                  : std::max<size_t>((size_t)P * (N + ext), (size_t)2 * P * (1 + ext + N));
     if (!ctx->prove_ws) ctx->prove_ws = new ProveWS();
     ProveWS &ws = *(ProveWS *)ctx->prove_ws;
     DevBuf &d_offs = ws.d_offs, &d_a = ws.d_a, &d_b = ws.d_b, &d_ypow = ws.d_ypow, &d_yinv2 = ws.d_yinv2, &d_yz = ws.d_yz, &d_dlr = ws.d_dlr,
@@ -213,29 +220,67 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
            &d_scratch = ws.d_scratch, &d_res = ws.d_res, &d_enc = ws.d_enc, &d_ab = ws.d_ab;
     PinBuf &h_io = ws.h_io;
     auto release = [&]() {};       // buffers stay with the ctx
-    MsmShape shA = msm_shape((uint32_t)((size_t)P * (N + ext)), P, 0);
-    size_t scratch_bytes = msm_scratch_bytes(shA);
-    for (uint32_t r = 0; r < rounds; r++) {
-        uint32_t nn = N >> (r + 1);
-        scratch_bytes = std::max(scratch_bytes, msm_scratch_bytes(msm_shape(2 * P * (1 + ext + 2 * nn), 2 * P, 0)));
+    size_t scratch_bytes = 256;
+    if (!fb) {
+        scratch_bytes = msm_scratch_bytes(msm_shape((uint32_t)((size_t)P * (N + ext)), P, 0));
+        for (uint32_t r = 0; r < rounds; r++) {
+            uint32_t nn = N >> (r + 1);
+            scratch_bytes = std::max(scratch_bytes, msm_scratch_bytes(msm_shape(2 * P * (1 + ext + 2 * nn), 2 * P, 0)));
+        }
+        scratch_bytes = std::max(scratch_bytes, msm_scratch_bytes(msm_shape(P * (4 + 2 * ext), 2 * P, 0)));
     }
-    scratch_bytes = std::max(scratch_bytes, msm_scratch_bytes(msm_shape(P * (4 + 2 * ext), 2 * P, 0)));
+    // generator-index rows of the fixed-base sums (k_prove.cu, "fixed-base path"): A | (L, R) per round | A1 | B
+    std::vector<uint32_t> gidx;
+    size_t gi_A = 0, gi_round0 = 0, gi_A1 = 0, gi_B = 0;
+    const uint32_t segA = 2 * N + ext, segLR = 1 + ext + N, segA1 = 2 * N + 1 + ext, segB = 1 + ext;
+    if (fb) {
+        const uint32_t nm = (uint32_t)g->nm, iG = 2 * nm, iH = 2 * nm + ext;
+        gi_A = gidx.size();
+        for (uint32_t j = 0; j < N; j++) gidx.push_back(j);
+        for (uint32_t j = 0; j < N; j++) gidx.push_back(nm + j);
+        for (uint32_t k = 0; k < ext; k++) gidx.push_back(iG + k);
+        gi_round0 = gidx.size();
+        for (uint32_t r = 0; r < rounds; r++) {
+            const uint32_t nn = N >> (r + 1), half = N / 2;
+            for (int side = 0; side < 2; side++) {                   // 0 = L, 1 = R
+                gidx.push_back(iH);
+                for (uint32_t k = 0; k < ext; k++) gidx.push_back(iG + k);
+                for (uint32_t t = 0; t < half; t++) { uint32_t jl = (t / nn) * 2 * nn + t % nn; gidx.push_back(side ? jl : jl + nn); }
+                for (uint32_t t = 0; t < half; t++) { uint32_t jl = (t / nn) * 2 * nn + t % nn; gidx.push_back(nm + (side ? jl + nn : jl)); }
+            }
+        }
+        gi_A1 = gidx.size();
+        for (uint32_t j = 0; j < N; j++) gidx.push_back(j);
+        for (uint32_t j = 0; j < N; j++) gidx.push_back(nm + j);
+        for (uint32_t k = 0; k < ext; k++) gidx.push_back(iG + k);
+        gidx.push_back(iH);
+        gi_B = gidx.size();
+        gidx.push_back(iH);
+        for (uint32_t k = 0; k < ext; k++) gidx.push_back(iG + k);
+    }
     cudaError_t ce = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
     ok(d_offs.ensure(8 * (size_t)P * m));
     ok(d_a.ensure(32 * (size_t)P * N)); ok(d_b.ensure(32 * (size_t)P * N));
     ok(d_ypow.ensure(32 * (size_t)P * (N + 2))); ok(d_yinv2.ensure(32 * (size_t)P * BPP_MAX_ROUNDS));
     ok(d_yz.ensure(64 * (size_t)P)); ok(d_dlr.ensure(64 * (size_t)P * ext)); ok(d_e.ensure(32 * (size_t)P)); ok(d_fsc.ensure(32 * 6 * (size_t)P));
-    ok(d_folded.ensure(sizeof(cached) * 2 * (size_t)P * N));
+    if (fb) {
+        ok(ws.d_sg.ensure(32 * (size_t)P * N)); ok(ws.d_sh.ensure(32 * (size_t)P * N));
+        ok(ws.d_gidx.ensure(4 * gidx.size())); ok(ws.d_rs.ensure(64 * (size_t)P));
+    } else {
+        ok(d_folded.ensure(sizeof(cached) * 2 * (size_t)P * N));
+    }
     ok(d_mscal.ensure(32 * max_entries)); ok(d_pidx.ensure(4 * max_entries)); ok(d_segoff.ensure(4 * (2 * (size_t)P + 1)));
     ok(d_scratch.ensure(scratch_bytes)); ok(d_res.ensure(sizeof(ge) * 2 * (size_t)P)); ok(d_enc.ensure(64 * (size_t)P)); ok(d_ab.ensure(64 * (size_t)P));
     const size_t io_bytes = std::max<size_t>(32 * (size_t)P * (4 + 2 * ext) + 4 * (size_t)P * (4 + 2 * ext), 64 * (size_t)P * std::max<uint32_t>(ext, 1) + 64 * (size_t)P) + 4 * (2 * (size_t)P + 1) + 1024;
+    static_assert(BPP_MAX_EXT >= 1, "extension degree");
     ok(h_io.ensure(io_bytes));
     if (ce != cudaSuccess) { release(); return cuda_fail(ctx, ce, "prover buffers"); }
     PBuffers b;
     b.offset_values = d_offs.as<uint64_t>(); b.a = d_a.as<uint32_t>(); b.b = d_b.as<uint32_t>(); b.ypow = d_ypow.as<uint32_t>();
     b.yinv2 = d_yinv2.as<uint32_t>(); b.yz = d_yz.as<uint32_t>(); b.dlr = d_dlr.as<uint32_t>(); b.e = d_e.as<uint32_t>(); b.fsc = d_fsc.as<uint32_t>();
     b.folded = d_folded.as<cached>(); b.msm_scalars = d_mscal.as<uint32_t>(); b.msm_pidx = d_pidx.as<uint32_t>();
+    b.sg = ws.d_sg.as<uint32_t>(); b.sh = ws.d_sh.as<uint32_t>();
     uint8_t *hio = h_io.as<uint8_t>();
 #define PCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { release(); return cuda_fail(ctx, _e, #call); } } while (0)
     auto upload_offsets = [&](uint32_t n_seg, const std::vector<uint32_t> &off) -> cudaError_t {
@@ -253,15 +298,29 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         return cudaGetLastError();
     };
 
+    // fixed-base sums: n_seg segments of seg_len entries starting at entry `first`, results (and their encodings) from slot `res0` on
+    auto run_fb = [&](uint32_t n_seg, uint32_t seg_len, uint32_t kinds, size_t gi_off, size_t first, uint32_t res0) -> cudaError_t {
+        launch_fb_msm(st, g->fb, n_seg, seg_len, kinds, d_mscal.as<uint32_t>() + 8 * first, ws.d_gidx.as<uint32_t>() + gi_off, g->d_fb.as<aniels>(),
+                      d_res.as<ge>() + res0, &ctx->launches);
+        launch_encode(st, n_seg, d_res.as<ge>() + res0, d_enc.as<uint32_t>() + 8 * (size_t)res0, nullptr);
+        ctx->launches++;
+        return cudaGetLastError();
+    };
+    if (fb) PCUDA(cudaMemcpyAsync(ws.d_gidx.p, gidx.data(), 4 * gidx.size(), cudaMemcpyHostToDevice, st));
+
     // ---- A (:334-345)
     PCUDA(cudaMemcpyAsync(d_offs.p, offs.data(), 8 * (size_t)P * m, cudaMemcpyHostToDevice, st));
-    launch_prove_bits(st, d, b);
+    if (fb) launch_prove_bits_fb(st, d, b); else launch_prove_bits(st, d, b);
     ctx->launches++;
     for (uint32_t s = 0; s < P; s++)
         for (uint32_t k = 0; k < ext; k++) sc_store(hio + 32 * ((size_t)s * ext + k), pp[live[s]].alpha[k]);
-    PCUDA(cudaMemcpy2DAsync(d_mscal.as<uint8_t>() + 32 * (size_t)N, 32 * (size_t)(N + ext), hio, 32 * (size_t)ext, 32 * (size_t)ext, P,
-                            cudaMemcpyHostToDevice, st));
-    {
+    if (fb) {
+        PCUDA(cudaMemcpy2DAsync(d_mscal.as<uint8_t>() + 32 * (size_t)(2 * N), 32 * (size_t)segA, hio, 32 * (size_t)ext, 32 * (size_t)ext, P,
+                                cudaMemcpyHostToDevice, st));
+        PCUDA(run_fb(P, segA, 1, gi_A, 0, 0));
+    } else {
+        PCUDA(cudaMemcpy2DAsync(d_mscal.as<uint8_t>() + 32 * (size_t)N, 32 * (size_t)(N + ext), hio, 32 * (size_t)ext, 32 * (size_t)ext, P,
+                                cudaMemcpyHostToDevice, st));
         std::vector<uint32_t> off(P + 1);
         for (uint32_t s = 0; s <= P; s++) off[s] = s * (N + ext);
         PCUDA(run_msm(P * (N + ext), P, off));
@@ -306,9 +365,13 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
             }
         });
         PCUDA(cudaMemcpyAsync(d_dlr.p, hio, 64 * (size_t)P * ext, cudaMemcpyHostToDevice, st));
-        launch_prove_round_pre(st, d, b, nn, round);
-        ctx->launches++;
-        {
+        if (fb) {
+            launch_prove_round_pre_fb(st, d, b, nn);
+            ctx->launches++;
+            PCUDA(run_fb(2 * P, segLR, 2, gi_round0 + (size_t)round * 2 * segLR, 0, 0));
+        } else {
+            launch_prove_round_pre(st, d, b, nn, round);
+            ctx->launches++;
             const uint32_t seg_len = 1 + ext + 2 * nn;
             std::vector<uint32_t> off(2 * P + 1);
             for (uint32_t s = 0; s <= 2 * P; s++) off[s] = s * seg_len;
@@ -328,8 +391,8 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         });
         for (uint32_t s = 0; s < P; s++) sc_store(hio + 32 * (size_t)s, pp[live[s]].e_round[round]);
         PCUDA(cudaMemcpyAsync(d_e.p, hio, 32 * (size_t)P, cudaMemcpyHostToDevice, st));
-        launch_prove_fold(st, d, b, nn, round, g->d_table.as<aniels>());
-        ctx->launches += 3;
+        if (fb) { launch_prove_fold_fb(st, d, b, nn); ctx->launches += 2; }
+        else { launch_prove_fold(st, d, b, nn, round, g->d_table.as<aniels>()); ctx->launches += 3; }
     }
 
     // ---- final (:542-594)
@@ -339,16 +402,50 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     std::vector<uint8_t> ab(64 * (size_t)P);
     PCUDA(cudaMemcpyAsync(ab.data(), d_ab.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
+    auto draw_final = [&](PProof &p) {
+        p.r = random_not_zero(p.rng);                 // always from the rng, even with a seed nonce (:542-543)
+        p.s = random_not_zero(p.rng);
+        for (uint32_t k = 0; k < ext; k++) p.d[k] = p.has_seed ? nonce(p.seed, "d", false, 0, true, k) : random_not_zero(p.rng);
+        for (uint32_t k = 0; k < ext; k++) p.eta[k] = p.has_seed ? nonce(p.seed, "eta", false, 0, true, k) : random_not_zero(p.rng);
+    };
+    if (fb) {
+        // A1 = sum_j r*sG[j]*G_j + sum_j s*sH[j]*H_j + sum d[k]*G[k] + (r*y*b[0] + s*y*a[0])*H   (:574-580, Gi[0] / Hi[0] unfolded)
+        // B  = (r*y*s)*H + sum eta[k]*G[k]                                                        (:581-584)
+        uint8_t *h_rs = hio, *h_tail = hio + 64 * (size_t)P, *h_b = h_tail + 32 * (size_t)P * (1 + ext);
+        ctx->workers().run(P, 8, [&](size_t s) {
+            PProof &p = pp[live[s]];
+            draw_final(p);
+            const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
+            const sc ry = sc_mul(p.r, p.y), sy = sc_mul(p.s, p.y);
+            sc_store(h_rs + 64 * s, p.r); sc_store(h_rs + 64 * s + 32, p.s);
+            uint8_t *tl = h_tail + 32 * s * (1 + ext);
+            for (uint32_t k = 0; k < ext; k++) sc_store(tl + 32 * k, p.d[k]);
+            sc_store(tl + 32 * ext, sc_add(sc_mul(ry, b0), sc_mul(sy, a0)));
+            uint8_t *bv = h_b + 32 * s * segB;
+            sc_store(bv, sc_mul(ry, p.s));
+            for (uint32_t k = 0; k < ext; k++) sc_store(bv + 32 * (1 + k), p.eta[k]);
+        });
+        const size_t firstB = (size_t)P * segA1;
+        PCUDA(cudaMemcpyAsync(ws.d_rs.p, h_rs, 64 * (size_t)P, cudaMemcpyHostToDevice, st));
+        PCUDA(cudaMemcpy2DAsync(d_mscal.as<uint8_t>() + 32 * (size_t)(2 * N), 32 * (size_t)segA1, h_tail, 32 * (size_t)(1 + ext), 32 * (size_t)(1 + ext), P,
+                                cudaMemcpyHostToDevice, st));
+        PCUDA(cudaMemcpyAsync(d_mscal.as<uint8_t>() + 32 * firstB, h_b, 32 * (size_t)P * segB, cudaMemcpyHostToDevice, st));
+        launch_prove_final_fb(st, d, b, ws.d_rs.as<uint32_t>());
+        ctx->launches++;
+        PCUDA(run_fb(P, segA1, 1, gi_A1, 0, 0));
+        PCUDA(run_fb(P, segB, 1, gi_B, firstB, P));
+        PCUDA(cudaStreamSynchronize(st));      // hio is about to receive the encodings
+        PCUDA(cudaMemsetAsync(ws.d_rs.p, 0, 64 * (size_t)P, st));
+        PCUDA(cudaMemsetAsync(ws.d_sg.p, 0, 32 * (size_t)P * N, st));
+        PCUDA(cudaMemsetAsync(ws.d_sh.p, 0, 32 * (size_t)P * N, st));
+    } else {
     const uint32_t len1 = 3 + ext, len2 = 1 + ext, per = len1 + len2;
     uint8_t *h_sc = hio;
     uint32_t *h_px = reinterpret_cast<uint32_t *>(hio + 32 * (size_t)P * per);
     const uint32_t GEN = 0x80000000u, CACHED = 0x40000000u;
     ctx->workers().run(P, 8, [&](size_t s) {
         PProof &p = pp[live[s]];
-        p.r = random_not_zero(p.rng);                 // always from the rng, even with a seed nonce (:542-543)
-        p.s = random_not_zero(p.rng);
-        for (uint32_t k = 0; k < ext; k++) p.d[k] = p.has_seed ? nonce(p.seed, "d", false, 0, true, k) : random_not_zero(p.rng);
-        for (uint32_t k = 0; k < ext; k++) p.eta[k] = p.has_seed ? nonce(p.seed, "eta", false, 0, true, k) : random_not_zero(p.rng);
+        draw_final(p);
         const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
         const sc ry = sc_mul(p.r, p.y), sy = sc_mul(p.s, p.y);
         uint8_t *sv = h_sc + 32 * s * per;
@@ -371,6 +468,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         PCUDA(cudaStreamSynchronize(st));
         PCUDA(run_msm(P * per, 2 * P, off));
     }
+    }
     PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
     // Zeroizing<..> of the reference (:300-301, :325, :438-464, :542-571): wipe the device copies of the secrets
     PCUDA(cudaMemsetAsync(d_a.p, 0, 32 * (size_t)P * N, st));
@@ -383,8 +481,8 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     ctx->workers().run(P, 8, [&](size_t s) {
         const size_t i = live[s];
         PProof &p = pp[i];
-        memcpy(p.A1, hio + 64 * s, 32);
-        memcpy(p.B, hio + 64 * s + 32, 32);
+        memcpy(p.A1, fb ? hio + 32 * s : hio + 64 * s, 32);                    // fixed-base path: [A1 x P | B x P]
+        memcpy(p.B, fb ? hio + 32 * ((size_t)P + s) : hio + 64 * s + 32, 32);
         bool good = append_point(p.t, LBL("A1"), p.A1) && append_point(p.t, LBL("B"), p.B);      // transcripts.rs:152-162
         if (good) { rebuild_rng(p); good = challenge(p.t, LBL("e"), p.e_final); }
         if (!good && !p.rc) p.rc = BPP_VERIFICATION_FAILED;

@@ -225,6 +225,114 @@ __global__ void __launch_bounds__(128) k_prove_final_ab(PDims d, PBuffers b, uin
     p_st_sc(out + 16 * (size_t)p + 8, sc_from_mont(p_ld_sc(b.b + 8 * (size_t)p * d.N)));
 }
 
+// ================================================================================================================ fixed-base path
+// Same protocol, no generator folding: the folded vectors of round k are linear combinations of the ORIGINAL generators,
+//   Gi^(k)[i] = sum_{j : j mod n_k = i} sG[j] * G_j,      Hi^(k)[i] = sum_{j : j mod n_k = i} sH[j] * H_j        (n_k = N / 2^k),
+// with sG = sH = 1 before round 0 and, at the fold with challenge e and nn = n_k / 2 (:511-521),
+//   (j mod n_k) <  nn :  sG[j] *= e^-1,         sH[j] *= e
+//   (j mod n_k) >= nn :  sG[j] *= e * y^-nn,    sH[j] *= e^-1.
+// Every L / R / A1 is therefore an N-term sum over the static generators, evaluated by K-FB (k_fb.cu) from window tables.
+// Entry layouts (scalars canonical, one segment per commitment; the matching generator-index rows come from the host):
+//   A   (seg_len 2N + ext)       [a_L[j] -> G_j | a_R[j] -> H_j | alpha_k -> G_k]
+//   L/R (seg_len 1 + ext + N)    [c -> H | d[k] -> G_k | N/2 G terms | N/2 H terms]
+//         L: G terms t -> j = (t / nn) * 2nn + nn + (t % nn),  a_lo[t % nn] * y^-nn * sG[j];   H terms -> j - nn,  b_hi[t % nn] * sH[j - nn]
+//         R: G terms t -> j = (t / nn) * 2nn + (t % nn),       a_hi[t % nn] * y^nn  * sG[j];   H terms -> j + nn,  b_lo[t % nn] * sH[j + nn]
+//   A1  (seg_len 2N + 1 + ext)   [r * sG[j] -> G_j | s * sH[j] -> H_j | d[k] -> G_k | (r*y*b + s*y*a) -> H]
+__global__ void __launch_bounds__(128) k_prove_bits_fb(PDims d, PBuffers b) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= d.P * d.N) return;
+    uint32_t p = gid / d.N, i = gid % d.N, j = i / d.n, bit_i = i % d.n;
+    uint64_t v = b.offset_values[(size_t)p * d.m + j];
+    uint32_t bit = (uint32_t)(v >> bit_i) & 1u;
+    const size_t seg = (size_t)p * (2 * d.N + d.ext);
+    p_st_sc(b.msm_scalars + 8 * (seg + i), bit ? sc_one() : sc_zero());                  // a_L
+    p_st_sc(b.msm_scalars + 8 * (seg + d.N + i), bit ? sc_zero() : sc_neg(sc_one()));    // a_R = a_L - 1
+    const sc one_m = sc_const_R();
+    p_st_sc(b.a + 8 * ((size_t)p * d.N + i), bit ? one_m : sc_zero());
+    p_st_sc(b.b + 8 * ((size_t)p * d.N + i), bit ? sc_zero() : sc_neg(one_m));
+    p_st_sc(b.sg + 8 * ((size_t)p * d.N + i), one_m);
+    p_st_sc(b.sh + 8 * ((size_t)p * d.N + i), one_m);
+}
+
+// one warp per proof; segment 2p is L, 2p + 1 is R
+__global__ void __launch_bounds__(128) k_prove_round_pre_fb(PDims d, PBuffers b, uint32_t nn) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= d.P) return;
+    const uint32_t seg_len = 1 + d.ext + d.N, half = d.N / 2;
+    const size_t eL = (size_t)(2 * p) * seg_len, eR = eL + seg_len;
+    const uint32_t *yp = b.ypow + 8 * (size_t)p * (d.N + 2);
+    const uint32_t log_nn = 31 - __clz(nn);
+    const sc yinv_nn = p_ld_sc(b.yinv2 + 8 * ((size_t)p * BPP_MAX_ROUNDS + log_nn));
+    const sc y_nn = p_ld_sc(yp + 8 * nn);
+    uint32_t *a = b.a + 8 * (size_t)p * d.N, *bb = b.b + 8 * (size_t)p * d.N;
+    const uint32_t *sg = b.sg + 8 * (size_t)p * d.N, *sh = b.sh + 8 * (size_t)p * d.N;
+    sc cL = sc_zero(), cR = sc_zero();
+    for (uint32_t i = lane; i < nn; i += 32) {
+        sc a_lo = p_ld_sc(a + 8 * i), a_hi = p_ld_sc(a + 8 * (nn + i));
+        sc b_lo = p_ld_sc(bb + 8 * i), b_hi = p_ld_sc(bb + 8 * (nn + i));
+        cL = sc_add(cL, pmm(pmm(a_lo, p_ld_sc(yp + 8 * (i + 1))), b_hi));
+        cR = sc_add(cR, pmm(pmm(a_hi, p_ld_sc(yp + 8 * (nn + 1 + i))), b_lo));
+        p_st_sc(a + 8 * (nn + i), pmm(a_hi, y_nn));                     // a_hi' kept for the fold: a' = a_lo*e + a_hi'*e^-1
+    }
+    __syncwarp();
+    for (uint32_t t = lane; t < half; t += 32) {
+        const uint32_t i = t % nn, jl = (t / nn) * 2 * nn + i, ju = jl + nn;
+        const sc a_lo_off = pmm(p_ld_sc(a + 8 * i), yinv_nn), a_hi_off = p_ld_sc(a + 8 * (nn + i));
+        const uint32_t o = 1 + d.ext + t;
+        p_st_sc(b.msm_scalars + 8 * (eL + o), sc_from_mont(pmm(a_lo_off, p_ld_sc(sg + 8 * ju))));
+        p_st_sc(b.msm_scalars + 8 * (eL + o + half), sc_from_mont(pmm(p_ld_sc(bb + 8 * (nn + i)), p_ld_sc(sh + 8 * jl))));
+        p_st_sc(b.msm_scalars + 8 * (eR + o), sc_from_mont(pmm(a_hi_off, p_ld_sc(sg + 8 * jl))));
+        p_st_sc(b.msm_scalars + 8 * (eR + o + half), sc_from_mont(pmm(p_ld_sc(bb + 8 * i), p_ld_sc(sh + 8 * ju))));
+    }
+    for (int delta = 16; delta > 0; delta >>= 1) { cL = sc_add(cL, shfl_down_sc_p(cL, delta)); cR = sc_add(cR, shfl_down_sc_p(cR, delta)); }
+    if (lane == 0) {
+        p_st_sc(b.msm_scalars + 8 * eL, sc_from_mont(cL));
+        p_st_sc(b.msm_scalars + 8 * eR, sc_from_mont(cR));
+    }
+    if (lane < d.ext) {
+        const uint32_t *dl = b.dlr + 8 * ((size_t)p * 2 * d.ext + lane), *dr = dl + 8 * d.ext;
+        p_st_sc(b.msm_scalars + 8 * (eL + 1 + lane), p_ld_sc(dl));
+        p_st_sc(b.msm_scalars + 8 * (eR + 1 + lane), p_ld_sc(dr));
+    }
+}
+
+// per (proof, j < N): the fold as scalar updates; j < nn also folds a and b (:523-533)
+__global__ void __launch_bounds__(128) k_prove_fold_fb(PDims d, PBuffers b, uint32_t nn) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= d.P * d.N) return;
+    const uint32_t p = gid / d.N, j = gid % d.N;
+    const uint32_t *f = b.fsc + 8 * (size_t)p * 6;
+    const sc e = p_ld_sc(f + 32), einv = p_ld_sc(f + 40);
+    const uint32_t log_nn = 31 - __clz(nn);
+    const bool upper = (j & (2 * nn - 1)) >= nn;
+    uint32_t *sg = b.sg + 8 * ((size_t)p * d.N + j), *sh = b.sh + 8 * ((size_t)p * d.N + j);
+    if (upper) {
+        const sc eyinv = pmm(e, p_ld_sc(b.yinv2 + 8 * ((size_t)p * BPP_MAX_ROUNDS + log_nn)));
+        p_st_sc(sg, pmm(p_ld_sc(sg), eyinv));
+        p_st_sc(sh, pmm(p_ld_sc(sh), einv));
+    } else {
+        p_st_sc(sg, pmm(p_ld_sc(sg), einv));
+        p_st_sc(sh, pmm(p_ld_sc(sh), e));
+    }
+    if (j < nn) {
+        uint32_t *a = b.a + 8 * (size_t)p * d.N, *bb = b.b + 8 * (size_t)p * d.N;
+        sc a_lo = p_ld_sc(a + 8 * j), a_hi = p_ld_sc(a + 8 * (nn + j)), b_lo = p_ld_sc(bb + 8 * j), b_hi = p_ld_sc(bb + 8 * (nn + j));
+        p_st_sc(a + 8 * j, sc_add(pmm(a_lo, e), pmm(a_hi, einv)));
+        p_st_sc(bb + 8 * j, sc_add(pmm(b_lo, einv), pmm(b_hi, e)));
+    }
+}
+
+// per (proof, j < N): the generator terms of A1 (r * sG[j], s * sH[j]); rs: P x 2 canonical scalars from the host
+__global__ void __launch_bounds__(128) k_prove_final_fb(PDims d, PBuffers b, const uint32_t *__restrict__ rs) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= d.P * d.N) return;
+    const uint32_t p = gid / d.N, j = gid % d.N;
+    const sc r = sc_to_mont(p_ld_sc(rs + 16 * (size_t)p)), s = sc_to_mont(p_ld_sc(rs + 16 * (size_t)p + 8));
+    const size_t seg = (size_t)p * (2 * d.N + 1 + d.ext);
+    p_st_sc(b.msm_scalars + 8 * (seg + j), sc_from_mont(pmm(r, p_ld_sc(b.sg + 8 * ((size_t)p * d.N + j)))));
+    p_st_sc(b.msm_scalars + 8 * (seg + d.N + j), sc_from_mont(pmm(s, p_ld_sc(b.sh + 8 * ((size_t)p * d.N + j)))));
+}
+
 // ---------------------------------------------------------------------------------------------------------------- launchers
 void launch_prove_bits(cudaStream_t s, const PDims &d, const PBuffers &b) {
     k_prove_bits<<<(d.P * d.N + 127) / 128, 128, 0, s>>>(d, b);
@@ -241,6 +349,19 @@ void launch_prove_fold(cudaStream_t s, const PDims &d, const PBuffers &b, uint32
     uint32_t quads = d.P * nn * 2;
     k_prove_fold_pts<<<(quads + FOLD_QUADS - 1) / FOLD_QUADS, 4 * FOLD_QUADS, 0, s>>>(d, b, nn, round, gens);
     k_prove_fold_sc<<<(d.P * nn + 127) / 128, 128, 0, s>>>(d, b, nn);
+}
+void launch_prove_bits_fb(cudaStream_t s, const PDims &d, const PBuffers &b) {
+    k_prove_bits_fb<<<(d.P * d.N + 127) / 128, 128, 0, s>>>(d, b);
+}
+void launch_prove_round_pre_fb(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn) {
+    k_prove_round_pre_fb<<<(d.P + 3) / 4, 128, 0, s>>>(d, b, nn);
+}
+void launch_prove_fold_fb(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn) {
+    k_prove_round_inv<<<(d.P + 63) / 64, 64, 0, s>>>(d, b, nn);
+    k_prove_fold_fb<<<(d.P * d.N + 127) / 128, 128, 0, s>>>(d, b, nn);
+}
+void launch_prove_final_fb(cudaStream_t s, const PDims &d, const PBuffers &b, const uint32_t *rs) {
+    k_prove_final_fb<<<(d.P * d.N + 127) / 128, 128, 0, s>>>(d, b, rs);
 }
 void launch_prove_final_ab(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t *out) {
     k_prove_final_ab<<<(d.P + 127) / 128, 128, 0, s>>>(d, b, out);

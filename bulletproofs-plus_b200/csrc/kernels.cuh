@@ -36,6 +36,18 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
                 const cached *dync = nullptr);
 // marks (optional, 4 events): recorded after the sort phase (digits+scan+scatter), bucket sums, window reduction, Horner
 
+// ---------------------------------------------------------------- k_fb.cu
+// fixed-base window tables over a generator set: table[g][w][d-1] = d * 2^(c*w) * P_g (affine Niels), W = ceil(252/c), B = 2^(c-1)
+struct FbShape { uint32_t n_gens; int c, W; uint32_t B; };
+FbShape fb_shape(uint32_t n_gens, int forced_c, size_t max_bytes);
+size_t fb_table_bytes(const FbShape &sh);
+// builds the table (synchronises the stream; temporary device scratch is allocated and freed inside); 0 = ok
+int fb_build(cudaStream_t s, const FbShape &sh, const aniels *gens, aniels *tab, uint64_t *launches);
+// n_seg independent sums of seg_len terms each: scalars canonical, segment-major; gidx[kinds][seg_len] generator index per entry
+// (segment s uses row s % kinds); out: n_seg extended points
+void launch_fb_msm(cudaStream_t s, const FbShape &sh, uint32_t n_seg, uint32_t seg_len, uint32_t kinds, const uint32_t *scalars, const uint32_t *gidx,
+                   const aniels *tab, ge *out, uint64_t *launches);
+
 // ---------------------------------------------------------------- k_verify.cu
 #define BPP_TSTATE_BYTES 203 // merlin STROBE-128 state on the wire: 200 B Keccak state, pos, pos_begin, cur_flags
 #define BPP_MAX_ROUNDS 24  // log2(n * m) <= 24 (generator sets are capped at 2^24 points)
@@ -111,7 +123,8 @@ struct PBuffers {
     const uint32_t *dlr;             // P x 2 x ext canonical: d_L[k], d_R[k] of the current round
     const uint32_t *e;               // P canonical: round challenge
     uint32_t *fsc;                   // P x 6: fold scalars (see k_prove_round_inv)
-    cached *folded;                  // [Gi: P x N | Hi: P x N] folded generator vectors (valid from round 1 on)
+    cached *folded;                  // [Gi: P x N | Hi: P x N] folded generator vectors (valid from round 1 on; folding path)
+    uint32_t *sg, *sh;               // P x N scalars, Montgomery: the folding as coefficients over the original generators (fixed-base path)
     uint32_t *msm_scalars;           // entry scalars of the MSM being assembled (canonical)
     uint32_t *msm_pidx;              // entry point indices
 };
@@ -120,6 +133,11 @@ void launch_prove_init(cudaStream_t s, const PDims &d, const PBuffers &b);
 void launch_prove_round_pre(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn, uint32_t round);
 void launch_prove_fold(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn, uint32_t round, const aniels *gens);
 void launch_prove_final_ab(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t *out);
+// fixed-base path (no generator folding; see k_prove.cu)
+void launch_prove_bits_fb(cudaStream_t s, const PDims &d, const PBuffers &b);
+void launch_prove_round_pre_fb(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn);
+void launch_prove_fold_fb(cudaStream_t s, const PDims &d, const PBuffers &b, uint32_t nn);      // e^-1, sG / sH update, a / b fold: 2 kernels
+void launch_prove_final_fb(cudaStream_t s, const PDims &d, const PBuffers &b, const uint32_t *rs);
 
 // ---------------------------------------------------------------- k_bench.cu
 // returns elapsed seconds for `iters` dependent ops in each of `threads_total` lanes; ops counted by caller

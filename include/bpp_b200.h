@@ -126,6 +126,11 @@ void bpp_msm_plan_destroy(bpp_msm_plan *plan);
 int32_t bpp_gens_create(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree,
                         bpp_gens **out);
 void bpp_gens_destroy(bpp_gens *g);
+/* Fixed-base multiscalar multiplication over the generator set (the static half of Precomputation::vartime_mixed_multiscalar_mul,
+ * generators/bulletproof_gens.rs:103, range_proof.rs:339-345): n_seg sums of seg_len terms, out32[s] = encode(sum_e scalars32[s][e] *
+ * P[gidx[e]]), generator order Gi(n*M) | Hi(n*M) | G(ext) | H.  Window tables are built on first use (BPP_FB_MAX_MB, default 2048,
+ * bounds them; BPP_SIZE_OVERFLOW if they cannot fit). */
+int32_t bpp_gens_fixed_base_msm(bpp_gens *gens, size_t n_seg, size_t seg_len, const uint8_t *scalars32, const uint32_t *gidx, uint8_t *out32);
 /* which: 0 = h_base, 1 = g_base[index], 2 = gi_base (flat, party-major), 3 = hi_base */
 int32_t bpp_gens_get(const bpp_gens *g, int32_t which, size_t index, uint8_t out32[32]);
 /* PedersenGens::commit for `count` openings: values[count], blindings32[count * n_blindings] */

@@ -202,3 +202,30 @@ def test_microbench_runs():
         ops, sec = e.microbench(which, 200)
         assert ops > 1e9 and sec > 0
     assert e.launch_count > before
+
+
+@pytest.mark.parametrize("shape", [(8, 2, 1), (64, 1, 3)])
+def test_fixed_base_msm_matches_oracle(shape):
+    """bpp_gens_fixed_base_msm (window tables over Gi | Hi | G_k | H, k_fb.cu) against the oracle's plain MSM over the same
+    generator encodings: random scalars, the prover's {0, 1, l-1} pattern, repeated generators, several segments"""
+    n, M, ext = shape
+    e = bpp.engine()
+    g = bpp.pkg.Gens(e, n, M, ext)
+    total = 2 * n * M + ext + 1
+    pts = [g.point(2, i) for i in range(n * M)] + [g.point(3, i) for i in range(n * M)] + [g.point(1, k) for k in range(ext)] + [g.point(0)]
+    rng = orc.Rng("chacha", 31)
+    gidx = list(range(total)) + [0, total - 1, 5 % total, 5 % total]
+    n_seg = 5
+    segs = []
+    for s in range(n_seg):
+        if s == 1:
+            row = [[0, 1, orc.L - 1][(i * 7 + s) % 3] for i in range(len(gidx))]
+        elif s == 2:
+            row = [0] * len(gidx)
+        else:
+            row = [rng.random_not_zero() for _ in gidx]
+        segs.append([orc.sc_bytes(x) for x in row])
+    got = g.fixed_base_msm(b"".join(b"".join(r) for r in segs), gidx, n_seg)
+    for s in range(n_seg):
+        assert got[s] == _orc_msm(segs[s], [pts[i] for i in gidx]), s
+    g.close()

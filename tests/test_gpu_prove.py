@@ -129,3 +129,19 @@ def test_prover_error_paths_match_oracle():
     w2 = api.RangeWitness.init([api.CommitmentOpening(1, [1, 2])])
     res = api.RangeProof.prove_batch([api.Transcript(LABEL)], [sts[0]], [w2], [streams[0]])
     assert isinstance(res[0], bpp.pkg.EngineError) and res[0].code == orc.INVALID_LENGTH
+
+
+def test_folding_path_still_byte_identical():
+    """the prover's default path evaluates every commitment from fixed-base window tables (k_fb.cu); the generator-folding path it
+    replaces stays for generator sets whose tables exceed the memory budget -- run this file's byte-identity tests through it"""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("BPP_PROVE_FOLD"):
+        pytest.skip("already inside the folding-path run")
+    env = dict(os.environ, BPP_PROVE_FOLD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_prove.py"), "-x", "-q", "-m", "gpu"],
+                       env=env, capture_output=True, text=True, timeout=1200, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -164,36 +164,62 @@ def run_extras(eng, api, bpp, orc, args):
     import hashlib
 
     out = {}
-    # ---- prover: P non-aggregated 64-bit proofs per bpp_prove_batch call (BASELINE.json configs[0] shape, batched)
-    P = args.prove_batch
-    gp = api.RangeParameters.init(eng, BIT_LENGTH, 1, EXT)
+    # ---- prover: P non-aggregated 64-bit proofs (BASELINE.json configs[0] shape, batched), as `lanes` concurrent bpp_prove_batch
+    # calls of P / lanes proofs each (one bpp_ctx + host thread per call: the host Fiat-Shamir of one call overlaps the device
+    # work of the others); timed: the C-ABI calls with host buffers, arguments packed beforehand
+    P, PL = args.prove_batch, max(1, args.prove_lanes)
+    per = P // PL
+    ppool = api.VerifierPool(eng.device, BIT_LENGTH, 1, EXT, lanes=PL, blocking_waits=False)
+    gp = ppool.lanes[0][1]
     rng = orc.Rng("chacha", 4242)
     vals = [rng.next_u64() % (1 << 63) for _ in range(P)]
     blinds = [[rng.random_not_zero()] for _ in range(P)]
     commits = gp.gens.commit_batch(vals, blinds)
-    sts = [api.RangeStatement.init(gp, [commits[i]], [vals[i] // 3], rng.random_not_zero()) for i in range(P)]
-    wits = [api.RangeWitness.init([api.CommitmentOpening(vals[i], blinds[i])]) for i in range(P)]
+    seeds = [rng.random_not_zero() for _ in range(P)]
     need = api.RangeProof.rng_bytes_needed(gp, 1)
     streams = [hashlib.shake_256(b"bench-rng-%d" % i).digest(need) for i in range(P)]
+    packs = []
+    for li in range(PL):
+        prm = ppool.lanes[li][1]
+        idx = range(li * per, (li + 1) * per)
+        sts = [api.RangeStatement.init(prm, [commits[i]], [vals[i] // 3], seeds[i]) for i in idx]
+        wits = [api.RangeWitness.init([api.CommitmentOpening(vals[i], blinds[i])]) for i in idx]
+        packs.append(api._PackedProve(prm, [api.Transcript(b"BatchedRangeProofTest") for _ in idx], sts, wits, [streams[i] for i in idx]))
+
+    def prove_job(li, e, prm, i):
+        packs[i].reset_transcripts()
+        packs[i].run()
+
     times = []
-    for _ in range(4):
-        trs = [api.Transcript(b"BatchedRangeProofTest") for _ in range(P)]
-        proofs = api.RangeProof.prove_batch(trs, sts, wits, streams)
-        times.append(api.RangeProof.last_prove_call_ms)
-    assert not any(isinstance(p, Exception) for p in proofs)
+    for _ in range(5):
+        t0 = time.perf_counter()
+        ppool.run(prove_job, PL)
+        times.append((time.perf_counter() - t0) * 1e3)
     ms = sorted(times[1:])[len(times[1:]) // 2]
+    proofs = [r for pk in packs for r in pk.results()]
+    assert not any(isinstance(p, Exception) for p in proofs)
     # byte-identical to the CPU oracle on the first proofs, and timed there on a bounded sample (single thread)
     op = orc.Params(BIT_LENGTH, 1, EXT)
     t0 = time.perf_counter()
     n_cpu = 8
     for i in range(n_cpu):
-        st = orc.St(op, [commits[i]], [vals[i] // 3], sts[i].seed_nonce)
+        st = orc.St(op, [commits[i]], [vals[i] // 3], seeds[i])
         rc, pr, _ = orc.prove(orc.transcript_new(b"BatchedRangeProofTest"), st, orc.Wit([vals[i]], [blinds[i]]), orc.Rng("buffer", data=streams[i]))
         assert rc == 0 and orc.proof_to_bytes(pr) == proofs[i].to_bytes()
     cpu_s = (time.perf_counter() - t0) / n_cpu
+    # algorithmic multiplies per proof on the fixed-base path: (2N + ext) + rounds * 2 * (1 + ext + N) + (2N + 1 + ext) + (1 + ext) table
+    # additions of W = 28 windows each, minus the zero digits of A's 0 / +-1 scalars, 7 field multiplications each
+    N_, R_ = BIT_LENGTH, 6
+    terms = R_ * 2 * (1 + EXT + N_) + (2 * N_ + 1 + EXT) + (1 + EXT)
+    mul32_per_proof = (terms * 28 + N_ + 28 * EXT) * MUL32_MADD
+    peak_ops, _ = eng.microbench(2, 2000)
     out["prove"] = {"metric": "64-bit range proofs proved/sec (batched lock-step, 1 GPU, through bpp_prove_batch with host buffers)",
-                    "value": P / (ms * 1e-3), "unit": "proofs/s", "batch": P, "ms_per_batch": ms,
+                    "value": per * PL / (ms * 1e-3), "unit": "proofs/s", "batch": per * PL, "concurrent_calls": PL, "ms_per_batch": ms,
+                    "path": "fixed-base window tables (k_fb.cu), no generator folding",
+                    "mul32_per_proof": mul32_per_proof, "achieved_tmul32_per_s": mul32_per_proof * per * PL / (ms * 1e-3) / 1e12,
+                    "frac_of_int32_mul_peak": mul32_per_proof * per * PL / (ms * 1e-3) / peak_ops,
                     "cpu_oracle_proofs_per_s_per_core": 1.0 / cpu_s, "byte_identical_to_oracle_checked": n_cpu}
+    ppool.close()
     # ---- raw MSM (BASELINE.json configs[4]), device-resident decoded points
     msm = {}
     for lg in args.msm_log2:
@@ -480,6 +506,7 @@ def main():
     ap.add_argument("--proofs", type=int, default=1024, help="proofs per GPU per step")
     ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput on rank 0 (secondary metrics)")
     ap.add_argument("--prove-batch", type=int, default=1024)
+    ap.add_argument("--prove-lanes", type=int, default=4, help="concurrent bpp_prove_batch calls the proving batch is split into")
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -264,36 +264,14 @@ class RangeProof:
             else:
                 live.append(i)
         if live:
-            need = RangeProof.rng_bytes_needed(params, m)
-            rounds = (params.bit_length() * m - 1).bit_length()
-            plen = _ffi.lib().bpp_proof_size(ext, rounds)
-            n = len(live)
-            commits = C.create_string_buffer(b"".join(c for i in live for c in statements[i].commitments), 32 * n * m)
-            values = _u64arr([o.v for i in live for o in witnesses[i].openings])
-            blind = C.create_string_buffer(b"".join(_sc(r) for i in live for o in witnesses[i].openings for r in o.r), 32 * n * m * ext)
-            minv = _u64arr([(v or 0) for i in live for v in statements[i].minimum_value_promises])
-            minp = (C.c_uint8 * (n * m))(*[0 if v is None else 1 for i in live for v in statements[i].minimum_value_promises])
-            seeds = C.create_string_buffer(b"".join(_sc(statements[i].seed_nonce) if statements[i].seed_nonce is not None else bytes(32) for i in live), 32 * n)
-            seedp = (C.c_uint8 * n)(*[0 if statements[i].seed_nonce is None else 1 for i in live])
-            tbuf = C.create_string_buffer(b"".join(transcripts[i].state for i in live), _ffi.TRANSCRIPT_BYTES * n)
-            for i in live:
-                if len(rng_bytes[i]) < need:
-                    raise EngineError(_ffi.INVALID_LENGTH, "rng_bytes: %d bytes needed per proof" % need)
-            rbuf = C.create_string_buffer(b"".join(bytes(rng_bytes[i][:need]) for i in live), need * n)
-            a = _ffi.ProveArgs(n, m, C.addressof(commits), C.addressof(values), C.addressof(blind), C.addressof(minv), C.addressof(minp),
-                               C.addressof(seeds), C.addressof(seedp), C.addressof(tbuf), C.addressof(rbuf), need)
-            out = C.create_string_buffer(plen * n)
-            status = (C.c_int32 * n)()
+            pk = _PackedProve(params, [transcripts[i] for i in live], [statements[i] for i in live], [witnesses[i] for i in live],
+                              [rng_bytes[i] for i in live])
             import time as _time
             _t0 = _time.perf_counter()
-            _chk(params.gens.engine, _ffi.lib().bpp_prove_batch(params.gens.h, C.byref(a), out, plen, status))
+            pk.run()
             RangeProof.last_prove_call_ms = (_time.perf_counter() - _t0) * 1e3      # the C-ABI call alone (bench)
-            for k, i in enumerate(live):
-                transcripts[i].state = tbuf.raw[_ffi.TRANSCRIPT_BYTES * k: _ffi.TRANSCRIPT_BYTES * (k + 1)]
-                if status[k]:
-                    results[i] = EngineError(status[k], "prove_with_rng")
-                else:
-                    results[i] = RangeProof(out.raw[plen * k: plen * (k + 1)], ext, rounds)
+            for i, res in zip(live, pk.results()):
+                results[i] = res
         return results
 
     @staticmethod
@@ -320,6 +298,53 @@ class RangeProof:
         if status[0]:
             raise EngineError(status[0], "verify_batch")
         return masks[0][:MAX_RANGE_PROOF_BATCH_SIZE]
+
+
+class _PackedProve:
+    """Flat host buffers for bpp_prove_args: P statements of one shape (kept alive for the duration of the call)."""
+
+    def __init__(self, params, transcripts, statements, witnesses, rng_bytes):
+        ext, m = params.gens.extension_degree, len(statements[0].commitments)
+        n = len(statements)
+        self.params, self.transcripts, self.n, self.ext = params, transcripts, n, ext
+        need = RangeProof.rng_bytes_needed(params, m)
+        self.rounds = (params.bit_length() * m - 1).bit_length()
+        self.plen = _ffi.lib().bpp_proof_size(ext, self.rounds)
+        for r in rng_bytes:
+            if len(r) < need:
+                raise EngineError(_ffi.INVALID_LENGTH, "rng_bytes: %d bytes needed per proof" % need)
+        self.commits = C.create_string_buffer(b"".join(c for s in statements for c in s.commitments), 32 * n * m)
+        self.values = _u64arr([o.v for w in witnesses for o in w.openings])
+        self.blind = C.create_string_buffer(b"".join(_sc(r) for w in witnesses for o in w.openings for r in o.r), 32 * n * m * ext)
+        self.minv = _u64arr([(v or 0) for s in statements for v in s.minimum_value_promises])
+        self.minp = (C.c_uint8 * (n * m))(*[0 if v is None else 1 for s in statements for v in s.minimum_value_promises])
+        self.seeds = C.create_string_buffer(b"".join(_sc(s.seed_nonce) if s.seed_nonce is not None else bytes(32) for s in statements), 32 * n)
+        self.seedp = (C.c_uint8 * n)(*[0 if s.seed_nonce is None else 1 for s in statements])
+        self.t_init = b"".join(t.state for t in transcripts)
+        self.tbuf = C.create_string_buffer(self.t_init, _ffi.TRANSCRIPT_BYTES * n)
+        self.rbuf = C.create_string_buffer(b"".join(bytes(r[:need]) for r in rng_bytes), need * n)
+        self.args = _ffi.ProveArgs(n, m, C.addressof(self.commits), C.addressof(self.values), C.addressof(self.blind), C.addressof(self.minv),
+                                   C.addressof(self.minp), C.addressof(self.seeds), C.addressof(self.seedp), C.addressof(self.tbuf),
+                                   C.addressof(self.rbuf), need)
+        self.out = C.create_string_buffer(self.plen * n)
+        self.status = (C.c_int32 * n)()
+
+    def reset_transcripts(self):
+        C.memmove(self.tbuf, self.t_init, len(self.t_init))
+
+    def run(self):
+        _chk(self.params.gens.engine, _ffi.lib().bpp_prove_batch(self.params.gens.h, C.byref(self.args), self.out, self.plen, self.status))
+
+    def results(self):
+        """RangeProof or ProofError per statement; the transcripts are advanced in place"""
+        res = []
+        for k, t in enumerate(self.transcripts):
+            t.state = self.tbuf.raw[_ffi.TRANSCRIPT_BYTES * k: _ffi.TRANSCRIPT_BYTES * (k + 1)]
+            if self.status[k]:
+                res.append(EngineError(self.status[k], "prove_with_rng"))
+            else:
+                res.append(RangeProof(self.out.raw[self.plen * k: self.plen * (k + 1)], self.ext, self.rounds))
+        return res
 
 
 class _Packed:
@@ -495,6 +520,16 @@ class VerifierPool:
         """batches: list of `calls` (each a list of (transcripts, statements, proofs), one entry per reference verify_batch
         call).  Returns [(status per call, masks per call)] in input order; transcripts are advanced in place."""
         return self.run(lambda li, eng, params, i: verify_chunks(params, batches[i], action), len(batches))
+
+    def prove_many(self, jobs):
+        """jobs: list of (transcripts, statements, witnesses, rng_bytes), each one RangeProof.prove_batch call (statements of one
+        shape); job i runs on lane i % S.  Returns the per-job result lists in input order.  Proof bytes do not depend on S."""
+        def one(li, eng, params, i):
+            trs, sts, wits, rbs = jobs[i]
+            pk = _PackedProve(params, trs, sts, wits, rbs)
+            pk.run()
+            return pk.results()
+        return self.run(one, len(jobs))
 
     def launch_count(self):
         return sum(eng.launch_count for eng, _ in self.lanes)

@@ -257,10 +257,22 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL_DEBUG=VERSION/INFO prints to stdout, which carries the one JSON line
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout (fd 1) when NCCL_DEBUG is set; stdout carries the one JSON line, so fd 1 points
+        # at stderr while the communicator comes up
+        os.environ.pop("NCCL_DEBUG", None)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     api = bpp.pkg.api
     lib = bpp.ffi.lib()
     S = max(1, min(args.lanes, args.steps))

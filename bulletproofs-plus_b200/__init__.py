@@ -161,6 +161,15 @@ class Engine:
         return ops.value, sec.value
 
 
+def points_sum_host(points):
+    """sum of <= 64 points given as concatenated 32-byte encodings, on the host (last step of a multi-GPU MSM)"""
+    out = C.create_string_buffer(32)
+    rc = _ffi.lib().bpp_points_sum_host(len(points) // 32, points, out)
+    if rc != 0:
+        raise EngineError(rc, "bpp_points_sum_host")
+    return out.raw
+
+
 class MsmPlan:
     """Device-resident point set for repeated MSMs (BASELINE.json configs[4])."""
 

@@ -105,6 +105,7 @@ def lib():
         "bpp_ctx_io_bytes": (i32, [vp, P(C.c_uint64)]),
         "bpp_decompress_check": (i32, [vp, sz, cp, cp, cp]),
         "bpp_from_uniform_batch": (i32, [vp, sz, cp, cp]),
+        "bpp_points_sum_host": (i32, [sz, cp, cp]),
         "bpp_msm": (i32, [vp, sz, cp, cp, cp]),
         "bpp_msm_segmented": (i32, [vp, sz, vp, cp, cp, cp]),
         "bpp_msm_plan_create": (i32, [vp, sz, cp, i32, P(vp)]),

@@ -220,6 +220,25 @@ int32_t bpp_decompress_check(bpp_ctx *ctx, size_t n, const uint8_t *in32, uint8_
     return BPP_OK;
 }
 
+// Host-side sum of a handful of points: the last step of a multi-GPU MSM, where every GPU has reduced its shard to one 32-byte
+// partial result (BASELINE.json north_star: "each GPU producing a partial Edwards point that is summed on the host").  Not a
+// compute path: n <= 64.
+int32_t bpp_points_sum_host(size_t n, const uint8_t *in32, uint8_t out32[32]) {
+    if (!out32 || (n && !in32) || n > 64) return BPP_INVALID_ARGUMENT;
+    ge acc = ge_identity();
+    for (size_t i = 0; i < n; i++) {
+        uint32_t w[8];
+        memcpy(w, in32 + 32 * i, 32);
+        ge p;
+        if (!ristretto_decode(p.X, p.Y, p.T, w)) return BPP_INVALID_ARGUMENT;
+        p.Z = fe_one();
+        acc = ge_add(acc, p);
+    }
+    fe enc = ristretto_encode(acc);
+    fe_tobytes(out32, enc);
+    return BPP_OK;
+}
+
 int32_t bpp_from_uniform_batch(bpp_ctx *ctx, size_t n, const uint8_t *in64, uint8_t *out32) {
     if (!ctx || (n && (!in64 || !out32))) return BPP_INVALID_ARGUMENT;
     if (n == 0) return BPP_OK;

@@ -53,5 +53,14 @@ def msm_distributed(engine, scalars, points, group=None):
         return partial
     parts = [None] * world
     dist.all_gather_object(parts, partial, group=group)
-    one = (1).to_bytes(32, "little")
-    return engine.msm(one * world, b"".join(parts))
+    return sum_partials(engine, b"".join(parts))
+
+
+def sum_partials(engine, parts):
+    """<= 8 partial results (32-byte encodings) -> their sum: added up on the host (bpp_points_sum_host); engines without that
+    entry point (the CPU stand-in of the gloo tests) fall back to a unit-scalar MSM"""
+    from . import points_sum_host
+
+    if hasattr(engine, "h"):
+        return points_sum_host(parts)
+    return engine.msm((1).to_bytes(32, "little") * (len(parts) // 32), parts)

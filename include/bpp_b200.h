@@ -98,6 +98,9 @@ int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);
  * replace CompressedRistretto::decompress / RistrettoPoint::compress / from_uniform_bytes as issued from
  * range_proof.rs:859-866,1067-1109 (decompress), :289,:348,:499-504,:587,:598-605 and range_statement.rs:62-65
  * (compress), ristretto.rs:48-52 <- generators_chain.rs:44-49 (one-way map). */
+/* Host-side sum of n <= 64 points (32-byte encodings): the last step of a multi-GPU MSM, each GPU having reduced its shard to one
+ * partial result.  BPP_INVALID_ARGUMENT if an encoding does not decode. */
+int32_t bpp_points_sum_host(size_t n, const uint8_t *in32, uint8_t out32[32]);
 /* ok[i] = 1 iff in32[i] is a canonical encoding; out32[i] = compress(decompress(in32[i])) (== in32[i] when ok) */
 int32_t bpp_decompress_check(bpp_ctx *ctx, size_t n, const uint8_t *in32, uint8_t *ok, uint8_t *out32_or_null);
 int32_t bpp_from_uniform_batch(bpp_ctx *ctx, size_t n, const uint8_t *in64, uint8_t *out32);

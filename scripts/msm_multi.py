@@ -24,7 +24,7 @@ rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_R
 torch.cuda.set_device(local)
 dist = None
 if world > 1:
-    os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.pop("NCCL_DEBUG", None)
     import torch.distributed as dist
 
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -61,7 +61,7 @@ for lg in sizes:
         buf.copy_(torch.frombuffer(bytearray(partial), dtype=torch.uint8))
         dist.all_gather_into_tensor(gathered, buf)
         parts = bytes(gathered.cpu().numpy())
-        return eng.msm((1).to_bytes(32, "little") * world, parts)
+        return par.sum_partials(eng, parts)
 
     res = once()
     reps = 5 if lg <= 20 else 3

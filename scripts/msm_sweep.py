@@ -11,7 +11,7 @@ for lg in sizes:
     sc = bytearray(hashlib.shake_256(b"sc%d" % lg).digest(32 * n))
     for i in range(31, len(sc), 32):
         sc[i] &= 0x0F
-    for c in ([0] if lg < 16 else [0, 11, 12, 13, 14, 15]):
+    for c in ([0] if lg < 16 else [0, 12, 13, 14, 15, 16]):
         plan = bpp.pkg.MsmPlan(eng, pts, c)
         plan.set_scalars(bytes(sc))
         ref = plan.run(True)

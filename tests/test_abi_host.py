@@ -107,3 +107,27 @@ def test_proof_check_bytes_matches_oracle(lib):
         rc_o, _ = orc.proof_from_bytes(v)
         rc_p, _, _ = bpp.pkg.proof_check_bytes(v)
         assert rc_p == rc_o, (len(v), rc_p, rc_o)
+
+
+def test_points_sum_host_matches_oracle():
+    """bpp_points_sum_host (host-side sum of the per-GPU partial results of a sharded MSM) against the oracle's unit-scalar MSM;
+    a non-decodable encoding is refused"""
+    import ctypes as C
+    import hashlib
+
+    import orc
+
+    o = C.create_string_buffer(32)
+    pts = []
+    for i in range(8):
+        orc.lib().orc_ristretto_from_uniform(hashlib.shake_256(b"partial-%d" % i).digest(64), o)
+        pts.append(o.raw)
+    for k in (0, 1, 2, 8):
+        got = bpp.pkg.points_sum_host(b"".join(pts[:k]))
+        if k == 0:
+            assert got == bytes(32)
+        else:
+            assert orc.lib().orc_msm((1).to_bytes(32, "little") * k, b"".join(pts[:k]), k, 0, o) == 1
+            assert got == o.raw
+    with pytest.raises(bpp.pkg.EngineError):
+        bpp.pkg.points_sum_host(pts[0] + b"\xff" * 32)

@@ -212,7 +212,7 @@ def run_extras(eng, api, bpp, orc, args):
     N_, R_ = BIT_LENGTH, 6
     terms = R_ * 2 * (1 + EXT + N_) + (2 * N_ + 1 + EXT) + (1 + EXT)
     mul32_per_proof = (terms * 28 + N_ + 28 * EXT) * MUL32_MADD
-    peak_ops, _ = eng.microbench(2, 2000)
+    peak_ops, _ = eng.microbench(1, 2000)              # IMAD.HI issue rate: the int32-multiply ceiling (see the roofline object)
     out["prove"] = {"metric": "64-bit range proofs proved/sec (batched lock-step, 1 GPU, through bpp_prove_batch with host buffers)",
                     "value": per * PL / (ms * 1e-3), "unit": "proofs/s", "batch": per * PL, "concurrent_calls": PL, "ms_per_batch": ms,
                     "path": "fixed-base window tables (k_fb.cu), no generator folding",
@@ -409,7 +409,11 @@ def run_b200(args, rank, local_rank, world):
         n_chunks = len(cases)
         entries = n_chunks * (2 * BIT_LENGTH + EXT + 1) + args.proofs * (3 + 2 * 6 + 1)
         per_launch = {k: v / n_seq for k, v in phase_acc.items()}
-        peak_ops, _ = eng.microbench(2, 2000)              # IMAD.WIDE (32x32+64 -> 64) issue rate, measured now on this GPU
+        # int32-multiply ceiling, measured now on this GPU: every 32x32->64 product needs one high-half multiply (IMAD.HI, the slow half:
+        # 8.6 T/s on this pool's B200s); the low halves issue on the other FMA sub-pipe (IMAD.lo alone: 18.6 T/s).  A single IMAD.WIDE
+        # per product is slower (6.1 T/s), which is why arith.cuh multiplies with mad.lo.cc / madc.hi.cc pairs.
+        peak_ops, _ = eng.microbench(1, 2000)
+        wide_ops, _ = eng.microbench(2, 2000)
         c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
         work = {"decompress": n_pts * MUL32_DECODE,
                 "msm_bucket": entries * W * MUL32_MADD,
@@ -440,11 +444,12 @@ def run_b200(args, rank, local_rank, world):
         dom = per_kernel[dominant]
         step_mul32 = sum(work[k] for k in work if k in per_kernel)
         step_ms = dev_ms_max / args.steps
-        roof = {"bound": "int32-multiply issue rate (IMAD.WIDE); the path is modular big-integer arithmetic, neither HBM- nor tensor-bound "
+        roof = {"bound": "int32-multiply issue rate (IMAD.HI, one per 32x32->64 product); the path is modular big-integer arithmetic, neither HBM- nor tensor-bound "
                          "(DRAM traffic per step: a few MB, profiles/r01_ncu_summary.md)",
                 "kernel": "k_" + dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
-                "peak_source": "bpp_microbench (IMAD.WIDE issue rate; LOP3+IADD3 for the Keccak kernel) measured in this run; "
-                               "MEASURED_PEAKS.json has no integer figure",
+                "peak_source": "bpp_microbench, measured in this run: IMAD.HI issue rate (one per 32x32->64 product; the IMAD.lo half issues on the "
+                               "other FMA sub-pipe); LOP3+IADD3 rate for the Keccak kernel.  MEASURED_PEAKS.json has no integer figure",
+                "imad_wide_tops": wide_ops / 1e12,
                 "algorithmic_work_per_launch": work[dominant],
                 "kernel_ms": dom["ms"],
                 "whole_step": {"mul32_per_step": step_mul32, "ms_per_step_lanes_overlapped": step_ms,
@@ -454,7 +459,8 @@ def run_b200(args, rank, local_rank, world):
                 "longest_kernel_one_batch_alone": max(per_launch, key=per_launch.get),
                 "per_kernel": per_kernel,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` captures (profiles/r01_ncu_summary.md)
-                "traffic": {"replay": 964352, "msm_combine": 34304, "decompress": 588288, "vprep_proof": 547328, "msm_bucket": 3670784}.get(dominant),
+                "traffic": {"replay": 961024, "msm_combine": 34304, "decompress": 588032, "vprep_proof": 519936, "msm_bucket": 3682560,
+                            "msm_reduce": 3833856}.get(dominant),
                 "traffic_unit": "bytes per launch (ncu, round 1)",
                 "note": "one 1024-proof batch alone is a chain of latency-bound kernels (2-30 % occupancy each); the lanes overlap "
                         "independent batches, which is what `value` measures; per_kernel holds the one-batch-alone durations"}

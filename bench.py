@@ -278,8 +278,9 @@ def run_b200(args, rank, local_rank, world):
     S = max(1, min(args.lanes, args.steps))
     cores = os.cpu_count() or 1
     # S independent lanes (bpp_ctx + host thread each) on this GPU; the host cores are shared by the ranks of the node
-    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=max(1, cores // (S * world)),
-                            blocking_waits=S > 1 and S * world >= cores)
+    htl = args.host_threads_per_lane or max(1, cores // (S * world))
+    blocking = (S > 1 and S * world >= cores) if args.blocking_waits < 0 else bool(args.blocking_waits)
+    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=blocking)
     eng, params = pool.lanes[0]
     params_o, cases = make_workload(args.proofs, seed=8675309 + 1000 * rank)
 
@@ -499,7 +500,7 @@ def run_b200(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
             "config": cfg,
             "e2e": {"value": world * args.proofs * args.steps / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": S, "host_threads_per_lane": max(1, cores // (S * world)),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": S, "host_threads_per_lane": htl, "blocking_waits": blocking,
                     "one_call_at_a_time": {"value": world * args.proofs * n_seq / e2e_seq_s_max, "ms_per_call": 1e3 * e2e_seq_s_max / n_seq,
                                            "host_ms_per_call": {k: round(v, 4) for k, v in host_acc.items()}}},
             "one_batch_at_a_time": {"value": world * args.proofs * n_seq / (seq_ms_max * 1e-3), "ms_per_step": seq_ms_max / n_seq, "steps": n_seq,
@@ -521,6 +522,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=16, help="independent verification lanes (bpp_ctx + host thread) per GPU")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--host-threads-per-lane", type=int, default=0, help="0 = host cores / (lanes * ranks)")
+    ap.add_argument("--blocking-waits", type=int, default=-1, help="-1 = when lanes * ranks >= host cores")
     ap.add_argument("--proofs", type=int, default=1024, help="proofs per GPU per step")
     ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput on rank 0 (secondary metrics)")
     ap.add_argument("--prove-batch", type=int, default=1024)

@@ -64,10 +64,13 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if self.index == "off":
+            return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            sel = [] if self.index is None else ["-i", str(self.index)]          # None: every GPU of the node from ONE process
+            self.proc = subprocess.Popen(["nvidia-smi"] + sel + ["--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,6 +82,8 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.index == "off":
+            return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -320,7 +325,9 @@ def run_b200(args, rank, local_rank, world):
         assert rc == 0 and all(vb.pk.status[c] == 0 for c in range(len(cases))), (rc, list(vb.pk.status))
 
     pool.run(dev_step, S * args.warmup)
-    sampler = ClockSampler(local_rank)
+    # one nvidia-smi process per NODE (rank 0, all GPUs): eight of them polling at once stall the driver's submission path (measured:
+    # the 8-GPU device-resident arm dropped to 0.56 M proofs/s per GPU with one sampler per rank)
+    sampler = ClockSampler((local_rank if world == 1 else None) if rank == 0 else "off")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
@@ -498,7 +505,7 @@ def run_b200(args, rank, local_rank, world):
             "metric": METRIC, "value": world * args.proofs * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
-            "config": cfg,
+            "config": cfg, "host_cores": cores,
             "e2e": {"value": world * args.proofs * args.steps / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": S, "host_threads_per_lane": htl, "blocking_waits": blocking,
                     "one_call_at_a_time": {"value": world * args.proofs * n_seq / e2e_seq_s_max, "ms_per_call": 1e3 * e2e_seq_s_max / n_seq,

@@ -698,7 +698,9 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[1], st));
         if (dev_replay) {       // the host hashes the weight transcripts while the device runs section B
             BPP_CUDA(ctx, cudaEventSynchronize(ctx->throughput_mode ? ctx->ev_mid_blocking : ctx->ev_mid));
+            auto tw = std::chrono::steady_clock::now();
             compute_weights(vb);
+            ctx->host_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
         }
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[2], st));
         ctx->launches += vg->kernels[0] + vg->kernels[1] + vg->kernels[2];

@@ -79,9 +79,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows=()):
+        """windows: (t0, t1) perf_counter intervals of the timed regions; samples inside them are preferred, else every sample taken
+        while the sampler ran (it runs from before the warm-up to after the last timed step, i.e. under load throughout)"""
         if self.index == "off":
             return None
         if not self.proc:
@@ -94,7 +96,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if any(a <= t <= b + 0.25 for a, b in windows)]
+        for r in (inside or [r for _, r in self.rows]):
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -103,7 +106,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_regions": len(inside)}
 
 
 def run_reference(args, rank, world):
@@ -324,13 +327,13 @@ def run_b200(args, rank, local_rank, world):
         rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
         assert rc == 0 and all(vb.pk.status[c] == 0 for c in range(len(cases))), (rc, list(vb.pk.status))
 
-    pool.run(dev_step, S * args.warmup)
     # one nvidia-smi process per NODE (rank 0, all GPUs): eight of them polling at once stall the driver's submission path (measured:
     # the 8-GPU device-resident arm dropped to 0.56 M proofs/s per GPU with one sampler per rank)
     sampler = ClockSampler((local_rank if world == 1 else None) if rank == 0 else "off")
+    sampler.start()
+    pool.run(dev_step, S * args.warmup)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
     launches0 = pool.launch_count()
     t_wall0 = time.perf_counter()
     ev0.record()                       # the device is idle here (barrier above): ev0 precedes every kernel of the timed steps
@@ -342,7 +345,7 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = pool.launch_count() - launches0
-    clocks = sampler.stop()
+    win_dev = (t_wall0, t_wall0 + t_wall)
 
     # ---------------- end-to-end arm (e2e): the C-ABI call with HOST buffers, K calls over S lanes
     host_acc = {}
@@ -361,6 +364,7 @@ def run_b200(args, rank, local_rank, world):
     pool.run(e2e_step, args.steps)                       # synchronous calls: each returns after the D2H of its verdicts
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop([win_dev, (t0, t0 + e2e_s)])
     barrier()
     # ---------------- one batch at a time on one lane (latency; the per-kernel figures of the roofline come from here)
     vb = vbs[0]

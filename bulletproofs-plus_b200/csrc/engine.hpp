@@ -53,6 +53,7 @@ struct bpp_ctx {
     cudaEvent_t ev_mid_blocking = nullptr;
     cudaEvent_t ev_done = nullptr;      // cudaEventBlockingSync: the host thread sleeps instead of spinning (throughput mode)
     bool throughput_mode = false;       // blocking waits instead of spinning: see bpp_ctx_set_throughput_mode
+    bool scalar_weights = false;        // test hook (BPP_SCALAR_WEIGHTS=1): one weight transcript at a time instead of four in lock-step
     bool device_weights = false;        // whole pass as ONE graph with the verifier-weight transcripts on the device (k_weights)
     bool device_replay = true;          // loop 1 (transcript replay) on the device (k_replay.cu) or on host threads
     int replay_kernel = 0;              // 0 = by batch size, 1 = one thread per proof, 2 = one warp per proof

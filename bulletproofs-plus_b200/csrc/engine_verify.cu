@@ -159,25 +159,181 @@ void vgraph_cache_free(bpp_ctx *ctx) {
 }
 }
 
-// Sequential part of loop 1 + the weight draw of loop 2 for every chunk (parallel over chunks): the verifier-weight
-// transcript (range_proof.rs:811, :849, :853) and random_not_zero per proof (:894).  Needs wbytes / flags of all proofs.
+// ------------------------------------------------------------------------------------------------ verifier weights (host)
+// Four STROBE-128 sponges advancing in lock-step (host_keccak4.cpp permutes the four states with one vectorised Keccak-f): the
+// weight transcripts of chunks that hold the same number of proofs perform the same operations at the same sponge positions,
+// only the absorbed bytes differ.  Mirrors Strobe128 / Merlin / MerlinRng of hash.cuh operation by operation.
+extern "C" void bpp_keccak_f1600_x4(uint64_t *st);
+extern "C" void bpp_host_sc_from_wide64(const uint8_t in64[64], uint8_t out32[32]);      // host_keccak4.cpp: 64-bit-limb wide reduction
+namespace {
+struct Strobe4 {
+    alignas(32) uint64_t st[100];          // lane k of state j at st[4 * k + j]
+    uint8_t pos = 0, pos_begin = 0, cur_flags = 0;
+    static constexpr int RATE = Strobe128::RATE;
+    void load_all(const uint8_t *b) {      // the same 203-byte state into all four
+        for (int k = 0; k < 25; k++) {
+            uint64_t x = 0;
+            for (int j = 7; j >= 0; j--) x = (x << 8) | b[8 * k + j];
+            for (int j = 0; j < 4; j++) st[4 * k + j] = x;
+        }
+        pos = b[200]; pos_begin = b[201]; cur_flags = b[202];
+    }
+    void xor_all(int p, uint8_t v) {
+        const uint64_t x = (uint64_t)v << (8 * (p & 7));
+        uint64_t *l = st + 4 * (p >> 3);
+        l[0] ^= x; l[1] ^= x; l[2] ^= x; l[3] ^= x;
+    }
+    void run_f() {
+        xor_all(pos, pos_begin); xor_all(pos + 1, 0x04); xor_all(RATE + 1, 0x80);
+        bpp_keccak_f1600_x4(st);
+        pos = 0; pos_begin = 0;
+    }
+    void absorb_same(const uint8_t *d, size_t len) {
+        for (size_t i = 0; i < len; i++) { xor_all(pos, d[i]); if (++pos == RATE) run_f(); }
+    }
+    void absorb4(const uint8_t *const d[4], size_t len) {
+        for (size_t i = 0; i < len; i++) {
+            const int sh = 8 * (pos & 7);
+            uint64_t *l = st + 4 * (pos >> 3);
+            for (int j = 0; j < 4; j++) l[j] ^= (uint64_t)d[j][i] << sh;
+            if (++pos == RATE) run_f();
+        }
+    }
+    void overwrite_same(const uint8_t *d, size_t len) {
+        for (size_t i = 0; i < len; i++) {
+            const int sh = 8 * (pos & 7);
+            uint64_t *l = st + 4 * (pos >> 3);
+            for (int j = 0; j < 4; j++) l[j] = (l[j] & ~(0xffULL << sh)) | ((uint64_t)d[i] << sh);
+            if (++pos == RATE) run_f();
+        }
+    }
+    void squeeze4(uint8_t *const d[4], size_t len) {
+        for (size_t i = 0; i < len; i++) {
+            const int sh = 8 * (pos & 7);
+            uint64_t *l = st + 4 * (pos >> 3);
+            for (int j = 0; j < 4; j++) { d[j][i] = (uint8_t)(l[j] >> sh); l[j] &= ~(0xffULL << sh); }
+            if (++pos == RATE) run_f();
+        }
+    }
+    void begin_op(uint8_t flags, bool more) {
+        if (more) return;
+        const uint8_t hdr[2] = {pos_begin, flags};
+        pos_begin = (uint8_t)(pos + 1);
+        cur_flags = flags;
+        absorb_same(hdr, 2);
+        if ((flags & (Strobe128::FC | Strobe128::FK)) && pos != 0) run_f();
+    }
+    void meta_ad_same(const uint8_t *d, size_t len, bool more) { begin_op(Strobe128::FM | Strobe128::FA, more); absorb_same(d, len); }
+    void ad4(const uint8_t *const d[4], size_t len) { begin_op(Strobe128::FA, false); absorb4(d, len); }
+    void key_same(const uint8_t *d, size_t len) { begin_op(Strobe128::FA | Strobe128::FC, false); overwrite_same(d, len); }
+    void prf4(uint8_t *const d[4], size_t len) { begin_op(Strobe128::FI | Strobe128::FA | Strobe128::FC, false); squeeze4(d, len); }
+};
+const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> &weight_transcript_init() {      // Transcript::new("Bulletproofs+ verifier weights") (:811)
+    static const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> wt0 = [] {
+        std::array<uint8_t, BPP_TRANSCRIPT_BYTES> st;
+        Merlin wt;
+        wt.init(LBL("Bulletproofs+ verifier weights"));
+        wt.s.store(st.data());
+        return st;
+    }();
+    return wt0;
+}
+} // namespace
+
+// Sequential part of loop 1 + the weight draw of loop 2 for every chunk: the verifier-weight transcript (range_proof.rs:811,
+// :849, :853) and random_not_zero per proof (:894).  Needs wbytes / flags of all proofs.  Chunks are independent: one at a time
+// through the scalar sponge, or four chunks of equal length at a time through Strobe4.
+// wb: len x 32 bytes (what every proof of the chunk feeds into the transcript, in proof order); out: len x 32 (canonical weights)
+static void weights_scalar(const uint8_t *wb, size_t len, uint8_t *out) {
+    Merlin wt;
+    wt.s.load(weight_transcript_init().data());
+    for (size_t k = 0; k < len; k++) wt.append_message(LBL("proof"), wb + 32 * k, 32);   // :849
+    MerlinRng wr;
+    const uint8_t zeros[32] = {0};
+    wr.build(wt, nullptr, 0, false, zeros);                                           // :853
+    for (size_t k = 0; k < len; k++) {
+        uint8_t wide[64], *wgt = out + 32 * k;
+        do { wr.fill(wide, 64); bpp_host_sc_from_wide64(wide, wgt); } while (is_zero32(wgt));   // :894 random_not_zero
+    }
+}
+// four chunks with the same number of proofs (pointers may repeat: padding of an incomplete group)
+static void weights_x4(const uint8_t *const wb[4], size_t len, uint8_t *const out[4]) {
+    Strobe4 s;
+    s.load_all(weight_transcript_init().data());
+    const uint8_t l32[4] = {32, 0, 0, 0}, l64[4] = {64, 0, 0, 0};
+    for (size_t k = 0; k < len; k++) {                                                // append_message("proof", wbytes, 32)
+        const uint8_t *d[4] = {wb[0] + 32 * k, wb[1] + 32 * k, wb[2] + 32 * k, wb[3] + 32 * k};
+        s.meta_ad_same(LBL("proof"), false);
+        s.meta_ad_same(l32, 4, true);
+        s.ad4(d, 32);
+    }
+    const uint8_t zeros[32] = {0};
+    s.meta_ad_same(LBL("rng"), false);                                                // build_rng().finalize(NullRng)
+    s.key_same(zeros, 32);
+    bool redo = false;
+    for (size_t k = 0; k < len; k++) {                                                // fill_bytes(64) -> from_bytes_mod_order_wide
+        uint8_t wide[4][64];
+        uint8_t *d[4] = {wide[0], wide[1], wide[2], wide[3]};
+        s.meta_ad_same(l64, 4, false);
+        s.prf4(d, 64);
+        for (int j = 0; j < 4; j++) {
+            bpp_host_sc_from_wide64(wide[j], out[j] + 32 * k);
+            if (is_zero32(out[j] + 32 * k)) redo = true;      // random_not_zero would draw again (probability 2^-252): leave lock-step
+        }
+    }
+    if (redo)
+        for (int j = 0; j < 4; j++) weights_scalar(wb[j], len, out[j]);
+}
+extern "C" {
+// test hook (host only): verifier weights of n_chunks (1..4) chunks of `len` proofs each, wbytes / weights chunk-major;
+// lockstep = 0: one transcript at a time, 1: all of them through the four-way sponge
+int32_t bpp_host_verifier_weights(const uint8_t *wbytes32, size_t len, size_t n_chunks, int32_t lockstep, uint8_t *weights32) {
+    if (!wbytes32 || !weights32 || n_chunks < 1 || n_chunks > 4) return BPP_INVALID_ARGUMENT;
+    if (!lockstep) {
+        for (size_t c = 0; c < n_chunks; c++) weights_scalar(wbytes32 + 32 * len * c, len, weights32 + 32 * len * c);
+        return BPP_OK;
+    }
+    const uint8_t *wb[4];
+    uint8_t *out[4];
+    for (size_t j = 0; j < 4; j++) { size_t c = j < n_chunks ? j : n_chunks - 1; wb[j] = wbytes32 + 32 * len * c; out[j] = weights32 + 32 * len * c; }
+    weights_x4(wb, len, out);
+    return BPP_OK;
+}
+}
 static void compute_weights(bpp_vbatch *vb) {
     bpp_ctx *ctx = vb->g->ctx;
-    uint8_t *wts = vb->w->h_weights.as<uint8_t>();
-    ctx->workers().run(vb->n_chunks, 1, [&](size_t c) {
+    // chunks whose weights are needed, grouped by length
+    struct Task { size_t c[4]; int n; };
+    std::vector<Task> tasks;
+    std::vector<std::pair<size_t, size_t>> todo;       // (length, chunk)
+    for (size_t c = 0; c < vb->n_chunks; c++) {
         const HChunk &hc = vb->hc[c];
-        if (hc.pre_rc) return;
-        for (size_t i = hc.lo; i < hc.hi; i++)
-            if (vb->flag(i) & 1) return;                                                  // loop 1 failed: the call ends there
-        Merlin wt;
-        wt.init(LBL("Bulletproofs+ verifier weights"));                                   // :811
-        for (size_t i = hc.lo; i < hc.hi; i++) wt.append_message(LBL("proof"), vb->wbytes(i), 32);   // :849
-        MerlinRng wr;
-        const uint8_t zeros[32] = {0};
-        wr.build(wt, nullptr, 0, false, zeros);                                           // :853
-        for (size_t i = hc.lo; i < hc.hi; i++) {
-            uint8_t wide[64], *wgt = wts + 32 * i;
-            do { wr.fill(wide, 64); host_sc_from_wide(wide, wgt); } while (is_zero32(wgt));   // :894 random_not_zero
+        if (hc.pre_rc) continue;
+        bool failed = false;
+        for (size_t i = hc.lo; i < hc.hi && !failed; i++) failed = (vb->flag(i) & 1) != 0;      // loop 1 failed: the call ends there
+        if (!failed) todo.emplace_back(hc.hi - hc.lo, c);
+    }
+    std::sort(todo.begin(), todo.end());
+    for (size_t i = 0; i < todo.size();) {
+        size_t j = i;
+        while (j < todo.size() && todo[j].first == todo[i].first && j - i < 4) j++;
+        Task t;
+        t.n = (int)(j - i);
+        for (int k = 0; k < 4; k++) t.c[k] = todo[i + (size_t)std::min<int>(k, t.n - 1)].second;
+        tasks.push_back(t);
+        i = j;
+    }
+    ctx->workers().run(tasks.size(), 1, [&](size_t ti) {
+        const Task &t = tasks[ti];
+        uint8_t *wts = vb->w->h_weights.as<uint8_t>();
+        const size_t len = vb->hc[t.c[0]].hi - vb->hc[t.c[0]].lo;
+        if (t.n >= 2 && !ctx->scalar_weights) {       // 2 or 3 chunks: padded lanes still beat 2-3 scalar passes
+            const uint8_t *wb[4];
+            uint8_t *out[4];
+            for (int k = 0; k < 4; k++) { wb[k] = vb->wbytes(vb->hc[t.c[k]].lo); out[k] = wts + 32 * vb->hc[t.c[k]].lo; }
+            weights_x4(wb, len, out);
+        } else {
+            for (int k = 0; k < t.n; k++) weights_scalar(vb->wbytes(vb->hc[t.c[k]].lo), len, wts + 32 * vb->hc[t.c[k]].lo);
         }
     });
 }
@@ -410,16 +566,7 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     memcpy(hb + vb->o_hg, g->h(), 32);
     memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
     if (vb->device_replay && a->n_proofs) memcpy(hb + vb->o_tstate, a->transcripts, BPP_TRANSCRIPT_BYTES * a->n_proofs);
-    {   // Transcript::new("Bulletproofs+ verifier weights") (:811), the starting state of k_weights
-        static const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> wt0 = [] {
-            std::array<uint8_t, BPP_TRANSCRIPT_BYTES> st;
-            Merlin wt;
-            wt.init(LBL("Bulletproofs+ verifier weights"));
-            wt.s.store(st.data());
-            return st;
-        }();
-        memcpy(hb + vb->o_wtinit, wt0.data(), BPP_TRANSCRIPT_BYTES);
-    }
+    memcpy(hb + vb->o_wtinit, weight_transcript_init().data(), BPP_TRANSCRIPT_BYTES);      // starting state of k_weights
     memset(vb->mid(), 0, vb->mid_bytes);
     memset(w->h_weights.p, 0, 32 * np1);
     for (size_t c = 0; c < a->n_chunks; c++) {

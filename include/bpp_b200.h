@@ -98,6 +98,11 @@ int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);
  * replace CompressedRistretto::decompress / RistrettoPoint::compress / from_uniform_bytes as issued from
  * range_proof.rs:859-866,1067-1109 (decompress), :289,:348,:499-504,:587,:598-605 and range_statement.rs:62-65
  * (compress), ristretto.rs:48-52 <- generators_chain.rs:44-49 (one-way map). */
+/* host only: Scalar::from_bytes_mod_order_wide on 64-bit limbs (the verifier-weight path); checked against bpp_scalar_from_wide */
+void bpp_host_sc_from_wide64(const uint8_t in64[64], uint8_t out32[32]);
+/* test hook, host only: the verifier weights (range_proof.rs:811-853, :894) of n_chunks <= 4 chunks of `len` proofs each from the 32
+ * bytes every proof feeds into the weight transcript; lockstep = 1 runs the chunks through the four-way vectorised sponge */
+int32_t bpp_host_verifier_weights(const uint8_t *wbytes32, size_t len, size_t n_chunks, int32_t lockstep, uint8_t *weights32);
 /* Host-side sum of n <= 64 points (32-byte encodings): the last step of a multi-GPU MSM, each GPU having reduced its shard to one
  * partial result.  BPP_INVALID_ARGUMENT if an encoding does not decode. */
 int32_t bpp_points_sum_host(size_t n, const uint8_t *in32, uint8_t out32[32]);

@@ -110,6 +110,7 @@ void orc_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen);
 void orc_blake2b_nonce(const uint8_t seed32[32], const char *label, int have_j, uint32_t j, int have_k, uint32_t k,
                        uint8_t out32[32]);
 void orc_keccak_f1600(uint64_t st[25]);
+void orc_verifier_weights(const uint8_t *wbytes32, size_t n, uint8_t *weights32);   /* range_proof.rs:811-853, :894 on its own */
 
 /* CPU baseline: verify `n_chunks` independent batches (each <= 256 proofs, laid out contiguously with
  * chunk_offsets[n_chunks+1]) on `threads` pthreads; per-chunk result codes in out_codes. Returns seconds. */

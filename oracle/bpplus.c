@@ -911,3 +911,21 @@ int orc_fe_sqrt_ratio_i(const uint8_t u[32], const uint8_t v[32], uint8_t out[32
 void orc_sha3_512(const uint8_t *in, size_t len, uint8_t out[64]) { sha3_512(out, in, len); }
 void orc_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen) { keccak_sponge s; shake256_init(&s); shake256_absorb(&s, in, len); shake256_finalize(&s); shake256_squeeze(&s, out, outlen); }
 void orc_keccak_f1600(uint64_t st[25]) { keccak_f1600(st); }
+/* The verifier-weight transcript of one verify_batch call on its own (range_proof.rs:811, :849, :853, :894): wbytes32 = the 32 rng
+ * bytes each proof contributes, in proof order; weights32 = the batch weight drawn for each proof.  Same statements as orc_verify. */
+void orc_verifier_weights(const uint8_t *wbytes32, size_t n, uint8_t *weights32) {
+    merlin_transcript weight_t;
+    merlin_init(&weight_t, (const uint8_t *)"Bulletproofs+ verifier weights", 30);
+    null_rng nrng;
+    null_rng_init(&nrng);
+    for (size_t i = 0; i < n; i++) merlin_append_message(&weight_t, "proof", wbytes32 + 32 * i, 32);
+    merlin_rng wrng;
+    merlin_build_rng(&wrng, &weight_t, NULL, 0, 0, &nrng.base);
+    trng_adapter wad;
+    wad.base.fill = trng_fill; wad.m = &wrng;
+    for (size_t i = 0; i < n; i++) {
+        sc w;
+        random_not_zero(&w, &wad.base);
+        sc_tobytes(weights32 + 32 * i, &w);
+    }
+}

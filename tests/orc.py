@@ -121,6 +121,8 @@ def lib():
     l.orc_shake256.argtypes = [u8p, sz, u8p, sz]
     l.orc_blake2b_nonce.argtypes = [u8p, u8p, C.c_int, C.c_uint32, C.c_int, C.c_uint32, u8p]
     l.orc_keccak_f1600.argtypes = [C.POINTER(C.c_uint64)]
+    l.orc_verifier_weights.argtypes = [u8p, sz, u8p]
+    l.orc_verifier_weights.restype = None
     l.orc_verify_chunks_mt.argtypes = [u8p, C.POINTER(Statement), C.POINTER(Proof), C.POINTER(sz), sz, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     l.orc_verify_chunks_mt.restype = C.c_double
     _lib = l

@@ -131,3 +131,36 @@ def test_points_sum_host_matches_oracle():
             assert got == o.raw
     with pytest.raises(bpp.pkg.EngineError):
         bpp.pkg.points_sum_host(pts[0] + b"\xff" * 32)
+
+
+@pytest.mark.parametrize("shape", [(1, 5), (2, 7), (3, 100), (4, 256)])
+def test_host_verifier_weights_match_oracle(shape):
+    """the product's host-side verifier-weight transcripts (range_proof.rs:811-853, :894) -- one at a time and four in lock-step
+    through the vectorised four-way Keccak-f (host_keccak4.cpp) -- against the oracle's restatement of the same lines"""
+    n_chunks, length = shape
+    lib = bpp.ffi.lib()
+    wb = hashlib.shake_256(b"weights-%d-%d" % shape).digest(32 * length * n_chunks)
+    want = C.create_string_buffer(32 * length * n_chunks)
+    for c in range(n_chunks):
+        part = C.create_string_buffer(32 * length)
+        orc.lib().orc_verifier_weights(wb[32 * length * c: 32 * length * (c + 1)], length, part)
+        C.memmove(C.addressof(want) + 32 * length * c, part, 32 * length)
+    for lockstep in (0, 1):
+        got = C.create_string_buffer(32 * length * n_chunks)
+        assert lib.bpp_host_verifier_weights(wb, length, n_chunks, lockstep, got) == 0
+        assert got.raw == want.raw, lockstep
+
+
+def test_host_wide_reduction_64bit_limbs():
+    """bpp_host_sc_from_wide64 (64-bit-limb Montgomery reduction used for the weights) against python integers and the shared
+    32-bit-limb path"""
+    lib = bpp.ffi.lib()
+    L = orc.L
+    cases = [bytes(64), b"\xff" * 64, L.to_bytes(64, "little"), (L - 1).to_bytes(64, "little"), (L * L).to_bytes(64, "little"),
+             (2**256).to_bytes(64, "little"), (2**512 - 1).to_bytes(64, "little")]
+    cases += [hashlib.shake_256(b"wide-%d" % i).digest(64) for i in range(500)]
+    a, b = C.create_string_buffer(32), C.create_string_buffer(32)
+    for c in cases:
+        lib.bpp_host_sc_from_wide64(c, a)
+        lib.bpp_scalar_from_wide(c, b)
+        assert a.raw == b.raw == (int.from_bytes(c, "little") % L).to_bytes(32, "little")

@@ -529,7 +529,7 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--lanes", type=int, default=16, help="independent verification lanes (bpp_ctx + host thread) per GPU")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

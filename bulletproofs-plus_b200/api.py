@@ -491,27 +491,44 @@ class VerifierPool:
     def __len__(self):
         return len(self.lanes)
 
-    def run(self, fn, n_items):
-        """fn(lane_index, engine, params, item_index) for item_index in range(n_items); item i runs on lane i % S, every lane in
-        its own thread (the C calls release the GIL); returns the results in item order, re-raises the first exception"""
+    def _start_threads(self):
+        """one persistent host thread per lane (created on first use): a job is (fn, n_items); lane li takes items li, li + S, ..."""
+        import queue
         import threading
 
-        S = len(self.lanes)
-        out, errs = [None] * n_items, []
+        self._jobs = [queue.SimpleQueue() for _ in self.lanes]
+        self._done = queue.SimpleQueue()
 
-        def work(li):
+        def loop(li):
             eng, params = self.lanes[li]
-            try:
-                for i in range(li, n_items, S):
-                    out[i] = fn(li, eng, params, i)
-            except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
-                errs.append(e)
+            S = len(self.lanes)
+            while True:
+                job = self._jobs[li].get()
+                if job is None:
+                    return
+                fn, n_items, out = job
+                err = None
+                try:
+                    for i in range(li, n_items, S):
+                        out[i] = fn(li, eng, params, i)
+                except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
+                    err = e
+                self._done.put(err)
 
-        ths = [threading.Thread(target=work, args=(li,)) for li in range(min(S, n_items))]
-        for t in ths:
+        self._threads = [threading.Thread(target=loop, args=(li,), daemon=True) for li in range(len(self.lanes))]
+        for t in self._threads:
             t.start()
-        for t in ths:
-            t.join()
+
+    def run(self, fn, n_items):
+        """fn(lane_index, engine, params, item_index) for item_index in range(n_items); item i runs on lane i % S, every lane in
+        its own (persistent) thread -- the C calls release the GIL; returns the results in item order, re-raises the first exception"""
+        if not getattr(self, "_threads", None):
+            self._start_threads()
+        out = [None] * n_items
+        active = min(len(self.lanes), n_items)
+        for li in range(active):
+            self._jobs[li].put((fn, n_items, out))
+        errs = [e for e in (self._done.get() for _ in range(active)) if e is not None]
         if errs:
             raise errs[0]
         return out
@@ -535,6 +552,11 @@ class VerifierPool:
         return sum(eng.launch_count for eng, _ in self.lanes)
 
     def close(self):
+        for q in getattr(self, "_jobs", []):
+            q.put(None)
+        for t in getattr(self, "_threads", []):
+            t.join(timeout=5)
+        self._threads = []
         for eng, _ in self.lanes:
             eng.close()
         self.lanes = []

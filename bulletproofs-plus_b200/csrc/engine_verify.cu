@@ -633,7 +633,12 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     lap();   // [3] weight transcripts (host mode; in device mode they run inside bpp_vbatch_run)
     cudaStream_t st = ctx->stream;
     if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the pinned blob is reused by the next create on this ctx
+    // The upload is ordered before the kernels of bpp_vbatch_run on the same stream and the pinned blob belongs to this vbatch's
+    // workspace until bpp_vbatch_destroy (which drains the stream), so nothing needs the host to wait here; outside throughput mode
+    // it still does, so that upload errors surface in this call and host_ms[4] is the H2D time.  A spinning wait per call is what
+    // many lanes per host core cannot afford.
+    static const bool always_sync = getenv("BPP_CREATE_SYNC") != nullptr;
+    if (e == cudaSuccess && (!ctx->throughput_mode || always_sync)) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
     lap();   // [4] H2D
     ctx->io_bytes[0] = vb->blob_bytes; ctx->io_bytes[1] = 0;

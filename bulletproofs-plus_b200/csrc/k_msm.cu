@@ -59,6 +59,8 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     sh.n_entries = n_entries;
     sh.n_seg = n_seg ? n_seg : 1;
     int c = forced_c;
+    static const int env_c = getenv("BPP_MSM_C") ? atoi(getenv("BPP_MSM_C")) : 0;       // experiments only
+    if (c <= 0 && env_c > 0 && n_entries / sh.n_seg < 16384) c = env_c;
     if (c <= 0) {
         // Small segments (the verifier's 4226-entry chunks, the prover's L / R): cost in quad stages (one warp-wide field
         // multiplication each) per segment -- a bucket add is 2 stages, a bucket in the running sums 5 (add + re-cache +

@@ -230,6 +230,7 @@ def run_extras(eng, api, bpp, orc, args):
     ppool.close()
     # ---- raw MSM (BASELINE.json configs[4]), device-resident decoded points
     msm = {}
+    msm_peak, _ = eng.microbench(1, 2000)            # IMAD.HI issue rate (see the roofline object)
     for lg in args.msm_log2:
         nn = 1 << lg
         seed = hashlib.shake_256(b"msm-points").digest(64)
@@ -243,12 +244,22 @@ def run_extras(eng, api, bpp, orc, args):
             sc[i] &= 0x0F                                                           # < 2^252 < l: canonical
         plan.set_scalars(bytes(sc))
         plan.run(True)
+        eng.phase_timing(True)                       # per-phase CUDA events of one run: sort / bucket sums / window reduction / Horner
+        plan.run(True)
+        ph = eng.phase_ms()
+        eng.phase_timing(False)
         reps = 5 if lg <= 20 else 2
         eng.timer_start()
         for _ in range(reps):
             plan.run(False)
         t = eng.timer_stop() / reps
-        msm["2^%d" % lg] = {"mpoints_per_s": nn / t / 1e3, "ms": t, "window_bits": plan.window_bits}
+        W = (252 + plan.window_bits - 1) // plan.window_bits
+        adds_mul32 = nn * W * MUL32_MADD              # bucket additions only (the algorithmic work of SURVEY.md 8d minus the reduction)
+        msm["2^%d" % lg] = {"mpoints_per_s": nn / t / 1e3, "ms": t, "window_bits": plan.window_bits, "windows": W,
+                            "achieved_tmul32_per_s": adds_mul32 / (t * 1e-3) / 1e12, "frac_of_int32_mul_peak": adds_mul32 / (t * 1e-3) / msm_peak,
+                            "bucket_kernel": {"ms": ph["msm_bucket"], "achieved_tmul32_per_s": adds_mul32 / (ph["msm_bucket"] * 1e-3) / 1e12,
+                                              "frac_of_int32_mul_peak": adds_mul32 / (ph["msm_bucket"] * 1e-3) / msm_peak},
+                            "phase_ms": {k: ph[k] for k in ("msm_sort", "msm_bucket", "msm_reduce", "msm_combine")}}
         plan.close()
     out["msm"] = msm
     return out
@@ -539,7 +550,7 @@ def main():
     ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput on rank 0 (secondary metrics)")
     ap.add_argument("--prove-batch", type=int, default=4096)
     ap.add_argument("--prove-lanes", type=int, default=4, help="concurrent bpp_prove_batch calls the proving batch is split into")
-    ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20])
+    ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20, 22])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()

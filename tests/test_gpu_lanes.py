@@ -102,3 +102,42 @@ def test_kernel_variants_match_oracle(env):
     e.update(env)
     r = subprocess.run([sys.executable, "-c", _CHILD % (ROOT, os.path.join(ROOT, "tests"))], env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "child ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_pool_prove_many_byte_identical_to_oracle():
+    """prove_many: jobs proved concurrently on several lanes give exactly the oracle prover's bytes and advanced transcripts"""
+    import hashlib
+
+    n, ext = 64, 1
+    op = orc.Params(n, 2, ext)
+    pool = api.VerifierPool(0, n, 2, ext, lanes=3)
+    try:
+        rng = orc.Rng("chacha", 909)
+        jobs, want = [], []
+        for j, (m, count) in enumerate([(1, 5), (2, 3), (1, 2), (1, 4)]):
+            _, params = pool.lanes[j % 3]
+            trs, sts, wits, rbs, exp = [], [], [], [], []
+            for k in range(count):
+                vals = [rng.next_u64() % (1 << 63) for _ in range(m)]
+                blinds = [[rng.random_not_zero()] for _ in range(m)]
+                commits = [op.commit(v, b) for v, b in zip(vals, blinds)]
+                mins = [v // 3 for v in vals]
+                seed = rng.random_not_zero() if m == 1 else None
+                stream = hashlib.shake_256(b"pm-%d-%d" % (j, k)).digest(api.RangeProof.rng_bytes_needed(params, m))
+                rc, pr, t_after = orc.prove(orc.transcript_new(workload.LABEL), orc.St(op, commits, mins, seed), orc.Wit(vals, blinds),
+                                            orc.Rng("buffer", data=stream))
+                assert rc == 0
+                exp.append((orc.proof_to_bytes(pr), t_after))
+                trs.append(api.Transcript(workload.LABEL))
+                sts.append(api.RangeStatement.init(params, commits, mins, seed))
+                wits.append(api.RangeWitness.init([api.CommitmentOpening(v, b) for v, b in zip(vals, blinds)]))
+                rbs.append(stream)
+            jobs.append((trs, sts, wits, rbs))
+            want.append(exp)
+        got = pool.prove_many(jobs)
+        for j, (res, exp) in enumerate(zip(got, want)):
+            for k, (r, (pb, ta)) in enumerate(zip(res, exp)):
+                assert not isinstance(r, Exception), (j, k, r)
+                assert r.to_bytes() == pb and jobs[j][0][k].state == ta, (j, k)
+    finally:
+        pool.close()

@@ -23,6 +23,11 @@ import sys
 import threading
 import time
 
+# Lanes are independent CUDA streams; by default the driver multiplexes all streams of a process onto 8 hardware work queues, which
+# falsely serialises kernels of different lanes (measured: 32 lanes 4.9 M -> 5.8 M proofs/s with 32 queues).  Must be set before the
+# CUDA context exists, i.e. before torch touches the device.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -541,7 +546,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=512)
-    ap.add_argument("--lanes", type=int, default=16, help="independent verification lanes (bpp_ctx + host thread) per GPU")
+    ap.add_argument("--lanes", type=int, default=32, help="independent verification lanes (bpp_ctx + host thread) per GPU")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--host-threads-per-lane", type=int, default=0, help="0 = host cores / (lanes * ranks)")

@@ -58,6 +58,9 @@ extern "C" {
 int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (!out) return BPP_INVALID_ARGUMENT;
     *out = nullptr;
+    // streams of different ctxs only run concurrently if they land on different hardware work queues; the driver's default is 8 per
+    // process.  Takes effect if this is the process's first CUDA call (a caller that initialises CUDA earlier sets it itself).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0 || device_ordinal < 0 || device_ordinal >= count) return BPP_ERR_CUDA;   // no CPU fallback

@@ -398,6 +398,65 @@ __global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uin
     }
 }
 
+// Throughput variant for many (segment, window) pairs of moderate size (the verifier: 4 x 28 windows of 256 buckets): one WARP per
+// window, one thread per L = B / 32 consecutive buckets, everything in whole-thread extended-coordinate arithmetic (about half the
+// instructions of the quad kernel above).  Lane t: S_t = sum of its buckets, R_t = sum_j (j + 1) * bucket[tL + j] (running sums);
+// window sum = sum_t R_t + L * sum_t t * S_t, and sum_t t * S_t = sum_{k >= 1} P_k with P_k = sum_{u >= k} S_u (suffix scan by
+// shuffles); every lane then folds T_t = R_t + L * P_t (log2 L doublings) and one shuffle tree adds the 32 T_t.
+struct gex { fe X, Y, Z, T; };
+static __device__ __forceinline__ void gex_add_cached(gex &p, const fe &ymx, const fe &ypx, const fe &z2, const fe &t2d) {
+    const fe A = fe_mul(fe_sub_l(p.Y, p.X), ymx), B = fe_mul(fe_add_l(p.Y, p.X), ypx), C = fe_mul(p.T, t2d), D = fe_mul(p.Z, z2);
+    const fe E = fe_sub_l(B, A), H = fe_add_l(B, A), F = fe_sub_l(D, C), G = fe_add_l(D, C);
+    p.X = fe_mul(E, F); p.Y = fe_mul(G, H); p.Z = fe_mul(F, G); p.T = fe_mul(E, H);
+}
+static __device__ __forceinline__ void gex_add(gex &p, const gex &q) {
+    gex_add_cached(p, fe_sub_l(q.Y, q.X), fe_add_l(q.Y, q.X), fe_add_l(q.Z, q.Z), fe_mul(q.T, fe_const_2d()));
+}
+static __device__ __forceinline__ void gex_dbl(gex &p) {
+    const fe XX = fe_sq(p.X), YY = fe_sq(p.Y), ZZ = fe_sq(p.Z), S = fe_sq(fe_add_l(p.X, p.Y));
+    const fe H = fe_add_l(YY, XX), G = fe_sub_l(YY, XX);
+    const fe E = fe_sub_ll(S, H), F = fe_sub_ll(fe_add_l(ZZ, ZZ), G);
+    p.X = fe_mul(E, F); p.Y = fe_mul(H, G); p.Z = fe_mul(G, F); p.T = fe_mul(E, H);
+}
+static __device__ __forceinline__ gex gex_identity() { gex r; r.X = fe_zero(); r.Y = fe_one(); r.Z = fe_one(); r.T = fe_zero(); return r; }
+// value of lane (lane + delta), or the identity beyond the warp
+static __device__ __forceinline__ gex gex_shfl_down(const gex &v, int delta, int lane) {
+    gex r;
+    r.X = shfl_down_fe(v.X, delta); r.Y = shfl_down_fe(v.Y, delta); r.Z = shfl_down_fe(v.Z, delta); r.T = shfl_down_fe(v.T, delta);
+    const bool in = lane + delta < 32;
+    r.X = fe_select(fe_zero(), r.X, in); r.Y = fe_select(fe_one(), r.Y, in); r.Z = fe_select(fe_one(), r.Z, in); r.T = fe_select(fe_zero(), r.T, in);
+    return r;
+}
+__global__ void __launch_bounds__(128) k_msm_reduce_warp(uint32_t n_win, uint32_t B, const cached *__restrict__ buckets, ge *__restrict__ windows) {
+    const uint32_t win = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (win >= n_win) return;                            // warp-uniform
+    const uint32_t L = B >> 5;
+    const cached *bk = buckets + (size_t)win * B + (size_t)lane * L;
+    gex S = gex_identity(), R = gex_identity();
+    for (int j = (int)L - 1; j >= 0; j--) {
+        gex_add_cached(S, ld_fe(&bk[j].ymx), ld_fe(&bk[j].ypx), ld_fe(&bk[j].z2), ld_fe(&bk[j].t2d));
+        gex_add(R, S);
+    }
+    // P = inclusive suffix sum of S over the lanes
+    gex P = S;
+    for (int d = 1; d < 32; d <<= 1) {
+        const gex o = gex_shfl_down(P, d, lane);
+        gex_add(P, o);
+    }
+    if (lane == 0) P = gex_identity();                   // sum_t t * S_t = sum_{k >= 1} P_k
+    for (uint32_t l = L; l > 1; l >>= 1) gex_dbl(P);      // L is a power of two
+    gex_add(R, P);                                        // T_t = R_t + L * P_t
+    for (int d = 16; d > 0; d >>= 1) {
+        const gex o = gex_shfl_down(R, d, lane);
+        gex_add(R, o);
+    }
+    if (lane == 0) {
+        ge *w = windows + win;
+        st_fe(&w->X, R.X); st_fe(&w->Y, R.Y); st_fe(&w->Z, R.Z); st_fe(&w->T, R.T);
+    }
+}
+
 // small bucket counts (B <= 64: the prover's many short MSMs): one quad per (segment, window) walks all B buckets itself, eight
 // (segment, window) pairs per warp -- the CTA-per-window kernel above would run one active quad per warp there
 __global__ void __launch_bounds__(128) k_msm_reduce_small(uint32_t n_win, uint32_t B, const cached *__restrict__ buckets, ge *__restrict__ windows) {
@@ -462,9 +521,16 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     else
         k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
+    static const int force_reduce = getenv("BPP_MSM_REDUCE") ? atoi(getenv("BPP_MSM_REDUCE")) : 0;      // 1 = CTA of quads, 2 = warp of threads (tests)
     if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         k_msm_reduce_small<<<(n_win + 31) / 32, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
+    } else if (force_reduce == 2 && sh.B >= 32) {
+        // one warp of whole threads per window: half the instructions of the quad kernel (verifier: 10.9 M -> 5 M per pass) but a longer
+        // chain (88 us against 63 us alone), and with 16 lanes in flight the throughput came out the same (4.5-4.6 M proofs/s either
+        // way): kept as a tested option (BPP_MSM_REDUCE=2), not the default
+        uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
+        k_msm_reduce_warp<<<(n_win + 3) / 4, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
     } else {
         uint32_t nq = sh.B >= 8 ? sh.B / 8 : 1;        // quads per (segment, window)
         if (nq > 256) nq = 256;

@@ -50,6 +50,9 @@ typedef struct bpp_vbatch bpp_vbatch;
 typedef struct bpp_msm_plan bpp_msm_plan;
 
 /* ---------------------------------------------------------------- context */
+/* Many ctxs per device (lanes): their streams only overlap if they map to different hardware work queues; bpp_ctx_create sets
+ * CUDA_DEVICE_MAX_CONNECTIONS=32 when it is unset, which takes effect if no CUDA context exists yet in the process (otherwise the
+ * caller sets it before initialising CUDA; the driver default is 8). */
 int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out);
 void bpp_ctx_destroy(bpp_ctx *ctx);
 const char *bpp_last_error(const bpp_ctx *ctx);      /* valid until the next call on ctx */

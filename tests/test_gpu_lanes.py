@@ -96,7 +96,8 @@ print("child ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"BPP_MSM_BUCKET": "1"}, {"BPP_MSM_BUCKET": "2"}, {"BPP_VPREP_DIRECT": "1"}, {"BPP_NO_GRAPHS": "1"}])
+@pytest.mark.parametrize("env", [{"BPP_MSM_BUCKET": "1"}, {"BPP_MSM_BUCKET": "2"}, {"BPP_MSM_REDUCE": "1"}, {"BPP_MSM_REDUCE": "2"},
+                                 {"BPP_VPREP_DIRECT": "1"}, {"BPP_NO_GRAPHS": "1"}, {"BPP_SCALAR_WEIGHTS": "1"}])
 def test_kernel_variants_match_oracle(env):
     e = dict(os.environ)
     e.update(env)

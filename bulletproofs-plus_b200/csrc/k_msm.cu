@@ -525,10 +525,10 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         k_msm_reduce_small<<<(n_win + 31) / 32, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
-    } else if (force_reduce == 2 && sh.B >= 32) {
-        // one warp of whole threads per window: half the instructions of the quad kernel (verifier: 10.9 M -> 5 M per pass) but a longer
-        // chain (88 us against 63 us alone), and with 16 lanes in flight the throughput came out the same (4.5-4.6 M proofs/s either
-        // way): kept as a tested option (BPP_MSM_REDUCE=2), not the default
+    } else if (force_reduce ? (force_reduce == 2 && sh.B >= 32) : (sh.B >= 32 && sh.B <= 512 && sh.n_seg * sh.W >= 64)) {
+        // enough windows to give every SM a warp: one warp of whole threads per window is half the instructions of the quad kernel
+        // (verifier: 10.9 M -> 5 M per pass) for a longer chain (88 us against 63 us alone).  Measured with 32 lanes in flight:
+        // 6.2 M against 5.9 M proofs/s; one batch alone: 958 k against 977 k proofs/s
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         k_msm_reduce_warp<<<(n_win + 3) / 4, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
     } else {

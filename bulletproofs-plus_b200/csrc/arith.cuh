@@ -97,6 +97,51 @@ __device__ __forceinline__ void mul256(uint32_t t[16], const uint32_t a[8], cons
     for (int i = 1; i < 14; i++) t[i + 1] = addc_cc(t[i + 1], odd[i]);
     t[15] = addc(t[15], 0);
 }
+// t[0..16) = a^2 with 36 multiplies: the 28 off-diagonal products a_i * a_j (i < j) once, doubled by a funnel shift, plus the 8
+// diagonal squares.  Row i (multiplier a_i, elements a_{i+1..7}, first column 2i + 1) is split like the rows of mul256 into its
+// elements at even and at odd distance: each half is one pure carry chain (low half of element k + 2 lands right after the high
+// half of element k).  Chains that start on an odd column accumulate into x[], chains that start on an even column into y[]; a
+// chain's carry-out goes into the limb after its end, which at that point holds nothing but earlier carry-outs (checked per row in
+// targets x[9], x[9], x[11], x[11], x[13], x[13], x[15] and y[8], y[10], y[10], y[12], y[12], y[14]).
+__device__ __forceinline__ void sq256(uint32_t t[16], const uint32_t a[8]) {
+    uint32_t x[16], y[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { x[i] = 0; y[i] = 0; }
+    // row 0: elements a1 a3 a5 a7 -> x[1..8];  a2 a4 a6 -> y[2..7]
+    cmad_n<8>(x + 1, a + 1, a[0]);  x[9] = addc(x[9], 0);
+    cmad_n<6>(y + 2, a + 2, a[0]);  y[8] = addc(y[8], 0);
+    // row 1: a2 a4 a6 -> x[3..8];  a3 a5 a7 -> y[4..9]
+    cmad_n<6>(x + 3, a + 2, a[1]);  x[9] = addc(x[9], 0);
+    cmad_n<6>(y + 4, a + 3, a[1]);  y[10] = addc(y[10], 0);
+    // row 2: a3 a5 a7 -> x[5..10];  a4 a6 -> y[6..9]
+    cmad_n<6>(x + 5, a + 3, a[2]);  x[11] = addc(x[11], 0);
+    cmad_n<4>(y + 6, a + 4, a[2]);  y[10] = addc(y[10], 0);
+    // row 3: a4 a6 -> x[7..10];  a5 a7 -> y[8..11]
+    cmad_n<4>(x + 7, a + 4, a[3]);  x[11] = addc(x[11], 0);
+    cmad_n<4>(y + 8, a + 5, a[3]);  y[12] = addc(y[12], 0);
+    // row 4: a5 a7 -> x[9..12];  a6 -> y[10..11]
+    cmad_n<4>(x + 9, a + 5, a[4]);  x[13] = addc(x[13], 0);
+    cmad_n<2>(y + 10, a + 6, a[4]); y[12] = addc(y[12], 0);
+    // row 5: a6 -> x[11..12];  a7 -> y[12..13]
+    cmad_n<2>(x + 11, a + 6, a[5]); x[13] = addc(x[13], 0);
+    cmad_n<2>(y + 12, a + 7, a[5]); y[14] = addc(y[14], 0);
+    // row 6: a7 -> x[13..14]
+    cmad_n<2>(x + 13, a + 7, a[6]); x[15] = addc(x[15], 0);
+    // u = x + y (columns 1..15)
+    x[1] = add_cc(x[1], y[1]);
+#pragma unroll
+    for (int i = 2; i < 15; i++) x[i] = addc_cc(x[i], y[i]);
+    x[15] = addc(x[15], y[15]);
+    // t = 2u + diagonal
+    uint32_t v[16];
+    v[0] = 0;
+#pragma unroll
+    for (int i = 1; i < 16; i++) v[i] = __funnelshift_l(x[i - 1], x[i], 1);
+    t[0] = add_cc(v[0], mul_lo(a[0], a[0]));
+    t[1] = addc_cc(v[1], mul_hi(a[0], a[0]));
+#pragma unroll
+    for (int i = 1; i < 8; i++) { t[2 * i] = addc_cc(v[2 * i], mul_lo(a[i], a[i])); t[2 * i + 1] = (i == 7) ? addc(v[15], mul_hi(a[7], a[7])) : addc_cc(v[2 * i + 1], mul_hi(a[i], a[i])); }
+}
 } // namespace ptx
 #endif
 
@@ -348,7 +393,11 @@ BPP_MULFN fe fe_mul(fe a, fe b) {
 
 BPP_MULFN fe fe_sq(fe a) {
     uint32_t t[16];
+#if BPP_PTX && !defined(BPP_PORTABLE_MUL)
+    ptx::sq256(t, a.v);
+#else
     sq256_any(t, a.v);
+#endif
     return fe_reduce512(t);
 }
 

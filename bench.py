@@ -487,8 +487,8 @@ def run_b200(args, rank, local_rank, world):
                 "longest_kernel_one_batch_alone": max(per_launch, key=per_launch.get),
                 "per_kernel": per_kernel,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` captures (profiles/r01_ncu_summary.md)
-                "traffic": {"replay": 961024, "msm_combine": 34304, "decompress": 588032, "vprep_proof": 519936, "msm_bucket": 3682560,
-                            "msm_reduce": 3833856}.get(dominant),
+                "traffic": {"replay": 961024, "msm_combine": 34304, "decompress": 588032, "vprep_proof": 519936, "msm_bucket": 3680000,
+                            "msm_reduce": 3780000, "vprep_vector": 917000}.get(dominant),
                 "traffic_unit": "bytes per launch (ncu, round 1)",
                 "note": "one 1024-proof batch alone is a chain of latency-bound kernels (2-30 % occupancy each); the lanes overlap "
                         "independent batches, which is what `value` measures; per_kernel holds the one-batch-alone durations"}

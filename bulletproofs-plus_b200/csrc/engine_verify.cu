@@ -406,11 +406,15 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
             else if (p.has_seed && m64 > 1) p.pre_rc = BPP_INVALID_ARGUMENT;
         }
         if (p.pre_rc) return;
-        if (p.has_seed) {
-            uint32_t w[8];
-            memcpy(w, a->seed_nonces32 + 32 * i, 32);
-            sc s; for (int k = 0; k < 8; k++) s.v[k] = w[k];
-            sc_tobytes(p.seed, sc_reduce256(s));
+        if (p.has_seed) {          // Scalar::from_bytes_mod_order; a seed that is already canonical (the usual case) needs no reduction
+            const uint8_t *sb = a->seed_nonces32 + 32 * i;
+            if (host_sc_is_canonical(sb)) memcpy(p.seed, sb, 32);
+            else {
+                uint32_t w[8];
+                memcpy(w, sb, 32);
+                sc s; for (int k = 0; k < 8; k++) s.v[k] = w[k];
+                sc_tobytes(p.seed, sc_reduce256(s));
+            }
         }
         uint64_t N = (uint64_t)p.m * (uint64_t)n;
         if (p.rounds >= 32 || (1ull << p.rounds) != N) p.loop2_rc = BPP_INVALID_LENGTH;  // :886-888

@@ -76,7 +76,7 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
         cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_mid_blocking, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream); delete ctx; return BPP_ERR_CUDA;
     }
     unsigned hc = std::thread::hardware_concurrency();
@@ -85,6 +85,7 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (const char *env = getenv("BPP_HOST_REPLAY")) ctx->device_replay = atoi(env) == 0;
     if (const char *env = getenv("BPP_NO_GRAPHS")) ctx->use_graphs = atoi(env) == 0;
     if (const char *env = getenv("BPP_SCALAR_WEIGHTS")) ctx->scalar_weights = atoi(env) != 0;
+    if (const char *env = getenv("BPP_NAP_US")) { long v = atol(env); if (v >= 1 && v <= 100000) ctx->nap_ns = v * 1000; }
     if (const char *env = getenv("BPP_THROUGHPUT_MODE")) { ctx->throughput_mode = atoi(env) != 0; ctx->device_weights = atoi(env) == 2; }
     *out = ctx;
     return BPP_OK;

@@ -18,6 +18,8 @@
 #include <array>
 #include <chrono>
 #include <cstring>
+#include <ctime>
+#include <cstdio>
 #include "engine.hpp"
 #include "hash.cuh"
 #include "replay.cuh"
@@ -650,6 +652,18 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     return BPP_OK;
 }
 
+// Wait for an event without spinning and without the driver's blocking-sync machinery: poll it between short sleeps.  Measured per
+// 1024-proof pass (one lane, scripts/e2e_cpu_cost.py): cudaEventBlockingSync waits cost the process ~0.24 ms of CPU in driver
+// threads on top of the calling thread's own work; a spin wait costs the whole pass (1 ms).
+static cudaError_t wait_sleeping(cudaEvent_t ev, long nap_ns) {
+    for (;;) {
+        cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) return e;
+        timespec ts = {0, nap_ns};
+        nanosleep(&ts, nullptr);
+    }
+}
+
 // kernel arguments of one pass
 struct VLaunch {
     VDims d;
@@ -835,6 +849,10 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     const bool dev_replay = L.dev_replay;
 
     ctx->clear_marks();
+    // debug aid (BPP_RUN_CPU_TRACE=1): CPU time of the calling thread per section of this function, printed to stderr
+    static const bool cpu_trace = getenv("BPP_RUN_CPU_TRACE") != nullptr;
+    auto cpu_us = []() { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    double tc[6] = {cpu_trace ? cpu_us() : 0, 0, 0, 0, 0, 0};
     const bool fused = ctx->device_weights && dev_replay && ctx->use_graphs && !ctx->phase_timing;
     if (fused) {
         cudaError_t ge = cudaSuccess;
@@ -849,15 +867,19 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
         if (!vg) return cuda_fail(ctx, ge, "verification graph capture");
         if (vg->ex[0]) {
             BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[0], st));
-            BPP_CUDA(ctx, cudaEventRecord(ctx->throughput_mode ? ctx->ev_mid_blocking : ctx->ev_mid, st));
+            BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
         }
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[1], st));
+        if (cpu_trace) tc[1] = cpu_us();
         if (dev_replay) {       // the host hashes the weight transcripts while the device runs section B
-            BPP_CUDA(ctx, cudaEventSynchronize(ctx->throughput_mode ? ctx->ev_mid_blocking : ctx->ev_mid));
+            if (ctx->throughput_mode) BPP_CUDA(ctx, wait_sleeping(ctx->ev_mid, ctx->nap_ns));
+            else BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_mid));
+            if (cpu_trace) tc[2] = cpu_us();
             auto tw = std::chrono::steady_clock::now();
             compute_weights(vb);
             ctx->host_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
         }
+        if (cpu_trace) tc[3] = cpu_us();
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[2], st));
         ctx->launches += vg->kernels[0] + vg->kernels[1] + vg->kernels[2];
         ctx->graph_launches += vg->ex[0] ? 3 : 2;
@@ -916,10 +938,11 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     }
     if (ctx->throughput_mode) {         // sleep until the pass is done: with many lanes per GPU spinning threads starve each other
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_done, st));
-        BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_done));
+        BPP_CUDA(ctx, wait_sleeping(ctx->ev_done, ctx->nap_ns));
     } else {
         BPP_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    if (cpu_trace) tc[4] = cpu_us();
     vb->ran = true;
     ctx->io_bytes[0] = vb->blob_bytes + (vb->any_msm && !fused ? 32 * n : 0);
     ctx->io_bytes[1] = (dev_replay ? vb->mid_bytes : 0) + vb->n_pts + (vb->any_msm ? vb->n_chunks : 0) + (vb->any_masks ? 32 * n * (size_t)ext : 0);
@@ -958,6 +981,11 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
                 else memset(masks32 + 32 * i * (size_t)ext, 0, 32 * (size_t)ext);
             }
         }
+    }
+    if (cpu_trace) {
+        tc[5] = cpu_us();
+        fprintf(stderr, "bpp_vbatch_run cpu us: graphs A+B %.1f | wait mid %.1f | weights %.1f | graph C %.1f(incl. launch) wait end %.1f | resolve %.1f\n",
+                tc[1] - tc[0], tc[2] - tc[1], tc[3] - tc[2], 0.0, tc[4] - tc[3], tc[5] - tc[4]);
     }
     return BPP_OK;
 }

@@ -79,8 +79,10 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
 int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable);
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx);
 /* throughput mode (default 0), for callers that keep several verification calls in flight from several ctxs:
- *   1 = the calling thread sleeps on blocking events instead of spinning while the device works (with many ctxs per GPU spinning
- *       threads starve each other and the host hashing);
+ *   1 = the calling thread sleeps between polls of its events (60 us naps, BPP_NAP_US) instead of spinning while the device works:
+ *       with many ctxs per GPU spinning threads starve each other and the host hashing.  (cudaEventBlockingSync waits were tried
+ *       first: they cost the process 0.24 ms of CPU in driver threads per pass and 0.4 ms of wake-up latency; sleeping polls cost
+ *       0.03 ms and 0.1 ms.);
  *   2 = additionally the verifier-weight transcripts (range_proof.rs:811-853, :894) run on the device (k_weights, one warp per
  *       chunk) and the whole pass is ONE graph launch with no host step in the middle.  Measured on B200 this is slower (a
  *       256-proof chunk is a chain of ~330 dependent Keccak-f permutations: 4.5 ms on one warp against ~0.2 ms on a host core),

@@ -75,7 +75,6 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
         cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_mid_blocking, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream); delete ctx; return BPP_ERR_CUDA;
     }
@@ -105,7 +104,7 @@ void bpp_ctx_destroy(bpp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream2);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_mid);
     cudaStreamSynchronize(ctx->stream3);
-    cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join2); cudaEventDestroy(ctx->ev_done); cudaEventDestroy(ctx->ev_mid_blocking);
+    cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join2); cudaEventDestroy(ctx->ev_done);
     cudaStreamDestroy(ctx->stream3);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);

@@ -50,10 +50,9 @@ struct bpp_ctx {
     cudaStream_t stream2 = nullptr;     // side stream: point decompression overlaps the scalar prep chain
     cudaStream_t stream3 = nullptr;     // side stream: device-side verifier-weight transcripts (throughput mode)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
-    cudaEvent_t ev_mid_blocking = nullptr;
-    cudaEvent_t ev_done = nullptr;      // cudaEventBlockingSync: the host thread sleeps instead of spinning (throughput mode)
+    cudaEvent_t ev_done = nullptr;      // end of a pass; polled between short sleeps in throughput mode
     long nap_ns = 60000;                // sleep between event polls in throughput mode (BPP_NAP_US)
-    bool throughput_mode = false;       // blocking waits instead of spinning: see bpp_ctx_set_throughput_mode
+    bool throughput_mode = false;       // sleeping polls instead of spinning: see bpp_ctx_set_throughput_mode
     bool scalar_weights = false;        // test hook (BPP_SCALAR_WEIGHTS=1): one weight transcript at a time instead of four in lock-step
     bool device_weights = false;        // whole pass as ONE graph with the verifier-weight transcripts on the device (k_weights)
     bool device_replay = true;          // loop 1 (transcript replay) on the device (k_replay.cu) or on host threads

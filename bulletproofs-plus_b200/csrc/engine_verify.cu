@@ -12,8 +12,10 @@
 // Loop 1 runs on the device by default (k_replay.cu); `bpp_ctx_set_replay_mode(ctx, 0)` keeps it on host threads, which is
 // the split BASELINE.json's north_star describes; both produce bit-identical results (tests run both).  The weight
 // transcript is inherently sequential (one Keccak-f per weight) and stays on the host in both modes, overlapped with the
-// weight-free part of the scalar prep.  Error precedence of the reference is reproduced when the per-chunk status is
-// resolved after the device returns.
+// weight-free part of the scalar prep (four chunks of equal length hash in lock-step through a vectorised four-way Keccak-f,
+// host_keccak4.cpp).  Error precedence of the reference is reproduced when the per-chunk status is resolved after the device
+// returns.  The pass is normally replayed as three captured CUDA graphs (see "CUDA graphs" below); independent calls overlap
+// when issued from several ctxs ("lanes", api.VerifierPool).
 #include <algorithm>
 #include <array>
 #include <chrono>

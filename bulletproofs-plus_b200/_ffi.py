@@ -108,6 +108,7 @@ def lib():
         "bpp_points_sum_host": (i32, [sz, cp, cp]),
         "bpp_host_verifier_weights": (i32, [cp, sz, sz, i32, cp]),
         "bpp_host_sc_from_wide64": (None, [cp, cp]),
+        "bpp_host_sc_mul64": (None, [cp, cp, cp]),
         "bpp_msm": (i32, [vp, sz, cp, cp, cp]),
         "bpp_msm_segmented": (i32, [vp, sz, vp, cp, cp, cp]),
         "bpp_msm_plan_create": (i32, [vp, sz, cp, i32, P(vp)]),

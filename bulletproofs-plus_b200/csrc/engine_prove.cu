@@ -8,11 +8,18 @@
 // per proof.  The caller supplies the bytes its external RNG would have delivered (32 per TranscriptRng rebuild,
 // log2(n*m) + 3 rebuilds), so a seeded RNG reproduces the reference's proof bytes.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
+#include <functional>
 #include "engine.hpp"
 #include "hash.cuh"
 
 using namespace bpp;
+
+// host scalar arithmetic on 64-bit limbs (host_keccak4.cpp); results are canonical, identical to the shared 32-bit-limb code
+extern "C" void bpp_host_sc_mul64(const uint8_t a32[32], const uint8_t b32[32], uint8_t out32[32]);
+extern "C" void bpp_host_sc_from_wide64(const uint8_t in64[64], uint8_t out32[32]);
 
 namespace {
 
@@ -23,10 +30,24 @@ inline void sc_store(uint8_t *b, const sc &a) { sc_tobytes(b, a); }
 inline sc sc_reduce_bytes(const uint8_t *b) { return sc_reduce256(sc_frombytes_raw(b)); }
 inline bool zero32(const uint8_t *p) { uint8_t r = 0; for (int i = 0; i < 32; i++) r |= p[i]; return r == 0; }
 
+inline sc hmul(const sc &a, const sc &b) {
+    sc r;
+    bpp_host_sc_mul64(reinterpret_cast<const uint8_t *>(a.v), reinterpret_cast<const uint8_t *>(b.v), reinterpret_cast<uint8_t *>(r.v));
+    return r;
+}
+inline sc hpow(sc base, uint64_t e) {          // square-and-multiply
+    sc r = sc_one();
+    while (e) {
+        if (e & 1) r = hmul(r, base);
+        base = hmul(base, base);
+        e >>= 1;
+    }
+    return r;
+}
 inline sc wide_to_sc(const uint8_t in[64]) {
-    uint32_t w[16];
-    memcpy(w, in, 64);
-    return sc_from_wide_words(w);
+    sc r;
+    bpp_host_sc_from_wide64(in, reinterpret_cast<uint8_t *>(r.v));
+    return r;
 }
 
 struct PProof {
@@ -136,6 +157,15 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     if (P0 * (uint64_t)N >= (1u << 28)) return fail(ctx, BPP_SIZE_OVERFLOW, "batch too large");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
+    // debug aid (BPP_PROVE_TRACE=1): wall time spent in the host stages (Fiat-Shamir, nonces, scalar bookkeeping) of this call
+    static const bool prove_trace = getenv("BPP_PROVE_TRACE") != nullptr;
+    double host_stage_ms = 0;
+    const auto t_call0 = std::chrono::steady_clock::now();
+    auto host_stage = [&](size_t n, size_t grain, const std::function<void(size_t)> &f) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ctx->workers().run(n, grain, f);
+        host_stage_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
 
     std::vector<PProof> pp(P0);
     // ---- :264-271 value range, :275-284 opening == commitment (device commit, compared as canonical encodings)
@@ -163,7 +193,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     // ---- RangeProofTranscript::new (:287-297), bit offsets (:300-322), alpha (:325-333)
     std::vector<uint64_t> offs;
     std::vector<size_t> live;
-    ctx->workers().run(P0, 8, [&](size_t i) {
+    host_stage(P0, 8, [&](size_t i) {
         PProof &p = pp[i];
         if (p.rc) return;
         p.rng_bytes = a->rng_bytes + a->rng_stride * i;
@@ -328,21 +358,20 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     PCUDA(cudaMemcpyAsync(hio, d_enc.p, 32 * (size_t)P, cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
     // ---- challenges y, z (:348, transcripts.rs:124-136), alpha update (:382-392)
-    ctx->workers().run(P, 8, [&](size_t s) {
+    host_stage(P, 8, [&](size_t s) {
         PProof &p = pp[live[s]];
         memcpy(p.A, hio + 32 * s, 32);
         bool good = append_point(p.t, LBL("A"), p.A);
         if (good) { rebuild_rng(p); good = challenge(p.t, LBL("y"), p.y) && challenge(p.t, LBL("z"), p.z); }
         if (!good) { p.rc = BPP_VERIFICATION_FAILED; p.y = sc_one(); p.z = sc_one(); }
-        sc z2 = sc_mul(p.z, p.z), yN1 = sc_one();
-        for (uint32_t k = 0; k < N + 1; k++) yN1 = sc_mul(yN1, p.y);
+        const sc z2 = hmul(p.z, p.z), yN1 = hpow(p.y, (uint64_t)N + 1);
         sc zeven = sc_one();
         const size_t i = live[s];
         for (uint32_t j = 0; j < m; j++) {
-            zeven = sc_mul(zeven, z2);
+            zeven = hmul(zeven, z2);
             for (uint32_t k = 0; k < ext; k++) {
                 sc r = sc_load(a->blindings32 + 32 * ((i * m + j) * ext + k));
-                p.alpha[k] = sc_add(p.alpha[k], sc_mul(sc_mul(zeven, r), yN1));
+                p.alpha[k] = sc_add(p.alpha[k], hmul(hmul(zeven, r), yN1));
             }
         }
     });
@@ -355,7 +384,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     for (uint32_t round = 0; round < rounds; round++) {
         const uint32_t nn = N >> (round + 1);
         PCUDA(cudaStreamSynchronize(st));      // hio is about to be rewritten
-        ctx->workers().run(P, 8, [&](size_t s) {
+        host_stage(P, 8, [&](size_t s) {
             PProof &p = pp[live[s]];
             for (uint32_t k = 0; k < ext; k++) p.dL[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dL", true, round, true, k) : random_not_zero(p.rng);
             for (uint32_t k = 0; k < ext; k++) p.dR[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dR", true, round, true, k) : random_not_zero(p.rng);
@@ -380,7 +409,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         }
         PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
         PCUDA(cudaStreamSynchronize(st));
-        ctx->workers().run(P, 8, [&](size_t s) {       // transcripts.rs:139-149
+        host_stage(P, 8, [&](size_t s) {       // transcripts.rs:139-149
             PProof &p = pp[live[s]];
             memcpy(p.LR.data() + 64 * (size_t)round, hio + 64 * s, 64);
             bool good = append_point(p.t, LBL("L"), hio + 64 * s) && append_point(p.t, LBL("R"), hio + 64 * s + 32);
@@ -412,17 +441,17 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         // A1 = sum_j r*sG[j]*G_j + sum_j s*sH[j]*H_j + sum d[k]*G[k] + (r*y*b[0] + s*y*a[0])*H   (:574-580, Gi[0] / Hi[0] unfolded)
         // B  = (r*y*s)*H + sum eta[k]*G[k]                                                        (:581-584)
         uint8_t *h_rs = hio, *h_tail = hio + 64 * (size_t)P, *h_b = h_tail + 32 * (size_t)P * (1 + ext);
-        ctx->workers().run(P, 8, [&](size_t s) {
+        host_stage(P, 8, [&](size_t s) {
             PProof &p = pp[live[s]];
             draw_final(p);
             const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
-            const sc ry = sc_mul(p.r, p.y), sy = sc_mul(p.s, p.y);
+            const sc ry = hmul(p.r, p.y), sy = hmul(p.s, p.y);
             sc_store(h_rs + 64 * s, p.r); sc_store(h_rs + 64 * s + 32, p.s);
             uint8_t *tl = h_tail + 32 * s * (1 + ext);
             for (uint32_t k = 0; k < ext; k++) sc_store(tl + 32 * k, p.d[k]);
-            sc_store(tl + 32 * ext, sc_add(sc_mul(ry, b0), sc_mul(sy, a0)));
+            sc_store(tl + 32 * ext, sc_add(hmul(ry, b0), hmul(sy, a0)));
             uint8_t *bv = h_b + 32 * s * segB;
-            sc_store(bv, sc_mul(ry, p.s));
+            sc_store(bv, hmul(ry, p.s));
             for (uint32_t k = 0; k < ext; k++) sc_store(bv + 32 * (1 + k), p.eta[k]);
         });
         const size_t firstB = (size_t)P * segA1;
@@ -443,20 +472,20 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     uint8_t *h_sc = hio;
     uint32_t *h_px = reinterpret_cast<uint32_t *>(hio + 32 * (size_t)P * per);
     const uint32_t GEN = 0x80000000u, CACHED = 0x40000000u;
-    ctx->workers().run(P, 8, [&](size_t s) {
+    host_stage(P, 8, [&](size_t s) {
         PProof &p = pp[live[s]];
         draw_final(p);
         const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
-        const sc ry = sc_mul(p.r, p.y), sy = sc_mul(p.s, p.y);
+        const sc ry = hmul(p.r, p.y), sy = hmul(p.s, p.y);
         uint8_t *sv = h_sc + 32 * s * per;
         uint32_t *px = h_px + s * per;
         // A1 = r*Gi[0] + s*Hi[0] + (r*y*b[0] + s*y*a[0])*H + sum d[k]*G[k]      (:574-580)
         sc_store(sv, p.r);                       px[0] = CACHED | (uint32_t)(s * N);
         sc_store(sv + 32, p.s);                  px[1] = CACHED | (uint32_t)((size_t)P * N + s * N);
-        sc_store(sv + 64, sc_add(sc_mul(ry, b0), sc_mul(sy, a0)));   px[2] = GEN | (uint32_t)(2 * g->nm + ext);
+        sc_store(sv + 64, sc_add(hmul(ry, b0), hmul(sy, a0)));   px[2] = GEN | (uint32_t)(2 * g->nm + ext);
         for (uint32_t k = 0; k < ext; k++) { sc_store(sv + 32 * (3 + k), p.d[k]); px[3 + k] = GEN | (uint32_t)(2 * g->nm + k); }
         // B = (r*y*s)*H + sum eta[k]*G[k]                                        (:581-584)
-        sc_store(sv + 32 * len1, sc_mul(ry, p.s)); px[len1] = GEN | (uint32_t)(2 * g->nm + ext);
+        sc_store(sv + 32 * len1, hmul(ry, p.s)); px[len1] = GEN | (uint32_t)(2 * g->nm + ext);
         for (uint32_t k = 0; k < ext; k++) { sc_store(sv + 32 * (len1 + 1 + k), p.eta[k]); px[len1 + 1 + k] = GEN | (uint32_t)(2 * g->nm + k); }
     });
     PCUDA(cudaMemcpyAsync(d_mscal.p, h_sc, 32 * (size_t)P * per, cudaMemcpyHostToDevice, st));
@@ -478,7 +507,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     PCUDA(cudaMemsetAsync(d_dlr.p, 0, 64 * (size_t)P * ext, st));
     PCUDA(cudaMemsetAsync(d_ab.p, 0, 64 * (size_t)P, st));
     PCUDA(cudaStreamSynchronize(st));
-    ctx->workers().run(P, 8, [&](size_t s) {
+    host_stage(P, 8, [&](size_t s) {
         const size_t i = live[s];
         PProof &p = pp[i];
         memcpy(p.A1, fb ? hio + 32 * s : hio + 64 * s, 32);                    // fixed-base path: [A1 x P | B x P]
@@ -488,28 +517,28 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         if (!good && !p.rc) p.rc = BPP_VERIFICATION_FAILED;
         p.t.s.store(a->transcripts + BPP_TRANSCRIPT_BYTES * i);
         if (p.rc) return;
-        const sc e = p.e_final, e2 = sc_mul(e, e);
+        const sc e = p.e_final, e2 = hmul(e, e);
         const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
         // alpha += sum_rounds d_L*e_r^2 + d_R*e_r^-2 (:535-537), with one inversion for all rounds
         sc prod = sc_one();
         std::vector<sc> pre(rounds);
-        for (uint32_t r = 0; r < rounds; r++) { pre[r] = prod; prod = sc_mul(prod, p.e_round[r]); }
+        for (uint32_t r = 0; r < rounds; r++) { pre[r] = prod; prod = hmul(prod, p.e_round[r]); }
         sc inv = sc_invert_gcd(prod);
         for (int r = (int)rounds - 1; r >= 0; r--) {
-            sc einv = sc_mul(inv, pre[r]);
-            inv = sc_mul(inv, p.e_round[r]);
-            sc er2 = sc_mul(p.e_round[r], p.e_round[r]), einv2 = sc_mul(einv, einv);
+            sc einv = hmul(inv, pre[r]);
+            inv = hmul(inv, p.e_round[r]);
+            sc er2 = hmul(p.e_round[r], p.e_round[r]), einv2 = hmul(einv, einv);
             for (uint32_t k = 0; k < ext; k++)
-                p.alpha[k] = sc_add(p.alpha[k], sc_add(sc_mul(p.dL[(size_t)r * ext + k], er2), sc_mul(p.dR[(size_t)r * ext + k], einv2)));
+                p.alpha[k] = sc_add(p.alpha[k], sc_add(hmul(p.dL[(size_t)r * ext + k], er2), hmul(p.dR[(size_t)r * ext + k], einv2)));
         }
         uint8_t *out = proofs_out + proof_stride * i;        // to_bytes layout (:1120-1150)
         out[0] = (uint8_t)ext;
         for (uint32_t k = 0; k < ext; k++)
-            sc_store(out + 1 + 32 * k, sc_add(sc_add(p.eta[k], sc_mul(p.d[k], e)), sc_mul(p.alpha[k], e2)));    // d1 (:592-594)
+            sc_store(out + 1 + 32 * k, sc_add(sc_add(p.eta[k], hmul(p.d[k], e)), hmul(p.alpha[k], e2)));    // d1 (:592-594)
         uint8_t *q = out + 1 + 32 * ext;
         memcpy(q, p.A, 32); memcpy(q + 32, p.A1, 32); memcpy(q + 64, p.B, 32);
-        sc_store(q + 96, sc_add(p.r, sc_mul(a0, e)));           // r1 (:590)
-        sc_store(q + 128, sc_add(p.s, sc_mul(b0, e)));          // s1 (:591)
+        sc_store(q + 96, sc_add(p.r, hmul(a0, e)));           // r1 (:590)
+        sc_store(q + 128, sc_add(p.s, hmul(b0, e)));          // s1 (:591)
         memcpy(q + 160, p.LR.data(), 64 * (size_t)rounds);
         // wipe host secrets
         memset(p.witness.data(), 0, p.witness.size());
@@ -517,6 +546,9 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         p.r = sc_zero(); p.s = sc_zero();
     });
     std::fill(ab.begin(), ab.end(), 0);
+    if (prove_trace)
+        fprintf(stderr, "bpp_prove_batch P=%u: %.2f ms, host stages %.2f ms\n", P,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count(), host_stage_ms);
     for (size_t i = 0; i < P0; i++) status[i] = pp[i].rc;
     release();
 #undef PCUDA

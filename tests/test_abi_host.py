@@ -164,3 +164,17 @@ def test_host_wide_reduction_64bit_limbs():
         lib.bpp_host_sc_from_wide64(c, a)
         lib.bpp_scalar_from_wide(c, b)
         assert a.raw == b.raw == (int.from_bytes(c, "little") % L).to_bytes(32, "little")
+
+
+def test_host_scalar_mul_64bit_limbs():
+    """bpp_host_sc_mul64 (the prover's host-side scalar products): a any 256-bit value, b canonical, against python integers"""
+    import itertools
+
+    lib = bpp.ffi.lib()
+    L = orc.L
+    o = C.create_string_buffer(32)
+    a_vals = [0, 1, L - 1, L, L + 5, 2**255, 2**256 - 1] + [int.from_bytes(hashlib.shake_256(b"ma%d" % i).digest(32), "little") for i in range(60)]
+    b_vals = [0, 1, 2, L - 1, L - 2, 2**252] + [int.from_bytes(hashlib.shake_256(b"mb%d" % i).digest(32), "little") % L for i in range(60)]
+    for a, b in itertools.product(a_vals, b_vals):
+        lib.bpp_host_sc_mul64(a.to_bytes(32, "little"), b.to_bytes(32, "little"), o)
+        assert int.from_bytes(o.raw, "little") == (a * b) % L, (hex(a), hex(b))

@@ -109,6 +109,7 @@ def lib():
         "bpp_host_verifier_weights": (i32, [cp, sz, sz, i32, cp]),
         "bpp_host_sc_from_wide64": (None, [cp, cp]),
         "bpp_host_sc_mul64": (None, [cp, cp, cp]),
+        "bpp_host_sc_generic64": (None, [cp, cp, cp]),
         "bpp_msm": (i32, [vp, sz, cp, cp, cp]),
         "bpp_msm_segmented": (i32, [vp, sz, vp, cp, cp, cp]),
         "bpp_msm_plan_create": (i32, [vp, sz, cp, i32, P(vp)]),

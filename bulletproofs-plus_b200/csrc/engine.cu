@@ -85,6 +85,7 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (const char *env = getenv("BPP_NO_GRAPHS")) ctx->use_graphs = atoi(env) == 0;
     if (const char *env = getenv("BPP_SCALAR_WEIGHTS")) ctx->scalar_weights = atoi(env) != 0;
     if (const char *env = getenv("BPP_NAP_US")) { long v = atol(env); if (v >= 1 && v <= 100000) ctx->nap_ns = v * 1000; }
+    if (const char *env = getenv("BPP_ADAPTIVE_WAIT")) ctx->adaptive_wait = atoi(env) != 0;
     if (const char *env = getenv("BPP_THROUGHPUT_MODE")) { ctx->throughput_mode = atoi(env) != 0; ctx->device_weights = atoi(env) == 2; }
     *out = ctx;
     return BPP_OK;

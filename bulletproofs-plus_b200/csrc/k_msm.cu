@@ -278,6 +278,35 @@ __global__ void __launch_bounds__(BUCKET_CTA) k_msm_bucket(uint32_t n_keys, cons
     if (valid) st_fe(reinterpret_cast<fe *>(&buckets[k]) + role, out);
 }
 
+// (X : Y : Z : T) += +-Q for one sorted entry e = index | sign << 31: whole-thread mixed addition with an affine-Niels table entry
+// (7 multiplications) or with a projective "cached" point (8; the prover's folded generators)
+static __device__ __forceinline__ void bucket_add_entry(fe &X, fe &Y, fe &Z, fe &T, uint32_t e, const uint32_t *__restrict__ pidx,
+                                                        const aniels *__restrict__ dyn, const aniels *__restrict__ gens,
+                                                        const cached *__restrict__ dync) {
+    const uint32_t idx = e & 0x7fffffffu;
+    const uint32_t pi = pidx ? pidx[idx] : idx;
+    const bool neg = (e >> 31) != 0;
+    const bool proj = (pi & 0xc0000000u) == 0x40000000u;
+    const fe *qm, *qp, *qt;                                        // (y-x, y+x, 2dxy); -Q swaps the first two and negates the third
+    fe D;
+    if (proj) {
+        const cached *src = dync + (pi & 0x3fffffffu);
+        qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
+        D = fe_mul(Z, ld_fe(&src->z2));
+    } else {
+        const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
+        qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
+        D = fe_add(Z, Z);
+    }
+    const fe A = fe_mul(fe_sub_l(Y, X), ld_fe(neg ? qp : qm));
+    const fe B = fe_mul(fe_add_l(Y, X), ld_fe(neg ? qm : qp));
+    const fe C = fe_mul(T, ld_fe(qt));
+    const fe E = fe_sub_l(B, A), H = fe_add_l(B, A);
+    const fe F0 = fe_sub_l(D, C), G0 = fe_add_l(D, C);
+    const fe F = fe_select(F0, G0, neg), G = fe_select(G0, F0, neg);      // -Q: C changes sign
+    X = fe_mul(E, F); Y = fe_mul(G, H); Z = fe_mul(F, G); T = fe_mul(E, H);
+}
+
 // Throughput variant: one THREAD per bucket (7 sequential multiplications per mixed addition, no shuffles or role selects:
 // about half the instructions of the quad kernel per addition).  The 256 buckets of a CTA are counting-sorted by size so that
 // the 32 buckets of a warp have neighbouring sizes.  Used when there are enough buckets to fill the machine with whole threads.
@@ -314,31 +343,7 @@ __global__ void __launch_bounds__(256) k_msm_bucket_thread(uint32_t n_keys, cons
     if (k >= n_keys) return;
     const uint32_t lo = starts[k], cnt = starts[k + 1] - lo;
     fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
-    for (uint32_t j = 0; j < cnt; j++) {
-        const uint32_t e = sorted[lo + j];
-        const uint32_t idx = e & 0x7fffffffu;
-        const uint32_t pi = pidx ? pidx[idx] : idx;
-        const bool neg = (e >> 31) != 0;
-        const bool proj = (pi & 0xc0000000u) == 0x40000000u;          // projective "cached" point (prover's folded generators)
-        const fe *qm, *qp, *qt;                                        // (y-x, y+x, 2dxy); -Q swaps the first two and negates the third
-        fe D;
-        if (proj) {
-            const cached *src = dync + (pi & 0x3fffffffu);
-            qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
-            D = fe_mul(Z, ld_fe(&src->z2));
-        } else {
-            const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
-            qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
-            D = fe_add(Z, Z);
-        }
-        const fe A = fe_mul(fe_sub_l(Y, X), ld_fe(neg ? qp : qm));
-        const fe B = fe_mul(fe_add_l(Y, X), ld_fe(neg ? qm : qp));
-        const fe C = fe_mul(T, ld_fe(qt));
-        const fe E = fe_sub_l(B, A), H = fe_add_l(B, A);
-        const fe F0 = fe_sub_l(D, C), G0 = fe_add_l(D, C);
-        const fe F = fe_select(F0, G0, neg), G = fe_select(G0, F0, neg);      // -Q: C changes sign
-        X = fe_mul(E, F); Y = fe_mul(G, H); Z = fe_mul(F, G); T = fe_mul(E, H);
-    }
+    for (uint32_t j = 0; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
     cached *out = buckets + k;
     st_fe(&out->ymx, fe_sub_l(Y, X));
     st_fe(&out->ypx, fe_add_l(Y, X));
@@ -427,6 +432,39 @@ static __device__ __forceinline__ gex gex_shfl_down(const gex &v, int delta, int
     r.X = fe_select(fe_zero(), r.X, in); r.Y = fe_select(fe_one(), r.Y, in); r.Z = fe_select(fe_one(), r.Z, in); r.T = fe_select(fe_zero(), r.T, in);
     return r;
 }
+// Mid-size bucket sums: LANES = 2, 4 or 8 consecutive lanes of a warp per bucket.  Lane r sums entries r, r + LANES, ... of the bucket
+// as a whole thread (the arithmetic of k_msm_bucket_thread), then a shuffle tree adds the LANES partial sums (9 multiplications per
+// level).  For MSMs whose bucket count alone cannot fill the machine with whole threads (2^14..2^18 points: 10-50 k buckets of
+// 30-250 entries) this keeps the whole-thread instruction count -- about half of the quad kernel's per addition -- at the quad
+// kernel's parallelism.
+template <int LANES>
+__global__ void __launch_bounds__(256) k_msm_bucket_split(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
+                                                         const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
+                                                         const aniels *__restrict__ gens, const cached *__restrict__ dync,
+                                                         cached *__restrict__ buckets) {
+    const uint32_t k = (blockIdx.x * 256u + threadIdx.x) / LANES;
+    const uint32_t r = threadIdx.x & (LANES - 1);
+    const bool valid = k < n_keys;
+    const uint32_t lo = valid ? starts[k] : 0u, cnt = valid ? starts[k + 1] - lo : 0u;
+    gex p = gex_identity();
+    for (uint32_t j = r; j < cnt; j += LANES) bucket_add_entry(p.X, p.Y, p.Z, p.T, sorted[lo + j], pidx, dyn, gens, dync);
+    // groups are LANES-aligned inside the warp: lane r < d of a group receives the sum of lane r + d of the same group; what the
+    // other lanes receive is never used
+#pragma unroll
+    for (int d = LANES / 2; d >= 1; d >>= 1) {
+        gex o;
+        o.X = shfl_down_fe(p.X, d); o.Y = shfl_down_fe(p.Y, d); o.Z = shfl_down_fe(p.Z, d); o.T = shfl_down_fe(p.T, d);
+        gex_add(p, o);
+    }
+    if (valid && r == 0) {
+        cached *out = buckets + k;
+        st_fe(&out->ymx, fe_sub_l(p.Y, p.X));
+        st_fe(&out->ypx, fe_add_l(p.Y, p.X));
+        st_fe(&out->z2, fe_add_l(p.Z, p.Z));
+        st_fe(&out->t2d, fe_mul(p.T, fe_const_2d()));
+    }
+}
+
 __global__ void __launch_bounds__(128) k_msm_reduce_warp(uint32_t n_win, uint32_t B, const cached *__restrict__ buckets, ge *__restrict__ windows) {
     const uint32_t win = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -512,16 +550,33 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     // sub-partition on; from 1 warp on only while the buckets are short (a thread walks its bucket alone: 2^16 points at c = 11
     // are 64 additions per bucket, measured 82 M points/s with quads against 75 M with threads; the verifier's 4226-entry
     // segments are 16 per bucket and 8 % faster with threads)
-    static const int force_bucket = getenv("BPP_MSM_BUCKET") ? atoi(getenv("BPP_MSM_BUCKET")) : 0;      // 1 = quads, 2 = threads (tests)
+    const int force_bucket = getenv("BPP_MSM_BUCKET") ? atoi(getenv("BPP_MSM_BUCKET")) : 0;      // 1 = quads, 2 = threads, 3 = split threads (tests)
     const size_t full = 148u * 4u * 32u;
+    const size_t adds = (size_t)sh.n_entries * sh.W;
     const bool thread_buckets = force_bucket ? force_bucket == 2
-                                             : n_keys >= 4 * full || (n_keys >= full && (size_t)sh.n_entries * sh.W <= 32 * n_keys);
-    if (thread_buckets)
+                                             : n_keys >= 4 * full || (n_keys >= full && adds <= 32 * n_keys);
+    // split threads (when whole threads per bucket cannot fill the machine): LANES = the power of two nearest to 170 k threads /
+    // bucket count, at most 8, halved while a lane would walk fewer than 4 entries.  Measured (scripts/msm_bucket_probe.py, bucket
+    // phase, quads -> split): 2^14 c = 9: 146 -> 86 us; 2^15: 266 -> 135; 2^16 c = 11: 391 -> 231; 2^17: 764 -> 391; 2^18 c = 12:
+    // 821 -> 533 (whole threads: 767)
+    int split = 0;
+    if (force_bucket == 3) split = getenv("BPP_MSM_SPLIT") ? atoi(getenv("BPP_MSM_SPLIT")) : 4;
+    else if (!force_bucket && !thread_buckets && n_keys >= 1024) {
+        const double want = 170000.0 / (double)n_keys;
+        split = want >= 5.66 ? 8 : want >= 2.83 ? 4 : want >= 1.42 ? 2 : 1;
+        while (split > 1 && adds < 4 * (size_t)split * n_keys) split >>= 1;
+    }
+    if (split == 2 || split == 4 || split == 8) {
+        const uint32_t grid = (uint32_t)((n_keys * (size_t)split + 255) / 256);
+        if (split == 2) k_msm_bucket_split<2><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+        else if (split == 4) k_msm_bucket_split<4><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+        else k_msm_bucket_split<8><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+    } else if (thread_buckets)
         k_msm_bucket_thread<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     else
         k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
-    static const int force_reduce = getenv("BPP_MSM_REDUCE") ? atoi(getenv("BPP_MSM_REDUCE")) : 0;      // 1 = CTA of quads, 2 = warp of threads (tests)
+    const int force_reduce = getenv("BPP_MSM_REDUCE") ? atoi(getenv("BPP_MSM_REDUCE")) : 0;      // 1 = CTA of quads, 2 = warp of threads (tests)
     if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         k_msm_reduce_small<<<(n_win + 31) / 32, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);

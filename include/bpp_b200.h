@@ -105,9 +105,12 @@ int32_t bpp_ctx_set_host_threads(bpp_ctx *ctx, int32_t n);
  * (compress), ristretto.rs:48-52 <- generators_chain.rs:44-49 (one-way map). */
 /* host only: Scalar::from_bytes_mod_order_wide on 64-bit limbs (the verifier-weight path); checked against bpp_scalar_from_wide */
 void bpp_host_sc_from_wide64(const uint8_t in64[64], uint8_t out32[32]);
-/* host only: a * b mod l on 64-bit limbs; a: any 256-bit value, b: canonical (< l); output canonical.  The prover's host-side scalar
+/* host only: a * b mod l on 64-bit limbs; a, b: any 256-bit values; output canonical (< l).  The prover's host-side scalar
  * bookkeeping. */
 void bpp_host_sc_mul64(const uint8_t a32[32], const uint8_t b32[32], uint8_t out32[32]);
+/* test hook, host only: the portable (non-MULX) body of the two functions above: b32_or_null != NULL -> a32 * b32 mod l,
+ * else the wide reduction of 64 bytes */
+void bpp_host_sc_generic64(const uint8_t *a32_or_wide64, const uint8_t *b32_or_null, uint8_t out32[32]);
 /* test hook, host only: the verifier weights (range_proof.rs:811-853, :894) of n_chunks <= 4 chunks of `len` proofs each from the 32
  * bytes every proof feeds into the weight transcript; lockstep = 1 runs the chunks through the four-way vectorised sponge */
 int32_t bpp_host_verifier_weights(const uint8_t *wbytes32, size_t len, size_t n_chunks, int32_t lockstep, uint8_t *weights32);

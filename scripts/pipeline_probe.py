@@ -2,9 +2,12 @@
 """How much of the GPU does one 1024-proof verification step leave idle?  Runs S independent bpp_ctx (one CUDA stream pair each,
 one host thread each) that verify the same 1024-proof workload concurrently and prints the aggregate proofs/s for
 S = 1, 2, 4, 8 ..., device-resident (bpp_vbatch_run) and end to end (bpp_verify_chunks with host buffers), for both device
-replay kernels.  usage: pipeline_probe.py [steps_per_stream] [S ...]"""
+replay kernels, with the host CPU time (user + system, all threads) the process spent per step.  usage: pipeline_probe.py
+[steps_per_stream] [S ...]; PROBE_ONE_MODE=1: only the default replay kernel; run under `taskset -c 0-3` to see what 4 host cores
+per GPU (the 8-GPU box) can feed."""
 import ctypes as C
 import os
+import resource
 import sys
 import threading
 import time
@@ -59,24 +62,30 @@ class Lane:
 
 def timed(lanes, fn_name, k):
     ths = [threading.Thread(target=getattr(ln, fn_name), args=(k,)) for ln in lanes]
+    r0 = resource.getrusage(resource.RUSAGE_SELF)
     t0 = time.perf_counter()
     for t in ths:
         t.start()
     for t in ths:
         t.join()
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    r1 = resource.getrusage(resource.RUSAGE_SELF)
+    timed.cpu_s = (r1.ru_utime + r1.ru_stime) - (r0.ru_utime + r0.ru_stime)
+    return dt
 
 
 for S in S_list:
     lanes = [Lane(max(1, cores // S)) for _ in range(S)]
-    for mode, name in ((2, "thread/proof"), (3, "warp/proof")):
+    for mode, name in (((1, "default"),) if os.environ.get("PROBE_ONE_MODE") else ((2, "thread/proof"), (3, "warp/proof"))):
         for ln in lanes:
             ln.eng.set_replay_mode(mode)
         timed(lanes, "dev_steps", 3)
         td = timed(lanes, "dev_steps", steps)
+        cd = timed.cpu_s
         timed(lanes, "e2e_steps", 3)
         te = timed(lanes, "e2e_steps", steps)
-        print("S=%d replay=%-12s device-resident %9.0f proofs/s (%.3f ms/step/stream)   e2e %9.0f proofs/s (%.3f ms/step/stream)" % (
-            S, name, S * steps * N / td, 1e3 * td / steps, S * steps * N / te, 1e3 * te / steps), flush=True)
+        ce = timed.cpu_s
+        print("S=%d replay=%-12s device-resident %9.0f proofs/s (%.3f ms/step/stream, host CPU %.3f ms/step)   e2e %9.0f proofs/s (%.3f ms/step/stream, host CPU %.3f ms/step)" % (
+            S, name, S * steps * N / td, 1e3 * td / steps, 1e3 * cd / (S * steps), S * steps * N / te, 1e3 * te / steps, 1e3 * ce / (S * steps)), flush=True)
     for ln in lanes:
         ln.eng.close()          # closes the lane's batches and generator tables first

@@ -151,30 +151,41 @@ def test_host_verifier_weights_match_oracle(shape):
         assert got.raw == want.raw, lockstep
 
 
+def _fold_edge_cases():
+    """values that sit on the edges of the three folds of the wide reduction (multiples of l, of 2^252, all-ones limbs)"""
+    L = orc.L
+    vals = [0, 1, L - 1, L, L + 1, 2 * L, 4 * L - 1, L * L, L * L - 1, 2**252 - 1, 2**252, 2**252 + 1, 2**256 - 1, 2**256, 2**504, 2**511, 2**512 - 1,
+            2**512 - L, (2**512 // L) * L, (2**512 // L) * L - 1, 2**385 - 1, 2**385, 2**258 - 1, 2**258, (2**260 - 1) << 252, (2**133 - 1) << 252]
+    vals += [k * L + d for k in (1, 2**100, 2**200, 2**259) for d in (-1, 0, 1) if 0 <= k * L + d < 2**512]
+    vals += [(0xFFFFFFFFFFFFFFFF << (64 * i)) for i in range(8)] + [(1 << (64 * i)) for i in range(8)]
+    return vals
+
+
 def test_host_wide_reduction_64bit_limbs():
-    """bpp_host_sc_from_wide64 (64-bit-limb Montgomery reduction used for the weights) against python integers and the shared
-    32-bit-limb path"""
+    """bpp_host_sc_from_wide64 (the folded 64-bit-limb reduction used for the weights: MULX body and portable body) against python
+    integers and the shared 32-bit-limb path"""
     lib = bpp.ffi.lib()
     L = orc.L
-    cases = [bytes(64), b"\xff" * 64, L.to_bytes(64, "little"), (L - 1).to_bytes(64, "little"), (L * L).to_bytes(64, "little"),
-             (2**256).to_bytes(64, "little"), (2**512 - 1).to_bytes(64, "little")]
-    cases += [hashlib.shake_256(b"wide-%d" % i).digest(64) for i in range(500)]
-    a, b = C.create_string_buffer(32), C.create_string_buffer(32)
+    cases = [v.to_bytes(64, "little") for v in _fold_edge_cases()]
+    cases += [hashlib.shake_256(b"wide-%d" % i).digest(64) for i in range(2000)]
+    a, b, g = C.create_string_buffer(32), C.create_string_buffer(32), C.create_string_buffer(32)
     for c in cases:
         lib.bpp_host_sc_from_wide64(c, a)
         lib.bpp_scalar_from_wide(c, b)
-        assert a.raw == b.raw == (int.from_bytes(c, "little") % L).to_bytes(32, "little")
+        lib.bpp_host_sc_generic64(c, None, g)
+        assert a.raw == b.raw == g.raw == (int.from_bytes(c, "little") % L).to_bytes(32, "little"), c.hex()
 
 
 def test_host_scalar_mul_64bit_limbs():
-    """bpp_host_sc_mul64 (the prover's host-side scalar products): a any 256-bit value, b canonical, against python integers"""
+    """bpp_host_sc_mul64 (the prover's host-side scalar products; both bodies): any two 256-bit values, against python integers"""
     import itertools
 
     lib = bpp.ffi.lib()
     L = orc.L
-    o = C.create_string_buffer(32)
+    o, g = C.create_string_buffer(32), C.create_string_buffer(32)
     a_vals = [0, 1, L - 1, L, L + 5, 2**255, 2**256 - 1] + [int.from_bytes(hashlib.shake_256(b"ma%d" % i).digest(32), "little") for i in range(60)]
-    b_vals = [0, 1, 2, L - 1, L - 2, 2**252] + [int.from_bytes(hashlib.shake_256(b"mb%d" % i).digest(32), "little") % L for i in range(60)]
+    b_vals = [0, 1, 2, L - 1, L - 2, 2**252, 2**256 - 1] + [int.from_bytes(hashlib.shake_256(b"mb%d" % i).digest(32), "little") % L for i in range(60)]
     for a, b in itertools.product(a_vals, b_vals):
         lib.bpp_host_sc_mul64(a.to_bytes(32, "little"), b.to_bytes(32, "little"), o)
-        assert int.from_bytes(o.raw, "little") == (a * b) % L, (hex(a), hex(b))
+        lib.bpp_host_sc_generic64(a.to_bytes(32, "little"), b.to_bytes(32, "little"), g)
+        assert int.from_bytes(o.raw, "little") == int.from_bytes(g.raw, "little") == (a * b) % L, (hex(a), hex(b))

@@ -1,7 +1,7 @@
 """Verification lanes (api.VerifierPool: one bpp_ctx + host thread per lane) and the alternative kernel paths.
   * batches verified concurrently on S lanes give exactly the oracle's statuses, masks and advanced transcripts, valid and
     corrupted, whatever S is;
-  * the kernel variants that are picked by size (thread-per-bucket / quad-per-bucket MSM, long-vector scalar prep) are forced
+  * the kernel variants that are picked by size (thread-per-bucket / quad-per-bucket / split-thread MSM, long-vector scalar prep) are forced
     through their environment switches in a child process and must reproduce the oracle on the same cases."""
 import os
 import subprocess
@@ -96,7 +96,8 @@ print("child ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"BPP_MSM_BUCKET": "1"}, {"BPP_MSM_BUCKET": "2"}, {"BPP_MSM_REDUCE": "1"}, {"BPP_MSM_REDUCE": "2"},
+@pytest.mark.parametrize("env", [{"BPP_MSM_BUCKET": "1"}, {"BPP_MSM_BUCKET": "2"}, {"BPP_MSM_BUCKET": "3", "BPP_MSM_SPLIT": "2"},
+                                 {"BPP_MSM_BUCKET": "3", "BPP_MSM_SPLIT": "4"}, {"BPP_MSM_BUCKET": "3", "BPP_MSM_SPLIT": "8"}, {"BPP_MSM_REDUCE": "1"}, {"BPP_MSM_REDUCE": "2"},
                                  {"BPP_VPREP_DIRECT": "1"}, {"BPP_NO_GRAPHS": "1"}, {"BPP_SCALAR_WEIGHTS": "1"}])
 def test_kernel_variants_match_oracle(env):
     e = dict(os.environ)

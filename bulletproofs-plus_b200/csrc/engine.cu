@@ -511,6 +511,35 @@ int32_t bpp_pedersen_commit_batch(bpp_gens *g, size_t count, const uint64_t *val
         if (!host_sc_is_canonical(blindings32 + 32 * i)) return fail(ctx, BPP_INVALID_ARGUMENT, "non-canonical scalar");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
+    // Every term sits on a static generator: with the fixed-base window tables at hand (built by an earlier proving call, or worth
+    // building for a large batch) a commitment is W table additions per term -- no sort, no buckets, no 252-doubling Horner chain
+    // (the prover's opening check of 1024 commitments: 0.6 ms through K-MSM).  BPP_COMMIT_KMSM=1 keeps the K-MSM path (tests).
+    static const bool force_kmsm = getenv("BPP_COMMIT_KMSM") != nullptr && atoi(getenv("BPP_COMMIT_KMSM")) != 0;
+    if (!force_kmsm && (g->fb_state > 0 || (count >= 256 && gens_fb_ensure(g)))) {
+        std::vector<uint32_t> sc(8 * n), gidx(per);
+        gidx[0] = (uint32_t)(2 * g->nm + g->ext);
+        for (int k = 0; k < n_blindings; k++) gidx[1 + k] = (uint32_t)(2 * g->nm + k);
+        for (size_t i = 0; i < count; i++) {
+            uint32_t *s = &sc[8 * i * per];
+            memset(s, 0, 32);
+            s[0] = (uint32_t)values[i]; s[1] = (uint32_t)(values[i] >> 32);
+            memcpy(s + 8, blindings32 + 32 * i * (size_t)n_blindings, 32 * (size_t)n_blindings);
+        }
+        BPP_CUDA(ctx, ctx->d_in.ensure(32 * n));
+        BPP_CUDA(ctx, ctx->d_in2.ensure(4 * per));
+        BPP_CUDA(ctx, ctx->d_res.ensure(sizeof(ge) * count));
+        BPP_CUDA(ctx, ctx->d_out.ensure(32 * count));
+        BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, sc.data(), 32 * n, cudaMemcpyHostToDevice, st));
+        BPP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in2.p, gidx.data(), 4 * per, cudaMemcpyHostToDevice, st));
+        launch_fb_msm(st, g->fb, (uint32_t)count, (uint32_t)per, 1, ctx->d_in.as<uint32_t>(), ctx->d_in2.as<uint32_t>(), g->d_fb.as<aniels>(),
+                      ctx->d_res.as<ge>(), &ctx->launches);
+        launch_encode(st, count, ctx->d_res.as<ge>(), ctx->d_out.as<uint32_t>(), nullptr);
+        ctx->launches++;
+        BPP_CUDA(ctx, cudaGetLastError());
+        BPP_CUDA(ctx, cudaMemcpyAsync(out32, ctx->d_out.p, 32 * count, cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(ctx, cudaStreamSynchronize(st));      // sc / gidx are pageable: the copies above have been staged, the sync covers the rest
+        return BPP_OK;
+    }
     // entries per opening: [value -> H, blinding_k -> G[k]]
     std::vector<uint32_t> sc(8 * n), pidx(n), off(count + 1);
     for (size_t i = 0; i < count; i++) {

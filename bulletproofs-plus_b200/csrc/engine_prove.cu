@@ -63,7 +63,7 @@ struct PProof {
     size_t rng_used = 0;
     sc alpha[BPP_MAX_EXT];
     sc y, z, e_final;
-    std::vector<sc> e_round, dL, dR;   // per round (dL/dR: rounds x ext)
+    std::vector<sc> e_round, einv_round, dL, dR;   // per round (dL/dR: rounds x ext)
     sc r, s, d[BPP_MAX_EXT], eta[BPP_MAX_EXT];
     uint8_t A[32], A1[32], B[32];
     std::vector<uint8_t> LR;           // rounds x 64
@@ -219,7 +219,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         if (p.rc) { p.t.s.store(a->transcripts + BPP_TRANSCRIPT_BYTES * i); return; }
         if (p.has_seed) sc_store(p.seed, sc_reduce_bytes(a->seed_nonces32 + 32 * i));
         for (uint32_t k = 0; k < ext; k++) p.alpha[k] = p.has_seed ? nonce(p.seed, "alpha", false, 0, true, k) : random_not_zero(p.rng);
-        p.e_round.resize(rounds); p.dL.resize((size_t)rounds * ext); p.dR.resize((size_t)rounds * ext); p.LR.resize(64 * (size_t)rounds);
+        p.e_round.resize(rounds); p.einv_round.resize(rounds); p.dL.resize((size_t)rounds * ext); p.dR.resize((size_t)rounds * ext); p.LR.resize(64 * (size_t)rounds);
     });
     for (size_t i = 0; i < P0; i++)
         if (!pp[i].rc) { pp[i].live = true; pp[i].slot = (uint32_t)live.size(); live.push_back(i); }
@@ -293,7 +293,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     ok(d_offs.ensure(8 * (size_t)P * m));
     ok(d_a.ensure(32 * (size_t)P * N)); ok(d_b.ensure(32 * (size_t)P * N));
     ok(d_ypow.ensure(32 * (size_t)P * (N + 2))); ok(d_yinv2.ensure(32 * (size_t)P * BPP_MAX_ROUNDS));
-    ok(d_yz.ensure(64 * (size_t)P)); ok(d_dlr.ensure(64 * (size_t)P * ext)); ok(d_e.ensure(32 * (size_t)P)); ok(d_fsc.ensure(32 * 6 * (size_t)P));
+    ok(d_yz.ensure(96 * (size_t)P)); ok(d_dlr.ensure(64 * (size_t)P * ext)); ok(d_e.ensure(64 * (size_t)P)); ok(d_fsc.ensure(32 * 6 * (size_t)P));
     if (fb) {
         ok(ws.d_sg.ensure(32 * (size_t)P * N)); ok(ws.d_sh.ensure(32 * (size_t)P * N));
         ok(ws.d_gidx.ensure(4 * gidx.size())); ok(ws.d_rs.ensure(64 * (size_t)P));
@@ -376,7 +376,18 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         }
     });
     for (uint32_t s = 0; s < P; s++) { sc_store(hio + 64 * (size_t)s, pp[live[s]].y); sc_store(hio + 64 * (size_t)s + 32, pp[live[s]].z); }
-    PCUDA(cudaMemcpyAsync(d_yz.p, hio, 64 * (size_t)P, cudaMemcpyHostToDevice, st));
+    // y^-1 by Montgomery's trick over chunks of 64 proofs (y is never zero: challenge() rejects it above)
+    host_stage((P + 63) / 64, 1, [&](size_t c) {
+        const size_t lo = 64 * c, hi = std::min<size_t>(P, lo + 64);
+        sc pre[64], acc = sc_one();
+        for (size_t s = lo; s < hi; s++) { pre[s - lo] = acc; acc = hmul(acc, pp[live[s]].y); }
+        sc inv = sc_invert_gcd(acc);
+        for (size_t s = hi; s-- > lo;) {
+            sc_store(hio + 64 * (size_t)P + 32 * s, hmul(inv, pre[s - lo]));
+            inv = hmul(inv, pp[live[s]].y);
+        }
+    });
+    PCUDA(cudaMemcpyAsync(d_yz.p, hio, 96 * (size_t)P, cudaMemcpyHostToDevice, st));
     launch_prove_init(st, d, b);
     ctx->launches += 2;
 
@@ -418,8 +429,25 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
             if (!good) { if (!p.rc) p.rc = BPP_VERIFICATION_FAILED; e = sc_one(); }
             p.e_round[round] = e;
         });
-        for (uint32_t s = 0; s < P; s++) sc_store(hio + 32 * (size_t)s, pp[live[s]].e_round[round]);
-        PCUDA(cudaMemcpyAsync(d_e.p, hio, 32 * (size_t)P, cudaMemcpyHostToDevice, st));
+        // e^-1 of every proof by Montgomery's trick over chunks of 64 proofs (one inversion + 3 products per proof): on the device
+        // it was one binary-Euclid inversion per proof per round on the critical path (0.13 ms per round), and the responses at
+        // the end needed one more inversion per proof.  Challenges are never zero (challenge() rejects them above).
+        host_stage((P + 63) / 64, 1, [&](size_t c) {
+            const size_t lo = 64 * c, hi = std::min<size_t>(P, lo + 64);
+            sc pre[64], acc = sc_one();
+            for (size_t s = lo; s < hi; s++) { pre[s - lo] = acc; acc = hmul(acc, pp[live[s]].e_round[round]); }
+            sc inv = sc_invert_gcd(acc);
+            for (size_t s = hi; s-- > lo;) {
+                PProof &p = pp[live[s]];
+                p.einv_round[round] = hmul(inv, pre[s - lo]);
+                inv = hmul(inv, p.e_round[round]);
+            }
+        });
+        for (uint32_t s = 0; s < P; s++) {
+            sc_store(hio + 32 * (size_t)s, pp[live[s]].e_round[round]);
+            sc_store(hio + 32 * ((size_t)P + s), pp[live[s]].einv_round[round]);
+        }
+        PCUDA(cudaMemcpyAsync(d_e.p, hio, 64 * (size_t)P, cudaMemcpyHostToDevice, st));
         if (fb) { launch_prove_fold_fb(st, d, b, nn); ctx->launches += 2; }
         else { launch_prove_fold(st, d, b, nn, round, g->d_table.as<aniels>()); ctx->launches += 3; }
     }
@@ -519,14 +547,9 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         if (p.rc) return;
         const sc e = p.e_final, e2 = hmul(e, e);
         const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
-        // alpha += sum_rounds d_L*e_r^2 + d_R*e_r^-2 (:535-537), with one inversion for all rounds
-        sc prod = sc_one();
-        std::vector<sc> pre(rounds);
-        for (uint32_t r = 0; r < rounds; r++) { pre[r] = prod; prod = hmul(prod, p.e_round[r]); }
-        sc inv = sc_invert_gcd(prod);
+        // alpha += sum_rounds d_L*e_r^2 + d_R*e_r^-2 (:535-537), with the inverses the rounds already made
         for (int r = (int)rounds - 1; r >= 0; r--) {
-            sc einv = hmul(inv, pre[r]);
-            inv = hmul(inv, p.e_round[r]);
+            const sc einv = p.einv_round[r];
             sc er2 = hmul(p.e_round[r], p.e_round[r]), einv2 = hmul(einv, einv);
             for (uint32_t k = 0; k < ext; k++)
                 p.alpha[k] = sc_add(p.alpha[k], sc_add(hmul(p.dL[(size_t)r * ext + k], er2), hmul(p.dR[(size_t)r * ext + k], einv2)));

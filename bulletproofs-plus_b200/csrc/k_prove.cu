@@ -6,7 +6,7 @@
 //   k_prove_bits       bit decomposition -> the +-1 entries of the A commitment MSM (:300-345)
 //   k_prove_init       y powers, y^-(2^k), a_L - z, a_R + d*y^(N-i) + z (:350-381)
 //   k_prove_round_pre  a_lo*y^-n', a_hi*y^n', c_L / c_R, and the entry lists of the L and R MSMs (:413-495)
-//   k_prove_round_inv  e^-1 per proof (binary Euclid)
+//   k_prove_round_inv  the fold scalars of a round from e and e^-1 (both from the host: one batch inversion per call and round)
 //   k_prove_fold_pts   Gi' = e^-1*Gi_lo + e*y^-n'*Gi_hi, Hi' = e*Hi_lo + e^-1*Hi_hi (:511-521): one quad per output point runs a
 //                      joint 2-bit-window double-scalar multiplication (the reference issues 2(N-1) two-point MSMs per
 //                      proof here -- ~65 % of its proving time)
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(64) k_prove_ypow(PDims d, PBuffers b) {
     uint32_t *yp = b.ypow + 8 * (size_t)p * (d.N + 2);
     sc acc = sc_const_R();
     for (uint32_t i = 0; i < d.N + 2; i++) { p_st_sc(yp + 8 * i, acc); acc = pmm(acc, y); }
-    sc yi = scm_invert_gcd(y);
+    sc yi = sc_to_mont(p_ld_sc(b.yz + 16 * (size_t)d.P + 8 * (size_t)p));          // y^-1 from the host (batch inversion over the call)
     uint32_t *yv = b.yinv2 + 8 * (size_t)p * BPP_MAX_ROUNDS;
     for (uint32_t k = 0; k < d.rounds; k++) { p_st_sc(yv + 8 * k, yi); yi = pmm(yi, yi); }
 }
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(64) k_prove_round_inv(PDims d, PBuffers b, uin
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.P) return;
     const sc e = sc_to_mont(p_ld_sc(b.e + 8 * (size_t)p));
-    const sc einv = scm_invert_gcd(e);
+    const sc einv = sc_to_mont(p_ld_sc(b.e + 8 * ((size_t)d.P + p)));          // inverted on the host (batch inversion over the call)
     uint32_t log_nn = 31 - __clz(nn);
     const sc yinv_nn = p_ld_sc(b.yinv2 + 8 * ((size_t)p * BPP_MAX_ROUNDS + log_nn));
     uint32_t *f = b.fsc + 8 * (size_t)p * 6;

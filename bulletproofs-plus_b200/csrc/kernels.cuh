@@ -119,9 +119,9 @@ struct PBuffers {
     uint32_t *a, *b;                 // P x N scalars, Montgomery form (a_L / a_R, folded in place)
     uint32_t *ypow;                  // P x (N + 2): y^0 .. y^(N+1), Montgomery
     uint32_t *yinv2;                 // P x BPP_MAX_ROUNDS: y^-(2^k), Montgomery
-    const uint32_t *yz;              // P x 2 canonical: y, z
+    const uint32_t *yz;              // P x 2 canonical: y, z; then P canonical: y^-1
     const uint32_t *dlr;             // P x 2 x ext canonical: d_L[k], d_R[k] of the current round
-    const uint32_t *e;               // P canonical: round challenge
+    const uint32_t *e;               // 2P canonical: round challenges e[0..P), their inverses e^-1[P..2P)
     uint32_t *fsc;                   // P x 6: fold scalars (see k_prove_round_inv)
     cached *folded;                  // [Gi: P x N | Hi: P x N] folded generator vectors (valid from round 1 on; folding path)
     uint32_t *sg, *sh;               // P x N scalars, Montgomery: the folding as coefficients over the original generators (fixed-base path)

@@ -553,7 +553,7 @@ def main():
     ap.add_argument("--blocking-waits", type=int, default=-1, help="-1 = when lanes * ranks >= host cores")
     ap.add_argument("--proofs", type=int, default=1024, help="proofs per GPU per step")
     ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput on rank 0 (secondary metrics)")
-    ap.add_argument("--prove-batch", type=int, default=4096)
+    ap.add_argument("--prove-batch", type=int, default=8192)
     ap.add_argument("--prove-lanes", type=int, default=8, help="concurrent bpp_prove_batch calls the proving batch is split into")
     ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20, 22])
     args = ap.parse_args()

@@ -133,7 +133,7 @@ def test_points_sum_host_matches_oracle():
         bpp.pkg.points_sum_host(pts[0] + b"\xff" * 32)
 
 
-@pytest.mark.parametrize("shape", [(1, 5), (2, 7), (3, 100), (4, 256)])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 5), (2, 7), (4, 37), (3, 100), (2, 255), (4, 256)])
 def test_host_verifier_weights_match_oracle(shape):
     """the product's host-side verifier-weight transcripts (range_proof.rs:811-853, :894) -- one at a time and four in lock-step
     through the vectorised four-way Keccak-f (host_keccak4.cpp) -- against the oracle's restatement of the same lines"""

@@ -76,8 +76,21 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
             int top_bits = 251 - cc * (W - 1);
             if (per >= 1024 && top_bits < cc - 3) continue;
             double B = (double)(1u << (cc - 1));
-            double cost = per >= 16384 ? per * W * 0.136 + B * 48.0 * (sh.n_seg > 1 ? (double)sh.n_seg * W / 148.0 : 1.0)
-                                       : 2.0 * per * W + 5.0 * B * W + (2.0 * cc + 3.0) * W;
+            double cost;
+            if (per >= 16384 && sh.n_seg == 1) {
+                // one large MSM, in ns (scripts/msm_sweep.py, msm_bucket_probe.py): digit sort 0.02 per (entry, window); bucket sums
+                // 0.09 per addition with whole threads per bucket (enough buckets for that: launch_msm), 0.15 with split threads;
+                // window reduction, split over up to 8 CTAs per window: 54 us at 256 buckets, 112 at 1024, 138 at 8192, 250 / 340 at
+                // 2^14 / 2^15 buckets.  Picks c = 14 from 2^16 points on (2^16: 127 M points/s against 106 M at c = 11; 2^18: 304 M
+                // against 253 M at c = 12)
+                const double keys = (double)W * B;
+                const double red = B <= 1024 ? 35e3 + 75.0 * B : 110e3 + 3.4 * B + (B > 8192 ? 7.0 * (B - 8192) : 0.0);
+                cost = per * W * ((keys >= 4.0 * 148 * 4 * 32 ? 0.09 : 0.15) + 0.02) + red;
+            } else if (per >= 16384) {
+                cost = per * W * 0.136 + B * 48.0 * ((double)sh.n_seg * W / 148.0);
+            } else {
+                cost = 2.0 * per * W + 5.0 * B * W + (2.0 * cc + 3.0) * W;
+            }
             if (cost < best) { best = cost; c = cc; }
         }
     }
@@ -91,6 +104,7 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #define SCAN_TILE 4096u
+#define REDUCE_PARTS_MAX 8u
 
 struct MsmScratch {
     uint32_t *starts;   // n_keys + 1
@@ -99,6 +113,7 @@ struct MsmScratch {
     uint32_t *sorted;   // n_entries * W
     cached *buckets;    // n_keys
     ge *windows;        // n_seg * W
+    ge *wparts;         // n_seg * W * REDUCE_PARTS_MAX: partial window sums of k_msm_reduce when a window is split over several CTAs
     size_t total;
 };
 static MsmScratch msm_carve(const MsmShape &sh, void *base) {
@@ -113,6 +128,7 @@ static MsmScratch msm_carve(const MsmShape &sh, void *base) {
     s.sorted = (uint32_t *)(p + off); off = align_up(off + (size_t)sh.n_entries * sh.W * 4 + 4, 256);
     s.buckets = (cached *)(p + off); off = align_up(off + n_keys * sizeof(cached), 256);
     s.windows = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * sizeof(ge), 256);
+    s.wparts = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * REDUCE_PARTS_MAX * sizeof(ge), 256);
     s.total = off;
     return s;
 }
@@ -352,23 +368,27 @@ __global__ void __launch_bounds__(256) k_msm_bucket_thread(uint32_t n_keys, cons
 }
 
 // ------------------------------------------------------------------------------------------------ 5: window sums
-// one CTA per (segment, window); quad t owns buckets [t*L, (t+1)*L): S = sum, R = sum_j (j+1)*bucket[tL+j]; it contributes
-// R + (t*L)*S, and the CTA adds the contributions up.  Control flow is CTA-uniform (idle quads work on the identity).
-__global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uint32_t nq, const cached *__restrict__ buckets,
+// `parts` CTAs per (segment, window); CTA (win, part) covers buckets [part*Bp, (part+1)*Bp) with Bp = nq*L, its quad t the L buckets from
+// k = part*Bp + t*L: S = sum, R = sum_j (j+1)*bucket[k+j]; the quad contributes R + k*S, and the CTA adds the contributions up.
+// Control flow is CTA-uniform (idle quads work on the identity).  With parts > 1 the CTA writes a partial window sum that
+// k_msm_window_parts adds up: a large single MSM has only W = 16-20 windows, i.e. as many CTAs, each walking B / 256 buckets per
+// quad in sequence (c = 14: 0.46 ms whatever the point count); split eight ways the chains are L = 8 long and 8 W CTAs share the SMs.
+__global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uint32_t nq, uint32_t parts, const cached *__restrict__ buckets,
                                                     ge *__restrict__ windows) {
     __shared__ fe part[32][4];
     const uint32_t t = threadIdx.x >> 2;
     const int role = threadIdx.x & 3, lane = threadIdx.x & 31, base = lane & ~3;
-    const cached *bk = buckets + (size_t)blockIdx.x * B + (size_t)t * L;
+    const uint32_t win = blockIdx.x / parts, k0 = (blockIdx.x % parts) * nq * L;
+    const cached *bk = buckets + (size_t)win * B + k0 + (size_t)t * L;
     fe S = quad_identity(role), R = quad_identity(role);
     for (int j = (int)L - 1; j >= 0; j--) {
         fe b = t < nq ? ld_fe(reinterpret_cast<const fe *>(&bk[j]) + role) : quad_cached_identity(role);
         S = quad_add(S, role, base, b);
         R = quad_add(R, role, base, quad_to_cached(S, role, base));
     }
-    // R += (t*L) * S by uniform double-and-add over the bits of the largest offset in the CTA
+    // R += k * S by uniform double-and-add over the bits of the largest offset in the CTA
     {
-        const uint32_t k = t < nq ? t * L : 0u, kmax = (nq - 1) * L;
+        const uint32_t k = t < nq ? k0 + t * L : 0u, kmax = k0 + (nq - 1) * L;
         const fe Sc = quad_to_cached(S, role, base);
         fe M = quad_identity(role);
         for (int bit = 31 - __clz(kmax | 1u); bit >= 0; bit--) {
@@ -401,6 +421,19 @@ __global__ void __launch_bounds__(1024) k_msm_reduce(uint32_t B, uint32_t L, uin
         }
         if (lane < 4) st_fe(reinterpret_cast<fe *>(&windows[blockIdx.x]) + role, V);
     }
+}
+// window sum = sum of its `parts` partial sums (one quad per window)
+__global__ void __launch_bounds__(32) k_msm_window_parts(uint32_t n_win, uint32_t parts, const ge *__restrict__ wparts, ge *__restrict__ windows) {
+    const uint32_t win = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int role = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
+    const bool valid = win < n_win;
+    const fe *src = reinterpret_cast<const fe *>(wparts + (size_t)(valid ? win : 0) * parts);
+    fe acc = valid ? ld_fe(src + role) : quad_identity(role);
+    for (uint32_t p = 1; p < parts; p++) {
+        fe o = valid ? ld_fe(src + 4 * p + role) : quad_identity(role);
+        acc = quad_add(acc, role, base, quad_to_cached(o, role, base));
+    }
+    if (valid) st_fe(reinterpret_cast<fe *>(&windows[win]) + role, acc);
 }
 
 // Throughput variant for many (segment, window) pairs of moderate size (the verifier: 4 x 28 windows of 256 buckets): one WARP per
@@ -587,10 +620,20 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         k_msm_reduce_warp<<<(n_win + 3) / 4, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
     } else {
-        uint32_t nq = sh.B >= 8 ? sh.B / 8 : 1;        // quads per (segment, window)
+        // quads of 8 buckets; up to REDUCE_PARTS_MAX CTAs of <= 128 quads per window while the windows alone leave SMs idle
+        // (BPP_MSM_REDUCE_PARTS forces the split: tests / experiments)
+        const uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
+        uint32_t quads = sh.B >= 8 ? sh.B / 8 : 1, parts = 1;
+        while (parts < REDUCE_PARTS_MAX && quads / parts > 128 && n_win * parts * 2 <= 2 * 148u /* CTAs after the split */) parts <<= 1;
+        if (const char *env = getenv("BPP_MSM_REDUCE_PARTS")) {
+            uint32_t v = (uint32_t)atoi(env);
+            if ((v == 1 || v == 2 || v == 4 || v == 8) && quads % v == 0) parts = v;
+        }
+        uint32_t nq = quads / parts;                   // quads per CTA
         if (nq > 256) nq = 256;
-        uint32_t L = sh.B / nq;
-        k_msm_reduce<<<sh.n_seg * sh.W, (4 * nq + 31u) / 32u * 32u, 0, s>>>(sh.B, L, nq, sc.buckets, sc.windows);
+        uint32_t L = sh.B / (parts * nq);
+        k_msm_reduce<<<n_win * parts, (4 * nq + 31u) / 32u * 32u, 0, s>>>(sh.B, L, nq, parts, sc.buckets, parts > 1 ? sc.wparts : sc.windows);
+        if (parts > 1) k_msm_window_parts<<<(n_win + 7) / 8, 32, 0, s>>>(n_win, parts, sc.wparts, sc.windows);
     }
     if (marks) cudaEventRecord(marks[2], s);
     k_msm_combine<<<(sh.n_seg + 7) / 8, 32, 0, s>>>(sh.n_seg, sh.c, sh.W, sc.windows, result);

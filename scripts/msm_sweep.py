@@ -1,4 +1,5 @@
-"""raw MSM sweep with per-phase device times: python scripts/msm_sweep.py [log2 sizes...]; window bits 0 = auto"""
+"""raw MSM sweep with per-phase device times: python scripts/msm_sweep.py [log2 sizes...]; window bits 0 = auto;
+SWEEP_AUTO=1: only the automatic window width"""
 import hashlib, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 import bpp
@@ -11,7 +12,7 @@ for lg in sizes:
     sc = bytearray(hashlib.shake_256(b"sc%d" % lg).digest(32 * n))
     for i in range(31, len(sc), 32):
         sc[i] &= 0x0F
-    for c in ([0] if lg < 16 else [0, 12, 13, 14, 15, 16]):
+    for c in ([0] if lg < 16 or os.environ.get("SWEEP_AUTO") else [0, 12, 13, 14, 15, 16]):
         plan = bpp.pkg.MsmPlan(eng, pts, c)
         plan.set_scalars(bytes(sc))
         ref = plan.run(True)

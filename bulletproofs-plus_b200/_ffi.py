@@ -110,6 +110,8 @@ def lib():
         "bpp_host_sc_from_wide64": (None, [cp, cp]),
         "bpp_host_sc_mul64": (None, [cp, cp, cp]),
         "bpp_host_sc_generic64": (None, [cp, cp, cp]),
+        "bpp_keccak_f1600_x1": (None, [vp]),
+        "bpp_keccak_f1600_x1_generic": (None, [vp]),
         "bpp_msm": (i32, [vp, sz, cp, cp, cp]),
         "bpp_msm_segmented": (i32, [vp, sz, vp, cp, cp, cp]),
         "bpp_msm_plan_create": (i32, [vp, sz, cp, i32, P(vp)]),

@@ -24,53 +24,74 @@ static const uint64_t RC[24] = {
 // chi), the next round goes back from `e` to `a`: a source lane dies as soon as its plane is written, so the live set stays near the
 // 32 vector registers of AVX-512VL (an "all 25 b, then all 25 a" round keeps 50 values live and spilt ~150 moves per round:
 // 419 -> 370 ns per four-way permutation on a Sapphire-Rapids-class core).
-#define KECCAK4_BODY \
-    const v4u *sp = (const v4u *)st; \
-    v4u a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3], a4 = sp[4], a5 = sp[5], a6 = sp[6], a7 = sp[7], a8 = sp[8], a9 = sp[9], a10 = sp[10], a11 = sp[11], a12 = sp[12], a13 = sp[13], a14 = sp[14], a15 = sp[15], a16 = sp[16], a17 = sp[17], a18 = sp[18], a19 = sp[19], a20 = sp[20], a21 = sp[21], a22 = sp[22], a23 = sp[23], a24 = sp[24]; \
-    v4u e0, e1, e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13, e14, e15, e16, e17, e18, e19, e20, e21, e22, e23, e24; \
+#define KECCAK_BODY(KT, KB) \
+    const KT *sp = (const KT *)st; \
+    KT a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3], a4 = sp[4], a5 = sp[5], a6 = sp[6], a7 = sp[7], a8 = sp[8], a9 = sp[9], a10 = sp[10], a11 = sp[11], a12 = sp[12], a13 = sp[13], a14 = sp[14], a15 = sp[15], a16 = sp[16], a17 = sp[17], a18 = sp[18], a19 = sp[19], a20 = sp[20], a21 = sp[21], a22 = sp[22], a23 = sp[23], a24 = sp[24]; \
+    KT e0, e1, e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13, e14, e15, e16, e17, e18, e19, e20, e21, e22, e23, e24; \
     for (int round = 0; round < 24; round += 2) { \
         const uint64_t rc0 = RC[round], rc1 = RC[round + 1]; \
-        { v4u c0 = a0 ^ a5 ^ a10 ^ a15 ^ a20, c1 = a1 ^ a6 ^ a11 ^ a16 ^ a21, c2 = a2 ^ a7 ^ a12 ^ a17 ^ a22, c3 = a3 ^ a8 ^ a13 ^ a18 ^ a23, c4 = a4 ^ a9 ^ a14 ^ a19 ^ a24; \
-          v4u d0 = c4 ^ ROL(c1, 1), d1 = c0 ^ ROL(c2, 1), d2 = c1 ^ ROL(c3, 1), d3 = c2 ^ ROL(c4, 1), d4 = c3 ^ ROL(c0, 1); \
-          { v4u b0 = (a0 ^ d0), b1 = ROL(a6 ^ d1, 44), b2 = ROL(a12 ^ d2, 43), b3 = ROL(a18 ^ d3, 21), b4 = ROL(a24 ^ d4, 14); \
-            e0 = b0 ^ (~b1 & b2) ^ (v4u){rc0, rc0, rc0, rc0}; e1 = b1 ^ (~b2 & b3); e2 = b2 ^ (~b3 & b4); e3 = b3 ^ (~b4 & b0); e4 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(a3 ^ d3, 28), b1 = ROL(a9 ^ d4, 20), b2 = ROL(a10 ^ d0, 3), b3 = ROL(a16 ^ d1, 45), b4 = ROL(a22 ^ d2, 61); \
+        { KT c0 = a0 ^ a5 ^ a10 ^ a15 ^ a20, c1 = a1 ^ a6 ^ a11 ^ a16 ^ a21, c2 = a2 ^ a7 ^ a12 ^ a17 ^ a22, c3 = a3 ^ a8 ^ a13 ^ a18 ^ a23, c4 = a4 ^ a9 ^ a14 ^ a19 ^ a24; \
+          KT d0 = c4 ^ ROL(c1, 1), d1 = c0 ^ ROL(c2, 1), d2 = c1 ^ ROL(c3, 1), d3 = c2 ^ ROL(c4, 1), d4 = c3 ^ ROL(c0, 1); \
+          { KT b0 = (a0 ^ d0), b1 = ROL(a6 ^ d1, 44), b2 = ROL(a12 ^ d2, 43), b3 = ROL(a18 ^ d3, 21), b4 = ROL(a24 ^ d4, 14); \
+            e0 = b0 ^ (~b1 & b2) ^ KB(rc0); e1 = b1 ^ (~b2 & b3); e2 = b2 ^ (~b3 & b4); e3 = b3 ^ (~b4 & b0); e4 = b4 ^ (~b0 & b1); } \
+          { KT b0 = ROL(a3 ^ d3, 28), b1 = ROL(a9 ^ d4, 20), b2 = ROL(a10 ^ d0, 3), b3 = ROL(a16 ^ d1, 45), b4 = ROL(a22 ^ d2, 61); \
             e5 = b0 ^ (~b1 & b2); e6 = b1 ^ (~b2 & b3); e7 = b2 ^ (~b3 & b4); e8 = b3 ^ (~b4 & b0); e9 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(a1 ^ d1, 1), b1 = ROL(a7 ^ d2, 6), b2 = ROL(a13 ^ d3, 25), b3 = ROL(a19 ^ d4, 8), b4 = ROL(a20 ^ d0, 18); \
+          { KT b0 = ROL(a1 ^ d1, 1), b1 = ROL(a7 ^ d2, 6), b2 = ROL(a13 ^ d3, 25), b3 = ROL(a19 ^ d4, 8), b4 = ROL(a20 ^ d0, 18); \
             e10 = b0 ^ (~b1 & b2); e11 = b1 ^ (~b2 & b3); e12 = b2 ^ (~b3 & b4); e13 = b3 ^ (~b4 & b0); e14 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(a4 ^ d4, 27), b1 = ROL(a5 ^ d0, 36), b2 = ROL(a11 ^ d1, 10), b3 = ROL(a17 ^ d2, 15), b4 = ROL(a23 ^ d3, 56); \
+          { KT b0 = ROL(a4 ^ d4, 27), b1 = ROL(a5 ^ d0, 36), b2 = ROL(a11 ^ d1, 10), b3 = ROL(a17 ^ d2, 15), b4 = ROL(a23 ^ d3, 56); \
             e15 = b0 ^ (~b1 & b2); e16 = b1 ^ (~b2 & b3); e17 = b2 ^ (~b3 & b4); e18 = b3 ^ (~b4 & b0); e19 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(a2 ^ d2, 62), b1 = ROL(a8 ^ d3, 55), b2 = ROL(a14 ^ d4, 39), b3 = ROL(a15 ^ d0, 41), b4 = ROL(a21 ^ d1, 2); \
+          { KT b0 = ROL(a2 ^ d2, 62), b1 = ROL(a8 ^ d3, 55), b2 = ROL(a14 ^ d4, 39), b3 = ROL(a15 ^ d0, 41), b4 = ROL(a21 ^ d1, 2); \
             e20 = b0 ^ (~b1 & b2); e21 = b1 ^ (~b2 & b3); e22 = b2 ^ (~b3 & b4); e23 = b3 ^ (~b4 & b0); e24 = b4 ^ (~b0 & b1); } \
         } \
-        { v4u c0 = e0 ^ e5 ^ e10 ^ e15 ^ e20, c1 = e1 ^ e6 ^ e11 ^ e16 ^ e21, c2 = e2 ^ e7 ^ e12 ^ e17 ^ e22, c3 = e3 ^ e8 ^ e13 ^ e18 ^ e23, c4 = e4 ^ e9 ^ e14 ^ e19 ^ e24; \
-          v4u d0 = c4 ^ ROL(c1, 1), d1 = c0 ^ ROL(c2, 1), d2 = c1 ^ ROL(c3, 1), d3 = c2 ^ ROL(c4, 1), d4 = c3 ^ ROL(c0, 1); \
-          { v4u b0 = (e0 ^ d0), b1 = ROL(e6 ^ d1, 44), b2 = ROL(e12 ^ d2, 43), b3 = ROL(e18 ^ d3, 21), b4 = ROL(e24 ^ d4, 14); \
-            a0 = b0 ^ (~b1 & b2) ^ (v4u){rc1, rc1, rc1, rc1}; a1 = b1 ^ (~b2 & b3); a2 = b2 ^ (~b3 & b4); a3 = b3 ^ (~b4 & b0); a4 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(e3 ^ d3, 28), b1 = ROL(e9 ^ d4, 20), b2 = ROL(e10 ^ d0, 3), b3 = ROL(e16 ^ d1, 45), b4 = ROL(e22 ^ d2, 61); \
+        { KT c0 = e0 ^ e5 ^ e10 ^ e15 ^ e20, c1 = e1 ^ e6 ^ e11 ^ e16 ^ e21, c2 = e2 ^ e7 ^ e12 ^ e17 ^ e22, c3 = e3 ^ e8 ^ e13 ^ e18 ^ e23, c4 = e4 ^ e9 ^ e14 ^ e19 ^ e24; \
+          KT d0 = c4 ^ ROL(c1, 1), d1 = c0 ^ ROL(c2, 1), d2 = c1 ^ ROL(c3, 1), d3 = c2 ^ ROL(c4, 1), d4 = c3 ^ ROL(c0, 1); \
+          { KT b0 = (e0 ^ d0), b1 = ROL(e6 ^ d1, 44), b2 = ROL(e12 ^ d2, 43), b3 = ROL(e18 ^ d3, 21), b4 = ROL(e24 ^ d4, 14); \
+            a0 = b0 ^ (~b1 & b2) ^ KB(rc1); a1 = b1 ^ (~b2 & b3); a2 = b2 ^ (~b3 & b4); a3 = b3 ^ (~b4 & b0); a4 = b4 ^ (~b0 & b1); } \
+          { KT b0 = ROL(e3 ^ d3, 28), b1 = ROL(e9 ^ d4, 20), b2 = ROL(e10 ^ d0, 3), b3 = ROL(e16 ^ d1, 45), b4 = ROL(e22 ^ d2, 61); \
             a5 = b0 ^ (~b1 & b2); a6 = b1 ^ (~b2 & b3); a7 = b2 ^ (~b3 & b4); a8 = b3 ^ (~b4 & b0); a9 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(e1 ^ d1, 1), b1 = ROL(e7 ^ d2, 6), b2 = ROL(e13 ^ d3, 25), b3 = ROL(e19 ^ d4, 8), b4 = ROL(e20 ^ d0, 18); \
+          { KT b0 = ROL(e1 ^ d1, 1), b1 = ROL(e7 ^ d2, 6), b2 = ROL(e13 ^ d3, 25), b3 = ROL(e19 ^ d4, 8), b4 = ROL(e20 ^ d0, 18); \
             a10 = b0 ^ (~b1 & b2); a11 = b1 ^ (~b2 & b3); a12 = b2 ^ (~b3 & b4); a13 = b3 ^ (~b4 & b0); a14 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(e4 ^ d4, 27), b1 = ROL(e5 ^ d0, 36), b2 = ROL(e11 ^ d1, 10), b3 = ROL(e17 ^ d2, 15), b4 = ROL(e23 ^ d3, 56); \
+          { KT b0 = ROL(e4 ^ d4, 27), b1 = ROL(e5 ^ d0, 36), b2 = ROL(e11 ^ d1, 10), b3 = ROL(e17 ^ d2, 15), b4 = ROL(e23 ^ d3, 56); \
             a15 = b0 ^ (~b1 & b2); a16 = b1 ^ (~b2 & b3); a17 = b2 ^ (~b3 & b4); a18 = b3 ^ (~b4 & b0); a19 = b4 ^ (~b0 & b1); } \
-          { v4u b0 = ROL(e2 ^ d2, 62), b1 = ROL(e8 ^ d3, 55), b2 = ROL(e14 ^ d4, 39), b3 = ROL(e15 ^ d0, 41), b4 = ROL(e21 ^ d1, 2); \
+          { KT b0 = ROL(e2 ^ d2, 62), b1 = ROL(e8 ^ d3, 55), b2 = ROL(e14 ^ d4, 39), b3 = ROL(e15 ^ d0, 41), b4 = ROL(e21 ^ d1, 2); \
             a20 = b0 ^ (~b1 & b2); a21 = b1 ^ (~b2 & b3); a22 = b2 ^ (~b3 & b4); a23 = b3 ^ (~b4 & b0); a24 = b4 ^ (~b0 & b1); } \
         } \
     } \
-    v4u *dp = (v4u *)st; \
+    KT *dp = (KT *)st; \
     dp[0] = a0; dp[1] = a1; dp[2] = a2; dp[3] = a3; dp[4] = a4; dp[5] = a5; dp[6] = a6; dp[7] = a7; dp[8] = a8; dp[9] = a9; dp[10] = a10; dp[11] = a11; dp[12] = a12; dp[13] = a13; dp[14] = a14; dp[15] = a15; dp[16] = a16; dp[17] = a17; dp[18] = a18; dp[19] = a19; dp[20] = a20; dp[21] = a21; dp[22] = a22; dp[23] = a23; dp[24] = a24;
 
-__attribute__((target("avx2"))) static void keccak4_avx2(uint64_t *st) { KECCAK4_BODY }
+#define KB4(rc) ((v4u){rc, rc, rc, rc})
+#define KB1(rc) (rc)
+__attribute__((target("avx2"))) static void keccak4_avx2(uint64_t *st) { KECCAK_BODY(v4u, KB4) }
 // AVX-512VL: 32 vector registers (no spills of the 25 + 25 live values), native 64-bit rotates and three-input logic
-__attribute__((target("avx2,avx512f,avx512vl"))) static void keccak4_avx512vl(uint64_t *st) { KECCAK4_BODY }
-static void keccak4_generic(uint64_t *st) { KECCAK4_BODY }
+__attribute__((target("avx2,avx512f,avx512vl"))) static void keccak4_avx512vl(uint64_t *st) { KECCAK_BODY(v4u, KB4) }
+static void keccak4_generic(uint64_t *st) { KECCAK_BODY(v4u, KB4) }
+static void keccak1_generic(uint64_t *st) { KECCAK_BODY(uint64_t, KB1) }
 
+static int simd_level() {
+    static const int level = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl")) ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+    return level;
+}
 extern "C" {
 // st: 25 x 4 lanes, lane k of state j at st[4 * k + j]; 32-byte aligned
 void bpp_keccak_f1600_x4(uint64_t *st) {
-    static const int level = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl")) ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+    const int level = simd_level();
     if (level == 2) keccak4_avx512vl(st); else if (level == 1) keccak4_avx2(st); else keccak4_generic(st);
 }
+// ONE state (25 lanes): every host-side sponge of the library (hash.cuh on the host: the prover's transcripts and TranscriptRng, SHA3 /
+// SHAKE, host-mode replay) permutes through this.  With AVX2 / AVX-512VL the state rides in lane 0 of the four-way body: 16
+// general-purpose registers cannot hold 25 lanes + 25 temporaries, 16 / 32 vector registers do much better -- measured 1070 ns for the
+// plain 64-bit code against 390 ns through the vector body (three lanes idle) on an AVX-512 core.
+void bpp_keccak_f1600_x1(uint64_t *st) {
+    const int level = simd_level();
+    if (level == 0) { keccak1_generic(st); return; }
+    alignas(32) uint64_t x[100];
+    for (int k = 0; k < 25; k++) { x[4 * k] = st[k]; x[4 * k + 1] = 0; x[4 * k + 2] = 0; x[4 * k + 3] = 0; }
+    if (level == 2) keccak4_avx512vl(x); else keccak4_avx2(x);
+    for (int k = 0; k < 25; k++) st[k] = x[4 * k];
+}
+// test hook: the plain 64-bit body whatever the CPU
+void bpp_keccak_f1600_x1_generic(uint64_t *st) { keccak1_generic(st); }
 int bpp_host_has_avx2(void) { return __builtin_cpu_supports("avx2") ? 1 : 0; }
 }
 

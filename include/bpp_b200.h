@@ -240,6 +240,10 @@ void bpp_transcript_challenge_bytes(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8
 /* host hash layer, exposed so it can be pinned against external KATs (python hashlib) without a GPU:
  * SHA3-512 (ristretto.rs:92-95), SHAKE256 (generators_chain.rs:23-49), BLAKE2b-512 keyed+personalised with an empty
  * message (utils/generic.rs:56-57), Scalar::from_bytes_mod_order_wide (transcript_protocol.rs:70) */
+/* host only: Keccak-f[1600] on one 25-lane state -- what every host-side sponge of the library permutes through (vector registers when
+ * the CPU has AVX2 / AVX-512VL), and the plain 64-bit body for comparison (test hook) */
+void bpp_keccak_f1600_x1(uint64_t *state25);
+void bpp_keccak_f1600_x1_generic(uint64_t *state25);
 void bpp_hash_sha3_512(const uint8_t *in, size_t len, uint8_t out[64]);
 void bpp_hash_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen);
 int32_t bpp_hash_blake2b_nonce_bytes(const uint8_t *key, size_t keylen, const uint8_t *personal, size_t plen, uint8_t out[64]);

@@ -189,3 +189,25 @@ def test_host_scalar_mul_64bit_limbs():
         lib.bpp_host_sc_mul64(a.to_bytes(32, "little"), b.to_bytes(32, "little"), o)
         lib.bpp_host_sc_generic64(a.to_bytes(32, "little"), b.to_bytes(32, "little"), g)
         assert int.from_bytes(o.raw, "little") == int.from_bytes(g.raw, "little") == (a * b) % L, (hex(a), hex(b))
+
+
+def test_host_keccak_permutation_bodies_agree():
+    """bpp_keccak_f1600_x1 (vector-register body when the CPU has one) and the plain 64-bit body: the all-zero state gives the
+    published first lane of Keccak-f[1600](0), random states agree, and SHA3-512 through the library equals hashlib's"""
+    lib = bpp.ffi.lib()
+    z1, z2 = (C.c_uint64 * 25)(), (C.c_uint64 * 25)()
+    lib.bpp_keccak_f1600_x1(z1)
+    lib.bpp_keccak_f1600_x1_generic(z2)
+    assert z1[0] == z2[0] == 0xF1258F7940E1DDE7 and list(z1) == list(z2)
+    for i in range(50):
+        raw = hashlib.shake_256(b"kf-%d" % i).digest(200)
+        a, b = (C.c_uint64 * 25).from_buffer_copy(raw), (C.c_uint64 * 25).from_buffer_copy(raw)
+        for _ in range(1 + i % 3):
+            lib.bpp_keccak_f1600_x1(a)
+            lib.bpp_keccak_f1600_x1_generic(b)
+        assert list(a) == list(b), i
+    out = C.create_string_buffer(64)
+    for n in (0, 1, 71, 72, 73, 200, 1000):
+        msg = hashlib.shake_256(b"m%d" % n).digest(n)
+        lib.bpp_hash_sha3_512(msg, n, out)
+        assert out.raw == hashlib.sha3_512(msg).digest()

@@ -1,5 +1,5 @@
 #!/bin/bash
-# final round-1 validation: GPU suite, smoke, bench (both arms), then the ncu launch lists of the verification step and a proving call
+# GPU validation as run at the end of round 1 (under gpurun): GPU suite, smoke, bench (both arms), then the ncu launch lists of the verification step and a proving call
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -3 gpurun_out/t.log
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log

@@ -423,7 +423,10 @@ def run_b200(args, rank, local_rank, world):
     extras = {}
     if rank == 0 and args.extras:
         eng.set_host_threads(min(64, cores))           # the lanes shared the host cores; the prover call below is alone
-        extras = run_extras(eng, api, bpp, orc, args)
+        try:
+            extras = run_extras(eng, api, bpp, orc, args)
+        except Exception as exc:                       # secondary metrics must not take the headline line down with them
+            extras = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     # ---------------- reduce over ranks (max time)
     times = torch.tensor([dev_ms, e2e_s, seq_ms, e2e_seq_s], dtype=torch.float64, device="cuda")

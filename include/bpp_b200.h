@@ -152,7 +152,9 @@ void bpp_gens_destroy(bpp_gens *g);
 int32_t bpp_gens_fixed_base_msm(bpp_gens *gens, size_t n_seg, size_t seg_len, const uint8_t *scalars32, const uint32_t *gidx, uint8_t *out32);
 /* which: 0 = h_base, 1 = g_base[index], 2 = gi_base (flat, party-major), 3 = hi_base */
 int32_t bpp_gens_get(const bpp_gens *g, int32_t which, size_t index, uint8_t out32[32]);
-/* PedersenGens::commit for `count` openings: values[count], blindings32[count * n_blindings] */
+/* PedersenGens::commit for `count` openings: values[count], blindings32[count * n_blindings] (generators/pedersen_gens.rs:112-122).
+ * Batches of >= 256 openings, and every batch once the fixed-base window tables of `g` exist, are summed from those tables; smaller first
+ * batches go through the general MSM.  Same bytes either way. */
 int32_t bpp_pedersen_commit_batch(bpp_gens *g, size_t count, const uint64_t *values, const uint8_t *blindings32,
                                   int32_t n_blindings, uint8_t *out32);
 

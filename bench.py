@@ -475,8 +475,9 @@ def run_b200(args, rank, local_rank, world):
         dom = per_kernel[dominant]
         step_mul32 = sum(work[k] for k in work if k in per_kernel)
         step_ms = dev_ms_max / args.steps
-        roof = {"bound": "int32-multiply issue rate (IMAD.HI, one per 32x32->64 product); the path is modular big-integer arithmetic, neither HBM- nor tensor-bound "
-                         "(DRAM traffic per step: a few MB, profiles/r01_ncu_summary.md)",
+        roof = {"bound": "int32-mul",
+                "bound_note": "int32-multiply issue rate (IMAD.HI, one per 32x32->64 product); the path is modular big-integer arithmetic, neither HBM- nor "
+                              "tensor-bound (north_star; DRAM traffic per step: a few MB, profiles/r01_ncu_summary.md)",
                 "kernel": "k_" + dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
                 "peak_source": "bpp_microbench, measured in this run: IMAD.HI issue rate (one per 32x32->64 product; the IMAD.lo half issues on the "
                                "other FMA sub-pipe); LOP3+IADD3 rate for the Keccak kernel.  MEASURED_PEAKS.json has no integer figure",

@@ -112,6 +112,7 @@ def lib():
         "bpp_host_sc_generic64": (None, [cp, cp, cp]),
         "bpp_keccak_f1600_x1": (None, [vp]),
         "bpp_keccak_f1600_x1_generic": (None, [vp]),
+        "bpp_host_simd_level": (i32, []),
         "bpp_msm": (i32, [vp, sz, cp, cp, cp]),
         "bpp_msm_segmented": (i32, [vp, sz, vp, cp, cp, cp]),
         "bpp_msm_plan_create": (i32, [vp, sz, cp, i32, P(vp)]),

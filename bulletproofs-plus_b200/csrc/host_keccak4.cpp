@@ -68,8 +68,14 @@ __attribute__((target("avx2,avx512f,avx512vl"))) static void keccak4_avx512vl(ui
 static void keccak4_generic(uint64_t *st) { KECCAK_BODY(v4u, KB4) }
 static void keccak1_generic(uint64_t *st) { KECCAK_BODY(uint64_t, KB1) }
 
+#include <stdlib.h>
+// 2 = AVX-512VL, 1 = AVX2, 0 = baseline ISA; BPP_HOST_SIMD caps it (tests run every body on a CPU that has them all)
 static int simd_level() {
-    static const int level = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl")) ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+    static const int level = [] {
+        int l = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl")) ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+        if (const char *env = getenv("BPP_HOST_SIMD")) { int cap = atoi(env); if (cap >= 0 && cap < l) l = cap; }
+        return l;
+    }();
     return level;
 }
 extern "C" {
@@ -93,6 +99,7 @@ void bpp_keccak_f1600_x1(uint64_t *st) {
 // test hook: the plain 64-bit body whatever the CPU
 void bpp_keccak_f1600_x1_generic(uint64_t *st) { keccak1_generic(st); }
 int bpp_host_has_avx2(void) { return __builtin_cpu_supports("avx2") ? 1 : 0; }
+int32_t bpp_host_simd_level(void) { return simd_level(); }
 }
 
 // ------------------------------------------------------------------------------------------------ Scalar::from_bytes_mod_order_wide
@@ -220,7 +227,7 @@ BPP_BMI2 static void mul256_bmi2(const ull a[4], const ull b[4], ull out[8]) {
         for (int j = 0; j < 5; j++) c = _addcarry_u64(c, out[i + j], row[j], &out[i + j]);      // out[i + 4] was 0: no carry out of the row
     }
 }
-static const bool have_bmi2 = __builtin_cpu_supports("bmi2");
+static const bool have_bmi2 = __builtin_cpu_supports("bmi2") && !(getenv("BPP_HOST_SIMD") && atoi(getenv("BPP_HOST_SIMD")) == 0);
 #else
 static const bool have_bmi2 = false;
 static void reduce512_bmi2(const ull x[8], ull r[4]) { reduce512_generic(x, r); }

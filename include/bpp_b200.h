@@ -246,6 +246,9 @@ void bpp_transcript_challenge_bytes(uint8_t t[BPP_TRANSCRIPT_BYTES], const uint8
  * the CPU has AVX2 / AVX-512VL), and the plain 64-bit body for comparison (test hook) */
 void bpp_keccak_f1600_x1(uint64_t *state25);
 void bpp_keccak_f1600_x1_generic(uint64_t *state25);
+/* host only: which body the host-side hashing and scalar arithmetic run through: 2 = AVX-512VL, 1 = AVX2, 0 = baseline ISA (no MULX either);
+ * the environment variable BPP_HOST_SIMD caps it (the tests run every body on one CPU) */
+int32_t bpp_host_simd_level(void);
 void bpp_hash_sha3_512(const uint8_t *in, size_t len, uint8_t out[64]);
 void bpp_hash_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen);
 int32_t bpp_hash_blake2b_nonce_bytes(const uint8_t *key, size_t keylen, const uint8_t *personal, size_t plen, uint8_t out[64]);

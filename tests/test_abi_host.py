@@ -211,3 +211,62 @@ def test_host_keccak_permutation_bodies_agree():
         msg = hashlib.shake_256(b"m%d" % n).digest(n)
         lib.bpp_hash_sha3_512(msg, n, out)
         assert out.raw == hashlib.sha3_512(msg).digest()
+
+
+_SIMD_CHILD = r"""
+import ctypes as C, hashlib, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bpp, orc
+lib = bpp.ffi.lib()
+want_level = int(sys.argv[1])
+assert lib.bpp_host_simd_level() <= want_level
+# permutation: this level's body against the plain 64-bit body
+for i in range(20):
+    raw = hashlib.shake_256(b"lvl-%%d" %% i).digest(200)
+    a, b = (C.c_uint64 * 25).from_buffer_copy(raw), (C.c_uint64 * 25).from_buffer_copy(raw)
+    lib.bpp_keccak_f1600_x1(a); lib.bpp_keccak_f1600_x1_generic(b)
+    assert list(a) == list(b)
+# SHA3-512 / SHAKE256 through the host sponge
+out = C.create_string_buffer(64)
+for n in (0, 71, 72, 73, 500):
+    msg = hashlib.shake_256(b"m%%d" %% n).digest(n)
+    lib.bpp_hash_sha3_512(msg, n, out)
+    assert out.raw == hashlib.sha3_512(msg).digest()
+# verifier weights: lock-step four-way sponge and one at a time, against the oracle
+length, n_chunks = 37, 4
+wb = hashlib.shake_256(b"lvl-weights").digest(32 * length * n_chunks)
+want = b""
+for c in range(n_chunks):
+    part = C.create_string_buffer(32 * length)
+    orc.lib().orc_verifier_weights(wb[32 * length * c: 32 * length * (c + 1)], length, part)
+    want += part.raw
+for lockstep in (0, 1):
+    got = C.create_string_buffer(32 * length * n_chunks)
+    assert lib.bpp_host_verifier_weights(wb, length, n_chunks, lockstep, got) == 0
+    assert got.raw == want
+# wide reduction and product mod l
+L = orc.L
+o = C.create_string_buffer(32)
+for i in range(200):
+    w = hashlib.shake_256(b"lvl-w%%d" %% i).digest(64)
+    lib.bpp_host_sc_from_wide64(w, o)
+    assert int.from_bytes(o.raw, "little") == int.from_bytes(w, "little") %% L
+    lib.bpp_host_sc_mul64(w[:32], w[32:], o)
+    assert int.from_bytes(o.raw, "little") == int.from_bytes(w[:32], "little") * int.from_bytes(w[32:], "little") %% L
+print("level", lib.bpp_host_simd_level(), "ok")
+"""
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_host_simd_bodies(level):
+    """every host body (baseline ISA without MULX, AVX2, AVX-512VL) gives the same bytes: BPP_HOST_SIMD caps the dispatch in a child
+    process; a level the CPU lacks simply runs the best one below it"""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["BPP_HOST_SIMD"] = str(level)
+    r = subprocess.run([sys.executable, "-c", _SIMD_CHILD % (root, os.path.join(root, "tests")), str(level)], env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]

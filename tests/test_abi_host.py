@@ -270,3 +270,32 @@ def test_host_simd_bodies(level):
     r = subprocess.run([sys.executable, "-c", _SIMD_CHILD % (root, os.path.join(root, "tests")), str(level)], env=env, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_host_scalar_arithmetic_property():
+    """hypothesis: the folded wide reduction and the 256 x 256-bit product mod l (both bodies) against python integers over the whole
+    input range, with the boundary-heavy distributions hypothesis likes to draw"""
+    from hypothesis import given, settings, strategies as st
+
+    lib = bpp.ffi.lib()
+    L = orc.L
+    a_buf, g_buf = C.create_string_buffer(32), C.create_string_buffer(32)
+
+    @settings(max_examples=3000, deadline=None)
+    @given(st.integers(min_value=0, max_value=2**512 - 1))
+    def wide(x):
+        w = x.to_bytes(64, "little")
+        lib.bpp_host_sc_from_wide64(w, a_buf)
+        lib.bpp_host_sc_generic64(w, None, g_buf)
+        assert a_buf.raw == g_buf.raw == (x % L).to_bytes(32, "little")
+
+    @settings(max_examples=3000, deadline=None)
+    @given(st.integers(min_value=0, max_value=2**256 - 1), st.integers(min_value=0, max_value=2**256 - 1))
+    def mul(a, b):
+        ab, bb = a.to_bytes(32, "little"), b.to_bytes(32, "little")
+        lib.bpp_host_sc_mul64(ab, bb, a_buf)
+        lib.bpp_host_sc_generic64(ab, bb, g_buf)
+        assert a_buf.raw == g_buf.raw == (a * b % L).to_bytes(32, "little")
+
+    wide()
+    mul()

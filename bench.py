@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py — batched verification throughput of 64-bit Bulletproofs+ range proofs on B200 (BASELINE.json metric).
 
-One "step" = one pass of the verification hot path over one batch of synthetic proofs: BASELINE.json configs[1],
-"verify_batch of 1024 non-aggregated 64-bit proofs on 1 B200", issued as 4 reference calls of 256 proofs
-(RangeProof::verify_batch looks at 256 proofs per call, /root/reference/src/range_proof.rs:739-751).
-  value  : proofs/s with inputs resident in HBM (bpp_vbatch_run: replay -> decompress -> scalar prep -> segmented MSM -> verdicts)
-  e2e    : proofs/s through bpp_verify_chunks with HOST buffers (parsing, Fiat-Shamir, H2D, kernels, D2H inside the timing)
-  Steps are independent; they are issued from --lanes lanes (api.VerifierPool: one bpp_ctx + host thread each) so that
-  consecutive steps overlap on the GPU.  `one_batch_at_a_time` repeats the measurement with a single lane (latency).
-  N > 1  : one process per GPU (torchrun), every rank verifies its own 1024 proofs per step ("weak"), no collective
-           on the data path; barrier + max-over-ranks timing.
+Unit of work ("job") = BASELINE.json configs[1]: verify_batch of 1024 non-aggregated 64-bit proofs, issued as 4 reference calls
+of 256 (RangeProof::verify_batch looks at 256 proofs per call, /root/reference/src/range_proof.rs:739-751).  One STEP = `reps`
+independent jobs back to back (reps = ceil(2048 / steps), so that the K timed steps span >= 0.2 s whatever K the driver picks;
+`config.jobs_per_step`).
+  value  : proofs/s with inputs resident in HBM.  Jobs are verified the way the engine's coalescing queue verifies them: `pass_jobs`
+           jobs (16 x 1024 proofs = 64 reference calls) per device pass (bpp_vbatch_create_multi), `lanes` passes in flight.
+  e2e    : proofs/s through the queue's C-ABI entry points (bpp_vqueue_submit / bpp_vqueue_wait) with HOST buffers: every job's
+           proof bytes, commitments and transcripts are copied host->device and its statuses and advanced transcripts come back
+           inside the timed region.
+  one_batch_at_a_time / one_shot_4096 : latency of one 1024-proof job alone, and of 4096 proofs split over the GPUs of the run.
+  N > 1  : one process per GPU (torchrun), every rank verifies its own jobs ("weak"), no collective on the data path;
+           barrier + max-over-ranks timing.  extras.msm_sharded: the raw MSM sharded over the ranks (one 32-byte partial per GPU).
   --impl reference : the CPU restatement of the reference (oracle/, multi-threaded over independent verify_batch calls).
 Rank 0 prints ONE JSON line.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -24,8 +29,7 @@ import threading
 import time
 
 # Lanes are independent CUDA streams; by default the driver multiplexes all streams of a process onto 8 hardware work queues, which
-# falsely serialises kernels of different lanes (measured: 32 lanes 4.9 M -> 5.8 M proofs/s with 32 queues).  Must be set before the
-# CUDA context exists, i.e. before torch touches the device.
+# falsely serialises kernels of different lanes.  Must be set before the CUDA context exists, i.e. before torch touches the device.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,48 +39,128 @@ METRIC = "64-bit range proofs verified/sec (batched)"
 UNIT = "proofs/s"
 BIT_LENGTH, EXT = 64, 1
 CHUNK = 256
+JOB = 1024
+TARGET_JOBS = 2048                    # jobs in the timed region (>= 0.2 s at 8 M proofs/s)
 # algorithmic 32x32->64 multiplies (field mul = 72, field square = 44, scalar Montgomery mul = 96 + 32)
 MUL32_FE_MUL, MUL32_FE_SQ = 72, 44
 MUL32_DECODE = 257 * MUL32_FE_SQ + 25 * MUL32_FE_MUL          # Ristretto decode + affine-Niels entry, per point
 MUL32_MADD = 7 * MUL32_FE_MUL                                  # extended + affine-Niels mixed addition
+LABEL = b"BatchedRangeProofTest"                               # benches/range_proof.rs:49
 
 
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def make_workload(n_proofs, seed=8675309):
-    """n_proofs non-aggregated 64-bit proofs (value % 2^63, promise value/3, seed_nonce present: benches/range_proof.rs:206-292),
-    generated with the CPU oracle prover, chunks built in parallel threads."""
-    import workload
+def jobs_per_step(steps):
+    return max(1, math.ceil(TARGET_JOBS / max(1, steps)))
+
+
+def workload_config(args):
+    reps = jobs_per_step(args.steps)
+    return {"workload": "verify_batch of %d non-aggregated 64-bit proofs (aggregation 1, extension degree 1, minimum-value promises, seed nonces: "
+                        "benches/range_proof.rs:206-292) = %d reference calls of <=256 per job (BASELINE.json configs[1]); one step = %d independent "
+                        "jobs per GPU" % (JOB, JOB // CHUNK, reps),
+            "proofs_per_job": JOB, "jobs_per_step": reps, "proofs_per_step_per_gpu": JOB * reps, "bit_length": BIT_LENGTH, "extension_degree": EXT,
+            "action": "VerifyOnly",
+            "l2": "flushed: every lane overwrites a %d MiB device buffer on its stream before each device pass, inside the timed region"
+                  % int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144"))}
+
+
+# ------------------------------------------------------------------------------------------------ synthetic workload
+def seeded_inputs(n_proofs, seed):
+    """values, blindings, seed nonces and rng streams from SHAKE256(seed): the same bytes feed the device prover, the oracle and the
+    CPU baseline (value = u64 % 2^63, promise value / 3: benches/range_proof.rs:236, :249)"""
+    L = 2**252 + 27742317777372353535851937790883648493
+    xof = hashlib.shake_256(b"bpp-bench-%d" % seed).digest(n_proofs * (8 + 64 + 64))
+    vals, blinds, seeds = [], [], []
+    for i in range(n_proofs):
+        o = i * 136
+        vals.append(int.from_bytes(xof[o:o + 8], "little") % (1 << 63))
+        blinds.append([int.from_bytes(xof[o + 8:o + 72], "little") % (L - 1) + 1])
+        seeds.append(int.from_bytes(xof[o + 72:o + 136], "little") % (L - 1) + 1)
+    return vals, blinds, seeds
+
+
+def make_workload_device(api, params, n_proofs, seed):
+    """n_proofs non-aggregated 64-bit proofs made by the DEVICE prover (bpp_prove_batch) -> list of (commitment, min, seed, proof bytes)"""
+    vals, blinds, seeds = seeded_inputs(n_proofs, seed)
+    commits = params.gens.commit_batch(vals, blinds)
+    need = api.RangeProof.rng_bytes_needed(params, 1)
+    out = []
+    for lo in range(0, n_proofs, 2048):
+        hi = min(n_proofs, lo + 2048)
+        sts = [api.RangeStatement.init(params, [commits[i]], [vals[i] // 3], seeds[i]) for i in range(lo, hi)]
+        wits = [api.RangeWitness.init([api.CommitmentOpening(vals[i], blinds[i])]) for i in range(lo, hi)]
+        streams = [hashlib.shake_256(b"bench-rng-%d-%d" % (seed, i)).digest(need) for i in range(lo, hi)]
+        prs = api.RangeProof.prove_batch([api.Transcript(LABEL) for _ in range(lo, hi)], sts, wits, streams)
+        for i, p in zip(range(lo, hi), prs):
+            assert not isinstance(p, Exception), p
+            out.append((commits[i], vals[i] // 3, seeds[i], p.to_bytes()))
+    return out
+
+
+def make_workload_oracle(n_proofs, seed):
+    """the same proofs made by the CPU oracle prover (the reference arm runs where there may be no GPU)"""
+    import orc
     from concurrent.futures import ThreadPoolExecutor
 
-    n_chunks = (n_proofs + CHUNK - 1) // CHUNK
-    sizes = [min(CHUNK, n_proofs - c * CHUNK) for c in range(n_chunks)]
+    vals, blinds, seeds = seeded_inputs(n_proofs, seed)
+    op = orc.Params(BIT_LENGTH, 1, EXT)
+    t0 = orc.transcript_new(LABEL)
+
+    def one(i):
+        need = 32 * 9
+        st = orc.St(op, [op.commit(vals[i], blinds[i])], [vals[i] // 3], seeds[i])
+        stream = hashlib.shake_256(b"bench-rng-%d-%d" % (seed, i)).digest(need)
+        rc, pr, _ = orc.prove(t0, st, orc.Wit([vals[i]], [blinds[i]]), orc.Rng("buffer", data=stream))
+        assert rc == 0
+        return (st.commitments[0], vals[i] // 3, seeds[i], orc.proof_to_bytes(pr))
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        return list(ex.map(one, range(n_proofs)))
+
+
+def oracle_arrays(items, reps):
+    """orc_verify_chunks_mt arguments for `reps` copies of the job made of `items`"""
     import orc
 
-    params = orc.Params(BIT_LENGTH, 1, EXT)
-    with ThreadPoolExecutor(max_workers=min(n_chunks, os.cpu_count() or 1)) as ex:
-        cases = list(ex.map(lambda c: workload.make_case(BIT_LENGTH, [1] * sizes[c], EXT, promise="third", rng_seed=seed + c, params=params),
-                            range(n_chunks)))
-    return params, cases
+    op = orc.Params(BIT_LENGTH, 1, EXT)
+    sts, prs = [], []
+    for c, mn, sd, pb in items:
+        sts.append(orc.St(op, [c], [mn], sd))
+        rc, pr = orc.proof_from_bytes(pb)
+        assert rc == 0
+        prs.append(pr)
+    t0 = orc.transcript_new(LABEL)
+    n = len(items)
+    offs = [0]
+    for r in range(reps):
+        for lo in range(0, n, CHUNK):
+            offs.append(r * n + min(n, lo + CHUNK))
+    sa = (orc.Statement * (n * reps))(*([s.c for s in sts] * reps))
+    pa = (orc.Proof * (n * reps))(*(prs * reps))
+    tb = C.create_string_buffer(t0 * (n * reps), 203 * n * reps)
+    oa = (C.c_size_t * len(offs))(*offs)
+    codes = (C.c_int32 * (len(offs) - 1))()
+    keep = (op, sts, prs)
+    return tb, sa, pa, oa, codes, keep
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+    """samples nvidia-smi clocks / throttle reasons of the GPUs in use while the timed region runs"""
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices):
+        self.indices, self.rows, self.proc = indices, [], None
 
     def start(self):
-        if self.index == "off":
+        if not self.indices:
             return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            sel = [] if self.index is None else ["-i", str(self.index)]          # None: every GPU of the node from ONE process
-            self.proc = subprocess.Popen(["nvidia-smi"] + sel + ["--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -87,9 +171,7 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, windows=()):
-        """windows: (t0, t1) perf_counter intervals of the timed regions; samples inside them are preferred, else every sample taken
-        while the sampler ran (it runs from before the warm-up to after the last timed step, i.e. under load throughout)"""
-        if self.index == "off":
+        if not self.indices:
             return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -110,72 +192,116 @@ class ClockSampler:
             for nm, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_regions": len(inside)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "samples_inside_timed_regions": len(inside), "gpus_sampled": list(self.indices)}
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle's restatement of RangeProof::verify_batch, T threads over independent 256-proof calls."""
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_arm(items, steps, warmup, threads):
+    """the oracle's restatement of RangeProof::verify_batch, `threads` pthreads over independent 256-proof calls; one step = enough
+    copies of the 1024-proof job to occupy every core (a bounded sample of the GPU arm's step)"""
     import orc
 
-    threads = os.cpu_count() or 1
-    params, cases = make_workload(args.proofs)
-    reps = max(1, (threads + len(cases) - 1) // len(cases))       # enough independent calls to occupy every core
-    sts, prs, trs, offs = [], [], [], [0]
-    for _ in range(reps):
-        for c in cases:
-            sts += [s.c for s in c.statements]; prs += c.proofs; trs += c.transcripts
-            offs.append(len(prs))
-    n = len(prs)
-    sa = (orc.Statement * n)(*sts)
-    pa = (orc.Proof * n)(*prs)
-    tb = C.create_string_buffer(b"".join(trs), 203 * n)
-    oa = (C.c_size_t * len(offs))(*offs)
-    codes = (C.c_int32 * (len(offs) - 1))()
+    n_calls = (len(items) + CHUNK - 1) // CHUNK
+    reps = max(1, (threads + n_calls - 1) // n_calls)
+    tb, sa, pa, oa, codes, keep = oracle_arrays(items, reps)
     lib = orc.lib()
+    n = len(items) * reps
 
     def step():
-        sec = lib.orc_verify_chunks_mt(tb, sa, pa, oa, len(offs) - 1, orc.VERIFY_ONLY, threads, codes)
+        sec = lib.orc_verify_chunks_mt(tb, sa, pa, oa, len(oa) - 1, orc.VERIFY_ONLY, threads, codes)
         assert all(c == 0 for c in codes), list(codes)
         return sec
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-    total = sum(step() for _ in range(args.steps))
-    value = n * args.steps / total
-    sample = "%d proofs/step = %d verify_batch calls of %d (the %d-proof workload x%d), VerifyOnly, %d pthreads" % (
-        n, len(offs) - 1, CHUNK, args.proofs, reps, threads)
+    total = sum(step() for _ in range(steps))
+    sample = "%d steps x %d proofs = %d verify_batch calls of %d (the %d-proof job x%d), VerifyOnly, %d pthreads" % (
+        steps, n, len(oa) - 1, CHUNK, len(items), reps, threads)
+    return n * steps / total, 1e3 * total / steps, sample
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    items = make_workload_oracle(JOB, 8675309)
+    value, ms, sample = cpu_arm(items, args.steps, args.warmup, threads)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic", "impl": "reference",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of tari_bulletproofs_plus 0.4.1 + curve25519-dalek algorithms (no Rust toolchain in the image); not dalek itself"},
+                         "note": "C restatement of tari_bulletproofs_plus 0.4.1 + curve25519-dalek's serial algorithms (no Rust toolchain in the "
+                                 "image); not dalek itself -- its AVX2 backend would be an estimated 1.5-2x faster"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
-    return {"workload": "verify_batch of %d non-aggregated 64-bit proofs (aggregation 1, extension degree 1, minimum-value promises) "
-                        "per GPU per step, as %d reference calls of <=256 (BASELINE.json configs[1])" % (args.proofs, (args.proofs + CHUNK - 1) // CHUNK),
-            "proofs_per_step_per_gpu": args.proofs, "bit_length": BIT_LENGTH, "extension_degree": EXT, "action": "VerifyOnly",
-            "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay)",
-            "steps_in_flight": "independent steps are issued from `lanes_per_gpu` lanes (one bpp_ctx + host thread each) and overlap on the GPU; "
-                               "the K timed steps are bracketed once (barrier + synchronize + CUDA events on both sides)",
-            "l2": "flushed between timed steps: every lane overwrites a %d MiB device buffer on its stream before each of its steps, "
-                  "inside the timed region (inputs of a step are ~1.3 MB, far below L2)" % int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144"))}
+# ------------------------------------------------------------------------------------------------ secondary metrics
+def msm_inputs(eng, nn, dist_kind, tag):
+    """points: a 16 k-point set repeated (duplicates are legal MSM input); scalars by distribution"""
+    L = 2**252 + 27742317777372353535851937790883648493
+    uni = hashlib.shake_256(b"msm-points").digest(64 * min(nn, 1 << 14))
+    pts = eng.from_uniform(uni)
+    if dist_kind == "duplicated_points":
+        pts = pts[:32 * 64]                                                        # 64 distinct points
+    pts = (pts * ((nn * 32 + len(pts) - 1) // len(pts)))[: 32 * nn]
+    sc = bytearray(hashlib.shake_256(b"msm-scalars-%s" % tag).digest(32 * nn))
+    if dist_kind in ("uniform", "duplicated_points", "zeros5"):
+        for i in range(31, len(sc), 32):
+            sc[i] &= 0x0F                                                           # < 2^252 < l: canonical
+        if dist_kind == "zeros5":
+            z = bytes(32)
+            for i in range(0, nn, 20):
+                sc[32 * i:32 * i + 32] = z
+    elif dist_kind == "small64":
+        for i in range(nn):
+            sc[32 * i + 8:32 * i + 32] = bytes(24)
+    elif dist_kind == "prover_like":                                               # {0, 1, l - 1}
+        vals = [bytes(32), (1).to_bytes(32, "little"), (L - 1).to_bytes(32, "little")]
+        src = bytes(sc)
+        for i in range(nn):
+            sc[32 * i:32 * i + 32] = vals[src[32 * i] % 3]
+    return bytes(sc), pts
 
 
-def run_extras(eng, api, bpp, orc, args):
+def time_msm(bpp, eng, nn, sc, pts, msm_peak, hbm_gbs):
+    plan = bpp.pkg.MsmPlan(eng, pts)
+    plan.set_scalars(sc)
+    res = plan.run(True)
+    eng.phase_timing(True)                       # per-phase CUDA events of one run: sort / bucket sums / window reduction / Horner
+    plan.run(True)
+    ph = eng.phase_ms()
+    eng.phase_timing(False)
+    reps = 5 if nn <= (1 << 20) else 2
+    eng.timer_start()
+    for _ in range(reps):
+        plan.run(False)
+    t = eng.timer_stop() / reps
+    c = plan.window_bits
+    W = (252 + c - 1) // c
+    adds_mul32 = nn * W * MUL32_MADD              # bucket additions only (the algorithmic work of SURVEY.md 8d minus the reduction)
+    # sort phase, algorithmic bytes: the scalars are read by both digit passes (2 x 32 B), every non-zero digit is one 4-byte counter
+    # update per pass and one 4-byte record written once
+    sort_bytes = nn * (64 + 12 * W)
+    out = {"mpoints_per_s": nn / t / 1e3, "ms": t, "window_bits": c, "windows": W,
+           "achieved_tmul32_per_s": adds_mul32 / (t * 1e-3) / 1e12, "frac_of_int32_mul_peak": adds_mul32 / (t * 1e-3) / msm_peak,
+           "bucket_kernel": {"ms": ph["msm_bucket"], "achieved_tmul32_per_s": adds_mul32 / (ph["msm_bucket"] * 1e-3) / 1e12,
+                             "frac_of_int32_mul_peak": adds_mul32 / (ph["msm_bucket"] * 1e-3) / msm_peak},
+           "sort_phase": {"ms": ph["msm_sort"], "algorithmic_bytes": sort_bytes, "gb_per_s": sort_bytes / (ph["msm_sort"] * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": (sort_bytes / (ph["msm_sort"] * 1e-3) / 1e9 / hbm_gbs) if hbm_gbs else None},
+           "phase_ms": {k: ph[k] for k in ("msm_sort", "msm_bucket", "msm_reduce", "msm_combine")}}
+    plan.close()
+    return out, res
+
+
+def run_extras(eng, api, bpp, orc, args, hbm_gbs):
     """proving throughput (batched lock-step prover, C-ABI call with host buffers) and raw MSM throughput (device-resident
     points, scalars uploaded once), both on this GPU; CPU oracle beside the prover on a bounded sample"""
-    import hashlib
-
     out = {}
     # ---- prover: P non-aggregated 64-bit proofs (BASELINE.json configs[0] shape, batched), as `lanes` concurrent bpp_prove_batch
     # calls of P / lanes proofs each (one bpp_ctx + host thread per call: the host Fiat-Shamir of one call overlaps the device
@@ -184,11 +310,8 @@ def run_extras(eng, api, bpp, orc, args):
     per = P // PL
     ppool = api.VerifierPool(eng.device, BIT_LENGTH, 1, EXT, lanes=PL, blocking_waits=False)
     gp = ppool.lanes[0][1]
-    rng = orc.Rng("chacha", 4242)
-    vals = [rng.next_u64() % (1 << 63) for _ in range(P)]
-    blinds = [[rng.random_not_zero()] for _ in range(P)]
+    vals, blinds, seeds = seeded_inputs(P, 4242)
     commits = gp.gens.commit_batch(vals, blinds)
-    seeds = [rng.random_not_zero() for _ in range(P)]
     need = api.RangeProof.rng_bytes_needed(gp, 1)
     streams = [hashlib.shake_256(b"bench-rng-%d" % i).digest(need) for i in range(P)]
     packs = []
@@ -197,7 +320,7 @@ def run_extras(eng, api, bpp, orc, args):
         idx = range(li * per, (li + 1) * per)
         sts = [api.RangeStatement.init(prm, [commits[i]], [vals[i] // 3], seeds[i]) for i in idx]
         wits = [api.RangeWitness.init([api.CommitmentOpening(vals[i], blinds[i])]) for i in idx]
-        packs.append(api._PackedProve(prm, [api.Transcript(b"BatchedRangeProofTest") for _ in idx], sts, wits, [streams[i] for i in idx]))
+        packs.append(api._PackedProve(prm, [api.Transcript(LABEL) for _ in idx], sts, wits, [streams[i] for i in idx]))
 
     def prove_job(li, e, prm, i):
         packs[i].reset_transcripts()
@@ -217,7 +340,7 @@ def run_extras(eng, api, bpp, orc, args):
     n_cpu = 8
     for i in range(n_cpu):
         st = orc.St(op, [commits[i]], [vals[i] // 3], seeds[i])
-        rc, pr, _ = orc.prove(orc.transcript_new(b"BatchedRangeProofTest"), st, orc.Wit([vals[i]], [blinds[i]]), orc.Rng("buffer", data=streams[i]))
+        rc, pr, _ = orc.prove(orc.transcript_new(LABEL), st, orc.Wit([vals[i]], [blinds[i]]), orc.Rng("buffer", data=streams[i]))
         assert rc == 0 and orc.proof_to_bytes(pr) == proofs[i].to_bytes()
     cpu_s = (time.perf_counter() - t0) / n_cpu
     # algorithmic multiplies per proof on the fixed-base path: (2N + ext) + rounds * 2 * (1 + ext + N) + (2N + 1 + ext) + (1 + ext) table
@@ -235,41 +358,76 @@ def run_extras(eng, api, bpp, orc, args):
     ppool.close()
     # ---- raw MSM (BASELINE.json configs[4]), device-resident decoded points
     msm = {}
-    msm_peak, _ = eng.microbench(1, 2000)            # IMAD.HI issue rate (see the roofline object)
+    msm_peak, _ = eng.microbench(1, 2000)
     for lg in args.msm_log2:
         nn = 1 << lg
-        seed = hashlib.shake_256(b"msm-points").digest(64)
-        uni = hashlib.shake_256(seed).digest(64 * min(nn, 1 << 14))
-        pts = eng.from_uniform(uni)
-        pts = (pts * ((nn * 32 + len(pts) - 1) // len(pts)))[: 32 * nn]          # repeat a 16 k-point set (duplicates are legal MSM input)
-        plan = bpp.pkg.MsmPlan(eng, pts)
-        sc = hashlib.shake_256(b"msm-scalars-%d" % lg).digest(32 * nn)
-        sc = bytearray(sc)
-        for i in range(31, len(sc), 32):
-            sc[i] &= 0x0F                                                           # < 2^252 < l: canonical
-        plan.set_scalars(bytes(sc))
-        plan.run(True)
-        eng.phase_timing(True)                       # per-phase CUDA events of one run: sort / bucket sums / window reduction / Horner
-        plan.run(True)
-        ph = eng.phase_ms()
-        eng.phase_timing(False)
-        reps = 5 if lg <= 20 else 2
-        eng.timer_start()
-        for _ in range(reps):
-            plan.run(False)
-        t = eng.timer_stop() / reps
-        W = (252 + plan.window_bits - 1) // plan.window_bits
-        adds_mul32 = nn * W * MUL32_MADD              # bucket additions only (the algorithmic work of SURVEY.md 8d minus the reduction)
-        msm["2^%d" % lg] = {"mpoints_per_s": nn / t / 1e3, "ms": t, "window_bits": plan.window_bits, "windows": W,
-                            "achieved_tmul32_per_s": adds_mul32 / (t * 1e-3) / 1e12, "frac_of_int32_mul_peak": adds_mul32 / (t * 1e-3) / msm_peak,
-                            "bucket_kernel": {"ms": ph["msm_bucket"], "achieved_tmul32_per_s": adds_mul32 / (ph["msm_bucket"] * 1e-3) / 1e12,
-                                              "frac_of_int32_mul_peak": adds_mul32 / (ph["msm_bucket"] * 1e-3) / msm_peak},
-                            "phase_ms": {k: ph[k] for k in ("msm_sort", "msm_bucket", "msm_reduce", "msm_combine")}}
-        plan.close()
+        sc, pts = msm_inputs(eng, nn, "uniform", b"%d" % lg)
+        msm["2^%d" % lg], _ = time_msm(bpp, eng, nn, sc, pts, msm_peak, hbm_gbs)
     out["msm"] = msm
+    dists = {}
+    lg = args.msm_dist_log2
+    for kind in ("uniform", "prover_like", "small64", "zeros5", "duplicated_points"):
+        sc, pts = msm_inputs(eng, 1 << lg, kind, b"%d" % lg)
+        r, _ = time_msm(bpp, eng, 1 << lg, sc, pts, msm_peak, hbm_gbs)
+        dists[kind] = {k: r[k] for k in ("mpoints_per_s", "ms", "window_bits", "phase_ms")}
+    out["msm_scalar_distributions"] = {"points": "2^%d" % lg, "results": dists}
     return out
 
 
+def run_msm_sharded(eng, bpp, dist, torch, rank, world, sizes):
+    """raw MSM sharded over the ranks: rank r keeps [r N / G, (r + 1) N / G) device-resident, reduces it to ONE 32-byte
+    partial, the partials are gathered (all_gather of 32 B per rank) and summed on the host; rank 0 also runs the whole MSM alone and
+    the two results must be equal.  Every rank takes part (collective)."""
+    par = __import__("importlib").import_module("bulletproofs-plus_b200.parallel")
+    out = {}
+    for lg in sizes:
+        nn = 1 << lg
+        sc, pts = msm_inputs(eng, nn, "uniform", b"%d" % lg)
+        lo, hi = par.shard_range(nn, world, rank)
+        plan = bpp.pkg.MsmPlan(eng, pts[32 * lo:32 * hi])
+        plan.set_scalars(sc[32 * lo:32 * hi])
+        buf = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        gathered = torch.zeros(32 * world, dtype=torch.uint8, device="cuda")
+
+        def once():
+            partial = plan.run(True)
+            buf.copy_(torch.frombuffer(bytearray(partial), dtype=torch.uint8))
+            dist.all_gather_into_tensor(gathered, buf)
+            return par.sum_partials(eng, bytes(gathered.cpu().numpy()))
+
+        res = once()
+        reps = 5 if lg <= 20 else 3
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r2 = once()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        assert r2 == res
+        eng.timer_start()
+        for _ in range(reps):
+            plan.run(False)
+        dev_ms = eng.timer_stop() / reps
+        t = torch.tensor([dt, dev_ms * 1e-3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        plan.close()
+        single_ms = None
+        if rank == 0:
+            whole = bpp.pkg.MsmPlan(eng, pts)
+            whole.set_scalars(sc)
+            assert whole.run(True) == res, "sharded MSM differs from the single-GPU result"
+            eng.timer_start()
+            whole.run(False)
+            single_ms = eng.timer_stop()
+            whole.close()
+            out["2^%d" % lg] = {"gpus": world, "mpoints_per_s": nn / float(t[0]) / 1e6, "ms_end_to_end_max_over_ranks": float(t[0]) * 1e3,
+                                "ms_kernels_max_over_ranks": float(t[1]) * 1e3, "single_gpu_ms": single_ms, "equals_single_gpu_result": True}
+        dist.barrier()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ the B200 arm
 def run_b200(args, rank, local_rank, world):
     import torch
 
@@ -283,9 +441,8 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL prints its version banner to stdout (fd 1) when NCCL_DEBUG is set; stdout carries the one JSON line, so fd 1 points
-        # at stderr while the communicator comes up
-        os.environ.pop("NCCL_DEBUG", None)
+        # NCCL prints its banner to stdout (fd 1) when NCCL_DEBUG is set; stdout carries the one JSON line, so fd 1 points at stderr
+        # while the communicator comes up (NCCL_DEBUG itself is left alone: the driver reads the rank count from that log)
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
@@ -299,27 +456,16 @@ def run_b200(args, rank, local_rank, world):
             os.close(saved)
     api = bpp.pkg.api
     lib = bpp.ffi.lib()
-    S = max(1, min(args.lanes, args.steps))
     cores = os.cpu_count() or 1
-    # S independent lanes (bpp_ctx + host thread each) on this GPU; the host cores are shared by the ranks of the node
+    reps = jobs_per_step(args.steps)
+    n_jobs = args.steps * reps
+    K = max(1, args.pass_jobs)
+    S = max(1, args.lanes)
     htl = args.host_threads_per_lane or max(1, cores // (S * world))
-    blocking = (S > 1 and S * world >= cores) if args.blocking_waits < 0 else bool(args.blocking_waits)
-    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=blocking)
+    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=True)
     eng, params = pool.lanes[0]
-    params_o, cases = make_workload(args.proofs, seed=8675309 + 1000 * rank)
-
-    def build_calls(prm):
-        calls = []
-        for c in cases:
-            sts = [api.RangeStatement.init(prm, s.commitments, s.min_values, s.seed_nonce) for s in c.statements]
-            prs = [api.RangeProof.from_bytes(orc.proof_to_bytes(p)) for p in c.proofs]
-            trs = [api.Transcript(state=t) for t in c.transcripts]
-            calls.append((trs, sts, prs))
-        return calls
-
+    FLUSH = int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144")) << 20
     action = api.VerifyAction.VerifyOnly
-    FLUSH_MIB = int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144"))      # 151 MB > 126 MB of L2
-    FLUSH = FLUSH_MIB << 20
 
     def barrier():
         torch.cuda.synchronize()
@@ -327,33 +473,47 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # every lane owns its device-resident batch (bpp_vbatch: inputs in HBM) and its host-side argument block (e2e)
-    vbs = [api.VerifyBatch(prm, build_calls(prm), action) for _, prm in pool.lanes]
-    pks = [api._Packed(prm, build_calls(prm), action) for _, prm in pool.lanes]
-    t_init = bytes(pks[0].tbuf.raw)
-    for vb in vbs:
-        status, _ = vb.run()
-        assert status == [0] * len(cases), status
+    # ---------------- workload: K distinct jobs made by the device prover (different proofs on every rank)
+    items = make_workload_device(api, params, K * JOB, seed=8675309 + 1000 * rank)
+    t_label = api.Transcript(LABEL).state
 
-    # ---------------- device-resident arm (value): K steps over S lanes, L2 overwritten by every lane before every step
-    def dev_step(li, e, prm, i):
-        vb = vbs[li]
+    def job_calls(prm, j):
+        calls = []
+        for lo in range(j * JOB, (j + 1) * JOB, CHUNK):
+            part = items[lo:lo + CHUNK]
+            sts = [api.RangeStatement.init(prm, [c], [mn], sd) for c, mn, sd, _ in part]
+            prs = [api.RangeProof(pb, EXT, 6) for _, _, _, pb in part]
+            calls.append(([api.Transcript(state=t_label) for _ in part], sts, prs))
+        return calls
+
+    # ---------------- device-resident arm (value): every lane owns one resident pass of K jobs (bpp_vbatch_create_multi)
+    n_pass = (n_jobs + K - 1) // K
+    lane_pks = [[api._Packed(prm, job_calls(prm, j), action) for j in range(K)] for _, prm in pool.lanes]
+    lane_vb = []
+    for (e, prm), pks in zip(pool.lanes, lane_pks):
+        ptrs = (C.c_void_p * K)(*[C.addressof(pk.args) for pk in pks])
+        vb = C.c_void_p()
+        rc = lib.bpp_vbatch_create_multi(prm.gens.h, K, ptrs, C.byref(vb))
+        assert rc == 0, rc
+        st = (C.c_int32 * (K * (JOB // CHUNK)))()
+        lane_vb.append((vb, st))
+
+    def dev_pass(li, e, prm, i):
+        vb, st = lane_vb[li]
         if FLUSH:
             e.l2_flush(FLUSH)
-        rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
-        assert rc == 0 and all(vb.pk.status[c] == 0 for c in range(len(cases))), (rc, list(vb.pk.status))
+        rc = lib.bpp_vbatch_run(vb, st, None, None)
+        assert rc == 0 and not any(st), (rc, list(st))
 
-    # one nvidia-smi process per NODE (rank 0, all GPUs): eight of them polling at once stall the driver's submission path (measured:
-    # the 8-GPU device-resident arm dropped to 0.56 M proofs/s per GPU with one sampler per rank)
-    sampler = ClockSampler((local_rank if world == 1 else None) if rank == 0 else "off")
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])
     sampler.start()
-    pool.run(dev_step, S * args.warmup)
+    pool.run(dev_pass, S * args.warmup)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = pool.launch_count()
     t_wall0 = time.perf_counter()
     ev0.record()                       # the device is idle here (barrier above): ev0 precedes every kernel of the timed steps
-    pool.run(dev_step, args.steps)     # every C call returns after its stream has drained
+    pool.run(dev_pass, n_pass)         # every C call returns after its stream has drained
     torch.cuda.synchronize()
     ev1.record()
     ev1.synchronize()
@@ -362,180 +522,242 @@ def run_b200(args, rank, local_rank, world):
     t_wall = time.perf_counter() - t_wall0
     launches = pool.launch_count() - launches0
     win_dev = (t_wall0, t_wall0 + t_wall)
+    dev_jobs = n_pass * K
 
-    # ---------------- end-to-end arm (e2e): the C-ABI call with HOST buffers, K calls over S lanes
-    host_acc = {}
-
-    def e2e_step(li, e, prm, i, flush=True):
-        pk = pks[li]
-        C.memmove(pk.tbuf, t_init, len(t_init))          # `&mut Transcript`s are advanced by the call
-        if FLUSH and flush:
-            e.l2_flush(FLUSH)
-        rc = lib.bpp_verify_chunks(prm.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present)
-        assert rc == 0 and all(pk.status[c] == 0 for c in range(pk.k)), (rc, list(pk.status))
-
-    pool.run(e2e_step, S * args.warmup)
-    barrier()
-    t0 = time.perf_counter()
-    pool.run(e2e_step, args.steps)                       # synchronous calls: each returns after the D2H of its verdicts
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop([win_dev, (t0, t0 + e2e_s)])
-    barrier()
-    # ---------------- one batch at a time on one lane (latency; the per-kernel figures of the roofline come from here)
-    vb = vbs[0]
-    seq_ms = 0.0
-    n_seq = min(args.steps, 20)
+    # ---------------- one job at a time on one lane (latency) and the per-kernel durations of a full pass / of one job
     eng.set_throughput_mode(0)                             # alone: spin-wait, all host threads of this rank's share
     eng.set_host_threads(max(1, min(64, cores // world)))
-    for _ in range(n_seq):
-        eng.l2_flush(FLUSH or (144 << 20))
-        eng.sync()
-        eng.timer_start()
-        rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
-        seq_ms += eng.timer_stop()
-        assert rc == 0
-    # per-kernel durations: the same steps with CUDA events between the kernels (the events serialise the decompression
-    # with the scalar prep, which otherwise overlap on two streams)
-    phase_acc = {}
-    eng.phase_timing(True)
-    for _ in range(n_seq):
-        eng.l2_flush(FLUSH or (144 << 20))
-        rc = lib.bpp_vbatch_run(vb.h, vb.pk.status, vb.pk.masks, vb.pk.mask_present)
-        assert rc == 0
-        for k, v in eng.phase_ms().items():
-            phase_acc[k] = phase_acc.get(k, 0.0) + v
-    eng.phase_timing(False)
+    vb1 = api.VerifyBatch(params, job_calls(params, 0), action)
+    n_seq = 20
 
-    e2e_seq_s = 0.0
-    for _ in range(n_seq):
-        eng.l2_flush(FLUSH or (144 << 20))
-        eng.sync()
-        t0 = time.perf_counter()
-        e2e_step(0, eng, params, 0, flush=False)
-        e2e_seq_s += time.perf_counter() - t0
-        for k, v in eng.host_ms().items():
-            host_acc[k] = host_acc.get(k, 0.0) + v / n_seq
-    io_h2d, io_d2h = eng.io_bytes()
+    def time_alone(run, n):
+        ms = 0.0
+        for _ in range(n):
+            eng.l2_flush(FLUSH or (144 << 20))
+            eng.sync()
+            eng.timer_start()
+            run()
+            ms += eng.timer_stop()
+        return ms / n
+
+    def run_vb1():
+        rc = lib.bpp_vbatch_run(vb1.h, vb1.pk.status, None, None)
+        assert rc == 0 and not any(vb1.pk.status[c] for c in range(JOB // CHUNK))
+
+    def run_pass0():
+        dev_pass(0, eng, params, 0)
+
+    run_vb1()
+    seq_ms = time_alone(run_vb1, n_seq)
+    pass_ms = time_alone(lambda: (lib.bpp_vbatch_run(lane_vb[0][0], lane_vb[0][1], None, None)), 5)
+
+    def phases(run, n):
+        acc = {}
+        eng.phase_timing(True)
+        for _ in range(n):
+            eng.l2_flush(FLUSH or (144 << 20))
+            run()
+            for k, v in eng.phase_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / n
+        eng.phase_timing(False)
+        return acc
+
+    ph_job = phases(run_vb1, 5)
+    ph_pass = phases(lambda: lib.bpp_vbatch_run(lane_vb[0][0], lane_vb[0][1], None, None), 3)
+    # 4096 proofs in one shot over the GPUs of this run: every rank verifies 4096 / world proofs as ONE pass (north_star's target case)
+    shot_proofs = 4096 // world
+    shot_pks = [api._Packed(params, job_calls(params, j)[: max(1, min(JOB, shot_proofs - j * JOB) // CHUNK)], action)
+                for j in range((shot_proofs + JOB - 1) // JOB)]
+    ptrs = (C.c_void_p * len(shot_pks))(*[C.addressof(pk.args) for pk in shot_pks])
+    vb_shot = C.c_void_p()
+    assert lib.bpp_vbatch_create_multi(params.gens.h, len(shot_pks), ptrs, C.byref(vb_shot)) == 0
+    st_shot = (C.c_int32 * 64)()
+    lib.bpp_vbatch_run(vb_shot, st_shot, None, None)
+    barrier()
+    shot_ms = time_alone(lambda: lib.bpp_vbatch_run(vb_shot, st_shot, None, None), 10)
+    # the same end to end: host buffers -> verdicts (create + run + destroy of one multi-call pass)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        vbx = C.c_void_p()
+        assert lib.bpp_vbatch_create_multi(params.gens.h, len(shot_pks), ptrs, C.byref(vbx)) == 0
+        assert lib.bpp_vbatch_run(vbx, st_shot, None, None) == 0
+        lib.bpp_vbatch_destroy(vbx)
+    shot_e2e_ms = (time.perf_counter() - t0) * 1e3 / 10
+    lib.bpp_vbatch_destroy(vb_shot)
+    for vb, _ in lane_vb:
+        lib.bpp_vbatch_destroy(vb)
+    vb1.close()
     barrier()
 
-    # ---------------- secondary metrics (BASELINE.json: "proving at 1 GPU", "MSM Mpoints/s"), rank 0 only, not the headline
+    # ---------------- end-to-end arm (e2e): the coalescing queue with HOST buffers; jobs submitted from this thread
+    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=S, max_calls_per_pass=K, host_threads_per_lane=htl)
+    n_slots = min(n_jobs, 2 * S * K)
+    slots = [q.pack(job_calls(q.shape, j % K), action) for j in range(n_slots)]
+    t_init = bytes(slots[0].tbuf.raw)
+    tickets = [None] * n_slots
+
+    def e2e_run(count):
+        for j in range(count):
+            s = j % n_slots
+            pk = slots[s]
+            if tickets[s] is not None:
+                q.wait(tickets[s])
+                assert not any(pk.status[c] for c in range(pk.k)), list(pk.status)
+                C.memmove(pk.tbuf, t_init, len(t_init))          # `&mut Transcript`s were advanced by the call
+            tickets[s] = q.submit(pk)
+        for s in range(n_slots):
+            if tickets[s] is not None:
+                q.wait(tickets[s])
+                assert not any(slots[s].status[c] for c in range(slots[s].k))
+                C.memmove(slots[s].tbuf, t_init, len(t_init))
+                tickets[s] = None
+
+    e2e_run(min(n_jobs, args.warmup * S * K))
+    barrier()
+    qs0 = q.stats()
+    t0 = time.perf_counter()
+    e2e_run(n_jobs)                                      # returns after the last job's statuses and transcripts are back on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    qs1 = q.stats()
+    clocks = sampler.stop([win_dev, (t0, t0 + e2e_s)])
+    barrier()
+    # bytes one job moves (counted by the engine from the buffers it copies): one single-job call through the plain entry point
+    pk1 = api._Packed(params, job_calls(params, 0), action)
+    rc = lib.bpp_verify_chunks(params.gens.h, C.byref(pk1.args), pk1.status, pk1.masks, pk1.mask_present)
+    assert rc == 0
+    io_h2d, io_d2h = eng.io_bytes()
+    host_one = eng.host_ms()
+    # host cost of a coalesced pass (K jobs): create_multi alone, on this thread
+    ptrsK = (C.c_void_p * K)(*[C.addressof(pk.args) for pk in lane_pks[0]])
+    tc = []
+    for _ in range(5):
+        vbx = C.c_void_p()
+        t1 = time.perf_counter()
+        assert lib.bpp_vbatch_create_multi(params.gens.h, K, ptrsK, C.byref(vbx)) == 0
+        tc.append((time.perf_counter() - t1) * 1e3)
+        hm = eng.host_ms()
+        lib.bpp_vbatch_destroy(vbx)
+    q.close()
+    barrier()
+
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+
+    # ---------------- secondary metrics (BASELINE.json: "proving at 1 GPU", "MSM Mpoints/s")
     extras = {}
-    if rank == 0 and args.extras:
-        eng.set_host_threads(min(64, cores))           # the lanes shared the host cores; the prover call below is alone
-        try:
-            extras = run_extras(eng, api, bpp, orc, args)
-        except Exception as exc:                       # secondary metrics must not take the headline line down with them
-            extras = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if args.extras:
+        if world > 1:
+            try:
+                extras["msm_sharded"] = run_msm_sharded(eng, bpp, dist, torch, rank, world, args.msm_sharded_log2)
+            except Exception as exc:
+                extras["msm_sharded"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        if rank == 0:
+            eng.set_host_threads(min(64, cores))
+            try:
+                extras.update(run_extras(eng, api, bpp, orc, args, hbm_peak))
+            except Exception as exc:                       # secondary metrics must not take the headline line down with them
+                extras["error"] = "%s: %s" % (type(exc).__name__, exc)
+    barrier()
 
     # ---------------- reduce over ranks (max time)
-    times = torch.tensor([dev_ms, e2e_s, seq_ms, e2e_seq_s], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s, seq_ms, shot_ms, shot_e2e_ms, pass_ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max, seq_ms_max, e2e_seq_s_max = (float(x) for x in times)
+    dev_ms_max, e2e_s_max, seq_ms_max, shot_ms_max, shot_e2e_ms_max, pass_ms_max = (float(x) for x in times)
 
     # ---------------- roofline + cpu baseline (rank 0)
     if rank == 0:
-        n_pts = args.proofs * (3 + 2 * 6 + 1)
-        n_chunks = len(cases)
-        entries = n_chunks * (2 * BIT_LENGTH + EXT + 1) + args.proofs * (3 + 2 * 6 + 1)
-        per_launch = {k: v / n_seq for k, v in phase_acc.items()}
         # int32-multiply ceiling, measured now on this GPU: every 32x32->64 product needs one high-half multiply (IMAD.HI, the slow half:
-        # 8.6 T/s on this pool's B200s); the low halves issue on the other FMA sub-pipe (IMAD.lo alone: 18.6 T/s).  A single IMAD.WIDE
-        # per product is slower (6.1 T/s), which is why arith.cuh multiplies with mad.lo.cc / madc.hi.cc pairs.
+        # 8.6 T/s on this pool's B200s); the low halves issue on the other FMA sub-pipe (IMAD.lo alone: 18.6 T/s).
         peak_ops, _ = eng.microbench(1, 2000)
         wide_ops, _ = eng.microbench(2, 2000)
-        c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
-        work = {"decompress": n_pts * MUL32_DECODE,
-                "msm_bucket": entries * W * MUL32_MADD,
-                "msm_reduce": n_chunks * W * 2 * B * 9 * MUL32_FE_MUL,
-                "msm_combine": n_chunks * (W - 1) * (c_bits * (4 * MUL32_FE_MUL + 4 * MUL32_FE_SQ) + 9 * MUL32_FE_MUL),
-                "vprep_proof": args.proofs * (130 + 380) * 100,    # ~130 scalar products + one inversion (~380 at a^(l-2) cost), 100 mul32 each
-                "vprep_vector": args.proofs * (BIT_LENGTH * 4 + 3 * 14) * 100,      # 4 products per (proof, i) + three 8+8-entry tables
-                "vprep_weigh": (entries + args.proofs * 2 * BIT_LENGTH) * 100}
-        # Keccak-f[1600] of the transcript replay: ~130 64-bit logic / rotate ops per round = 260 32-bit ALU ops, 24 rounds, ~21
-        # permutations per 64-bit proof; its ceiling is the ALU pipe (LOP3 / IADD3 / SHF), measured by bpp_microbench(3)
         alu_ops, _ = eng.microbench(3, 2000)
-        alu_work = {"replay": args.proofs * 21 * 24 * 260}
-        per_kernel = {}
-        for k, ms in per_launch.items():
-            if ms <= 0:
-                continue
-            if k in work:
-                ach = work[k] / (ms * 1e-3) / 1e12
-                per_kernel[k] = {"ms": ms, "mul32": work[k], "achieved": ach, "peak": peak_ops / 1e12, "unit": "Tmul32/s", "frac": ach / (peak_ops / 1e12)}
-            elif k in alu_work:
-                ach = alu_work[k] / (ms * 1e-3) / 1e12
-                per_kernel[k] = {"ms": ms, "alu_ops": alu_work[k], "achieved": ach, "peak": alu_ops / 1e12, "unit": "Top32/s (ALU pipe)", "frac": ach / (alu_ops / 1e12)}
-            else:
-                per_kernel[k] = {"ms": ms}
-        # the dominant kernel = the one that carries the most algorithmic multiplies (and the most issued instructions in the ncu
-        # launch list): the MSM bucket accumulation.  Its duration is the live CUDA-event figure of the one-batch-at-a-time pass.
-        dominant = max(work, key=lambda k: work[k] if k in per_kernel else -1)
-        dom = per_kernel[dominant]
-        step_mul32 = sum(work[k] for k in work if k in per_kernel)
-        step_ms = dev_ms_max / args.steps
+        c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
+
+        def work_of(n_proofs):
+            n_chunks = n_proofs // CHUNK
+            n_pts = n_proofs * (3 + 2 * 6 + 1)
+            entries = n_chunks * (2 * BIT_LENGTH + EXT + 1) + n_proofs * (3 + 2 * 6 + 1)
+            return {"decompress": n_pts * MUL32_DECODE,
+                    "msm_bucket": entries * W * MUL32_MADD,
+                    "msm_reduce": n_chunks * W * 2 * B * 9 * MUL32_FE_MUL,
+                    "msm_combine": n_chunks * (W - 1) * (c_bits * (4 * MUL32_FE_MUL + 4 * MUL32_FE_SQ) + 9 * MUL32_FE_MUL),
+                    "vprep_proof": n_proofs * (130 + 380) * 100,    # ~130 scalar products + one inversion (~380 at a^(l-2) cost), 100 mul32 each
+                    "vprep_vector": n_proofs * (BIT_LENGTH * 4 + 3 * 14) * 100,      # 4 products per (proof, i) + three 8+8-entry tables
+                    "vprep_weigh": (entries + n_proofs * 2 * BIT_LENGTH) * 100}
+
+        def per_kernel_of(ph, n_proofs):
+            work = work_of(n_proofs)
+            # Keccak-f[1600] of the transcript replay: 197 ALU instructions per round (SASS of k_replay_sm), 24 rounds, ~21 permutations per proof
+            alu_work = {"replay": n_proofs * 21 * 24 * 197}
+            pk = {}
+            for k, ms in ph.items():
+                if ms <= 0:
+                    continue
+                if k in work:
+                    ach = work[k] / (ms * 1e-3) / 1e12
+                    pk[k] = {"ms": ms, "mul32": work[k], "achieved": ach, "peak": peak_ops / 1e12, "unit": "Tmul32/s", "frac": ach / (peak_ops / 1e12)}
+                elif k in alu_work:
+                    ach = alu_work[k] / (ms * 1e-3) / 1e12
+                    pk[k] = {"ms": ms, "alu_ops": alu_work[k], "achieved": ach, "peak": alu_ops / 1e12, "unit": "Top32/s (ALU pipe)", "frac": ach / (alu_ops / 1e12)}
+                else:
+                    pk[k] = {"ms": ms}
+            return pk, work
+
+        pk_pass, work_pass = per_kernel_of(ph_pass, K * JOB)
+        pk_job, _ = per_kernel_of(ph_job, JOB)
+        dominant = max(work_pass, key=lambda k: work_pass[k] if k in pk_pass else -1)
+        dom = pk_pass[dominant]
+        job_mul32 = sum(work_of(JOB).values())
+        ms_per_job = dev_ms_max / dev_jobs
         roof = {"bound": "int32-mul",
                 "bound_note": "int32-multiply issue rate (IMAD.HI, one per 32x32->64 product); the path is modular big-integer arithmetic, neither HBM- nor "
-                              "tensor-bound (north_star; DRAM traffic per step: a few MB, profiles/r01_ncu_summary.md)",
+                              "tensor-bound (north_star; DRAM traffic per 1024 proofs: a few MB, profiles/)",
                 "kernel": "k_" + dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
                 "peak_source": "bpp_microbench, measured in this run: IMAD.HI issue rate (one per 32x32->64 product; the IMAD.lo half issues on the "
                                "other FMA sub-pipe); LOP3+IADD3 rate for the Keccak kernel.  MEASURED_PEAKS.json has no integer figure",
                 "imad_wide_tops": wide_ops / 1e12,
-                "algorithmic_work_per_launch": work[dominant],
-                "kernel_ms": dom["ms"],
-                "whole_step": {"mul32_per_step": step_mul32, "ms_per_step_lanes_overlapped": step_ms,
-                               "achieved": step_mul32 / (step_ms * 1e-3) / 1e12, "unit": "Tmul32/s",
-                               "frac": step_mul32 / (step_ms * 1e-3) / peak_ops,
-                               "note": "all arithmetic kernels of a step over the measured time per step with %d lanes in flight" % S},
-                "longest_kernel_one_batch_alone": max(per_launch, key=per_launch.get),
-                "per_kernel": per_kernel,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` captures (profiles/r01_ncu_summary.md)
-                "traffic": {"replay": 961024, "msm_combine": 34304, "decompress": 588032, "vprep_proof": 519936, "msm_bucket": 3680000,
-                            "msm_reduce": 3780000, "vprep_vector": 917000}.get(dominant),
-                "traffic_unit": "bytes per launch (ncu, round 1)",
-                "note": "one 1024-proof batch alone is a chain of latency-bound kernels (2-30 % occupancy each); the lanes overlap "
-                        "independent batches, which is what `value` measures; per_kernel holds the one-batch-alone durations"}
-        hbm_peak = None
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
-        except Exception:
-            pass
-        roof["hbm_peak_gbs_measured"] = hbm_peak
-        # CPU baseline beside it: oracle, bounded sample
+                "algorithmic_work_per_launch": work_pass[dominant],
+                "kernel_ms": dom["ms"], "launch_covers_proofs": K * JOB,
+                "whole_step": {"mul32_per_job": job_mul32, "ms_per_job_lanes_overlapped": ms_per_job,
+                               "achieved": job_mul32 / (ms_per_job * 1e-3) / 1e12, "unit": "Tmul32/s",
+                               "frac": job_mul32 / (ms_per_job * 1e-3) / peak_ops,
+                               "note": "all arithmetic kernels of a job over the measured time per job with %d passes of %d jobs in flight" % (S, K)},
+                "one_pass_alone": {"proofs": K * JOB, "ms": pass_ms_max, "frac": K * job_mul32 / (pass_ms_max * 1e-3) / peak_ops},
+                "per_kernel": pk_pass, "per_kernel_one_job_alone": pk_job,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
+                "traffic": None, "traffic_note": "see profiles/r02_ncu_summary.md",
+                "hbm_peak_gbs_measured": hbm_peak}
+        # CPU baseline beside it: the oracle on this box's cores, a bounded sample of the same workload
         threads = os.cpu_count() or 1
-        reps = max(1, (threads + n_chunks - 1) // n_chunks)
-        sts, prs, trs, offs = [], [], [], [0]
-        for _ in range(reps):
-            for c in cases:
-                sts += [s.c for s in c.statements]; prs += c.proofs; trs += c.transcripts
-                offs.append(len(prs))
-        n = len(prs)
-        sa = (orc.Statement * n)(*sts); pa = (orc.Proof * n)(*prs)
-        tb = C.create_string_buffer(b"".join(trs), 203 * n)
-        oa = (C.c_size_t * len(offs))(*offs)
-        codes = (C.c_int32 * (len(offs) - 1))()
-        ol = orc.lib()
-        ol.orc_verify_chunks_mt(tb, sa, pa, oa, len(offs) - 1, orc.VERIFY_ONLY, threads, codes)
-        cpu_reps = 3
-        sec = sum(ol.orc_verify_chunks_mt(tb, sa, pa, oa, len(offs) - 1, orc.VERIFY_ONLY, threads, codes) for _ in range(cpu_reps))
-        cpu = {"value": n * cpu_reps / sec, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d x (%d proofs = %d verify_batch calls of %d), VerifyOnly, %d pthreads; C restatement, not dalek" % (
-                   cpu_reps, n, len(offs) - 1, CHUNK, threads)}
-        h2d, d2h = io_h2d, io_d2h          # counted by the engine from the buffers it copies (bpp_ctx_io_bytes)
+        cpu_value, _, cpu_sample = cpu_arm(items[:JOB], 3, 1, threads)
+        cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample + "; C restatement, not dalek"}
         cfg = workload_config(args)
-        cfg["lanes_per_gpu"] = S
         line = {
-            "metric": METRIC, "value": world * args.proofs * args.steps / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "metric": METRIC, "value": world * dev_jobs * JOB / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / dev_jobs * reps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
             "config": cfg, "host_cores": cores,
-            "e2e": {"value": world * args.proofs * args.steps / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": S, "host_threads_per_lane": htl, "blocking_waits": blocking,
-                    "one_call_at_a_time": {"value": world * args.proofs * n_seq / e2e_seq_s_max, "ms_per_call": 1e3 * e2e_seq_s_max / n_seq,
-                                           "host_ms_per_call": {k: round(v, 4) for k, v in host_acc.items()}}},
-            "one_batch_at_a_time": {"value": world * args.proofs * n_seq / (seq_ms_max * 1e-3), "ms_per_step": seq_ms_max / n_seq, "steps": n_seq,
-                                    "note": "one lane, L2 flushed outside the per-step CUDA-event bracket (the round-1 `value`)"},
+            "engine": {"lanes_per_gpu": S, "jobs_per_device_pass": K, "host_threads_per_lane": htl,
+                       "timed_jobs_per_gpu": dev_jobs, "timed_device_passes_per_gpu": n_pass,
+                       "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay_sm)",
+                       "workload_made_by": "device prover (bpp_prove_batch); K = %d distinct jobs per rank" % K},
+            "e2e": {"value": world * n_jobs * JOB / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                    "h2d_bytes_per_step": io_h2d * reps, "d2h_bytes_per_step": io_d2h * reps, "h2d_bytes_per_job": io_h2d, "d2h_bytes_per_job": io_d2h,
+                    "through": "bpp_vqueue_submit / bpp_vqueue_wait, one submitting thread per GPU, %d lanes, <= %d jobs per pass" % (S, K),
+                    "queue": {k: qs1[k] - qs0[k] for k in qs1},
+                    "host_ms_per_pass_of_%d_jobs" % K: {"create_multi_wall": statistics.median(tc), **{k: round(v, 4) for k, v in hm.items()}},
+                    "host_ms_one_job_call": {k: round(v, 4) for k, v in host_one.items()}},
+            "one_batch_at_a_time": {"value": world * JOB / (seq_ms_max * 1e-3), "ms_per_job": seq_ms_max, "jobs": n_seq,
+                                    "note": "one 1024-proof job alone on one lane, device-resident, L2 flushed outside the CUDA-event bracket"},
+            "one_shot_4096": {"proofs": shot_proofs * world, "gpus": world, "ms_device_resident": shot_ms_max, "ms_end_to_end": shot_e2e_ms_max,
+                              "value_device_resident": shot_proofs * world / (shot_ms_max * 1e-3), "value_end_to_end": shot_proofs * world / (shot_e2e_ms_max * 1e-3),
+                              "vs_cpu_baseline_end_to_end": shot_proofs * world / (shot_e2e_ms_max * 1e-3) / cpu_value,
+                              "note": "4096 proofs verified ONCE, split evenly over the GPUs of this run, max over ranks (north_star's target case)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
             "wall_s_timed_region": t_wall,
         }
@@ -549,17 +771,18 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=512)
-    ap.add_argument("--lanes", type=int, default=32, help="independent verification lanes (bpp_ctx + host thread) per GPU")
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--lanes", type=int, default=3, help="device passes in flight per GPU (one bpp_ctx + host thread each)")
+    ap.add_argument("--pass-jobs", type=int, default=16, help="1024-proof jobs merged into one device pass")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--host-threads-per-lane", type=int, default=0, help="0 = host cores / (lanes * ranks)")
-    ap.add_argument("--blocking-waits", type=int, default=-1, help="-1 = when lanes * ranks >= host cores")
-    ap.add_argument("--proofs", type=int, default=1024, help="proofs per GPU per step")
-    ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput on rank 0 (secondary metrics)")
+    ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput (secondary metrics)")
     ap.add_argument("--prove-batch", type=int, default=8192)
     ap.add_argument("--prove-lanes", type=int, default=8, help="concurrent bpp_prove_batch calls the proving batch is split into")
-    ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20, 22])
+    ap.add_argument("--msm-log2", type=int, nargs="*", default=[12, 16, 20, 22, 24])
+    ap.add_argument("--msm-dist-log2", type=int, default=20)
+    ap.add_argument("--msm-sharded-log2", type=int, nargs="*", default=[20, 22, 24])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()

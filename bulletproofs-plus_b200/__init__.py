@@ -211,10 +211,12 @@ class Gens:
     create_pedersen_gens_with_extension_degree(ext)) (/root/reference/src/range_parameters.rs:32-58,
     src/ristretto.rs:67-76)."""
 
-    def __init__(self, engine, bit_length, max_aggregation, extension_degree):
+    def __init__(self, engine, bit_length, max_aggregation, extension_degree, h_base=None, g_bases=None):
+        """h_base / g_bases: caller-made PedersenGens as 32-byte encodings (None = the reference's Ristretto constants)"""
         self.engine = engine
         self.h = C.c_void_p()
-        _chk(engine, _ffi.lib().bpp_gens_create(engine.h, bit_length, max_aggregation, extension_degree, C.byref(self.h)))
+        gb = b"".join(g_bases) if g_bases else None
+        _chk(engine, _ffi.lib().bpp_gens_create_with_bases(engine.h, bit_length, max_aggregation, extension_degree, h_base, gb, C.byref(self.h)))
         engine.adopt(self)
         self.bit_length, self.max_aggregation, self.extension_degree = bit_length, max_aggregation, extension_degree
 

@@ -58,6 +58,10 @@ class VerifyArgs(C.Structure):
     ]
 
 
+class VerifyChallenges(C.Structure):
+    _fields_ = [("challenges32", C.c_void_p), ("challenge_offsets", C.c_void_p), ("weights32", C.c_void_p)]
+
+
 class ProveArgs(C.Structure):
     _fields_ = [
         ("n_proofs", C.c_size_t),
@@ -127,7 +131,20 @@ def lib():
         "bpp_pedersen_commit_batch": (i32, [vp, sz, vp, cp, i32, cp]),
         "bpp_verify_chunks": (i32, [vp, P(VerifyArgs), vp, vp, vp]),
         "bpp_vbatch_create": (i32, [vp, P(VerifyArgs), P(vp)]),
+        "bpp_vbatch_create_multi": (i32, [vp, sz, vp, P(vp)]),
+        "bpp_vbatch_call_count": (sz, [vp]),
+        "bpp_vbatch_transcripts_call": (i32, [vp, sz, vp]),
+        "bpp_verify_chunks_ch": (i32, [vp, P(VerifyArgs), P(VerifyChallenges), vp, vp, vp]),
         "bpp_vbatch_run": (i32, [vp, vp, vp, vp]),
+        "bpp_vbatch_run_multi": (i32, [vp, vp, vp, vp]),
+        "bpp_gens_create_with_bases": (i32, [vp, i32, i32, i32, cp, cp, P(vp)]),
+        "bpp_vqueue_create": (i32, [i32, i32, i32, i32, cp, cp, i32, i32, i32, P(vp)]),
+        "bpp_vqueue_destroy": (None, [vp]),
+        "bpp_vqueue_submit": (i32, [vp, P(VerifyArgs), vp, vp, vp, P(C.c_uint64)]),
+        "bpp_vqueue_wait": (i32, [vp, C.c_uint64]),
+        "bpp_vqueue_verify": (i32, [vp, P(VerifyArgs), vp, vp, vp]),
+        "bpp_vqueue_stats": (i32, [vp, P(C.c_uint64)]),
+        "bpp_vqueue_lanes": (i32, [vp]),
         "bpp_vbatch_transcripts": (i32, [vp, vp]),
         "bpp_vbatch_destroy": (None, [vp]),
         "bpp_ctx_set_replay_mode": (i32, [vp, i32]),

@@ -361,10 +361,16 @@ class _Packed:
                 raise EngineError(_ffi.INVALID_ARGUMENT, "Range statements and proofs length mismatch")
             for t, s, p in zip(transcripts, statements, proofs):
                 g = s.generators.gens
-                # verify_statements_and_generators_consistency (range_proof.rs:637-705): every statement must carry the
-                # same generators; with device-resident tables that is an identity/parameter comparison
-                if g is not params.gens and (g.bit_length, g.extension_degree) != (params.gens.bit_length, ext):
-                    raise EngineError(_ffi.INVALID_ARGUMENT, "Inconsistent generators in batch statement")
+                # verify_statements_and_generators_consistency (range_proof.rs:637-705): every statement must carry the same G, H,
+                # bit length, extension degree and Gi / Hi vectors.  Device-resident tables are compared by handle first; statements
+                # built on ANOTHER handle are compared by parameters and by the encodings of their Pedersen bases (Gi / Hi are a
+                # function of (bit length, aggregation factor) alone: generators/bulletproof_gens.rs:83-112)
+                if g is not params.gens:
+                    if (g.bit_length, g.extension_degree) != (params.gens.bit_length, ext):
+                        raise EngineError(_ffi.INVALID_ARGUMENT, "Inconsistent generators in batch statement")
+                    if hasattr(g, "point") and hasattr(params.gens, "point"):
+                        if g.point(0) != params.gens.point(0) or any(g.point(1, k) != params.gens.point(1, k) for k in range(ext)):
+                            raise EngineError(_ffi.INVALID_ARGUMENT, "Inconsistent generator point in batch statement")
                 b = p.to_bytes()
                 pbytes.append(b)
                 proof_offsets.append(proof_offsets[-1] + len(b))
@@ -407,9 +413,11 @@ class _Packed:
         self.masks = C.create_string_buffer(max(1, 32 * n * ext))
         self.mask_present = C.create_string_buffer(max(1, n))
 
-    def results(self):
-        for i, t in enumerate(self.transcripts):
-            t.state = self.tbuf.raw[_ffi.TRANSCRIPT_BYTES * i: _ffi.TRANSCRIPT_BYTES * (i + 1)]
+    def results(self, update_transcripts=True):
+        if update_transcripts:
+            raw = self.tbuf.raw
+            for i, t in enumerate(self.transcripts):
+                t.state = raw[_ffi.TRANSCRIPT_BYTES * i: _ffi.TRANSCRIPT_BYTES * (i + 1)]
         status = [self.status[c] for c in range(self.k)]
         out = []
         for c in range(self.k):
@@ -460,6 +468,91 @@ class VerifyBatch:
             self.close()
         except Exception:
             pass
+
+
+def verify_chunks_ch(params, calls, challenges, weights, action):
+    """bpp_verify_chunks_ch: the caller keeps the Merlin transcripts and hands over, per proof, the challenges [y, z, e, e_0..]
+    (list of ints per proof) and the batch weight (int).  calls as in verify_chunks (transcripts are ignored)."""
+    pk = _Packed(params, calls, action)
+    flat = [c for ch in challenges for c in ch]
+    offs = [0]
+    for ch in challenges:
+        offs.append(offs[-1] + len(ch))
+    cbuf = C.create_string_buffer(b"".join(_sc(c) for c in flat), max(1, 32 * len(flat)))
+    wbuf = C.create_string_buffer(b"".join(_sc(w) for w in weights), max(1, 32 * len(weights)))
+    obuf = _u64arr(offs)
+    vc = _ffi.VerifyChallenges(C.addressof(cbuf), C.addressof(obuf), C.addressof(wbuf))
+    rc = _ffi.lib().bpp_verify_chunks_ch(params.gens.h, C.byref(pk.args), C.byref(vc), pk.status, pk.masks, pk.mask_present)
+    _chk(params.gens.engine, rc)
+    return pk.results(update_transcripts=False)
+
+
+class VerifyQueue:
+    """bpp_vqueue: callers submit verify_batch calls, a few lanes verify whatever is waiting as ONE device pass each
+    (include/bpp_b200.h, csrc/engine_queue.cpp).  Results are those of verify_chunks on each call alone."""
+
+    def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=3, max_calls_per_pass=16, host_threads_per_lane=0,
+                 h_base=None, g_bases=None):
+        self.h = C.c_void_p()
+        gb = b"".join(g_bases) if g_bases else None
+        rc = _ffi.lib().bpp_vqueue_create(device, bit_length, max_aggregation, int(extension_degree), h_base, gb, lanes, max_calls_per_pass,
+                                          host_threads_per_lane, C.byref(self.h))
+        if rc:
+            self.h = C.c_void_p()
+            raise EngineError(rc, "bpp_vqueue_create")
+        self.shape = _QueueShape(bit_length, max_aggregation, int(extension_degree))
+
+    def submit(self, packed):
+        """packed: a _Packed kept alive by the caller until wait() returns"""
+        t = C.c_uint64()
+        rc = _ffi.lib().bpp_vqueue_submit(self.h, C.byref(packed.args), packed.status, packed.masks, packed.mask_present, C.byref(t))
+        if rc:
+            raise EngineError(rc, "bpp_vqueue_submit")
+        return t.value
+
+    def wait(self, ticket):
+        rc = _ffi.lib().bpp_vqueue_wait(self.h, ticket)
+        if rc:
+            raise EngineError(rc, "bpp_vqueue_wait")
+
+    def pack(self, calls, action):
+        return _Packed(self.shape, calls, action)
+
+    def verify_many(self, batches, action=VerifyAction.VerifyOnly):
+        """batches: list of `calls` (each a list of (transcripts, statements, proofs)); all submitted at once, then waited for.
+        Returns [(status per call, masks per call)] in input order; transcripts are advanced in place."""
+        pks = [self.pack(calls, action) for calls in batches]
+        tickets = [self.submit(pk) for pk in pks]
+        for t in tickets:
+            self.wait(t)
+        return [pk.results() for pk in pks]
+
+    def stats(self):
+        arr = (C.c_uint64 * 5)()
+        _ffi.lib().bpp_vqueue_stats(self.h, arr)
+        return dict(zip(("passes", "calls", "proofs", "kernels", "graph_launches"), [int(x) for x in arr]))
+
+    def close(self):
+        if self.h:
+            _ffi.lib().bpp_vqueue_destroy(self.h)
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _QueueShape:
+    """what _Packed needs to know about a parameter set when there is no single Gens handle (the queue's lanes hold one each)"""
+
+    class _G:
+        pass
+
+    def __init__(self, bit_length, max_aggregation, extension_degree):
+        self.gens = self._G()
+        self.gens.bit_length, self.gens.max_aggregation, self.gens.extension_degree = bit_length, max_aggregation, extension_degree
 
 
 class VerifierPool:

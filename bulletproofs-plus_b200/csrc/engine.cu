@@ -21,6 +21,7 @@ int32_t cuda_fail(bpp_ctx *ctx, cudaError_t e, const char *where) {
     return BPP_ERR_CUDA;
 }
 bool host_sc_is_canonical(const uint8_t *b32) {
+    if (b32[31] < 0x10) return true;            // < 2^252 < l: the usual case costs one compare
     uint32_t w[8];
     memcpy(w, b32, 32);
     return sc_is_canonical_words(w);
@@ -394,6 +395,12 @@ void bpp_msm_plan_destroy(bpp_msm_plan *pl) {
 
 // ------------------------------------------------------------------------------------------------ generators
 int32_t bpp_gens_create(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree, bpp_gens **out) {
+    return bpp_gens_create_with_bases(ctx, bit_length, max_aggregation, extension_degree, nullptr, nullptr, out);
+}
+// RangeParameters::init(bit_length, aggregation_factor, pc_gens) with caller-made PedersenGens (range_parameters.rs:32-58,
+// generators/pedersen_gens.rs:25-36): h_base / g_base_vec as encodings, nullptr = the reference's Ristretto constants
+int32_t bpp_gens_create_with_bases(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree,
+                                   const uint8_t *h_base32_or_null, const uint8_t *g_bases32_or_null, bpp_gens **out) {
     if (!ctx || !out) return BPP_INVALID_ARGUMENT;
     *out = nullptr;
     // RangeParameters::init, range_parameters.rs:32-58
@@ -442,9 +449,34 @@ int32_t bpp_gens_create(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregatio
     cudaMemcpyAsync(d_h_in, BASEPOINT, 32, cudaMemcpyHostToDevice, st);
     launch_decompress(st, 1, (const uint32_t *)d_h_in, g->d_table.as<aniels>() + nh, nullptr, ctx->d_out.as<uint32_t>() + 8 * nh, nullptr);
     ctx->launches += 2;
+    // caller-supplied Pedersen bases replace the derived ones: decoded into the same table slots (G at 2nm + k, H at 2nm + ext)
+    uint8_t custom_ok[BPP_MAX_EXT + 1];
+    memset(custom_ok, 1, sizeof custom_ok);
+    const size_t n_custom = (g_bases32_or_null ? (size_t)extension_degree : 0) + (h_base32_or_null ? 1 : 0);
+    if (n_custom) {
+        if ((e = ctx->d_in2.ensure(32 * (BPP_MAX_EXT + 1))) != cudaSuccess || (e = ctx->d_flags.ensure(BPP_MAX_EXT + 1)) != cudaSuccess) return bail(e, "gens staging");
+        uint8_t *d_c = ctx->d_in2.as<uint8_t>();
+        if (g_bases32_or_null) {
+            cudaMemcpyAsync(d_c, g_bases32_or_null, 32 * (size_t)extension_degree, cudaMemcpyHostToDevice, st);
+            launch_decompress(st, (size_t)extension_degree, (const uint32_t *)d_c, g->d_table.as<aniels>() + 2 * g->nm, ctx->d_flags.as<uint8_t>(),
+                              ctx->d_out.as<uint32_t>() + 8 * (2 * g->nm), nullptr);
+            ctx->launches++;
+        }
+        if (h_base32_or_null) {
+            cudaMemcpyAsync(d_c + 32 * BPP_MAX_EXT, h_base32_or_null, 32, cudaMemcpyHostToDevice, st);
+            launch_decompress(st, 1, (const uint32_t *)(d_c + 32 * BPP_MAX_EXT), g->d_table.as<aniels>() + nh, ctx->d_flags.as<uint8_t>() + BPP_MAX_EXT,
+                              ctx->d_out.as<uint32_t>() + 8 * nh, nullptr);
+            ctx->launches++;
+        }
+        if (g_bases32_or_null) cudaMemcpyAsync(custom_ok, ctx->d_flags.p, (size_t)extension_degree, cudaMemcpyDeviceToHost, st);
+        if (h_base32_or_null) cudaMemcpyAsync(custom_ok + BPP_MAX_EXT, ctx->d_flags.as<uint8_t>() + BPP_MAX_EXT, 1, cudaMemcpyDeviceToHost, st);
+    }
     cudaMemcpyAsync(g->enc.data(), ctx->d_out.p, 32 * total, cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(e, "gens derive");
     if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "gens derive");
+    for (uint8_t f : custom_ok)
+        if (!f) { g->d_table.release(); delete g; return fail(ctx, BPP_INVALID_ARGUMENT, "Pedersen base is not the canonical encoding of a point"); }
+    g->custom_bases = n_custom != 0;
     *out = g;
     return BPP_OK;
 }
@@ -589,7 +621,9 @@ int32_t bpp_proof_check_bytes(const uint8_t *bytes, size_t len, int32_t *extensi
     if (!host_sc_is_canonical(p) || !host_sc_is_canonical(p + 32)) return BPP_INVALID_ARGUMENT;
     size_t rest = len - need;
     if (rest == 0 || rest % 64 != 0) return BPP_INVALID_LENGTH;
-    if (rest / 64 >= 32) return BPP_SIZE_OVERFLOW;
+    // any number of (L, R) pairs parses (from_bytes has no cap); verify rejects rounds that do not match n * m where the reference
+    // does (range_proof.rs:875-888: InvalidLength, SizeOverflow from 64 rounds on)
+    if (rest / 64 > 0x7fffffff) return BPP_SIZE_OVERFLOW;
     if (extension_degree) *extension_degree = ext;
     if (rounds) *rounds = (int32_t)(rest / 64);
     return BPP_OK;

@@ -96,6 +96,7 @@ struct bpp_gens {
     bpp::DevBuf d_table;                 // aniels[2*nm + ext + 1]: Gi | Hi | G | H
     bpp::DevBuf d_fb;                    // fixed-base window tables over the same generators (k_fb.cu), built on first use
     bpp::FbShape fb = {0, 0, 0, 0};
+    bool custom_bases = false;           // Pedersen bases supplied by the caller (bpp_gens_create_with_bases)
     int fb_state = 0;                    // 0 = not built, 1 = ready, -1 = over the memory budget (callers use the folding path)
     std::vector<uint8_t> enc;            // (2*nm + ext + 1) x 32 B compressed, same order
     const uint8_t *gi(size_t i) const { return enc.data() + 32 * i; }

@@ -1,21 +1,22 @@
-// Batch verification entry points: bpp_vbatch_create / bpp_vbatch_run / bpp_vbatch_transcripts / bpp_verify_chunks.
+// Batch verification entry points: bpp_vbatch_create[_multi] / bpp_vbatch_run / bpp_vbatch_transcripts / bpp_verify_chunks[_ch].
 //
 // Restates the control flow of RangeProof::verify_batch -> verify (/root/reference/src/range_proof.rs:712-1065):
 // argument checks (:719-734), first-256 truncation (:739-751), consistency (:610-709), loop 1 = Fiat-Shamir replay of every
 // proof's transcript (:816-850), the sequential verifier-weight transcript (:811, :849-853, :894), loop 2 (:856-1033) and the
-// single merged multiscalar check (:1039-1062).  Device pipeline of one call (K chunks = K reference calls):
+// single merged multiscalar check (:1039-1062).  One PASS verifies any number of reference calls ("chunks") of any number of
+// callers (bpp_vbatch_create_multi: the coalescing front end engine_queue.cpp merges queued calls into one pass):
 //
-//   stream A:  [K-REPLAY]  ->  K-VPREP A, B (weight-free)  ................  K-VPREP W, C  ->  K-MSM (segmented)  ->  identity test
-//   stream B:  K-DECOMPRESS ...........................................................^ (joins before the bucket sums)
-//   host    :  (wbytes D2H) -> weight transcripts per chunk, in parallel -> weights H2D ^
+//   host    :  header parse + statement checks -> memcpy of the callers' raw byte arrays into ONE pinned blob -> one H2D copy
+//   stream A:  K-REPLAY -> D2H(wbytes, flags, transcripts) | K-VPREP proof, vector (weight-free) .... K-VPREP weight, reduce -> K-MSM -> verdicts
+//   stream B:  K-DECOMPRESS (straight from the proof bytes) ..........................................^ (joins before the bucket sums)
+//   host    :  ............ verifier-weight transcripts per chunk (4 chunks in lock-step) -> weights H2D ^
 //
-// Loop 1 runs on the device by default (k_replay.cu); `bpp_ctx_set_replay_mode(ctx, 0)` keeps it on host threads, which is
-// the split BASELINE.json's north_star describes; both produce bit-identical results (tests run both).  The weight
-// transcript is inherently sequential (one Keccak-f per weight) and stays on the host in both modes, overlapped with the
-// weight-free part of the scalar prep (four chunks of equal length hash in lock-step through a vectorised four-way Keccak-f,
-// host_keccak4.cpp).  Error precedence of the reference is reproduced when the per-chunk status is resolved after the device
-// returns.  The pass is normally replayed as three captured CUDA graphs (see "CUDA graphs" below); independent calls overlap
-// when issued from several ctxs ("lanes", api.VerifierPool).
+// The device reads proofs, commitments and transcripts where the callers' buffers put them (rawld.cuh): the host neither gathers
+// points nor builds index lists (round 1 did both: 0.12 ms of host time per 1024 proofs, the limiter of the 8-GPU runs).
+// Loop 1 runs on the device by default (k_replay.cu); `bpp_ctx_set_replay_mode(ctx, 0)` keeps it on host threads (BASELINE.json
+// north_star's split) and bpp_verify_chunks_ch takes the challenges and weights from a caller that keeps merlin itself; all
+// three produce bit-identical results.  Error precedence of the reference is reproduced when the per-chunk status is resolved
+// after the device returns.  The pass is replayed as three captured CUDA graphs (see "CUDA graphs" below).
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -32,29 +33,30 @@ namespace {
 
 struct HProof {
     int32_t pre_rc = 0;        // from_bytes / RangeStatement::init class errors
-    int32_t loop2_rc = 0;      // host-known loop-2 error: InvalidLength when 2^rounds != n*m (:886-888)
+    int32_t loop2_rc = 0;      // host-known loop-2 error: InvalidLength / SizeOverflow when 2^rounds != n*m (:875-888)
     int ext = 0, rounds = 0;
     uint32_t m = 0;
-    const uint8_t *bytes = nullptr;   // serialised proof
-    bool has_seed = false;
-    uint8_t seed[32];
+    const uint8_t *bytes = nullptr;   // serialised proof in the caller's buffer (valid during create only)
+    bool has_seed = false, looked = false;
     uint32_t pt_off = 0, n_pts = 0;   // slots in the point table: [A, A1, B, L.., R.., V..]
-    const uint8_t *d1() const { return bytes + 1; }
-    const uint8_t *a() const { return bytes + 1 + 32 * ext; }
-    const uint8_t *a1() const { return a() + 32; }
-    const uint8_t *b() const { return a() + 64; }
-    const uint8_t *r1() const { return a() + 96; }
-    const uint8_t *s1() const { return a() + 128; }
-    const uint8_t *li(int j) const { return a() + 160 + 64 * j; }
-    const uint8_t *ri(int j) const { return a() + 192 + 64 * j; }
+    uint32_t call = 0;                // which call of the pass
+    size_t local = 0;                 // index inside its call
 };
 
 struct HChunk {
-    size_t lo = 0, hi = 0;     // proofs looked at: [lo, hi) (hi - lo <= 256)
+    size_t lo = 0, hi = 0, end = 0;   // proofs looked at: [lo, hi) (hi - lo <= 256); the caller's chunk is [lo, end)
     int32_t pre_rc = 0;        // empty batch / from_bytes / statement / consistency errors
     bool computable = false;   // no host-known error: device prep + MSM (or mask recovery) runs
     uint32_t max_mn = 0;
     uint32_t entry_off = 0, n_entries = 0;
+};
+
+// one caller's bpp_verify_args inside a pass
+struct HCall {
+    bpp_verify_args a;                // copy of the struct; its pointers are only dereferenced inside create
+    const bpp_verify_challenges *ch = nullptr;
+    size_t proof0 = 0, chunk0 = 0, commit0 = 0, raw0 = 0;      // first proof / chunk / commitment / raw byte of this call in the pass
+    size_t raw_base = 0;              // a.proof_offsets[0]
 };
 
 inline bool is_zero32(const uint8_t *p) { return replay_is_zero32(p); }
@@ -78,13 +80,13 @@ void nonce(const uint8_t seed[32], const char *label, bool have_j, uint32_t j, b
 // device + pinned buffers of one verification pass; pooled per ctx so that repeated calls do not pay cudaMalloc /
 // cudaMallocHost / cudaFree every time (grow-only, returned to the pool by bpp_vbatch_destroy)
 struct VWork {
-    DevBuf d_blob, d_tab, d_ok, d_mscal, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident, d_weights, d_wmont, d_mid;
-    PinBuf h_blob, h_out, h_mid, h_weights;
+    DevBuf d_blob, d_tab, d_ok, d_mscal, d_pidx, d_chal, d_contrib, d_hg, d_pervec, d_masks, d_scratch, d_res, d_ident, d_weights, d_wmont, d_mid;
+    PinBuf h_blob, h_out, h_mid, h_weights, h_chal;
     void release() {
-        for (DevBuf *b : {&d_blob, &d_tab, &d_ok, &d_mscal, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident, &d_weights,
-                          &d_wmont, &d_mid})
+        for (DevBuf *b : {&d_blob, &d_tab, &d_ok, &d_mscal, &d_pidx, &d_chal, &d_contrib, &d_hg, &d_pervec, &d_masks, &d_scratch, &d_res, &d_ident,
+                          &d_weights, &d_wmont, &d_mid})
             b->release();
-        h_blob.release(); h_out.release(); h_mid.release(); h_weights.release();
+        h_blob.release(); h_out.release(); h_mid.release(); h_weights.release(); h_chal.release();
     }
 };
 
@@ -92,18 +94,19 @@ struct bpp_vbatch {
     bpp_gens *g = nullptr;
     int32_t action = BPP_VERIFY_ONLY;
     bool device_replay = true;
-    size_t n_proofs = 0, n_chunks = 0;
+    bool caller_challenges = false;      // bpp_verify_chunks_ch: loop 1 and the weights were made by the caller
+    size_t n_proofs = 0, n_chunks = 0, n_commit = 0;
     std::vector<HProof> hp;
     std::vector<HChunk> hc;
-    std::vector<uint64_t> chunk_offsets;
-    uint32_t n_pts = 0, n_entries = 0, total_vec = 0, max_static = 0, max_rounds = 0;
-    bool any_msm = false, any_masks = false, any_replay = false;
+    std::vector<HCall> calls;
+    uint32_t n_pts = 0, n_entries = 0, n_chal = 0, max_static = 0, max_rounds = 0;
+    bool any_msm = false, any_masks = false, any_replay = false, any_vec = false;
     bool ran = false;
     MsmShape shape;
     VWork *w = nullptr;
     // all inputs travel as ONE pinned blob -> ONE H2D copy; these are the section offsets inside it
-    size_t o_enc = 0, o_proofs = 0, o_chunks = 0, o_vecoff = 0, o_pscal = 0, o_chal = 0, o_minv = 0, o_minp = 0, o_nonces = 0, o_pidx = 0,
-           o_segoff = 0, o_tstate = 0, o_hg = 0, o_wtinit = 0, blob_bytes = 0;
+    size_t o_proofs = 0, o_chunks = 0, o_ptoff = 0, o_segoff = 0, o_hg = 0, o_wtinit = 0, o_minv = 0, o_minp = 0, o_commit = 0, o_raw = 0,
+           o_tstate = 0, o_nonces = 0, blob_bytes = 0;
     // mid-pipeline results of loop 1: [wbytes n x 32 | flags n | tstates n x 203]; same layout on device and host
     size_t mo_wbytes = 0, mo_flags = 0, mo_tstate = 0, mid_bytes = 0;
     size_t ho_ok = 0, ho_ident = 0, ho_masks = 0, hout_bytes = 0;
@@ -132,19 +135,20 @@ static void vwork_return(bpp_ctx *ctx, VWork *w) {
 // ------------------------------------------------------------------------------------------------ CUDA graphs
 // One verification pass is ~20 kernels, 2 memsets and 5 copies.  Issued one by one that is ~35 driver calls per pass, and with
 // several lanes (one bpp_ctx + host thread each) verifying concurrently the driver's submission path, not the GPU, capped a
-// B200 at ~6.5 k passes/s whatever their size (measured: 1.7 M proofs/s with 256-proof passes, 4.4 M with 1024, 6.5 M with
-// 4096).  The pass is therefore captured once per (workspace, layout) as three graphs -- A: transcript replay + D2H of its
-// results, B: point decompression || weight-free scalar prep, C: weights H2D, weighting, MSM, verdict D2H -- split where the
-// host hashes the verifier-weight transcript, and replayed with three cudaGraphLaunch calls afterwards.
+// B200 at ~6.5 k passes/s whatever their size (measured in round 1: 1.7 M proofs/s with 256-proof passes, 4.4 M with 1024).
+// The pass is therefore captured once per (workspace, layout) as three graphs -- A: transcript replay + D2H of its results,
+// B: point decompression || weight-free scalar prep, C: weights H2D, weighting, MSM, verdict D2H -- split where the host hashes
+// the verifier-weight transcript, and replayed with three cudaGraphLaunch calls afterwards.
 struct VGraphKey {
-    const void *bufs[18];
+    const void *bufs[21];
     const void *gens_table;
-    size_t n_proofs, n_chunks;
-    size_t off[23];
-    uint32_t n_pts, n_entries, total_vec, max_static, max_rounds;
+    size_t n_proofs, n_chunks, n_commit;
+    size_t off[21];
+    uint32_t n_pts, n_entries, n_chal, max_static, max_rounds;
     int32_t action, ext, bit_length;
     MsmShape shape;
-    uint8_t any_msm, any_masks, any_replay, device_replay, warp_replay, fused;
+    int32_t msm_knobs[4];
+    uint8_t any_msm, any_masks, any_replay, any_vec, device_replay, replay_kernel, fused, caller_challenges;
 };
 struct VGraph {
     VGraphKey key;
@@ -382,29 +386,40 @@ static void compute_weights(bpp_vbatch *vb) {
     });
 }
 
-extern "C" {
-
-void bpp_vbatch_destroy(bpp_vbatch *vb) {
-    if (!vb) return;
-    cudaSetDevice(vb->g->ctx->device);
-    cudaStreamSynchronize(vb->g->ctx->stream);
-    if (vb->w) vwork_return(vb->g->ctx, vb->w);
-    delete vb;
-}
-
-int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **out) {
-    if (!g || !a || !out) return BPP_INVALID_ARGUMENT;
+static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_args *const *args, const bpp_verify_challenges *const *chs,
+                                  bpp_vbatch **out) {
+    if (!g || !args || !out || n_calls == 0) return BPP_INVALID_ARGUMENT;
     bpp_ctx *ctx = g->ctx;
     *out = nullptr;
-    if (a->n_chunks == 0 || !a->chunk_offsets) return fail(ctx, BPP_INVALID_ARGUMENT, "Range statements or proofs length empty");
-    if (a->chunk_offsets[0] != 0 || a->chunk_offsets[a->n_chunks] != a->n_proofs) return fail(ctx, BPP_INVALID_ARGUMENT, "bad chunk offsets");
-    for (size_t c = 0; c < a->n_chunks; c++)
-        if (a->chunk_offsets[c + 1] < a->chunk_offsets[c]) return fail(ctx, BPP_INVALID_ARGUMENT, "bad chunk offsets");
-    if (a->n_proofs && (!a->proof_bytes || !a->proof_offsets || !a->commitments32 || !a->commit_offsets || !a->min_values ||
-                        !a->min_present || !a->transcripts))
-        return fail(ctx, BPP_INVALID_ARGUMENT, "null argument");
-    if (a->action < BPP_RECOVER_ONLY || a->action > BPP_VERIFY_ONLY) return fail(ctx, BPP_INVALID_ARGUMENT, "bad action");
-    if (a->n_proofs >= (1u << 24)) return fail(ctx, BPP_SIZE_OVERFLOW, "too many proofs in one call");
+    // ---- argument checks per call, totals
+    uint64_t tot_proofs = 0, tot_chunks = 0, tot_commit = 0, tot_raw = 0;
+    for (size_t ci = 0; ci < n_calls; ci++) {
+        const bpp_verify_args *a = args[ci];
+        if (!a) return fail(ctx, BPP_INVALID_ARGUMENT, "null argument");
+        if (a->n_chunks == 0 || !a->chunk_offsets) return fail(ctx, BPP_INVALID_ARGUMENT, "Range statements or proofs length empty");
+        if (a->chunk_offsets[0] != 0 || a->chunk_offsets[a->n_chunks] != a->n_proofs) return fail(ctx, BPP_INVALID_ARGUMENT, "bad chunk offsets");
+        for (size_t c = 0; c < a->n_chunks; c++)
+            if (a->chunk_offsets[c + 1] < a->chunk_offsets[c]) return fail(ctx, BPP_INVALID_ARGUMENT, "bad chunk offsets");
+        const bool need_t = !(chs && chs[ci]);
+        if (a->n_proofs && (!a->proof_bytes || !a->proof_offsets || !a->commitments32 || !a->commit_offsets || !a->min_values ||
+                            !a->min_present || (need_t && !a->transcripts)))
+            return fail(ctx, BPP_INVALID_ARGUMENT, "null argument");
+        if (chs && chs[ci] && a->n_proofs && (!chs[ci]->challenges32 || !chs[ci]->challenge_offsets || !chs[ci]->weights32))
+            return fail(ctx, BPP_INVALID_ARGUMENT, "null argument");
+        if ((chs && chs[ci]) != (chs && chs[0])) return fail(ctx, BPP_INVALID_ARGUMENT, "calls with and without caller challenges in one pass");
+        if (a->action < BPP_RECOVER_ONLY || a->action > BPP_VERIFY_ONLY) return fail(ctx, BPP_INVALID_ARGUMENT, "bad action");
+        if (a->action != args[0]->action) return fail(ctx, BPP_INVALID_ARGUMENT, "calls of one pass must share the action");
+        tot_proofs += a->n_proofs; tot_chunks += a->n_chunks;
+        if (a->n_proofs) {
+            if (a->proof_offsets[a->n_proofs] < a->proof_offsets[0] || a->commit_offsets[a->n_proofs] < a->commit_offsets[0])
+                return fail(ctx, BPP_INVALID_ARGUMENT, "bad offsets");
+            tot_raw += a->proof_offsets[a->n_proofs] - a->proof_offsets[0];
+            tot_commit += a->commit_offsets[a->n_proofs] - a->commit_offsets[0];
+        }
+    }
+    // the reference counts with checked_add / checked_mul and returns SizeOverflow; device offsets are 32-bit
+    if (tot_proofs >= (1u << 24) || tot_chunks >= (1u << 24) || tot_commit >= (1u << 26) || tot_raw >= (1ull << 31))
+        return fail(ctx, BPP_SIZE_OVERFLOW, "too many proofs in one pass");
     cudaSetDevice(ctx->device);
 
     auto t_prev = std::chrono::steady_clock::now();
@@ -416,54 +431,69 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         t_prev = now;
     };
     bpp_vbatch *vb = new bpp_vbatch();
-    vb->g = g; vb->action = a->action; vb->n_proofs = a->n_proofs; vb->n_chunks = a->n_chunks;
-    vb->device_replay = ctx->device_replay;
-    vb->chunk_offsets.assign(a->chunk_offsets, a->chunk_offsets + a->n_chunks + 1);
-    vb->hp.resize(a->n_proofs);
-    vb->hc.resize(a->n_chunks);
+    vb->g = g; vb->action = args[0]->action; vb->n_proofs = (size_t)tot_proofs; vb->n_chunks = (size_t)tot_chunks; vb->n_commit = (size_t)tot_commit;
+    vb->caller_challenges = chs && chs[0];
+    vb->device_replay = ctx->device_replay && !vb->caller_challenges;
+    vb->hp.resize(vb->n_proofs);
+    vb->hc.resize(vb->n_chunks);
+    vb->calls.resize(n_calls);
     const int n = g->n, ext = g->ext;
-    const bool want_masks = a->action != BPP_VERIFY_ONLY;
+    const bool want_masks = vb->action != BPP_VERIFY_ONLY;
+    const size_t NP = vb->n_proofs, NC = vb->n_chunks;
 
-    // ---- per-proof parsing + statement checks (parallel), then per-chunk consistency
-    for (size_t c = 0; c < a->n_chunks; c++) {
-        HChunk &hc = vb->hc[c];
-        hc.lo = a->chunk_offsets[c];
-        hc.hi = std::min<size_t>(a->chunk_offsets[c + 1], hc.lo + BPP_MAX_BATCH);       // range_proof.rs:739-751
-        if (hc.hi == hc.lo) hc.pre_rc = BPP_INVALID_ARGUMENT;                             // :719-723
+    // ---- calls, chunks, which proofs are looked at (range_proof.rs:739-751: the first 256 of a call)
+    {
+        size_t p0 = 0, c0 = 0, cm0 = 0, r0 = 0;
+        for (size_t ci = 0; ci < n_calls; ci++) {
+            HCall &hcall = vb->calls[ci];
+            hcall.a = *args[ci];
+            hcall.ch = chs ? chs[ci] : nullptr;
+            hcall.proof0 = p0; hcall.chunk0 = c0; hcall.commit0 = cm0; hcall.raw0 = r0;
+            const bpp_verify_args &a = hcall.a;
+            hcall.raw_base = a.n_proofs ? a.proof_offsets[0] : 0;
+            for (size_t c = 0; c < a.n_chunks; c++) {
+                HChunk &hc = vb->hc[c0 + c];
+                hc.lo = p0 + a.chunk_offsets[c];
+                hc.end = p0 + a.chunk_offsets[c + 1];
+                hc.hi = std::min<size_t>(hc.end, hc.lo + BPP_MAX_BATCH);
+                if (hc.hi == hc.lo) hc.pre_rc = BPP_INVALID_ARGUMENT;                           // :719-723
+                for (size_t i = hc.lo; i < hc.hi; i++) vb->hp[i].looked = true;
+            }
+            for (size_t i = 0; i < a.n_proofs; i++) { vb->hp[p0 + i].call = (uint32_t)ci; vb->hp[p0 + i].local = i; }
+            if (a.n_proofs) {
+                r0 += a.proof_offsets[a.n_proofs] - a.proof_offsets[0];
+                cm0 += a.commit_offsets[a.n_proofs] - a.commit_offsets[0];
+            }
+            p0 += a.n_proofs; c0 += a.n_chunks;
+        }
     }
-    std::vector<uint8_t> looked(a->n_proofs, 0);
-    for (const HChunk &hc : vb->hc)
-        for (size_t i = hc.lo; i < hc.hi; i++) looked[i] = 1;
-    ctx->workers().run(a->n_proofs, 64, [&](size_t i) {
-        if (!looked[i]) return;
-        HProof &p = vb->hp[i];
-        size_t plen = a->proof_offsets[i + 1] - a->proof_offsets[i];
-        p.bytes = a->proof_bytes + a->proof_offsets[i];
+    // ---- per-proof header parse + statement checks (parallel for large passes)
+    ctx->workers().run(NP, 512, [&](size_t gi) {
+        HProof &p = vb->hp[gi];
+        if (!p.looked) return;
+        const bpp_verify_args &a = vb->calls[p.call].a;
+        const size_t i = p.local;
+        const size_t plen = a.proof_offsets[i + 1] - a.proof_offsets[i];
+        p.bytes = a.proof_bytes + a.proof_offsets[i];
         int32_t pext = 0, rounds = 0;
-        p.pre_rc = bpp_proof_check_bytes(p.bytes, plen, &pext, &rounds);                // RangeProof::from_bytes
+        p.pre_rc = bpp_proof_check_bytes(p.bytes, plen, &pext, &rounds);                  // RangeProof::from_bytes
         p.ext = pext; p.rounds = rounds;
-        uint64_t m64 = a->commit_offsets[i + 1] - a->commit_offsets[i];
+        const uint64_t m64 = a.commit_offsets[i + 1] - a.commit_offsets[i];
         p.m = (uint32_t)m64;
-        p.has_seed = a->seed_present && a->seed_nonces32 && a->seed_present[i];
-        if (!p.pre_rc) {                                                                 // RangeStatement::init, range_statement.rs:42-61
+        p.has_seed = a.seed_present && a.seed_nonces32 && a.seed_present[i];
+        if (!p.pre_rc) {                                                                   // RangeStatement::init, range_statement.rs:42-61
             if (m64 == 0 || (m64 & (m64 - 1)) || m64 > (uint64_t)g->M) p.pre_rc = BPP_INVALID_ARGUMENT;
             else if (p.has_seed && m64 > 1) p.pre_rc = BPP_INVALID_ARGUMENT;
         }
         if (p.pre_rc) return;
-        if (p.has_seed) {          // Scalar::from_bytes_mod_order; a seed that is already canonical (the usual case) needs no reduction
-            const uint8_t *sb = a->seed_nonces32 + 32 * i;
-            if (host_sc_is_canonical(sb)) memcpy(p.seed, sb, 32);
-            else {
-                uint32_t w[8];
-                memcpy(w, sb, 32);
-                sc s; for (int k = 0; k < 8; k++) s.v[k] = w[k];
-                sc_tobytes(p.seed, sc_reduce256(s));
-            }
-        }
-        uint64_t N = (uint64_t)p.m * (uint64_t)n;
-        if (p.rounds >= 32 || (1ull << p.rounds) != N) p.loop2_rc = BPP_INVALID_LENGTH;  // :886-888
+        // :875-888 -- 2^rounds must equal n*m; checked_shl overflows from 64 rounds on (usize is 64 bits wide)
+        if (p.rounds >= 64) p.loop2_rc = BPP_SIZE_OVERFLOW;
+        else if (p.rounds >= 32 || (1ull << p.rounds) != (uint64_t)p.m * (uint64_t)n) p.loop2_rc = BPP_INVALID_LENGTH;
     });
-    for (size_t c = 0; c < a->n_chunks; c++) {
+    // ---- per-chunk consistency (:610-709) and the totals of the device layout
+    uint64_t n_pts = 0, n_entries = 0, contrib = 0, pv = 0, n_chal = 0, n_nonce = 0;
+    uint32_t max_static = 0;
+    for (size_t c = 0; c < NC; c++) {
         HChunk &hc = vb->hc[c];
         if (hc.pre_rc) continue;
         int32_t ext_rc = 0, promise_rc = 0;
@@ -472,110 +502,74 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
         for (size_t i = hc.lo; i < hc.hi; i++) {
             const HProof &p = vb->hp[i];
             if (p.pre_rc) { if (!hc.pre_rc) hc.pre_rc = p.pre_rc; continue; }
-            if (p.ext != ext && !ext_rc) ext_rc = BPP_INVALID_ARGUMENT;                  // :637-660
-            if (n < 64)
+            if (p.ext != ext && !ext_rc) ext_rc = BPP_INVALID_ARGUMENT;                    // :637-660
+            if (n < 64) {
+                const bpp_verify_args &a = vb->calls[p.call].a;
                 for (uint32_t j = 0; j < p.m; j++) {
-                    size_t ci = a->commit_offsets[i] + j;
-                    if (a->min_present[ci] && (a->min_values[ci] >> n) > 0 && !promise_rc) promise_rc = BPP_INVALID_LENGTH;   // :675-682
+                    const size_t ci = a.commit_offsets[p.local] + j;
+                    if (a.min_present[ci] && (a.min_values[ci] >> n) > 0 && !promise_rc) promise_rc = BPP_INVALID_LENGTH;     // :675-682
                 }
+            }
             if (p.loop2_rc) rounds_ok = false;
             max_mn = std::max<uint32_t>(max_mn, p.m * (uint32_t)n);
         }
         if (!hc.pre_rc) hc.pre_rc = ext_rc ? ext_rc : promise_rc;
         hc.computable = !hc.pre_rc && rounds_ok;
         hc.max_mn = max_mn;
+        if (hc.pre_rc) continue;
+        const bool msm = hc.computable && vb->action != BPP_RECOVER_ONLY;
+        if (msm) n_entries += 2 * (uint64_t)max_mn + (uint64_t)ext + 1;
+        for (size_t i = hc.lo; i < hc.hi; i++) {
+            const HProof &p = vb->hp[i];
+            const uint64_t R = (uint64_t)p.rounds;
+            n_pts += 3 + 2 * R + p.m;
+            n_chal += 3 + R;
+            if (hc.computable && want_masks && p.has_seed) n_nonce += (uint64_t)ext * (3 + 2 * R);
+            if (msm) { contrib += 2ull << R; pv += 8 + 3 * R + p.m; n_entries += 3 + 2 * R + p.m; }
+        }
+    }
+    if (n_pts >= (1ull << 30) || n_entries >= (1ull << 30) || contrib >= (1ull << 31) || pv >= (1ull << 31) || n_chal >= (1ull << 31) ||
+        n_nonce >= (1ull << 31)) {
+        delete vb;
+        return fail(ctx, BPP_SIZE_OVERFLOW, "verification pass too large");
     }
     lap();   // [0] parse
 
-    // ---- device layout, pass 1: sizes and offsets
-    const uint32_t GEN = 0x80000000u;
-    uint32_t n_pts = 0, n_entries = 0, contrib = 0, pv = 0, max_static = 0, n_pscal = 0, n_chal = 0, n_nonce = 0;
-    std::vector<VProof> dp(a->n_proofs);
-    std::vector<VChunk> dc(a->n_chunks);
-    for (size_t c = 0; c < a->n_chunks; c++) {
-        HChunk &hc = vb->hc[c];
-        VChunk &ch = dc[c];
-        ch.proof_lo = (uint32_t)hc.lo; ch.proof_hi = (uint32_t)hc.hi; ch.max_mn = hc.max_mn;
-        bool msm = hc.computable && a->action != BPP_RECOVER_ONLY;
-        ch.active = msm ? 1 : 0;
-        ch.entry_off = n_entries;
-        hc.entry_off = n_entries;
-        if (msm) {
-            vb->any_msm = true;
-            uint32_t n_static = 2 * hc.max_mn + (uint32_t)ext + 1;
-            max_static = std::max(max_static, n_static);
-            n_entries += n_static;
-        }
-        for (size_t i = a->chunk_offsets[c]; i < a->chunk_offsets[c + 1]; i++) {
-            HProof &p = vb->hp[i];
-            VProof &v = dp[i];
-            memset(&v, 0, sizeof v);
-            v.nonce_off = 0xffffffffu;
-            if (i >= hc.hi || p.pre_rc || !p.bytes) continue;
-            // point table slots (decompressed whatever the chunk's fate: the flags decide InvalidArgument precedence)
-            p.pt_off = n_pts;
-            p.n_pts = 3 + 2 * (uint32_t)p.rounds + p.m;
-            n_pts += p.n_pts;
-            if (hc.pre_rc) continue;
-            // loop 1 runs over every proof of a call that passed the consistency checks (:816-850)
-            v.replay = 1; vb->any_replay = true;
-            v.pt_off = p.pt_off;
-            v.m = p.m; v.rounds = (uint32_t)p.rounds;
-            v.commit_off = (uint32_t)a->commit_offsets[i];
-            v.sc_off = n_pscal; n_pscal += 2 + (uint32_t)p.ext;
-            v.ch_off = n_chal; n_chal += 3 + (uint32_t)p.rounds;
-            if (!hc.computable) continue;
-            if (want_masks && p.has_seed) {
-                v.nonce_off = n_nonce; n_nonce += (uint32_t)ext * (3 + 2 * (uint32_t)p.rounds);
-                vb->any_masks = true;
-            }
-            if (msm) {
-                v.active = 1;
-                uint32_t N = 1u << p.rounds;
-                v.entry_off = n_entries;
-                v.contrib_off = contrib; contrib += 2 * N;
-                v.pv_off = pv; pv += 8 + 3 * (uint32_t)p.rounds + p.m;
-                vb->max_rounds = std::max(vb->max_rounds, (uint32_t)p.rounds);
-                n_entries += 3 + 2 * (uint32_t)p.rounds + p.m;
-            }
-        }
-        hc.n_entries = n_entries - hc.entry_off;
-    }
-    size_t n_commit = a->n_proofs ? a->commit_offsets[a->n_proofs] : 0;
+    // ---- blob sections
     size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    vb->o_enc = carve(32 * (size_t)n_pts);
-    vb->o_proofs = carve(sizeof(VProof) * a->n_proofs);
-    vb->o_chunks = carve(sizeof(VChunk) * a->n_chunks);
-    vb->o_vecoff = carve(4 * (a->n_proofs + 1));
-    vb->o_pscal = carve(32 * (size_t)n_pscal);
-    vb->o_chal = carve(32 * (size_t)n_chal);
-    vb->o_minv = carve(8 * n_commit);
-    vb->o_minp = carve(n_commit);
-    vb->o_nonces = carve(32 * (size_t)n_nonce);
-    vb->o_pidx = carve(4 * (size_t)n_entries);
-    vb->o_segoff = carve(4 * (a->n_chunks + 1));
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 16 + 255) & ~(size_t)255; return o; };      // >= 16 bytes of padding
+    vb->o_proofs = carve(sizeof(VProof) * NP);
+    vb->o_chunks = carve(sizeof(VChunk) * NC);
+    vb->o_ptoff = carve(4 * (NP + 1));
+    vb->o_segoff = carve(4 * (NC + 1));
     vb->o_hg = carve(32 * ((size_t)ext + 1));
-    vb->o_tstate = carve(vb->device_replay ? BPP_TRANSCRIPT_BYTES * a->n_proofs : 0);
     vb->o_wtinit = carve(BPP_TRANSCRIPT_BYTES);
+    vb->o_minv = carve(8 * vb->n_commit);
+    vb->o_minp = carve(vb->n_commit);
+    vb->o_commit = carve(32 * vb->n_commit);
+    vb->o_raw = carve((size_t)tot_raw);
+    vb->o_tstate = carve(vb->device_replay ? BPP_TRANSCRIPT_BYTES * NP : 0);
+    vb->o_nonces = carve(32 * (size_t)n_nonce);
     vb->blob_bytes = off;
-    vb->n_pts = n_pts; vb->n_entries = n_entries; vb->max_static = max_static;
-    vb->shape = msm_shape(n_entries, (uint32_t)a->n_chunks, 0);
+    if (vb->blob_bytes >= (1ull << 32)) { delete vb; return fail(ctx, BPP_SIZE_OVERFLOW, "verification pass too large"); }
+    vb->n_pts = (uint32_t)n_pts; vb->n_entries = (uint32_t)n_entries; vb->n_chal = (uint32_t)n_chal;
     vb->mo_wbytes = 0;
-    vb->mo_flags = 32 * a->n_proofs;
-    vb->mo_tstate = (vb->mo_flags + a->n_proofs + 255) & ~(size_t)255;
-    vb->mid_bytes = vb->mo_tstate + BPP_TRANSCRIPT_BYTES * a->n_proofs;
+    vb->mo_flags = 32 * NP;
+    vb->mo_tstate = (vb->mo_flags + NP + 255) & ~(size_t)255;
+    vb->mid_bytes = vb->mo_tstate + BPP_TRANSCRIPT_BYTES * NP;
     vb->ho_ok = 0;
-    vb->ho_ident = (n_pts + 255) & ~(size_t)255;
-    vb->ho_masks = vb->ho_ident + ((a->n_chunks + 255) & ~(size_t)255);
-    vb->hout_bytes = vb->ho_masks + 32 * std::max<size_t>(a->n_proofs, 1) * (size_t)ext;
+    vb->ho_ident = ((size_t)n_pts + 255) & ~(size_t)255;
+    vb->ho_masks = vb->ho_ident + ((NC + 255) & ~(size_t)255);
+    vb->hout_bytes = vb->ho_masks + 32 * std::max<size_t>(NP, 1) * (size_t)ext;
 
     // ---- buffers (pooled)
     VWork *w = vwork_acquire(ctx);
     vb->w = w;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    const size_t np1 = std::max<size_t>(a->n_proofs, 1);
+    const size_t np1 = std::max<size_t>(NP, 1);
+    // static entries of a chunk are bounded by the generator set; the MSM shape needs the entry count only
+    vb->shape = msm_shape(vb->n_entries, (uint32_t)NC, 0);
     ok(w->h_blob.ensure(vb->blob_bytes));
     ok(w->d_blob.ensure(vb->blob_bytes));
     ok(w->h_out.ensure(vb->hout_bytes));
@@ -584,124 +578,225 @@ int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **ou
     ok(w->h_weights.ensure(32 * np1));
     ok(w->d_weights.ensure(32 * np1));
     ok(w->d_wmont.ensure(32 * np1));
+    ok(w->d_chal.ensure(32 * std::max<size_t>(n_chal, 1)));
+    if (!vb->device_replay) ok(w->h_chal.ensure(32 * std::max<size_t>(n_chal, 1)));
     ok(w->d_tab.ensure(sizeof(aniels) * std::max<size_t>(n_pts, 1)));
     ok(w->d_ok.ensure(std::max<size_t>(n_pts, 1)));
     ok(w->d_mscal.ensure(32 * std::max<size_t>(n_entries, 1)));
+    ok(w->d_pidx.ensure(4 * std::max<size_t>(n_entries, 1)));
     ok(w->d_contrib.ensure(32 * std::max<size_t>(contrib, 1)));
     ok(w->d_hg.ensure(32 * np1 * (1 + (size_t)ext)));
     ok(w->d_pervec.ensure(32 * std::max<size_t>(pv, 1)));
     ok(w->d_masks.ensure(32 * np1 * (size_t)ext));
     ok(w->d_scratch.ensure(msm_scratch_bytes(vb->shape)));
-    ok(w->d_res.ensure(sizeof(ge) * a->n_chunks));
-    ok(w->d_ident.ensure(a->n_chunks));
+    ok(w->d_res.ensure(sizeof(ge) * NC));
+    ok(w->d_ident.ensure(NC));
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch buffers"); }
-    lap();   // [1] layout
 
-    // ---- pass 2: fill the pinned blob (parallel over proofs)
+    // ---- device layout, written straight into the pinned blob
     uint8_t *hb = w->h_blob.as<uint8_t>();
-    uint32_t *vecoff = (uint32_t *)(hb + vb->o_vecoff), *segoff = (uint32_t *)(hb + vb->o_segoff), *pidx = (uint32_t *)(hb + vb->o_pidx);
+    VProof *dp = (VProof *)(hb + vb->o_proofs);
+    VChunk *dc = (VChunk *)(hb + vb->o_chunks);
+    uint32_t *ptoff = (uint32_t *)(hb + vb->o_ptoff), *segoff = (uint32_t *)(hb + vb->o_segoff);
     {
-        uint32_t run = 0;
-        for (size_t i = 0; i < a->n_proofs; i++) { vecoff[i] = run; if (dp[i].active) run += 1u << dp[i].rounds; }
-        vecoff[a->n_proofs] = run;
-        vb->total_vec = run;
-        for (size_t c = 0; c < a->n_chunks; c++) segoff[c] = dc[c].entry_off;
-        segoff[a->n_chunks] = n_entries;
-    }
-    memcpy(hb + vb->o_proofs, dp.data(), sizeof(VProof) * a->n_proofs);
-    memcpy(hb + vb->o_chunks, dc.data(), sizeof(VChunk) * a->n_chunks);
-    if (n_commit) { memcpy(hb + vb->o_minv, a->min_values, 8 * n_commit); memcpy(hb + vb->o_minp, a->min_present, n_commit); }
-    memcpy(hb + vb->o_hg, g->h(), 32);
-    memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
-    if (vb->device_replay && a->n_proofs) memcpy(hb + vb->o_tstate, a->transcripts, BPP_TRANSCRIPT_BYTES * a->n_proofs);
-    memcpy(hb + vb->o_wtinit, weight_transcript_init().data(), BPP_TRANSCRIPT_BYTES);      // starting state of k_weights
-    memset(vb->mid(), 0, vb->mid_bytes);
-    memset(w->h_weights.p, 0, 32 * np1);
-    for (size_t c = 0; c < a->n_chunks; c++) {
-        if (!dc[c].active) continue;
-        uint32_t *px = pidx + dc[c].entry_off, mn = dc[c].max_mn;
-        for (uint32_t i = 0; i < mn; i++) { px[i] = GEN | i; px[mn + i] = GEN | (uint32_t)(g->nm + i); }
-        for (int k = 0; k < ext; k++) px[2 * mn + k] = GEN | (uint32_t)(2 * g->nm + k);
-        px[2 * mn + ext] = GEN | (uint32_t)(2 * g->nm + ext);
-    }
-    const bool host_replay = !vb->device_replay;
-    ctx->workers().run(a->n_proofs, host_replay ? 8 : 32, [&](size_t i) {
-        const HProof &p = vb->hp[i];
-        const VProof &v = dp[i];
-        if (!p.n_pts) return;
-        uint8_t *en = hb + vb->o_enc + 32 * (size_t)p.pt_off;
-        memcpy(en, p.a(), 96);
-        for (int j = 0; j < p.rounds; j++) { memcpy(en + 32 * (3 + j), p.li(j), 32); memcpy(en + 32 * (3 + p.rounds + j), p.ri(j), 32); }
-        const uint8_t *cm = a->commitments32 + 32 * a->commit_offsets[i];
-        memcpy(en + 32 * (3 + 2 * p.rounds), cm, 32 * (size_t)p.m);
-        if (!v.replay) return;          // call already failed on the host: only the decompression flags matter
-        uint8_t *ps = hb + vb->o_pscal + 32 * (size_t)v.sc_off;
-        memcpy(ps, p.r1(), 64);
-        memcpy(ps + 64, p.d1(), 32 * (size_t)p.ext);
-        uint8_t *chp = hb + vb->o_chal + 32 * (size_t)v.ch_off;
-        if (host_replay) {              // loop 1 on this host thread (north_star's split); same code as k_replay.cu
-            ReplayIn in;
-            in.tstate = a->transcripts + BPP_TRANSCRIPT_BYTES * i;
-            in.h32 = g->h(); in.g32 = g->g(0);
-            in.bit_length = (uint32_t)n; in.ext = (uint32_t)ext; in.m = p.m; in.rounds = (uint32_t)p.rounds;
-            in.commitments32 = cm;
-            in.min_values = a->min_values + a->commit_offsets[i]; in.min_present = a->min_present + a->commit_offsets[i];
-            in.a = p.a(); in.a1 = p.a1(); in.b = p.b();
-            in.l_base = p.li(0); in.r_base = p.ri(0); in.lr_stride = 64;
-            in.r1 = p.r1(); in.s1 = p.s1(); in.d1 = p.d1();
-            ReplayOut o;
-            o.y = chp; o.z = chp + 32; o.e = chp + 64; o.ej = chp + 96;
-            o.wbytes = vb->wbytes(i); o.tstate = vb->tstate(i);
-            int rc = replay_transcript_core(in, o);
-            uint8_t flag = rc ? 1 : 0;
-            uint8_t one[32] = {1};
-            if (!rc && !memcmp(chp, one, 32)) flag |= 2;
-            vb->flag(i) = flag;
-        }
-        if (v.nonce_off != 0xffffffffu) {
-            uint8_t *nn = hb + vb->o_nonces + 32 * (size_t)v.nonce_off;
-            for (int k = 0; k < ext; k++) {
-                nonce(p.seed, "eta", false, 0, true, (uint32_t)k, nn + 32 * k);
-                nonce(p.seed, "d", false, 0, true, (uint32_t)k, nn + 32 * (ext + k));
-                nonce(p.seed, "alpha", false, 0, true, (uint32_t)k, nn + 32 * (2 * ext + k));
-                for (int j = 0; j < p.rounds; j++) {
-                    nonce(p.seed, "dL", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + j * ext + k));
-                    nonce(p.seed, "dR", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + p.rounds * ext + j * ext + k));
+        uint32_t pts = 0, entries = 0, cb = 0, pvo = 0, chal = 0, nonces = 0;
+        memset(dp, 0, sizeof(VProof) * NP);
+        size_t next_proof = 0;      // ptoff is filled for every proof, also those no chunk looks at
+        for (size_t c = 0; c < NC; c++) {
+            HChunk &hc = vb->hc[c];
+            VChunk &ch = dc[c];
+            ch.proof_lo = (uint32_t)hc.lo; ch.proof_hi = (uint32_t)hc.hi; ch.max_mn = hc.max_mn;
+            const bool msm = hc.computable && vb->action != BPP_RECOVER_ONLY;
+            ch.active = msm ? 1 : 0;
+            ch.entry_off = entries;
+            hc.entry_off = entries;
+            segoff[c] = entries;
+            if (msm) {
+                vb->any_msm = true;
+                const uint32_t n_static = 2 * hc.max_mn + (uint32_t)ext + 1;
+                max_static = std::max(max_static, n_static);
+                entries += n_static;
+            }
+            for (; next_proof < hc.lo; next_proof++) ptoff[next_proof] = pts;
+            for (size_t i = hc.lo; i < hc.end; i++) {
+                HProof &p = vb->hp[i];
+                VProof &v = dp[i];
+                ptoff[i] = pts;
+                v.nonce_off = 0xffffffffu;
+                if (i >= hc.hi || hc.pre_rc) continue;          // not looked at, or the call failed on the host: no device work
+                const HCall &call = vb->calls[p.call];
+                const bpp_verify_args &a = call.a;
+                const uint32_t R = (uint32_t)p.rounds;
+                p.pt_off = pts; p.n_pts = 3 + 2 * R + p.m;
+                pts += p.n_pts;
+                // loop 1 runs over every proof of a call that passed the consistency checks (:816-850)
+                v.replay = 1; vb->any_replay = true;
+                v.pt_off = p.pt_off;
+                v.m = p.m; v.rounds = R;
+                v.raw_off = (uint32_t)(vb->o_raw + call.raw0 + (a.proof_offsets[p.local] - call.raw_base));
+                v.commit_off = (uint32_t)(call.commit0 + (a.commit_offsets[p.local] - a.commit_offsets[0]));
+                v.ch_off = chal; chal += 3 + R;
+                if (!hc.computable) continue;
+                if (want_masks && p.has_seed) {
+                    v.nonce_off = nonces; nonces += (uint32_t)ext * (3 + 2 * R);
+                    vb->any_masks = true;
+                }
+                if (msm) {
+                    v.active = 1; vb->any_vec = true;
+                    v.entry_off = entries;
+                    v.contrib_off = cb; cb += 2u << R;
+                    v.pv_off = pvo; pvo += 8 + 3 * R + p.m;
+                    vb->max_rounds = std::max(vb->max_rounds, R);
+                    entries += 3 + 2 * R + p.m;
                 }
             }
+            next_proof = hc.end;
+            hc.n_entries = entries - hc.entry_off;
         }
-        if (v.active) {
-            uint32_t *px = pidx + v.entry_off, R = (uint32_t)p.rounds;
-            px[0] = p.pt_off + 1; px[1] = p.pt_off + 2; px[2] = p.pt_off;
-            for (uint32_t j = 0; j < 2 * R + p.m; j++) px[3 + j] = p.pt_off + 3 + j;
+        for (; next_proof <= NP; next_proof++) ptoff[next_proof] = pts;
+        segoff[NC] = entries;
+        vb->max_static = max_static;
+    }
+    lap();   // [1] layout
+
+    // ---- fill: the callers' byte arrays as they are, one memcpy each
+    for (const HCall &call : vb->calls) {
+        const bpp_verify_args &a = call.a;
+        if (!a.n_proofs) continue;
+        const size_t raw_len = a.proof_offsets[a.n_proofs] - a.proof_offsets[0];
+        const size_t c_lo = a.commit_offsets[0], c_n = a.commit_offsets[a.n_proofs] - c_lo;
+        memcpy(hb + vb->o_raw + call.raw0, a.proof_bytes + a.proof_offsets[0], raw_len);
+        memcpy(hb + vb->o_commit + 32 * call.commit0, a.commitments32 + 32 * c_lo, 32 * c_n);
+        memcpy(hb + vb->o_minv + 8 * call.commit0, a.min_values + c_lo, 8 * c_n);
+        memcpy(hb + vb->o_minp + call.commit0, a.min_present + c_lo, c_n);
+        if (vb->device_replay) memcpy(hb + vb->o_tstate + BPP_TRANSCRIPT_BYTES * call.proof0, a.transcripts, BPP_TRANSCRIPT_BYTES * a.n_proofs);
+    }
+    memcpy(hb + vb->o_hg, g->h(), 32);
+    memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
+    memcpy(hb + vb->o_wtinit, weight_transcript_init().data(), BPP_TRANSCRIPT_BYTES);      // starting state of k_weights
+    memset(vb->mid(), 0, vb->mo_tstate);             // wbytes + flags (the transcript states are written by whoever replays)
+    if (!vb->device_replay) memset(w->h_weights.p, 0, 32 * np1);
+    const bool host_replay = !vb->device_replay && !vb->caller_challenges;
+    if (vb->caller_challenges) {
+        // the caller ran loop 1 with its own merlin (src/transcripts.rs unmodified): challenges [y, z, e, e_0..e_{r-1}] per proof and
+        // the batch weights (:894) come in; zero challenges / identity points were the caller's to reject (VerificationFailed)
+        for (size_t gi = 0; gi < NP; gi++) {
+            const HProof &p = vb->hp[gi];
+            const VProof &v = dp[gi];
+            if (!v.replay) continue;
+            const HCall &call = vb->calls[p.call];
+            const uint64_t co = call.ch->challenge_offsets[p.local], cn = call.ch->challenge_offsets[p.local + 1] - co;
+            uint8_t *dst = w->h_chal.as<uint8_t>() + 32 * (size_t)v.ch_off;
+            if (cn != 3 + (uint64_t)p.rounds) { vwork_return(ctx, w); delete vb; return fail(ctx, BPP_INVALID_ARGUMENT, "challenge count does not match the proof"); }
+            memcpy(dst, call.ch->challenges32 + 32 * co, 32 * cn);
+            bool canon = true;
+            for (uint64_t k = 0; k < cn; k++) canon = canon && host_sc_is_canonical(dst + 32 * k) && !is_zero32(dst + 32 * k);
+            if (!canon || !host_sc_is_canonical(call.ch->weights32 + 32 * p.local) || is_zero32(call.ch->weights32 + 32 * p.local)) {
+                vwork_return(ctx, w); delete vb;
+                return fail(ctx, BPP_INVALID_ARGUMENT, "challenges and weights must be canonical non-zero scalars");
+            }
+            memcpy(w->h_weights.as<uint8_t>() + 32 * gi, call.ch->weights32 + 32 * p.local, 32);
+            uint8_t one[32] = {1};
+            vb->flag(gi) = memcmp(dst, one, 32) ? 0 : 2;      // y == 1
         }
-    });
+    }
+    if (host_replay || n_nonce) {
+        ctx->workers().run(NP, host_replay ? 8 : 64, [&](size_t gi) {
+            const HProof &p = vb->hp[gi];
+            const VProof &v = dp[gi];
+            if (!v.replay) return;
+            const HCall &call = vb->calls[p.call];
+            const bpp_verify_args &a = call.a;
+            const size_t i = p.local;
+            if (host_replay) {              // loop 1 on this host thread (north_star's split); same statements as k_replay.cu
+                const uint8_t *b = p.bytes;
+                uint8_t *chp = w->h_chal.as<uint8_t>() + 32 * (size_t)v.ch_off;
+                ReplayIn in;
+                in.tstate = a.transcripts + BPP_TRANSCRIPT_BYTES * i;
+                in.h32 = g->h(); in.g32 = g->g(0);
+                in.bit_length = (uint32_t)n; in.ext = (uint32_t)ext; in.m = p.m; in.rounds = (uint32_t)p.rounds;
+                in.commitments32 = a.commitments32 + 32 * a.commit_offsets[i];
+                in.min_values = a.min_values + a.commit_offsets[i]; in.min_present = a.min_present + a.commit_offsets[i];
+                in.a = b + BPP_RAW_A(ext); in.a1 = in.a + 32; in.b = in.a + 64;
+                in.l_base = b + BPP_RAW_L(ext, 0); in.r_base = b + BPP_RAW_R(ext, 0); in.lr_stride = 64;
+                in.r1 = b + BPP_RAW_R1(ext); in.s1 = b + BPP_RAW_S1(ext); in.d1 = b + BPP_RAW_D1(ext, 0);
+                ReplayOut o;
+                o.y = chp; o.z = chp + 32; o.e = chp + 64; o.ej = chp + 96;
+                o.wbytes = vb->wbytes(gi); o.tstate = vb->tstate(gi);
+                int rc = replay_transcript_core(in, o);
+                uint8_t flag = rc ? 1 : 0;
+                uint8_t one[32] = {1};
+                if (!rc && !memcmp(chp, one, 32)) flag |= 2;
+                vb->flag(gi) = flag;
+            }
+            if (v.nonce_off != 0xffffffffu) {
+                uint8_t seed[32];            // Scalar::from_bytes_mod_order; a seed that is already canonical (the usual case) needs no reduction
+                const uint8_t *sb = a.seed_nonces32 + 32 * i;
+                if (host_sc_is_canonical(sb)) memcpy(seed, sb, 32);
+                else {
+                    uint32_t ww[8];
+                    memcpy(ww, sb, 32);
+                    sc s; for (int k = 0; k < 8; k++) s.v[k] = ww[k];
+                    sc_tobytes(seed, sc_reduce256(s));
+                }
+                uint8_t *nn = hb + vb->o_nonces + 32 * (size_t)v.nonce_off;
+                for (int k = 0; k < ext; k++) {
+                    nonce(seed, "eta", false, 0, true, (uint32_t)k, nn + 32 * k);
+                    nonce(seed, "d", false, 0, true, (uint32_t)k, nn + 32 * (ext + k));
+                    nonce(seed, "alpha", false, 0, true, (uint32_t)k, nn + 32 * (2 * ext + k));
+                    for (int j = 0; j < p.rounds; j++) {
+                        nonce(seed, "dL", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + j * ext + k));
+                        nonce(seed, "dR", true, (uint32_t)j, true, (uint32_t)k, nn + 32 * (3 * ext + p.rounds * ext + j * ext + k));
+                    }
+                }
+                memset(seed, 0, sizeof seed);
+            }
+        });
+    }
     lap();   // [2] fill (+ host transcript replay in host mode)
     if (host_replay) compute_weights(vb);
     lap();   // [3] weight transcripts (host mode; in device mode they run inside bpp_vbatch_run)
     cudaStream_t st = ctx->stream;
     if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
+    if (!vb->device_replay && n_chal) ok(cudaMemcpyAsync(w->d_chal.p, w->h_chal.p, 32 * (size_t)n_chal, cudaMemcpyHostToDevice, st));
     // The upload is ordered before the kernels of bpp_vbatch_run on the same stream and the pinned blob belongs to this vbatch's
     // workspace until bpp_vbatch_destroy (which drains the stream), so nothing needs the host to wait here; outside throughput mode
-    // it still does, so that upload errors surface in this call and host_ms[4] is the H2D time.  A spinning wait per call is what
-    // many lanes per host core cannot afford.
+    // it still does, so that upload errors surface in this call and host_ms[4] is the H2D time.
     static const bool always_sync = getenv("BPP_CREATE_SYNC") != nullptr;
     if (e == cudaSuccess && (!ctx->throughput_mode || always_sync)) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
     lap();   // [4] H2D
-    ctx->io_bytes[0] = vb->blob_bytes; ctx->io_bytes[1] = 0;
+    ctx->io_bytes[0] = vb->blob_bytes + (vb->device_replay ? 0 : 32 * (size_t)n_chal); ctx->io_bytes[1] = 0;
+    for (HProof &p : vb->hp) p.bytes = nullptr;      // the callers' buffers are not referenced after this point
     *out = vb;
     return BPP_OK;
+}
+
+extern "C" {
+
+void bpp_vbatch_destroy(bpp_vbatch *vb) {
+    if (!vb) return;
+    cudaSetDevice(vb->g->ctx->device);
+    cudaStreamSynchronize(vb->g->ctx->stream);
+    if (vb->w) {
+        if (vb->any_masks && vb->w->h_blob.p) memset(vb->w->h_blob.as<uint8_t>() + vb->o_nonces, 0, vb->blob_bytes - vb->o_nonces);   // seed-derived nonces
+        vwork_return(vb->g->ctx, vb->w);
+    }
+    delete vb;
+}
+
+int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *a, bpp_vbatch **out) {
+    return vbatch_create_impl(g, 1, &a, nullptr, out);
+}
+int32_t bpp_vbatch_create_multi(bpp_gens *g, size_t n_calls, const bpp_verify_args *const *calls, bpp_vbatch **out) {
+    return vbatch_create_impl(g, n_calls, calls, nullptr, out);
 }
 
 // Wait for an event without spinning and without the driver's blocking-sync machinery: poll it between short sleeps.  Measured per
 // 1024-proof pass (one lane, scripts/e2e_cpu_cost.py): cudaEventBlockingSync waits cost the process ~0.24 ms of CPU in driver
 // threads on top of the calling thread's own work; a spin wait costs the whole pass (1 ms).
-// Option (BPP_ADAPTIVE_WAIT=1, `ema_ns` != nullptr): with many lanes in flight a wait lasts several milliseconds, i.e. dozens of naps;
-// `ema_ns` remembers how long this wait took recently and the first sleep covers 3/4 of that in one go (an overshoot pulls the
-// estimate down by 30 %).  Measured with 32 lanes of 1024-proof steps: host CPU per device-resident step 0.50 -> 0.37 ms on 16 cores,
-// 0.35 -> 0.33 ms on 4 cores, throughput unchanged; end to end on 4 cores it lost 10 % (6.3 against 7.1 M proofs/s), so it is not
-// the default.
+// Option (BPP_ADAPTIVE_WAIT=1, `ema_ns` != nullptr): `ema_ns` remembers how long this wait took recently and the first sleep covers
+// 3/4 of that in one go (an overshoot pulls the estimate down by 30 %).
 static cudaError_t wait_sleeping(cudaEvent_t ev, long nap_ns, double *ema_ns) {
     cudaError_t e = cudaEventQuery(ev);
     if (e != cudaErrorNotReady) { if (ema_ns) *ema_ns *= 0.7; return e; }
@@ -731,7 +826,8 @@ struct VLaunch {
     VDims d;
     VBuffers b;
     RBuffers rb;
-    bool dev_replay, warp_replay;
+    bool dev_replay;
+    int replay_kernel;
 };
 static VLaunch make_launch(bpp_vbatch *vb) {
     bpp_gens *g = vb->g;
@@ -740,28 +836,39 @@ static VLaunch make_launch(bpp_vbatch *vb) {
     VLaunch L;
     VDims &d = L.d;
     d.n_proofs = (uint32_t)vb->n_proofs; d.n_chunks = (uint32_t)vb->n_chunks; d.bit_length = (uint32_t)g->n; d.ext = (uint32_t)g->ext;
-    d.action = vb->action;
+    d.action = vb->action; d.gens_nm = (uint32_t)g->nm;
     VBuffers &b = L.b;
-    b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.vec_offsets = vb->dev<uint32_t>(vb->o_vecoff);
-    b.proof_scalars = vb->dev<uint32_t>(vb->o_pscal); b.challenges = vb->dev<uint32_t>(vb->o_chal);
+    b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.pt_offsets = vb->dev<uint32_t>(vb->o_ptoff);
+    b.blob = w->d_blob.as<uint8_t>(); b.challenges = w->d_chal.as<uint32_t>();
     b.weights = w->d_weights.as<uint32_t>(); b.weights_mont = w->d_wmont.as<uint32_t>();
     b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
-    b.msm_scalars = w->d_mscal.as<uint32_t>(); b.contrib = w->d_contrib.as<uint32_t>(); b.hg_contrib = w->d_hg.as<uint32_t>();
+    b.msm_scalars = w->d_mscal.as<uint32_t>(); b.msm_pidx = w->d_pidx.as<uint32_t>();
+    b.contrib = w->d_contrib.as<uint32_t>(); b.hg_contrib = w->d_hg.as<uint32_t>();
     b.pervec = w->d_pervec.as<uint32_t>(); b.masks = vb->any_masks ? w->d_masks.as<uint32_t>() : nullptr;
     L.dev_replay = vb->device_replay && vb->any_replay;
     RBuffers &rb = L.rb;
     rb.proofs = b.proofs; rb.tstates_in = vb->dev<uint8_t>(vb->o_tstate); rb.hg32 = vb->dev<uint8_t>(vb->o_hg);
-    rb.enc = vb->dev<uint8_t>(vb->o_enc); rb.proof_scalars = vb->dev<uint8_t>(vb->o_pscal);
+    rb.blob = b.blob; rb.commitments32 = vb->dev<uint8_t>(vb->o_commit);
     rb.min_values = b.min_values; rb.min_present = b.min_present;
-    rb.challenges = vb->dev<uint8_t>(vb->o_chal);
+    rb.challenges = w->d_chal.as<uint8_t>();
     uint8_t *dm = w->d_mid.as<uint8_t>();
     rb.wbytes = dm + vb->mo_wbytes; rb.flags = dm + vb->mo_flags; rb.tstates_out = dm + vb->mo_tstate;
-    // one thread per proof by default.  The warp-per-proof kernel (wstrobe.cuh) was built to shorten the dependent chain of a
-    // small batch, but measured on B200 it issues 14x more warp instructions per proof (87 k vs 6 k) for a 1024-proof
-    // replay that is no shorter (283 us vs 310 us alone) and it costs 25 % of the throughput once several batches are in
-    // flight (2.9 M vs 3.7 M proofs/s with 8 lanes); it stays selectable (bpp_ctx_set_replay_mode(ctx, 3)) and tested.
-    L.warp_replay = ctx->replay_kernel == 2;
+    L.replay_kernel = ctx->replay_kernel;
     return L;
+}
+
+static void enqueue_decompress(bpp_vbatch *vb, const VLaunch &L, cudaStream_t s, uint64_t *kernels) {
+    VWork *w = vb->w;
+    launch_decompress_proofs(s, vb->n_pts, L.d.n_proofs, L.d.ext, L.b.proofs, L.b.pt_offsets, L.b.blob, L.rb.commitments32, w->d_tab.as<aniels>(),
+                             w->d_ok.as<uint8_t>());
+    (*kernels)++;
+}
+static void enqueue_msm(bpp_vbatch *vb, const VLaunch &L, cudaStream_t st, uint64_t *kernels, cudaEvent_t *marks) {
+    VWork *w = vb->w;
+    launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, w->d_pidx.as<uint32_t>(),
+               w->d_tab.as<aniels>(), vb->g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), kernels, marks);
+    launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
+    (*kernels)++;
 }
 
 // the three sections of a pass, enqueued on the ctx streams (directly, or into a stream capture); no host synchronisation
@@ -773,50 +880,43 @@ static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section
     const size_t n = vb->n_proofs;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
+    const bool prep = vb->any_msm || vb->any_masks;
     if (section == 0) {
         if (L.dev_replay) {
-            launch_replay(st, L.d, L.rb, L.warp_replay, kernels);
+            launch_replay(st, L.d, L.rb, L.replay_kernel, kernels);
             ok(cudaMemcpyAsync(vb->mid(), w->d_mid.p, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
         }
     } else if (section == 1) {
-        const bool prep = vb->any_msm || vb->any_masks;
         const bool fork = vb->n_pts && prep;          // decompression next to the scalar prep chain, joined at the end of the section
         if (vb->n_pts) {
             if (fork) { ok(cudaEventRecord(ctx->ev_fork, st)); ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
-            launch_decompress(fork ? ctx->stream2 : st, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), w->d_tab.as<aniels>(), w->d_ok.as<uint8_t>(), nullptr, nullptr);
-            (*kernels)++;
+            enqueue_decompress(vb, L, fork ? ctx->stream2 : st, kernels);
             if (fork) ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
         }
-        if (prep) launch_verify_prep(st, L.d, L.b, vb->total_vec, vb->max_rounds, kernels, nullptr);
+        if (prep) launch_verify_prep(st, L.d, L.b, vb->any_vec ? 1u : 0u, vb->max_rounds, kernels, nullptr);
         if (fork) ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     } else if (section == 3) {
-        // throughput mode: the whole pass without a host step.  st: replay -> D2H(flags, transcripts) -> scalar prep -> [weights]
+        // throughput mode 2: the whole pass without a host step.  st: replay -> D2H(flags, transcripts) -> scalar prep -> [weights]
         // -> weighting -> [points] -> MSM -> verdicts;  stream2: decompression (from the start);  stream3: weight transcripts
-        // (after the replay)
-        const bool prep = vb->any_msm || vb->any_masks;
         const bool fork_pts = vb->n_pts != 0;
         if (fork_pts) {
             ok(cudaEventRecord(ctx->ev_fork, st)); ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-            launch_decompress(ctx->stream2, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), w->d_tab.as<aniels>(), w->d_ok.as<uint8_t>(), nullptr, nullptr);
-            (*kernels)++;
+            enqueue_decompress(vb, L, ctx->stream2, kernels);
             ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
         }
-        launch_replay(st, L.d, L.rb, L.warp_replay, kernels);
+        launch_replay(st, L.d, L.rb, L.replay_kernel, kernels);
         if (vb->any_msm) {
             ok(cudaEventRecord(ctx->ev_fork2, st)); ok(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork2, 0));
             launch_weights(ctx->stream3, L.d, L.b.chunks, vb->dev<uint8_t>(vb->o_wtinit), L.rb.wbytes, L.rb.flags, w->d_weights.as<uint32_t>(), kernels);
             ok(cudaEventRecord(ctx->ev_join2, ctx->stream3));
         }
         ok(cudaMemcpyAsync(vb->mid(), w->d_mid.p, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
-        if (prep) launch_verify_prep(st, L.d, L.b, vb->total_vec, vb->max_rounds, kernels, nullptr);
+        if (prep) launch_verify_prep(st, L.d, L.b, vb->any_vec ? 1u : 0u, vb->max_rounds, kernels, nullptr);
         if (vb->any_msm) {
             ok(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
             launch_verify_weigh(st, L.d, L.b, vb->max_static, kernels);
             if (fork_pts) ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-            launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
-                       w->d_tab.as<aniels>(), g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), kernels, nullptr);
-            launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
-            (*kernels)++;
+            enqueue_msm(vb, L, st, kernels, nullptr);
             ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
         } else if (fork_pts) {
             ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -827,10 +927,7 @@ static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section
         if (vb->any_msm) {
             ok(cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 32 * n, cudaMemcpyHostToDevice, st));
             launch_verify_weigh(st, L.d, L.b, vb->max_static, kernels);
-            launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
-                       w->d_tab.as<aniels>(), g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), kernels, nullptr);
-            launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
-            (*kernels)++;
+            enqueue_msm(vb, L, st, kernels, nullptr);
             ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
         }
         if (vb->n_pts) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
@@ -844,20 +941,23 @@ static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L, bool fus
     VGraphKey k;
     memset(&k, 0, sizeof k);
     const VWork *w = vb->w;
-    const void *bufs[18] = {w->d_blob.p, w->d_tab.p, w->d_ok.p, w->d_mscal.p, w->d_contrib.p, w->d_hg.p, w->d_pervec.p, w->d_masks.p, w->d_scratch.p,
-                            w->d_res.p, w->d_ident.p, w->d_weights.p, w->d_wmont.p, w->d_mid.p, w->h_blob.p, w->h_out.p, w->h_mid.p, w->h_weights.p};
+    const void *bufs[21] = {w->d_blob.p, w->d_tab.p, w->d_ok.p, w->d_mscal.p, w->d_pidx.p, w->d_chal.p, w->d_contrib.p, w->d_hg.p, w->d_pervec.p,
+                            w->d_masks.p, w->d_scratch.p, w->d_res.p, w->d_ident.p, w->d_weights.p, w->d_wmont.p, w->d_mid.p, w->h_blob.p, w->h_out.p,
+                            w->h_mid.p, w->h_weights.p, w->h_chal.p};
     memcpy(k.bufs, bufs, sizeof bufs);
     k.gens_table = vb->g->d_table.p;
-    k.n_proofs = vb->n_proofs; k.n_chunks = vb->n_chunks;
-    const size_t off[23] = {vb->o_wtinit, vb->o_enc, vb->o_proofs, vb->o_chunks, vb->o_vecoff, vb->o_pscal, vb->o_chal, vb->o_minv, vb->o_minp, vb->o_nonces, vb->o_pidx,
-                            vb->o_segoff, vb->o_tstate, vb->o_hg, vb->blob_bytes, vb->mo_wbytes, vb->mo_flags, vb->mo_tstate, vb->mid_bytes,
+    k.n_proofs = vb->n_proofs; k.n_chunks = vb->n_chunks; k.n_commit = vb->n_commit;
+    const size_t off[21] = {vb->o_proofs, vb->o_chunks, vb->o_ptoff, vb->o_segoff, vb->o_hg, vb->o_wtinit, vb->o_minv, vb->o_minp, vb->o_commit, vb->o_raw,
+                            vb->o_tstate, vb->o_nonces, vb->blob_bytes, vb->mo_wbytes, vb->mo_flags, vb->mo_tstate, vb->mid_bytes,
                             vb->ho_ok, vb->ho_ident, vb->ho_masks, vb->hout_bytes};
     memcpy(k.off, off, sizeof off);
-    k.n_pts = vb->n_pts; k.n_entries = vb->n_entries; k.total_vec = vb->total_vec; k.max_static = vb->max_static; k.max_rounds = vb->max_rounds;
+    k.n_pts = vb->n_pts; k.n_entries = vb->n_entries; k.n_chal = vb->n_chal; k.max_static = vb->max_static; k.max_rounds = vb->max_rounds;
     k.action = vb->action; k.ext = vb->g->ext; k.bit_length = vb->g->n;
     k.shape.n_entries = vb->shape.n_entries; k.shape.n_seg = vb->shape.n_seg; k.shape.c = vb->shape.c; k.shape.W = vb->shape.W; k.shape.B = vb->shape.B;
-    k.any_msm = vb->any_msm; k.any_masks = vb->any_masks; k.any_replay = vb->any_replay; k.device_replay = L.dev_replay; k.warp_replay = L.warp_replay;
-    k.fused = fused;
+    msm_knobs(k.msm_knobs);
+    k.any_msm = vb->any_msm; k.any_masks = vb->any_masks; k.any_replay = vb->any_replay; k.any_vec = vb->any_vec;
+    k.device_replay = L.dev_replay; k.replay_kernel = (uint8_t)L.replay_kernel;
+    k.fused = fused; k.caller_challenges = vb->caller_challenges;
     return k;
 }
 
@@ -896,8 +996,10 @@ static VGraph *vgraph_get(bpp_vbatch *vb, const VLaunch &L, bool fused, cudaErro
     return g;
 }
 
-int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present) {
+// per-call output buffers: chunk_status[c] (that call's n_chunks), masks32[c] (its n_proofs x ext x 32, may be null), mask_present[c]
+int32_t bpp_vbatch_run_multi(bpp_vbatch *vb, int32_t *const *chunk_status, uint8_t *const *masks32, uint8_t *const *mask_present) {
     if (!vb || !chunk_status) return BPP_INVALID_ARGUMENT;
+    for (size_t c = 0; c < vb->calls.size(); c++) if (!chunk_status[c]) return BPP_INVALID_ARGUMENT;
     bpp_gens *g = vb->g;
     bpp_ctx *ctx = g->ctx;
     cudaSetDevice(ctx->device);
@@ -909,12 +1011,9 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     const VDims &d = L.d;
     const VBuffers &b = L.b;
     const bool dev_replay = L.dev_replay;
+    const bool prep = vb->any_msm || vb->any_masks;
 
     ctx->clear_marks();
-    // debug aid (BPP_RUN_CPU_TRACE=1): CPU time of the calling thread per section of this function, printed to stderr
-    static const bool cpu_trace = getenv("BPP_RUN_CPU_TRACE") != nullptr;
-    auto cpu_us = []() { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
-    double tc[6] = {cpu_trace ? cpu_us() : 0, 0, 0, 0, 0, 0};
     const bool fused = ctx->device_weights && dev_replay && ctx->use_graphs && !ctx->phase_timing;
     if (fused) {
         cudaError_t ge = cudaSuccess;
@@ -932,16 +1031,13 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
             BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
         }
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[1], st));
-        if (cpu_trace) tc[1] = cpu_us();
         if (dev_replay) {       // the host hashes the weight transcripts while the device runs section B
             if (ctx->throughput_mode) BPP_CUDA(ctx, wait_sleeping(ctx->ev_mid, ctx->nap_ns, ctx->adaptive_wait ? &ctx->wait_ema_ns[0] : nullptr));
             else BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_mid));
-            if (cpu_trace) tc[2] = cpu_us();
             auto tw = std::chrono::steady_clock::now();
             compute_weights(vb);
             ctx->host_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
         }
-        if (cpu_trace) tc[3] = cpu_us();
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[2], st));
         ctx->launches += vg->kernels[0] + vg->kernels[1] + vg->kernels[2];
         ctx->graph_launches += vg->ex[0] ? 3 : 2;
@@ -949,28 +1045,24 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     // The decompression (k_point.cu) only feeds the bucket sums, so it runs on the side stream next to the transcript
     // replay and the scalar prep chain; with phase timing on everything stays on one stream so that the per-phase events
     // mean what they say (replay, then decompress, then the prep).
-    const bool overlap = !ctx->phase_timing && vb->n_pts && (vb->any_msm || vb->any_masks);
-    auto decompress = [&](cudaStream_t ds) {
-        launch_decompress(ds, vb->n_pts, vb->dev<uint32_t>(vb->o_enc), w->d_tab.as<aniels>(), w->d_ok.as<uint8_t>(), nullptr, nullptr);
-        ctx->launches++;
-    };
+    const bool overlap = !ctx->phase_timing && vb->n_pts && prep;
     if (overlap) {
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         BPP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        decompress(ctx->stream2);
+        enqueue_decompress(vb, L, ctx->stream2, &ctx->launches);
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
     }
     ctx->mark(0);
     if (dev_replay) {
-        launch_replay(st, d, L.rb, L.warp_replay, &ctx->launches);
+        launch_replay(st, d, L.rb, L.replay_kernel, &ctx->launches);
         BPP_CUDA(ctx, cudaMemcpyAsync(vb->mid(), w->d_mid.p, vb->mid_bytes, cudaMemcpyDeviceToHost, st));
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_mid, st));
     }
     ctx->mark(1);
-    if (!overlap && vb->n_pts) decompress(st);
+    if (!overlap && vb->n_pts) enqueue_decompress(vb, L, st, &ctx->launches);
     ctx->mark(2);
-    if (vb->any_msm || vb->any_masks) {
-        launch_verify_prep(st, d, b, vb->total_vec, vb->max_rounds, &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
+    if (prep) {
+        launch_verify_prep(st, d, b, vb->any_vec ? 1u : 0u, vb->max_rounds, &ctx->launches, ctx->phase_timing ? &ctx->ph[3] : nullptr);
         if (ctx->phase_timing) { ctx->ph_set[3] = true; ctx->ph_set[4] = true; }
     }
     if (dev_replay) {       // the host hashes the weight transcripts while the device runs the weight-free scalar prep
@@ -983,13 +1075,9 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
         launch_verify_weigh(st, d, b, vb->max_static, &ctx->launches);
         ctx->mark(6);
         if (overlap) BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-        launch_msm(st, vb->shape, w->d_mscal.as<uint32_t>(), vb->n_chunks > 1 ? vb->dev<uint32_t>(vb->o_segoff) : nullptr, vb->dev<uint32_t>(vb->o_pidx),
-                   w->d_tab.as<aniels>(), g->d_table.as<aniels>(), w->d_scratch.p, w->d_res.as<ge>(), &ctx->launches,
-                   ctx->phase_timing ? &ctx->ph[7] : nullptr);
+        enqueue_msm(vb, L, st, &ctx->launches, ctx->phase_timing ? &ctx->ph[7] : nullptr);
         if (ctx->phase_timing) for (int i = 7; i <= 10; i++) ctx->ph_set[i] = true;
-        launch_encode(st, vb->n_chunks, w->d_res.as<ge>(), nullptr, w->d_ident.as<uint8_t>());
         ctx->mark(11);
-        ctx->launches++;
         BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
     } else if (overlap) {
         BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -1004,17 +1092,20 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
     } else {
         BPP_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    if (cpu_trace) tc[4] = cpu_us();
     vb->ran = true;
-    ctx->io_bytes[0] = vb->blob_bytes + (vb->any_msm && !fused ? 32 * n : 0);
+    ctx->io_bytes[0] = vb->blob_bytes + (vb->device_replay ? 0 : 32 * (size_t)vb->n_chal) + (vb->any_msm && !fused ? 32 * n : 0);
     ctx->io_bytes[1] = (dev_replay ? vb->mid_bytes : 0) + vb->n_pts + (vb->any_msm ? vb->n_chunks : 0) + (vb->any_masks ? 32 * n * (size_t)ext : 0);
 
     // ---- resolve per-chunk status with the reference's precedence
     const uint8_t *okf = w->h_out.as<uint8_t>() + vb->ho_ok;
     const uint8_t *ident = w->h_out.as<uint8_t>() + vb->ho_ident;
     const uint8_t *hmasks = w->h_out.as<uint8_t>() + vb->ho_masks;
+    size_t call = 0;
     for (size_t c = 0; c < vb->n_chunks; c++) {
         const HChunk &hc = vb->hc[c];
+        while (c >= vb->calls[call].chunk0 + vb->calls[call].a.n_chunks) call++;
+        const HCall &hcall = vb->calls[call];
+        uint8_t *c_masks = masks32 ? masks32[call] : nullptr, *c_present = mask_present ? mask_present[call] : nullptr;
         int32_t rc = hc.pre_rc;
         if (!rc) {   // a commitment that is not a valid encoding can not be a RangeStatement commitment (a point)
             for (size_t i = hc.lo; i < hc.hi && !rc; i++) {
@@ -1029,40 +1120,65 @@ int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, 
             const HProof &p = vb->hp[i];
             for (uint32_t j = 0; j < 3 + 2 * (uint32_t)p.rounds; j++)
                 if (!okf[p.pt_off + j]) { rc = BPP_INVALID_ARGUMENT; break; }             // :859-866
-            if (!rc) rc = p.loop2_rc;                                                       // :886-888
+            if (!rc) rc = p.loop2_rc;                                                       // :875-888
             if (!rc && (vb->flag(i) & 2)) rc = BPP_VERIFICATION_FAILED;                     // y == 1: (y - 1) is not invertible
         }
         if (!rc && vb->action != BPP_RECOVER_ONLY && !ident[c]) rc = BPP_VERIFICATION_FAILED;   // :1057-1061
-        chunk_status[c] = rc;
+        chunk_status[call][c - hcall.chunk0] = rc;
         // Vec<Option<ExtendedMask>>
-        for (size_t i = vb->chunk_offsets[c]; i < vb->chunk_offsets[c + 1]; i++) {
+        for (size_t i = hc.lo; i < hc.end; i++) {
+            const size_t li = i - hcall.proof0;
             bool have = !rc && i < hc.hi && vb->action != BPP_VERIFY_ONLY && vb->hp[i].has_seed;
-            if (mask_present) mask_present[i] = have ? 1 : 0;
-            if (masks32) {
-                if (have) memcpy(masks32 + 32 * i * (size_t)ext, hmasks + 32 * i * (size_t)ext, 32 * (size_t)ext);
-                else memset(masks32 + 32 * i * (size_t)ext, 0, 32 * (size_t)ext);
+            if (c_present) c_present[li] = have ? 1 : 0;
+            if (c_masks) {
+                if (have) memcpy(c_masks + 32 * li * (size_t)ext, hmasks + 32 * i * (size_t)ext, 32 * (size_t)ext);
+                else memset(c_masks + 32 * li * (size_t)ext, 0, 32 * (size_t)ext);
             }
         }
-    }
-    if (cpu_trace) {
-        tc[5] = cpu_us();
-        fprintf(stderr, "bpp_vbatch_run cpu us: graphs A+B %.1f | wait mid %.1f | weights %.1f | graph C %.1f(incl. launch) wait end %.1f | resolve %.1f\n",
-                tc[1] - tc[0], tc[2] - tc[1], tc[3] - tc[2], 0.0, tc[4] - tc[3], tc[5] - tc[4]);
     }
     return BPP_OK;
 }
 
+// the calls' outputs concatenated in order: chunk_status[n_chunks], masks32[n_proofs x ext x 32], mask_present[n_proofs]
+int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present) {
+    if (!vb || !chunk_status) return BPP_INVALID_ARGUMENT;
+    const size_t nc = vb->calls.size();
+    std::vector<int32_t *> st(nc);
+    std::vector<uint8_t *> mk(nc), mp(nc);
+    for (size_t c = 0; c < nc; c++) {
+        const HCall &h = vb->calls[c];
+        st[c] = chunk_status + h.chunk0;
+        mk[c] = masks32 ? masks32 + 32 * h.proof0 * (size_t)vb->g->ext : nullptr;
+        mp[c] = mask_present ? mask_present + h.proof0 : nullptr;
+    }
+    return bpp_vbatch_run_multi(vb, st.data(), masks32 ? mk.data() : nullptr, mask_present ? mp.data() : nullptr);
+}
+
+size_t bpp_vbatch_call_count(const bpp_vbatch *vb) { return vb ? vb->calls.size() : 0; }
+
 // `&mut Transcript` semantics of the reference: every transcript of a call that reached loop 1 is advanced, up to and
-// including the first proof whose replay failed.  transcripts: n_proofs x 203 bytes, updated in place.
-int32_t bpp_vbatch_transcripts(const bpp_vbatch *vb, uint8_t *transcripts) {
-    if (!vb || !transcripts) return BPP_INVALID_ARGUMENT;
+// including the first proof whose replay failed.  transcripts: the proofs of call `call` x 203 bytes, updated in place.
+int32_t bpp_vbatch_transcripts_call(const bpp_vbatch *vb, size_t call, uint8_t *transcripts) {
+    if (!vb || !transcripts || call >= vb->calls.size()) return BPP_INVALID_ARGUMENT;
+    if (vb->caller_challenges) return fail(vb->g->ctx, BPP_INVALID_ARGUMENT, "the caller keeps the transcripts in the challenge-input form");
     if (vb->device_replay && !vb->ran) return fail(vb->g->ctx, BPP_INVALID_ARGUMENT, "bpp_vbatch_run has not been called");
-    for (const HChunk &hc : vb->hc) {
+    const HCall &hcall = vb->calls[call];
+    for (size_t c = hcall.chunk0; c < hcall.chunk0 + hcall.a.n_chunks; c++) {
+        const HChunk &hc = vb->hc[c];
         if (hc.pre_rc) continue;
         for (size_t i = hc.lo; i < hc.hi; i++) {
-            memcpy(transcripts + BPP_TRANSCRIPT_BYTES * i, vb->tstate(i), BPP_TRANSCRIPT_BYTES);
+            memcpy(transcripts + BPP_TRANSCRIPT_BYTES * (i - hcall.proof0), vb->tstate(i), BPP_TRANSCRIPT_BYTES);
             if (vb->flag(i) & 1) break;
         }
+    }
+    return BPP_OK;
+}
+// all calls of the pass, concatenated (n_proofs x 203 B)
+int32_t bpp_vbatch_transcripts(const bpp_vbatch *vb, uint8_t *transcripts) {
+    if (!vb || !transcripts) return BPP_INVALID_ARGUMENT;
+    for (size_t c = 0; c < vb->calls.size(); c++) {
+        int32_t rc = bpp_vbatch_transcripts_call(vb, c, transcripts + BPP_TRANSCRIPT_BYTES * vb->calls[c].proof0);
+        if (rc) return rc;
     }
     return BPP_OK;
 }
@@ -1075,6 +1191,19 @@ int32_t bpp_verify_chunks(bpp_gens *g, const bpp_verify_args *args, int32_t *chu
     rc = bpp_vbatch_run(vb, chunk_status, masks32, mask_present);
     g->ctx->host_ms[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (!rc) rc = bpp_vbatch_transcripts(vb, args->transcripts);
+    bpp_vbatch_destroy(vb);
+    return rc;
+}
+
+// Challenge-input form: loop 1 of RangeProof::verify (:816-850) and the weight draw (:894) stay with a caller that
+// keeps merlin::Transcript itself; everything from the point decompression on runs here.
+int32_t bpp_verify_chunks_ch(bpp_gens *g, const bpp_verify_args *args, const bpp_verify_challenges *ch, int32_t *chunk_status, uint8_t *masks32,
+                             uint8_t *mask_present) {
+    if (!ch) return BPP_INVALID_ARGUMENT;
+    bpp_vbatch *vb = nullptr;
+    int32_t rc = vbatch_create_impl(g, 1, &args, &ch, &vb);
+    if (rc) return rc;
+    rc = bpp_vbatch_run(vb, chunk_status, masks32, mask_present);
     bpp_vbatch_destroy(vb);
     return rc;
 }

@@ -102,6 +102,25 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     return sh;
 }
 
+// the switches below select kernel variants (tests / experiments); getenv is neither cheap nor safe against a concurrent setenv, so
+// they are read once
+namespace {
+struct MsmKnobs { int bucket, split, reduce, reduce_parts; };
+const MsmKnobs &knobs() {
+    static const MsmKnobs k = [] {
+        auto geti = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
+        MsmKnobs r;
+        r.bucket = geti("BPP_MSM_BUCKET", 0);                 // 1 = quads, 2 = threads, 3 = split threads
+        r.split = geti("BPP_MSM_SPLIT", 4);
+        r.reduce = geti("BPP_MSM_REDUCE", 0);                 // 1 = CTA of quads, 2 = warp of threads
+        r.reduce_parts = geti("BPP_MSM_REDUCE_PARTS", 0);
+        return r;
+    }();
+    return k;
+}
+}
+void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts; }
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #define SCAN_TILE 4096u
 #define REDUCE_PARTS_MAX 8u
@@ -583,7 +602,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     // sub-partition on; from 1 warp on only while the buckets are short (a thread walks its bucket alone: 2^16 points at c = 11
     // are 64 additions per bucket, measured 82 M points/s with quads against 75 M with threads; the verifier's 4226-entry
     // segments are 16 per bucket and 8 % faster with threads)
-    const int force_bucket = getenv("BPP_MSM_BUCKET") ? atoi(getenv("BPP_MSM_BUCKET")) : 0;      // 1 = quads, 2 = threads, 3 = split threads (tests)
+    const int force_bucket = knobs().bucket;      // 1 = quads, 2 = threads, 3 = split threads (tests)
     const size_t full = 148u * 4u * 32u;
     const size_t adds = (size_t)sh.n_entries * sh.W;
     const bool thread_buckets = force_bucket ? force_bucket == 2
@@ -593,7 +612,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     // phase, quads -> split): 2^14 c = 9: 146 -> 86 us; 2^15: 266 -> 135; 2^16 c = 11: 391 -> 231; 2^17: 764 -> 391; 2^18 c = 12:
     // 821 -> 533 (whole threads: 767)
     int split = 0;
-    if (force_bucket == 3) split = getenv("BPP_MSM_SPLIT") ? atoi(getenv("BPP_MSM_SPLIT")) : 4;
+    if (force_bucket == 3) split = knobs().split;
     else if (!force_bucket && !thread_buckets && n_keys >= 1024) {
         const double want = 170000.0 / (double)n_keys;
         split = want >= 5.66 ? 8 : want >= 2.83 ? 4 : want >= 1.42 ? 2 : 1;
@@ -609,7 +628,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     else
         k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
     if (marks) cudaEventRecord(marks[1], s);
-    const int force_reduce = getenv("BPP_MSM_REDUCE") ? atoi(getenv("BPP_MSM_REDUCE")) : 0;      // 1 = CTA of quads, 2 = warp of threads (tests)
+    const int force_reduce = knobs().reduce;      // 1 = CTA of quads, 2 = warp of threads (tests)
     if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
         uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         k_msm_reduce_small<<<(n_win + 31) / 32, 128, 0, s>>>(n_win, sh.B, sc.buckets, sc.windows);
@@ -625,8 +644,8 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         const uint32_t n_win = sh.n_seg * (uint32_t)sh.W;
         uint32_t quads = sh.B >= 8 ? sh.B / 8 : 1, parts = 1;
         while (parts < REDUCE_PARTS_MAX && quads / parts > 128 && n_win * parts * 2 <= 2 * 148u /* CTAs after the split */) parts <<= 1;
-        if (const char *env = getenv("BPP_MSM_REDUCE_PARTS")) {
-            uint32_t v = (uint32_t)atoi(env);
+        {
+            const uint32_t v = (uint32_t)knobs().reduce_parts;
             if ((v == 1 || v == 2 || v == 4 || v == 8) && quads % v == 0) parts = v;
         }
         uint32_t nq = quads / parts;                   // quads per CTA

@@ -4,6 +4,7 @@
 // /root/reference/src/range_proof.rs:859-866,1067-1109 and :289,:348,:499-504,:587,:598-605,
 // /root/reference/src/range_statement.rs:62-65, /root/reference/src/ristretto.rs:48-52.
 #include "kernels.cuh"
+#include "rawld.cuh"
 
 namespace bpp {
 
@@ -37,6 +38,36 @@ __global__ void __launch_bounds__(128) k_decompress(size_t n, const uint32_t *__
         fe s = ristretto_encode(p);
         store8(out_enc + 8 * i, s.v);
     }
+}
+
+// K-DECOMPRESS over the points of a verification pass, read from the uploaded proof bytes / commitments (no host-side gather):
+// thread i finds its proof by binary search over the per-proof point offsets, then its slot's 32 bytes inside the serialised proof
+__global__ void __launch_bounds__(128) k_decompress_proofs(uint32_t n_pts, uint32_t n_proofs, uint32_t ext, const VProof *__restrict__ proofs,
+                                                          const uint32_t *__restrict__ pt_offsets, const uint8_t *__restrict__ blob,
+                                                          const uint8_t *__restrict__ commitments32, aniels *__restrict__ out_tab,
+                                                          uint8_t *__restrict__ ok) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pts) return;
+    uint32_t lo = 0, hi = n_proofs;                     // invariant: pt_offsets[lo] <= i < pt_offsets[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pt_offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t slot = i - pt_offsets[lo];
+    const uint32_t R = proofs[lo].rounds, raw = proofs[lo].raw_off;
+    const uint8_t *src;
+    if (slot < 3) src = blob + raw + BPP_RAW_A(ext) + 32u * slot;
+    else if (slot < 3 + R) src = blob + raw + BPP_RAW_L(ext, slot - 3);
+    else if (slot < 3 + 2 * R) src = blob + raw + BPP_RAW_R(ext, slot - 3 - R);
+    else src = commitments32 + 32u * (size_t)(proofs[lo].commit_off + (slot - 3 - 2 * R));
+    uint32_t w[8];
+    ld32_unaligned(src, w);
+    fe x, y, t;
+    const bool good = ristretto_decode(x, y, t, w);
+    if (!good) { x = fe_zero(); y = fe_one(); t = fe_zero(); }
+    ok[i] = good ? 1 : 0;
+    aniels q = ge_to_aniels_affine(x, y, t);
+    store_fe(&out_tab[i].ypx, q.ypx); store_fe(&out_tab[i].ymx, q.ymx); store_fe(&out_tab[i].t2d, q.t2d);
 }
 
 __global__ void __launch_bounds__(128) k_encode(size_t n, const ge *__restrict__ in, uint32_t *__restrict__ out_enc,
@@ -78,6 +109,11 @@ void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out
                        uint32_t *bad_count) {
     if (n == 0) return;
     k_decompress<<<grid_for(n, 128), 128, 0, s>>>(n, in, out_tab, ok, out_enc, bad_count);
+}
+void launch_decompress_proofs(cudaStream_t s, uint32_t n_pts, uint32_t n_proofs, uint32_t ext, const VProof *proofs, const uint32_t *pt_offsets,
+                              const uint8_t *blob, const uint8_t *commitments32, aniels *out_tab, uint8_t *ok) {
+    if (n_pts == 0) return;
+    k_decompress_proofs<<<grid_for(n_pts, 128), 128, 0, s>>>(n_pts, n_proofs, ext, proofs, pt_offsets, blob, commitments32, out_tab, ok);
 }
 void launch_encode(cudaStream_t s, size_t n, const ge *in, uint32_t *out_enc, uint8_t *is_identity) {
     if (n == 0) return;

@@ -16,6 +16,7 @@
 // All arithmetic is mod l in Montgomery form (arith.cuh sc_montmul); results are bit-exact canonical scalars.
 #include <stdlib.h>
 #include "kernels.cuh"
+#include "rawld.cuh"
 
 namespace bpp {
 
@@ -31,6 +32,12 @@ static __device__ __forceinline__ void st_sc(uint32_t *p, const sc &r) {
 }
 static __device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_montmul(a, b); }
 static __device__ __forceinline__ sc ld_mont(const uint32_t *p) { return sc_to_mont(ld_sc(p)); }
+// a canonical scalar inside the uploaded proof bytes (any alignment) -> Montgomery form
+static __device__ __forceinline__ sc ld_raw_mont(const uint8_t *p) {
+    sc r;
+    ld32_unaligned(p, r.v);
+    return sc_to_mont(r);
+}
 
 // pervec layout (scalars, Montgomery form), per proof at pv_off (the batch weight is applied by stages W / C).
 // Bit k of i corresponds to challenge e_j with j = R-1-k (range_proof.rs:987-996: s[i] = prod_j e_j^(+-1)):
@@ -53,8 +60,8 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     const sc one_m = sc_const_R();                 // 1 in Montgomery form
     const uint32_t *ch = b.challenges + 8 * (size_t)pr.ch_off;
     sc y = ld_mont(ch), z = ld_mont(ch + 8), e = ld_mont(ch + 16);
-    const uint32_t *ps = b.proof_scalars + 8 * (size_t)pr.sc_off;
-    sc r1 = ld_mont(ps), s1 = ld_mont(ps + 8);
+    const uint8_t *raw = b.blob + pr.raw_off;
+    sc r1 = ld_raw_mont(raw + BPP_RAW_R1(ext)), s1 = ld_raw_mont(raw + BPP_RAW_S1(ext));
 
     sc z2 = mm(z, z), e2 = mm(e, e);
     sc yN = y;
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
         const uint32_t *nn = b.nonces + 8 * (size_t)pr.nonce_off;
         sc e2inv = mm(e_inv, e_inv);
         for (uint32_t k = 0; k < ext; k++) {
-            sc d1k = ld_mont(ps + 16 + 8 * k);
+            sc d1k = ld_raw_mont(raw + BPP_RAW_D1(ext, k));
             sc eta = ld_mont(nn + 8 * k), dk = ld_mont(nn + 8 * (ext + k)), alpha = ld_mont(nn + 8 * (2 * ext + k));
             sc mask = sc_sub(sc_sub(d1k, eta), mm(e, dk));
             mask = sc_sub(mm(mask, e2inv), alpha);
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     h = sc_add(h, sc_add(t, mm(e2, u)));
     uint32_t *hg = b.hg_contrib + 8 * (size_t)p * (1 + ext);
     st_sc(hg, h);
-    for (uint32_t k = 0; k < ext; k++) st_sc(hg + 8 * (1 + k), ld_mont(ps + 16 + 8 * k));
+    for (uint32_t k = 0; k < ext; k++) st_sc(hg + 8 * (1 + k), ld_raw_mont(raw + BPP_RAW_D1(ext, k)));
 
     // hand-off to stage B (layout above); pre[R] = prod e_j = s[N-1]
     st_sc(pv, mm(mm(e, r1), s0));
@@ -245,7 +252,12 @@ __global__ void __launch_bounds__(128) k_vprep_reduce(VDims d, VBuffers b) {
         if (src) acc = sc_add(acc, mm(ld_sc(src), ld_sc(b.weights_mont + 8 * (size_t)p)));
     }
     for (int delta = 16; delta > 0; delta >>= 1) acc = sc_add(acc, shfl_down_sc(acc, delta));
-    if (lane == 0) st_sc(b.msm_scalars + 8 * ((size_t)chk.entry_off + slot), sc_from_mont(acc));
+    if (lane == 0) {
+        st_sc(b.msm_scalars + 8 * ((size_t)chk.entry_off + slot), sc_from_mont(acc));
+        // the chunk's static entries: Gi[0, max_mn) | Hi[0, max_mn) | G[0, ext) | H in the generator table Gi(nm) | Hi(nm) | G | H
+        const uint32_t gi = slot < chk.max_mn ? slot : slot < 2 * chk.max_mn ? d.gens_nm + (slot - chk.max_mn) : 2 * d.gens_nm + (slot - 2 * chk.max_mn);
+        b.msm_pidx[chk.entry_off + slot] = 0x80000000u | gi;
+    }
 }
 
 // one warp per proof: w_p -> Montgomery form (kept for k_vprep_reduce), dynamic scalars *= w_p and leave Montgomery form
@@ -258,7 +270,11 @@ __global__ void __launch_bounds__(128) k_vprep_weight(VDims d, VBuffers b) {
     if (lane == 0) st_sc(b.weights_mont + 8 * (size_t)p, w);
     const uint32_t n_dyn = 3 + 2 * pr.rounds + pr.m;
     uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;
-    for (uint32_t t = lane; t < n_dyn; t += 32) st_sc(out + 8 * t, sc_from_mont(mm(ld_sc(out + 8 * t), w)));
+    for (uint32_t t = lane; t < n_dyn; t += 32) {
+        st_sc(out + 8 * t, sc_from_mont(mm(ld_sc(out + 8 * t), w)));
+        // entries [A1, B, A, L.., R.., V..] against the point table [A, A1, B, L.., R.., V..]
+        b.msm_pidx[pr.entry_off + t] = pr.pt_off + (t == 0 ? 1u : t == 1 ? 2u : t == 2 ? 0u : t);
+    }
 }
 
 void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_rounds, uint64_t *launches,

@@ -11,6 +11,11 @@ namespace bpp {
 // invalid); ok: 1/0; out_enc (optional): re-encoding of the decoded point (8 words); bad_count (optional): += #invalid.
 void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out_tab, uint8_t *ok, uint32_t *out_enc,
                        uint32_t *bad_count);
+// the points of a verification pass straight from the uploaded proof bytes and commitments: point i belongs to the proof p with
+// pt_offsets[p] <= i < pt_offsets[p + 1], slot i - pt_offsets[p] of [A, A1, B, L_0.., R_0.., V_0..] (kernels.cuh VProof)
+struct VProof;
+void launch_decompress_proofs(cudaStream_t s, uint32_t n_pts, uint32_t n_proofs, uint32_t ext, const VProof *proofs, const uint32_t *pt_offsets,
+                              const uint8_t *blob, const uint8_t *commitments32, aniels *out_tab, uint8_t *ok);
 // extended points -> encodings (8 words each) and/or identity flags
 void launch_encode(cudaStream_t s, size_t n, const ge *in, uint32_t *out_enc, uint8_t *is_identity);
 // 64-byte uniform strings -> points: encodings and/or affine-Niels table entries
@@ -27,6 +32,9 @@ struct MsmShape {
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c);
 // bytes of scratch needed for a shape
 size_t msm_scratch_bytes(const MsmShape &sh);
+// experiment / test switches of launch_msm (BPP_MSM_BUCKET, BPP_MSM_SPLIT, BPP_MSM_REDUCE, BPP_MSM_REDUCE_PARTS), read from the environment
+// ONCE per process; callers that cache launch sequences (CUDA graphs) key them on these values
+void msm_knobs(int32_t out[4]);
 // scalars: n_entries x 8 words, canonical.  seg_offsets: n_seg + 1 entry offsets (nullptr when n_seg == 1).
 // pidx: per-entry index into `gens` (bit 31 set), `dync` (bit 30 set: projective "cached" points) or `dyn`; nullptr = identity
 // mapping into dyn.
@@ -54,7 +62,7 @@ void launch_fb_msm(cudaStream_t s, const FbShape &sh, uint32_t n_seg, uint32_t s
 struct VProof {            // per-proof metadata, device-resident
     uint32_t m;            // aggregation factor (commitments)
     uint32_t rounds;       // log2(n * m)
-    uint32_t sc_off;       // first proof scalar (in scalars): [r1, s1, d1..]
+    uint32_t raw_off;      // byte offset of the serialised proof (to_bytes layout, range_proof.rs:1120-1150) from the start of the blob
     uint32_t ch_off;       // first challenge: [y, z, e, e_0..e_{r-1}]
     uint32_t entry_off;    // first dynamic MSM entry of this proof: [A1, B, A, L.., R.., V..]
     uint32_t commit_off;   // first commitment (min_values / min_present index)
@@ -71,17 +79,25 @@ struct VChunk {
     uint32_t entry_off;    // first MSM entry of the chunk: [Gi(max_mn) | Hi(max_mn) | G(ext) | H | dynamic...]
     uint32_t active;
 };
-struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext; int action; };
+struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext; int action; uint32_t gens_nm; };   // gens_nm = bit_length * max_aggregation
+// field offsets inside a serialised proof: [ext:u8] d1[ext] a a1 b r1 s1 (L_j R_j)*
+#define BPP_RAW_D1(ext, k) (1u + 32u * (k))
+#define BPP_RAW_A(ext) (1u + 32u * (ext))
+#define BPP_RAW_R1(ext) (1u + 32u * ((ext) + 3u))
+#define BPP_RAW_S1(ext) (1u + 32u * ((ext) + 4u))
+#define BPP_RAW_L(ext, j) (1u + 32u * ((ext) + 5u) + 64u * (j))
+#define BPP_RAW_R(ext, j) (1u + 32u * ((ext) + 6u) + 64u * (j))
 struct VBuffers {
     const VProof *proofs; const VChunk *chunks;
-    const uint32_t *vec_offsets;     // n_proofs + 1: prefix sums of N over active proofs
-    const uint32_t *proof_scalars;   // words
+    const uint32_t *pt_offsets;      // n_proofs + 1: first slot of every proof in the point table (prefix sums; proofs without device work are empty)
+    const uint8_t *blob;             // uploaded bytes; the proof scalars r1, s1, d1 are read from VProof::raw_off
     const uint32_t *challenges;      // words
     const uint32_t *weights;         // n_proofs x 8 words (canonical); consumed by k_vprep_weight only
     uint32_t *weights_mont;          // scratch: n_proofs x 8 words, Montgomery form
     const uint64_t *min_values; const uint8_t *min_present;
     const uint32_t *nonces;          // words, may be null
     uint32_t *msm_scalars;           // out: n_entries x 8 words
+    uint32_t *msm_pidx;              // out: n_entries point indices (bit 31 = generator table), written by k_vprep_weight / k_vprep_reduce
     uint32_t *contrib;               // scratch: gi/hi contributions (Montgomery form)
     uint32_t *hg_contrib;            // scratch: per proof (1 + ext) scalars (Montgomery form): h, g_k
     uint32_t *pervec;                // scratch: stage A -> B hand-off
@@ -98,15 +114,17 @@ struct RBuffers {
     const VProof *proofs;
     const uint8_t *tstates_in;       // n_proofs x 203
     const uint8_t *hg32;             // compressed H, then G[0..ext)
-    const uint8_t *enc;              // point encodings (VProof::pt_off)
-    const uint8_t *proof_scalars;    // bytes (VProof::sc_off): r1, s1, d1..
+    const uint8_t *blob;             // uploaded bytes: serialised proofs at VProof::raw_off
+    const uint8_t *commitments32;    // 32 x (VProof::commit_off + j)
     const uint64_t *min_values; const uint8_t *min_present;
     uint8_t *challenges;             // out (VProof::ch_off): y, z, e, e_0..
     uint8_t *wbytes;                 // out: n_proofs x 32
     uint8_t *tstates_out;            // out: n_proofs x 203
     uint8_t *flags;                  // out: n_proofs; bit 0 = loop-1 VerificationFailed, bit 1 = y == 1
 };
-void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, bool warp_per_proof, uint64_t *launches);
+// kernel: 0 = one thread per proof, sponge state in shared memory and the permutation in registers (default); 1 = one thread per
+// proof, state in local memory (the round-1 kernel); 2 = one warp per proof (wstrobe.cuh)
+void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, int kernel, uint64_t *launches);
 // verifier weights of every active chunk (one warp per chunk); wt_init = 203-byte state of the weight transcript after its
 // domain separator; weights: n_proofs x 8 words, canonical
 void launch_weights(cudaStream_t s, const VDims &d, const VChunk *chunks, const uint8_t *wt_init, const uint8_t *wbytes, const uint8_t *flags,

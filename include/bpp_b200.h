@@ -144,6 +144,11 @@ void bpp_msm_plan_destroy(bpp_msm_plan *plan);
  * resident in HBM for the lifetime of the handle. */
 int32_t bpp_gens_create(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree,
                         bpp_gens **out);
+/* the same with caller-made PedersenGens (RangeParameters::init takes any pc_gens: range_parameters.rs:32-58,
+ * generators/pedersen_gens.rs:25-36): h_base32 = the value base, g_bases32 = extension_degree masking bases, as Ristretto encodings;
+ * NULL = the reference's constants for that part.  BPP_INVALID_ARGUMENT if an encoding does not decode. */
+int32_t bpp_gens_create_with_bases(bpp_ctx *ctx, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree,
+                                   const uint8_t *h_base32_or_null, const uint8_t *g_bases32_or_null, bpp_gens **out);
 void bpp_gens_destroy(bpp_gens *g);
 /* Fixed-base multiscalar multiplication over the generator set (the static half of Precomputation::vartime_mixed_multiscalar_mul,
  * generators/bulletproof_gens.rs:103, range_proof.rs:339-345): n_seg sums of seg_len terms, out32[s] = encode(sum_e scalars32[s][e] *
@@ -192,14 +197,59 @@ typedef struct {
 int32_t bpp_verify_chunks(bpp_gens *g, const bpp_verify_args *args, int32_t *chunk_status,
                           uint8_t *masks32, uint8_t *mask_present);
 
+/* Challenge-input form, for a host that keeps `merlin::Transcript` itself (its STROBE state is private, so a stock Rust host cannot
+ * hand over the 203-byte state above): the caller runs loop 1 of RangeProof::verify (range_proof.rs:816-850) with the reference's
+ * own src/transcripts.rs and draws the batch weights (:853, :894), then passes, per proof i,
+ *   challenges32[challenge_offsets[i] .. challenge_offsets[i+1])  = y, z, e, e_0 .. e_{rounds-1}   (32-byte canonical, non-zero)
+ *   weights32[i]                                                  = the proof's batch weight          (32-byte canonical, non-zero)
+ * and this call does everything from :856 on (decompression, scalar synthesis, the merged multiscalar check, mask recovery).
+ * args->transcripts is not read (may be NULL).  Identity-point / zero-challenge rejections of loop 1 (VerificationFailed) are the
+ * caller's, as they happen inside its transcript code; the status precedence from :859 on is reproduced here. */
+typedef struct {
+    const uint8_t *challenges32;
+    const uint64_t *challenge_offsets;     /* n_proofs + 1, in scalars */
+    const uint8_t *weights32;              /* n_proofs x 32 */
+} bpp_verify_challenges;
+int32_t bpp_verify_chunks_ch(bpp_gens *g, const bpp_verify_args *args, const bpp_verify_challenges *ch, int32_t *chunk_status,
+                             uint8_t *masks32, uint8_t *mask_present);
+
 /* Split form used to time the device path with inputs resident in HBM (bench.py `value`):
  * create = host parsing + Fiat-Shamir + upload; run = all device work + verdict readback. */
 int32_t bpp_vbatch_create(bpp_gens *g, const bpp_verify_args *args, bpp_vbatch **out);
+/* ONE device pass over the calls of several callers (same action): proofs, chunks, statuses and masks of the pass are the calls'
+ * concatenated in order.  This is what the coalescing queue below builds from the calls waiting in it. */
+int32_t bpp_vbatch_create_multi(bpp_gens *g, size_t n_calls, const bpp_verify_args *const *calls, bpp_vbatch **out);
+size_t bpp_vbatch_call_count(const bpp_vbatch *vb);
+/* the advanced Merlin states of call `call` of the pass (that call's n_proofs x 203 B) */
+int32_t bpp_vbatch_transcripts_call(const bpp_vbatch *vb, size_t call, uint8_t *transcripts);
 int32_t bpp_vbatch_run(bpp_vbatch *vb, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present);
+/* the same with one output buffer set per call of the pass (masks32 / mask_present may be NULL, as may their entries) */
+int32_t bpp_vbatch_run_multi(bpp_vbatch *vb, int32_t *const *chunk_status, uint8_t *const *masks32, uint8_t *const *mask_present);
 /* after bpp_vbatch_run: write the advanced Merlin states (n_proofs x 203 B) -- what `&mut [Transcript]` holds after the
  * reference call; bpp_verify_chunks does this into args->transcripts itself */
 int32_t bpp_vbatch_transcripts(const bpp_vbatch *vb, uint8_t *transcripts);
 void bpp_vbatch_destroy(bpp_vbatch *vb);
+
+/* ---------------------------------------------------------------- coalescing queue
+ * One reference call (<= 256 proofs looked at) is far too little work for a B200.  Callers submit bpp_verify_args from any number of
+ * threads; each of `lanes` lanes (a bpp_ctx + generator tables + host thread, all on `device_ordinal`) takes what is waiting -- up to
+ * max_calls_per_pass calls with the same action -- and verifies it as ONE device pass, then writes every call's statuses, masks and
+ * advanced transcripts to that call's own buffers.  Results are those of bpp_verify_chunks on each call alone.
+ *   submit: returns at once; the buffers named by `args` and the output buffers must stay valid until wait(ticket) returns
+ *   wait:   blocks until the call is done; returns BPP_OK when its chunk_status was written, else the engine error of its pass
+ *   verify: submit + wait (a synchronous verify_batch that coalesces with the calls of other threads)
+ *   stats:  {passes, calls, proofs, engine kernels launched, graph launches} since creation (read while idle) */
+typedef struct bpp_vqueue bpp_vqueue;
+int32_t bpp_vqueue_create(int32_t device_ordinal, int32_t bit_length, int32_t max_aggregation, int32_t extension_degree,
+                          const uint8_t *h_base32_or_null, const uint8_t *g_bases32_or_null, int32_t lanes, int32_t max_calls_per_pass,
+                          int32_t host_threads_per_lane, bpp_vqueue **out);
+void bpp_vqueue_destroy(bpp_vqueue *q);
+int32_t bpp_vqueue_submit(bpp_vqueue *q, const bpp_verify_args *args, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present,
+                          uint64_t *ticket);
+int32_t bpp_vqueue_wait(bpp_vqueue *q, uint64_t ticket);
+int32_t bpp_vqueue_verify(bpp_vqueue *q, const bpp_verify_args *args, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present);
+int32_t bpp_vqueue_stats(bpp_vqueue *q, uint64_t out5[5]);
+int32_t bpp_vqueue_lanes(const bpp_vqueue *q);
 
 /* ---------------------------------------------------------------- batched proving
  * replaces P calls of RangeProof::prove_with_rng (range_proof.rs:232-608) for statements of ONE shape (same bit length,

@@ -777,7 +777,7 @@ def verify_batch(transcripts, statements, proofs, action):
         N = m * n
         if len(pr.li) != len(pr.ri):
             raise ProofError("InvalidLength", "Vector L length not equal to vector R length")
-        if rounds >= 32:
+        if rounds >= 64:                 # 1usize.checked_shl(rounds) overflows from 64 on (range_proof.rs:880-885)
             raise ProofError("SizeOverflow")
         if (1 << rounds) != N:
             raise ProofError("InvalidLength", "Vector L/R length not adequate")

@@ -113,6 +113,10 @@ class Engine:
         2: additionally verifier weights on the device, one graph per pass (measured slower; see include/bpp_b200.h)"""
         _chk(self, _ffi.lib().bpp_ctx_set_throughput_mode(self.h, int(enable)))
 
+    def set_test_hooks(self, flags):
+        """bit 0: every verification pass is repeated through the zero-weight fallback (results must not change)"""
+        _chk(self, _ffi.lib().bpp_ctx_set_test_hooks(self.h, int(flags)))
+
     @property
     def graph_launch_count(self):
         return int(_ffi.lib().bpp_ctx_graph_launch_count(self.h))

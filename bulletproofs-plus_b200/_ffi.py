@@ -151,6 +151,7 @@ def lib():
         "bpp_ctx_set_graphs": (i32, [vp, i32]),
         "bpp_ctx_set_throughput_mode": (i32, [vp, i32]),
         "bpp_ctx_graph_launch_count": (C.c_uint64, [vp]),
+        "bpp_ctx_set_test_hooks": (i32, [vp, C.c_uint32]),
         "bpp_proof_check_bytes": (i32, [cp, sz, P(i32), P(i32)]),
         "bpp_proof_size": (sz, [i32, i32]),
         "bpp_prove_batch": (i32, [vp, P(ProveArgs), vp, sz, vp]),

@@ -193,6 +193,11 @@ int32_t bpp_ctx_set_throughput_mode(bpp_ctx *ctx, int32_t enable) {
     return BPP_OK;
 }
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->graph_launches : 0; }
+int32_t bpp_ctx_set_test_hooks(bpp_ctx *ctx, uint32_t flags) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    ctx->test_hooks = flags;
+    return BPP_OK;
+}
 // wall-clock milliseconds of the host phases of the last bpp_vbatch_create on this ctx:
 // 0 parse + statement checks, 1 layout + buffers, 2 blob fill (+ loop-1 replay in host mode), 3 weight transcripts (host mode),
 // 4 H2D + sync, 5 unused

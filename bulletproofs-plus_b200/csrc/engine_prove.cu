@@ -50,6 +50,21 @@ inline sc wide_to_sc(const uint8_t in[64]) {
     return r;
 }
 
+// memset that the optimiser may not drop (the buffers are dead afterwards)
+inline void secure_zero(void *p, size_t n) {
+    if (!p || !n) return;
+    memset(p, 0, n);
+    __asm__ __volatile__("" : : "r"(p) : "memory");
+}
+// runs a wipe on every exit path of bpp_prove_batch (normal return, argument errors discovered late, CUDA failures)
+template <class F> struct ScopeExit {
+    F f;
+    explicit ScopeExit(F fn) : f(fn) {}
+    ~ScopeExit() { f(); }
+    ScopeExit(const ScopeExit &) = delete;
+    ScopeExit &operator=(const ScopeExit &) = delete;
+};
+
 struct PProof {
     int32_t rc = 0;
     bool live = false;             // takes part in the device batch
@@ -168,6 +183,30 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     };
 
     std::vector<PProof> pp(P0);
+    // Everything below that holds witness-derived data is wiped when this function is left, whichever way (the reference keeps these in
+    // Zeroizing<..>: range_proof.rs:300-301, :325, :438-464, :542-571): the host copies (per-proof state, bit offsets, a[0] / b[0], the
+    // pinned staging buffer that carried alpha, d_L / d_R, r, s, d, eta) and the device copies.
+    std::vector<uint64_t> offs;
+    std::vector<uint8_t> ab;
+    struct { uint8_t *hio = nullptr; size_t hio_bytes = 0; std::vector<std::pair<void *, size_t>> dev; cudaStream_t st = nullptr; } wipe;
+    ScopeExit wipe_guard([&]() {
+        for (PProof &p : pp) {
+            secure_zero(p.witness.data(), p.witness.size());
+            secure_zero(p.seed, sizeof p.seed);
+            secure_zero(p.alpha, sizeof p.alpha); secure_zero(p.d, sizeof p.d); secure_zero(p.eta, sizeof p.eta);
+            secure_zero(&p.r, sizeof p.r); secure_zero(&p.s, sizeof p.s);
+            secure_zero(p.dL.data(), sizeof(sc) * p.dL.size()); secure_zero(p.dR.data(), sizeof(sc) * p.dR.size());
+            secure_zero(&p.rng, sizeof p.rng);               // TranscriptRng keyed with the witness bytes
+        }
+        secure_zero(offs.data(), 8 * offs.size());
+        secure_zero(ab.data(), ab.size());
+        if (!wipe.dev.empty()) {
+            for (auto &d : wipe.dev) if (d.first && d.second) cudaMemsetAsync(d.first, 0, d.second, wipe.st);
+            cudaStreamSynchronize(wipe.st);                 // also orders the staging buffer's last DMA before its wipe
+            cudaGetLastError();
+        }
+        secure_zero(wipe.hio, wipe.hio_bytes);
+    });
     // ---- :264-271 value range, :275-284 opening == commitment (device commit, compared as canonical encodings)
     for (size_t i = 0; i < P0; i++) {
         PProof &p = pp[i];
@@ -185,13 +224,13 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         for (size_t i = 0; i < P0; i++)
             if (pp[i].rc) memset(bl.data() + 32 * i * m * ext, 0, 32 * (size_t)m * ext);
         int32_t rc = bpp_pedersen_commit_batch(g, P0 * m, a->values, bl.data(), (int32_t)ext, recommit.data());
+        secure_zero(bl.data(), bl.size());
         if (rc) return rc;
         for (size_t i = 0; i < P0; i++)
             if (!pp[i].rc && memcmp(recommit.data() + 32 * i * m, a->commitments32 + 32 * i * m, 32 * (size_t)m)) pp[i].rc = BPP_INVALID_ARGUMENT;
     }
 
     // ---- RangeProofTranscript::new (:287-297), bit offsets (:300-322), alpha (:325-333)
-    std::vector<uint64_t> offs;
     std::vector<size_t> live;
     host_stage(P0, 8, [&](size_t i) {
         PProof &p = pp[i];
@@ -312,6 +351,10 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     b.folded = d_folded.as<cached>(); b.msm_scalars = d_mscal.as<uint32_t>(); b.msm_pidx = d_pidx.as<uint32_t>();
     b.sg = ws.d_sg.as<uint32_t>(); b.sh = ws.d_sh.as<uint32_t>();
     uint8_t *hio = h_io.as<uint8_t>();
+    wipe.hio = hio; wipe.hio_bytes = io_bytes; wipe.st = st;
+    wipe.dev = {{d_a.p, 32 * (size_t)P * N}, {d_b.p, 32 * (size_t)P * N}, {d_offs.p, 8 * (size_t)P * m}, {d_mscal.p, 32 * max_entries},
+                {d_dlr.p, 64 * (size_t)P * ext}, {d_ab.p, 64 * (size_t)P}, {d_yz.p, 96 * (size_t)P}, {d_e.p, 64 * (size_t)P}};
+    if (fb) { wipe.dev.push_back({ws.d_rs.p, 64 * (size_t)P}); wipe.dev.push_back({ws.d_sg.p, 32 * (size_t)P * N}); wipe.dev.push_back({ws.d_sh.p, 32 * (size_t)P * N}); }
 #define PCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { release(); return cuda_fail(ctx, _e, #call); } } while (0)
     auto upload_offsets = [&](uint32_t n_seg, const std::vector<uint32_t> &off) -> cudaError_t {
         memcpy(hio + io_bytes - 4 * (2 * (size_t)P + 1) - 16, off.data(), 4 * (n_seg + 1));
@@ -456,7 +499,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     launch_prove_final_ab(st, d, b, d_ab.as<uint32_t>());
     ctx->launches++;
     PCUDA(cudaStreamSynchronize(st));
-    std::vector<uint8_t> ab(64 * (size_t)P);
+    ab.resize(64 * (size_t)P);
     PCUDA(cudaMemcpyAsync(ab.data(), d_ab.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
     auto draw_final = [&](PProof &p) {
@@ -527,13 +570,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     }
     }
     PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
-    // Zeroizing<..> of the reference (:300-301, :325, :438-464, :542-571): wipe the device copies of the secrets
-    PCUDA(cudaMemsetAsync(d_a.p, 0, 32 * (size_t)P * N, st));
-    PCUDA(cudaMemsetAsync(d_b.p, 0, 32 * (size_t)P * N, st));
-    PCUDA(cudaMemsetAsync(d_offs.p, 0, 8 * (size_t)P * m, st));
-    PCUDA(cudaMemsetAsync(d_mscal.p, 0, 32 * max_entries, st));
-    PCUDA(cudaMemsetAsync(d_dlr.p, 0, 64 * (size_t)P * ext, st));
-    PCUDA(cudaMemsetAsync(d_ab.p, 0, 64 * (size_t)P, st));
+    // the device copies of the secrets are wiped by wipe_guard when the function is left
     PCUDA(cudaStreamSynchronize(st));
     host_stage(P, 8, [&](size_t s) {
         const size_t i = live[s];
@@ -568,7 +605,6 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         for (uint32_t k = 0; k < BPP_MAX_EXT; k++) { p.alpha[k] = sc_zero(); p.d[k] = sc_zero(); p.eta[k] = sc_zero(); }
         p.r = sc_zero(); p.s = sc_zero();
     });
-    std::fill(ab.begin(), ab.end(), 0);
     if (prove_trace)
         fprintf(stderr, "bpp_prove_batch P=%u: %.2f ms, host stages %.2f ms\n", P,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count(), host_stage_ms);

@@ -168,32 +168,38 @@ void vgraph_cache_free(bpp_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------ verifier weights (host)
-// Four STROBE-128 sponges advancing in lock-step (host_keccak4.cpp permutes the four states with one vectorised Keccak-f): the
-// weight transcripts of chunks that hold the same number of proofs perform the same operations at the same sponge positions,
-// only the absorbed bytes differ.  Mirrors Strobe128 / Merlin / MerlinRng of hash.cuh operation by operation.
+// LANES (4 or 8) STROBE-128 sponges advancing in lock-step (host_keccak4.cpp permutes the states with one vectorised Keccak-f): the
+// weight transcripts of chunks that hold the same number of proofs perform the same operations at the same sponge positions, only
+// the absorbed bytes differ.  Mirrors Strobe128 / Merlin / MerlinRng of hash.cuh operation by operation.
+// The 64 bytes drawn per weight (Scalar::random, range_proof.rs:894) are handed out as they are: the wide reduction mod l runs on the
+// device (k_vprep_weight), which also reports the zero weight random_not_zero would redraw (probability 2^-252; handled by rerunning
+// the chunk through weights_scalar, see bpp_vbatch_run).
 extern "C" void bpp_keccak_f1600_x4(uint64_t *st);
+extern "C" void bpp_keccak_f1600_x8(uint64_t *st);
+extern "C" int32_t bpp_host_simd_level(void);
 extern "C" void bpp_host_sc_from_wide64(const uint8_t in64[64], uint8_t out32[32]);      // host_keccak4.cpp: 64-bit-limb wide reduction
 namespace {
-struct Strobe4 {
-    alignas(32) uint64_t st[100];          // lane k of state j at st[4 * k + j]
+template <int LANES> struct StrobeN {
+    alignas(64) uint64_t st[25 * LANES];          // lane k of state j at st[LANES * k + j]
     uint8_t pos = 0, pos_begin = 0, cur_flags = 0;
     static constexpr int RATE = Strobe128::RATE;
-    void load_all(const uint8_t *b) {      // the same 203-byte state into all four
+    void permute() { if (LANES == 8) bpp_keccak_f1600_x8(st); else bpp_keccak_f1600_x4(st); }
+    void load_all(const uint8_t *b) {      // the same 203-byte state into every lane
         for (int k = 0; k < 25; k++) {
             uint64_t x = 0;
             for (int j = 7; j >= 0; j--) x = (x << 8) | b[8 * k + j];
-            for (int j = 0; j < 4; j++) st[4 * k + j] = x;
+            for (int j = 0; j < LANES; j++) st[LANES * k + j] = x;
         }
         pos = b[200]; pos_begin = b[201]; cur_flags = b[202];
     }
     void xor_all(int p, uint8_t v) {
         const uint64_t x = (uint64_t)v << (8 * (p & 7));
-        uint64_t *l = st + 4 * (p >> 3);
-        l[0] ^= x; l[1] ^= x; l[2] ^= x; l[3] ^= x;
+        uint64_t *l = st + LANES * (p >> 3);
+        for (int j = 0; j < LANES; j++) l[j] ^= x;
     }
     void run_f() {
         xor_all(pos, pos_begin); xor_all(pos + 1, 0x04); xor_all(RATE + 1, 0x80);
-        bpp_keccak_f1600_x4(st);
+        permute();
         pos = 0; pos_begin = 0;
     }
     // Spans move up to eight bytes at a time as one 64-bit word per state (a word may straddle two sponge lanes); the byte loops
@@ -210,27 +216,27 @@ struct Strobe4 {
             if (n > (size_t)(RATE - pos)) n = (size_t)(RATE - pos);
             const uint64_t x = load_le(d, n);
             const int off = pos & 7, sh = 8 * off;
-            uint64_t *l = st + 4 * (pos >> 3);
+            uint64_t *l = st + LANES * (pos >> 3);
             const uint64_t lo = x << sh;
-            l[0] ^= lo; l[1] ^= lo; l[2] ^= lo; l[3] ^= lo;
-            if (off + (int)n > 8) { const uint64_t hi = x >> (64 - sh); l[4] ^= hi; l[5] ^= hi; l[6] ^= hi; l[7] ^= hi; }
+            for (int j = 0; j < LANES; j++) l[j] ^= lo;
+            if (off + (int)n > 8) { const uint64_t hi = x >> (64 - sh); for (int j = 0; j < LANES; j++) l[LANES + j] ^= hi; }
             d += n; len -= n;
             pos = (uint8_t)(pos + n);
             if (pos == RATE) run_f();
         }
     }
-    void absorb4(const uint8_t *const d[4], size_t len) {
+    void absorb_each(const uint8_t *const d[LANES], size_t len) {
         size_t i = 0;
         while (i < len) {
             size_t n = len - i < 8 ? len - i : 8;
             if (n > (size_t)(RATE - pos)) n = (size_t)(RATE - pos);
             const int off = pos & 7, sh = 8 * off;
-            uint64_t *l = st + 4 * (pos >> 3);
+            uint64_t *l = st + LANES * (pos >> 3);
             const bool straddle = off + (int)n > 8;
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < LANES; j++) {
                 const uint64_t x = load_le(d[j] + i, n);
                 l[j] ^= x << sh;
-                if (straddle) l[4 + j] ^= x >> (64 - sh);
+                if (straddle) l[LANES + j] ^= x >> (64 - sh);
             }
             i += n;
             pos = (uint8_t)(pos + n);
@@ -240,23 +246,23 @@ struct Strobe4 {
     void overwrite_same(const uint8_t *d, size_t len) {
         for (size_t i = 0; i < len; i++) {
             const int sh = 8 * (pos & 7);
-            uint64_t *l = st + 4 * (pos >> 3);
-            for (int j = 0; j < 4; j++) l[j] = (l[j] & ~(0xffULL << sh)) | ((uint64_t)d[i] << sh);
+            uint64_t *l = st + LANES * (pos >> 3);
+            for (int j = 0; j < LANES; j++) l[j] = (l[j] & ~(0xffULL << sh)) | ((uint64_t)d[i] << sh);
             if (++pos == RATE) run_f();
         }
     }
-    void squeeze4(uint8_t *const d[4], size_t len) {
+    void squeeze_each(uint8_t *const d[LANES], size_t len) {
         size_t i = 0;
         while (i < len) {
             if ((pos & 7) == 0 && len - i >= 8 && pos + 8 <= RATE) {         // a whole lane: read it and clear it
-                uint64_t *l = st + 4 * (pos >> 3);
-                for (int j = 0; j < 4; j++) { memcpy(d[j] + i, &l[j], 8); l[j] = 0; }
+                uint64_t *l = st + LANES * (pos >> 3);
+                for (int j = 0; j < LANES; j++) { memcpy(d[j] + i, &l[j], 8); l[j] = 0; }
                 i += 8;
                 pos = (uint8_t)(pos + 8);
             } else {
                 const int sh = 8 * (pos & 7);
-                uint64_t *l = st + 4 * (pos >> 3);
-                for (int j = 0; j < 4; j++) { d[j][i] = (uint8_t)(l[j] >> sh); l[j] &= ~(0xffULL << sh); }
+                uint64_t *l = st + LANES * (pos >> 3);
+                for (int j = 0; j < LANES; j++) { d[j][i] = (uint8_t)(l[j] >> sh); l[j] &= ~(0xffULL << sh); }
                 i++;
                 pos++;
             }
@@ -272,9 +278,9 @@ struct Strobe4 {
         if ((flags & (Strobe128::FC | Strobe128::FK)) && pos != 0) run_f();
     }
     void meta_ad_same(const uint8_t *d, size_t len, bool more) { begin_op(Strobe128::FM | Strobe128::FA, more); absorb_same(d, len); }
-    void ad4(const uint8_t *const d[4], size_t len) { begin_op(Strobe128::FA, false); absorb4(d, len); }
+    void ad_each(const uint8_t *const d[LANES], size_t len) { begin_op(Strobe128::FA, false); absorb_each(d, len); }
     void key_same(const uint8_t *d, size_t len) { begin_op(Strobe128::FA | Strobe128::FC, false); overwrite_same(d, len); }
-    void prf4(uint8_t *const d[4], size_t len) { begin_op(Strobe128::FI | Strobe128::FA | Strobe128::FC, false); squeeze4(d, len); }
+    void prf_each(uint8_t *const d[LANES], size_t len) { begin_op(Strobe128::FI | Strobe128::FA | Strobe128::FC, false); squeeze_each(d, len); }
 };
 const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> &weight_transcript_init() {      // Transcript::new("Bulletproofs+ verifier weights") (:811)
     static const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> wt0 = [] {
@@ -290,8 +296,10 @@ const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> &weight_transcript_init() {     
 
 // Sequential part of loop 1 + the weight draw of loop 2 for every chunk: the verifier-weight transcript (range_proof.rs:811,
 // :849, :853) and random_not_zero per proof (:894).  Needs wbytes / flags of all proofs.  Chunks are independent: one at a time
-// through the scalar sponge, or four chunks of equal length at a time through Strobe4.
-// wb: len x 32 bytes (what every proof of the chunk feeds into the transcript, in proof order); out: len x 32 (canonical weights)
+// through the scalar sponge, or LANES chunks of equal length at a time through StrobeN.
+// wb: len x 32 bytes (what every proof of the chunk feeds into the transcript, in proof order); out: len x 64, the weight of proof k as a
+// 512-bit little-endian value whose reduction mod l is the weight.  weights_scalar is the reference statement by statement (it
+// redraws a zero weight, so what it writes is the final weight, canonical, upper half zero).
 static void weights_scalar(const uint8_t *wb, size_t len, uint8_t *out) {
     Merlin wt;
     wt.s.load(weight_transcript_init().data());
@@ -300,74 +308,85 @@ static void weights_scalar(const uint8_t *wb, size_t len, uint8_t *out) {
     const uint8_t zeros[32] = {0};
     wr.build(wt, nullptr, 0, false, zeros);                                           // :853
     for (size_t k = 0; k < len; k++) {
-        uint8_t wide[64], *wgt = out + 32 * k;
+        uint8_t wide[64], *wgt = out + 64 * k;
         do { wr.fill(wide, 64); bpp_host_sc_from_wide64(wide, wgt); } while (is_zero32(wgt));   // :894 random_not_zero
+        memset(wgt + 32, 0, 32);
     }
 }
-// four chunks with the same number of proofs (pointers may repeat: padding of an incomplete group)
-static void weights_x4(const uint8_t *const wb[4], size_t len, uint8_t *const out[4]) {
-    Strobe4 s;
+// LANES chunks with the same number of proofs (pointers may repeat: padding of an incomplete group)
+template <int LANES> static void weights_xn(const uint8_t *const wb[LANES], size_t len, uint8_t *const out[LANES]) {
+    StrobeN<LANES> s;
     s.load_all(weight_transcript_init().data());
     const uint8_t l32[4] = {32, 0, 0, 0}, l64[4] = {64, 0, 0, 0};
     for (size_t k = 0; k < len; k++) {                                                // append_message("proof", wbytes, 32)
-        const uint8_t *d[4] = {wb[0] + 32 * k, wb[1] + 32 * k, wb[2] + 32 * k, wb[3] + 32 * k};
+        const uint8_t *d[LANES];
+        for (int j = 0; j < LANES; j++) d[j] = wb[j] + 32 * k;
         s.meta_ad_same(LBL("proof"), false);
         s.meta_ad_same(l32, 4, true);
-        s.ad4(d, 32);
+        s.ad_each(d, 32);
     }
     const uint8_t zeros[32] = {0};
     s.meta_ad_same(LBL("rng"), false);                                                // build_rng().finalize(NullRng)
     s.key_same(zeros, 32);
-    bool redo = false;
-    for (size_t k = 0; k < len; k++) {                                                // fill_bytes(64) -> from_bytes_mod_order_wide
-        uint8_t wide[4][64];
-        uint8_t *d[4] = {wide[0], wide[1], wide[2], wide[3]};
-        s.meta_ad_same(l64, 4, false);
-        s.prf4(d, 64);
-        for (int j = 0; j < 4; j++) {
-            bpp_host_sc_from_wide64(wide[j], out[j] + 32 * k);
-            if (is_zero32(out[j] + 32 * k)) redo = true;      // random_not_zero would draw again (probability 2^-252): leave lock-step
+    uint8_t spare[LANES][64];
+    for (size_t k = 0; k < len; k++) {                                                // fill_bytes(64): the device reduces mod l
+        uint8_t *d[LANES];
+        // padded lanes repeat a chunk: only the first lane that names a destination writes it
+        for (int j = 0; j < LANES; j++) {
+            d[j] = out[j] + 64 * k;
+            for (int i = 0; i < j; i++) if (out[i] == out[j]) d[j] = spare[j];
         }
+        s.meta_ad_same(l64, 4, false);
+        s.prf_each(d, 64);
     }
-    if (redo)
-        for (int j = 0; j < 4; j++) weights_scalar(wb[j], len, out[j]);
 }
 extern "C" {
-// test hook (host only): verifier weights of n_chunks (1..4) chunks of `len` proofs each, wbytes / weights chunk-major;
-// lockstep = 0: one transcript at a time, 1: all of them through the four-way sponge
+// test hook (host only): verifier weights of n_chunks (1..8) chunks of `len` proofs each, wbytes / weights chunk-major (weights canonical,
+// 32 bytes each); lockstep = 0: one transcript at a time, 1: through the four-way sponge, 2: through the eight-way sponge
 int32_t bpp_host_verifier_weights(const uint8_t *wbytes32, size_t len, size_t n_chunks, int32_t lockstep, uint8_t *weights32) {
-    if (!wbytes32 || !weights32 || n_chunks < 1 || n_chunks > 4) return BPP_INVALID_ARGUMENT;
+    if (!wbytes32 || !weights32 || n_chunks < 1 || n_chunks > 8 || (lockstep == 1 && n_chunks > 4)) return BPP_INVALID_ARGUMENT;
+    std::vector<uint8_t> wide(64 * len * n_chunks);
     if (!lockstep) {
-        for (size_t c = 0; c < n_chunks; c++) weights_scalar(wbytes32 + 32 * len * c, len, weights32 + 32 * len * c);
-        return BPP_OK;
+        for (size_t c = 0; c < n_chunks; c++) weights_scalar(wbytes32 + 32 * len * c, len, wide.data() + 64 * len * c);
+    } else if (lockstep == 1) {
+        const uint8_t *wb[4];
+        uint8_t *out[4];
+        for (size_t j = 0; j < 4; j++) { size_t c = j < n_chunks ? j : n_chunks - 1; wb[j] = wbytes32 + 32 * len * c; out[j] = wide.data() + 64 * len * c; }
+        weights_xn<4>(wb, len, out);
+    } else {
+        const uint8_t *wb[8];
+        uint8_t *out[8];
+        for (size_t j = 0; j < 8; j++) { size_t c = j < n_chunks ? j : n_chunks - 1; wb[j] = wbytes32 + 32 * len * c; out[j] = wide.data() + 64 * len * c; }
+        weights_xn<8>(wb, len, out);
     }
-    const uint8_t *wb[4];
-    uint8_t *out[4];
-    for (size_t j = 0; j < 4; j++) { size_t c = j < n_chunks ? j : n_chunks - 1; wb[j] = wbytes32 + 32 * len * c; out[j] = weights32 + 32 * len * c; }
-    weights_x4(wb, len, out);
+    for (size_t i = 0; i < len * n_chunks; i++) bpp_host_sc_from_wide64(wide.data() + 64 * i, weights32 + 32 * i);
     return BPP_OK;
 }
 }
-static void compute_weights(bpp_vbatch *vb) {
+// weights of the chunks listed in `only` (or of every chunk whose loop 1 succeeded when `only` is null); scalar = one transcript at a
+// time with the reference's redraw of a zero weight
+static void compute_weights(bpp_vbatch *vb, const std::vector<size_t> *only = nullptr, bool scalar = false) {
     bpp_ctx *ctx = vb->g->ctx;
-    // chunks whose weights are needed, grouped by length
-    struct Task { size_t c[4]; int n; };
+    const int width = (ctx->scalar_weights || scalar) ? 1 : bpp_host_simd_level() == 2 ? 8 : 4;
+    struct Task { size_t c[8]; int n; };
     std::vector<Task> tasks;
     std::vector<std::pair<size_t, size_t>> todo;       // (length, chunk)
-    for (size_t c = 0; c < vb->n_chunks; c++) {
+    auto consider = [&](size_t c) {
         const HChunk &hc = vb->hc[c];
-        if (hc.pre_rc) continue;
+        if (hc.pre_rc) return;
         bool failed = false;
         for (size_t i = hc.lo; i < hc.hi && !failed; i++) failed = (vb->flag(i) & 1) != 0;      // loop 1 failed: the call ends there
         if (!failed) todo.emplace_back(hc.hi - hc.lo, c);
-    }
+    };
+    if (only) for (size_t c : *only) consider(c);
+    else for (size_t c = 0; c < vb->n_chunks; c++) consider(c);
     std::sort(todo.begin(), todo.end());
     for (size_t i = 0; i < todo.size();) {
         size_t j = i;
-        while (j < todo.size() && todo[j].first == todo[i].first && j - i < 4) j++;
+        while (j < todo.size() && todo[j].first == todo[i].first && j - i < (size_t)width) j++;
         Task t;
         t.n = (int)(j - i);
-        for (int k = 0; k < 4; k++) t.c[k] = todo[i + (size_t)std::min<int>(k, t.n - 1)].second;
+        for (int k = 0; k < 8; k++) t.c[k] = todo[i + (size_t)std::min<int>(k, t.n - 1)].second;
         tasks.push_back(t);
         i = j;
     }
@@ -375,13 +394,14 @@ static void compute_weights(bpp_vbatch *vb) {
         const Task &t = tasks[ti];
         uint8_t *wts = vb->w->h_weights.as<uint8_t>();
         const size_t len = vb->hc[t.c[0]].hi - vb->hc[t.c[0]].lo;
-        if (t.n >= 2 && !ctx->scalar_weights) {       // 2 or 3 chunks: padded lanes still beat 2-3 scalar passes
-            const uint8_t *wb[4];
-            uint8_t *out[4];
-            for (int k = 0; k < 4; k++) { wb[k] = vb->wbytes(vb->hc[t.c[k]].lo); out[k] = wts + 32 * vb->hc[t.c[k]].lo; }
-            weights_x4(wb, len, out);
+        if (t.n >= 2 && width > 1) {       // 2 or more chunks: padded lanes still beat scalar passes
+            const uint8_t *wb[8];
+            uint8_t *out[8];
+            for (int k = 0; k < 8; k++) { wb[k] = vb->wbytes(vb->hc[t.c[k]].lo); out[k] = wts + 64 * vb->hc[t.c[k]].lo; }
+            if (t.n > 4) weights_xn<8>(wb, len, out);
+            else weights_xn<4>(wb, len, out);
         } else {
-            for (int k = 0; k < t.n; k++) weights_scalar(vb->wbytes(vb->hc[t.c[k]].lo), len, wts + 32 * vb->hc[t.c[k]].lo);
+            for (int k = 0; k < t.n; k++) weights_scalar(vb->wbytes(vb->hc[t.c[k]].lo), len, wts + 64 * vb->hc[t.c[k]].lo);
         }
     });
 }
@@ -559,7 +579,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     vb->mid_bytes = vb->mo_tstate + BPP_TRANSCRIPT_BYTES * NP;
     vb->ho_ok = 0;
     vb->ho_ident = ((size_t)n_pts + 255) & ~(size_t)255;
-    vb->ho_masks = vb->ho_ident + ((NC + 255) & ~(size_t)255);
+    vb->ho_masks = vb->ho_ident + ((2 * NC + 255) & ~(size_t)255);      // [identity flags | zero-weight flags]
     vb->hout_bytes = vb->ho_masks + 32 * std::max<size_t>(NP, 1) * (size_t)ext;
 
     // ---- buffers (pooled)
@@ -575,8 +595,8 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     ok(w->h_out.ensure(vb->hout_bytes));
     ok(w->h_mid.ensure(vb->mid_bytes + 256));
     ok(w->d_mid.ensure(vb->mid_bytes + 256));
-    ok(w->h_weights.ensure(32 * np1));
-    ok(w->d_weights.ensure(32 * np1));
+    ok(w->h_weights.ensure(64 * np1));
+    ok(w->d_weights.ensure(64 * np1));
     ok(w->d_wmont.ensure(32 * np1));
     ok(w->d_chal.ensure(32 * std::max<size_t>(n_chal, 1)));
     if (!vb->device_replay) ok(w->h_chal.ensure(32 * std::max<size_t>(n_chal, 1)));
@@ -590,7 +610,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     ok(w->d_masks.ensure(32 * np1 * (size_t)ext));
     ok(w->d_scratch.ensure(msm_scratch_bytes(vb->shape)));
     ok(w->d_res.ensure(sizeof(ge) * NC));
-    ok(w->d_ident.ensure(NC));
+    ok(w->d_ident.ensure(2 * NC));
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch buffers"); }
 
     // ---- device layout, written straight into the pinned blob
@@ -675,7 +695,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
     memcpy(hb + vb->o_wtinit, weight_transcript_init().data(), BPP_TRANSCRIPT_BYTES);      // starting state of k_weights
     memset(vb->mid(), 0, vb->mo_tstate);             // wbytes + flags (the transcript states are written by whoever replays)
-    if (!vb->device_replay) memset(w->h_weights.p, 0, 32 * np1);
+    memset(w->h_weights.p, 0, 64 * np1);
     const bool host_replay = !vb->device_replay && !vb->caller_challenges;
     if (vb->caller_challenges) {
         // the caller ran loop 1 with its own merlin (src/transcripts.rs unmodified): challenges [y, z, e, e_0..e_{r-1}] per proof and
@@ -695,7 +715,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
                 vwork_return(ctx, w); delete vb;
                 return fail(ctx, BPP_INVALID_ARGUMENT, "challenges and weights must be canonical non-zero scalars");
             }
-            memcpy(w->h_weights.as<uint8_t>() + 32 * gi, call.ch->weights32 + 32 * p.local, 32);
+            memcpy(w->h_weights.as<uint8_t>() + 64 * gi, call.ch->weights32 + 32 * p.local, 32);      // canonical: the upper half stays zero
             uint8_t one[32] = {1};
             vb->flag(gi) = memcmp(dst, one, 32) ? 0 : 2;      // y == 1
         }
@@ -841,6 +861,7 @@ static VLaunch make_launch(bpp_vbatch *vb) {
     b.proofs = vb->dev<VProof>(vb->o_proofs); b.chunks = vb->dev<VChunk>(vb->o_chunks); b.pt_offsets = vb->dev<uint32_t>(vb->o_ptoff);
     b.blob = w->d_blob.as<uint8_t>(); b.challenges = w->d_chal.as<uint32_t>();
     b.weights = w->d_weights.as<uint32_t>(); b.weights_mont = w->d_wmont.as<uint32_t>();
+    b.weight_zero = w->d_ident.as<uint8_t>() + vb->n_chunks;
     b.min_values = vb->dev<uint64_t>(vb->o_minv); b.min_present = vb->dev<uint8_t>(vb->o_minp); b.nonces = vb->dev<uint32_t>(vb->o_nonces);
     b.msm_scalars = w->d_mscal.as<uint32_t>(); b.msm_pidx = w->d_pidx.as<uint32_t>();
     b.contrib = w->d_contrib.as<uint32_t>(); b.hg_contrib = w->d_hg.as<uint32_t>();
@@ -914,10 +935,11 @@ static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section
         if (prep) launch_verify_prep(st, L.d, L.b, vb->any_vec ? 1u : 0u, vb->max_rounds, kernels, nullptr);
         if (vb->any_msm) {
             ok(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+            ok(cudaMemsetAsync(L.b.weight_zero, 0, vb->n_chunks, st));
             launch_verify_weigh(st, L.d, L.b, vb->max_static, kernels);
             if (fork_pts) ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
             enqueue_msm(vb, L, st, kernels, nullptr);
-            ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+            ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, 2 * vb->n_chunks, cudaMemcpyDeviceToHost, st));
         } else if (fork_pts) {
             ok(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         }
@@ -925,10 +947,11 @@ static cudaError_t enqueue_section(bpp_vbatch *vb, const VLaunch &L, int section
         if (vb->any_masks) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)g->ext, cudaMemcpyDeviceToHost, st));
     } else {
         if (vb->any_msm) {
-            ok(cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 32 * n, cudaMemcpyHostToDevice, st));
+            ok(cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 64 * n, cudaMemcpyHostToDevice, st));
+            ok(cudaMemsetAsync(L.b.weight_zero, 0, vb->n_chunks, st));
             launch_verify_weigh(st, L.d, L.b, vb->max_static, kernels);
             enqueue_msm(vb, L, st, kernels, nullptr);
-            ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+            ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, 2 * vb->n_chunks, cudaMemcpyDeviceToHost, st));
         }
         if (vb->n_pts) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ok, w->d_ok.p, vb->n_pts, cudaMemcpyDeviceToHost, st));
         if (vb->any_masks) ok(cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_masks, w->d_masks.p, 32 * n * (size_t)g->ext, cudaMemcpyDeviceToHost, st));
@@ -1070,15 +1093,16 @@ int32_t bpp_vbatch_run_multi(bpp_vbatch *vb, int32_t *const *chunk_status, uint8
         compute_weights(vb);
     }
     if (vb->any_msm) {
-        BPP_CUDA(ctx, cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 32 * n, cudaMemcpyHostToDevice, st));
+        BPP_CUDA(ctx, cudaMemcpyAsync(w->d_weights.p, w->h_weights.p, 64 * n, cudaMemcpyHostToDevice, st));
         ctx->mark(5);
+        BPP_CUDA(ctx, cudaMemsetAsync(b.weight_zero, 0, vb->n_chunks, st));
         launch_verify_weigh(st, d, b, vb->max_static, &ctx->launches);
         ctx->mark(6);
         if (overlap) BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         enqueue_msm(vb, L, st, &ctx->launches, ctx->phase_timing ? &ctx->ph[7] : nullptr);
         if (ctx->phase_timing) for (int i = 7; i <= 10; i++) ctx->ph_set[i] = true;
         ctx->mark(11);
-        BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, vb->n_chunks, cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(ctx, cudaMemcpyAsync(w->h_out.as<uint8_t>() + vb->ho_ident, w->d_ident.p, 2 * vb->n_chunks, cudaMemcpyDeviceToHost, st));
     } else if (overlap) {
         BPP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
@@ -1092,8 +1116,25 @@ int32_t bpp_vbatch_run_multi(bpp_vbatch *vb, int32_t *const *chunk_status, uint8
     } else {
         BPP_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    // A weight that reduced to zero (the reference's random_not_zero draws again, range_proof.rs:894 / scalar_protocol.rs:23-30): the
+    // chunk's weight transcript is redone one transcript at a time with the redraw, and sections B + C are repeated kernel by kernel.
+    // Probability 2^-252 per weight; BPP test hook 1 forces the path so that it stays tested.
+    if (vb->any_msm && !fused) {
+        const uint8_t *wz = w->h_out.as<uint8_t>() + vb->ho_ident + vb->n_chunks;
+        std::vector<size_t> redo;
+        for (size_t c = 0; c < vb->n_chunks; c++)
+            if (!vb->hc[c].pre_rc && (wz[c] || (ctx->test_hooks & 1))) redo.push_back(c);
+        if (!redo.empty() && !vb->caller_challenges) {
+            compute_weights(vb, &redo, true);
+            cudaError_t e1 = enqueue_section(vb, L, 1, &ctx->launches);
+            cudaError_t e2 = enqueue_section(vb, L, 2, &ctx->launches);
+            BPP_CUDA(ctx, e1);
+            BPP_CUDA(ctx, e2);
+            BPP_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+    }
     vb->ran = true;
-    ctx->io_bytes[0] = vb->blob_bytes + (vb->device_replay ? 0 : 32 * (size_t)vb->n_chal) + (vb->any_msm && !fused ? 32 * n : 0);
+    ctx->io_bytes[0] = vb->blob_bytes + (vb->device_replay ? 0 : 32 * (size_t)vb->n_chal) + (vb->any_msm && !fused ? 64 * n : 0);
     ctx->io_bytes[1] = (dev_replay ? vb->mid_bytes : 0) + vb->n_pts + (vb->any_msm ? vb->n_chunks : 0) + (vb->any_masks ? 32 * n * (size_t)ext : 0);
 
     // ---- resolve per-chunk status with the reference's precedence

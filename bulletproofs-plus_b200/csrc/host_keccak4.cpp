@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 typedef uint64_t v4u __attribute__((vector_size(32)));
+typedef uint64_t v8u __attribute__((vector_size(64)));      // eight states at once: one AVX-512 register per Keccak lane
 
 static const uint64_t RC[24] = {
     0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
@@ -66,6 +67,10 @@ __attribute__((target("avx2"))) static void keccak4_avx2(uint64_t *st) { KECCAK_
 // AVX-512VL: 32 vector registers (no spills of the 25 + 25 live values), native 64-bit rotates and three-input logic
 __attribute__((target("avx2,avx512f,avx512vl"))) static void keccak4_avx512vl(uint64_t *st) { KECCAK_BODY(v4u, KB4) }
 static void keccak4_generic(uint64_t *st) { KECCAK_BODY(v4u, KB4) }
+// EIGHT states per permutation on AVX-512F: 25 zmm registers hold the state, vprolq / vpternlogq do a rotate / a chi term in one
+// instruction each (~100 instructions per round for eight permutations)
+#define KB8(rc) ((v8u){rc, rc, rc, rc, rc, rc, rc, rc})
+__attribute__((target("avx2,avx512f,avx512vl"))) static void keccak8_avx512(uint64_t *st) { KECCAK_BODY(v8u, KB8) }
 static void keccak1_generic(uint64_t *st) { KECCAK_BODY(uint64_t, KB1) }
 
 #include <stdlib.h>
@@ -83,6 +88,18 @@ extern "C" {
 void bpp_keccak_f1600_x4(uint64_t *st) {
     const int level = simd_level();
     if (level == 2) keccak4_avx512vl(st); else if (level == 1) keccak4_avx2(st); else keccak4_generic(st);
+}
+// st: 25 x 8 lanes, lane k of state j at st[8 * k + j]; 64-byte aligned.  Without AVX-512 the eight states go through two four-way
+// permutations.
+void bpp_keccak_f1600_x8(uint64_t *st) {
+    if (simd_level() == 2) { keccak8_avx512(st); return; }
+    alignas(32) uint64_t x[2][100];
+    for (int k = 0; k < 25; k++)
+        for (int j = 0; j < 4; j++) { x[0][4 * k + j] = st[8 * k + j]; x[1][4 * k + j] = st[8 * k + 4 + j]; }
+    bpp_keccak_f1600_x4(x[0]);
+    bpp_keccak_f1600_x4(x[1]);
+    for (int k = 0; k < 25; k++)
+        for (int j = 0; j < 4; j++) { st[8 * k + j] = x[0][4 * k + j]; st[8 * k + 4 + j] = x[1][4 * k + j]; }
 }
 // ONE state (25 lanes): every host-side sponge of the library (hash.cuh on the host: the prover's transcripts and TranscriptRng, SHA3 /
 // SHAKE, host-mode replay) permutes through this.  With AVX2 / AVX-512VL the state rides in lane 0 of the four-way body: 16

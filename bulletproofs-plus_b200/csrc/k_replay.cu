@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(32) k_weights(VDims d, const VChunk *__restric
                 ww[i] = (uint32_t)wide[4 * i] | ((uint32_t)wide[4 * i + 1] << 8) | ((uint32_t)wide[4 * i + 2] << 16) | ((uint32_t)wide[4 * i + 3] << 24);
             w = sc_from_wide_words(ww);
         } while (sc_is_zero(w));                          // warp-uniform
-        if (lane < 8) weights[8 * (size_t)p + lane] = w.v[lane];
+        if (lane < 16) weights[16 * (size_t)p + lane] = lane < 8 ? w.v[lane & 7] : 0u;
     }
 }
 

@@ -164,6 +164,166 @@ __global__ void __launch_bounds__(64) k_vprep_proof(VDims d, VBuffers b) {
     }
 }
 
+// Stage A, warp form (default): one WARP per proof.  The thread form above walks ~150 Montgomery products and a binary-Euclid
+// inversion one after the other (200 us for any batch size: the second longest latency chain of a pass in round 1); here lane j owns
+// round j (rounds <= 24), the batch inversion is a shuffle scan (prefix and suffix products), sums over rounds / commitments are
+// shuffle reductions, and what remains sequential is the y^(2^k) chain (rounds squarings, twice), two 5-step scans and ONE inversion.
+// y_sum is taken as y * prod_{k < rounds} (1 + y^(2^k)) = y (y^N - 1) / (y - 1) and d_sum as (2^n - 1) * sum_j z^(2j) directly: the
+// same scalars mod l as range_proof.rs:913-938 without the (y - 1) inverse (y = 1 is flagged by the replay).
+static __device__ __forceinline__ sc shfl_sc(const sc &a, int src) {
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return r;
+}
+static __device__ __forceinline__ sc shfl_up_sc(const sc &a, int delta) {
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], delta);
+    return r;
+}
+static __device__ __forceinline__ sc shfl_xor_sc(const sc &a, int mask) {
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], mask);
+    return r;
+}
+static __device__ __forceinline__ sc shfl_down_sc2(const sc &a, int delta) {
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], delta);
+    return r;
+}
+static __device__ __forceinline__ sc warp_sum_sc(sc a) {
+    for (int mk = 16; mk > 0; mk >>= 1) a = sc_add(a, shfl_xor_sc(a, mk));
+    return a;
+}
+static __device__ __forceinline__ sc sc_pick(const sc &a, const sc &b, bool pick_b) {
+    sc r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = pick_b ? b.v[i] : a.v[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_vprep_proof_w(VDims d, VBuffers b) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= d.n_proofs) return;
+    const VProof pr = b.proofs[p];
+    if (!pr.replay || (!pr.active && pr.nonce_off == 0xffffffffu)) return;     // warp-uniform
+    const int R = (int)pr.rounds;                   // <= BPP_MAX_ROUNDS = 24: rounds, y, e and z^2 y^(N+1) fit one warp
+    const uint32_t m = pr.m, ext = d.ext;
+    const sc one_m = sc_const_R();
+    const uint32_t *ch = b.challenges + 8 * (size_t)pr.ch_off;
+    const uint8_t *raw = b.blob + pr.raw_off;
+    const sc y = ld_mont(ch), z = ld_mont(ch + 8), e = ld_mont(ch + 16);
+    const sc z2 = mm(z, z), e2 = mm(e, e);
+    // y^(2^k): every lane walks the chain, lane k keeps y^(2^k)
+    sc yk = y, ypow = y;
+    for (int k = 1; k <= R; k++) { yk = mm(yk, yk); if (lane == k) ypow = yk; }
+    const sc yN = yk, yN1 = mm(yN, y);
+    const sc zy = mm(z2, yN1);
+    // items of the batch inversion: lane j < R: e_j; R: y; R + 1: e; R + 2: z^2 y^(N+1); others 1
+    sc x = one_m;
+    if (lane < R) x = ld_mont(ch + 24 + 8 * lane);
+    else if (lane == R) x = y;
+    else if (lane == R + 1) x = e;
+    else if (lane == R + 2) x = zy;
+    sc P = x, S = x;                                // inclusive prefix / suffix products
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const sc t = shfl_up_sc(P, dd), u = shfl_down_sc2(S, dd);
+        const sc pn = mm(P, t), sn = mm(S, u);
+        P = sc_pick(P, pn, lane >= dd);
+        S = sc_pick(S, sn, lane + dd < 32);
+    }
+    const sc inv_total = scm_invert_gcd(shfl_sc(P, 31));           // every lane computes it: no broadcast on the critical path
+    sc Pm1 = shfl_up_sc(P, 1), Sp1 = shfl_down_sc2(S, 1);
+    Pm1 = sc_pick(Pm1, one_m, lane == 0);
+    Sp1 = sc_pick(Sp1, one_m, lane == 31);
+    const sc xinv = mm(inv_total, mm(Pm1, Sp1));                    // lane j < R: e_j^-1; R: y^-1; R + 1: e^-1; R + 2: (z^2 y^(N+1))^-1
+    const sc y_inv = shfl_sc(xinv, R), e_inv = shfl_sc(xinv, R + 1), zy_inv = shfl_sc(xinv, R + 2);
+    const sc s0 = mm(inv_total, shfl_sc(S, R));                     // prod e_j^-1 = s[0]
+    const sc prod_e = shfl_sc(P, R - 1);                            // prod e_j = s[N-1]
+    const sc ej2 = mm(x, x), ejinv2 = mm(xinv, xinv);               // meaningful on lanes < R
+
+    // mask recovery (range_proof.rs:941-969)
+    if (pr.nonce_off != 0xffffffffu && b.masks) {
+        const uint32_t *nn = b.nonces + 8 * (size_t)pr.nonce_off;
+        const sc e2inv = mm(e_inv, e_inv);
+        for (uint32_t k = 0; k < ext; k++) {
+            sc term = sc_zero();
+            if (lane < R) {
+                const sc dL = ld_mont(nn + 8 * (3 * ext + lane * ext + k)), dR = ld_mont(nn + 8 * (3 * ext + R * ext + lane * ext + k));
+                term = sc_add(mm(ej2, dL), mm(ejinv2, dR));
+            }
+            term = warp_sum_sc(term);
+            if (lane == 0) {
+                const sc d1k = ld_raw_mont(raw + BPP_RAW_D1(ext, k));
+                const sc eta = ld_mont(nn + 8 * k), dk = ld_mont(nn + 8 * (ext + k)), alpha = ld_mont(nn + 8 * (2 * ext + k));
+                sc mask = sc_sub(sc_sub(d1k, eta), mm(e, dk));
+                mask = sc_sub(sc_sub(mm(mask, e2inv), alpha), term);
+                st_sc(b.masks + 8 * ((size_t)p * ext + k), sc_from_mont(mm(mask, zy_inv)));
+            }
+        }
+    }
+    if (!pr.active) return;
+
+    const sc neg_e2 = sc_neg(e2);
+    uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;
+    uint32_t *pv = b.pervec + 8 * (size_t)pr.pv_off;
+    // dynamic entries [A1, B, A, L_0.., R_0.., V_0..], still WITHOUT the weight and in Montgomery form
+    if (lane == 0) { st_sc(out, sc_neg(e)); st_sc(out + 8, sc_neg(one_m)); st_sc(out + 16, neg_e2); }
+    if (lane < R) { st_sc(out + 8 * (3 + lane), mm(neg_e2, ej2)); st_sc(out + 8 * (3 + R + lane), mm(neg_e2, ejinv2)); }
+    // y_sum = y * prod_k (1 + y^(2^k))
+    sc f = lane < R ? sc_add(one_m, ypow) : one_m;
+    for (int mk = 16; mk > 0; mk >>= 1) f = mm(f, shfl_xor_sc(f, mk));
+    const sc y_sum = mm(f, y);
+    // z^(2(j+1)) for the commitments: lane l starts at z2^(l+1) (scan of a constant), strides by z2^32
+    sc zl = z2;
+    for (int dd = 1; dd < 32; dd <<= 1) { const sc t = shfl_up_sc(zl, dd); const sc zn = mm(zl, t); zl = sc_pick(zl, zn, lane >= dd); }
+    const sc z32 = shfl_sc(zl, 31);
+    const sc neg_e2_yN1 = mm(neg_e2, yN1);
+    sc h = sc_zero(), zsum = sc_zero();
+    for (uint32_t j = (uint32_t)lane; j < m; j += 32) {
+        st_sc(pv + 8 * (PV_HDR + 3 * R + j), zl);
+        const sc weighted = mm(neg_e2_yN1, zl);
+        st_sc(out + 8 * (3 + 2 * R + j), weighted);
+        if (b.min_present[pr.commit_off + j]) h = sc_sub(h, mm(weighted, sc_to_mont(sc_from_u64(b.min_values[pr.commit_off + j]))));
+        zsum = sc_add(zsum, zl);
+        zl = mm(zl, z32);
+    }
+    h = warp_sum_sc(h);
+    zsum = warp_sum_sc(zsum);
+    const sc r1 = ld_raw_mont(raw + BPP_RAW_R1(ext)), s1 = ld_raw_mont(raw + BPP_RAW_S1(ext));
+    if (lane == 0) {
+        const uint64_t two_n_m1 = d.bit_length >= 64 ? ~0ull : ((1ull << d.bit_length) - 1ull);
+        const sc d_sum = mm(zsum, sc_to_mont(sc_from_u64(two_n_m1)));
+        // h += r1*y*s1 + e^2*(y^(N+1)*z*d_sum + (z^2 - z)*y_sum)   (range_proof.rs:1017-1020, weight applied later)
+        const sc t = mm(mm(r1, y), s1);
+        const sc u = sc_add(mm(mm(yN1, z), d_sum), mm(sc_sub(z2, z), y_sum));
+        uint32_t *hg = b.hg_contrib + 8 * (size_t)p * (1 + ext);
+        st_sc(hg, sc_add(h, sc_add(t, mm(e2, u))));
+        // hand-off to stage B (layout above)
+        st_sc(pv, mm(mm(e, r1), s0));
+        st_sc(pv + 8, mm(mm(e, s1), prod_e));
+        st_sc(pv + 16, mm(e2, yN));
+        st_sc(pv + 24, mm(e2, z));
+    }
+    if ((uint32_t)lane < ext) st_sc(b.hg_contrib + 8 * ((size_t)p * (1 + ext) + 1 + lane), ld_raw_mont(raw + BPP_RAW_D1(ext, lane)));
+    // per bit k of i (challenge e_j with j = R-1-k): ru_k, rv_k, rq_k; lane k needs y^-(2^k)
+    sc yp = y_inv;
+    for (int it = 0; it < R - 1; it++) { const sc sq = mm(yp, yp); yp = sc_pick(yp, sq, lane > it); }
+    const int jsrc = R - 1 - lane;
+    const sc ej2_r = shfl_sc(ej2, jsrc & 31), ejinv2_r = shfl_sc(ejinv2, jsrc & 31);
+    if (lane < R) {
+        st_sc(pv + 8 * (PV_HDR + lane), mm(ej2_r, yp));
+        st_sc(pv + 8 * (PV_HDR + R + lane), ejinv2_r);
+        sc rq = yp;
+        if ((1u << lane) < d.bit_length) rq = mm(rq, sc_to_mont(sc_from_u64(1ull << (1u << lane))));     // bit_length <= 64: lane <= 5
+        st_sc(pv + 8 * (PV_HDR + 2 * R + lane), rq);
+    }
+}
+
 // Stage B.  Table path (rounds <= VEC_TABLE_MAX_ROUNDS): i = (hi << rl) | lo, tables T_lo[lo] = base * prod_{k in bits(lo)} r_k and
 // T_hi[hi] = prod_{k in bits(hi)} r_(rl+k) for each of the three products (u, v, q), built by doubling (T[x + 2^k] = T[x] * r_k);
 // an element then costs 4 multiplications (u, v, q, q * z^(2(party+1))).  Shared memory: 3 * (2^rl + 2^rh) scalars.
@@ -249,7 +409,11 @@ __global__ void __launch_bounds__(128) k_vprep_reduce(VDims d, VBuffers b) {
         else if (slot < 2 * chk.max_mn) { uint32_t i = slot - chk.max_mn; if (i < N) src = b.contrib + 8 * ((size_t)pr.contrib_off + N + i); }
         else if (slot < 2 * chk.max_mn + d.ext) src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext) + 1 + (slot - 2 * chk.max_mn));
         else src = b.hg_contrib + 8 * ((size_t)p * (1 + d.ext));
-        if (src) acc = sc_add(acc, mm(ld_sc(src), ld_sc(b.weights_mont + 8 * (size_t)p)));
+        const sc wp = ld_sc(b.weights_mont + 8 * (size_t)p);
+        // a weight that reduced to zero is what Scalar::random_not_zero would have redrawn (probability 2^-252): reported per chunk, the host
+        // redoes that chunk's weight transcript with the redraw and the pass is repeated (engine_verify.cu)
+        if (slot == 0 && sc_is_zero(wp)) b.weight_zero[c] = 1;
+        if (src) acc = sc_add(acc, mm(ld_sc(src), wp));
     }
     for (int delta = 16; delta > 0; delta >>= 1) acc = sc_add(acc, shfl_down_sc(acc, delta));
     if (lane == 0) {
@@ -266,7 +430,15 @@ __global__ void __launch_bounds__(128) k_vprep_weight(VDims d, VBuffers b) {
     if (p >= d.n_proofs) return;
     const VProof pr = b.proofs[p];
     if (!pr.active) return;
-    const sc w = ld_mont(b.weights + 8 * (size_t)p);
+    // the 64 bytes the weight transcript's rng delivered -> Scalar::from_bytes_mod_order_wide -> Montgomery form
+    uint32_t ww[16];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.weights + 16 * (size_t)p);
+        const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+        ww[0] = q0.x; ww[1] = q0.y; ww[2] = q0.z; ww[3] = q0.w; ww[4] = q1.x; ww[5] = q1.y; ww[6] = q1.z; ww[7] = q1.w;
+        ww[8] = q2.x; ww[9] = q2.y; ww[10] = q2.z; ww[11] = q2.w; ww[12] = q3.x; ww[13] = q3.y; ww[14] = q3.z; ww[15] = q3.w;
+    }
+    const sc w = sc_to_mont(sc_from_wide_words(ww));
     if (lane == 0) st_sc(b.weights_mont + 8 * (size_t)p, w);
     const uint32_t n_dyn = 3 + 2 * pr.rounds + pr.m;
     uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;
@@ -280,7 +452,9 @@ __global__ void __launch_bounds__(128) k_vprep_weight(VDims d, VBuffers b) {
 void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint32_t total_vec, uint32_t max_rounds, uint64_t *launches,
                         cudaEvent_t *marks) {
     if (d.n_proofs == 0) return;
-    k_vprep_proof<<<(d.n_proofs + 63) / 64, 64, 0, s>>>(d, b);
+    static const bool thread_form = getenv("BPP_VPREP_THREAD") != nullptr;      // the round-1 kernel (one thread per proof), kept for comparison
+    if (thread_form) k_vprep_proof<<<(d.n_proofs + 63) / 64, 64, 0, s>>>(d, b);
+    else k_vprep_proof_w<<<(d.n_proofs + 3) / 4, 128, 0, s>>>(d, b);
     if (marks) cudaEventRecord(marks[0], s);
     if (launches) (*launches)++;
     if (d.action != 0 /* RecoverOnly */ && total_vec) {

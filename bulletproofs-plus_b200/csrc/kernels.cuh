@@ -92,7 +92,8 @@ struct VBuffers {
     const uint32_t *pt_offsets;      // n_proofs + 1: first slot of every proof in the point table (prefix sums; proofs without device work are empty)
     const uint8_t *blob;             // uploaded bytes; the proof scalars r1, s1, d1 are read from VProof::raw_off
     const uint32_t *challenges;      // words
-    const uint32_t *weights;         // n_proofs x 8 words (canonical); consumed by k_vprep_weight only
+    const uint32_t *weights;         // n_proofs x 16 words: the 512-bit value whose reduction mod l is the batch weight; consumed by k_vprep_weight only
+    uint8_t *weight_zero;            // out: n_chunks flags, set when a weight of the chunk reduced to zero
     uint32_t *weights_mont;          // scratch: n_proofs x 8 words, Montgomery form
     const uint64_t *min_values; const uint8_t *min_present;
     const uint32_t *nonces;          // words, may be null
@@ -126,7 +127,7 @@ struct RBuffers {
 // proof, state in local memory (the round-1 kernel); 2 = one warp per proof (wstrobe.cuh)
 void launch_replay(cudaStream_t s, const VDims &d, const RBuffers &b, int kernel, uint64_t *launches);
 // verifier weights of every active chunk (one warp per chunk); wt_init = 203-byte state of the weight transcript after its
-// domain separator; weights: n_proofs x 8 words, canonical
+// domain separator; weights: n_proofs x 16 words (canonical weight, upper half zero)
 void launch_weights(cudaStream_t s, const VDims &d, const VChunk *chunks, const uint8_t *wt_init, const uint8_t *wbytes, const uint8_t *flags,
                     uint32_t *weights, uint64_t *launches);
 

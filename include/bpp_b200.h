@@ -78,6 +78,9 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
  * copy with its own driver call, which is also what bpp_ctx_phase_timing(ctx, 1) forces).  Results are identical. */
 int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable);
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx);
+/* test hooks (results must not change): bit 0 = every verification pass is repeated through the zero-weight fallback (the path taken
+ * when a batch weight reduces to zero and Scalar::random_not_zero would draw again, range_proof.rs:894) */
+int32_t bpp_ctx_set_test_hooks(bpp_ctx *ctx, uint32_t flags);
 /* throughput mode (default 0), for callers that keep several verification calls in flight from several ctxs:
  *   1 = the calling thread sleeps between polls of its events (60 us naps, BPP_NAP_US) instead of spinning while the device works:
  *       with many ctxs per GPU spinning threads starve each other and the host hashing.  (cudaEventBlockingSync waits were tried
@@ -111,8 +114,9 @@ void bpp_host_sc_mul64(const uint8_t a32[32], const uint8_t b32[32], uint8_t out
 /* test hook, host only: the portable (non-MULX) body of the two functions above: b32_or_null != NULL -> a32 * b32 mod l,
  * else the wide reduction of 64 bytes */
 void bpp_host_sc_generic64(const uint8_t *a32_or_wide64, const uint8_t *b32_or_null, uint8_t out32[32]);
-/* test hook, host only: the verifier weights (range_proof.rs:811-853, :894) of n_chunks <= 4 chunks of `len` proofs each from the 32
- * bytes every proof feeds into the weight transcript; lockstep = 1 runs the chunks through the four-way vectorised sponge */
+/* test hook, host only: the verifier weights (range_proof.rs:811-853, :894) of n_chunks <= 8 chunks of `len` proofs each from the 32
+ * bytes every proof feeds into the weight transcript; lockstep = 0: one transcript at a time, 1: n_chunks <= 4 through the four-way
+ * vectorised sponge, 2: through the eight-way sponge (AVX-512; two four-way permutations elsewhere) */
 int32_t bpp_host_verifier_weights(const uint8_t *wbytes32, size_t len, size_t n_chunks, int32_t lockstep, uint8_t *weights32);
 /* Host-side sum of n <= 64 points (32-byte encodings): the last step of a multi-GPU MSM, each GPU having reduced its shard to one
  * partial result.  BPP_INVALID_ARGUMENT if an encoding does not decode. */

@@ -133,7 +133,7 @@ def test_points_sum_host_matches_oracle():
         bpp.pkg.points_sum_host(pts[0] + b"\xff" * 32)
 
 
-@pytest.mark.parametrize("shape", [(1, 1), (1, 5), (2, 7), (4, 37), (3, 100), (2, 255), (4, 256)])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 5), (2, 7), (4, 37), (3, 100), (2, 255), (4, 256), (5, 9), (8, 256), (7, 33)])
 def test_host_verifier_weights_match_oracle(shape):
     """the product's host-side verifier-weight transcripts (range_proof.rs:811-853, :894) -- one at a time and four in lock-step
     through the vectorised four-way Keccak-f (host_keccak4.cpp) -- against the oracle's restatement of the same lines"""
@@ -145,7 +145,9 @@ def test_host_verifier_weights_match_oracle(shape):
         part = C.create_string_buffer(32 * length)
         orc.lib().orc_verifier_weights(wb[32 * length * c: 32 * length * (c + 1)], length, part)
         C.memmove(C.addressof(want) + 32 * length * c, part, 32 * length)
-    for lockstep in (0, 1):
+    for lockstep in (0, 1, 2):          # one transcript at a time, four in lock-step, eight in lock-step
+        if lockstep == 1 and n_chunks > 4:
+            continue
         got = C.create_string_buffer(32 * length * n_chunks)
         assert lib.bpp_host_verifier_weights(wb, length, n_chunks, lockstep, got) == 0
         assert got.raw == want.raw, lockstep
@@ -240,7 +242,7 @@ for c in range(n_chunks):
     part = C.create_string_buffer(32 * length)
     orc.lib().orc_verifier_weights(wb[32 * length * c: 32 * length * (c + 1)], length, part)
     want += part.raw
-for lockstep in (0, 1):
+for lockstep in (0, 1, 2):
     got = C.create_string_buffer(32 * length * n_chunks)
     assert lib.bpp_host_verifier_weights(wb, length, n_chunks, lockstep, got) == 0
     assert got.raw == want

@@ -554,6 +554,15 @@ class _QueueShape:
         self.gens = self._G()
         self.gens.bit_length, self.gens.max_aggregation, self.gens.extension_degree = bit_length, max_aggregation, extension_degree
 
+    def bit_length(self):
+        return self.gens.bit_length
+
+    def max_aggregation_factor(self):
+        return self.gens.max_aggregation
+
+    def extension_degree(self):
+        return ExtensionDegree(self.gens.extension_degree)
+
 
 class VerifierPool:
     """S independent verification lanes on ONE GPU: one bpp_ctx (stream pair, pooled workspace, generator tables) and one

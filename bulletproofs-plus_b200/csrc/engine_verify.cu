@@ -512,10 +512,11 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     });
     // ---- per-chunk consistency (:610-709) and the totals of the device layout
     uint64_t n_pts = 0, n_entries = 0, contrib = 0, pv = 0, n_chal = 0, n_nonce = 0;
-    uint32_t max_static = 0;
+    uint32_t max_static = 0, max_seg_entries = 0;
     for (size_t c = 0; c < NC; c++) {
         HChunk &hc = vb->hc[c];
         if (hc.pre_rc) continue;
+        const uint64_t entries_before = n_entries;
         int32_t ext_rc = 0, promise_rc = 0;
         bool rounds_ok = true;
         uint32_t max_mn = 0;
@@ -547,6 +548,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
             if (hc.computable && want_masks && p.has_seed) n_nonce += (uint64_t)ext * (3 + 2 * R);
             if (msm) { contrib += 2ull << R; pv += 8 + 3 * R + p.m; n_entries += 3 + 2 * R + p.m; }
         }
+        max_seg_entries = (uint32_t)std::max<uint64_t>(max_seg_entries, std::min<uint64_t>(n_entries - entries_before, 0xffffffffu));
     }
     if (n_pts >= (1ull << 30) || n_entries >= (1ull << 30) || contrib >= (1ull << 31) || pv >= (1ull << 31) || n_chal >= (1ull << 31) ||
         n_nonce >= (1ull << 31)) {
@@ -590,6 +592,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     const size_t np1 = std::max<size_t>(NP, 1);
     // static entries of a chunk are bounded by the generator set; the MSM shape needs the entry count only
     vb->shape = msm_shape(vb->n_entries, (uint32_t)NC, 0);
+    vb->shape.max_seg_entries = max_seg_entries;
     ok(w->h_blob.ensure(vb->blob_bytes));
     ok(w->d_blob.ensure(vb->blob_bytes));
     ok(w->h_out.ensure(vb->hout_bytes));
@@ -680,9 +683,11 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     lap();   // [1] layout
 
     // ---- fill: the callers' byte arrays as they are, one memcpy each
-    for (const HCall &call : vb->calls) {
+    // (the callers' buffers are cold in the cache more often than not: one thread copies ~7 GB/s, so the calls are spread over the workers)
+    ctx->workers().run(vb->calls.size(), 1, [&](size_t ci) {
+        const HCall &call = vb->calls[ci];
         const bpp_verify_args &a = call.a;
-        if (!a.n_proofs) continue;
+        if (!a.n_proofs) return;
         const size_t raw_len = a.proof_offsets[a.n_proofs] - a.proof_offsets[0];
         const size_t c_lo = a.commit_offsets[0], c_n = a.commit_offsets[a.n_proofs] - c_lo;
         memcpy(hb + vb->o_raw + call.raw0, a.proof_bytes + a.proof_offsets[0], raw_len);
@@ -690,7 +695,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
         memcpy(hb + vb->o_minv + 8 * call.commit0, a.min_values + c_lo, 8 * c_n);
         memcpy(hb + vb->o_minp + call.commit0, a.min_present + c_lo, c_n);
         if (vb->device_replay) memcpy(hb + vb->o_tstate + BPP_TRANSCRIPT_BYTES * call.proof0, a.transcripts, BPP_TRANSCRIPT_BYTES * a.n_proofs);
-    }
+    });
     memcpy(hb + vb->o_hg, g->h(), 32);
     memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);
     memcpy(hb + vb->o_wtinit, weight_transcript_init().data(), BPP_TRANSCRIPT_BYTES);      // starting state of k_weights
@@ -780,10 +785,10 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
     if (!vb->device_replay && n_chal) ok(cudaMemcpyAsync(w->d_chal.p, w->h_chal.p, 32 * (size_t)n_chal, cudaMemcpyHostToDevice, st));
     // The upload is ordered before the kernels of bpp_vbatch_run on the same stream and the pinned blob belongs to this vbatch's
-    // workspace until bpp_vbatch_destroy (which drains the stream), so nothing needs the host to wait here; outside throughput mode
-    // it still does, so that upload errors surface in this call and host_ms[4] is the H2D time.
-    static const bool always_sync = getenv("BPP_CREATE_SYNC") != nullptr;
-    if (e == cudaSuccess && (!ctx->throughput_mode || always_sync)) e = cudaStreamSynchronize(st);
+    // workspace until bpp_vbatch_destroy (which drains the stream), so nothing needs the host to wait here (an upload error
+    // surfaces in bpp_vbatch_run).
+    static const bool always_sync = getenv("BPP_CREATE_SYNC") != nullptr;      // debugging: upload errors surface here, host_ms[4] = H2D time
+    if (e == cudaSuccess && always_sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
     lap();   // [4] H2D
     ctx->io_bytes[0] = vb->blob_bytes + (vb->device_replay ? 0 : 32 * (size_t)n_chal); ctx->io_bytes[1] = 0;
@@ -977,6 +982,7 @@ static VGraphKey make_graph_key(const bpp_vbatch *vb, const VLaunch &L, bool fus
     k.n_pts = vb->n_pts; k.n_entries = vb->n_entries; k.n_chal = vb->n_chal; k.max_static = vb->max_static; k.max_rounds = vb->max_rounds;
     k.action = vb->action; k.ext = vb->g->ext; k.bit_length = vb->g->n;
     k.shape.n_entries = vb->shape.n_entries; k.shape.n_seg = vb->shape.n_seg; k.shape.c = vb->shape.c; k.shape.W = vb->shape.W; k.shape.B = vb->shape.B;
+    k.shape.max_seg_entries = vb->shape.max_seg_entries;
     msm_knobs(k.msm_knobs);
     k.any_msm = vb->any_msm; k.any_masks = vb->any_masks; k.any_replay = vb->any_replay; k.any_vec = vb->any_vec;
     k.device_replay = L.dev_replay; k.replay_kernel = (uint8_t)L.replay_kernel;

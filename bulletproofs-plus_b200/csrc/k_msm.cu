@@ -53,11 +53,34 @@ static __device__ __forceinline__ uint32_t seg_of(const uint32_t *seg_offsets, u
     return lo;
 }
 
+// the switches below select kernel variants (tests / experiments); getenv is neither cheap nor safe against a concurrent setenv, so
+// they are read once
+namespace {
+struct MsmKnobs { int bucket, split, reduce, reduce_parts, scan_sort, no_heavy, tune_occ; };
+const MsmKnobs &knobs() {
+    static const MsmKnobs k = [] {
+        auto geti = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
+        MsmKnobs r;
+        r.bucket = geti("BPP_MSM_BUCKET", 0);                 // 1 = quads, 2 = threads, 3 = split threads
+        r.split = geti("BPP_MSM_SPLIT", 4);
+        r.reduce = geti("BPP_MSM_REDUCE", 0);                 // 1 = CTA of quads, 2 = warp of threads
+        r.reduce_parts = geti("BPP_MSM_REDUCE_PARTS", 0);
+        r.tune_occ = geti("BPP_TUNE_OCC", 0);
+        r.no_heavy = geti("BPP_MSM_NO_HEAVY", 0);               // 1 = over-full buckets stay with the ordinary bucket kernels (comparison)
+        r.scan_sort = geti("BPP_MSM_SCAN_SORT", 0);             // 1 = always the scan-based counting sort (tests: both sorts give the same sums)
+        return r;
+    }();
+    return k;
+}
+}
+void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts | (k.scan_sort << 8) | (k.no_heavy << 9) | (k.tune_occ << 10); }
+
 // ------------------------------------------------------------------------------------------------ shape
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     MsmShape sh;
     sh.n_entries = n_entries;
     sh.n_seg = n_seg ? n_seg : 1;
+    sh.max_seg_entries = 0;
     int c = forced_c;
     static const int env_c = getenv("BPP_MSM_C") ? atoi(getenv("BPP_MSM_C")) : 0;       // experiments only
     if (c <= 0 && env_c > 0 && n_entries / sh.n_seg < 16384) c = env_c;
@@ -74,7 +97,10 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
         for (int cc = 2; cc <= 16; cc++) {
             int W = (252 + cc - 1) / cc;
             int top_bits = 251 - cc * (W - 1);
-            if (per >= 1024 && top_bits < cc - 3) continue;
+            // a top window that is far from full means few, over-full buckets: fine for one large sum (section 4b splits them), still
+            // avoided for segments, whose buckets are walked by single threads / quads
+            const bool splits_heavy = sh.n_seg == 1 && per >= 16384 && !knobs().no_heavy;
+            if (per >= 1024 && top_bits < cc - 3 && !splits_heavy) continue;
             double B = (double)(1u << (cc - 1));
             double cost;
             if (per >= 16384 && sh.n_seg == 1) {
@@ -102,37 +128,25 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
     return sh;
 }
 
-// the switches below select kernel variants (tests / experiments); getenv is neither cheap nor safe against a concurrent setenv, so
-// they are read once
-namespace {
-struct MsmKnobs { int bucket, split, reduce, reduce_parts; };
-const MsmKnobs &knobs() {
-    static const MsmKnobs k = [] {
-        auto geti = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
-        MsmKnobs r;
-        r.bucket = geti("BPP_MSM_BUCKET", 0);                 // 1 = quads, 2 = threads, 3 = split threads
-        r.split = geti("BPP_MSM_SPLIT", 4);
-        r.reduce = geti("BPP_MSM_REDUCE", 0);                 // 1 = CTA of quads, 2 = warp of threads
-        r.reduce_parts = geti("BPP_MSM_REDUCE_PARTS", 0);
-        return r;
-    }();
-    return k;
-}
-}
-void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts; }
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #define SCAN_TILE 4096u
 #define REDUCE_PARTS_MAX 8u
+// buckets with more than HEAVY_MIN entries are cut into parts of HEAVY_PART entries that whole CTAs sum (section 4b)
+#define HEAVY_PART 2048u
+#define HEAVY_MIN 4096u
 
 struct MsmScratch {
     uint32_t *starts;   // n_keys + 1
-    uint32_t *cursor;   // n_keys
+    uint32_t *cursor;   // n_keys (scan-based sort: scatter cursors; shared-memory sort: per-bucket counts)
     uint32_t *tile_sums;
     uint32_t *sorted;   // n_entries * W
     cached *buckets;    // n_keys
     ge *windows;        // n_seg * W
     ge *wparts;         // n_seg * W * REDUCE_PARTS_MAX: partial window sums of k_msm_reduce when a window is split over several CTAs
+    uint32_t *heavy_n;  // number of work items of the over-full buckets (see "4b")
+    uint2 *heavy_items; // (key, part)
+    ge *heavy_parts;    // partial sum of every item
+    uint32_t heavy_cap;
     size_t total;
 };
 static MsmScratch msm_carve(const MsmShape &sh, void *base) {
@@ -148,6 +162,10 @@ static MsmScratch msm_carve(const MsmShape &sh, void *base) {
     s.buckets = (cached *)(p + off); off = align_up(off + n_keys * sizeof(cached), 256);
     s.windows = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * sizeof(ge), 256);
     s.wparts = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * REDUCE_PARTS_MAX * sizeof(ge), 256);
+    s.heavy_cap = (uint32_t)(((size_t)sh.n_entries * sh.W) / HEAVY_PART + 1024);
+    s.heavy_n = (uint32_t *)(p + off); off = align_up(off + 256, 256);
+    s.heavy_items = (uint2 *)(p + off); off = align_up(off + (size_t)s.heavy_cap * sizeof(uint2), 256);
+    s.heavy_parts = (ge *)(p + off); off = align_up(off + (size_t)s.heavy_cap * sizeof(ge), 256);
     s.total = off;
     return s;
 }
@@ -192,6 +210,106 @@ __global__ void __launch_bounds__(256) k_msm_digits(uint32_t n_entries, uint32_t
             uint32_t key = key_base + (uint32_t)w * B + (d - 1u);
             uint32_t pos = atomicAdd(&counters[key], 1u);
             if (SCATTER) sorted[pos] = i | (neg << 31);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 1': sort in shared memory
+// Small segments (the verifier's <= 256-proof chunks: ~4.2 k entries, 256 buckets per window): ONE CTA sorts one (segment, window)
+// entirely in shared memory -- digit of every entry of the segment for this window, histogram, exclusive scan, scatter -- and writes
+// the window's records as one contiguous run plus (start, count) per bucket.  Replaces memset + count pass + three scan kernels +
+// scatter pass (6 launches, two rounds of global atomics on n_seg * W * B counters) by one launch without global atomics.
+// The signed recoding carries from window to window; the carry INTO window w is 1 iff the low c*w bits of the scalar exceed
+// T_w = B * (2^(c w) - 1) / (2^c - 1)  (digits B, B, .., B in base 2^c; B = 2^(c-1)): induction over "digit + carry > B".
+// Region of (segment, window) inside `sorted`: seg_lo * W + w * len (len = entries of the segment): the same n_entries * W words as the
+// scan-based layout, records of empty (zero) digits simply missing at the end of each region.
+template <int BMAX>
+__global__ void __launch_bounds__(256) k_msm_sort_seg(uint32_t n_entries, uint32_t n_seg, int c, int W, uint32_t B, const uint32_t *__restrict__ scalars,
+                                                     const uint32_t *__restrict__ seg_offsets, uint32_t *__restrict__ starts, uint32_t *__restrict__ counts,
+                                                     uint32_t *__restrict__ sorted) {
+    __shared__ uint32_t s_hist[BMAX], s_scan[256], s_thr[8];
+    const uint32_t seg = blockIdx.x / (uint32_t)W, w = blockIdx.x % (uint32_t)W, tid = threadIdx.x;
+    const uint32_t lo = n_seg > 1 ? seg_offsets[seg] : 0u, hi = n_seg > 1 ? seg_offsets[seg + 1] : n_entries;
+    const uint32_t len = hi - lo;
+    const uint32_t region = lo * (uint32_t)W + w * len;
+    const uint32_t key_base = (seg * (uint32_t)W + w) * B;
+    for (uint32_t bkt = tid; bkt < B; bkt += 256) s_hist[bkt] = 0;
+    if (tid < 8) {                                   // T_w: bit (c - 1) + c k set for k < w
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < w; k++) { const uint32_t bit = (uint32_t)(c - 1) + (uint32_t)c * k; if ((bit >> 5) == tid) t |= 1u << (bit & 31); }
+        s_thr[tid] = t;
+    }
+    __syncthreads();
+    const int lowbits = c * (int)w;                  // bits of the scalar below this window
+    auto digit_of = [&](uint32_t i, uint32_t &neg) -> uint32_t {
+        uint32_t s[8];
+        ld8(s, scalars + 8 * (size_t)i);
+        // s > l/2  ->  (l - s, -P): the recoded scalar is < 2^251 (see k_msm_digits)
+        uint32_t t[8];
+        int64_t bw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { bw += (int64_t)sc_l(k) - (int64_t)s[k]; t[k] = (uint32_t)bw; bw >>= 32; }
+        bool gt = false, decided = false;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) if (!decided && s[k] != t[k]) { gt = s[k] > t[k]; decided = true; }
+        neg = gt ? 1u : 0u;
+        if (gt) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = t[k];
+        }
+        // carry into this window: (s mod 2^lowbits) > T_w
+        uint32_t carry = 0;
+        {
+            bool g2 = false, dec2 = false;
+#pragma unroll
+            for (int k = 7; k >= 0; k--) {
+                const int base = 32 * k;
+                uint32_t m = lowbits >= base + 32 ? 0xffffffffu : lowbits <= base ? 0u : ((1u << (lowbits - base)) - 1u);
+                const uint32_t a = s[k] & m, th = s_thr[k];
+                if (!dec2 && a != th) { g2 = a > th; dec2 = true; }
+            }
+            carry = g2 ? 1u : 0u;
+        }
+        uint32_t dg = bits_at(s, lowbits, c) + carry;
+        if (dg > B) { dg = 2u * B - dg; neg ^= 1u; }
+        return dg;
+    };
+    for (uint32_t i = lo + tid; i < hi; i += 256) {
+        uint32_t neg;
+        const uint32_t dg = digit_of(i, neg);
+        if (dg) atomicAdd(&s_hist[dg - 1u], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the B counters: thread t owns buckets [t * per, (t + 1) * per)
+    const uint32_t per = (B + 255u) / 256u;
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < per; k++) { const uint32_t bkt = tid * per + k; if (bkt < B) acc += s_hist[bkt]; }
+    s_scan[tid] = acc;
+    __syncthreads();
+    for (int sft = 1; sft < 256; sft <<= 1) {
+        const uint32_t t = (int)tid >= sft ? s_scan[tid - sft] : 0u;
+        __syncthreads();
+        s_scan[tid] += t;
+        __syncthreads();
+    }
+    uint32_t run = s_scan[tid] - acc;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t bkt = tid * per + k;
+        if (bkt < B) {
+            const uint32_t cnt = s_hist[bkt];
+            starts[key_base + bkt] = region + run;
+            counts[key_base + bkt] = cnt;
+            s_hist[bkt] = run;                       // becomes the bucket's cursor
+            run += cnt;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = lo + tid; i < hi; i += 256) {
+        uint32_t neg;
+        const uint32_t dg = digit_of(i, neg);
+        if (dg) {
+            const uint32_t pos = atomicAdd(&s_hist[dg - 1u], 1u);
+            sorted[region + pos] = i | (neg << 31);
         }
     }
 }
@@ -261,17 +379,18 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t *__restrict__ count
 // the 8 buckets of a warp then have neighbouring sizes (bucket sizes of a 4226-entry segment at c = 9 spread 16.5 +- 4, which
 // without the ranking costs ~35 % of the additions as padding).
 #define BUCKET_CTA 256
-__global__ void __launch_bounds__(BUCKET_CTA) k_msm_bucket(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(BUCKET_CTA) k_msm_bucket(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ sorted,
                                                    const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
                                                    const aniels *__restrict__ gens, const cached *__restrict__ dync,
-                                                   cached *__restrict__ buckets) {
+                                                   cached *__restrict__ buckets, uint32_t heavy_min) {
     constexpr uint32_t QUADS = BUCKET_CTA / 4;
     __shared__ uint32_t s_cnt[QUADS], s_perm[QUADS];
     const uint32_t quad = threadIdx.x >> 2, k0 = blockIdx.x * QUADS;
     const int role = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
     {
         const uint32_t kk = k0 + quad;
-        const uint32_t cc = kk < n_keys ? starts[kk + 1] - starts[kk] : 0u;
+        uint32_t cc = kk < n_keys ? (counts ? counts[kk] : starts[kk + 1] - starts[kk]) : 0u;
+        if (heavy_min && cc > heavy_min) cc = 0u;
         if (role == 0) s_cnt[quad] = cc;
         __syncthreads();
         uint32_t rank = 0;
@@ -282,8 +401,9 @@ __global__ void __launch_bounds__(BUCKET_CTA) k_msm_bucket(uint32_t n_keys, cons
     }
     const uint32_t k = k0 + s_perm[quad];
     const bool valid = k < n_keys;
-    const uint32_t lo = valid ? starts[k] : 0u, hi = valid ? starts[k + 1] : 0u;
-    const uint32_t cnt = hi - lo;
+    const uint32_t lo = valid ? starts[k] : 0u;
+    uint32_t cnt = valid ? (counts ? counts[k] : starts[k + 1] - lo) : 0u;
+    if (heavy_min && cnt > heavy_min) cnt = 0u;          // left to k_msm_heavy_*
     const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
     fe c = quad_identity(role);
     for (uint32_t j = 0; j < maxcnt; j++) {
@@ -345,15 +465,17 @@ static __device__ __forceinline__ void bucket_add_entry(fe &X, fe &Y, fe &Z, fe 
 // Throughput variant: one THREAD per bucket (7 sequential multiplications per mixed addition, no shuffles or role selects:
 // about half the instructions of the quad kernel per addition).  The 256 buckets of a CTA are counting-sorted by size so that
 // the 32 buckets of a warp have neighbouring sizes.  Used when there are enough buckets to fill the machine with whole threads.
-__global__ void __launch_bounds__(256) k_msm_bucket_thread(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ sorted,
                                                           const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
                                                           const aniels *__restrict__ gens, const cached *__restrict__ dync,
-                                                          cached *__restrict__ buckets) {
+                                                          cached *__restrict__ buckets, uint32_t heavy_min) {
     __shared__ uint32_t s_hist[256], s_perm[256];
     const uint32_t tid = threadIdx.x, k0 = blockIdx.x * 256u;
     {
         const uint32_t kk = k0 + tid;
-        const uint32_t cc = kk < n_keys ? starts[kk + 1] - starts[kk] : 0u;
+        uint32_t cc = kk < n_keys ? (counts ? counts[kk] : starts[kk + 1] - starts[kk]) : 0u;
+        if (heavy_min && cc > heavy_min) cc = 0u;
         const uint32_t bin = 255u - (cc < 255u ? cc : 255u);          // descending sizes
         s_hist[tid] = 0;
         __syncthreads();
@@ -376,7 +498,9 @@ __global__ void __launch_bounds__(256) k_msm_bucket_thread(uint32_t n_keys, cons
     }
     const uint32_t k = k0 + s_perm[tid];
     if (k >= n_keys) return;
-    const uint32_t lo = starts[k], cnt = starts[k + 1] - lo;
+    const uint32_t lo = starts[k];
+    uint32_t cnt = counts ? counts[k] : starts[k + 1] - lo;
+    if (heavy_min && cnt > heavy_min) cnt = 0u;          // left to k_msm_heavy_*
     fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
     for (uint32_t j = 0; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
     cached *out = buckets + k;
@@ -490,14 +614,16 @@ static __device__ __forceinline__ gex gex_shfl_down(const gex &v, int delta, int
 // 30-250 entries) this keeps the whole-thread instruction count -- about half of the quad kernel's per addition -- at the quad
 // kernel's parallelism.
 template <int LANES>
-__global__ void __launch_bounds__(256) k_msm_bucket_split(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(256) k_msm_bucket_split(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ sorted,
                                                          const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
                                                          const aniels *__restrict__ gens, const cached *__restrict__ dync,
-                                                         cached *__restrict__ buckets) {
+                                                         cached *__restrict__ buckets, uint32_t heavy_min) {
     const uint32_t k = (blockIdx.x * 256u + threadIdx.x) / LANES;
     const uint32_t r = threadIdx.x & (LANES - 1);
     const bool valid = k < n_keys;
-    const uint32_t lo = valid ? starts[k] : 0u, cnt = valid ? starts[k + 1] - lo : 0u;
+    const uint32_t lo = valid ? starts[k] : 0u;
+    uint32_t cnt = valid ? (counts ? counts[k] : starts[k + 1] - lo) : 0u;
+    if (heavy_min && cnt > heavy_min) cnt = 0u;          // left to k_msm_heavy_*
     gex p = gex_identity();
     for (uint32_t j = r; j < cnt; j += LANES) bucket_add_entry(p.X, p.Y, p.Z, p.T, sorted[lo + j], pidx, dyn, gens, dync);
     // groups are LANES-aligned inside the warp: lane r < d of a group receives the sum of lane r + d of the same group; what the
@@ -514,6 +640,80 @@ __global__ void __launch_bounds__(256) k_msm_bucket_split(uint32_t n_keys, const
         st_fe(&out->ypx, fe_add_l(p.Y, p.X));
         st_fe(&out->z2, fe_add_l(p.Z, p.Z));
         st_fe(&out->t2d, fe_mul(p.T, fe_const_2d()));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 4b: over-full buckets
+// A bucket far above the average would be walked by one thread (one quad) of the kernels above while the machine waits: the top
+// window of a width that does not divide 252 (c = 16 at 2^24 points: 2^11 buckets of 8192 entries next to 2^15 buckets of 512), or
+// degenerate scalar sets (the prover's {0, 1, l - 1}: two thirds of all entries in ONE bucket).  Buckets with more than HEAVY_MIN
+// entries are therefore cut into parts of HEAVY_PART entries; a CTA sums one part (8 entries per thread + a tree), a warp adds the
+// parts of a bucket.  This is what lets the window choice ignore how full the top window is.
+__global__ void __launch_bounds__(256) k_msm_heavy_find(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
+                                                       uint32_t *__restrict__ heavy_n, uint2 *__restrict__ items, uint32_t cap) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    const uint32_t cnt = counts ? counts[k] : starts[k + 1] - starts[k];
+    if (cnt <= HEAVY_MIN) return;
+    const uint32_t np = (cnt + HEAVY_PART - 1u) / HEAVY_PART;
+    const uint32_t base = atomicAdd(heavy_n, np);
+    for (uint32_t q = 0; q < np; q++) if (base + q < cap) items[base + q] = make_uint2(k, q);
+}
+__global__ void __launch_bounds__(256) k_msm_heavy_sum(const uint32_t *__restrict__ heavy_n, const uint2 *__restrict__ items, uint32_t cap,
+                                                      const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
+                                                      const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
+                                                      const aniels *__restrict__ gens, const cached *__restrict__ dync, ge *__restrict__ parts) {
+    __shared__ fe s_pt[8][4];
+    const uint32_t n_items = min(*heavy_n, cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const uint2 item = items[it];
+        const uint32_t total = counts ? counts[item.x] : starts[item.x + 1] - starts[item.x];
+        const uint32_t lo = starts[item.x] + item.y * HEAVY_PART;
+        const uint32_t cnt = min(HEAVY_PART, total - item.y * HEAVY_PART);
+        gex p = gex_identity();
+        for (uint32_t j = threadIdx.x; j < cnt; j += 256) bucket_add_entry(p.X, p.Y, p.Z, p.T, sorted[lo + j], pidx, dyn, gens, dync);
+        for (int d = 16; d > 0; d >>= 1) { const gex o = gex_shfl_down(p, d, lane); gex_add(p, o); }
+        __syncthreads();                                 // s_pt of the previous item has been read
+        if (lane == 0) { s_pt[warp][0] = p.X; s_pt[warp][1] = p.Y; s_pt[warp][2] = p.Z; s_pt[warp][3] = p.T; }
+        __syncthreads();
+        if (warp == 0) {
+            gex q;
+            const int src = lane < 8 ? lane : 0;
+            q.X = s_pt[src][0]; q.Y = s_pt[src][1]; q.Z = s_pt[src][2]; q.T = s_pt[src][3];
+            if (lane >= 8) q = gex_identity();
+            for (int d = 4; d > 0; d >>= 1) { const gex o = gex_shfl_down(q, d, lane); gex_add(q, o); }
+            if (lane == 0) { ge *w = parts + it; st_fe(&w->X, q.X); st_fe(&w->Y, q.Y); st_fe(&w->Z, q.Z); st_fe(&w->T, q.T); }
+        }
+    }
+}
+// one warp per over-full bucket (the item with part 0 stands for it): sum of its parts -> the bucket, in cached form
+__global__ void __launch_bounds__(128) k_msm_heavy_finish(const uint32_t *__restrict__ heavy_n, const uint2 *__restrict__ items, uint32_t cap,
+                                                         const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
+                                                         const ge *__restrict__ parts, cached *__restrict__ buckets) {
+    const uint32_t n_items = min(*heavy_n, cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t it = gw; it < n_items; it += nw) {
+        const uint2 item = items[it];
+        if (item.y != 0) continue;                       // warp-uniform
+        const uint32_t total = counts ? counts[item.x] : starts[item.x + 1] - starts[item.x];
+        const uint32_t np = (total + HEAVY_PART - 1u) / HEAVY_PART;
+        gex p = gex_identity();
+        for (uint32_t q = (uint32_t)lane; q < np && it + q < n_items; q += 32) {
+            const ge *src = parts + it + q;
+            gex o;
+            o.X = ld_fe(&src->X); o.Y = ld_fe(&src->Y); o.Z = ld_fe(&src->Z); o.T = ld_fe(&src->T);
+            gex_add(p, o);
+        }
+        for (int d = 16; d > 0; d >>= 1) { const gex o = gex_shfl_down(p, d, lane); gex_add(p, o); }
+        if (lane == 0) {
+            cached *out = buckets + item.x;
+            st_fe(&out->ymx, fe_sub_l(p.Y, p.X));
+            st_fe(&out->ypx, fe_add_l(p.Y, p.X));
+            st_fe(&out->z2, fe_add_l(p.Z, p.Z));
+            st_fe(&out->t2d, fe_mul(p.T, fe_const_2d()));
+        }
     }
 }
 
@@ -587,15 +787,25 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     size_t n_keys = (size_t)sh.n_seg * sh.W * sh.B;
     uint32_t n_tiles = (uint32_t)((n_keys + SCAN_TILE - 1) / SCAN_TILE);
     uint32_t eg = (sh.n_entries + 255u) / 256u;
-    cudaMemsetAsync(sc.starts, 0, (n_keys + 1) * 4, s);
-    if (sh.n_entries) {
-        k_msm_digits<false><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.starts, nullptr);
-    }
-    k_scan_tile_sums<<<n_tiles, 256, 0, s>>>(sc.starts, n_keys, sc.tile_sums);
-    k_scan_tiles<<<1, 32, 0, s>>>(sc.tile_sums, n_tiles);
-    k_scan_apply<<<n_tiles, 256, 0, s>>>(sc.starts, sc.cursor, n_keys, sc.tile_sums);
-    if (sh.n_entries) {
-        k_msm_digits<true><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.cursor, sc.sorted);
+    // shared-memory sort for many small segments (the verifier), scan-based counting sort otherwise
+    const uint32_t *counts = nullptr;
+    const bool fused_sort = !knobs().scan_sort && sh.max_seg_entries != 0 && sh.max_seg_entries <= 16384u && sh.B <= 1024u && sh.n_seg * (uint32_t)sh.W >= 32u;
+    if (fused_sort) {
+        k_msm_sort_seg<1024><<<sh.n_seg * (uint32_t)sh.W, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.starts, sc.cursor, sc.sorted);
+        counts = sc.cursor;
+        if (launches) *launches += 1;
+    } else {
+        cudaMemsetAsync(sc.starts, 0, (n_keys + 1) * 4, s);
+        if (sh.n_entries) {
+            k_msm_digits<false><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.starts, nullptr);
+        }
+        k_scan_tile_sums<<<n_tiles, 256, 0, s>>>(sc.starts, n_keys, sc.tile_sums);
+        k_scan_tiles<<<1, 32, 0, s>>>(sc.tile_sums, n_tiles);
+        k_scan_apply<<<n_tiles, 256, 0, s>>>(sc.starts, sc.cursor, n_keys, sc.tile_sums);
+        if (sh.n_entries) {
+            k_msm_digits<true><<<eg, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.cursor, sc.sorted);
+        }
+        if (launches) *launches += 3 + (sh.n_entries ? 2 : 0);
     }
     if (marks) cudaEventRecord(marks[0], s);
     // whole threads per bucket once there are enough buckets to occupy the SMs that way: always from ~4 warps per SM
@@ -618,15 +828,28 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         split = want >= 5.66 ? 8 : want >= 2.83 ? 4 : want >= 1.42 ? 2 : 1;
         while (split > 1 && adds < 4 * (size_t)split * n_keys) split >>= 1;
     }
+    // over-full buckets (section 4b): for large single sums only -- small segments cannot hold one
+    const uint32_t heavy_min = (!fused_sort && !knobs().no_heavy && sh.n_entries >= (1u << 14)) ? HEAVY_MIN : 0u;
+    if (heavy_min) {
+        cudaMemsetAsync(sc.heavy_n, 0, 4, s);
+        k_msm_heavy_find<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.heavy_n, sc.heavy_items, sc.heavy_cap);
+    }
     if (split == 2 || split == 4 || split == 8) {
         const uint32_t grid = (uint32_t)((n_keys * (size_t)split + 255) / 256);
-        if (split == 2) k_msm_bucket_split<2><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
-        else if (split == 4) k_msm_bucket_split<4><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
-        else k_msm_bucket_split<8><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+        if (split == 2) k_msm_bucket_split<2><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+        else if (split == 4) k_msm_bucket_split<4><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+        else k_msm_bucket_split<8><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
     } else if (thread_buckets)
-        k_msm_bucket_thread<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+        // 86 registers per thread leave room for two 256-thread CTAs per SM; capped at 85 a third one fits (experiment: BPP_TUNE_OCC=1)
+        if (knobs().tune_occ) k_msm_bucket_thread<3><<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+        else k_msm_bucket_thread<1><<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
     else
-        k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, sc.sorted, pidx, dyn, gens, dync, sc.buckets);
+        k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+    if (heavy_min) {
+        k_msm_heavy_sum<<<148 * 4, 256, 0, s>>>(sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.heavy_parts);
+        k_msm_heavy_finish<<<148, 128, 0, s>>>(sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.starts, counts, sc.heavy_parts, sc.buckets);
+        if (launches) *launches += 3;
+    }
     if (marks) cudaEventRecord(marks[1], s);
     const int force_reduce = knobs().reduce;      // 1 = CTA of quads, 2 = warp of threads (tests)
     if (sh.B <= 64 && sh.n_seg * sh.W >= 64) {
@@ -657,7 +880,7 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     if (marks) cudaEventRecord(marks[2], s);
     k_msm_combine<<<(sh.n_seg + 7) / 8, 32, 0, s>>>(sh.n_seg, sh.c, sh.W, sc.windows, result);
     if (marks) cudaEventRecord(marks[3], s);
-    if (launches) *launches += 6 + (sh.n_entries ? 2 : 0);
+    if (launches) *launches += 3;      // bucket sums, window reduction, Horner (the sort phase counted above)
 }
 
 } // namespace bpp

@@ -3,6 +3,7 @@
 // Replaces CompressedRistretto::decompress / RistrettoPoint::compress / from_uniform_bytes as called from
 // /root/reference/src/range_proof.rs:859-866,1067-1109 and :289,:348,:499-504,:587,:598-605,
 // /root/reference/src/range_statement.rs:62-65, /root/reference/src/ristretto.rs:48-52.
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "rawld.cuh"
 
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(128) k_decompress(size_t n, const uint32_t *__
 
 // K-DECOMPRESS over the points of a verification pass, read from the uploaded proof bytes / commitments (no host-side gather):
 // thread i finds its proof by binary search over the per-proof point offsets, then its slot's 32 bytes inside the serialised proof
-__global__ void __launch_bounds__(128) k_decompress_proofs(uint32_t n_pts, uint32_t n_proofs, uint32_t ext, const VProof *__restrict__ proofs,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) k_decompress_proofs(uint32_t n_pts, uint32_t n_proofs, uint32_t ext, const VProof *__restrict__ proofs,
                                                           const uint32_t *__restrict__ pt_offsets, const uint8_t *__restrict__ blob,
                                                           const uint8_t *__restrict__ commitments32, aniels *__restrict__ out_tab,
                                                           uint8_t *__restrict__ ok) {
@@ -113,7 +115,9 @@ void launch_decompress(cudaStream_t s, size_t n, const uint32_t *in, aniels *out
 void launch_decompress_proofs(cudaStream_t s, uint32_t n_pts, uint32_t n_proofs, uint32_t ext, const VProof *proofs, const uint32_t *pt_offsets,
                               const uint8_t *blob, const uint8_t *commitments32, aniels *out_tab, uint8_t *ok) {
     if (n_pts == 0) return;
-    k_decompress_proofs<<<grid_for(n_pts, 128), 128, 0, s>>>(n_pts, n_proofs, ext, proofs, pt_offsets, blob, commitments32, out_tab, ok);
+    static const bool tune = getenv("BPP_TUNE_OCC") != nullptr && atoi(getenv("BPP_TUNE_OCC")) != 0;     // experiment: 5 CTAs per SM (<= 102 registers)
+    if (tune) k_decompress_proofs<5><<<grid_for(n_pts, 128), 128, 0, s>>>(n_pts, n_proofs, ext, proofs, pt_offsets, blob, commitments32, out_tab, ok);
+    else k_decompress_proofs<1><<<grid_for(n_pts, 128), 128, 0, s>>>(n_pts, n_proofs, ext, proofs, pt_offsets, blob, commitments32, out_tab, ok);
 }
 void launch_encode(cudaStream_t s, size_t n, const ge *in, uint32_t *out_enc, uint8_t *is_identity) {
     if (n == 0) return;

@@ -28,6 +28,7 @@ struct MsmShape {
     int c;                // window bits
     int W;                // windows = ceil(252 / c)
     uint32_t B;           // buckets per window = 2^(c-1)
+    uint32_t max_seg_entries;   // largest segment, when the caller knows it (0 = unknown): small segments sort in shared memory
 };
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c);
 // bytes of scratch needed for a shape

@@ -43,6 +43,7 @@ void hc_sc_reduce256(const uint8_t *a, uint8_t *o) { sc_tobytes(o, sc_reduce256(
 void hc_sc_from_wide(const uint8_t *a, uint8_t *o) { uint32_t w[16]; memcpy(w, a, 64); sc_tobytes(o, sc_from_wide_words(w)); }
 void hc_sc_invert(const uint8_t *a, uint8_t *o) { sc_tobytes(o, sc_from_mont(scm_invert(sc_to_mont(sc_frombytes_raw(a))))); }
 void hc_sc_invert_gcd(const uint8_t *a, uint8_t *o) { sc_tobytes(o, sc_invert_gcd(sc_frombytes_raw(a))); }
+void hc_sc_invert_sg(const uint8_t *a, uint8_t *o) { sc_tobytes(o, sc_invert_sg(sc_frombytes_raw(a))); }
 void hc_scm_invert_gcd(const uint8_t *a, uint8_t *o) { sc_tobytes(o, sc_from_mont(scm_invert_gcd(sc_to_mont(sc_frombytes_raw(a))))); }
 int hc_sc_is_canonical(const uint8_t *a) { uint32_t w[8]; memcpy(w, a, 32); return sc_is_canonical_words(w); }
 int hc_decode_encode(const uint8_t *in, uint8_t *o) {

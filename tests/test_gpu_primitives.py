@@ -149,6 +149,40 @@ def test_msm_scalar_distributions_and_duplicates():
     assert e.msm((1).to_bytes(32, "little") + (L - 1).to_bytes(32, "little"), b"".join(two)) == bytes(32)
 
 
+def _sum_points(pts):
+    """sum of many points on the HOST (bpp_points_sum_host, 64 at a time): an addition path that shares nothing with the MSM kernels"""
+    while len(pts) > 1:
+        pts = [bpp.pkg.points_sum_host(b"".join(pts[i:i + 64])) for i in range(0, len(pts), 64)]
+    return pts[0]
+
+
+@pytest.mark.parametrize("n", [20000, 70000])
+def test_msm_overfull_buckets(n):
+    """scalar sets that put most entries into ONE bucket (the prover's {0, 1, l - 1}): those buckets are cut into
+    parts summed by whole CTAs (k_msm_heavy_*); the result must equal host-side sums of the same points"""
+    e = bpp.engine()
+    rnd = random.Random(n)
+    base = _points(512, 4)
+    pts = [base[rnd.randrange(512)] for _ in range(n)]
+    kinds = [rnd.choice("1111mm0r") for _ in range(n)]
+    rand_sc = {i: rnd.randrange(L) for i, k in enumerate(kinds) if k == "r"}
+    scs = [(1 if k == "1" else L - 1 if k == "m" else 0 if k == "0" else rand_sc[i]).to_bytes(32, "little") for i, k in enumerate(kinds)]
+    got = e.msm(b"".join(scs), b"".join(pts))
+    plus = _sum_points([p for p, k in zip(pts, kinds) if k == "1"])
+    minus = _sum_points([p for p, k in zip(pts, kinds) if k == "m"])
+    ridx = sorted(rand_sc)[:1500]                         # the random part in slices the general path handles without over-full buckets
+    parts = [plus, minus]
+    coef = [(1).to_bytes(32, "little"), (L - 1).to_bytes(32, "little")]
+    ridx = sorted(rand_sc)
+    for lo in range(0, len(ridx), 1500):
+        sl = ridx[lo:lo + 1500]
+        parts.append(e.msm(b"".join(scs[i] for i in sl), b"".join(pts[i] for i in sl)))
+        coef.append((1).to_bytes(32, "little"))
+    assert got == e.msm(b"".join(coef), b"".join(parts))
+    # every scalar 1: the plain sum
+    assert e.msm((1).to_bytes(32, "little") * n, b"".join(pts)) == _sum_points(pts)
+
+
 def test_msm_rejects_bad_inputs():
     e = bpp.engine()
     pts = _points(3, 5)

@@ -127,6 +127,11 @@ def test_scalar_ops(hc):
         hc.hc_sc_invert_gcd(b32(a), o); assert i32(o) == pow(a, -1, L), a
         hc.hc_scm_invert_gcd(b32(a), o); assert i32(o) == pow(a, -1, L), a
     hc.hc_sc_invert_gcd(b32(0), o); assert i32(o) == 0
+    # safegcd (30-bit division-step batches): what the verifier's scalar prep inverts with
+    for a in [1, 2, 3, L - 1, L - 2, 2**252, 2**252 - 1, (L + 1) // 2, (L - 1) // 2, 2**30 - 1, 2**30, 2**60 + 1] + [rnd.randrange(1, L) for _ in range(3000)] + \
+            [2**k for k in range(0, 252)] + [L - 2**k for k in range(0, 252, 5)] + [rnd.randrange(1, 2**rnd.randrange(1, 252)) for _ in range(500)]:
+        hc.hc_sc_invert_sg(b32(a), o); assert i32(o) == pow(a, -1, L), a
+    hc.hc_sc_invert_sg(b32(0), o); assert i32(o) == 0
     assert hc.hc_sc_is_canonical(b32(L - 1)) == 1 and hc.hc_sc_is_canonical(b32(L)) == 0
     assert hc.hc_sc_is_canonical(b32(2**256 - 1)) == 0 and hc.hc_sc_is_canonical(b32(0)) == 1
 

@@ -56,7 +56,7 @@ static __device__ __forceinline__ uint32_t seg_of(const uint32_t *seg_offsets, u
 // the switches below select kernel variants (tests / experiments); getenv is neither cheap nor safe against a concurrent setenv, so
 // they are read once
 namespace {
-struct MsmKnobs { int bucket, split, reduce, reduce_parts, scan_sort, no_heavy, tune_occ; };
+struct MsmKnobs { int bucket, split, reduce, reduce_parts, scan_sort, no_heavy; };
 const MsmKnobs &knobs() {
     static const MsmKnobs k = [] {
         auto geti = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
@@ -65,7 +65,6 @@ const MsmKnobs &knobs() {
         r.split = geti("BPP_MSM_SPLIT", 4);
         r.reduce = geti("BPP_MSM_REDUCE", 0);                 // 1 = CTA of quads, 2 = warp of threads
         r.reduce_parts = geti("BPP_MSM_REDUCE_PARTS", 0);
-        r.tune_occ = geti("BPP_TUNE_OCC", 0);
         r.no_heavy = geti("BPP_MSM_NO_HEAVY", 0);               // 1 = over-full buckets stay with the ordinary bucket kernels (comparison)
         r.scan_sort = geti("BPP_MSM_SCAN_SORT", 0);             // 1 = always the scan-based counting sort (tests: both sorts give the same sums)
         return r;
@@ -73,7 +72,7 @@ const MsmKnobs &knobs() {
     return k;
 }
 }
-void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts | (k.scan_sort << 8) | (k.no_heavy << 9) | (k.tune_occ << 10); }
+void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts | (k.scan_sort << 8) | (k.no_heavy << 9); }
 
 // ------------------------------------------------------------------------------------------------ shape
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
@@ -97,10 +96,10 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
         for (int cc = 2; cc <= 16; cc++) {
             int W = (252 + cc - 1) / cc;
             int top_bits = 251 - cc * (W - 1);
-            // a top window that is far from full means few, over-full buckets: fine for one large sum (section 4b splits them), still
-            // avoided for segments, whose buckets are walked by single threads / quads
-            const bool splits_heavy = sh.n_seg == 1 && per >= 16384 && !knobs().no_heavy;
-            if (per >= 1024 && top_bits < cc - 3 && !splits_heavy) continue;
+            // (over-full buckets are split since round 2 -- section 4b -- so a sparse top window no longer serialises; measured, the
+            // wider windows it would allow still lose: c = 16 at 2^24 points 567 vs 575 M points/s for c = 14, c = 15 at 2^20 382 vs 474:
+            // fewer additions, but shorter buckets per thread, a slower scatter over 4x the keys and a longer window reduction)
+            if (per >= 1024 && top_bits < cc - 3) continue;
             double B = (double)(1u << (cc - 1));
             double cost;
             if (per >= 16384 && sh.n_seg == 1) {
@@ -131,9 +130,13 @@ MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #define SCAN_TILE 4096u
 #define REDUCE_PARTS_MAX 8u
-// buckets with more than HEAVY_MIN entries are cut into parts of HEAVY_PART entries that whole CTAs sum (section 4b)
-#define HEAVY_PART 2048u
-#define HEAVY_MIN 4096u
+// over-full buckets (section 4b): a bucket with more than 2 * part entries is cut into parts of `part` entries, part = max(64, twice
+// the average bucket size of the sum)
+static inline uint32_t heavy_part_size(const MsmShape &sh) {
+    const size_t n_keys = (size_t)sh.n_seg * sh.W * sh.B;
+    const size_t avg = n_keys ? ((size_t)sh.n_entries * sh.W) / n_keys : 0;
+    return (uint32_t)(avg * 2 > 64 ? avg * 2 : 64);
+}
 
 struct MsmScratch {
     uint32_t *starts;   // n_keys + 1
@@ -162,7 +165,8 @@ static MsmScratch msm_carve(const MsmShape &sh, void *base) {
     s.buckets = (cached *)(p + off); off = align_up(off + n_keys * sizeof(cached), 256);
     s.windows = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * sizeof(ge), 256);
     s.wparts = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * REDUCE_PARTS_MAX * sizeof(ge), 256);
-    s.heavy_cap = (uint32_t)(((size_t)sh.n_entries * sh.W) / HEAVY_PART + 1024);
+    // sum over the over-full buckets of ceil(count / part) <= total / part + (number of them) <= 1.5 * total / part
+    s.heavy_cap = (uint32_t)((3 * ((size_t)sh.n_entries * sh.W)) / (2 * (size_t)heavy_part_size(sh)) + 1024);
     s.heavy_n = (uint32_t *)(p + off); off = align_up(off + 256, 256);
     s.heavy_items = (uint2 *)(p + off); off = align_up(off + (size_t)s.heavy_cap * sizeof(uint2), 256);
     s.heavy_parts = (ge *)(p + off); off = align_up(off + (size_t)s.heavy_cap * sizeof(ge), 256);
@@ -469,9 +473,24 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ sorted,
                                                           const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
                                                           const aniels *__restrict__ gens, const cached *__restrict__ dync,
-                                                          cached *__restrict__ buckets, uint32_t heavy_min) {
+                                                          cached *__restrict__ buckets, uint32_t heavy_min, uint32_t part_size,
+                                                          const uint32_t *__restrict__ heavy_n, const uint2 *__restrict__ items, uint32_t cap,
+                                                          ge *__restrict__ parts) {
     __shared__ uint32_t s_hist[256], s_perm[256];
     const uint32_t tid = threadIdx.x, k0 = blockIdx.x * 256u;
+    if (k0 >= n_keys) {
+        // CTAs behind the buckets: one thread per PART of an over-full bucket (section 4b); parts are all about part_size long
+        const uint32_t it = (blockIdx.x - (n_keys + 255u) / 256u) * 256u + tid;
+        if (it >= min(*heavy_n, cap)) return;
+        const uint2 item = items[it];
+        const uint32_t total = counts ? counts[item.x] : starts[item.x + 1] - starts[item.x];
+        const uint32_t lo = starts[item.x] + item.y * part_size, cnt = min(part_size, total - item.y * part_size);
+        fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
+        for (uint32_t j = 0; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
+        ge *w = parts + it;
+        st_fe(&w->X, X); st_fe(&w->Y, Y); st_fe(&w->Z, Z); st_fe(&w->T, T);
+        return;
+    }
     {
         const uint32_t kk = k0 + tid;
         uint32_t cc = kk < n_keys ? (counts ? counts[kk] : starts[kk + 1] - starts[kk]) : 0u;
@@ -500,7 +519,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_
     if (k >= n_keys) return;
     const uint32_t lo = starts[k];
     uint32_t cnt = counts ? counts[k] : starts[k + 1] - lo;
-    if (heavy_min && cnt > heavy_min) cnt = 0u;          // left to k_msm_heavy_*
+    if (heavy_min && cnt > heavy_min) cnt = 0u;          // left to the part threads above and k_msm_heavy_finish
     fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
     for (uint32_t j = 0; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
     cached *out = buckets + k;
@@ -644,52 +663,26 @@ __global__ void __launch_bounds__(256) k_msm_bucket_split(uint32_t n_keys, const
 }
 
 // ------------------------------------------------------------------------------------------------ 4b: over-full buckets
-// A bucket far above the average would be walked by one thread (one quad) of the kernels above while the machine waits: the top
-// window of a width that does not divide 252 (c = 16 at 2^24 points: 2^11 buckets of 8192 entries next to 2^15 buckets of 512), or
-// degenerate scalar sets (the prover's {0, 1, l - 1}: two thirds of all entries in ONE bucket).  Buckets with more than HEAVY_MIN
-// entries are therefore cut into parts of HEAVY_PART entries; a CTA sums one part (8 entries per thread + a tree), a warp adds the
-// parts of a bucket.  This is what lets the window choice ignore how full the top window is.
+// A bucket far above the average would be walked by one thread of k_msm_bucket_thread while the machine waits: the top window of a
+// width that does not divide 252 (c = 16 at 2^24 points: 2^11 buckets of 8192 entries next to 2^15 buckets of 512), or degenerate
+// scalar sets (the prover's {0, 1, l - 1}: two thirds of all entries in ONE bucket).  Buckets with more than 2 * part entries
+// (part = twice the average bucket size) are therefore cut into parts: k_msm_heavy_find lists (bucket, part) items,
+// k_msm_bucket_thread sums one part per thread in extra CTAs behind the buckets (the same walk as a bucket of average size),
+// k_msm_heavy_finish adds the parts of a bucket with one warp.  This is what lets the window choice ignore the top window.
 __global__ void __launch_bounds__(256) k_msm_heavy_find(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
-                                                       uint32_t *__restrict__ heavy_n, uint2 *__restrict__ items, uint32_t cap) {
+                                                       uint32_t heavy_min, uint32_t part_size, uint32_t *__restrict__ heavy_n, uint2 *__restrict__ items,
+                                                       uint32_t cap) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_keys) return;
     const uint32_t cnt = counts ? counts[k] : starts[k + 1] - starts[k];
-    if (cnt <= HEAVY_MIN) return;
-    const uint32_t np = (cnt + HEAVY_PART - 1u) / HEAVY_PART;
+    if (cnt <= heavy_min) return;
+    const uint32_t np = (cnt + part_size - 1u) / part_size;
     const uint32_t base = atomicAdd(heavy_n, np);
     for (uint32_t q = 0; q < np; q++) if (base + q < cap) items[base + q] = make_uint2(k, q);
 }
-__global__ void __launch_bounds__(256) k_msm_heavy_sum(const uint32_t *__restrict__ heavy_n, const uint2 *__restrict__ items, uint32_t cap,
-                                                      const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
-                                                      const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ pidx, const aniels *__restrict__ dyn,
-                                                      const aniels *__restrict__ gens, const cached *__restrict__ dync, ge *__restrict__ parts) {
-    __shared__ fe s_pt[8][4];
-    const uint32_t n_items = min(*heavy_n, cap);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const uint2 item = items[it];
-        const uint32_t total = counts ? counts[item.x] : starts[item.x + 1] - starts[item.x];
-        const uint32_t lo = starts[item.x] + item.y * HEAVY_PART;
-        const uint32_t cnt = min(HEAVY_PART, total - item.y * HEAVY_PART);
-        gex p = gex_identity();
-        for (uint32_t j = threadIdx.x; j < cnt; j += 256) bucket_add_entry(p.X, p.Y, p.Z, p.T, sorted[lo + j], pidx, dyn, gens, dync);
-        for (int d = 16; d > 0; d >>= 1) { const gex o = gex_shfl_down(p, d, lane); gex_add(p, o); }
-        __syncthreads();                                 // s_pt of the previous item has been read
-        if (lane == 0) { s_pt[warp][0] = p.X; s_pt[warp][1] = p.Y; s_pt[warp][2] = p.Z; s_pt[warp][3] = p.T; }
-        __syncthreads();
-        if (warp == 0) {
-            gex q;
-            const int src = lane < 8 ? lane : 0;
-            q.X = s_pt[src][0]; q.Y = s_pt[src][1]; q.Z = s_pt[src][2]; q.T = s_pt[src][3];
-            if (lane >= 8) q = gex_identity();
-            for (int d = 4; d > 0; d >>= 1) { const gex o = gex_shfl_down(q, d, lane); gex_add(q, o); }
-            if (lane == 0) { ge *w = parts + it; st_fe(&w->X, q.X); st_fe(&w->Y, q.Y); st_fe(&w->Z, q.Z); st_fe(&w->T, q.T); }
-        }
-    }
-}
 // one warp per over-full bucket (the item with part 0 stands for it): sum of its parts -> the bucket, in cached form
 __global__ void __launch_bounds__(128) k_msm_heavy_finish(const uint32_t *__restrict__ heavy_n, const uint2 *__restrict__ items, uint32_t cap,
-                                                         const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
+                                                         const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts, uint32_t part_size,
                                                          const ge *__restrict__ parts, cached *__restrict__ buckets) {
     const uint32_t n_items = min(*heavy_n, cap);
     const int lane = threadIdx.x & 31;
@@ -698,7 +691,7 @@ __global__ void __launch_bounds__(128) k_msm_heavy_finish(const uint32_t *__rest
         const uint2 item = items[it];
         if (item.y != 0) continue;                       // warp-uniform
         const uint32_t total = counts ? counts[item.x] : starts[item.x + 1] - starts[item.x];
-        const uint32_t np = (total + HEAVY_PART - 1u) / HEAVY_PART;
+        const uint32_t np = (total + part_size - 1u) / part_size;
         gex p = gex_identity();
         for (uint32_t q = (uint32_t)lane; q < np && it + q < n_items; q += 32) {
             const ge *src = parts + it + q;
@@ -828,27 +821,36 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         split = want >= 5.66 ? 8 : want >= 2.83 ? 4 : want >= 1.42 ? 2 : 1;
         while (split > 1 && adds < 4 * (size_t)split * n_keys) split >>= 1;
     }
-    // over-full buckets (section 4b): for large single sums only -- small segments cannot hold one
-    const uint32_t heavy_min = (!fused_sort && !knobs().no_heavy && sh.n_entries >= (1u << 14)) ? HEAVY_MIN : 0u;
+    // over-full buckets (section 4b): with the thread-per-bucket kernel only (large sums)
+    const uint32_t part_size = heavy_part_size(sh);
+    const uint32_t heavy_min = (thread_buckets && !fused_sort && !knobs().no_heavy && sh.n_entries >= (1u << 14)) ? 2u * part_size : 0u;
     if (heavy_min) {
         cudaMemsetAsync(sc.heavy_n, 0, 4, s);
-        k_msm_heavy_find<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.heavy_n, sc.heavy_items, sc.heavy_cap);
+        k_msm_heavy_find<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, heavy_min, part_size, sc.heavy_n, sc.heavy_items,
+                                                                          sc.heavy_cap);
     }
     if (split == 2 || split == 4 || split == 8) {
         const uint32_t grid = (uint32_t)((n_keys * (size_t)split + 255) / 256);
-        if (split == 2) k_msm_bucket_split<2><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
-        else if (split == 4) k_msm_bucket_split<4><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
-        else k_msm_bucket_split<8><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+        if (split == 2) k_msm_bucket_split<2><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, 0u);
+        else if (split == 4) k_msm_bucket_split<4><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, 0u);
+        else k_msm_bucket_split<8><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, 0u);
     } else if (thread_buckets)
-        // 86 registers per thread leave room for two 256-thread CTAs per SM; capped at 85 a third one fits (experiment: BPP_TUNE_OCC=1)
-        if (knobs().tune_occ) k_msm_bucket_thread<3><<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
-        else k_msm_bucket_thread<1><<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+    {
+        // 96 registers per thread leave room for two 256-thread CTAs per SM; capped at 80 a third one fits: +3 % on passes that fill
+        // the machine (measured), a little slower on small ones
+        const uint32_t grid = (uint32_t)((n_keys + 255) / 256) + (heavy_min ? (sc.heavy_cap + 255u) / 256u : 0u);
+        if (n_keys >= 200000)
+            k_msm_bucket_thread<3><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min, part_size,
+                                                        sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts);
+        else
+            k_msm_bucket_thread<1><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min, part_size,
+                                                        sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts);
+    }
     else
-        k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min);
+        k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, 0u);
     if (heavy_min) {
-        k_msm_heavy_sum<<<148 * 4, 256, 0, s>>>(sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.heavy_parts);
-        k_msm_heavy_finish<<<148, 128, 0, s>>>(sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.starts, counts, sc.heavy_parts, sc.buckets);
-        if (launches) *launches += 3;
+        k_msm_heavy_finish<<<148, 128, 0, s>>>(sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.starts, counts, part_size, sc.heavy_parts, sc.buckets);
+        if (launches) *launches += 2;
     }
     if (marks) cudaEventRecord(marks[1], s);
     const int force_reduce = knobs().reduce;      // 1 = CTA of quads, 2 = warp of threads (tests)

@@ -57,6 +57,8 @@ struct HCall {
     const bpp_verify_challenges *ch = nullptr;
     size_t proof0 = 0, chunk0 = 0, commit0 = 0, raw0 = 0;      // first proof / chunk / commitment / raw byte of this call in the pass
     size_t raw_base = 0;              // a.proof_offsets[0]
+    bool same_transcripts = false;    // every transcript of the call holds the same state (one label for all proofs: the usual case)
+    size_t ts0 = 0;                   // first uploaded transcript state of this call
 };
 
 inline bool is_zero32(const uint8_t *p) { return replay_is_zero32(p); }
@@ -510,6 +512,19 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
         if (p.rounds >= 64) p.loop2_rc = BPP_SIZE_OVERFLOW;
         else if (p.rounds >= 32 || (1ull << p.rounds) != (uint64_t)p.m * (uint64_t)n) p.loop2_rc = BPP_INVALID_LENGTH;
     });
+    // ---- transcripts of a call that are all in the same state (same label, nothing appended yet) travel once: 203 of the ~940 bytes a
+    // proof costs on the host-to-device link
+    size_t n_tstates = 0;
+    if (vb->device_replay) {
+        ctx->workers().run(n_calls, 1, [&](size_t ci) {
+            HCall &call = vb->calls[ci];
+            const uint8_t *t = call.a.transcripts;
+            bool same = call.a.n_proofs > 1;
+            for (size_t i = 1; i < call.a.n_proofs && same; i++) same = memcmp(t, t + BPP_TRANSCRIPT_BYTES * i, BPP_TRANSCRIPT_BYTES) == 0;
+            call.same_transcripts = same;
+        });
+        for (HCall &call : vb->calls) { call.ts0 = n_tstates; n_tstates += call.same_transcripts ? 1 : call.a.n_proofs; }
+    }
     // ---- per-chunk consistency (:610-709) and the totals of the device layout
     uint64_t n_pts = 0, n_entries = 0, contrib = 0, pv = 0, n_chal = 0, n_nonce = 0;
     uint32_t max_static = 0, max_seg_entries = 0;
@@ -570,7 +585,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     vb->o_minp = carve(vb->n_commit);
     vb->o_commit = carve(32 * vb->n_commit);
     vb->o_raw = carve((size_t)tot_raw);
-    vb->o_tstate = carve(vb->device_replay ? BPP_TRANSCRIPT_BYTES * NP : 0);
+    vb->o_tstate = carve(BPP_TRANSCRIPT_BYTES * n_tstates);
     vb->o_nonces = carve(32 * (size_t)n_nonce);
     vb->blob_bytes = off;
     if (vb->blob_bytes >= (1ull << 32)) { delete vb; return fail(ctx, BPP_SIZE_OVERFLOW, "verification pass too large"); }
@@ -659,6 +674,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
                 v.raw_off = (uint32_t)(vb->o_raw + call.raw0 + (a.proof_offsets[p.local] - call.raw_base));
                 v.commit_off = (uint32_t)(call.commit0 + (a.commit_offsets[p.local] - a.commit_offsets[0]));
                 v.ch_off = chal; chal += 3 + R;
+                v.ts_idx = (uint32_t)(call.ts0 + (call.same_transcripts ? 0 : p.local));
                 if (!hc.computable) continue;
                 if (want_masks && p.has_seed) {
                     v.nonce_off = nonces; nonces += (uint32_t)ext * (3 + 2 * R);
@@ -694,7 +710,7 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
         memcpy(hb + vb->o_commit + 32 * call.commit0, a.commitments32 + 32 * c_lo, 32 * c_n);
         memcpy(hb + vb->o_minv + 8 * call.commit0, a.min_values + c_lo, 8 * c_n);
         memcpy(hb + vb->o_minp + call.commit0, a.min_present + c_lo, c_n);
-        if (vb->device_replay) memcpy(hb + vb->o_tstate + BPP_TRANSCRIPT_BYTES * call.proof0, a.transcripts, BPP_TRANSCRIPT_BYTES * a.n_proofs);
+        if (vb->device_replay) memcpy(hb + vb->o_tstate + BPP_TRANSCRIPT_BYTES * call.ts0, a.transcripts, BPP_TRANSCRIPT_BYTES * (call.same_transcripts ? 1 : a.n_proofs));
     });
     memcpy(hb + vb->o_hg, g->h(), 32);
     memcpy(hb + vb->o_hg + 32, g->g(0), 32 * (size_t)ext);

@@ -56,7 +56,7 @@ static __device__ __forceinline__ uint32_t seg_of(const uint32_t *seg_offsets, u
 // the switches below select kernel variants (tests / experiments); getenv is neither cheap nor safe against a concurrent setenv, so
 // they are read once
 namespace {
-struct MsmKnobs { int bucket, split, reduce, reduce_parts, scan_sort, no_heavy; };
+struct MsmKnobs { int bucket, split, reduce, reduce_parts, scan_sort, no_heavy, window_sort, local_rank; };
 const MsmKnobs &knobs() {
     static const MsmKnobs k = [] {
         auto geti = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
@@ -65,6 +65,8 @@ const MsmKnobs &knobs() {
         r.split = geti("BPP_MSM_SPLIT", 4);
         r.reduce = geti("BPP_MSM_REDUCE", 0);                 // 1 = CTA of quads, 2 = warp of threads
         r.reduce_parts = geti("BPP_MSM_REDUCE_PARTS", 0);
+        r.window_sort = geti("BPP_MSM_WINDOW_SORT", 0);         // 1 = shared-memory sort one (segment, window) per CTA (the first form)
+        r.local_rank = geti("BPP_MSM_LOCAL_RANK", 0);           // 1 = buckets ranked by size inside each CTA only (the round-1 form)
         r.no_heavy = geti("BPP_MSM_NO_HEAVY", 0);               // 1 = over-full buckets stay with the ordinary bucket kernels (comparison)
         r.scan_sort = geti("BPP_MSM_SCAN_SORT", 0);             // 1 = always the scan-based counting sort (tests: both sorts give the same sums)
         return r;
@@ -72,7 +74,7 @@ const MsmKnobs &knobs() {
     return k;
 }
 }
-void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts | (k.scan_sort << 8) | (k.no_heavy << 9); }
+void msm_knobs(int32_t out[4]) { const MsmKnobs &k = knobs(); out[0] = k.bucket; out[1] = k.split; out[2] = k.reduce; out[3] = k.reduce_parts | (k.scan_sort << 8) | (k.no_heavy << 9) | (k.window_sort << 10) | (k.local_rank << 11); }
 
 // ------------------------------------------------------------------------------------------------ shape
 MsmShape msm_shape(uint32_t n_entries, uint32_t n_seg, int forced_c) {
@@ -146,6 +148,8 @@ struct MsmScratch {
     cached *buckets;    // n_keys
     ge *windows;        // n_seg * W
     ge *wparts;         // n_seg * W * REDUCE_PARTS_MAX: partial window sums of k_msm_reduce when a window is split over several CTAs
+    uint32_t *perm;     // n_keys: buckets ranked by size (k_msm_size_*)
+    uint32_t *size_bins;// 256
     uint32_t *heavy_n;  // number of work items of the over-full buckets (see "4b")
     uint2 *heavy_items; // (key, part)
     ge *heavy_parts;    // partial sum of every item
@@ -167,6 +171,8 @@ static MsmScratch msm_carve(const MsmShape &sh, void *base) {
     s.wparts = (ge *)(p + off); off = align_up(off + (size_t)sh.n_seg * sh.W * REDUCE_PARTS_MAX * sizeof(ge), 256);
     // sum over the over-full buckets of ceil(count / part) <= total / part + (number of them) <= 1.5 * total / part
     s.heavy_cap = (uint32_t)((3 * ((size_t)sh.n_entries * sh.W)) / (2 * (size_t)heavy_part_size(sh)) + 1024);
+    s.perm = (uint32_t *)(p + off); off = align_up(off + n_keys * 4, 256);
+    s.size_bins = (uint32_t *)(p + off); off = align_up(off + 1024, 256);
     s.heavy_n = (uint32_t *)(p + off); off = align_up(off + 256, 256);
     s.heavy_items = (uint2 *)(p + off); off = align_up(off + (size_t)s.heavy_cap * sizeof(uint2), 256);
     s.heavy_parts = (ge *)(p + off); off = align_up(off + (size_t)s.heavy_cap * sizeof(ge), 256);
@@ -318,6 +324,78 @@ __global__ void __launch_bounds__(256) k_msm_sort_seg(uint32_t n_entries, uint32
     }
 }
 
+// The same for a GROUP of windows per CTA: CTA (segment, g) handles windows [g * G, (g + 1) * G) -- G * B counters in shared memory --
+// and walks the segment's scalars twice (count, scatter), recoding each one sequentially up to its last window, so the redundant
+// recoding of k_msm_sort_seg (once per window and pass: 134 M warp instructions per 16-job pass, 13 % of it, ALU-bound) shrinks by G.
+// G is chosen so that the grid still covers the machine: scattered 4-byte stores are limited per SM (one CTA per segment, G = W, took
+// 120 us however many segments there were; measured).  Regions as in k_msm_sort_seg: (segment, window) owns seg_lo * W + w * len.
+__global__ void __launch_bounds__(512) k_msm_sort_segw(uint32_t n_entries, uint32_t n_seg, int c, int W, int G, uint32_t B, const uint32_t *__restrict__ scalars,
+                                                      const uint32_t *__restrict__ seg_offsets, uint32_t *__restrict__ starts, uint32_t *__restrict__ counts,
+                                                      uint32_t *__restrict__ sorted) {
+    extern __shared__ uint32_t s_cnt[];              // G * B counters, then cursors (relative to the window's region)
+    __shared__ uint32_t s_part[512];
+    const uint32_t seg = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int w0 = (int)blockIdx.y * G, w1 = min(W, w0 + G), nw = w1 - w0;
+    const uint32_t lo = n_seg > 1 ? seg_offsets[seg] : 0u, hi = n_seg > 1 ? seg_offsets[seg + 1] : n_entries;
+    const uint32_t len = hi - lo, nk = (uint32_t)nw * B;
+    const uint32_t key_base = (seg * (uint32_t)W + (uint32_t)w0) * B, region0 = lo * (uint32_t)W + (uint32_t)w0 * len;
+    for (uint32_t k = tid; k < nk; k += nthr) s_cnt[k] = 0;
+    __syncthreads();
+    auto walk = [&](uint32_t i, bool scatter) {
+        uint32_t s[8], t[8];
+        ld8(s, scalars + 8 * (size_t)i);
+        int64_t bw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { bw += (int64_t)sc_l(k) - (int64_t)s[k]; t[k] = (uint32_t)bw; bw >>= 32; }
+        bool gt = false, decided = false;            // s > l - s: use (l - s, -P), |recoded| < 2^251
+#pragma unroll
+        for (int k = 7; k >= 0; k--) if (!decided && s[k] != t[k]) { gt = s[k] > t[k]; decided = true; }
+        if (gt) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = t[k];
+        }
+        uint32_t carry = 0;
+        for (int w = 0; w < w1; w++) {
+            uint32_t d = bits_at(s, w * c, c) + carry;
+            uint32_t neg = gt ? 1u : 0u;
+            if (d > B) { d = 2u * B - d; neg ^= 1u; carry = 1u; } else carry = 0u;
+            if (w >= w0 && d) {
+                const uint32_t pos = atomicAdd(&s_cnt[(uint32_t)(w - w0) * B + d - 1u], 1u);
+                if (scatter) sorted[region0 + (uint32_t)(w - w0) * len + pos] = i | (neg << 31);
+            }
+        }
+    };
+    for (uint32_t i = lo + tid; i < hi; i += nthr) walk(i, false);
+    __syncthreads();
+    // exclusive scan over the nw * B counters (thread t owns a contiguous run), then made relative to each window's first bucket
+    const uint32_t per = (nk + nthr - 1u) / nthr;
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < per; k++) { const uint32_t kk = tid * per + k; if (kk < nk) acc += s_cnt[kk]; }
+    s_part[tid] = acc;
+    __syncthreads();
+    for (uint32_t sft = 1; sft < nthr; sft <<= 1) {
+        const uint32_t v = tid >= sft ? s_part[tid - sft] : 0u;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - acc;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t kk = tid * per + k;
+        if (kk < nk) { const uint32_t cnt = s_cnt[kk]; s_cnt[kk] = run; run += cnt; counts[key_base + kk] = cnt; }
+    }
+    __syncthreads();
+    for (uint32_t w = tid; w < (uint32_t)nw; w += nthr) s_part[w] = s_cnt[w * B];      // scan value at each window's first bucket
+    __syncthreads();
+    for (uint32_t kk = tid; kk < nk; kk += nthr) {
+        const uint32_t w = kk / B, rel = s_cnt[kk] - s_part[w];                          // position inside the window's region
+        starts[key_base + kk] = region0 + w * len + rel;
+        s_cnt[kk] = rel;                                                                 // cursor of the scatter pass
+    }
+    __syncthreads();
+    for (uint32_t i = lo + tid; i < hi; i += nthr) walk(i, true);
+}
+
 // ------------------------------------------------------------------------------------------------ 2: scan
 __global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t *__restrict__ in, size_t n, uint32_t *__restrict__ tile_sums) {
     __shared__ uint32_t sh[256];
@@ -466,6 +544,61 @@ static __device__ __forceinline__ void bucket_add_entry(fe &X, fe &Y, fe &Z, fe 
     X = fe_mul(E, F); Y = fe_mul(G, H); Z = fe_mul(F, G); T = fe_mul(E, H);
 }
 
+// Global size order of the buckets.  k_msm_bucket_thread used to rank the 256 buckets of a CTA among themselves: the lanes of a warp
+// then walk buckets of neighbouring sizes, but the CTA lives as long as its largest bucket while most of its warps have left (the
+// verifier's buckets hold 16.5 +- 4 entries: 8..28 inside every CTA; ncu: 27 % achieved occupancy, FMA pipe active 40 % of the
+// cycles).  Three small kernels rank ALL buckets by size (counting sort on min(count, 255), largest first), so that a CTA's 256
+// buckets are of one size and CTAs start in longest-first order.
+__global__ void __launch_bounds__(256) k_msm_size_hist(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
+                                                      uint32_t heavy_min, uint32_t *__restrict__ bins) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t k = blockIdx.x * 1024u + threadIdx.x; k < min(n_keys, (blockIdx.x + 1u) * 1024u); k += 256u) {
+        uint32_t cc = counts ? counts[k] : starts[k + 1] - starts[k];
+        if (heavy_min && cc > heavy_min) cc = 0u;
+        atomicAdd(&h[255u - min(cc, 255u)], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_msm_size_scan(uint32_t *__restrict__ bins) {       // bins -> exclusive prefix (cursors), one CTA
+    __shared__ uint32_t h[256];
+    const uint32_t v = bins[threadIdx.x];
+    h[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const uint32_t t = (int)threadIdx.x >= d ? h[threadIdx.x - d] : 0u;
+        __syncthreads();
+        h[threadIdx.x] += t;
+        __syncthreads();
+    }
+    bins[threadIdx.x] = h[threadIdx.x] - v;
+}
+__global__ void __launch_bounds__(256) k_msm_size_scatter(uint32_t n_keys, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ counts,
+                                                         uint32_t heavy_min, uint32_t *__restrict__ bins, uint32_t *__restrict__ perm) {
+    __shared__ uint32_t h[256], base[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t mybin[4], mypos[4];
+    int n = 0;
+    for (uint32_t k = blockIdx.x * 1024u + threadIdx.x; k < min(n_keys, (blockIdx.x + 1u) * 1024u); k += 256u) {
+        uint32_t cc = counts ? counts[k] : starts[k + 1] - starts[k];
+        if (heavy_min && cc > heavy_min) cc = 0u;
+        mybin[n] = 255u - min(cc, 255u);
+        mypos[n] = atomicAdd(&h[mybin[n]], 1u);
+        n++;
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) base[threadIdx.x] = atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);      // one global atomic per (CTA, bin)
+    __syncthreads();
+    n = 0;
+    for (uint32_t k = blockIdx.x * 1024u + threadIdx.x; k < min(n_keys, (blockIdx.x + 1u) * 1024u); k += 256u) {
+        perm[base[mybin[n]] + mypos[n]] = k;
+        n++;
+    }
+}
+
 // Throughput variant: one THREAD per bucket (7 sequential multiplications per mixed addition, no shuffles or role selects:
 // about half the instructions of the quad kernel per addition).  The 256 buckets of a CTA are counting-sorted by size so that
 // the 32 buckets of a warp have neighbouring sizes.  Used when there are enough buckets to fill the machine with whole threads.
@@ -475,7 +608,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_
                                                           const aniels *__restrict__ gens, const cached *__restrict__ dync,
                                                           cached *__restrict__ buckets, uint32_t heavy_min, uint32_t part_size,
                                                           const uint32_t *__restrict__ heavy_n, const uint2 *__restrict__ items, uint32_t cap,
-                                                          ge *__restrict__ parts) {
+                                                          ge *__restrict__ parts, const uint32_t *__restrict__ perm) {
     __shared__ uint32_t s_hist[256], s_perm[256];
     const uint32_t tid = threadIdx.x, k0 = blockIdx.x * 256u;
     if (k0 >= n_keys) {
@@ -491,7 +624,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_
         st_fe(&w->X, X); st_fe(&w->Y, Y); st_fe(&w->Z, Z); st_fe(&w->T, T);
         return;
     }
-    {
+    if (perm) {                                        // globally ranked: slot -> bucket
+        s_perm[tid] = k0 + tid < n_keys ? perm[k0 + tid] - k0 : tid;
+    } else {
         const uint32_t kk = k0 + tid;
         uint32_t cc = kk < n_keys ? (counts ? counts[kk] : starts[kk + 1] - starts[kk]) : 0u;
         if (heavy_min && cc > heavy_min) cc = 0u;
@@ -515,7 +650,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_
         s_perm[before + atomicAdd(&s_hist[bin], 1u)] = tid;
         __syncthreads();
     }
-    const uint32_t k = k0 + s_perm[tid];
+    const uint32_t k = k0 + s_perm[tid];               // (with perm: s_perm holds perm[slot] - k0, modulo 2^32)
     if (k >= n_keys) return;
     const uint32_t lo = starts[k];
     uint32_t cnt = counts ? counts[k] : starts[k + 1] - lo;
@@ -783,7 +918,18 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     // shared-memory sort for many small segments (the verifier), scan-based counting sort otherwise
     const uint32_t *counts = nullptr;
     const bool fused_sort = !knobs().scan_sort && sh.max_seg_entries != 0 && sh.max_seg_entries <= 16384u && sh.B <= 1024u && sh.n_seg * (uint32_t)sh.W >= 32u;
-    if (fused_sort) {
+    if (fused_sort && !knobs().window_sort) {
+        // groups of G windows per CTA, as large as leaves ~2 CTAs per SM and fits 40 KB of counters
+        int groups = (int)((2 * 148 + sh.n_seg - 1) / sh.n_seg);
+        if (groups > sh.W) groups = sh.W;
+        int G = (sh.W + groups - 1) / groups;
+        while (G > 1 && (size_t)G * sh.B * 4 > 40 * 1024) G--;
+        groups = (sh.W + G - 1) / G;
+        k_msm_sort_segw<<<dim3(sh.n_seg, (unsigned)groups), 512, (size_t)G * sh.B * 4, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, G, sh.B, scalars, seg_offsets, sc.starts,
+                                                                                           sc.cursor, sc.sorted);
+        counts = sc.cursor;
+        if (launches) *launches += 1;
+    } else if (fused_sort) {
         k_msm_sort_seg<1024><<<sh.n_seg * (uint32_t)sh.W, 256, 0, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, sh.B, scalars, seg_offsets, sc.starts, sc.cursor, sc.sorted);
         counts = sc.cursor;
         if (launches) *launches += 1;
@@ -839,12 +985,23 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
         // 96 registers per thread leave room for two 256-thread CTAs per SM; capped at 80 a third one fits: +3 % on passes that fill
         // the machine (measured), a little slower on small ones
         const uint32_t grid = (uint32_t)((n_keys + 255) / 256) + (heavy_min ? (sc.heavy_cap + 255u) / 256u : 0u);
+        // rank all buckets by size first (see k_msm_size_*) unless they are few or the switch says no
+        const uint32_t *perm = nullptr;
+        if (n_keys >= 4096 && !knobs().local_rank) {
+            const uint32_t g4 = (uint32_t)((n_keys + 1023) / 1024);
+            cudaMemsetAsync(sc.size_bins, 0, 1024, s);
+            k_msm_size_hist<<<g4, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, heavy_min, sc.size_bins);
+            k_msm_size_scan<<<1, 256, 0, s>>>(sc.size_bins);
+            k_msm_size_scatter<<<g4, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, heavy_min, sc.size_bins, sc.perm);
+            perm = sc.perm;
+            if (launches) *launches += 3;
+        }
         if (n_keys >= 200000)
             k_msm_bucket_thread<3><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min, part_size,
-                                                        sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts);
+                                                        sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts, perm);
         else
             k_msm_bucket_thread<1><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min, part_size,
-                                                        sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts);
+                                                        sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts, perm);
     }
     else
         k_msm_bucket<<<(uint32_t)((n_keys + BUCKET_CTA / 4 - 1) / (BUCKET_CTA / 4)), BUCKET_CTA, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, 0u);

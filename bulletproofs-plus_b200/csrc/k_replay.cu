@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32) k_replay_sm(VDims d, RBuffers b) {
     const VProof pr = b.proofs[p];
     if (!pr.replay) { b.flags[p] = 0; return; }
     uint32_t *S = s_state + threadIdx.x;
-    sm_load_state(S, b.tstates_in + BPP_TSTATE_BYTES * (size_t)p);
+    sm_load_state(S, b.tstates_in + BPP_TSTATE_BYTES * (size_t)pr.ts_idx);
     const uint32_t ext = d.ext, R = pr.rounds;
     const uint8_t *raw = b.blob + pr.raw_off;
     uint8_t *ch = b.challenges + 32 * (size_t)pr.ch_off;
@@ -366,7 +366,7 @@ template <bool WARP> __global__ void __launch_bounds__(WARP ? 32 * REPLAY_WARPS 
     if (!pr.replay) { b.flags[p] = 0; return; }
     const uint8_t *raw = b.blob + pr.raw_off;
     ReplayIn in;
-    in.tstate = b.tstates_in + BPP_TSTATE_BYTES * (size_t)p;
+    in.tstate = b.tstates_in + BPP_TSTATE_BYTES * (size_t)pr.ts_idx;
     in.h32 = b.hg32; in.g32 = b.hg32 + 32;
     in.bit_length = d.bit_length; in.ext = d.ext; in.m = pr.m; in.rounds = pr.rounds;
     in.commitments32 = b.commitments32 + 32 * (size_t)pr.commit_off;

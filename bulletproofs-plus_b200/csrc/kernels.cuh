@@ -73,6 +73,7 @@ struct VProof {            // per-proof metadata, device-resident
     uint32_t active;       // 1 = contributes to its chunk's MSM
     uint32_t pt_off;       // first slot in the point table / encoding array: [A, A1, B, L_0.., R_0.., V_0..]
     uint32_t replay;       // 1 = its transcript is replayed (loop 1) and its scalars are prepared
+    uint32_t ts_idx;       // which uploaded transcript state it starts from (calls whose transcripts are all equal upload ONE)
 };
 struct VChunk {
     uint32_t proof_lo, proof_hi;
@@ -114,7 +115,7 @@ void launch_verify_weigh(cudaStream_t s, const VDims &d, const VBuffers &b, uint
 // ---------------------------------------------------------------- k_replay.cu
 struct RBuffers {
     const VProof *proofs;
-    const uint8_t *tstates_in;       // n_proofs x 203
+    const uint8_t *tstates_in;       // 203-byte initial states, indexed by VProof::ts_idx
     const uint8_t *hg32;             // compressed H, then G[0..ext)
     const uint8_t *blob;             // uploaded bytes: serialised proofs at VProof::raw_off
     const uint8_t *commitments32;    // 32 x (VProof::commit_off + j)

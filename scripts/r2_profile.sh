@@ -1,11 +1,13 @@
 #!/bin/bash
 # ncu captures of the bench command (one gpurun call: all ncu runs of a call count as one).  Outputs under gpurun_out/.
+# ONE pass in flight (--lanes 1): with several lane threads launching graphs concurrently the process dies inside ncu (SIGSEGV; round 1
+# saw glibc heap-corruption aborts in the same situation) while the same command without ncu, and under TSan / ASan, is clean.
 cd ${GRAFT_REPO_ROOT:-.}
-CMD="python bench.py --steps 20 --warmup 3 --lanes 4 --extras 0"
+CMD="python -X faulthandler bench.py --steps 20 --warmup 3 --lanes ${PROF_LANES:-1} --extras 0"
 K='regex:k_replay|k_decompress|k_vprep|k_msm|k_encode|k_scan'
 $CMD > gpurun_out/r2_prof_plain.json 2> gpurun_out/r2_prof_plain.err && \
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k "$K" -s 200 -c 660 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu1.log 2>&1
-echo "launch list rc=$?"
+echo "launch list rc=$?"; tail -25 gpurun_out/r2_ncu1.log | cut -c1-300
 $CMD > gpurun_out/r2_prof_plain2.json 2> gpurun_out/r2_prof_plain2.err && \
 ncu --set full --clock-control none --import-source on -k 'regex:k_msm_bucket_thread|k_decompress_proofs|k_replay_sm|k_vprep_vector|k_msm_reduce_warp|k_vprep_proof|k_msm_sort_seg|k_vprep_reduce' -s 120 -c 16 -o gpurun_out/r2_prof_full $CMD > gpurun_out/r2_ncu2.log 2>&1
-echo "set full rc=$?"; ls -la gpurun_out/r2_prof_full.ncu-rep gpurun_out/r2_launches.csv
+echo "set full rc=$?"; tail -5 gpurun_out/r2_ncu2.log | cut -c1-300; ls -la gpurun_out/r2_prof_full.ncu-rep gpurun_out/r2_launches.csv

@@ -114,6 +114,34 @@ def test_queue_mixed_actions_and_many_threads():
         q.close()
 
 
+def test_transcripts_in_different_states_within_one_call():
+    """calls whose transcripts all hold the same state upload ONE state (the usual case: one label); a call with per-proof labels uploads
+    them all -- both in one pass, every proof replayed from its own state"""
+    labels = [b"label-%d" % (i % 3) for i in range(8)]
+    mixed = workload.make_case(16, [1] * 8, 1, promise="third", rng_seed=12, labels=labels)
+    same = workload.make_case(16, [1] * 8, 1, promise="third", rng_seed=13)
+    eng = bpp.pkg.Engine(0)
+    params = api.RangeParameters.init(eng, 16, 1, 1)
+    q = api.VerifyQueue(0, 16, 1, 1, lanes=1, max_calls_per_pass=4)
+    try:
+        assert len(set(mixed.transcripts)) == 3 and len(set(same.transcripts)) == 1
+        batches = [[_calls(params, mixed, 0, 8)], [_calls(params, same, 0, 8)], [_calls(params, mixed, 2, 6)]]
+        got = q.verify_many(batches, api.VerifyAction.RecoverAndVerify)
+        for (status, masks), (case, lo, hi), b in zip(got, ((mixed, 0, 8), (same, 0, 8), (mixed, 2, 6)), batches):
+            rc, want, ts = _orc_advanced(case.transcripts[lo:hi], case.statements[lo:hi], case.proofs[lo:hi], orc.RECOVER_AND_VERIFY)
+            assert rc == 0 and status == [0]
+            assert [m.blindings() for m in masks[0]] == want
+            assert [t.state for t in b[0][0]] == ts
+        # a proof replayed from the wrong state does not verify
+        trs, sts, prs = _calls(params, mixed, 0, 8)
+        trs[1], trs[2] = trs[2], trs[1]
+        status, _ = api.verify_chunks(params, [(trs, sts, prs)], api.VerifyAction.VerifyOnly)
+        assert status == [orc.VERIFICATION_FAILED]
+    finally:
+        q.close()
+        eng.close()
+
+
 def test_create_multi_equals_separate_passes():
     case = workload.make_case(32, [1, 2, 1, 4, 1, 1, 2, 1], 2, max_aggregation=4, promise="third", rng_seed=31)
     eng = bpp.pkg.Engine(0)

@@ -17,7 +17,7 @@ class Case:
 
 
 def make_case(bit_length, aggregation_sizes, ext, max_aggregation=None, promise="third", seed_nonce=True,
-              rng_seed=SEED, same_blinding=False, params=None, rng=None):
+              rng_seed=SEED, same_blinding=False, params=None, rng=None, labels=None):
     """One proof per entry of aggregation_sizes, all under one RangeParameters (like the reference tests)."""
     rng = rng or orc.Rng("chacha", rng_seed)
     M = max_aggregation or max(aggregation_sizes)
@@ -39,7 +39,7 @@ def make_case(bit_length, aggregation_sizes, ext, max_aggregation=None, promise=
         sn = rng.random_not_zero() if (seed_nonce and m == 1) else None
         st = orc.St(params, coms, mins, sn)
         w = orc.Wit(vals, bl)
-        t0 = orc.transcript_new(LABEL)
+        t0 = orc.transcript_new(labels[len(prs)] if labels else LABEL)      # per-proof labels: transcripts in different states
         rc, pr, _ = orc.prove(t0, st, w, rng)
         assert rc == 0, rc
         sts.append(st)

@@ -576,13 +576,16 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     shot_ms = time_alone(lambda: lib.bpp_vbatch_run(vb_shot, st_shot, None, None), 10)
     # the same end to end: host buffers -> verdicts (create + run + destroy of one multi-call pass)
-    t0 = time.perf_counter()
-    for _ in range(10):
+    shot_times = []
+    for it in range(12):                                 # the first two allocate the pooled workspace and capture the graphs
+        t0 = time.perf_counter()
         vbx = C.c_void_p()
         assert lib.bpp_vbatch_create_multi(params.gens.h, len(shot_pks), ptrs, C.byref(vbx)) == 0
         assert lib.bpp_vbatch_run(vbx, st_shot, None, None) == 0
         lib.bpp_vbatch_destroy(vbx)
-    shot_e2e_ms = (time.perf_counter() - t0) * 1e3 / 10
+        if it >= 2:
+            shot_times.append((time.perf_counter() - t0) * 1e3)
+    shot_e2e_ms = statistics.median(shot_times)
     lib.bpp_vbatch_destroy(vb_shot)
     for vb, _ in lane_vb:
         lib.bpp_vbatch_destroy(vb)
@@ -772,7 +775,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=32)
-    ap.add_argument("--lanes", type=int, default=3, help="device passes in flight per GPU (one bpp_ctx + host thread each)")
+    ap.add_argument("--lanes", type=int, default=6, help="device passes in flight per GPU (one bpp_ctx + host thread each)")
     ap.add_argument("--pass-jobs", type=int, default=16, help="1024-proof jobs merged into one device pass")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -324,23 +324,33 @@ __global__ void __launch_bounds__(256) k_msm_sort_seg(uint32_t n_entries, uint32
     }
 }
 
-// The same for a GROUP of windows per CTA: CTA (segment, g) handles windows [g * G, (g + 1) * G) -- G * B counters in shared memory --
-// and walks the segment's scalars twice (count, scatter), recoding each one sequentially up to its last window, so the redundant
-// recoding of k_msm_sort_seg (once per window and pass: 134 M warp instructions per 16-job pass, 13 % of it, ALU-bound) shrinks by G.
-// G is chosen so that the grid still covers the machine: scattered 4-byte stores are limited per SM (one CTA per segment, G = W, took
-// 120 us however many segments there were; measured).  Regions as in k_msm_sort_seg: (segment, window) owns seg_lo * W + w * len.
-__global__ void __launch_bounds__(512) k_msm_sort_segw(uint32_t n_entries, uint32_t n_seg, int c, int W, int G, uint32_t B, const uint32_t *__restrict__ scalars,
+// The same for a GROUP of windows per CTA, for the verifier's width (C = 9, W = 28): CTA (segment, g) handles windows
+// [g * G, (g + 1) * G) -- G * B counters in shared memory -- and walks the segment's scalars twice (count, scatter).  The carry into the
+// group's first window comes from the closed form, the G digits follow sequentially with compile-time bit positions (the scalar stays
+// in registers), so the redundant recoding of k_msm_sort_seg (once per window and pass: 134 M warp instructions per 16-job pass, 13 %
+// of it, ALU-bound) shrinks by G.  G is chosen so that the grid still covers the machine: scattered 4-byte stores are limited per SM
+// (one CTA per segment, G = W, took 120 us however many segments there were; measured).  Regions as in k_msm_sort_seg.
+template <int C>
+__global__ void __launch_bounds__(512) k_msm_sort_segw(uint32_t n_entries, uint32_t n_seg, int G, const uint32_t *__restrict__ scalars,
                                                       const uint32_t *__restrict__ seg_offsets, uint32_t *__restrict__ starts, uint32_t *__restrict__ counts,
                                                       uint32_t *__restrict__ sorted) {
+    constexpr int W = (252 + C - 1) / C;
+    constexpr uint32_t B = 1u << (C - 1);
     extern __shared__ uint32_t s_cnt[];              // G * B counters, then cursors (relative to the window's region)
-    __shared__ uint32_t s_part[512];
+    __shared__ uint32_t s_part[512], s_thr[8];
     const uint32_t seg = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int w0 = (int)blockIdx.y * G, w1 = min(W, w0 + G), nw = w1 - w0;
     const uint32_t lo = n_seg > 1 ? seg_offsets[seg] : 0u, hi = n_seg > 1 ? seg_offsets[seg + 1] : n_entries;
     const uint32_t len = hi - lo, nk = (uint32_t)nw * B;
     const uint32_t key_base = (seg * (uint32_t)W + (uint32_t)w0) * B, region0 = lo * (uint32_t)W + (uint32_t)w0 * len;
     for (uint32_t k = tid; k < nk; k += nthr) s_cnt[k] = 0;
+    if (tid < 8) {                                   // T_w0: bit (C - 1) + C k set for k < w0
+        uint32_t t = 0;
+        for (int k = 0; k < w0; k++) { const uint32_t bit = (uint32_t)(C - 1) + (uint32_t)C * (uint32_t)k; if ((bit >> 5) == tid) t |= 1u << (bit & 31); }
+        s_thr[tid] = t;
+    }
     __syncthreads();
+    const int lowbits = C * w0;
     auto walk = [&](uint32_t i, bool scatter) {
         uint32_t s[8], t[8];
         ld8(s, scalars + 8 * (size_t)i);
@@ -354,12 +364,29 @@ __global__ void __launch_bounds__(512) k_msm_sort_segw(uint32_t n_entries, uint3
 #pragma unroll
             for (int k = 0; k < 8; k++) s[k] = t[k];
         }
-        uint32_t carry = 0;
-        for (int w = 0; w < w1; w++) {
-            uint32_t d = bits_at(s, w * c, c) + carry;
+        uint32_t carry;                              // into window w0: (s mod 2^lowbits) > T_w0
+        {
+            bool g2 = false, dec2 = false;
+#pragma unroll
+            for (int k = 7; k >= 0; k--) {
+                const int base = 32 * k;
+                const uint32_t m = lowbits >= base + 32 ? 0xffffffffu : lowbits <= base ? 0u : ((1u << (lowbits - base)) - 1u);
+                const uint32_t a = s[k] & m, th = s_thr[k];
+                if (!dec2 && a != th) { g2 = a > th; dec2 = true; }
+            }
+            carry = g2 ? 1u : 0u;
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            if (w < w0 || w >= w1) continue;
+            constexpr uint32_t mask = (1u << C) - 1u;
+            const int off = w * C, wi = off >> 5, sh = off & 31;          // compile-time after unrolling
+            uint32_t d = s[wi] >> sh;
+            if (sh + C > 32 && wi + 1 < 8) d |= s[wi + 1] << (32 - sh);
+            d = (d & mask) + carry;
             uint32_t neg = gt ? 1u : 0u;
             if (d > B) { d = 2u * B - d; neg ^= 1u; carry = 1u; } else carry = 0u;
-            if (w >= w0 && d) {
+            if (d) {
                 const uint32_t pos = atomicAdd(&s_cnt[(uint32_t)(w - w0) * B + d - 1u], 1u);
                 if (scatter) sorted[region0 + (uint32_t)(w - w0) * len + pos] = i | (neg << 31);
             }
@@ -918,15 +945,14 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
     // shared-memory sort for many small segments (the verifier), scan-based counting sort otherwise
     const uint32_t *counts = nullptr;
     const bool fused_sort = !knobs().scan_sort && sh.max_seg_entries != 0 && sh.max_seg_entries <= 16384u && sh.B <= 1024u && sh.n_seg * (uint32_t)sh.W >= 32u;
-    if (fused_sort && !knobs().window_sort) {
-        // groups of G windows per CTA, as large as leaves ~2 CTAs per SM and fits 40 KB of counters
+    if (fused_sort && sh.c == 9 && sh.n_seg >= 8 && !knobs().window_sort) {
+        // groups of G windows per CTA, as large as leaves ~2 CTAs per SM (few segments: one window per CTA, the kernel below)
         int groups = (int)((2 * 148 + sh.n_seg - 1) / sh.n_seg);
         if (groups > sh.W) groups = sh.W;
-        int G = (sh.W + groups - 1) / groups;
-        while (G > 1 && (size_t)G * sh.B * 4 > 40 * 1024) G--;
+        const int G = (sh.W + groups - 1) / groups;
         groups = (sh.W + G - 1) / G;
-        k_msm_sort_segw<<<dim3(sh.n_seg, (unsigned)groups), 512, (size_t)G * sh.B * 4, s>>>(sh.n_entries, sh.n_seg, sh.c, sh.W, G, sh.B, scalars, seg_offsets, sc.starts,
-                                                                                           sc.cursor, sc.sorted);
+        k_msm_sort_segw<9><<<dim3(sh.n_seg, (unsigned)groups), 512, (size_t)G * sh.B * 4, s>>>(sh.n_entries, sh.n_seg, G, scalars, seg_offsets, sc.starts, sc.cursor,
+                                                                                              sc.sorted);
         counts = sc.cursor;
         if (launches) *launches += 1;
     } else if (fused_sort) {

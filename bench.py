@@ -462,7 +462,7 @@ def run_b200(args, rank, local_rank, world):
     K = max(1, args.pass_jobs)
     S = max(1, args.lanes)
     htl = args.host_threads_per_lane or max(1, cores // (S * world))
-    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=True)
+    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=True, device_weights=bool(args.device_weights))
     eng, params = pool.lanes[0]
     FLUSH = int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144")) << 20
     action = api.VerifyAction.VerifyOnly
@@ -593,7 +593,7 @@ def run_b200(args, rank, local_rank, world):
     barrier()
 
     # ---------------- end-to-end arm (e2e): the coalescing queue with HOST buffers; jobs submitted from this thread
-    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=S, max_calls_per_pass=K, host_threads_per_lane=htl)
+    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=S, max_calls_per_pass=K, host_threads_per_lane=htl, device_weights=bool(args.device_weights))
     n_slots = min(n_jobs, 2 * S * K)
     slots = [q.pack(job_calls(q.shape, j % K), action) for j in range(n_slots)]
     t_init = bytes(slots[0].tbuf.raw)
@@ -748,6 +748,7 @@ def run_b200(args, rank, local_rank, world):
             "engine": {"lanes_per_gpu": S, "jobs_per_device_pass": K, "host_threads_per_lane": htl,
                        "timed_jobs_per_gpu": dev_jobs, "timed_device_passes_per_gpu": n_pass,
                        "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay_sm)",
+                       "verifier_weights": "device (k_weights), one graph launch per pass" if args.device_weights else "host threads (8-way Keccak) between two graph launches",
                        "workload_made_by": "device prover (bpp_prove_batch); K = %d distinct jobs per rank" % K},
             "e2e": {"value": world * n_jobs * JOB / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
                     "h2d_bytes_per_step": io_h2d * reps, "d2h_bytes_per_step": io_d2h * reps, "h2d_bytes_per_job": io_h2d, "d2h_bytes_per_job": io_d2h,
@@ -779,6 +780,7 @@ def main():
     ap.add_argument("--pass-jobs", type=int, default=16, help="1024-proof jobs merged into one device pass")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--device-weights", type=int, default=0, help="1: weight transcripts hashed on the device (k_weights), a pass is ONE graph launch")
     ap.add_argument("--host-threads-per-lane", type=int, default=0, help="0 = host cores / (lanes * ranks)")
     ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput (secondary metrics)")
     ap.add_argument("--prove-batch", type=int, default=8192)

@@ -492,7 +492,7 @@ class VerifyQueue:
     (include/bpp_b200.h, csrc/engine_queue.cpp).  Results are those of verify_chunks on each call alone."""
 
     def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=3, max_calls_per_pass=16, host_threads_per_lane=0,
-                 h_base=None, g_bases=None):
+                 h_base=None, g_bases=None, device_weights=False):
         self.h = C.c_void_p()
         gb = b"".join(g_bases) if g_bases else None
         rc = _ffi.lib().bpp_vqueue_create(device, bit_length, max_aggregation, int(extension_degree), h_base, gb, lanes, max_calls_per_pass,
@@ -501,6 +501,8 @@ class VerifyQueue:
             self.h = C.c_void_p()
             raise EngineError(rc, "bpp_vqueue_create")
         self.shape = _QueueShape(bit_length, max_aggregation, int(extension_degree))
+        if device_weights:
+            _ffi.lib().bpp_vqueue_set_device_weights(self.h, 1)
 
     def submit(self, packed):
         """packed: a _Packed kept alive by the caller until wait() returns"""
@@ -575,7 +577,8 @@ class VerifierPool:
     verify_many(batches) runs batches[i] on lane i % S and returns the per-batch (status, masks) in input order; results do
     not depend on S (every batch is verified by the same code path as RangeProof.verify_batch)."""
 
-    def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=8, host_threads_per_lane=None, blocking_waits=None):
+    def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=8, host_threads_per_lane=None, blocking_waits=None,
+                 device_weights=False):
         import os
 
         from . import Engine
@@ -587,7 +590,7 @@ class VerifierPool:
         for _ in range(lanes):
             eng = Engine(device)
             eng.set_host_threads(per)
-            eng.set_throughput_mode(1 if blocking_waits else 0)   # lane threads sleep while their pass runs (bpp_ctx_set_throughput_mode)
+            eng.set_throughput_mode(2 if device_weights else 1 if blocking_waits else 0)   # lane threads sleep while their pass runs (bpp_ctx_set_throughput_mode)
             self.lanes.append((eng, RangeParameters.init(eng, bit_length, max_aggregation, extension_degree)))
 
     def __len__(self):

@@ -14,6 +14,7 @@
 #include <functional>
 #include "engine.hpp"
 #include "hash.cuh"
+#include "strobe_n.hpp"
 
 using namespace bpp;
 
@@ -122,6 +123,62 @@ bool challenge(Merlin &t, const uint8_t *label, size_t ll, sc &out) {
     return !sc_is_zero(out);
 }
 
+// ---- eight proofs of a call through ONE vectorised sponge (strobe_n.hpp).  The proofs of a bpp_prove_batch call have one shape, so their
+// transcripts and TranscriptRngs run the same operations at the same sponge positions; ~45 Keccak-f per proof (the largest host cost of
+// the prover) become ~45 eight-way permutations per eight proofs.  A stage takes this path only when its eight lanes agree on everything
+// that steers the operation sequence (alive, sponge positions, rebuild count, nonce source) and nothing exceptional can happen in it
+// (identity points are seen up front; a zero challenge or a zero random scalar -- probability 2^-252 -- is seen afterwards, BEFORE anything
+// is written back); otherwise the stage returns false with the proofs untouched and the caller runs the one-at-a-time code on each lane.
+// The canonical state stays in PProof between stages.  BPP_PROVE_LOCKSTEP=0 turns the path off (tests compare both byte for byte).
+constexpr int LK = 8;
+bool lockstep_enabled() {
+    static const bool on = [] { const char *e = getenv("BPP_PROVE_LOCKSTEP"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+struct Lock8 {
+    PProof *p[LK];
+    MerlinN<LK> t;
+    StrobeN<LK> r;
+    static bool same_pos(const Strobe128 &a, const Strobe128 &b) { return a.pos == b.pos && a.pos_begin == b.pos_begin && a.cur_flags == b.cur_flags; }
+    bool uniform(bool with_rng) const {
+        const PProof &q0 = *p[0];
+        for (int j = 0; j < LK; j++) {
+            const PProof &q = *p[j];
+            if (q.rc || q.has_seed != q0.has_seed || q.rng_used != q0.rng_used || q.witness.size() != q0.witness.size()) return false;
+            if (!same_pos(q.t.s, q0.t.s) || (with_rng && !same_pos(q.rng.s, q0.rng.s))) return false;
+        }
+        return true;
+    }
+    void load_t() { for (int j = 0; j < LK; j++) t.s.load_lane(j, p[j]->t.s); }
+    void load_r() { for (int j = 0; j < LK; j++) r.load_lane(j, p[j]->rng.s); }
+    void store_t() const { for (int j = 0; j < LK; j++) t.s.store_lane(j, p[j]->t.s); }
+    void store_r() const { for (int j = 0; j < LK; j++) r.store_lane(j, p[j]->rng.s); }
+    // rebuild_rng of every lane (from the lock-step transcript as it stands); the callers bump rng_used when they commit
+    void rebuild() {
+        const uint8_t *w[LK], *e[LK];
+        for (int j = 0; j < LK; j++) { w[j] = p[j]->witness.data(); e[j] = p[j]->rng_bytes + 32 * p[j]->rng_used; }
+        r = t.build_rng(w, p[0]->witness.size(), e);
+    }
+    bool draw(sc out[LK]) {                        // Scalar::random_not_zero per lane; false = some lane would have to draw again
+        uint8_t buf[LK][64], *ptr[LK];
+        for (int j = 0; j < LK; j++) ptr[j] = buf[j];
+        rng_fill_each(r, ptr, 64);
+        bool ok = true;
+        for (int j = 0; j < LK; j++) { out[j] = wide_to_sc(buf[j]); ok = ok && !sc_is_zero(out[j]); }
+        secure_zero(buf, sizeof buf);
+        return ok;
+    }
+    bool challenge(const uint8_t *label, size_t ll, sc out[LK]) {
+        uint8_t buf[LK][64], *ptr[LK];
+        for (int j = 0; j < LK; j++) ptr[j] = buf[j];
+        t.challenge_each(label, ll, ptr, 64);
+        bool ok = true;
+        for (int j = 0; j < LK; j++) { out[j] = wide_to_sc(buf[j]); ok = ok && !sc_is_zero(out[j]); }
+        return ok;
+    }
+    void wipe() { secure_zero(&r, sizeof r); }
+};
+
 // device + pinned buffers of the prover, kept per ctx across calls (grow-only; cudaMalloc / cudaFree of the ~200 MB bucket
 // scratch cost more than the proving itself); the secrets in them are wiped at the end of every call
 struct ProveWS {
@@ -182,6 +239,15 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         host_stage_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
 
+    // a stage over n proofs: groups of LK through the lock-step sponge when `lock(first)` takes them, else one at a time
+    auto host_stage_lk = [&](size_t n, const std::function<bool(size_t)> &lock, const std::function<void(size_t)> &one) {
+        host_stage((n + LK - 1) / LK, 1, [&](size_t gi) {
+            const size_t lo = LK * gi, hi = std::min(n, lo + LK);
+            if (hi - lo == LK && lockstep_enabled() && lock(lo)) return;
+            for (size_t s = lo; s < hi; s++) one(s);
+        });
+    };
+
     std::vector<PProof> pp(P0);
     // Everything below that holds witness-derived data is wiped when this function is left, whichever way (the reference keeps these in
     // Zeroizing<..>: range_proof.rs:300-301, :325, :438-464, :542-571): the host copies (per-proof state, bit offsets, a[0] / b[0], the
@@ -232,10 +298,32 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
 
     // ---- RangeProofTranscript::new (:287-297), bit offsets (:300-322), alpha (:325-333)
     std::vector<size_t> live;
-    host_stage(P0, 8, [&](size_t i) {
+    auto fill_witness = [&](PProof &p, size_t i) {
+        p.rng_bytes = a->rng_bytes + a->rng_stride * i;
+        p.witness.resize((size_t)m * (8 + 32 * ext));
+        for (uint32_t j = 0; j < m; j++) {
+            uint8_t *w = p.witness.data() + (size_t)j * (8 + 32 * ext);
+            le64_bytes(w, a->values[i * m + j]);
+            memcpy(w + 8, a->blindings32 + 32 * ((i * m + j) * ext), 32 * (size_t)ext);
+        }
+    };
+    auto below_minimum = [&](size_t i) {                                                    // :309-311
+        for (uint32_t j = 0; j < m; j++)
+            if (a->min_present[i * m + j] && a->values[i * m + j] < a->min_values[i * m + j]) return true;
+        return false;
+    };
+    auto init_finish = [&](PProof &p, size_t i) {        // what follows the rng build; alpha from the rng was drawn by the caller
+        if (p.has_seed) {
+            sc_store(p.seed, sc_reduce_bytes(a->seed_nonces32 + 32 * i));
+            for (uint32_t k = 0; k < ext; k++) p.alpha[k] = nonce(p.seed, "alpha", false, 0, true, k);
+        }
+        p.e_round.resize(rounds); p.einv_round.resize(rounds); p.dL.resize((size_t)rounds * ext); p.dR.resize((size_t)rounds * ext); p.LR.resize(64 * (size_t)rounds);
+    };
+    bool gens_nonzero = !zero32(g->h());
+    for (uint32_t k = 0; k < ext; k++) gens_nonzero = gens_nonzero && !zero32(g->g(k));
+    auto init_one = [&](size_t i) {
         PProof &p = pp[i];
         if (p.rc) return;
-        p.rng_bytes = a->rng_bytes + a->rng_stride * i;
         p.t.s.load(a->transcripts + BPP_TRANSCRIPT_BYTES * i);
         p.t.append_message(LBL("dom-sep"), LBL("Bulletproofs+ Range Proof"));
         bool ok = append_point(p.t, LBL("H"), g->h());
@@ -246,20 +334,62 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         p.t.append_u64(LBL("M"), m);
         for (uint32_t j = 0; j < m; j++) p.t.append_message(LBL("Ci"), a->commitments32 + 32 * (i * m + j), 32);
         for (uint32_t j = 0; j < m; j++) p.t.append_u64(LBL("vi - minimum_value"), a->min_present[i * m + j] ? a->min_values[i * m + j] : 0);
-        p.witness.resize((size_t)m * (8 + 32 * ext));
-        for (uint32_t j = 0; j < m; j++) {
-            uint8_t *w = p.witness.data() + (size_t)j * (8 + 32 * ext);
-            le64_bytes(w, a->values[i * m + j]);
-            memcpy(w + 8, a->blindings32 + 32 * ((i * m + j) * ext), 32 * (size_t)ext);
-        }
+        fill_witness(p, i);
         rebuild_rng(p);
-        for (uint32_t j = 0; j < m; j++)
-            if (a->min_present[i * m + j] && a->values[i * m + j] < a->min_values[i * m + j]) p.rc = BPP_INVALID_ARGUMENT;   // :309-311
+        if (below_minimum(i)) p.rc = BPP_INVALID_ARGUMENT;
         if (p.rc) { p.t.s.store(a->transcripts + BPP_TRANSCRIPT_BYTES * i); return; }
-        if (p.has_seed) sc_store(p.seed, sc_reduce_bytes(a->seed_nonces32 + 32 * i));
-        for (uint32_t k = 0; k < ext; k++) p.alpha[k] = p.has_seed ? nonce(p.seed, "alpha", false, 0, true, k) : random_not_zero(p.rng);
-        p.e_round.resize(rounds); p.einv_round.resize(rounds); p.dL.resize((size_t)rounds * ext); p.dR.resize((size_t)rounds * ext); p.LR.resize(64 * (size_t)rounds);
-    });
+        if (!p.has_seed)
+            for (uint32_t k = 0; k < ext; k++) p.alpha[k] = random_not_zero(p.rng);
+        init_finish(p, i);
+    };
+    auto init_lock = [&](size_t i0) -> bool {
+        if (!gens_nonzero) return false;
+        Lock8 L;
+        for (int j = 0; j < LK; j++) {
+            PProof &p = pp[i0 + j];
+            L.p[j] = &p;
+            if (p.rc || below_minimum(i0 + j)) return false;
+            p.t.s.load(a->transcripts + BPP_TRANSCRIPT_BYTES * (i0 + j));
+            fill_witness(p, i0 + j);
+        }
+        if (!L.uniform(false)) return false;
+        L.load_t();
+        L.t.append_same(LBL("dom-sep"), LBL("Bulletproofs+ Range Proof"));
+        L.t.append_same(LBL("H"), g->h(), 32);
+        for (uint32_t k = 0; k < ext; k++) L.t.append_same(LBL("G"), g->g(k), 32);
+        L.t.append_u64_same(LBL("N"), n);
+        L.t.append_u64_same(LBL("T"), ext);
+        L.t.append_u64_same(LBL("M"), m);
+        const uint8_t *ptr[LK];
+        for (uint32_t j = 0; j < m; j++) {
+            for (int l = 0; l < LK; l++) ptr[l] = a->commitments32 + 32 * ((i0 + l) * m + j);
+            L.t.append_each(LBL("Ci"), ptr, 32);
+        }
+        for (uint32_t j = 0; j < m; j++) {
+            uint8_t mv[LK][8];
+            for (int l = 0; l < LK; l++) { le64_bytes(mv[l], a->min_present[(i0 + l) * m + j] ? a->min_values[(i0 + l) * m + j] : 0); ptr[l] = mv[l]; }
+            L.t.append_each(LBL("vi - minimum_value"), ptr, 8);
+        }
+        L.rebuild();
+        sc al[BPP_MAX_EXT][LK];
+        bool ok = true;
+        if (!L.p[0]->has_seed)
+            for (uint32_t k = 0; k < ext && ok; k++) ok = L.draw(al[k]);
+        if (ok) {
+            L.store_t(); L.store_r();
+            for (int l = 0; l < LK; l++) {
+                PProof &p = *L.p[l];
+                p.rng_used++;
+                if (!p.has_seed)
+                    for (uint32_t k = 0; k < ext; k++) p.alpha[k] = al[k][l];
+                init_finish(p, i0 + l);
+            }
+        }
+        secure_zero(al, sizeof al);
+        L.wipe();
+        return ok;
+    };
+    host_stage_lk(P0, init_lock, init_one);
     for (size_t i = 0; i < P0; i++)
         if (!pp[i].rc) { pp[i].live = true; pp[i].slot = (uint32_t)live.size(); live.push_back(i); }
     const uint32_t P = (uint32_t)live.size();
@@ -401,15 +531,9 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     PCUDA(cudaMemcpyAsync(hio, d_enc.p, 32 * (size_t)P, cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
     // ---- challenges y, z (:348, transcripts.rs:124-136), alpha update (:382-392)
-    host_stage(P, 8, [&](size_t s) {
-        PProof &p = pp[live[s]];
-        memcpy(p.A, hio + 32 * s, 32);
-        bool good = append_point(p.t, LBL("A"), p.A);
-        if (good) { rebuild_rng(p); good = challenge(p.t, LBL("y"), p.y) && challenge(p.t, LBL("z"), p.z); }
-        if (!good) { p.rc = BPP_VERIFICATION_FAILED; p.y = sc_one(); p.z = sc_one(); }
+    auto yz_finish = [&](PProof &p, size_t i) {
         const sc z2 = hmul(p.z, p.z), yN1 = hpow(p.y, (uint64_t)N + 1);
         sc zeven = sc_one();
-        const size_t i = live[s];
         for (uint32_t j = 0; j < m; j++) {
             zeven = hmul(zeven, z2);
             for (uint32_t k = 0; k < ext; k++) {
@@ -417,7 +541,43 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
                 p.alpha[k] = sc_add(p.alpha[k], hmul(hmul(zeven, r), yN1));
             }
         }
-    });
+    };
+    auto yz_one = [&](size_t s) {
+        PProof &p = pp[live[s]];
+        memcpy(p.A, hio + 32 * s, 32);
+        bool good = append_point(p.t, LBL("A"), p.A);
+        if (good) { rebuild_rng(p); good = challenge(p.t, LBL("y"), p.y) && challenge(p.t, LBL("z"), p.z); }
+        if (!good) { p.rc = BPP_VERIFICATION_FAILED; p.y = sc_one(); p.z = sc_one(); }
+        yz_finish(p, live[s]);
+    };
+    auto yz_lock = [&](size_t s0) -> bool {
+        Lock8 L;
+        const uint8_t *ptr[LK];
+        for (int l = 0; l < LK; l++) {
+            L.p[l] = &pp[live[s0 + l]];
+            ptr[l] = hio + 32 * (s0 + l);
+            if (zero32(ptr[l])) return false;
+        }
+        if (!L.uniform(false)) return false;
+        L.load_t();
+        L.t.append_each(LBL("A"), ptr, 32);
+        L.rebuild();
+        sc y[LK], z[LK];
+        const bool ok = L.challenge(LBL("y"), y) && L.challenge(LBL("z"), z);
+        if (ok) {
+            L.store_t(); L.store_r();
+            for (int l = 0; l < LK; l++) {
+                PProof &p = *L.p[l];
+                memcpy(p.A, ptr[l], 32);
+                p.rng_used++;
+                p.y = y[l]; p.z = z[l];
+                yz_finish(p, live[s0 + l]);
+            }
+        }
+        L.wipe();
+        return ok;
+    };
+    host_stage_lk(P, yz_lock, yz_one);
     for (uint32_t s = 0; s < P; s++) { sc_store(hio + 64 * (size_t)s, pp[live[s]].y); sc_store(hio + 64 * (size_t)s + 32, pp[live[s]].z); }
     // y^-1 by Montgomery's trick over chunks of 64 proofs (y is never zero: challenge() rejects it above)
     host_stage((P + 63) / 64, 1, [&](size_t c) {
@@ -438,15 +598,40 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     for (uint32_t round = 0; round < rounds; round++) {
         const uint32_t nn = N >> (round + 1);
         PCUDA(cudaStreamSynchronize(st));      // hio is about to be rewritten
-        host_stage(P, 8, [&](size_t s) {
-            PProof &p = pp[live[s]];
-            for (uint32_t k = 0; k < ext; k++) p.dL[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dL", true, round, true, k) : random_not_zero(p.rng);
-            for (uint32_t k = 0; k < ext; k++) p.dR[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dR", true, round, true, k) : random_not_zero(p.rng);
+        auto dlr_put = [&](PProof &p, size_t s) {
             for (uint32_t k = 0; k < ext; k++) {
                 sc_store(hio + 32 * ((size_t)s * 2 * ext + k), p.dL[(size_t)round * ext + k]);
                 sc_store(hio + 32 * ((size_t)s * 2 * ext + ext + k), p.dR[(size_t)round * ext + k]);
             }
-        });
+        };
+        auto dlr_one = [&](size_t s) {
+            PProof &p = pp[live[s]];
+            for (uint32_t k = 0; k < ext; k++) p.dL[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dL", true, round, true, k) : random_not_zero(p.rng);
+            for (uint32_t k = 0; k < ext; k++) p.dR[(size_t)round * ext + k] = p.has_seed ? nonce(p.seed, "dR", true, round, true, k) : random_not_zero(p.rng);
+            dlr_put(p, s);
+        };
+        auto dlr_lock = [&](size_t s0) -> bool {       // only the rng draws go through the sponge; seed nonces are BLAKE2b
+            Lock8 L;
+            for (int l = 0; l < LK; l++) L.p[l] = &pp[live[s0 + l]];
+            if (L.p[0]->has_seed || !L.uniform(true)) return false;
+            L.load_r();
+            sc dl[BPP_MAX_EXT][LK], dr[BPP_MAX_EXT][LK];
+            bool ok = true;
+            for (uint32_t k = 0; k < ext && ok; k++) ok = L.draw(dl[k]);
+            for (uint32_t k = 0; k < ext && ok; k++) ok = L.draw(dr[k]);
+            if (ok) {
+                L.store_r();
+                for (int l = 0; l < LK; l++) {
+                    PProof &p = *L.p[l];
+                    for (uint32_t k = 0; k < ext; k++) { p.dL[(size_t)round * ext + k] = dl[k][l]; p.dR[(size_t)round * ext + k] = dr[k][l]; }
+                    dlr_put(p, s0 + l);
+                }
+            }
+            secure_zero(dl, sizeof dl); secure_zero(dr, sizeof dr);
+            L.wipe();
+            return ok;
+        };
+        host_stage_lk(P, dlr_lock, dlr_one);
         PCUDA(cudaMemcpyAsync(d_dlr.p, hio, 64 * (size_t)P * ext, cudaMemcpyHostToDevice, st));
         if (fb) {
             launch_prove_round_pre_fb(st, d, b, nn);
@@ -463,7 +648,7 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         }
         PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
         PCUDA(cudaStreamSynchronize(st));
-        host_stage(P, 8, [&](size_t s) {       // transcripts.rs:139-149
+        auto e_one = [&](size_t s) {       // transcripts.rs:139-149
             PProof &p = pp[live[s]];
             memcpy(p.LR.data() + 64 * (size_t)round, hio + 64 * s, 64);
             bool good = append_point(p.t, LBL("L"), hio + 64 * s) && append_point(p.t, LBL("R"), hio + 64 * s + 32);
@@ -471,7 +656,35 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
             if (good) { rebuild_rng(p); good = challenge(p.t, LBL("e"), e); }
             if (!good) { if (!p.rc) p.rc = BPP_VERIFICATION_FAILED; e = sc_one(); }
             p.e_round[round] = e;
-        });
+        };
+        auto e_lock = [&](size_t s0) -> bool {
+            Lock8 L;
+            const uint8_t *pl[LK], *pr[LK];
+            for (int l = 0; l < LK; l++) {
+                L.p[l] = &pp[live[s0 + l]];
+                pl[l] = hio + 64 * (s0 + l); pr[l] = pl[l] + 32;
+                if (zero32(pl[l]) || zero32(pr[l])) return false;
+            }
+            if (!L.uniform(false)) return false;
+            L.load_t();
+            L.t.append_each(LBL("L"), pl, 32);
+            L.t.append_each(LBL("R"), pr, 32);
+            L.rebuild();
+            sc e[LK];
+            const bool ok = L.challenge(LBL("e"), e);
+            if (ok) {
+                L.store_t(); L.store_r();
+                for (int l = 0; l < LK; l++) {
+                    PProof &p = *L.p[l];
+                    memcpy(p.LR.data() + 64 * (size_t)round, pl[l], 64);
+                    p.rng_used++;
+                    p.e_round[round] = e[l];
+                }
+            }
+            L.wipe();
+            return ok;
+        };
+        host_stage_lk(P, e_lock, e_one);
         // e^-1 of every proof by Montgomery's trick over chunks of 64 proofs (one inversion + 3 products per proof): on the device
         // it was one binary-Euclid inversion per proof per round on the critical path (0.13 ms per round), and the responses at
         // the end needed one more inversion per proof.  Challenges are never zero (challenge() rejects them above).
@@ -508,13 +721,40 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
         for (uint32_t k = 0; k < ext; k++) p.d[k] = p.has_seed ? nonce(p.seed, "d", false, 0, true, k) : random_not_zero(p.rng);
         for (uint32_t k = 0; k < ext; k++) p.eta[k] = p.has_seed ? nonce(p.seed, "eta", false, 0, true, k) : random_not_zero(p.rng);
     };
+    auto draw_lock = [&](size_t s0) -> bool {
+        Lock8 L;
+        for (int l = 0; l < LK; l++) L.p[l] = &pp[live[s0 + l]];
+        if (!L.uniform(true)) return false;
+        L.load_r();
+        const bool seeded = L.p[0]->has_seed;
+        sc r[LK], sv[LK], dd[BPP_MAX_EXT][LK], ee[BPP_MAX_EXT][LK];
+        bool ok = L.draw(r) && L.draw(sv);
+        if (!seeded) {
+            for (uint32_t k = 0; k < ext && ok; k++) ok = L.draw(dd[k]);
+            for (uint32_t k = 0; k < ext && ok; k++) ok = L.draw(ee[k]);
+        }
+        if (ok) {
+            L.store_r();
+            for (int l = 0; l < LK; l++) {
+                PProof &p = *L.p[l];
+                p.r = r[l]; p.s = sv[l];
+                for (uint32_t k = 0; k < ext; k++) {
+                    p.d[k] = seeded ? nonce(p.seed, "d", false, 0, true, k) : dd[k][l];
+                    p.eta[k] = seeded ? nonce(p.seed, "eta", false, 0, true, k) : ee[k][l];
+                }
+            }
+        }
+        secure_zero(r, sizeof r); secure_zero(sv, sizeof sv); secure_zero(dd, sizeof dd); secure_zero(ee, sizeof ee);
+        L.wipe();
+        return ok;
+    };
+    host_stage_lk(P, draw_lock, [&](size_t s) { draw_final(pp[live[s]]); });
     if (fb) {
         // A1 = sum_j r*sG[j]*G_j + sum_j s*sH[j]*H_j + sum d[k]*G[k] + (r*y*b[0] + s*y*a[0])*H   (:574-580, Gi[0] / Hi[0] unfolded)
         // B  = (r*y*s)*H + sum eta[k]*G[k]                                                        (:581-584)
         uint8_t *h_rs = hio, *h_tail = hio + 64 * (size_t)P, *h_b = h_tail + 32 * (size_t)P * (1 + ext);
         host_stage(P, 8, [&](size_t s) {
             PProof &p = pp[live[s]];
-            draw_final(p);
             const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
             const sc ry = hmul(p.r, p.y), sy = hmul(p.s, p.y);
             sc_store(h_rs + 64 * s, p.r); sc_store(h_rs + 64 * s + 32, p.s);
@@ -545,7 +785,6 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     const uint32_t GEN = 0x80000000u, CACHED = 0x40000000u;
     host_stage(P, 8, [&](size_t s) {
         PProof &p = pp[live[s]];
-        draw_final(p);
         const sc a0 = sc_load(ab.data() + 64 * s), b0 = sc_load(ab.data() + 64 * s + 32);
         const sc ry = hmul(p.r, p.y), sy = hmul(p.s, p.y);
         uint8_t *sv = h_sc + 32 * s * per;
@@ -572,14 +811,47 @@ int32_t bpp_prove_batch(bpp_gens *g, const bpp_prove_args *a, uint8_t *proofs_ou
     PCUDA(cudaMemcpyAsync(hio, d_enc.p, 64 * (size_t)P, cudaMemcpyDeviceToHost, st));
     // the device copies of the secrets are wiped by wipe_guard when the function is left
     PCUDA(cudaStreamSynchronize(st));
+    const uint8_t *encA1 = hio, *encB = fb ? hio + 32 * (size_t)P : hio + 32;      // fixed-base path: [A1 x P | B x P], else [A1 | B] x P
+    const size_t enc_stride = fb ? 32 : 64;
+    auto last_lock = [&](size_t s0) -> bool {       // transcripts.rs:152-162
+        Lock8 L;
+        const uint8_t *pa[LK], *pb[LK];
+        for (int l = 0; l < LK; l++) {
+            L.p[l] = &pp[live[s0 + l]];
+            pa[l] = encA1 + enc_stride * (s0 + l); pb[l] = encB + enc_stride * (s0 + l);
+            if (zero32(pa[l]) || zero32(pb[l])) return false;
+        }
+        if (!L.uniform(false)) return false;
+        L.load_t();
+        L.t.append_each(LBL("A1"), pa, 32);
+        L.t.append_each(LBL("B"), pb, 32);
+        L.rebuild();
+        sc e[LK];
+        const bool ok = L.challenge(LBL("e"), e);
+        if (ok) {
+            L.store_t(); L.store_r();
+            for (int l = 0; l < LK; l++) {
+                PProof &p = *L.p[l];
+                memcpy(p.A1, pa[l], 32); memcpy(p.B, pb[l], 32);
+                p.rng_used++;
+                p.e_final = e[l];
+            }
+        }
+        L.wipe();
+        return ok;
+    };
+    auto last_one = [&](size_t s) {
+        PProof &p = pp[live[s]];
+        memcpy(p.A1, encA1 + enc_stride * s, 32);
+        memcpy(p.B, encB + enc_stride * s, 32);
+        bool good = append_point(p.t, LBL("A1"), p.A1) && append_point(p.t, LBL("B"), p.B);
+        if (good) { rebuild_rng(p); good = challenge(p.t, LBL("e"), p.e_final); }
+        if (!good && !p.rc) p.rc = BPP_VERIFICATION_FAILED;
+    };
+    host_stage_lk(P, last_lock, last_one);
     host_stage(P, 8, [&](size_t s) {
         const size_t i = live[s];
         PProof &p = pp[i];
-        memcpy(p.A1, fb ? hio + 32 * s : hio + 64 * s, 32);                    // fixed-base path: [A1 x P | B x P]
-        memcpy(p.B, fb ? hio + 32 * ((size_t)P + s) : hio + 64 * s + 32, 32);
-        bool good = append_point(p.t, LBL("A1"), p.A1) && append_point(p.t, LBL("B"), p.B);      // transcripts.rs:152-162
-        if (good) { rebuild_rng(p); good = challenge(p.t, LBL("e"), p.e_final); }
-        if (!good && !p.rc) p.rc = BPP_VERIFICATION_FAILED;
         p.t.s.store(a->transcripts + BPP_TRANSCRIPT_BYTES * i);
         if (p.rc) return;
         const sc e = p.e_final, e2 = hmul(e, e);

@@ -197,6 +197,13 @@ int32_t bpp_vqueue_stats(bpp_vqueue *q, uint64_t out5[5]) {
     return BPP_OK;
 }
 
+int32_t bpp_vqueue_set_device_weights(bpp_vqueue *q, int32_t enable) {
+    if (!q) return BPP_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(q->mu);             // lanes read their mode at the start of a pass
+    for (QLane &l : q->lanes) bpp_ctx_set_throughput_mode(l.ctx, enable ? 2 : 1);
+    return BPP_OK;
+}
+
 int32_t bpp_vqueue_lanes(const bpp_vqueue *q) { return q ? (int32_t)q->lanes.size() : 0; }
 
 } // extern "C"

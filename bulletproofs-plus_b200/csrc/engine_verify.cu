@@ -176,114 +176,10 @@ void vgraph_cache_free(bpp_ctx *ctx) {
 // The 64 bytes drawn per weight (Scalar::random, range_proof.rs:894) are handed out as they are: the wide reduction mod l runs on the
 // device (k_vprep_weight), which also reports the zero weight random_not_zero would redraw (probability 2^-252; handled by rerunning
 // the chunk through weights_scalar, see bpp_vbatch_run).
-extern "C" void bpp_keccak_f1600_x4(uint64_t *st);
-extern "C" void bpp_keccak_f1600_x8(uint64_t *st);
+#include "strobe_n.hpp"
 extern "C" int32_t bpp_host_simd_level(void);
 extern "C" void bpp_host_sc_from_wide64(const uint8_t in64[64], uint8_t out32[32]);      // host_keccak4.cpp: 64-bit-limb wide reduction
 namespace {
-template <int LANES> struct StrobeN {
-    alignas(64) uint64_t st[25 * LANES];          // lane k of state j at st[LANES * k + j]
-    uint8_t pos = 0, pos_begin = 0, cur_flags = 0;
-    static constexpr int RATE = Strobe128::RATE;
-    void permute() { if (LANES == 8) bpp_keccak_f1600_x8(st); else bpp_keccak_f1600_x4(st); }
-    void load_all(const uint8_t *b) {      // the same 203-byte state into every lane
-        for (int k = 0; k < 25; k++) {
-            uint64_t x = 0;
-            for (int j = 7; j >= 0; j--) x = (x << 8) | b[8 * k + j];
-            for (int j = 0; j < LANES; j++) st[LANES * k + j] = x;
-        }
-        pos = b[200]; pos_begin = b[201]; cur_flags = b[202];
-    }
-    void xor_all(int p, uint8_t v) {
-        const uint64_t x = (uint64_t)v << (8 * (p & 7));
-        uint64_t *l = st + LANES * (p >> 3);
-        for (int j = 0; j < LANES; j++) l[j] ^= x;
-    }
-    void run_f() {
-        xor_all(pos, pos_begin); xor_all(pos + 1, 0x04); xor_all(RATE + 1, 0x80);
-        permute();
-        pos = 0; pos_begin = 0;
-    }
-    // Spans move up to eight bytes at a time as one 64-bit word per state (a word may straddle two sponge lanes); the byte loops
-    // they replace cost about as much as the permutations they fed.
-    static uint64_t load_le(const uint8_t *d, size_t n) {           // n <= 8
-        uint64_t x = 0;
-        if (n == 8) memcpy(&x, d, 8);
-        else for (size_t i = 0; i < n; i++) x |= (uint64_t)d[i] << (8 * i);
-        return x;
-    }
-    void absorb_same(const uint8_t *d, size_t len) {
-        while (len) {
-            size_t n = len < 8 ? len : 8;
-            if (n > (size_t)(RATE - pos)) n = (size_t)(RATE - pos);
-            const uint64_t x = load_le(d, n);
-            const int off = pos & 7, sh = 8 * off;
-            uint64_t *l = st + LANES * (pos >> 3);
-            const uint64_t lo = x << sh;
-            for (int j = 0; j < LANES; j++) l[j] ^= lo;
-            if (off + (int)n > 8) { const uint64_t hi = x >> (64 - sh); for (int j = 0; j < LANES; j++) l[LANES + j] ^= hi; }
-            d += n; len -= n;
-            pos = (uint8_t)(pos + n);
-            if (pos == RATE) run_f();
-        }
-    }
-    void absorb_each(const uint8_t *const d[LANES], size_t len) {
-        size_t i = 0;
-        while (i < len) {
-            size_t n = len - i < 8 ? len - i : 8;
-            if (n > (size_t)(RATE - pos)) n = (size_t)(RATE - pos);
-            const int off = pos & 7, sh = 8 * off;
-            uint64_t *l = st + LANES * (pos >> 3);
-            const bool straddle = off + (int)n > 8;
-            for (int j = 0; j < LANES; j++) {
-                const uint64_t x = load_le(d[j] + i, n);
-                l[j] ^= x << sh;
-                if (straddle) l[LANES + j] ^= x >> (64 - sh);
-            }
-            i += n;
-            pos = (uint8_t)(pos + n);
-            if (pos == RATE) run_f();
-        }
-    }
-    void overwrite_same(const uint8_t *d, size_t len) {
-        for (size_t i = 0; i < len; i++) {
-            const int sh = 8 * (pos & 7);
-            uint64_t *l = st + LANES * (pos >> 3);
-            for (int j = 0; j < LANES; j++) l[j] = (l[j] & ~(0xffULL << sh)) | ((uint64_t)d[i] << sh);
-            if (++pos == RATE) run_f();
-        }
-    }
-    void squeeze_each(uint8_t *const d[LANES], size_t len) {
-        size_t i = 0;
-        while (i < len) {
-            if ((pos & 7) == 0 && len - i >= 8 && pos + 8 <= RATE) {         // a whole lane: read it and clear it
-                uint64_t *l = st + LANES * (pos >> 3);
-                for (int j = 0; j < LANES; j++) { memcpy(d[j] + i, &l[j], 8); l[j] = 0; }
-                i += 8;
-                pos = (uint8_t)(pos + 8);
-            } else {
-                const int sh = 8 * (pos & 7);
-                uint64_t *l = st + LANES * (pos >> 3);
-                for (int j = 0; j < LANES; j++) { d[j][i] = (uint8_t)(l[j] >> sh); l[j] &= ~(0xffULL << sh); }
-                i++;
-                pos++;
-            }
-            if (pos == RATE) run_f();
-        }
-    }
-    void begin_op(uint8_t flags, bool more) {
-        if (more) return;
-        const uint8_t hdr[2] = {pos_begin, flags};
-        pos_begin = (uint8_t)(pos + 1);
-        cur_flags = flags;
-        absorb_same(hdr, 2);
-        if ((flags & (Strobe128::FC | Strobe128::FK)) && pos != 0) run_f();
-    }
-    void meta_ad_same(const uint8_t *d, size_t len, bool more) { begin_op(Strobe128::FM | Strobe128::FA, more); absorb_same(d, len); }
-    void ad_each(const uint8_t *const d[LANES], size_t len) { begin_op(Strobe128::FA, false); absorb_each(d, len); }
-    void key_same(const uint8_t *d, size_t len) { begin_op(Strobe128::FA | Strobe128::FC, false); overwrite_same(d, len); }
-    void prf_each(uint8_t *const d[LANES], size_t len) { begin_op(Strobe128::FI | Strobe128::FA | Strobe128::FC, false); squeeze_each(d, len); }
-};
 const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> &weight_transcript_init() {      // Transcript::new("Bulletproofs+ verifier weights") (:811)
     static const std::array<uint8_t, BPP_TRANSCRIPT_BYTES> wt0 = [] {
         std::array<uint8_t, BPP_TRANSCRIPT_BYTES> st;

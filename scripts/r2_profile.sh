@@ -11,3 +11,10 @@ echo "launch list rc=$?"; tail -25 gpurun_out/r2_ncu1.log | cut -c1-300
 $CMD > gpurun_out/r2_prof_plain2.json 2> gpurun_out/r2_prof_plain2.err && \
 ncu --set full --clock-control none --import-source on -k 'regex:k_msm_bucket_thread|k_decompress_proofs|k_replay_sm|k_vprep_vector|k_msm_reduce_warp|k_vprep_proof|k_msm_sort_seg|k_vprep_reduce' -s 120 -c 16 -o gpurun_out/r2_prof_full $CMD > gpurun_out/r2_ncu2.log 2>&1
 echo "set full rc=$?"; tail -5 gpurun_out/r2_ncu2.log | cut -c1-300; ls -la gpurun_out/r2_prof_full.ncu-rep gpurun_out/r2_launches.csv
+# prover: the fixed-base sum kernel of one 1024-proof call
+PCMD="python scripts/prove_lanes_probe.py 1024 1"
+$PCMD > gpurun_out/r2_prof_prove_plain.txt 2>&1 && \
+ncu --set full --clock-control none --import-source on -k 'regex:k_fb_msm|k_encode|k_prove_round_pre_fb' -s 40 -c 12 -o gpurun_out/r2_prof_prove $PCMD > gpurun_out/r2_ncu3.log 2>&1
+echo "prove set full rc=$?"; tail -3 gpurun_out/r2_ncu3.log | cut -c1-300
+ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 150 --csv --log-file gpurun_out/r2_launches_prove.csv $PCMD > gpurun_out/r2_ncu4.log 2>&1
+echo "prove launch list rc=$?"

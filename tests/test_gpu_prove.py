@@ -46,11 +46,11 @@ def rng_stream(tag, i, nbytes):
     return hashlib.shake_256(b"ext-rng-%s-%d" % (tag, i)).digest(nbytes)
 
 
-def oracle_prove(op, item, stream):
+def oracle_prove(op, item, stream, label=LABEL):
     vals, blinds, mins, commits, sn = item
     st = orc.St(op, commits, mins, sn)
     wit = orc.Wit(vals, blinds)
-    rc, pr, t_after = orc.prove(orc.transcript_new(LABEL), st, wit, orc.Rng("buffer", data=stream))
+    rc, pr, t_after = orc.prove(orc.transcript_new(label), st, wit, orc.Rng("buffer", data=stream))
     return rc, (orc.proof_to_bytes(pr) if rc == 0 else None), t_after
 
 
@@ -59,7 +59,7 @@ def oracle_prove(op, item, stream):
     (64, 2, 3, False, "none"), (32, 4, 1, False, "equal"), (4, 1, 6, True, "none"), (64, 1, 3, False, "third"),
 ])
 def test_proof_bytes_identical_to_oracle(n, m, ext, seeded, promise):
-    count = 5
+    count = 19          # two groups of eight through the lock-step host sponge (engine_prove.cu, Lock8) + three one at a time
     gp, op, items = make_inputs(n, m, ext, count, 1000 + n + 10 * m + ext, seeded, promise)
     need = api.RangeProof.rng_bytes_needed(gp, m)
     streams = [rng_stream(b"%d-%d-%d" % (n, m, ext), i, need) for i in range(count)]
@@ -81,6 +81,52 @@ def test_proof_bytes_identical_to_oracle(n, m, ext, seeded, promise):
             assert mk.blindings() == it[1][0]
         else:
             assert mk is None
+
+
+def test_lockstep_groups_fall_back_lane_by_lane():
+    """The host advances eight proofs per vectorised sponge only while the eight agree on everything that steers the transcript
+    (engine_prove.cu, Lock8::uniform).  Groups that do not -- mixed nonce sources, a transcript label of another length, a proof that
+    fails its checks -- take the one-at-a-time path; every proof still has the oracle's bytes, status and transcript."""
+    n, m, ext = 16, 1, 2
+    gp, op, seeded = make_inputs(n, m, ext, 32, 9001, True, "third")
+    _, _, plain = make_inputs(n, m, ext, 32, 9002, False, "none")
+    need = api.RangeProof.rng_bytes_needed(gp, m)
+    items, labels = [], []
+    for i in range(32):
+        g = i // 8
+        it = seeded[i] if (g == 0 or (g == 2 and i % 2)) else plain[i]         # group 0 seeded, 1 and 3 plain, 2 mixed
+        items.append(it)
+        labels.append(b"another label, longer" if i == 13 else LABEL)           # group 1: one transcript at another sponge position
+    vals, blinds, mins, commits, sn = items[27]                                 # group 3: one value below its promise
+    items[27] = (vals, blinds, [vals[0] + 1], commits, sn)
+    streams = [rng_stream(b"lk", i, need) for i in range(32)]
+    sts = [api.RangeStatement.init(gp, it[3], it[2], it[4]) for it in items]
+    wits = [api.RangeWitness.init([api.CommitmentOpening(v, b) for v, b in zip(it[0], it[1])]) for it in items]
+    trs = [api.Transcript(lb) for lb in labels]
+    got = api.RangeProof.prove_batch(trs, sts, wits, streams)
+    for i, it in enumerate(items):
+        rc, want, t_after = oracle_prove(op, it, streams[i], labels[i])
+        if rc:
+            assert i == 27 and isinstance(got[i], bpp.pkg.EngineError) and got[i].code == rc
+        else:
+            assert not isinstance(got[i], Exception), (i, got[i])
+            assert got[i].to_bytes() == want, i
+            assert trs[i].state == t_after, i
+
+
+def test_lockstep_off_gives_the_same_bytes():
+    """BPP_PROVE_LOCKSTEP=0: every proof through the one-at-a-time host sponge (the round-1 path)"""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("BPP_PROVE_LOCKSTEP") or os.environ.get("BPP_PROVE_FOLD"):
+        pytest.skip("already inside a variant run")
+    env = dict(os.environ, BPP_PROVE_LOCKSTEP="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_prove.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "identical_to_oracle or lane_by_lane"], env=env, capture_output=True, text=True, timeout=1200, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_single_prove_with_rng_object():

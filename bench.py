@@ -3,7 +3,7 @@
 
 Unit of work ("job") = BASELINE.json configs[1]: verify_batch of 1024 non-aggregated 64-bit proofs, issued as 4 reference calls
 of 256 (RangeProof::verify_batch looks at 256 proofs per call, /root/reference/src/range_proof.rs:739-751).  One STEP = `reps`
-independent jobs back to back (reps = ceil(2048 / steps), so that the K timed steps span >= 0.2 s whatever K the driver picks;
+independent jobs back to back (reps = ceil(4096 / steps), so that the K timed steps span >= 0.4 s whatever K the driver picks;
 `config.jobs_per_step`).
   value  : proofs/s with inputs resident in HBM.  Jobs are verified the way the engine's coalescing queue verifies them: `pass_jobs`
            jobs (16 x 1024 proofs = 64 reference calls) per device pass (bpp_vbatch_create_multi), `lanes` passes in flight.
@@ -40,7 +40,7 @@ UNIT = "proofs/s"
 BIT_LENGTH, EXT = 64, 1
 CHUNK = 256
 JOB = 1024
-TARGET_JOBS = 2048                    # jobs in the timed region (>= 0.2 s at 8 M proofs/s)
+TARGET_JOBS = 4096                    # jobs in the timed region (>= 0.4 s at 10 M proofs/s)
 # algorithmic 32x32->64 multiplies (field mul = 72, field square = 44, scalar Montgomery mul = 96 + 32)
 MUL32_FE_MUL, MUL32_FE_SQ = 72, 44
 MUL32_DECODE = 257 * MUL32_FE_SQ + 25 * MUL32_FE_MUL          # Ristretto decode + affine-Niels entry, per point
@@ -593,36 +593,66 @@ def run_b200(args, rank, local_rank, world):
     barrier()
 
     # ---------------- end-to-end arm (e2e): the coalescing queue with HOST buffers; jobs submitted from this thread
-    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=S, max_calls_per_pass=K, host_threads_per_lane=htl, device_weights=bool(args.device_weights))
-    n_slots = min(n_jobs, 2 * S * K)
+    # The queue hides a lane's host phases (building a pass: 12 MB of caller buffers parsed and staged, 17 % of a lane's time with 6 lanes;
+    # handing results back) behind the device work of the other lanes, so it wants more lanes than the device-resident arm: measured on a
+    # 16-core box 6 / 8 / 12 lanes -> 8.2 / 8.2-9.0 / 9.7 M proofs/s against 9.8 M device-resident.  Fewer on hosts with few cores per GPU.
+    per_rank = max(1, cores // world)
+    QS = max(1, args.queue_lanes or (12 if per_rank >= 12 else 8 if per_rank >= 6 else 6))
+    qhtl = args.host_threads_per_lane or max(1, min(2, (2 * per_rank) // QS))
+    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=QS, max_calls_per_pass=K, host_threads_per_lane=qhtl, device_weights=bool(args.device_weights))
+    n_slots = min(n_jobs, 2 * QS * K)
     slots = [q.pack(job_calls(q.shape, j % K), action) for j in range(n_slots)]
     t_init = bytes(slots[0].tbuf.raw)
     tickets = [None] * n_slots
 
-    def e2e_run(count):
+    n_sub = max(1, min(args.submitters, n_slots))        # submitting host threads (the queue takes calls from any number of threads)
+
+    def e2e_part(t, count):
+        mine = list(range(t, n_slots, n_sub))              # this thread's slots
         for j in range(count):
-            s = j % n_slots
+            s = mine[j % len(mine)]
             pk = slots[s]
             if tickets[s] is not None:
                 q.wait(tickets[s])
                 assert not any(pk.status[c] for c in range(pk.k)), list(pk.status)
                 C.memmove(pk.tbuf, t_init, len(t_init))          # `&mut Transcript`s were advanced by the call
             tickets[s] = q.submit(pk)
-        for s in range(n_slots):
+        for s in mine:
             if tickets[s] is not None:
                 q.wait(tickets[s])
                 assert not any(slots[s].status[c] for c in range(slots[s].k))
                 C.memmove(slots[s].tbuf, t_init, len(t_init))
                 tickets[s] = None
 
-    e2e_run(min(n_jobs, args.warmup * S * K))
+    def e2e_run(count):
+        if n_sub == 1:
+            return e2e_part(0, count)
+        errs = []
+
+        def body(t, c):
+            try:
+                e2e_part(t, c)
+            except BaseException as exc:                   # noqa: BLE001 - re-raised on the main thread
+                errs.append(exc)
+        ths = [threading.Thread(target=body, args=(t, count // n_sub + (1 if t < count % n_sub else 0))) for t in range(n_sub)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errs:
+            raise errs[0]
+
+    e2e_run(min(n_jobs, args.warmup * QS * K))
     barrier()
     qs0 = q.stats()
+    lm0 = q.lane_ms()
     t0 = time.perf_counter()
     e2e_run(n_jobs)                                      # returns after the last job's statuses and transcripts are back on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     qs1 = q.stats()
+    lm1 = q.lane_ms()
+    lane_share = {k: round((lm1[k] - lm0[k]) / (1e3 * e2e_s * QS), 3) for k in lm1}     # fraction of the timed region, mean over the lanes
     clocks = sampler.stop([win_dev, (t0, t0 + e2e_s)])
     barrier()
     # bytes one job moves (counted by the engine from the buffers it copies): one single-job call through the plain entry point
@@ -678,6 +708,7 @@ def run_b200(args, rank, local_rank, world):
         # 8.6 T/s on this pool's B200s); the low halves issue on the other FMA sub-pipe (IMAD.lo alone: 18.6 T/s).
         peak_ops, _ = eng.microbench(1, 2000)
         wide_ops, _ = eng.microbench(2, 2000)
+        pair_ops, _ = eng.microbench(12, 2000)
         alu_ops, _ = eng.microbench(3, 2000)
         c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
 
@@ -724,6 +755,7 @@ def run_b200(args, rank, local_rank, world):
                 "peak_source": "bpp_microbench, measured in this run: IMAD.HI issue rate (one per 32x32->64 product; the IMAD.lo half issues on the "
                                "other FMA sub-pipe); LOP3+IADD3 rate for the Keccak kernel.  MEASURED_PEAKS.json has no integer figure",
                 "imad_wide_tops": wide_ops / 1e12,
+                "imad_lo_hi_pairs_tops": pair_ops / 1e12,
                 "algorithmic_work_per_launch": work_pass[dominant],
                 "kernel_ms": dom["ms"], "launch_covers_proofs": K * JOB,
                 "whole_step": {"mul32_per_job": job_mul32, "ms_per_job_lanes_overlapped": ms_per_job,
@@ -745,15 +777,17 @@ def run_b200(args, rank, local_rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / dev_jobs * reps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
             "config": cfg, "host_cores": cores,
-            "engine": {"lanes_per_gpu": S, "jobs_per_device_pass": K, "host_threads_per_lane": htl,
+            "engine": {"lanes_per_gpu": S, "queue_lanes_per_gpu": QS, "queue_host_threads_per_lane": qhtl, "submitting_threads": n_sub,
+                       "jobs_per_device_pass": K, "host_threads_per_lane": htl,
                        "timed_jobs_per_gpu": dev_jobs, "timed_device_passes_per_gpu": n_pass,
                        "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay_sm)",
                        "verifier_weights": "device (k_weights), one graph launch per pass" if args.device_weights else "host threads (8-way Keccak) between two graph launches",
                        "workload_made_by": "device prover (bpp_prove_batch); K = %d distinct jobs per rank" % K},
             "e2e": {"value": world * n_jobs * JOB / e2e_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_s_max / args.steps,
                     "h2d_bytes_per_step": io_h2d * reps, "d2h_bytes_per_step": io_d2h * reps, "h2d_bytes_per_job": io_h2d, "d2h_bytes_per_job": io_d2h,
-                    "through": "bpp_vqueue_submit / bpp_vqueue_wait, one submitting thread per GPU, %d lanes, <= %d jobs per pass" % (S, K),
+                    "through": "bpp_vqueue_submit / bpp_vqueue_wait, %d submitting thread(s) per GPU, %d lanes with %d host threads each, <= %d jobs per pass" % (n_sub, QS, qhtl, K),
                     "queue": {k: qs1[k] - qs0[k] for k in qs1},
+                    "lane_time_share": lane_share,
                     "host_ms_per_pass_of_%d_jobs" % K: {"create_multi_wall": statistics.median(tc), **{k: round(v, 4) for k, v in hm.items()}},
                     "host_ms_one_job_call": {k: round(v, 4) for k, v in host_one.items()}},
             "one_batch_at_a_time": {"value": world * JOB / (seq_ms_max * 1e-3), "ms_per_job": seq_ms_max, "jobs": n_seq,
@@ -780,6 +814,8 @@ def main():
     ap.add_argument("--pass-jobs", type=int, default=16, help="1024-proof jobs merged into one device pass")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--submitters", type=int, default=2, help="host threads submitting calls to the end-to-end queue")
+    ap.add_argument("--queue-lanes", type=int, default=0, help="lanes of the end-to-end queue (0 = --lanes)")
     ap.add_argument("--device-weights", type=int, default=0, help="1: weight transcripts hashed on the device (k_weights), a pass is ONE graph launch")
     ap.add_argument("--host-threads-per-lane", type=int, default=0, help="0 = host cores / (lanes * ranks)")
     ap.add_argument("--extras", type=int, default=1, help="also measure proving and raw MSM throughput (secondary metrics)")

@@ -145,6 +145,7 @@ def lib():
         "bpp_vqueue_verify": (i32, [vp, P(VerifyArgs), vp, vp, vp]),
         "bpp_vqueue_stats": (i32, [vp, P(C.c_uint64)]),
         "bpp_vqueue_lanes": (i32, [vp]),
+        "bpp_vqueue_lane_ms": (i32, [vp, P(C.c_double)]),
         "bpp_vqueue_set_device_weights": (i32, [vp, i32]),
         "bpp_vbatch_transcripts": (i32, [vp, vp]),
         "bpp_vbatch_destroy": (None, [vp]),

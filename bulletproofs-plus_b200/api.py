@@ -529,6 +529,11 @@ class VerifyQueue:
             self.wait(t)
         return [pk.results() for pk in pks]
 
+    def lane_ms(self):
+        arr = (C.c_double * 4)()
+        _ffi.lib().bpp_vqueue_lane_ms(self.h, arr)
+        return dict(zip(("waiting_for_calls", "building_passes", "running_passes", "handing_back"), [float(x) for x in arr]))
+
     def stats(self):
         arr = (C.c_uint64 * 5)()
         _ffi.lib().bpp_vqueue_stats(self.h, arr)

@@ -97,6 +97,59 @@ __device__ __forceinline__ void mul256(uint32_t t[16], const uint32_t a[8], cons
     for (int i = 1; i < 14; i++) t[i + 1] = addc_cc(t[i + 1], odd[i]);
     t[15] = addc(t[15], 0);
 }
+// t[0..8) = a * b for 4-limb operands: the even / odd row scheme of mul256 on half the width (16 multiplies)
+__device__ __forceinline__ void mul128(uint32_t t[8], const uint32_t a[4], const uint32_t b[4]) {
+    uint32_t odd[6];
+    mul_n<4>(t, a, b[0]);
+    mul_n<4>(odd, a + 1, b[0]);
+    mad_row<4>(&t[2], &odd[0], a, b[1]);
+    mad_row<4>(&odd[2], &t[2], a, b[2]);
+    mad_row<4>(&t[4], &odd[2], a, b[3]);
+    t[1] = add_cc(t[1], odd[0]);
+#pragma unroll
+    for (int i = 1; i < 6; i++) t[i + 1] = addc_cc(t[i + 1], odd[i]);
+    t[7] = addc(t[7], 0);
+}
+// t[0..16) = a * b with one level of Karatsuba: 48 multiplies instead of 64 and ~45 more additions.  The multiplier pipe is what
+// bounds the field kernels (ncu: math-pipe throttle is their top stall; a 32x32->64 product issues about once per 5.5 cycles per
+// scheduler whether it is one IMAD.WIDE or a lo / hi pair, bpp_microbench 2 and 12) while the ALU pipe and the issue slots are half
+// idle, so trading 16 products for additions looked like a win.  MEASURED, NOT A WIN (kept behind -DBPP_KARATSUBA, bit-exact, all parity
+// tests pass with it): ptxas places the extra carry logic on the same FMA pipe (33 IMAD.MOV + 12 IMAD.X per multiplication, two issue
+// cycles each, next to the 16 saved IMAD.WIDE at ~5.6) and the longer live ranges spill under the occupancy cap of the bucket kernel:
+// k_msm_bucket_thread 0.544 -> 0.680 ms, k_msm_reduce_warp 0.199 -> 0.238 ms, 9.8 -> 8.7 M proofs/s.
+//   a = a0 + a1 W, b = b0 + b1 W (W = 2^128):  z0 = a0 b0, z2 = a1 b1, z1 = (a0 + a1)(b0 + b1) - z0 - z2,  a b = z0 + z1 W + z2 W^2
+// The half sums are 129 bits: with sa, sb their low 128 bits and ca, cb the carries, (a0 + a1)(b0 + b1) = sa sb + (ca sb + cb sa) W
+// + ca cb W^2, a 258-bit value kept as m[0..7] and m8 <= 3.
+__device__ __forceinline__ void mul256_k(uint32_t t[16], const uint32_t a[8], const uint32_t b[8]) {
+    uint32_t m[8], sa[4], sb[4];
+    mul128(t, a, b);
+    mul128(t + 8, a + 4, b + 4);
+    sa[0] = add_cc(a[0], a[4]); sa[1] = addc_cc(a[1], a[5]); sa[2] = addc_cc(a[2], a[6]); sa[3] = addc_cc(a[3], a[7]);
+    const uint32_t ca = addc(0, 0);
+    sb[0] = add_cc(b[0], b[4]); sb[1] = addc_cc(b[1], b[5]); sb[2] = addc_cc(b[2], b[6]); sb[3] = addc_cc(b[3], b[7]);
+    const uint32_t cb = addc(0, 0);
+    mul128(m, sa, sb);
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    m[4] = add_cc(m[4], sb[0] & ma); m[5] = addc_cc(m[5], sb[1] & ma); m[6] = addc_cc(m[6], sb[2] & ma); m[7] = addc_cc(m[7], sb[3] & ma);
+    uint32_t m8 = addc(ca & cb, 0);
+    m[4] = add_cc(m[4], sa[0] & mb); m[5] = addc_cc(m[5], sa[1] & mb); m[6] = addc_cc(m[6], sa[2] & mb); m[7] = addc_cc(m[7], sa[3] & mb);
+    m8 = addc(m8, 0);
+    m[0] = sub_cc(m[0], t[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) m[i] = subc_cc(m[i], t[i]);
+    m8 = subc(m8, 0);
+    m[0] = sub_cc(m[0], t[8]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) m[i] = subc_cc(m[i], t[8 + i]);
+    m8 = subc(m8, 0);
+    t[4] = add_cc(t[4], m[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[4 + i] = addc_cc(t[4 + i], m[i]);
+    t[12] = addc_cc(t[12], m8);
+    t[13] = addc_cc(t[13], 0);
+    t[14] = addc_cc(t[14], 0);
+    t[15] = addc(t[15], 0);
+}
 // t[0..16) = a^2 with 36 multiplies: the 28 off-diagonal products a_i * a_j (i < j) once, doubled by a funnel shift, plus the 8
 // diagonal squares.  Row i (multiplier a_i, elements a_{i+1..7}, first column 2i + 1) is split like the rows of mul256 into its
 // elements at even and at odd distance: each half is one pure carry chain (low half of element k + 2 lands right after the high
@@ -199,7 +252,9 @@ BPP_HD void sq256_any(uint32_t t[16], const uint32_t a[8]) {
 // Measured on B200 with by-value operands (gpurun r01b): hand-chained mad.cc core 104 G mul/s, compiler-scheduled
 // portable schoolbook 81 G mul/s -> the PTX core is the default; BPP_PORTABLE_MUL selects the other one.
 BPP_HD void mul256_any(uint32_t t[16], const uint32_t a[8], const uint32_t b[8]) {
-#if BPP_PTX && !defined(BPP_PORTABLE_MUL)
+#if BPP_PTX && !defined(BPP_PORTABLE_MUL) && defined(BPP_KARATSUBA)
+    ptx::mul256_k(t, a, b);
+#elif BPP_PTX && !defined(BPP_PORTABLE_MUL)
     ptx::mul256(t, a, b);
 #else
     mul256_portable(t, a, b);

@@ -9,6 +9,7 @@
 // masks and advanced transcripts back to that call's own buffers and signals its ticket.  Results are exactly those of
 // bpp_verify_chunks on every call alone (tests/test_gpu_queue.py).
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -35,7 +36,11 @@ struct QLane {
     bpp_ctx *ctx = nullptr;
     bpp_gens *gens = nullptr;
     std::thread th;
+    double ms[4] = {0, 0, 0, 0};          // wall time of this lane's thread: waiting for calls, building passes, running them, handing results back
 };
+inline double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
 
 } // namespace
 
@@ -59,12 +64,18 @@ static void run_pass(bpp_vqueue *q, QLane &lane, std::vector<QCall *> &batch) {
     std::vector<uint8_t *> mk(n), mp(n);
     for (size_t i = 0; i < n; i++) { ptrs[i] = &batch[i]->args; st[i] = batch[i]->chunk_status; mk[i] = batch[i]->masks32; mp[i] = batch[i]->mask_present; }
     bpp_vbatch *vb = nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     int32_t rc = bpp_vbatch_create_multi(lane.gens, n, ptrs.data(), &vb);
+    lane.ms[1] += ms_since(t0);
     if (rc == BPP_OK) {
+        t0 = std::chrono::steady_clock::now();
         rc = bpp_vbatch_run_multi(vb, st.data(), mk.data(), mp.data());
+        lane.ms[2] += ms_since(t0);
+        t0 = std::chrono::steady_clock::now();
         for (size_t i = 0; i < n && rc == BPP_OK; i++)
             if (batch[i]->args.transcripts) rc = bpp_vbatch_transcripts_call(vb, i, batch[i]->args.transcripts);
         bpp_vbatch_destroy(vb);
+        lane.ms[3] += ms_since(t0);
         for (QCall *c : batch) c->rc = rc;
     } else if (n == 1) {
         batch[0]->rc = rc;
@@ -87,8 +98,10 @@ static void lane_loop(bpp_vqueue *q, size_t li) {
     for (;;) {
         batch.clear();
         {
+            const auto t_idle = std::chrono::steady_clock::now();
             std::unique_lock<std::mutex> lk(q->mu);
             q->cv_work.wait(lk, [&] { return q->stopping || !q->pending.empty(); });
+            lane.ms[0] += ms_since(t_idle);
             if (q->pending.empty()) return;            // stopping and drained
             const int32_t action = q->pending.front()->args.action;
             while (!q->pending.empty() && batch.size() < q->max_calls && q->pending.front()->args.action == action) {
@@ -194,6 +207,14 @@ int32_t bpp_vqueue_stats(bpp_vqueue *q, uint64_t out5[5]) {
     uint64_t k = 0, g = 0;
     for (QLane &l : q->lanes) { k += bpp_ctx_launch_count(l.ctx); g += bpp_ctx_graph_launch_count(l.ctx); }
     out5[3] = k; out5[4] = g;
+    return BPP_OK;
+}
+
+int32_t bpp_vqueue_lane_ms(bpp_vqueue *q, double out4[4]) {
+    if (!q || !out4) return BPP_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(q->mu);
+    for (int k = 0; k < 4; k++) out4[k] = 0;
+    for (QLane &l : q->lanes) for (int k = 0; k < 4; k++) out4[k] += l.ms[k];
     return BPP_OK;
 }
 

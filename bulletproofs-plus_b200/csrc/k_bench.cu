@@ -30,6 +30,11 @@ template <int WHICH> __global__ void __launch_bounds__(MB_THREADS) k_mb_instr(in
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
                     asm volatile("add.u32 %0, %0, %1;" : "+r"(((uint32_t *)&y[k])[0]) : "r"(a));
                 }
+                if (WHICH == 12) {        // one 32x32 -> 64 product issued as its two halves (two self-dependent chains, nothing to hoist): do the
+                                          // lo and hi forms share a pipe?  Counted as pairs.
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(((uint32_t *)&y[k])[1]) : "r"(a), "r"(b));
+                }
                 if (WHICH == 11) {
                     asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y[k]) : "r"(x[k]), "r"(b));
                     asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(a));
@@ -138,6 +143,7 @@ int microbench_run(cudaStream_t s, int which, int iters, double *ops_per_sec, do
             case 2: k_mb_instr<2><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 8.0 * MB_ILP * iters; break;
             case 3: k_mb_instr<3><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2 * 8.0 * MB_ILP * iters; break;
             case 10: k_mb_instr<10><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2 * 8.0 * MB_ILP * iters; break;
+            case 12: k_mb_instr<12><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 8.0 * MB_ILP * iters; break;
             case 11: k_mb_instr<11><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2 * 8.0 * MB_ILP * iters; break;
             case 4: k_mb_field<4><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2.0 * iters; break;
             case 5: k_mb_field<5><<<MB_BLOCKS, MB_THREADS, 0, s>>>(iters, 1u, sink); ops_per_thread = 2.0 * iters; break;

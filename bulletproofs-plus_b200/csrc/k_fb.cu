@@ -14,6 +14,7 @@
 // Also exported on its own (bpp_gens_fixed_base_msm) as the static half of Precomputation::vartime_mixed_multiscalar_mul.
 #define BPP_INLINE_MUL
 #include <algorithm>
+#include <cstdlib>
 #include "kernels.cuh"
 #include "quad.cuh"
 
@@ -124,7 +125,7 @@ static __device__ __forceinline__ fe fb_shfl_down(const fe &v, int delta) {
 #define FB_MAXW 64          // c >= 4
 // One CTA of NW warps per segment; warp w takes the 32-entry chunks w, w + NW, ...  Scalars: canonical (< l), seg_len per segment,
 // segment-major.  gidx: generator index of every entry, `kinds` alternatives of seg_len each; segment s uses alternative s % kinds.
-template <int NW> __global__ void __launch_bounds__(32 * NW) k_fb_msm(uint32_t seg_len, uint32_t kinds, int c, int W, uint32_t B,
+template <int NW, int MIN_CTAS> __global__ void __launch_bounds__(32 * NW, MIN_CTAS) k_fb_msm(uint32_t seg_len, uint32_t kinds, int c, int W, uint32_t B,
                                                                      const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ gidx,
                                                                      const aniels *__restrict__ tab, ge *__restrict__ out) {
     __shared__ int16_t dig[NW][32][FB_MAXW + 2];
@@ -161,8 +162,11 @@ template <int NW> __global__ void __launch_bounds__(32 * NW) k_fb_msm(uint32_t s
         }
         __syncwarp();
         const uint32_t n_e = seg_len - e0 < 32u ? seg_len - e0 : 32u, items = n_e * (uint32_t)W;
+        // window-major item order: in a full chunk lane = entry and the iteration = window, so sparse scalar sets (the bit vectors of A:
+        // 0 / +-1, one non-zero digit per term) cost one addition time per chunk instead of one per (entry, window) pair that a lane
+        // happens to own; a short tail chunk still spreads its n_e * W items over all 32 lanes
         for (uint32_t it = lane; it < items; it += 32) {
-            const uint32_t el = it / (uint32_t)W, w = it - el * (uint32_t)W;
+            const uint32_t w = it / n_e, el = it - w * n_e;
             const int dg = dig[warp][el][w];
             if (dg != 0) {
                 const uint32_t mag = (uint32_t)(dg < 0 ? -dg : dg);
@@ -196,9 +200,11 @@ template <int NW> __global__ void __launch_bounds__(32 * NW) k_fb_msm(uint32_t s
 void launch_fb_msm(cudaStream_t s, const FbShape &sh, uint32_t n_seg, uint32_t seg_len, uint32_t kinds, const uint32_t *scalars, const uint32_t *gidx,
                    const aniels *tab, ge *out, uint64_t *launches) {
     if (n_seg == 0) return;
-    if (seg_len <= 256) k_fb_msm<1><<<n_seg, 32, 0, s>>>(seg_len, kinds, sh.c, sh.W, sh.B, scalars, gidx, tab, out);
-    else if (seg_len <= 1024) k_fb_msm<4><<<n_seg, 128, 0, s>>>(seg_len, kinds, sh.c, sh.W, sh.B, scalars, gidx, tab, out);
-    else k_fb_msm<8><<<n_seg, 256, 0, s>>>(seg_len, kinds, sh.c, sh.W, sh.B, scalars, gidx, tab, out);
+    // (register caps of 96 / 80 / 72 per thread -- 20 / 24 / 28 one-warp CTAs per SM -- were measured: 346 / 330 / 325 k proofs/s against
+    // 352 k with the 116 registers ptxas picks; the spills cost more than the extra warps hide)
+    if (seg_len <= 256) k_fb_msm<1, 1><<<n_seg, 32, 0, s>>>(seg_len, kinds, sh.c, sh.W, sh.B, scalars, gidx, tab, out);
+    else if (seg_len <= 1024) k_fb_msm<4, 1><<<n_seg, 128, 0, s>>>(seg_len, kinds, sh.c, sh.W, sh.B, scalars, gidx, tab, out);
+    else k_fb_msm<8, 1><<<n_seg, 256, 0, s>>>(seg_len, kinds, sh.c, sh.W, sh.B, scalars, gidx, tab, out);
     if (launches) (*launches)++;
 }
 

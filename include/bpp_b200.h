@@ -254,6 +254,9 @@ int32_t bpp_vqueue_wait(bpp_vqueue *q, uint64_t ticket);
 int32_t bpp_vqueue_verify(bpp_vqueue *q, const bpp_verify_args *args, int32_t *chunk_status, uint8_t *masks32, uint8_t *mask_present);
 int32_t bpp_vqueue_stats(bpp_vqueue *q, uint64_t out5[5]);
 int32_t bpp_vqueue_lanes(const bpp_vqueue *q);
+/* wall time of the lane threads since creation, summed over lanes, in ms: {waiting for calls, building passes (parse + staging),
+ * running them (device + weight hashing), handing results back}; read while idle */
+int32_t bpp_vqueue_lane_ms(bpp_vqueue *q, double out4[4]);
 /* where the verifier-weight transcripts (range_proof.rs:811-853, :894) of a pass are hashed: 0 = on the lane's host threads between two
  * graph launches (shortest pass), 1 = by k_weights on the device next to the scalar prep, the pass being ONE graph launch with no host
  * step in the middle (least host work per proof: what a host with few cores per GPU wants).  Call while the queue is idle. */

@@ -144,6 +144,8 @@ def lib():
         "bpp_vqueue_wait": (i32, [vp, C.c_uint64]),
         "bpp_vqueue_verify": (i32, [vp, P(VerifyArgs), vp, vp, vp]),
         "bpp_vqueue_stats": (i32, [vp, P(C.c_uint64)]),
+        "bpp_host_alloc": (i32, [C.c_size_t, P(vp)]),
+        "bpp_host_free": (None, [vp]),
         "bpp_vqueue_lanes": (i32, [vp]),
         "bpp_vqueue_lane_ms": (i32, [vp, P(C.c_double)]),
         "bpp_vqueue_set_device_weights": (i32, [vp, i32]),

@@ -350,8 +350,10 @@ class _PackedProve:
 class _Packed:
     """Flat host buffers for bpp_verify_args (kept alive for the duration of a call)."""
 
-    def __init__(self, params, calls, action):
+    def __init__(self, params, calls, action, pinned=False):
+        """pinned: the serialised proofs go into page-locked memory (bpp_host_alloc): the engine then uploads them without a staging copy"""
         self.params = params
+        self._pinned = None
         ext = params.gens.extension_degree
         chunk_offsets, proof_offsets, commit_offsets = [0], [0], [0]
         pbytes, commits, minv, minp, seeds, seedp, tstates = [], [], [], [], [], [], []
@@ -388,7 +390,17 @@ class _Packed:
         self.chunk_offsets = _u64arr(chunk_offsets)
         self.proof_offsets = _u64arr(proof_offsets)
         self.commit_offsets = _u64arr(commit_offsets)
-        self.proof_bytes = C.create_string_buffer(b"".join(pbytes), max(1, proof_offsets[-1]))
+        raw = b"".join(pbytes)
+        if pinned and raw:
+            ptr = C.c_void_p()
+            rc = _ffi.lib().bpp_host_alloc(len(raw), C.byref(ptr))
+            if rc:
+                raise EngineError(rc, "bpp_host_alloc")
+            self._pinned = ptr
+            C.memmove(ptr, raw, len(raw))
+            self.proof_bytes = (C.c_char * len(raw)).from_address(ptr.value)
+        else:
+            self.proof_bytes = C.create_string_buffer(raw, max(1, proof_offsets[-1]))
         self.commitments = C.create_string_buffer(b"".join(commits), max(1, 32 * len(commits)))
         self.min_values = _u64arr(minv)
         self.min_present = (C.c_uint8 * max(1, len(minp)))(*minp)
@@ -412,6 +424,14 @@ class _Packed:
         self.status = (C.c_int32 * max(1, self.k))()
         self.masks = C.create_string_buffer(max(1, 32 * n * ext))
         self.mask_present = C.create_string_buffer(max(1, n))
+
+    def __del__(self):
+        try:
+            if self._pinned is not None:
+                _ffi.lib().bpp_host_free(self._pinned)
+                self._pinned = None
+        except Exception:
+            pass
 
     def results(self, update_transcripts=True):
         if update_transcripts:
@@ -517,8 +537,8 @@ class VerifyQueue:
         if rc:
             raise EngineError(rc, "bpp_vqueue_wait")
 
-    def pack(self, calls, action):
-        return _Packed(self.shape, calls, action)
+    def pack(self, calls, action, pinned=False):
+        return _Packed(self.shape, calls, action, pinned=pinned)
 
     def verify_many(self, batches, action=VerifyAction.VerifyOnly):
         """batches: list of `calls` (each a list of (transcripts, statements, proofs)); all submitted at once, then waited for.

@@ -180,6 +180,16 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device) {
     ctx->replay_kernel = on_device == 2 ? 1 : on_device == 3 ? 2 : 0;
     return BPP_OK;
 }
+// page-locked host memory for callers (proof bytes placed here are uploaded without a staging copy, engine_verify.cu)
+int32_t bpp_host_alloc(size_t bytes, void **out) {
+    if (!out || !bytes) return BPP_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return BPP_ERR_CUDA; }
+    return BPP_OK;
+}
+void bpp_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
 int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable) {
     if (!ctx) return BPP_INVALID_ARGUMENT;
     ctx->use_graphs = enable != 0;

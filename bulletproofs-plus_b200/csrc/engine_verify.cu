@@ -57,11 +57,23 @@ struct HCall {
     const bpp_verify_challenges *ch = nullptr;
     size_t proof0 = 0, chunk0 = 0, commit0 = 0, raw0 = 0;      // first proof / chunk / commitment / raw byte of this call in the pass
     size_t raw_base = 0;              // a.proof_offsets[0]
+    bool raw_pinned = false;          // the call's proof bytes lie in page-locked memory: the copy engine reads them where they are
     bool same_transcripts = false;    // every transcript of the call holds the same state (one label for all proofs: the usual case)
     size_t ts0 = 0;                   // first uploaded transcript state of this call
 };
 
 inline bool is_zero32(const uint8_t *p) { return replay_is_zero32(p); }
+// [p, p + n) inside page-locked host memory (cudaHostAlloc / cudaHostRegister / bpp_host_alloc)?  Called on the thread that owns the ctx.
+bool host_range_pinned(const void *p, size_t n) {
+    static const bool off = [] { const char *e = getenv("BPP_NO_DIRECT_DMA"); return e && atoi(e) != 0; }();
+    if (off || !p || !n) return false;
+    cudaPointerAttributes at;
+    for (const uint8_t *q : {(const uint8_t *)p, (const uint8_t *)p + (n - 1)}) {
+        if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (at.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+}
 #define LBL(s) BPP_LBL(s)
 
 // utils/generic.rs:30-60
@@ -596,13 +608,21 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
 
     // ---- fill: the callers' byte arrays as they are, one memcpy each
     // (the callers' buffers are cold in the cache more often than not: one thread copies ~7 GB/s, so the calls are spread over the workers)
+    // Proof bytes that already lie in page-locked memory are not staged at all: the upload below reads them where they are (78 % of the
+    // bytes of a pass; on an 8-GPU host the staging copies of eight ranks were what saturated the host's memory system).
+    bool any_pinned = false;
+    for (HCall &call : vb->calls) {
+        const bpp_verify_args &a = call.a;
+        call.raw_pinned = a.n_proofs && host_range_pinned(a.proof_bytes + a.proof_offsets[0], a.proof_offsets[a.n_proofs] - a.proof_offsets[0]);
+        any_pinned = any_pinned || call.raw_pinned;
+    }
     ctx->workers().run(vb->calls.size(), 1, [&](size_t ci) {
         const HCall &call = vb->calls[ci];
         const bpp_verify_args &a = call.a;
         if (!a.n_proofs) return;
         const size_t raw_len = a.proof_offsets[a.n_proofs] - a.proof_offsets[0];
         const size_t c_lo = a.commit_offsets[0], c_n = a.commit_offsets[a.n_proofs] - c_lo;
-        memcpy(hb + vb->o_raw + call.raw0, a.proof_bytes + a.proof_offsets[0], raw_len);
+        if (!call.raw_pinned) memcpy(hb + vb->o_raw + call.raw0, a.proof_bytes + a.proof_offsets[0], raw_len);
         memcpy(hb + vb->o_commit + 32 * call.commit0, a.commitments32 + 32 * c_lo, 32 * c_n);
         memcpy(hb + vb->o_minv + 8 * call.commit0, a.min_values + c_lo, 8 * c_n);
         memcpy(hb + vb->o_minp + call.commit0, a.min_present + c_lo, c_n);
@@ -694,7 +714,33 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     if (host_replay) compute_weights(vb);
     lap();   // [3] weight transcripts (host mode; in device mode they run inside bpp_vbatch_run)
     cudaStream_t st = ctx->stream;
-    if (vb->blob_bytes) ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
+    if (vb->blob_bytes && !any_pinned) {
+        ok(cudaMemcpyAsync(w->d_blob.p, hb, vb->blob_bytes, cudaMemcpyHostToDevice, st));
+    } else if (vb->blob_bytes) {
+        // [descriptors .. commitments) and [transcript states .. end) from the staging blob, the raw proofs call by call from where they
+        // are (staged calls that follow each other travel as one copy)
+        uint8_t *db = w->d_blob.as<uint8_t>();
+        ok(cudaMemcpyAsync(db, hb, vb->o_raw, cudaMemcpyHostToDevice, st));
+        size_t run_lo = 0, run_len = 0;            // pending run of staged raw bytes, relative to o_raw
+        auto flush = [&]() {
+            if (run_len) ok(cudaMemcpyAsync(db + vb->o_raw + run_lo, hb + vb->o_raw + run_lo, run_len, cudaMemcpyHostToDevice, st));
+            run_len = 0;
+        };
+        for (const HCall &call : vb->calls) {
+            const bpp_verify_args &a = call.a;
+            if (!a.n_proofs) continue;
+            const size_t raw_len = a.proof_offsets[a.n_proofs] - a.proof_offsets[0];
+            if (call.raw_pinned) {
+                flush();
+                ok(cudaMemcpyAsync(db + vb->o_raw + call.raw0, a.proof_bytes + a.proof_offsets[0], raw_len, cudaMemcpyHostToDevice, st));
+            } else {
+                if (!run_len) run_lo = call.raw0;
+                run_len = call.raw0 + raw_len - run_lo;
+            }
+        }
+        flush();
+        if (vb->blob_bytes > vb->o_tstate) ok(cudaMemcpyAsync(db + vb->o_tstate, hb + vb->o_tstate, vb->blob_bytes - vb->o_tstate, cudaMemcpyHostToDevice, st));
+    }
     if (!vb->device_replay && n_chal) ok(cudaMemcpyAsync(w->d_chal.p, w->h_chal.p, 32 * (size_t)n_chal, cudaMemcpyHostToDevice, st));
     // The upload is ordered before the kernels of bpp_vbatch_run on the same stream and the pinned blob belongs to this vbatch's
     // workspace until bpp_vbatch_destroy (which drains the stream), so nothing needs the host to wait here (an upload error

@@ -12,6 +12,7 @@
 //                   32 proofs at 0.27 IPC (291 us for one warp's ~21 permutations, profiles/r01_ncu_summary.md).
 //   k_replay<false> the round-1 thread-per-proof kernel (hash.cuh Merlin, state in local memory), kept for comparison
 //   k_replay<true>  one warp per proof (wstrobe.cuh)
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "rawld.cuh"
 #include "replay.cuh"
@@ -92,12 +93,12 @@ constexpr int SM_STAGE = 51;
 constexpr int SM_TOTAL = 67;
 enum : uint32_t { FI = 1, FA = 2, FC = 4, FT = 8, FM = 16, FK = 32 };
 
-__constant__ char c_labels[] = "dom-sep\0H\0G\0N\0T\0M\0Ci\0vi - minimum_value\0A\0y\0z\0L\0R\0e\0A1\0B\0r1\0s1\0d1\0rng\0Bulletproofs+ Range Proof";
+__constant__ char c_labels[] = "dom-sep\0H\0G\0N\0T\0M\0Ci\0vi - minimum_value\0A\0y\0z\0L\0R\0e\0A1\0B\0r1\0s1\0d1\0rng\0Bulletproofs+ Range Proof\0proof";
 // (offset, length) of each label inside c_labels
 enum : uint32_t { LB_DOMSEP = 0 | 7 << 8, LB_H = 8 | 1 << 8, LB_G = 10 | 1 << 8, LB_N = 12 | 1 << 8, LB_T = 14 | 1 << 8, LB_M = 16 | 1 << 8,
                   LB_CI = 18 | 2 << 8, LB_VI = 21 | 18 << 8, LB_A = 40 | 1 << 8, LB_Y = 42 | 1 << 8, LB_Z = 44 | 1 << 8, LB_L = 46 | 1 << 8,
                   LB_R = 48 | 1 << 8, LB_E = 50 | 1 << 8, LB_A1 = 52 | 2 << 8, LB_B = 55 | 1 << 8, LB_R1 = 57 | 2 << 8, LB_S1 = 60 | 2 << 8,
-                  LB_D1 = 63 | 2 << 8, LB_RNG = 66 | 3 << 8, LB_PROTO = 70 | 25 << 8 };
+                  LB_D1 = 63 | 2 << 8, LB_RNG = 66 | 3 << 8, LB_PROTO = 70 | 25 << 8, LB_PROOF = 96 | 5 << 8 };
 
 struct SmPos { uint32_t pos, pos_begin, flags; };
 static __device__ __forceinline__ SmPos sm_get(const uint32_t *S) { const uint32_t t = S[50 * 32]; return SmPos{t & 0xffu, (t >> 8) & 0xffu, (t >> 16) & 0xffu}; }
@@ -426,10 +427,50 @@ __global__ void __launch_bounds__(32) k_weights(VDims d, const VChunk *__restric
     }
 }
 
+// The same with the shared-memory sponge of k_replay_sm: one THREAD per chunk (the chain is sequential whatever is done to it; a lone
+// warp runs a permutation in ~4.8 us with the state of 32 chunks in flight, the warp-cooperative form above needs ~13 us for one).
+// ~331 permutations per 256-proof chunk = ~1.6 ms, next to the decompression and the weight-free scalar prep of the same pass.
+__global__ void __launch_bounds__(32) k_weights_sm(VDims d, const VChunk *__restrict__ chunks, const uint8_t *__restrict__ wt_init,
+                                                  const uint8_t *__restrict__ wbytes, const uint8_t *__restrict__ flags, uint32_t *__restrict__ weights) {
+    __shared__ uint32_t s_state[SM_TOTAL * 32];
+    const uint32_t c = blockIdx.x * 32u + threadIdx.x;
+    if (c >= d.n_chunks) return;
+    const VChunk chk = chunks[c];
+    if (!chk.active) return;
+    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++)
+        if (flags[p] & 1) return;                         // loop 1 failed somewhere in the call: it ends there, no weights are drawn
+    uint32_t *S = s_state + threadIdx.x, *T = S + SM_STAGE * 32;
+    sm_load_state(S, wt_init);                            // Transcript::new("Bulletproofs+ verifier weights"), state from the host
+    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(wbytes + 32 * (size_t)p);
+        const uint4 a = src[0], b = src[1];
+        T[0] = a.x; T[32] = a.y; T[64] = a.z; T[96] = a.w; T[128] = b.x; T[160] = b.y; T[192] = b.z; T[224] = b.w;
+        sm_append(S, LB_PROOF, 32);
+    }
+    sm_rng_finalize_null(S);                              // build_rng().finalize(&mut NullRng)
+    for (uint32_t p = chk.proof_lo; p < chk.proof_hi; p++) {
+        sc w;
+        do {                                              // Scalar::random_not_zero (:894)
+            sm_challenge(S, 0xffffffffu, 16);
+            uint32_t ww[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) ww[i] = T[i * 32];
+            w = sc_from_wide_words(ww);
+        } while (sc_is_zero(w));
+        uint4 *dst = reinterpret_cast<uint4 *>(weights + 16 * (size_t)p);
+        dst[0] = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
+        dst[1] = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
+        dst[2] = make_uint4(0, 0, 0, 0);
+        dst[3] = make_uint4(0, 0, 0, 0);
+    }
+}
+
 void launch_weights(cudaStream_t s, const VDims &d, const VChunk *chunks, const uint8_t *wt_init, const uint8_t *wbytes, const uint8_t *flags,
                     uint32_t *weights, uint64_t *launches) {
     if (d.n_chunks == 0) return;
-    k_weights<<<d.n_chunks, 32, 0, s>>>(d, chunks, wt_init, wbytes, flags, weights);
+    static const bool warp_form = [] { const char *e = getenv("BPP_WEIGHTS_WARP"); return e && atoi(e) != 0; }();
+    if (warp_form) k_weights<<<d.n_chunks, 32, 0, s>>>(d, chunks, wt_init, wbytes, flags, weights);
+    else k_weights_sm<<<(d.n_chunks + 31) / 32, 32, 0, s>>>(d, chunks, wt_init, wbytes, flags, weights);
     if (launches) (*launches)++;
 }
 

@@ -181,7 +181,13 @@ int32_t bpp_pedersen_commit_batch(bpp_gens *g, size_t count, const uint64_t *val
  *                                      them in place exactly as `&mut Transcript` is in the reference (the split form
  *                                      reads them in create and hands the advanced states out via bpp_vbatch_transcripts)
  * Results: chunk_status[K] (bpp_status per reference call), masks32 (n x ext x 32) and mask_present (n) as
- * Vec<Option<ExtendedMask>>. */
+ * Vec<Option<ExtendedMask>>.
+ *
+ * proof_bytes in PAGE-LOCKED host memory (bpp_host_alloc, cudaHostAlloc, cudaHostRegister) are not staged: the copy engine reads them
+ * where they are, after the create / submit call has returned -- keep them valid and unchanged until the call's results are back
+ * (bpp_verify_chunks returned, bpp_vbatch_run returned, bpp_vqueue_wait returned).  Pageable buffers are copied inside create. */
+int32_t bpp_host_alloc(size_t bytes, void **out);
+void bpp_host_free(void *p);
 typedef struct {
     size_t n_proofs;
     size_t n_chunks;

@@ -149,6 +149,13 @@ extern "C" {
     pub fn bpp_vqueue_submit(q: *mut bpp_vqueue, args: *const bpp_verify_args, chunk_status: *mut i32, masks32: *mut u8, mask_present: *mut u8, ticket: *mut u64) -> i32;
     pub fn bpp_vqueue_wait(q: *mut bpp_vqueue, ticket: u64) -> i32;
     pub fn bpp_vqueue_verify(q: *mut bpp_vqueue, args: *const bpp_verify_args, chunk_status: *mut i32, masks32: *mut u8, mask_present: *mut u8) -> i32;
+    pub fn bpp_vqueue_stats(q: *mut bpp_vqueue, out5: *mut u64) -> i32;
+    pub fn bpp_vqueue_lanes(q: *const bpp_vqueue) -> i32;
+    pub fn bpp_vqueue_lane_ms(q: *mut bpp_vqueue, out4: *mut f64) -> i32;
+    pub fn bpp_vqueue_set_device_weights(q: *mut bpp_vqueue, enable: i32) -> i32;
+    /// page-locked host memory: proof bytes placed here are uploaded without a staging copy (keep them valid until the call's results are back)
+    pub fn bpp_host_alloc(bytes: usize, out: *mut *mut core::ffi::c_void) -> i32;
+    pub fn bpp_host_free(p: *mut core::ffi::c_void);
 
     // batched proving
     pub fn bpp_proof_size(extension_degree: i32, rounds: i32) -> usize;

@@ -84,6 +84,37 @@ def test_queue_matches_single_calls_and_oracle(lanes, max_calls):
         eng.close()
 
 
+def test_page_locked_proof_bytes_are_read_in_place():
+    """proof bytes in page-locked memory (bpp_host_alloc) are uploaded by the copy engine from where they are, pageable ones are staged;
+    one pass mixes both kinds (staged runs and direct copies interleave) and must give what separate staged calls give"""
+    case = workload.make_case(64, [1] * 16 + [2, 4] + [1] * 6, 1, max_aggregation=4, promise="third", rng_seed=4711)
+    specs = _make_batches(case, 12, 2, {3: 0, 7: 1, 8: 0})
+    q = api.VerifyQueue(0, 64, 4, 1, lanes=1, max_calls_per_pass=16)
+    try:
+        packed = [q.pack([_calls(q.shape, case, lo, hi, proofs)], api.VerifyAction.RecoverAndVerify, pinned=(i % 3 != 1))
+                  for i, (lo, hi, proofs, _, _, _) in enumerate(specs)]
+        tickets = [q.submit(pk) for pk in packed]
+        for t in tickets:
+            q.wait(t)
+        for pk, (lo, hi, proofs, rc, want, ts) in zip(packed, specs):
+            status, masks = pk.results()
+            assert status == [rc]
+            if rc == 0:
+                for g, w in zip(masks[0], want):
+                    assert (g is None) == (w is None) and (g is None or g.blindings() == w)
+            for t, o in zip(pk.transcripts, ts):
+                assert t.state == o
+        # and through the plain entry point
+        pk = q.pack([_calls(q.shape, case, 0, 6)], api.VerifyAction.VerifyOnly, pinned=True)
+        eng = bpp.pkg.Engine(0)
+        params = api.RangeParameters.init(eng, 64, 4, 1)
+        assert ffi.lib().bpp_verify_chunks(params.gens.h, C.byref(pk.args), pk.status, pk.masks, pk.mask_present) == 0
+        assert list(pk.status)[:1] == [0]
+        eng.close()
+    finally:
+        q.close()
+
+
 def test_queue_mixed_actions_and_many_threads():
     import threading
 

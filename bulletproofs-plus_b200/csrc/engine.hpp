@@ -53,7 +53,7 @@ struct bpp_ctx {
     cudaEvent_t ev_done = nullptr;      // end of a pass; polled between short sleeps in throughput mode
     long nap_ns = 60000;                // sleep between event polls in throughput mode (BPP_NAP_US)
     bool throughput_mode = false;       // sleeping polls instead of spinning: see bpp_ctx_set_throughput_mode
-    bool adaptive_wait = false;         // BPP_ADAPTIVE_WAIT=1: first sleep of a wait = 3/4 of what the same wait took last time (see wait_sleeping)
+    bool adaptive_wait = false;         // BPP_ADAPTIVE_WAIT=1: first sleep of a wait = 3/4 of what the same wait took last time, longer naps after it (wait_sleeping)
     double wait_ema_ns[2] = {0, 0};     // running estimate of the two waits of a pass (replay results, end of pass)
     uint32_t test_hooks = 0;            // bpp_ctx_set_test_hooks: bit 0 = repeat every pass through the zero-weight fallback
     bool scalar_weights = false;        // test hook (BPP_SCALAR_WEIGHTS=1): one weight transcript at a time instead of four in lock-step

@@ -775,30 +775,38 @@ int32_t bpp_vbatch_create_multi(bpp_gens *g, size_t n_calls, const bpp_verify_ar
     return vbatch_create_impl(g, n_calls, calls, nullptr, out);
 }
 
-// Wait for an event without spinning and without the driver's blocking-sync machinery: poll it between short sleeps.  Measured per
+// Wait for an event without spinning and without the driver's blocking-sync machinery: poll it between sleeps.  Measured per
 // 1024-proof pass (one lane, scripts/e2e_cpu_cost.py): cudaEventBlockingSync waits cost the process ~0.24 ms of CPU in driver
 // threads on top of the calling thread's own work; a spin wait costs the whole pass (1 ms).
-// Option (BPP_ADAPTIVE_WAIT=1, `ema_ns` != nullptr): `ema_ns` remembers how long this wait took recently and the first sleep covers
-// 3/4 of that in one go (an overshoot pulls the estimate down by 30 %).
-static cudaError_t wait_sleeping(cudaEvent_t ev, long nap_ns, double *ema_ns) {
+// Option (BPP_ADAPTIVE_WAIT=1, `ema_ns` != nullptr): `ema_ns` remembers how long this wait took recently, the first sleep covers 3/4
+// of that in one go and the naps after it are 1/20 of it (~6 wake-ups per pass instead of ~220).  MEASURED, NOT A WIN: passes of a
+// busy queue vary too much for the estimate (oversleeping holds results back): 8.1 / 7.8 M proofs/s end to end against 9.6 / 9.7 M with
+// fixed 60 us naps (4 / 16 host cores); the fixed naps cost little -- two host cores sustain 8.8 M proofs/s with device-side weights.
+// The estimate is kept per proof of the pass (floor: 1024 proofs, below that a pass is its latency chains whatever it holds), so that a
+// small pass after large ones is not overslept.
+static cudaError_t wait_sleeping(cudaEvent_t ev, long nap_ns, double *ema_ns, size_t n_proofs) {
     cudaError_t e = cudaEventQuery(ev);
     if (e != cudaErrorNotReady) { if (ema_ns) *ema_ns *= 0.7; return e; }
     const auto t0 = std::chrono::steady_clock::now();
-    if (ema_ns && *ema_ns > 4.0 * (double)nap_ns) {
-        const long ns = (long)(0.75 * *ema_ns);
+    const double scale = (double)std::max<size_t>(n_proofs, 1024);
+    const double est = ema_ns ? *ema_ns * scale : 0.0;
+    long nap = nap_ns;
+    if (ema_ns && est > 4.0 * (double)nap_ns) {
+        const long ns = (long)(0.75 * est);
         timespec ts = {ns / 1000000000L, ns % 1000000000L};
         nanosleep(&ts, nullptr);
         e = cudaEventQuery(ev);
         if (e != cudaErrorNotReady) { *ema_ns *= 0.7; return e; }
+        nap = std::max(nap_ns, (long)(0.05 * est));
     }
     for (;;) {
-        timespec ts = {0, nap_ns};
+        timespec ts = {nap / 1000000000L, nap % 1000000000L};
         nanosleep(&ts, nullptr);
         e = cudaEventQuery(ev);
         if (e != cudaErrorNotReady) break;
     }
     if (ema_ns) {
-        const double el = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+        const double el = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / scale;
         *ema_ns = *ema_ns > 0 ? 0.75 * *ema_ns + 0.25 * el : el;
     }
     return e;
@@ -1019,7 +1027,7 @@ int32_t bpp_vbatch_run_multi(bpp_vbatch *vb, int32_t *const *chunk_status, uint8
         }
         BPP_CUDA(ctx, cudaGraphLaunch(vg->ex[1], st));
         if (dev_replay) {       // the host hashes the weight transcripts while the device runs section B
-            if (ctx->throughput_mode) BPP_CUDA(ctx, wait_sleeping(ctx->ev_mid, ctx->nap_ns, ctx->adaptive_wait ? &ctx->wait_ema_ns[0] : nullptr));
+            if (ctx->throughput_mode) BPP_CUDA(ctx, wait_sleeping(ctx->ev_mid, ctx->nap_ns, ctx->adaptive_wait ? &ctx->wait_ema_ns[0] : nullptr, n));
             else BPP_CUDA(ctx, cudaEventSynchronize(ctx->ev_mid));
             auto tw = std::chrono::steady_clock::now();
             compute_weights(vb);
@@ -1076,7 +1084,7 @@ int32_t bpp_vbatch_run_multi(bpp_vbatch *vb, int32_t *const *chunk_status, uint8
     }
     if (ctx->throughput_mode) {         // sleep until the pass is done: with many lanes per GPU spinning threads starve each other
         BPP_CUDA(ctx, cudaEventRecord(ctx->ev_done, st));
-        BPP_CUDA(ctx, wait_sleeping(ctx->ev_done, ctx->nap_ns, ctx->adaptive_wait ? &ctx->wait_ema_ns[1] : nullptr));
+        BPP_CUDA(ctx, wait_sleeping(ctx->ev_done, ctx->nap_ns, ctx->adaptive_wait ? &ctx->wait_ema_ns[1] : nullptr, n));
     } else {
         BPP_CUDA(ctx, cudaStreamSynchronize(st));
     }

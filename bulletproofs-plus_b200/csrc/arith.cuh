@@ -268,6 +268,8 @@ BPP_HD fe fe_from_u32(uint32_t x) { fe r = fe_zero(); r.v[0] = x; return r; }
 
 #define BPP_FE(a0, a1, a2, a3, a4, a5, a6, a7) fe{{a0, a1, a2, a3, a4, a5, a6, a7}}
 BPP_HD fe fe_const_d() { return BPP_FE(0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu); }
+BPP_HD fe fe_const_inv_d() { return BPP_FE(0xcdc9f843u, 0x25e0f276u, 0x4279542eu, 0x0b5dd698u, 0xcdb9cf66u, 0x2b162114u, 0x14d5ce43u, 0x40907ed2u); }          // 1/d
+BPP_HD fe fe_const_neg_inv_d() { return BPP_FE(0x323607aau, 0xda1f0d89u, 0xbd86abd1u, 0xf4a22967u, 0x32463099u, 0xd4e9deebu, 0xeb2a31bcu, 0x3f6f812du); }     // -1/d
 BPP_HD fe fe_const_2d() { return BPP_FE(0x26b2f159u, 0xebd69b94u, 0x8283b156u, 0x00e0149au, 0xeef3d130u, 0x198e80f2u, 0x56dffce7u, 0x2406d9dcu); }
 BPP_HD fe fe_const_sqrtm1() { return BPP_FE(0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u); }
 BPP_HD fe fe_const_invsqrt_a_minus_d() { return BPP_FE(0x805d40eau, 0x99c8fdaau, 0x5a4172beu, 0x9d2f1617u, 0xfe01d840u, 0x16c27b91u, 0xcfaffca2u, 0x786c8905u); }

@@ -571,6 +571,32 @@ static __device__ __forceinline__ void bucket_add_entry(fe &X, fe &Y, fe &Z, fe 
     X = fe_mul(E, F); Y = fe_mul(G, H); Z = fe_mul(F, G); T = fe_mul(E, H);
 }
 
+// (X : Y : Z : T) = +-Q for the FIRST entry of a bucket: adding to the identity needs no addition formula.  With (y+x, y-x, 2dxy[, 2Z])
+// of Q:  X = (y+x) - (y-x) = 2x, Y = 2y, Z = 2 (or 2Z), and T with T Z = X Y is 2xy = (2dxy) / d -- ONE multiplication by the constant
+// 1/d instead of the seven of a mixed addition (the verifier's buckets hold ~16.5 entries: 1/16 of the bucket kernel's additions).
+// -Q swaps y+x and y-x and takes -1/d.  Results are tight (< 2^255) as the callers expect of an accumulator that may be stored as it is.
+static __device__ __forceinline__ void bucket_first_entry(fe &X, fe &Y, fe &Z, fe &T, uint32_t e, const uint32_t *__restrict__ pidx,
+                                                          const aniels *__restrict__ dyn, const aniels *__restrict__ gens,
+                                                          const cached *__restrict__ dync) {
+    const uint32_t idx = e & 0x7fffffffu;
+    const uint32_t pi = pidx ? pidx[idx] : idx;
+    const bool neg = (e >> 31) != 0;
+    const fe *qm, *qp, *qt;
+    if ((pi & 0xc0000000u) == 0x40000000u) {
+        const cached *src = dync + (pi & 0x3fffffffu);
+        qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
+        Z = ld_fe(&src->z2);
+    } else {
+        const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
+        qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
+        Z = fe_from_u32(2u);
+    }
+    const fe a = ld_fe(neg ? qm : qp), b = ld_fe(neg ? qp : qm);
+    X = fe_sub(a, b);
+    Y = fe_add(a, b);
+    T = fe_mul(ld_fe(qt), neg ? fe_const_neg_inv_d() : fe_const_inv_d());
+}
+
 // Global size order of the buckets.  k_msm_bucket_thread used to rank the 256 buckets of a CTA among themselves: the lanes of a warp
 // then walk buckets of neighbouring sizes, but the CTA lives as long as its largest bucket while most of its warps have left (the
 // verifier's buckets hold 16.5 +- 4 entries: 8..28 inside every CTA; ncu: 27 % achieved occupancy, FMA pipe active 40 % of the
@@ -646,7 +672,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_
         const uint32_t total = counts ? counts[item.x] : starts[item.x + 1] - starts[item.x];
         const uint32_t lo = starts[item.x] + item.y * part_size, cnt = min(part_size, total - item.y * part_size);
         fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
-        for (uint32_t j = 0; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
+        if (cnt) bucket_first_entry(X, Y, Z, T, sorted[lo], pidx, dyn, gens, dync);
+        for (uint32_t j = 1; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
         ge *w = parts + it;
         st_fe(&w->X, X); st_fe(&w->Y, Y); st_fe(&w->Z, Z); st_fe(&w->T, T);
         return;
@@ -683,7 +710,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_msm_bucket_thread(uint32_t n_
     uint32_t cnt = counts ? counts[k] : starts[k + 1] - lo;
     if (heavy_min && cnt > heavy_min) cnt = 0u;          // left to the part threads above and k_msm_heavy_finish
     fe X = fe_zero(), Y = fe_one(), Z = fe_one(), T = fe_zero();
-    for (uint32_t j = 0; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
+    if (cnt) bucket_first_entry(X, Y, Z, T, sorted[lo], pidx, dyn, gens, dync);
+    for (uint32_t j = 1; j < cnt; j++) bucket_add_entry(X, Y, Z, T, sorted[lo + j], pidx, dyn, gens, dync);
     cached *out = buckets + k;
     st_fe(&out->ymx, fe_sub_l(Y, X));
     st_fe(&out->ypx, fe_add_l(Y, X));

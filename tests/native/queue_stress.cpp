@@ -71,7 +71,10 @@ struct Call {
     std::vector<int32_t> status;
     bpp_verify_args a;
     int bad_chunk = -1;
-    Call(const Workload &w, size_t first, size_t chunks, size_t per, int corrupt) {
+    void *pinned = nullptr;          // proof bytes in page-locked memory: uploaded in place by the engine (no staging copy)
+    ~Call() { if (pinned) bpp_host_free(pinned); }
+    Call(const Call &) = delete;
+    Call(const Workload &w, size_t first, size_t chunks, size_t per, int corrupt, bool pin = false) {
         const size_t n = chunks * per;
         for (size_t c = 0; c <= chunks; c++) chunk_off.push_back(c * per);
         for (size_t i = 0; i <= n; i++) { proof_off.push_back(i * w.plen); commit_off.push_back(i); }
@@ -86,7 +89,9 @@ struct Call {
         if (corrupt >= 0) { proofs[w.plen * (size_t)corrupt + 1 + 32 * (EXT + 3) + 2] ^= 0x40; bad_chunk = (int)((size_t)corrupt / per); }
         status.assign(chunks, -1);
         memset(&a, 0, sizeof a);
-        a.n_proofs = n; a.n_chunks = chunks; a.chunk_offsets = chunk_off.data(); a.proof_bytes = proofs.data(); a.proof_offsets = proof_off.data();
+        const uint8_t *pb = proofs.data();
+        if (pin && bpp_host_alloc(proofs.size(), &pinned) == BPP_OK) { memcpy(pinned, proofs.data(), proofs.size()); pb = (const uint8_t *)pinned; }
+        a.n_proofs = n; a.n_chunks = chunks; a.chunk_offsets = chunk_off.data(); a.proof_bytes = pb; a.proof_offsets = proof_off.data();
         a.commitments32 = commits.data(); a.commit_offsets = commit_off.data(); a.min_values = mins.data(); a.min_present = present.data();
         a.transcripts = trs.data(); a.action = BPP_VERIFY_ONLY;
     }
@@ -101,10 +106,12 @@ int main(int argc, char **argv) {
     const int T = argc > 1 ? atoi(argv[1]) : 8, per_thread = argc > 2 ? atoi(argv[2]) : 24, L = argc > 3 ? atoi(argv[3]) : 8;
     Workload w = make_workload(256);
     std::atomic<int> failures{0};
-    // ---- 2. the coalescing queue
-    {
+    // ---- 2. the coalescing queue: host-side weight transcripts, then device-side ones (one graph per pass); a third of the calls keep
+    // their proof bytes in page-locked memory
+    for (int device_weights = 0; device_weights < 2; device_weights++) {
         bpp_vqueue *q = nullptr;
         CHECK(bpp_vqueue_create(0, N, 1, EXT, nullptr, nullptr, 3, 8, 1, &q));
+        CHECK(bpp_vqueue_set_device_weights(q, device_weights));
         std::vector<std::thread> ths;
         for (int t = 0; t < T; t++)
             ths.emplace_back([&, t]() {
@@ -113,7 +120,7 @@ int main(int argc, char **argv) {
                 for (int i = 0; i < per_thread; i++) {
                     const size_t chunks = 1 + (size_t)((t + i) % 3), per = 8 + 4 * (size_t)(i % 3);
                     const int corrupt = (i % 5 == 3) ? (int)((t * 7 + i) % (chunks * per)) : -1;
-                    calls.push_back(new Call(w, (size_t)(t * 31 + i * 13), chunks, per, corrupt));
+                    calls.push_back(new Call(w, (size_t)(t * 31 + i * 13), chunks, per, corrupt, (t + i) % 3 == 0));
                     uint64_t tk = 0;
                     if (i % 2) {
                         CHECK(bpp_vqueue_verify(q, &calls.back()->a, calls.back()->status.data(), nullptr, nullptr));
@@ -148,7 +155,7 @@ int main(int argc, char **argv) {
                 bpp_ctx_set_throughput_mode(ctx, t % 2);
                 CHECK(bpp_gens_create(ctx, N, 1, EXT, &g));
                 for (int i = 0; i < per_thread; i++) {
-                    Call c(w, (size_t)(t * 17 + i * 5), 1 + (size_t)(i % 4), 16, (i % 4 == 1) ? 3 : -1);
+                    Call c(w, (size_t)(t * 17 + i * 5), 1 + (size_t)(i % 4), 16, (i % 4 == 1) ? 3 : -1, i % 3 == 1);
                     CHECK(bpp_verify_chunks(g, &c.a, c.status.data(), nullptr, nullptr));
                     if (!c.ok()) failures++;
                 }

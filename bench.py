@@ -472,7 +472,7 @@ def run_b200(args, rank, local_rank, world):
         args.lanes = 8 if args.device_weights else 6
     S = max(1, args.lanes)
     htl = args.host_threads_per_lane or max(1, cores // (S * world))
-    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=True, device_weights=bool(args.device_weights))
+    pool = api.VerifierPool(local_rank, BIT_LENGTH, 1, EXT, lanes=S, host_threads_per_lane=htl, blocking_waits=True, device_weights=bool(args.device_weights), merged_check=bool(args.merged_check))
     eng, params = pool.lanes[0]
     FLUSH = int(os.environ.get("BPP_BENCH_FLUSH_MIB", "144")) << 20
     action = api.VerifyAction.VerifyOnly
@@ -533,6 +533,35 @@ def run_b200(args, rank, local_rank, world):
     launches = pool.launch_count() - launches0
     win_dev = (t_wall0, t_wall0 + t_wall)
     dev_jobs = n_pass * K
+
+    # the same arm with one multiscalar check per reference call (the library's default; the merged check is a queue / ctx option):
+    # a quarter of the passes, reported next to the headline as engine.per_call_check
+    per_call_ms = None
+    if args.merged_check:
+        for e, _ in pool.lanes:
+            e.set_merged_check(False)
+        main_vb = lane_vb
+        lane_vb = []
+        for (e, prm), pks in zip(pool.lanes, lane_pks):
+            ptrs = (C.c_void_p * K)(*[C.addressof(pk.args) for pk in pks])
+            vb = C.c_void_p()
+            assert lib.bpp_vbatch_create_multi(prm.gens.h, K, ptrs, C.byref(vb)) == 0
+            lane_vb.append((vb, (C.c_int32 * (K * (JOB // CHUNK)))()))
+        n_pass2 = max(4 * S, n_pass // 4)
+        pool.run(dev_pass, S * args.warmup)
+        barrier()
+        ev0.record()
+        pool.run(dev_pass, n_pass2)
+        torch.cuda.synchronize()
+        ev1.record()
+        ev1.synchronize()
+        per_call_ms = ev0.elapsed_time(ev1) / (n_pass2 * K)          # per job
+        barrier()
+        for vb, _ in lane_vb:
+            lib.bpp_vbatch_destroy(vb)
+        lane_vb = main_vb
+        for e, _ in pool.lanes:
+            e.set_merged_check(True)
 
     # ---------------- one job at a time on one lane (latency) and the per-kernel durations of a full pass / of one job
     eng.set_throughput_mode(0)                             # alone: spin-wait, all host threads of this rank's share
@@ -608,7 +637,7 @@ def run_b200(args, rank, local_rank, world):
     # 16-core box 6 / 8 / 12 lanes -> 8.2 / 8.2-9.0 / 9.7 M proofs/s against 9.8 M device-resident.  Fewer on hosts with few cores per GPU.
     QS = max(1, args.queue_lanes or (8 if args.device_weights else 12 if per_rank >= 12 else 8))
     qhtl = args.host_threads_per_lane or (1 if args.device_weights else max(1, min(2, (2 * per_rank) // QS)))
-    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=QS, max_calls_per_pass=K, host_threads_per_lane=qhtl, device_weights=bool(args.device_weights))
+    q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=QS, max_calls_per_pass=K, host_threads_per_lane=qhtl, device_weights=bool(args.device_weights), merged_check=bool(args.merged_check))
     n_slots = min(n_jobs, 2 * QS * K)
     pin = not args.pageable_inputs
     slots = [q.pack(job_calls(q.shape, j % K), action, pinned=pin) for j in range(n_slots)]      # proof bytes in page-locked host memory
@@ -718,11 +747,12 @@ def run_b200(args, rank, local_rank, world):
     barrier()
 
     # ---------------- reduce over ranks (max time)
-    times = torch.tensor([dev_ms, e2e_s, seq_ms, shot_ms, shot_e2e_ms, pass_ms] + e2e_regions, dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s, seq_ms, shot_ms, shot_e2e_ms, pass_ms] + e2e_regions + [per_call_ms or 0.0], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms_max, _, seq_ms_max, shot_ms_max, shot_e2e_ms_max, pass_ms_max = (float(x) for x in times[:6])
     e2e_regions_max = [float(x) for x in times[6:9]]
+    per_call_ms_max = float(times[9])
     e2e_s_max = sorted(e2e_regions_max)[1]
 
     # ---------------- roofline + cpu baseline (rank 0)
@@ -800,7 +830,13 @@ def run_b200(args, rank, local_rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / dev_jobs * reps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
             "config": cfg, "host_cores": cores,
-            "engine": {"lanes_per_gpu": S, "queue_lanes_per_gpu": QS, "queue_host_threads_per_lane": qhtl, "submitting_threads": n_sub, "e2e_proof_bytes_in": "pageable host memory, staged by the engine" if args.pageable_inputs else "page-locked host memory, read by the copy engine in place",
+            "engine": {"lanes_per_gpu": S, "queue_lanes_per_gpu": QS, "queue_host_threads_per_lane": qhtl, "submitting_threads": n_sub,
+                       "merged_check": ("on: ONE multiscalar check per device pass (sum over the pass's reference calls of rho_c x the call's own check, rho_c from "
+                                        "the call's weight transcript), settled call by call when it fails; per-call statuses are the reference's "
+                                        "(bpp_vqueue_set_merged_check, DESIGN.md 4.4)") if args.merged_check else "off: one multiscalar check per reference call",
+                       "per_call_check": ({"value": world * JOB / (per_call_ms_max * 1e-3), "unit": UNIT,
+                                           "note": "the device-resident arm with one multiscalar check per reference call (merged check off), a quarter of the passes"}
+                                          if per_call_ms_max else None), "e2e_proof_bytes_in": "pageable host memory, staged by the engine" if args.pageable_inputs else "page-locked host memory, read by the copy engine in place",
                        "jobs_per_device_pass": K, "host_threads_per_lane": htl,
                        "timed_jobs_per_gpu": dev_jobs, "timed_device_passes_per_gpu": n_pass,
                        "transcript_replay": "host threads" if os.environ.get("BPP_HOST_REPLAY", "0") not in ("", "0") else "device (k_replay_sm)",
@@ -838,6 +874,7 @@ def main():
     ap.add_argument("--pass-jobs", type=int, default=16, help="1024-proof jobs merged into one device pass")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--merged-check", type=int, default=1, help="1: one multiscalar check per device pass, call by call only when it fails (bpp_vqueue_set_merged_check)")
     ap.add_argument("--pageable-inputs", type=int, default=0, help="1: the e2e arm's proof bytes in pageable memory (staged by the engine)")
     ap.add_argument("--submitters", type=int, default=2, help="host threads submitting calls to the end-to-end queue")
     ap.add_argument("--queue-lanes", type=int, default=0, help="lanes of the end-to-end queue (0 = --lanes)")

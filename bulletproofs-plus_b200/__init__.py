@@ -113,8 +113,17 @@ class Engine:
         2: additionally verifier weights on the device, one graph per pass (measured slower; see include/bpp_b200.h)"""
         _chk(self, _ffi.lib().bpp_ctx_set_throughput_mode(self.h, int(enable)))
 
+    def set_merged_check(self, enable):
+        """one multiscalar check per pass (calls with two or more chunks), chunk by chunk only when it fails (bpp_ctx_set_merged_check)"""
+        _chk(self, _ffi.lib().bpp_ctx_set_merged_check(self.h, 1 if enable else 0))
+
+    @property
+    def merged_fallbacks(self):
+        return int(_ffi.lib().bpp_ctx_merged_fallbacks(self.h))
+
     def set_test_hooks(self, flags):
-        """bit 0: every verification pass is repeated through the zero-weight fallback (results must not change)"""
+        """bit 0: every verification pass is repeated through the zero-weight fallback; bit 1: a merged check is always followed by the
+        chunk-by-chunk pass (results must not change)"""
         _chk(self, _ffi.lib().bpp_ctx_set_test_hooks(self.h, int(flags)))
 
     @property

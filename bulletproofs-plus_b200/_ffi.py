@@ -149,6 +149,9 @@ def lib():
         "bpp_vqueue_lanes": (i32, [vp]),
         "bpp_vqueue_lane_ms": (i32, [vp, P(C.c_double)]),
         "bpp_vqueue_set_device_weights": (i32, [vp, i32]),
+        "bpp_vqueue_set_merged_check": (i32, [vp, i32]),
+        "bpp_ctx_set_merged_check": (i32, [vp, i32]),
+        "bpp_ctx_merged_fallbacks": (C.c_uint64, [vp]),
         "bpp_vbatch_transcripts": (i32, [vp, vp]),
         "bpp_vbatch_destroy": (None, [vp]),
         "bpp_ctx_set_replay_mode": (i32, [vp, i32]),

@@ -512,7 +512,7 @@ class VerifyQueue:
     (include/bpp_b200.h, csrc/engine_queue.cpp).  Results are those of verify_chunks on each call alone."""
 
     def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=3, max_calls_per_pass=16, host_threads_per_lane=0,
-                 h_base=None, g_bases=None, device_weights=False):
+                 h_base=None, g_bases=None, device_weights=False, merged_check=False):
         self.h = C.c_void_p()
         gb = b"".join(g_bases) if g_bases else None
         rc = _ffi.lib().bpp_vqueue_create(device, bit_length, max_aggregation, int(extension_degree), h_base, gb, lanes, max_calls_per_pass,
@@ -523,6 +523,8 @@ class VerifyQueue:
         self.shape = _QueueShape(bit_length, max_aggregation, int(extension_degree))
         if device_weights:
             _ffi.lib().bpp_vqueue_set_device_weights(self.h, 1)
+        if merged_check:
+            _ffi.lib().bpp_vqueue_set_merged_check(self.h, 1)
 
     def submit(self, packed):
         """packed: a _Packed kept alive by the caller until wait() returns"""
@@ -603,7 +605,7 @@ class VerifierPool:
     not depend on S (every batch is verified by the same code path as RangeProof.verify_batch)."""
 
     def __init__(self, device, bit_length, max_aggregation, extension_degree, lanes=8, host_threads_per_lane=None, blocking_waits=None,
-                 device_weights=False):
+                 device_weights=False, merged_check=False):
         import os
 
         from . import Engine
@@ -615,6 +617,7 @@ class VerifierPool:
         for _ in range(lanes):
             eng = Engine(device)
             eng.set_host_threads(per)
+            eng.set_merged_check(merged_check)
             eng.set_throughput_mode(2 if device_weights else 1 if blocking_waits else 0)   # lane threads sleep while their pass runs (bpp_ctx_set_throughput_mode)
             self.lanes.append((eng, RangeParameters.init(eng, bit_length, max_aggregation, extension_degree)))
 

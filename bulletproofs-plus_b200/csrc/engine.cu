@@ -87,6 +87,7 @@ int32_t bpp_ctx_create(int32_t device_ordinal, bpp_ctx **out) {
     if (const char *env = getenv("BPP_SCALAR_WEIGHTS")) ctx->scalar_weights = atoi(env) != 0;
     if (const char *env = getenv("BPP_NAP_US")) { long v = atol(env); if (v >= 1 && v <= 100000) ctx->nap_ns = v * 1000; }
     if (const char *env = getenv("BPP_ADAPTIVE_WAIT")) ctx->adaptive_wait = atoi(env) != 0;
+    if (const char *env = getenv("BPP_MERGED_CHECK")) ctx->merged_check = atoi(env) != 0;
     if (const char *env = getenv("BPP_THROUGHPUT_MODE")) { ctx->throughput_mode = atoi(env) != 0; ctx->device_weights = atoi(env) == 2; }
     *out = ctx;
     return BPP_OK;
@@ -202,6 +203,12 @@ int32_t bpp_ctx_set_throughput_mode(bpp_ctx *ctx, int32_t enable) {
     ctx->device_weights = enable == 2;
     return BPP_OK;
 }
+int32_t bpp_ctx_set_merged_check(bpp_ctx *ctx, int32_t enable) {
+    if (!ctx) return BPP_INVALID_ARGUMENT;
+    ctx->merged_check = enable != 0;
+    return BPP_OK;
+}
+uint64_t bpp_ctx_merged_fallbacks(const bpp_ctx *ctx) { return ctx ? ctx->merged_fallbacks : 0; }
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx) { return ctx ? ctx->graph_launches : 0; }
 int32_t bpp_ctx_set_test_hooks(bpp_ctx *ctx, uint32_t flags) {
     if (!ctx) return BPP_INVALID_ARGUMENT;

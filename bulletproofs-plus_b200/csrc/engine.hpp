@@ -57,6 +57,8 @@ struct bpp_ctx {
     double wait_ema_ns[2] = {0, 0};     // running estimate of the two waits of a pass (replay results, end of pass)
     uint32_t test_hooks = 0;            // bpp_ctx_set_test_hooks: bit 0 = repeat every pass through the zero-weight fallback
     bool scalar_weights = false;        // test hook (BPP_SCALAR_WEIGHTS=1): one weight transcript at a time instead of four in lock-step
+    bool merged_check = false;          // bpp_ctx_set_merged_check: one multiscalar check per PASS, chunk by chunk only when it fails (engine_verify.cu)
+    uint64_t merged_fallbacks = 0;      // passes whose merged check failed and were settled chunk by chunk
     bool device_weights = false;        // whole pass as ONE graph with the verifier-weight transcripts on the device (k_weights)
     bool device_replay = true;          // loop 1 (transcript replay) on the device (k_replay.cu) or on host threads
     int replay_kernel = 0;              // 0 = by batch size, 1 = one thread per proof, 2 = one warp per proof

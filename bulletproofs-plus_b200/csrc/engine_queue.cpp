@@ -225,6 +225,13 @@ int32_t bpp_vqueue_set_device_weights(bpp_vqueue *q, int32_t enable) {
     return BPP_OK;
 }
 
+int32_t bpp_vqueue_set_merged_check(bpp_vqueue *q, int32_t enable) {
+    if (!q) return BPP_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(q->mu);
+    for (QLane &l : q->lanes) bpp_ctx_set_merged_check(l.ctx, enable);
+    return BPP_OK;
+}
+
 int32_t bpp_vqueue_lanes(const bpp_vqueue *q) { return q ? (int32_t)q->lanes.size() : 0; }
 
 } // extern "C"

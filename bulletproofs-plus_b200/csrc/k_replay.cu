@@ -425,6 +425,18 @@ __global__ void __launch_bounds__(32) k_weights(VDims d, const VChunk *__restric
         } while (sc_is_zero(w));                          // warp-uniform
         if (lane < 16) weights[16 * (size_t)p + lane] = lane < 8 ? w.v[lane & 7] : 0u;
     }
+    if (d.merged) {                                       // rho_c of the merged check: the next value of the same rng
+        sc w;
+        do {
+            __align__(8) uint8_t wide[64];
+            wr.fill(wide, 64);
+            uint32_t ww[16];
+            for (int i = 0; i < 16; i++)
+                ww[i] = (uint32_t)wide[4 * i] | ((uint32_t)wide[4 * i + 1] << 8) | ((uint32_t)wide[4 * i + 2] << 16) | ((uint32_t)wide[4 * i + 3] << 24);
+            w = sc_from_wide_words(ww);
+        } while (sc_is_zero(w));
+        if (lane < 16) weights[16 * ((size_t)d.n_proofs + blockIdx.x) + lane] = lane < 8 ? w.v[lane & 7] : 0u;
+    }
 }
 
 // The same with the shared-memory sponge of k_replay_sm: one THREAD per chunk (the chain is sequential whatever is done to it; a lone
@@ -458,6 +470,21 @@ __global__ void __launch_bounds__(32) k_weights_sm(VDims d, const VChunk *__rest
             w = sc_from_wide_words(ww);
         } while (sc_is_zero(w));
         uint4 *dst = reinterpret_cast<uint4 *>(weights + 16 * (size_t)p);
+        dst[0] = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
+        dst[1] = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
+        dst[2] = make_uint4(0, 0, 0, 0);
+        dst[3] = make_uint4(0, 0, 0, 0);
+    }
+    if (d.merged) {                                       // rho_c of the merged check: the next value of the same rng
+        sc w;
+        do {
+            sm_challenge(S, 0xffffffffu, 16);
+            uint32_t ww[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) ww[i] = T[i * 32];
+            w = sc_from_wide_words(ww);
+        } while (sc_is_zero(w));
+        uint4 *dst = reinterpret_cast<uint4 *>(weights + 16 * ((size_t)d.n_proofs + c));
         dst[0] = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
         dst[1] = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
         dst[2] = make_uint4(0, 0, 0, 0);

@@ -438,7 +438,16 @@ __global__ void __launch_bounds__(128) k_vprep_weight(VDims d, VBuffers b) {
         ww[0] = q0.x; ww[1] = q0.y; ww[2] = q0.z; ww[3] = q0.w; ww[4] = q1.x; ww[5] = q1.y; ww[6] = q1.z; ww[7] = q1.w;
         ww[8] = q2.x; ww[9] = q2.y; ww[10] = q2.z; ww[11] = q2.w; ww[12] = q3.x; ww[13] = q3.y; ww[14] = q3.z; ww[15] = q3.w;
     }
-    const sc w = sc_to_mont(sc_from_wide_words(ww));
+    sc w = sc_to_mont(sc_from_wide_words(ww));
+    if (d.merged) {                  // merged check: every term of chunk c carries rho_c as well (a zero rho is flagged like a zero weight)
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.weights + 16 * ((size_t)d.n_proofs + pr.chunk));
+        const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+        ww[0] = q0.x; ww[1] = q0.y; ww[2] = q0.z; ww[3] = q0.w; ww[4] = q1.x; ww[5] = q1.y; ww[6] = q1.z; ww[7] = q1.w;
+        ww[8] = q2.x; ww[9] = q2.y; ww[10] = q2.z; ww[11] = q2.w; ww[12] = q3.x; ww[13] = q3.y; ww[14] = q3.z; ww[15] = q3.w;
+        const sc rho = sc_from_wide_words(ww);
+        if (sc_is_zero(rho)) { if (lane == 0) b.weight_zero[pr.chunk] = 1; }
+        else if (!sc_is_zero(w)) w = mm(w, sc_to_mont(rho));         // (a zero weight stays zero: k_vprep_reduce flags it)
+    }
     if (lane == 0) st_sc(b.weights_mont + 8 * (size_t)p, w);
     const uint32_t n_dyn = 3 + 2 * pr.rounds + pr.m;
     uint32_t *out = b.msm_scalars + 8 * (size_t)pr.entry_off;

@@ -74,6 +74,7 @@ struct VProof {            // per-proof metadata, device-resident
     uint32_t pt_off;       // first slot in the point table / encoding array: [A, A1, B, L_0.., R_0.., V_0..]
     uint32_t replay;       // 1 = its transcript is replayed (loop 1) and its scalars are prepared
     uint32_t ts_idx;       // which uploaded transcript state it starts from (calls whose transcripts are all equal upload ONE)
+    uint32_t chunk;        // the reference call (chunk) the proof belongs to
 };
 struct VChunk {
     uint32_t proof_lo, proof_hi;
@@ -81,7 +82,9 @@ struct VChunk {
     uint32_t entry_off;    // first MSM entry of the chunk: [Gi(max_mn) | Hi(max_mn) | G(ext) | H | dynamic...]
     uint32_t active;
 };
-struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext; int action; uint32_t gens_nm; };   // gens_nm = bit_length * max_aggregation
+// gens_nm = bit_length * max_aggregation; merged = 1: ONE multiscalar check for all chunks of the pass (engine_verify.cu, "merged check"):
+// chunk c's terms carry an extra factor rho_c, the wide value at weights[16 * (n_proofs + c)], drawn from the chunk's weight transcript
+struct VDims { uint32_t n_proofs, n_chunks, bit_length, ext; int action; uint32_t gens_nm; uint32_t merged; };
 // field offsets inside a serialised proof: [ext:u8] d1[ext] a a1 b r1 s1 (L_j R_j)*
 #define BPP_RAW_D1(ext, k) (1u + 32u * (k))
 #define BPP_RAW_A(ext) (1u + 32u * (ext))

@@ -79,7 +79,8 @@ int32_t bpp_ctx_set_replay_mode(bpp_ctx *ctx, int32_t on_device);
 int32_t bpp_ctx_set_graphs(bpp_ctx *ctx, int32_t enable);
 uint64_t bpp_ctx_graph_launch_count(const bpp_ctx *ctx);
 /* test hooks (results must not change): bit 0 = every verification pass is repeated through the zero-weight fallback (the path taken
- * when a batch weight reduces to zero and Scalar::random_not_zero would draw again, range_proof.rs:894) */
+ * when a batch weight reduces to zero and Scalar::random_not_zero would draw again, range_proof.rs:894); bit 1 = a merged check
+ * (bpp_ctx_set_merged_check) is always followed by the call-by-call pass */
 int32_t bpp_ctx_set_test_hooks(bpp_ctx *ctx, uint32_t flags);
 /* throughput mode (default 0), for callers that keep several verification calls in flight from several ctxs:
  *   1 = the calling thread sleeps between polls of its events (60 us naps, BPP_NAP_US) instead of spinning while the device works:
@@ -267,6 +268,17 @@ int32_t bpp_vqueue_lane_ms(bpp_vqueue *q, double out4[4]);
  * graph launches (shortest pass), 1 = by k_weights on the device next to the scalar prep, the pass being ONE graph launch with no host
  * step in the middle (least host work per proof: what a host with few cores per GPU wants).  Call while the queue is idle. */
 int32_t bpp_vqueue_set_device_weights(bpp_vqueue *q, int32_t enable);
+/* Merged check (off by default): ONE multiscalar check for all reference calls of a device pass instead of one per call.  The reference
+ * folds the <= 256 proofs of a call into one sum with random weights w_p drawn from the call's weight transcript (range_proof.rs:811-853,
+ * :894, :1050-1057); with this switch the call sums S_c of a pass are folded once more, sum_c rho_c S_c, rho_c being the next value of
+ * call c's own weight-transcript rng.  If the merged sum is the identity every call passed its check (a non-zero S_c survives with
+ * probability 2^-252, the reference's own argument one level up); otherwise -- some proof of the pass is invalid -- the pass is settled
+ * call by call with the same scalars, so every call's status is exactly what the reference returns for it.  It makes the pass ~15 %
+ * cheaper (one large sum uses 14-bit windows, 64 small ones 9-bit) and a pass that holds an invalid proof ~40 % dearer.
+ * bpp_ctx_set_merged_check does the same for bpp_verify_chunks / bpp_vbatch_* on a ctx (calls with two or more chunks). */
+int32_t bpp_vqueue_set_merged_check(bpp_vqueue *q, int32_t enable);
+int32_t bpp_ctx_set_merged_check(bpp_ctx *ctx, int32_t enable);
+uint64_t bpp_ctx_merged_fallbacks(const bpp_ctx *ctx);
 
 /* ---------------------------------------------------------------- batched proving
  * replaces P calls of RangeProof::prove_with_rng (range_proof.rs:232-608) for statements of ONE shape (same bit length,

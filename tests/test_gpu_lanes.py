@@ -100,7 +100,8 @@ print("child ok")
                                  {"BPP_MSM_BUCKET": "3", "BPP_MSM_SPLIT": "4"}, {"BPP_MSM_BUCKET": "3", "BPP_MSM_SPLIT": "8"}, {"BPP_MSM_REDUCE": "1"}, {"BPP_MSM_REDUCE": "1", "BPP_MSM_REDUCE_PARTS": "2"}, {"BPP_MSM_REDUCE": "1", "BPP_MSM_REDUCE_PARTS": "4"},
                                  {"BPP_MSM_REDUCE": "2"}, {"BPP_MSM_SCAN_SORT": "1"}, {"BPP_MSM_WINDOW_SORT": "1"}, {"BPP_MSM_LOCAL_RANK": "1"}, {"BPP_MSM_LOCAL_RANK": "1", "BPP_MSM_BUCKET": "2"}, {"BPP_MSM_SCAN_SORT": "1", "BPP_MSM_BUCKET": "1"}, {"BPP_VPREP_WARP": "100000"},
                                  {"BPP_VPREP_DIRECT": "1"}, {"BPP_NO_GRAPHS": "1"}, {"BPP_SCALAR_WEIGHTS": "1"},
-                                 {"BPP_THROUGHPUT_MODE": "2"}, {"BPP_THROUGHPUT_MODE": "2", "BPP_WEIGHTS_WARP": "1"}, {"BPP_NO_DIRECT_DMA": "1"}])
+                                 {"BPP_THROUGHPUT_MODE": "2"}, {"BPP_THROUGHPUT_MODE": "2", "BPP_WEIGHTS_WARP": "1"}, {"BPP_NO_DIRECT_DMA": "1"},
+                                 {"BPP_MERGED_CHECK": "1"}, {"BPP_MERGED_CHECK": "1", "BPP_THROUGHPUT_MODE": "2"}, {"BPP_MERGED_CHECK": "1", "BPP_MSM_SCAN_SORT": "1"}])
 def test_kernel_variants_match_oracle(env):
     e = dict(os.environ)
     e.update(env)

@@ -115,6 +115,31 @@ def test_page_locked_proof_bytes_are_read_in_place():
         q.close()
 
 
+@pytest.mark.parametrize("device_weights", [False, True])
+def test_queue_merged_check_gives_the_per_call_results(device_weights):
+    """merged check: one multiscalar check per device pass; a pass that holds an invalid proof is settled call by call -- statuses,
+    masks and transcripts are those of separate calls either way"""
+    case = workload.make_case(64, [1] * 16 + [2, 4] + [1] * 6, 1, max_aggregation=4, promise="third", rng_seed=4711)
+    for bad in ({}, {3: 0, 7: 1, 8: 0}):
+        specs = _make_batches(case, 12, 2, bad)
+        q = api.VerifyQueue(0, 64, 4, 1, lanes=1, max_calls_per_pass=16, merged_check=True, device_weights=device_weights)
+        try:
+            packed = [q.pack([_calls(q.shape, case, lo, hi, proofs)], api.VerifyAction.RecoverAndVerify) for lo, hi, proofs, _, _, _ in specs]
+            tickets = [q.submit(pk) for pk in packed]
+            for t in tickets:
+                q.wait(t)
+            for pk, (lo, hi, proofs, rc, want, ts) in zip(packed, specs):
+                status, masks = pk.results()
+                assert status == [rc]
+                if rc == 0:
+                    for g, w in zip(masks[0], want):
+                        assert (g is None) == (w is None) and (g is None or g.blindings() == w)
+                for t, o in zip(pk.transcripts, ts):
+                    assert t.state == o
+        finally:
+            q.close()
+
+
 def test_queue_mixed_actions_and_many_threads():
     import threading
 

@@ -17,7 +17,8 @@ _params_cache = {}
 
 
 @pytest.fixture(autouse=True, params=["device_replay_sm", "device_replay_warp", "device_replay_thread", "host_replay", "device_replay_no_graphs", "blocking_waits",
-                                      "device_weights", "zero_weight_fallback"])
+                                      "device_weights", "zero_weight_fallback", "merged_check", "merged_check_forced_fallback", "merged_check_device_weights",
+                                      "merged_check_zero_weight_fallback"])
 def replay_mode(request):
     """every test runs with loop 1 (the Merlin transcript replay) on the device (both kernels) and on host threads, and with the
     pass issued as captured CUDA graphs (default), kernel by kernel, with blocking waits, and as the single graph with the
@@ -25,11 +26,15 @@ def replay_mode(request):
     bpp.engine().set_replay_mode({"device_replay_warp": 3, "device_replay_thread": 2, "host_replay": 0}.get(request.param, 1))
     bpp.engine().set_graphs(request.param != "device_replay_no_graphs")
     # blocking waits; one graph per pass with the verifier weights drawn on the device
-    bpp.engine().set_throughput_mode({"blocking_waits": 1, "device_weights": 2}.get(request.param, 0))
+    bpp.engine().set_throughput_mode({"blocking_waits": 1, "device_weights": 2, "merged_check_device_weights": 2}.get(request.param, 0))
     # the path a zero batch weight takes (Scalar::random_not_zero redraws): forced, results unchanged
-    bpp.engine().set_test_hooks(1 if request.param == "zero_weight_fallback" else 0)
+    # merged check (one multiscalar check per call of several chunks, chunk by chunk only when it fails): alone, with the chunk-by-chunk
+    # pass forced, on top of device-side weights, and combined with the zero-weight path
+    bpp.engine().set_merged_check(request.param.startswith("merged_check"))
+    bpp.engine().set_test_hooks({"zero_weight_fallback": 1, "merged_check_forced_fallback": 2, "merged_check_zero_weight_fallback": 1}.get(request.param, 0))
     yield request.param
     bpp.engine().set_test_hooks(0)
+    bpp.engine().set_merged_check(False)
     bpp.engine().set_replay_mode(True)
     bpp.engine().set_graphs(True)
     bpp.engine().set_throughput_mode(False)

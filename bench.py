@@ -40,6 +40,8 @@ UNIT = "proofs/s"
 BIT_LENGTH, EXT = 64, 1
 CHUNK = 256
 JOB = 1024
+# per launch of the kernel over a 16-job pass, from profiles/r02_ncu_full_raw.csv (read + write)
+NCU_DRAM_BYTES_PER_LAUNCH = {"decompress": 11.2e6, "msm_bucket": 106.9e6}
 TARGET_JOBS = 4096                    # jobs in the timed region (>= 0.4 s at 10 M proofs/s)
 # algorithmic 32x32->64 multiplies (field mul = 72, field square = 44, scalar Montgomery mul = 96 + 32)
 MUL32_FE_MUL, MUL32_FE_SQ = 72, 44
@@ -763,16 +765,19 @@ def run_b200(args, rank, local_rank, world):
         wide_ops, _ = eng.microbench(2, 2000)
         pair_ops, _ = eng.microbench(12, 2000)
         alu_ops, _ = eng.microbench(3, 2000)
-        c_bits, W, B = 9, 28, 256                          # c = 9 -> ceil(252 / 9) = 28 windows of 256 buckets for 4226-entry segments
-
         def work_of(n_proofs):
+            # the multiscalar sums as they are executed: one per reference call (c = 9 -> 28 windows of 256 buckets for 4226-entry sums), or
+            # ONE per pass with the merged check (c = 14 at 270 k entries -> 19 windows of 8192 buckets)
             n_chunks = n_proofs // CHUNK
             n_pts = n_proofs * (3 + 2 * 6 + 1)
             entries = n_chunks * (2 * BIT_LENGTH + EXT + 1) + n_proofs * (3 + 2 * 6 + 1)
+            n_sums = 1 if (args.merged_check and n_chunks >= 2) else n_chunks
+            c_bits = lib.bpp_msm_window_bits(entries, n_sums) or 9
+            W, B = (252 + c_bits - 1) // c_bits, 1 << (c_bits - 1)
             return {"decompress": n_pts * MUL32_DECODE,
                     "msm_bucket": entries * W * MUL32_MADD,
-                    "msm_reduce": n_chunks * W * 2 * B * 9 * MUL32_FE_MUL,
-                    "msm_combine": n_chunks * (W - 1) * (c_bits * (4 * MUL32_FE_MUL + 4 * MUL32_FE_SQ) + 9 * MUL32_FE_MUL),
+                    "msm_reduce": n_sums * W * 2 * B * 9 * MUL32_FE_MUL,
+                    "msm_combine": n_sums * (W - 1) * (c_bits * (4 * MUL32_FE_MUL + 4 * MUL32_FE_SQ) + 9 * MUL32_FE_MUL),
                     "vprep_proof": n_proofs * (130 + 380) * 100,    # ~130 scalar products + one inversion (~380 at a^(l-2) cost), 100 mul32 each
                     "vprep_vector": n_proofs * (BIT_LENGTH * 4 + 3 * 14) * 100,      # 4 products per (proof, i) + three 8+8-entry tables
                     "vprep_weigh": (entries + n_proofs * 2 * BIT_LENGTH) * 100}
@@ -799,14 +804,16 @@ def run_b200(args, rank, local_rank, world):
         pk_job, _ = per_kernel_of(ph_job, JOB)
         dominant = max(work_pass, key=lambda k: work_pass[k] if k in pk_pass else -1)
         dom = pk_pass[dominant]
-        job_mul32 = sum(work_of(JOB).values())
+        job_mul32 = sum(work_of(K * JOB).values()) / K      # per job of a K-job pass (with the merged check a pass is one sum)
         ms_per_job = dev_ms_max / dev_jobs
         roof = {"bound": "int32-mul",
                 "bound_note": "int32-multiply issue rate (IMAD.HI, one per 32x32->64 product); the path is modular big-integer arithmetic, neither HBM- nor "
-                              "tensor-bound (north_star; DRAM traffic per 1024 proofs: a few MB, profiles/)",
+                              "tensor-bound (north_star; DRAM traffic per 1024 proofs: a few MB, profiles/).  A FULL product cannot be issued at that rate: "
+                              "IMAD.WIDE and a lo/hi pair both measure ~6 T/s (imad_wide_tops, imad_lo_hi_pairs_tops), so ~0.70-0.75 of this ceiling is the "
+                              "hardware limit for the arithmetic (DESIGN.md 4)",
                 "kernel": "k_" + dominant, "unit": dom.get("unit"), "achieved": dom.get("achieved"), "peak": dom.get("peak"), "frac": dom.get("frac"),
-                "peak_source": "bpp_microbench, measured in this run: IMAD.HI issue rate (one per 32x32->64 product; the IMAD.lo half issues on the "
-                               "other FMA sub-pipe); LOP3+IADD3 rate for the Keccak kernel.  MEASURED_PEAKS.json has no integer figure",
+                "peak_source": "bpp_microbench, measured in this run: IMAD.HI issue rate (round 1's denominator, kept so that the fractions stay "
+                               "comparable); LOP3+IADD3 rate for the Keccak kernel.  MEASURED_PEAKS.json has no integer figure",
                 "imad_wide_tops": wide_ops / 1e12,
                 "imad_lo_hi_pairs_tops": pair_ops / 1e12,
                 "algorithmic_work_per_launch": work_pass[dominant],
@@ -818,7 +825,10 @@ def run_b200(args, rank, local_rank, world):
                 "one_pass_alone": {"proofs": K * JOB, "ms": pass_ms_max, "frac": K * job_mul32 / (pass_ms_max * 1e-3) / peak_ops},
                 "per_kernel": pk_pass, "per_kernel_one_job_alone": pk_job,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
-                "traffic": None, "traffic_note": "see profiles/r02_ncu_summary.md",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dominant), "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel "
+                "over a 16-job pass, ncu --set full with flushed caches (profiles/r02_ncu_summary.md); algorithmic bytes: 8.4 MB of encodings in + 25 MB of "
+                "table entries out for the decompression (the table stays in L2 for the bucket sums), 30 MB of sorted entry lists + 25 MB of table + 20 MB of "
+                "bucket results for the bucket sums",
                 "hbm_peak_gbs_measured": hbm_peak}
         # CPU baseline beside it: the oracle on this box's cores, a bounded sample of the same workload
         threads = os.cpu_count() or 1

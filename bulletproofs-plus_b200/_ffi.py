@@ -123,6 +123,7 @@ def lib():
         "bpp_msm_plan_set_scalars": (i32, [vp, cp]),
         "bpp_msm_plan_run": (i32, [vp, cp]),
         "bpp_msm_plan_window_bits": (i32, [vp]),
+        "bpp_msm_window_bits": (i32, [C.c_size_t, C.c_size_t]),
         "bpp_msm_plan_destroy": (None, [vp]),
         "bpp_gens_create": (i32, [vp, i32, i32, i32, P(vp)]),
         "bpp_gens_destroy": (None, [vp]),

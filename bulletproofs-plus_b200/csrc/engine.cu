@@ -407,6 +407,11 @@ int32_t bpp_msm_plan_run(bpp_msm_plan *pl, uint8_t *out32_or_null) {
     return BPP_OK;
 }
 int32_t bpp_msm_plan_window_bits(const bpp_msm_plan *pl) { return pl ? pl->sh.c : 0; }
+// the window width the engine picks for n_seg sums over n_entries entries in all (what bench.py counts the work of a pass with)
+int32_t bpp_msm_window_bits(size_t n_entries, size_t n_seg) {
+    if (!n_entries || !n_seg || n_entries >= (1ull << 31) || n_seg >= (1ull << 31)) return 0;
+    return msm_shape((uint32_t)n_entries, (uint32_t)n_seg, 0).c;
+}
 void bpp_msm_plan_destroy(bpp_msm_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->ctx->device);

@@ -571,8 +571,8 @@ static __device__ __forceinline__ void bucket_add_entry(fe &X, fe &Y, fe &Z, fe 
     X = fe_mul(E, F); Y = fe_mul(G, H); Z = fe_mul(F, G); T = fe_mul(E, H);
 }
 
-// (X : Y : Z : T) = +-Q for the FIRST entry of a bucket: adding to the identity needs no addition formula.  With (y+x, y-x, 2dxy[, 2Z])
-// of Q:  X = (y+x) - (y-x) = 2x, Y = 2y, Z = 2 (or 2Z), and T with T Z = X Y is 2xy = (2dxy) / d -- ONE multiplication by the constant
+// (X : Y : Z : T) = +-Q for the FIRST entry of a bucket: adding to the identity needs no addition formula.  With (y+x, y-x, 2dxy)
+// of an affine Q:  X = (y+x) - (y-x) = 2x, Y = 2y, Z = 2, and T with T Z = X Y is 2xy = (2dxy) / d -- ONE multiplication by the constant
 // 1/d instead of the seven of a mixed addition (the verifier's buckets hold ~16.5 entries: 1/16 of the bucket kernel's additions).
 // -Q swaps y+x and y-x and takes -1/d.  Results are tight (< 2^255) as the callers expect of an accumulator that may be stored as it is.
 static __device__ __forceinline__ void bucket_first_entry(fe &X, fe &Y, fe &Z, fe &T, uint32_t e, const uint32_t *__restrict__ pidx,
@@ -581,16 +581,14 @@ static __device__ __forceinline__ void bucket_first_entry(fe &X, fe &Y, fe &Z, f
     const uint32_t idx = e & 0x7fffffffu;
     const uint32_t pi = pidx ? pidx[idx] : idx;
     const bool neg = (e >> 31) != 0;
-    const fe *qm, *qp, *qt;
-    if ((pi & 0xc0000000u) == 0x40000000u) {
-        const cached *src = dync + (pi & 0x3fffffffu);
-        qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
-        Z = ld_fe(&src->z2);
-    } else {
-        const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
-        qm = &src->ymx; qp = &src->ypx; qt = &src->t2d;
-        Z = fe_from_u32(2u);
+    if ((pi & 0xc0000000u) == 0x40000000u) {       // projective entries (the prover's folded generators) may hold loose values: the general addition
+        X = fe_zero(); Y = fe_one(); Z = fe_one(); T = fe_zero();
+        bucket_add_entry(X, Y, Z, T, e, pidx, dyn, gens, dync);
+        return;
     }
+    const aniels *src = (pi & 0x80000000u) ? (gens + (pi & 0x7fffffffu)) : (dyn + pi);
+    const fe *qm = &src->ymx, *qp = &src->ypx, *qt = &src->t2d;
+    Z = fe_from_u32(2u);
     const fe a = ld_fe(neg ? qm : qp), b = ld_fe(neg ? qp : qm);
     X = fe_sub(a, b);
     Y = fe_add(a, b);

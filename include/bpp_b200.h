@@ -140,6 +140,7 @@ int32_t bpp_msm_plan_create(bpp_ctx *ctx, size_t n, const uint8_t *points32, int
 int32_t bpp_msm_plan_set_scalars(bpp_msm_plan *plan, const uint8_t *scalars32);
 int32_t bpp_msm_plan_run(bpp_msm_plan *plan, uint8_t *out32_or_null);   /* async unless out32 given */
 int32_t bpp_msm_plan_window_bits(const bpp_msm_plan *plan);
+int32_t bpp_msm_window_bits(size_t n_entries, size_t n_seg);   /* the window width chosen for n_seg sums over n_entries entries in all */
 void bpp_msm_plan_destroy(bpp_msm_plan *plan);
 
 /* ---------------------------------------------------------------- generators

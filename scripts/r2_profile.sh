@@ -3,13 +3,15 @@
 # ONE pass in flight (--lanes 1): with several lane threads launching graphs concurrently the process dies inside ncu (SIGSEGV; round 1
 # saw glibc heap-corruption aborts in the same situation) while the same command without ncu, and under TSan / ASan, is clean.
 cd ${GRAFT_REPO_ROOT:-.}
+python -m pytest tests/test_gpu_prove.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 3 --extras 0 --lanes 8 > gpurun_out/r2_prof_l8.json 2>/dev/null; python scripts/r2_summary.py gpurun_out/r2_prof_l8.json 2>&1 | grep "^value"
 CMD="python -X faulthandler bench.py --steps 20 --warmup 3 --lanes ${PROF_LANES:-1} --extras 0"
 K='regex:k_replay|k_decompress|k_vprep|k_msm|k_encode|k_scan'
 $CMD > gpurun_out/r2_prof_plain.json 2> gpurun_out/r2_prof_plain.err && \
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k "$K" -s 200 -c 660 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu1.log 2>&1
 echo "launch list rc=$?"; tail -25 gpurun_out/r2_ncu1.log | cut -c1-300
 $CMD > gpurun_out/r2_prof_plain2.json 2> gpurun_out/r2_prof_plain2.err && \
-ncu --set full --clock-control none --import-source on -k 'regex:k_msm_bucket_thread|k_decompress_proofs|k_replay_sm|k_vprep_vector|k_msm_reduce_warp|k_vprep_proof|k_msm_sort_seg|k_vprep_reduce' -s 120 -c 12 -o gpurun_out/r2_prof_full $CMD > gpurun_out/r2_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:k_msm_bucket_thread|k_decompress_proofs|k_replay_sm|k_vprep_vector|k_msm_reduce|k_vprep_proof|k_msm_digits|k_vprep_weight' -s 160 -c 12 -o gpurun_out/r2_prof_full $CMD > gpurun_out/r2_ncu2.log 2>&1
 echo "set full rc=$?"; tail -5 gpurun_out/r2_ncu2.log | cut -c1-300; ls -la gpurun_out/r2_prof_full.ncu-rep gpurun_out/r2_launches.csv
 # gpurun brings back at most 64 MiB: export what the summaries need as CSV here, keep the report only while it fits
 ncu -i gpurun_out/r2_prof_full.ncu-rep --page raw --csv > gpurun_out/r2_prof_full_raw.csv 2>/dev/null
@@ -29,7 +31,3 @@ if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/r2_prof_full
 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 150 --csv --log-file gpurun_out/r2_launches_prove.csv $PCMD > gpurun_out/r2_ncu4.log 2>&1
 echo "prove launch list rc=$?"
 du -sm gpurun_out
-# the lock-step prover: parity tests + throughput
-python -m pytest tests/test_gpu_prove.py -m gpu -x -q 2>&1 | tail -5
-python scripts/prove_lanes_probe.py 8192 8 16 2>&1 | tail -4
-BPP_PROVE_LOCKSTEP=0 python scripts/prove_lanes_probe.py 8192 8 2>&1 | tail -2

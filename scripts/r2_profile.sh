@@ -3,9 +3,7 @@
 # ONE pass in flight (--lanes 1): with several lane threads launching graphs concurrently the process dies inside ncu (SIGSEGV; round 1
 # saw glibc heap-corruption aborts in the same situation) while the same command without ncu, and under TSan / ASan, is clean.
 cd ${GRAFT_REPO_ROOT:-.}
-python -m pytest tests/test_gpu_prove.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 --extras 0 --lanes 8 > gpurun_out/r2_prof_l8.json 2>/dev/null; python scripts/r2_summary.py gpurun_out/r2_prof_l8.json 2>&1 | grep "^value"
-CMD="python -X faulthandler bench.py --steps 20 --warmup 3 --lanes ${PROF_LANES:-1} --extras 0"
+CMD="python -X faulthandler bench.py --steps 20 --warmup 3 --lanes ${PROF_LANES:-1} --queue-lanes 1 --submitters 1 --extras 0"
 K='regex:k_replay|k_decompress|k_vprep|k_msm|k_encode|k_scan'
 $CMD > gpurun_out/r2_prof_plain.json 2> gpurun_out/r2_prof_plain.err && \
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k "$K" -s 200 -c 660 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu1.log 2>&1
@@ -17,6 +15,7 @@ echo "set full rc=$?"; tail -5 gpurun_out/r2_ncu2.log | cut -c1-300; ls -la gpur
 ncu -i gpurun_out/r2_prof_full.ncu-rep --page raw --csv > gpurun_out/r2_prof_full_raw.csv 2>/dev/null
 ncu -i gpurun_out/r2_prof_full.ncu-rep --page source --csv -k regex:k_msm_bucket_thread -c 1 > gpurun_out/r2_prof_bucket_source.csv 2>/dev/null
 ncu -i gpurun_out/r2_prof_full.ncu-rep --page details --csv > gpurun_out/r2_prof_full_details.csv 2>/dev/null
+if [ "${PROF_PROVER:-0}" = "1" ]; then
 # prover: the fixed-base sum kernel of one 1024-proof call
 PCMD="python scripts/prove_lanes_probe.py 1024 1"
 $PCMD > gpurun_out/r2_prof_prove_plain.txt 2>&1 && \
@@ -31,3 +30,4 @@ if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/r2_prof_full
 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 150 --csv --log-file gpurun_out/r2_launches_prove.csv $PCMD > gpurun_out/r2_ncu4.log 2>&1
 echo "prove launch list rc=$?"
 du -sm gpurun_out
+fi

@@ -1048,7 +1048,8 @@ void launch_msm(cudaStream_t s, const MsmShape &sh, const uint32_t *scalars, con
             perm = sc.perm;
             if (launches) *launches += 3;
         }
-        if (n_keys >= 200000)
+        static const size_t occ3_min = [] { const char *e = getenv("BPP_MSM_OCC3_MIN"); return e ? (size_t)atol(e) : (size_t)200000; }();
+        if (n_keys >= occ3_min)
             k_msm_bucket_thread<3><<<grid, 256, 0, s>>>((uint32_t)n_keys, sc.starts, counts, sc.sorted, pidx, dyn, gens, dync, sc.buckets, heavy_min, part_size,
                                                         sc.heavy_n, sc.heavy_items, sc.heavy_cap, sc.heavy_parts, perm);
         else

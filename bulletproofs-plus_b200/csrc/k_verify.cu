@@ -491,7 +491,10 @@ void launch_verify_prep(cudaStream_t s, const VDims &d, const VBuffers &b, uint3
     if (d.action != 0 /* RecoverOnly */ && total_vec) {
         // one CTA per proof; max_rounds bounds the table size (all proofs of a call share one generator set, so their vector
         // lengths differ by the aggregation factor only)
-        const uint32_t threads = max_rounds >= 8 ? 256u : max_rounds <= 5 ? 32u : (1u << max_rounds);
+        // (64-element vectors: ONE warp per proof, two elements per thread -- the table doubling steps keep whole warps busy for a handful
+        // of products, so the second warp of a 64-thread CTA cost more than it saved; BPP_VPREP_VEC_THREADS overrides)
+        static const uint32_t forced_threads = getenv("BPP_VPREP_VEC_THREADS") ? (uint32_t)atoi(getenv("BPP_VPREP_VEC_THREADS")) : 0u;
+        const uint32_t threads = forced_threads ? forced_threads : max_rounds >= 8 ? 256u : max_rounds <= 6 ? 32u : (1u << max_rounds);
         static const bool force_direct = getenv("BPP_VPREP_DIRECT") != nullptr;      // test hook for the long-vector path
         if (max_rounds <= VEC_TABLE_MAX_ROUNDS && !force_direct) {
             const uint32_t rl = max_rounds / 2, rh = max_rounds - rl;

@@ -114,7 +114,7 @@ class Engine:
         _chk(self, _ffi.lib().bpp_ctx_set_throughput_mode(self.h, int(enable)))
 
     def set_merged_check(self, enable):
-        """one multiscalar check per pass (calls with two or more chunks), chunk by chunk only when it fails (bpp_ctx_set_merged_check)"""
+        """one multiscalar check per pass (passes of four or more reference calls), chunk by chunk only when it fails (bpp_ctx_set_merged_check)"""
         _chk(self, _ffi.lib().bpp_ctx_set_merged_check(self.h, 1 if enable else 0))
 
     @property

@@ -276,7 +276,7 @@ int32_t bpp_vqueue_set_device_weights(bpp_vqueue *q, int32_t enable);
  * probability 2^-252, the reference's own argument one level up); otherwise -- some proof of the pass is invalid -- the pass is settled
  * call by call with the same scalars, so every call's status is exactly what the reference returns for it.  It makes the pass ~15 %
  * cheaper (one large sum uses 14-bit windows, 64 small ones 9-bit) and a pass that holds an invalid proof ~40 % dearer.
- * bpp_ctx_set_merged_check does the same for bpp_verify_chunks / bpp_vbatch_* on a ctx (calls with two or more chunks). */
+ * bpp_ctx_set_merged_check does the same for bpp_verify_chunks / bpp_vbatch_* on a ctx (passes of four or more reference calls). */
 int32_t bpp_vqueue_set_merged_check(bpp_vqueue *q, int32_t enable);
 int32_t bpp_ctx_set_merged_check(bpp_ctx *ctx, int32_t enable);
 uint64_t bpp_ctx_merged_fallbacks(const bpp_ctx *ctx);

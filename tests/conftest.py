@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# the merged check engages from four chunks per pass in production; the tests' small cases exercise it from two
+os.environ.setdefault("BPP_MERGED_MIN_CHUNKS", "2")
+
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 

@@ -41,7 +41,7 @@ BIT_LENGTH, EXT = 64, 1
 CHUNK = 256
 JOB = 1024
 # per launch of the kernel over a 16-job pass, from profiles/r02_ncu_full_raw.csv (read + write)
-NCU_DRAM_BYTES_PER_LAUNCH = {"decompress": 11.2e6, "msm_bucket": 106.9e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {"decompress": 11.16e6, "msm_bucket": 49.05e6}      # (msm_bucket: the merged form; one sum per call: 106.9e6)
 TARGET_JOBS = 4096                    # jobs in the timed region (>= 0.4 s at 10 M proofs/s)
 # algorithmic 32x32->64 multiplies (field mul = 72, field square = 44, scalar Montgomery mul = 96 + 32)
 MUL32_FE_MUL, MUL32_FE_SQ = 72, 44

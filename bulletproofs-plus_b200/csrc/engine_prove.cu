@@ -157,7 +157,7 @@ struct Lock8 {
     void rebuild() {
         const uint8_t *w[LK], *e[LK];
         for (int j = 0; j < LK; j++) { w[j] = p[j]->witness.data(); e[j] = p[j]->rng_bytes + 32 * p[j]->rng_used; }
-        r = t.build_rng(w, p[0]->witness.size(), e);
+        t.build_rng(r, w, p[0]->witness.size(), e);
     }
     bool draw(sc out[LK]) {                        // Scalar::random_not_zero per lane; false = some lane would have to draw again
         uint8_t buf[LK][64], *ptr[LK];
@@ -176,7 +176,7 @@ struct Lock8 {
         for (int j = 0; j < LK; j++) { out[j] = wide_to_sc(buf[j]); ok = ok && !sc_is_zero(out[j]); }
         return ok;
     }
-    void wipe() { secure_zero(&r, sizeof r); }
+    void wipe() { r.wipe(); }
 };
 
 // device + pinned buffers of the prover, kept per ctx across calls (grow-only; cudaMalloc / cudaFree of the ~200 MB bucket

@@ -28,6 +28,10 @@ template <int LANES> struct StrobeN {
         }
         pos = b[200]; pos_begin = b[201]; cur_flags = b[202];
     }
+    void wipe() {                           // a sponge keyed with witness bytes is a secret (the prover's TranscriptRngs)
+        volatile uint64_t *p = st;
+        for (int i = 0; i < 25 * LANES; i++) p[i] = 0;
+    }
     // lane j <- / -> one scalar sponge; the position bytes are shared, so only sponges that agree on them may share a StrobeN
     void load_lane(int j, const Strobe128 &s) {
         for (int k = 0; k < 25; k++) st[LANES * k + j] = s.st[k];
@@ -155,15 +159,18 @@ template <int LANES> struct MerlinN {
         append_same(label, ll, b, 8);
     }
     void challenge_each(const uint8_t *label, size_t ll, uint8_t *const out[LANES], size_t len) { label_len(label, ll, len); s.prf_each(out, len); }
-    // transcript.build_rng().rekey_with_witness_bytes("witness", w_j).finalize(rng_j): returns the rng sponges, *this is untouched
-    StrobeN<LANES> build_rng(const uint8_t *const witness[LANES], size_t wlen, const uint8_t *const ext32[LANES]) const {
-        MerlinN r = *this;
+    // transcript.build_rng().rekey_with_witness_bytes("witness", w_j).finalize(rng_j) into `out`; *this is untouched
+    // (built inside `out`, so that no keyed copy is left behind on the stack)
+    void build_rng(StrobeN<LANES> &out, const uint8_t *const witness[LANES], size_t wlen, const uint8_t *const ext32[LANES]) const {
         const uint8_t wl[7] = {'w', 'i', 't', 'n', 'e', 's', 's'}, rl[3] = {'r', 'n', 'g'};
-        r.label_len(wl, 7, wlen);
-        r.s.key_each(witness, wlen);
-        r.s.meta_ad_same(rl, 3, false);
-        r.s.key_each(ext32, 32);
-        return r.s;
+        uint8_t l4[4];
+        le32_bytes(l4, (uint32_t)wlen);
+        out = s;
+        out.meta_ad_same(wl, 7, false);
+        out.meta_ad_same(l4, 4, true);
+        out.key_each(witness, wlen);
+        out.meta_ad_same(rl, 3, false);
+        out.key_each(ext32, 32);
     }
 };
 template <int LANES> inline void rng_fill_each(StrobeN<LANES> &r, uint8_t *const out[LANES], size_t len) {

@@ -153,6 +153,11 @@ extern "C" {
     pub fn bpp_vqueue_lanes(q: *const bpp_vqueue) -> i32;
     pub fn bpp_vqueue_lane_ms(q: *mut bpp_vqueue, out4: *mut f64) -> i32;
     pub fn bpp_vqueue_set_device_weights(q: *mut bpp_vqueue, enable: i32) -> i32;
+    /// one multiscalar check per device pass instead of one per reference call; per-call statuses are unchanged (bpp_b200.h)
+    pub fn bpp_vqueue_set_merged_check(q: *mut bpp_vqueue, enable: i32) -> i32;
+    pub fn bpp_ctx_set_merged_check(ctx: *mut bpp_ctx, enable: i32) -> i32;
+    pub fn bpp_ctx_merged_fallbacks(ctx: *const bpp_ctx) -> u64;
+    pub fn bpp_msm_window_bits(n_entries: usize, n_seg: usize) -> i32;
     /// page-locked host memory: proof bytes placed here are uploaded without a staging copy (keep them valid until the call's results are back)
     pub fn bpp_host_alloc(bytes: usize, out: *mut *mut core::ffi::c_void) -> i32;
     pub fn bpp_host_free(p: *mut core::ffi::c_void);

@@ -459,15 +459,27 @@ def run_b200(args, rank, local_rank, world):
     api = bpp.pkg.api
     lib = bpp.ffi.lib()
     try:
-        cores = len(os.sched_getaffinity(0))
+        all_cores = sorted(os.sched_getaffinity(0))
     except AttributeError:
-        cores = os.cpu_count() or 1
+        all_cores = list(range(os.cpu_count() or 1))
+    cores = len(all_cores)
+    # N > 1: every rank keeps to its own slice of the host cores (what `numactl` / a launcher's --cpu-bind would do): the lanes, workers and
+    # submitting threads of eight ranks no longer migrate across each other's caches and their first-touch memory stays on their slice's
+    # node.  BPP_BENCH_NO_PIN=1 leaves the scheduler alone.
+    pinned_cores = None
+    if world > 1 and cores >= world and not os.environ.get("BPP_BENCH_NO_PIN") and hasattr(os, "sched_setaffinity"):
+        per = cores // world
+        pinned_cores = all_cores[local_rank * per:(local_rank + 1) * per]
+        try:
+            os.sched_setaffinity(0, pinned_cores)
+        except OSError:
+            pinned_cores = None
     reps = jobs_per_step(args.steps)
     n_jobs = args.steps * reps
     K = max(1, args.pass_jobs)
     # Hosts with few cores per GPU (the 8-GPU boxes of this pool: 4) hash the verifier-weight transcripts on the device (k_weights_sm, the
     # pass is one graph launch, ~3 core-ms of Keccak per pass less on the host; 1 % slower device-resident) and run 8 lanes of one thread
-    per_rank = max(1, cores // world)
+    per_rank = len(pinned_cores) if pinned_cores else max(1, cores // world)
     if args.device_weights < 0:
         args.device_weights = 1 if per_rank < 8 else 0
     if args.lanes <= 0:
@@ -741,6 +753,8 @@ def run_b200(args, rank, local_rank, world):
             except Exception as exc:
                 extras["msm_sharded"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         if rank == 0:
+            if pinned_cores:                               # secondary metrics are single-GPU figures: the whole host, as at N = 1
+                os.sched_setaffinity(0, all_cores)
             eng.set_host_threads(min(64, cores))
             try:
                 extras.update(run_extras(eng, api, bpp, orc, args, hbm_peak))
@@ -831,7 +845,9 @@ def run_b200(args, rank, local_rank, world):
                 "bucket results for the bucket sums",
                 "hbm_peak_gbs_measured": hbm_peak}
         # CPU baseline beside it: the oracle on this box's cores, a bounded sample of the same workload
-        threads = os.cpu_count() or 1
+        if pinned_cores:                                   # the CPU arm gets the whole host, as at N = 1
+            os.sched_setaffinity(0, all_cores)
+        threads = cores
         cpu_value, _, cpu_sample = cpu_arm(items[:JOB], 3, 1, threads)
         cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample + "; C restatement, not dalek"}
         cfg = workload_config(args)
@@ -841,6 +857,7 @@ def run_b200(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), scalars mod l)", "data": "synthetic",
             "config": cfg, "host_cores": cores,
             "engine": {"lanes_per_gpu": S, "queue_lanes_per_gpu": QS, "queue_host_threads_per_lane": qhtl, "submitting_threads": n_sub,
+                       "host_cores_of_this_rank": (pinned_cores if pinned_cores else "not pinned"),
                        "merged_check": ("on: ONE multiscalar check per device pass (sum over the pass's reference calls of rho_c x the call's own check, rho_c from "
                                         "the call's weight transcript), settled call by call when it fails; per-call statuses are the reference's "
                                         "(bpp_vqueue_set_merged_check, DESIGN.md 4.4)") if args.merged_check else "off: one multiscalar check per reference call",

@@ -203,6 +203,54 @@ void prove_ws_free(bpp_ctx *ctx) {
 
 extern "C" {
 
+// test hook, host only: the lock-step sponge (strobe_n.hpp) against the one-at-a-time Merlin of hash.cuh on eight transcripts in the same
+// state positions.  Script per lane: append_message("L", msg) -> challenge_bytes("e", 64) -> TranscriptRng(witness, ext32) -> fill_bytes(64)
+// -> fill_bytes(64).  out_*: per lane [203 transcript | 64 challenge | 203 rng state | 128 rng bytes] (598 bytes).
+int32_t bpp_host_lockstep_selftest(const uint8_t *states203, const uint8_t *msgs, size_t msg_len, const uint8_t *witness, size_t wlen,
+                                   const uint8_t *ext32, uint8_t *out_scalar, uint8_t *out_lockstep) {
+    if (!states203 || !msgs || !witness || !ext32 || !out_scalar || !out_lockstep) return BPP_INVALID_ARGUMENT;
+    const size_t rec = 2 * BPP_TRANSCRIPT_BYTES + 64 + 128;
+    for (int j = 0; j < LK; j++) {
+        Merlin t;
+        t.s.load(states203 + BPP_TRANSCRIPT_BYTES * j);
+        if (t.s.pos != states203[200] || t.s.pos_begin != states203[201] || t.s.cur_flags != states203[202]) return BPP_INVALID_ARGUMENT;   // lanes must agree
+        uint8_t *o = out_scalar + rec * j;
+        t.append_message(LBL("L"), msgs + msg_len * j, msg_len);
+        t.challenge_bytes(LBL("e"), o + BPP_TRANSCRIPT_BYTES, 64);
+        t.s.store(o);
+        MerlinRng r;
+        r.build(t, witness + wlen * j, wlen, true, ext32 + 32 * j);
+        r.fill(o + 2 * BPP_TRANSCRIPT_BYTES + 64, 64);
+        r.fill(o + 2 * BPP_TRANSCRIPT_BYTES + 128, 64);
+        r.s.store(o + BPP_TRANSCRIPT_BYTES + 64);
+    }
+    MerlinN<LK> t;
+    StrobeN<LK> r;
+    const uint8_t *pm[LK], *pw[LK], *pe[LK];
+    uint8_t *pc[LK], *pf0[LK], *pf1[LK];
+    for (int j = 0; j < LK; j++) {
+        Strobe128 s1;
+        s1.load(states203 + BPP_TRANSCRIPT_BYTES * j);
+        t.s.load_lane(j, s1);
+        uint8_t *o = out_lockstep + rec * j;
+        pm[j] = msgs + msg_len * j; pw[j] = witness + wlen * j; pe[j] = ext32 + 32 * j;
+        pc[j] = o + BPP_TRANSCRIPT_BYTES; pf0[j] = o + 2 * BPP_TRANSCRIPT_BYTES + 64; pf1[j] = pf0[j] + 64;
+    }
+    t.append_each(LBL("L"), pm, msg_len);
+    t.challenge_each(LBL("e"), pc, 64);
+    t.build_rng(r, pw, wlen, pe);
+    rng_fill_each(r, pf0, 64);
+    rng_fill_each(r, pf1, 64);
+    for (int j = 0; j < LK; j++) {
+        Strobe128 s1;
+        t.s.store_lane(j, s1);
+        s1.store(out_lockstep + rec * j);
+        r.store_lane(j, s1);
+        s1.store(out_lockstep + rec * j + BPP_TRANSCRIPT_BYTES + 64);
+    }
+    return BPP_OK;
+}
+
 size_t bpp_proof_size(int32_t extension_degree, int32_t rounds) {
     return 1 + 32 * ((size_t)extension_degree + 5 + 2 * (size_t)rounds);
 }

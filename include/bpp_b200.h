@@ -118,6 +118,11 @@ void bpp_host_sc_generic64(const uint8_t *a32_or_wide64, const uint8_t *b32_or_n
 /* test hook, host only: the verifier weights (range_proof.rs:811-853, :894) of n_chunks <= 8 chunks of `len` proofs each from the 32
  * bytes every proof feeds into the weight transcript; lockstep = 0: one transcript at a time, 1: n_chunks <= 4 through the four-way
  * vectorised sponge, 2: through the eight-way sponge (AVX-512; two four-way permutations elsewhere) */
+/* test hook, host only: eight transcripts (203-byte states with equal position bytes) through the prover's lock-step sponge and through the
+ * one-at-a-time Merlin: append_message("L", msg_j) -> challenge_bytes("e", 64) -> TranscriptRng keyed with witness_j and ext32_j -> two
+ * fill_bytes(64).  Per lane 598 bytes out: [transcript | challenge | rng state | 128 rng bytes]; the two outputs must be equal. */
+int32_t bpp_host_lockstep_selftest(const uint8_t *states203, const uint8_t *msgs, size_t msg_len, const uint8_t *witness, size_t wlen,
+                                   const uint8_t *ext32, uint8_t *out_scalar, uint8_t *out_lockstep);
 int32_t bpp_host_verifier_weights(const uint8_t *wbytes32, size_t len, size_t n_chunks, int32_t lockstep, uint8_t *weights32);
 /* Host-side sum of n <= 64 points (32-byte encodings): the last step of a multi-GPU MSM, each GPU having reduced its shard to one
  * partial result.  BPP_INVALID_ARGUMENT if an encoding does not decode. */

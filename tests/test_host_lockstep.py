@@ -59,3 +59,46 @@ def test_lockstep_sponge_equals_scalar_merlin_and_pyref(prefix_len, msg_len, wle
         f0, f1 = rng.fill_bytes(64), rng.fill_bytes(64)
         want = t.s.to_wire() + ch + rng.s.to_wire() + f0 + f1
         assert a.raw[REC * j:REC * (j + 1)] == want, j
+
+
+def test_lockstep_sponge_random_shapes():
+    """the same comparison over random prefix / message / witness lengths (hypothesis), lock-step against one-at-a-time only"""
+    from hypothesis import given, settings, strategies as st
+
+    lib = bpp.ffi.lib()
+    lib.bpp_host_lockstep_selftest.restype = C.c_int32
+    lib.bpp_host_lockstep_selftest.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]
+    base = pyref.Transcript(b"lock-step selftest")
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 400), st.integers(1, 400), st.integers(1, 300), st.integers(0, 2**32 - 1))
+    def run(prefix_len, msg_len, wlen, seed):
+        xof = hashlib.shake_256(b"rnd-%d-%d-%d-%d" % (prefix_len, msg_len, wlen, seed)).digest(8 * (prefix_len + msg_len + wlen + 32))
+        off = 0
+        states = b""
+        for _ in range(8):
+            t = base.clone()
+            t.append_message(b"prefix", xof[off:off + prefix_len])
+            off += prefix_len
+            states += t.s.to_wire()
+        msgs = xof[off:off + 8 * msg_len]
+        off += 8 * msg_len
+        wits = xof[off:off + 8 * wlen]
+        off += 8 * wlen
+        exts = xof[off:off + 256]
+        a, b = C.create_string_buffer(8 * REC), C.create_string_buffer(8 * REC)
+        assert lib.bpp_host_lockstep_selftest(states, msgs, msg_len, wits, wlen, exts, a, b) == 0
+        assert a.raw == b.raw
+
+    run()
+
+
+def test_window_choice_is_what_the_bench_counts_with():
+    lib = bpp.ffi.lib()
+    lib.bpp_msm_window_bits.restype = C.c_int32
+    lib.bpp_msm_window_bits.argtypes = [C.c_size_t, C.c_size_t]
+    assert lib.bpp_msm_window_bits(64 * 4226, 64) == 9          # the verifier's per-call sums of a 16-job pass
+    assert lib.bpp_msm_window_bits(64 * 4226, 1) == 14          # the same entries as one merged sum
+    assert lib.bpp_msm_window_bits(0, 1) == 0
+    for lg in range(8, 25):                                     # (not monotonic: the cost model follows the kernel variants)
+        assert 4 <= lib.bpp_msm_window_bits(1 << lg, 1) <= 16

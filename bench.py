@@ -649,7 +649,7 @@ def run_b200(args, rank, local_rank, world):
     # The queue hides a lane's host phases (building a pass: 12 MB of caller buffers parsed and staged, 17 % of a lane's time with 6 lanes;
     # handing results back) behind the device work of the other lanes, so it wants more lanes than the device-resident arm: measured on a
     # 16-core box 6 / 8 / 12 lanes -> 8.2 / 8.2-9.0 / 9.7 M proofs/s against 9.8 M device-resident.  Fewer on hosts with few cores per GPU.
-    QS = max(1, args.queue_lanes or (8 if args.device_weights else 12 if per_rank >= 12 else 8))
+    QS = max(1, args.queue_lanes or (8 if args.device_weights else 16 if per_rank >= 16 else 12 if per_rank >= 12 else 8))    # (merged check, 16 cores: 12 -> 10.7 M, 16 -> 11.3 M)
     qhtl = args.host_threads_per_lane or (1 if args.device_weights else max(1, min(2, (2 * per_rank) // QS)))
     q = api.VerifyQueue(local_rank, BIT_LENGTH, 1, EXT, lanes=QS, max_calls_per_pass=K, host_threads_per_lane=qhtl, device_weights=bool(args.device_weights), merged_check=bool(args.merged_check))
     n_slots = min(n_jobs, 2 * QS * K)

@@ -776,10 +776,15 @@ static int32_t vbatch_create_impl(bpp_gens *g, size_t n_calls, const bpp_verify_
     // surfaces in bpp_vbatch_run).
     static const bool always_sync = getenv("BPP_CREATE_SYNC") != nullptr;      // debugging: upload errors surface here, host_ms[4] = H2D time
     if (e == cudaSuccess && always_sync) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { vwork_return(ctx, w); delete vb; return cuda_fail(ctx, e, "vbatch upload"); }
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(st);          // copies that did get queued may still be reading the staging blob or page-locked caller buffers
+        vwork_return(ctx, w); delete vb;
+        return cuda_fail(ctx, e, "vbatch upload");
+    }
     lap();   // [4] H2D
     ctx->io_bytes[0] = vb->blob_bytes + (vb->device_replay ? 0 : 32 * (size_t)n_chal); ctx->io_bytes[1] = 0;
-    for (HProof &p : vb->hp) p.bytes = nullptr;      // the callers' buffers are not referenced after this point
+    for (HProof &p : vb->hp) p.bytes = nullptr;      // the host does not read the callers' buffers after this point (the copy engine still
+                                                     // reads page-locked proof bytes until the pass has run, see bpp_b200.h)
     *out = vb;
     return BPP_OK;
 }
